@@ -1,0 +1,167 @@
+/*
+ * microcket_b200.h — C ABI of libmicrocket_b200.so, the B200-native (sm_100a)
+ * implementation of Microcket's post-alignment hot path.
+ *
+ * The reference (hellosunking/Microcket v1.4) has no in-process API for this
+ * path: its boundary is process + argv + stdio.  Each group of
+ * entry points below therefore replaces one reference *program*; the drop-in
+ * executables built from microcket_b200/csrc/cli_*.cpp are thin argv/stdio
+ * shells over these calls.
+ *
+ *   mk_s2p_*    replaces  src/sam2pairs/sam2pairs.cpp:23-229 (main: argv
+ *               :33-54, batch loop :143-190, log :195-219) with
+ *               pairutil.h:63-208, flash2pairs.h:17-155, unc2pairs.h:16-358
+ *   mk_dedup_*  replaces  src/preprocess/krmdup.cpp:278-397 (main) with
+ *               load_batch :88-149 and do_rmdup :151-227; also
+ *               src/preprocess/krmdup.pipe.cpp (same algorithm, stdout)
+ *   mk_pairs_*  coordinate-keyed duplicate removal + binning of packed pairs;
+ *               replaces the `juicer_tools pre` call at microcket:525-529 up
+ *               to COO counts (no reference source exists: parity unpinned)
+ *
+ * Conventions: plain C types only; caller-owned host buffers; callee-owned
+ * device memory; return 0 = ok, negative = error (text from mk_last_error(),
+ * thread-local).  A context is bound to one GPU and is not thread-safe;
+ * distinct contexts are independent.  Every compute entry point needs a CUDA
+ * device: there is no CPU fallback.
+ */
+#ifndef MICROCKET_B200_H
+#define MICROCKET_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MK_OK             0
+#define MK_ERR_ARG       -1
+#define MK_ERR_CUDA      -2
+#define MK_ERR_NOMEM     -3
+#define MK_ERR_CAPACITY  -4   /* an internal per-window capacity was exceeded (lines, output bytes, carry) */
+#define MK_ERR_STATE     -5
+#define MK_ERR_INPUT     -6   /* malformed input the reference itself is undefined on */
+
+typedef struct mk_ctx mk_ctx;
+
+const char *mk_last_error(void);
+int  mk_version(void);
+int  mk_device_count(void);          /* CUDA devices visible; 0 when there is no GPU (no error) */
+void mk_destroy(mk_ctx *);
+
+/* ------------------------------------------------------------------ packed pair record (16 B) */
+typedef struct {
+    uint32_t pos1, pos2;   /* 1-based 5' ends, after the reference's ordering rule (unc2pairs.h:310-348) */
+    uint16_t chr1, chr2;   /* chromosome ids: index into the table given to / learnt by the context */
+    uint8_t  strands;      /* bit0: strand1 == '-', bit1: strand2 == '-' */
+    uint8_t  cls;          /* 0 trans, 1 cis10K, 2 cis1K, 3 cis0 (sam2pairs.cpp:211-218 classes) */
+    uint16_t lane;         /* sequencing lane / replicate id for `-b` style per-lane dedup (microcket:428-451) */
+} mk_pair;
+
+/* ------------------------------------------------------------------ sam2pairs */
+typedef struct {
+    int   mode;              /* 0 = flash (stitched reads), 1 = unc (paired reads): argv[2], sam2pairs.cpp:57-67 */
+    float min_mapped_ratio;  /* argv[5], default 0.5 (pairutil.h:52) — compared in fp32 like the reference */
+    int   min_mapq;          /* argv[6], default 10 (pairutil.h:50) */
+    int   write_sam;         /* argv[7]: pass through the kept lines of every emitted group */
+    int   emu_threads;       /* argv[4] (T >= 2): reproduces the reference's selfCircle log value, which only
+                                counts thread 0's share of each 2^18-group batch (sam2pairs.cpp:150,172,202-210) */
+    int   device;            /* CUDA device ordinal */
+    int   emit_text;         /* produce .pairs text lines (stdout of the reference) */
+    int   emit_packed;       /* produce mk_pair records for the fused dedup/binning path */
+    size_t window_bytes;     /* bytes of SAM text per device window; 0 = default (256 MiB) */
+    uint16_t lane;           /* stamped into mk_pair.lane */
+    int   sharded;           /* 1: this context sees one shard of a larger stream; the selfCircle log value is
+                                settled in mk_s2p_finish_sharded once the global group indices are known */
+} mk_s2p_cfg;
+
+typedef struct {
+    uint32_t lowMap, manyHits, unpaired, selfCircle, trans, cis10K, cis1K, cis0; /* log order, sam2pairs.cpp:211-218 */
+    uint64_t selfCircle_true;  /* every self-circle, not only emulated thread 0's */
+    uint64_t groups;           /* read groups processed (the stream's last group is not, pairutil.h:176) */
+    uint64_t lines;            /* SAM lines seen (headers included) */
+    uint64_t cigar_errors;     /* groups dropped where the reference's cigar2segment returns false (UB there) */
+    uint64_t pairs;            /* pair lines emitted */
+} mk_s2p_stats;
+
+void mk_s2p_default_cfg(mk_s2p_cfg *);
+/* chrom_names may be NULL/0: names are then learnt from the RNAME column (any name is accepted,
+ * order is bytewise like std::string::compare).  Pre-registered names get ids 0..n-1. */
+int  mk_s2p_create(const mk_s2p_cfg *, const char *const *chrom_names, int n_chrom, mk_ctx **);
+/* Host streaming API (what the sam2pairs CLI uses).  `sam_bytes` may be split anywhere; the
+ * library carries partial lines and the trailing read group over to the next call. */
+int  mk_s2p_push(mk_ctx *, const char *sam_bytes, size_t n, int is_last);
+/* Drains produced output; *n_out == 0 and *n_out2 == 0 when nothing is pending.  Either buffer may be NULL. */
+int  mk_s2p_pull(mk_ctx *, char *pairs_out, size_t cap, size_t *n_out,
+                 char *sam_out, size_t cap2, size_t *n_out2);
+int  mk_s2p_pull_packed(mk_ctx *, mk_pair *recs, size_t cap, size_t *n);
+int  mk_s2p_finish(mk_ctx *, mk_s2p_stats *);
+/* Sharded finish: this context processed groups [group_base, group_base + stats.groups) of a stream of
+ * total_groups processed groups (multi-GPU: bases from an all-gather of per-rank group counts). */
+int  mk_s2p_finish_sharded(mk_ctx *, uint64_t group_base, uint64_t total_groups, mk_s2p_stats *);
+/* Chromosome table after (or during) a run: id → name. */
+int  mk_s2p_chrom_count(mk_ctx *);
+int  mk_s2p_chrom_name(mk_ctx *, int id, char *buf, size_t cap);
+
+/* Device-resident API: SAM text already in HBM (d_sam: device pointer, 16-byte aligned, readable up to
+ * the next 16-byte boundary past n).  Outputs stay on the device in caller-provided buffers.
+ * The text must end with '\n'.  When is_last == 0 the trailing read group is not processed and
+ * *consumed tells where it starts.  `stream` is a cudaStream_t (0 = default stream). */
+typedef struct {
+    char    *d_pairs_text;  size_t pairs_text_cap;   /* may be NULL when emit_text == 0 */
+    mk_pair *d_pairs;       size_t pairs_cap;        /* may be NULL when emit_packed == 0 */
+    char    *d_sam_text;    size_t sam_text_cap;     /* may be NULL when write_sam == 0 */
+    /* results (host values, valid after the call returns) */
+    size_t   pairs_text_len, n_pairs, sam_text_len, consumed;
+} mk_s2p_dev_io;
+int  mk_s2p_run_device(mk_ctx *, const char *d_sam, size_t n, int is_last, mk_s2p_dev_io *io, void *stream);
+/* number of kernel launches issued by this context so far (for bench accounting) */
+uint64_t mk_launch_count(mk_ctx *);
+
+/* ------------------------------------------------------------------ krmdup */
+typedef struct {
+    int hskip1, klen1, hskip2, klen2;  /* -k -s -K -S; defaults 5,16,5,16 (krmdup.cpp:231-234); 16 <= klen1+klen2 <= 32 */
+    int device;
+    size_t window_bytes;               /* bytes of FASTQ per device window; 0 = default */
+} mk_dedup_cfg;
+typedef struct { uint32_t uniq, dup, discard; uint64_t pairs; } mk_dedup_stats;   /* krmdup.cpp:383-389 */
+
+void mk_dedup_default_cfg(mk_dedup_cfg *);
+int  mk_dedup_create(const mk_dedup_cfg *, mk_ctx **);
+int  mk_dedup_push(mk_ctx *, const char *fq_bytes, size_t n, int is_last);
+/* read1/read2 records of kept pairs in the reference's file order (per 65 536-pair batch: buckets A,C,G,T;
+ * krmdup.cpp:216-226).  For krmdup.pipe interleave the two streams record by record. */
+int  mk_dedup_pull(mk_ctx *, char *r1_out, size_t cap1, size_t *n1, char *r2_out, size_t cap2, size_t *n2);
+int  mk_dedup_finish(mk_ctx *, mk_dedup_stats *);
+/* Device-resident key path: 64-bit krmdup keys (or any 64-bit keys) already in HBM.
+ * keep[i] = 1 iff key i is the first occurrence in index order.  d_keep: n bytes on the device. */
+int  mk_dedup_keys_device(int device, const uint64_t *d_keys, size_t n, uint8_t *d_keep,
+                          uint64_t *n_unique, void *stream);
+
+/* ------------------------------------------------------------------ packed pairs: dedup + binning */
+typedef struct mk_pairs_ws mk_pairs_ws;   /* reusable device workspace */
+int  mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **);
+void mk_pairs_ws_destroy(mk_pairs_ws *);
+/* Coordinate-keyed duplicate removal over (lane, chr1,pos1,strand1, chr2,pos2,strand2): first in index
+ * order wins.  d_pairs is compacted in place to the kept pairs, SORTED by key; *n_kept returns the count. */
+int  mk_pairs_dedup_device(mk_pairs_ws *, mk_pair *d_pairs, size_t n, size_t *n_kept, void *stream);
+/* Contact counts at one resolution: bin = chrom_bin_offset[chr] + pos / res with offsets the running sum of
+ * (len / res + 1) in the given chromosome order; COO triplets sorted by (bin1, bin2), bin1 <= bin2.
+ * chrom_id_map (host, may be NULL) maps mk_pair chromosome ids to indices of chrom_len. */
+int  mk_pairs_bin_device(mk_pairs_ws *, const mk_pair *d_pairs, size_t n,
+                         const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map,
+                         uint32_t res, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                         size_t *nnz, void *stream);
+uint64_t mk_pairs_launch_count(mk_pairs_ws *);
+
+/* ------------------------------------------------------------------ synthetic inputs (tests / bench) */
+/* Same bytes on host and device for a given (seed, mode, genome, first, count).  mode: 0 flash, 1 unc,
+ * 2 interleaved FASTQ.  genome: 0 hg38, 1 mm10.  Returns bytes written in *n_out (or needed when buf == NULL). */
+int  mk_synth_host(uint64_t seed, int mode, int genome, uint64_t first, uint64_t count,
+                   char *buf, size_t cap, size_t *n_out);
+int  mk_synth_device(int device, uint64_t seed, int mode, int genome, uint64_t first, uint64_t count,
+                     char *d_buf, size_t cap, size_t *n_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,352 @@
+"""ctypes binding of libmicrocket_b200.so — one Python method per C entry point.
+
+Host-side mirror of the reference's program interfaces:
+  Sam2Pairs  <-> sam2pairs <in.sam> <flash|unc> <prefix> [T] [ratio] [Q] [sam]   (sam2pairs.cpp:25-54)
+  Krmdup     <-> krmdup -i <fq> -o <prefix> [-k -K -s -S]                         (krmdup.cpp:229-276)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libmicrocket_b200.so")
+
+PAIR_DTYPE = np.dtype([("pos1", "<u4"), ("pos2", "<u4"), ("chr1", "<u2"), ("chr2", "<u2"),
+                       ("strands", "u1"), ("cls", "u1"), ("lane", "<u2")])
+
+
+class MkError(RuntimeError):
+    pass
+
+
+class S2PCfg(C.Structure):
+    _fields_ = [("mode", C.c_int), ("min_mapped_ratio", C.c_float), ("min_mapq", C.c_int), ("write_sam", C.c_int),
+                ("emu_threads", C.c_int), ("device", C.c_int), ("emit_text", C.c_int), ("emit_packed", C.c_int),
+                ("window_bytes", C.c_size_t), ("lane", C.c_uint16), ("sharded", C.c_int)]
+
+
+class S2PStats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("lowMap", "manyHits", "unpaired", "selfCircle", "trans", "cis10K", "cis1K", "cis0")] + \
+               [(n, C.c_uint64) for n in ("selfCircle_true", "groups", "lines", "cigar_errors", "pairs")]
+
+    def log_text(self):
+        """The 8 lines of <prefix>.<mode>2pairs.log (sam2pairs.cpp:211-218)."""
+        return ("lowMap\t%d\nmanyHits\t%d\nunpaired\t%d\nselfCircle\t%d\ntrans\t%d\ncis10K\t%d\ncis1K\t%d\ncis0\t%d\n" %
+                (self.lowMap, self.manyHits, self.unpaired, self.selfCircle, self.trans, self.cis10K, self.cis1K, self.cis0)).encode()
+
+
+class S2PDevIO(C.Structure):
+    _fields_ = [("d_pairs_text", C.c_void_p), ("pairs_text_cap", C.c_size_t), ("d_pairs", C.c_void_p), ("pairs_cap", C.c_size_t),
+                ("d_sam_text", C.c_void_p), ("sam_text_cap", C.c_size_t),
+                ("pairs_text_len", C.c_size_t), ("n_pairs", C.c_size_t), ("sam_text_len", C.c_size_t), ("consumed", C.c_size_t)]
+
+
+class DedupCfg(C.Structure):
+    _fields_ = [("hskip1", C.c_int), ("klen1", C.c_int), ("hskip2", C.c_int), ("klen2", C.c_int), ("device", C.c_int),
+                ("window_bytes", C.c_size_t)]
+
+
+class DedupStats(C.Structure):
+    _fields_ = [("uniq", C.c_uint32), ("dup", C.c_uint32), ("discard", C.c_uint32), ("pairs", C.c_uint64)]
+
+    def log_text(self):
+        """The 4 lines appended to <prefix>.log (krmdup.cpp:386-389)."""
+        return ("Total\t%d\nUniq\t%d\nDup\t%d\nDiscard\t%d\n" %
+                (self.uniq + self.dup + self.discard, self.uniq, self.dup, self.discard)).encode()
+
+
+def build(force=False, verbose=False):
+    """Compile libmicrocket_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp", "Makefile"))]
+    srcs.append(os.path.join(os.path.dirname(HERE), "include", "microcket_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
+        return LIB_PATH
+    r = subprocess.run(["make", "-C", CSRC, "all"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise MkError("building libmicrocket_b200.so failed")
+    return LIB_PATH
+
+
+class Lib:
+    """Loaded libmicrocket_b200.so with typed prototypes."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise MkError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+        L = self.L = C.CDLL(path)
+        vp, sz, i, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+        P = C.POINTER
+        L.mk_last_error.restype = C.c_char_p
+        L.mk_version.restype = i
+        L.mk_device_count.restype = i
+        L.mk_destroy.argtypes = [vp]
+        L.mk_s2p_default_cfg.argtypes = [P(S2PCfg)]
+        L.mk_s2p_create.argtypes = [P(S2PCfg), P(C.c_char_p), i, P(vp)]
+        L.mk_s2p_push.argtypes = [vp, C.c_char_p, sz, i]
+        L.mk_s2p_pull.argtypes = [vp, vp, sz, P(sz), vp, sz, P(sz)]
+        L.mk_s2p_pull_packed.argtypes = [vp, vp, sz, P(sz)]
+        L.mk_s2p_finish.argtypes = [vp, P(S2PStats)]
+        L.mk_s2p_finish_sharded.argtypes = [vp, u64, u64, P(S2PStats)]
+        L.mk_s2p_chrom_count.argtypes = [vp]
+        L.mk_s2p_chrom_name.argtypes = [vp, i, C.c_char_p, sz]
+        L.mk_s2p_run_device.argtypes = [vp, vp, sz, i, P(S2PDevIO), vp]
+        L.mk_launch_count.argtypes = [vp]
+        L.mk_launch_count.restype = u64
+        L.mk_synth_host.argtypes = [u64, i, i, u64, u64, vp, sz, P(sz)]
+        L.mk_synth_device.argtypes = [i, u64, i, i, u64, u64, vp, sz, P(sz), vp]
+        for name, args in (("mk_dedup_default_cfg", [P(DedupCfg)]), ("mk_dedup_create", [P(DedupCfg), P(vp)]),
+                           ("mk_dedup_push", [vp, C.c_char_p, sz, i]), ("mk_dedup_pull", [vp, vp, sz, P(sz), vp, sz, P(sz)]),
+                           ("mk_dedup_finish", [vp, P(DedupStats)]),
+                           ("mk_dedup_keys_device", [i, vp, sz, vp, P(u64), vp]),
+                           ("mk_pairs_ws_create", [i, sz, P(vp)]), ("mk_pairs_ws_destroy", [vp]),
+                           ("mk_pairs_dedup_device", [vp, vp, sz, P(sz), vp]),
+                           ("mk_pairs_bin_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, vp, vp, vp, sz, P(sz), vp]),
+                           ("mk_pairs_launch_count", [vp])):
+            if hasattr(L, name):
+                getattr(L, name).argtypes = args
+        if hasattr(L, "mk_pairs_launch_count"):
+            L.mk_pairs_launch_count.restype = u64
+
+    def check(self, rc):
+        if rc != 0:
+            raise MkError(f"microcket_b200 error {rc}: {self.L.mk_last_error().decode(errors='replace')}")
+
+    def device_count(self):
+        return self.L.mk_device_count()
+
+    def require_gpu(self):
+        if self.device_count() < 1:
+            raise MkError("no CUDA device visible: microcket_b200 has no CPU fallback")
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = Lib()
+    return _lib
+
+
+class S2PConfig:
+    def __init__(self, mode="unc", ratio=0.5, min_mapq=10, write_sam=False, threads=8, device=0, emit_text=True,
+                 emit_packed=False, window_bytes=0, lane=0, sharded=False):
+        self.c = S2PCfg()
+        lib().L.mk_s2p_default_cfg(C.byref(self.c))
+        self.c.mode = {"flash": 0, "unc": 1}[mode]
+        self.c.min_mapped_ratio = ratio
+        self.c.min_mapq = min_mapq
+        self.c.write_sam = int(write_sam)
+        self.c.emu_threads = threads
+        self.c.device = device
+        self.c.emit_text = int(emit_text)
+        self.c.emit_packed = int(emit_packed)
+        self.c.window_bytes = window_bytes
+        self.c.lane = lane
+        self.c.sharded = int(sharded)
+
+
+class Sam2Pairs:
+    """One sam2pairs run (one reference process).  Host streaming: push()/pull()/finish()."""
+
+    def __init__(self, cfg: S2PConfig, chrom_names=None):
+        self.lib = lib()
+        self.lib.require_gpu()
+        self.cfg = cfg
+        names = [n.encode() for n in (chrom_names or [])]
+        arr = (C.c_char_p * max(len(names), 1))(*names)
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.mk_s2p_create(C.byref(cfg.c), arr, len(names), C.byref(self.h)))
+        self._buf = C.create_string_buffer(8 << 20)
+        self._buf2 = C.create_string_buffer(8 << 20)
+
+    def close(self):
+        if self.h:
+            self.lib.L.mk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, data: bytes, is_last=False):
+        self.lib.check(self.lib.L.mk_s2p_push(self.h, data, len(data), int(is_last)))
+
+    def pull(self):
+        """→ (pairs_text, sam_text) produced so far."""
+        out, out2 = [], []
+        n, n2 = C.c_size_t(), C.c_size_t()
+        while True:
+            self.lib.check(self.lib.L.mk_s2p_pull(self.h, C.addressof(self._buf), len(self._buf), C.byref(n),
+                                                  C.addressof(self._buf2), len(self._buf2), C.byref(n2)))
+            if n.value == 0 and n2.value == 0:
+                break
+            out.append(self._buf.raw[:n.value])
+            out2.append(self._buf2.raw[:n2.value])
+        return b"".join(out), b"".join(out2)
+
+    def pull_packed(self):
+        chunks = []
+        cap = 1 << 18
+        arr = np.empty(cap, dtype=PAIR_DTYPE)
+        n = C.c_size_t()
+        while True:
+            self.lib.check(self.lib.L.mk_s2p_pull_packed(self.h, arr.ctypes.data, cap, C.byref(n)))
+            if n.value == 0:
+                break
+            chunks.append(arr[:n.value].copy())
+        return np.concatenate(chunks) if chunks else np.empty(0, dtype=PAIR_DTYPE)
+
+    def finish(self, group_base=None, total_groups=None) -> S2PStats:
+        st = S2PStats()
+        if group_base is None:
+            self.lib.check(self.lib.L.mk_s2p_finish(self.h, C.byref(st)))
+        else:
+            self.lib.check(self.lib.L.mk_s2p_finish_sharded(self.h, group_base, total_groups, C.byref(st)))
+        return st
+
+    def chrom_names(self):
+        n = self.lib.L.mk_s2p_chrom_count(self.h)
+        buf = C.create_string_buffer(64)
+        out = []
+        for i in range(n):
+            self.lib.check(self.lib.L.mk_s2p_chrom_name(self.h, i, buf, 64))
+            out.append(buf.value.decode())
+        return out
+
+    def run(self, sam: bytes, chunk=None):
+        """Whole input through push/pull.  → (pairs_text, sam_text, stats)"""
+        if chunk is None:
+            self.push(sam, True)
+        else:
+            for o in range(0, len(sam), chunk):
+                self.push(sam[o:o + chunk], False)
+            self.push(b"", True)
+        p, s = self.pull()
+        return p, s, self.finish()
+
+    def run_device(self, d_ptr, n, is_last, d_text=0, text_cap=0, d_pairs=0, pairs_cap=0, d_sam=0, sam_cap=0, stream=0):
+        io = S2PDevIO(d_text, text_cap, d_pairs, pairs_cap, d_sam, sam_cap, 0, 0, 0, 0)
+        self.lib.check(self.lib.L.mk_s2p_run_device(self.h, d_ptr, n, int(is_last), C.byref(io), stream))
+        return io
+
+    def launches(self):
+        return self.lib.L.mk_launch_count(self.h)
+
+
+class Krmdup:
+    """One krmdup process (persistent key sets): push()/pull()/finish()."""
+
+    def __init__(self, hskip1=5, klen1=16, hskip2=5, klen2=16, device=0, window_bytes=0):
+        self.lib = lib()
+        self.lib.require_gpu()
+        c = DedupCfg()
+        self.lib.L.mk_dedup_default_cfg(C.byref(c))
+        c.hskip1, c.klen1, c.hskip2, c.klen2, c.device, c.window_bytes = hskip1, klen1, hskip2, klen2, device, window_bytes
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.mk_dedup_create(C.byref(c), C.byref(self.h)))
+        self._b1 = C.create_string_buffer(8 << 20)
+        self._b2 = C.create_string_buffer(8 << 20)
+
+    def close(self):
+        if self.h:
+            self.lib.L.mk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, data: bytes, is_last=False):
+        self.lib.check(self.lib.L.mk_dedup_push(self.h, data, len(data), int(is_last)))
+
+    def pull(self):
+        o1, o2 = [], []
+        n1, n2 = C.c_size_t(), C.c_size_t()
+        while True:
+            self.lib.check(self.lib.L.mk_dedup_pull(self.h, C.addressof(self._b1), len(self._b1), C.byref(n1),
+                                                    C.addressof(self._b2), len(self._b2), C.byref(n2)))
+            if n1.value == 0 and n2.value == 0:
+                break
+            o1.append(self._b1.raw[:n1.value])
+            o2.append(self._b2.raw[:n2.value])
+        return b"".join(o1), b"".join(o2)
+
+    def finish(self) -> DedupStats:
+        st = DedupStats()
+        self.lib.check(self.lib.L.mk_dedup_finish(self.h, C.byref(st)))
+        return st
+
+    def run(self, fq: bytes, chunk=None):
+        if chunk is None:
+            self.push(fq, True)
+        else:
+            for o in range(0, len(fq), chunk):
+                self.push(fq[o:o + chunk], False)
+            self.push(b"", True)
+        r1, r2 = self.pull()
+        return r1, r2, self.finish()
+
+
+class PairsWorkspace:
+    """Device workspace for coordinate dedup + binning of packed pairs (device pointers in, device pointers out)."""
+
+    def __init__(self, max_pairs, device=0):
+        self.lib = lib()
+        self.lib.require_gpu()
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.mk_pairs_ws_create(device, max_pairs, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.L.mk_pairs_ws_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dedup(self, d_pairs, n, stream=0):
+        kept = C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_dedup_device(self.h, d_pairs, n, C.byref(kept), stream))
+        return kept.value
+
+    def bin(self, d_pairs, n, chrom_len, res, d_bin1, d_bin2, d_cnt, cap, chrom_id_map=None, stream=0):
+        cl = (C.c_uint32 * len(chrom_len))(*chrom_len)
+        if chrom_id_map is not None:
+            mp = (C.c_uint16 * len(chrom_id_map))(*chrom_id_map)
+            nm = len(chrom_id_map)
+        else:
+            mp, nm = None, 0
+        nnz = C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_bin_device(self.h, d_pairs, n, cl, len(chrom_len), mp, nm, res,
+                                                      d_bin1, d_bin2, d_cnt, cap, C.byref(nnz), stream))
+        return nnz.value
+
+    def launches(self):
+        return self.lib.L.mk_pairs_launch_count(self.h)
+
+
+def synth_host(seed, mode, genome, first, count) -> bytes:
+    """Synthetic SAM ('flash'/'unc') or interleaved FASTQ ('fastq') for groups/pairs [first, first+count) — host side."""
+    m = {"flash": 0, "unc": 1, "fastq": 2}[mode]
+    g = {"hg38": 0, "mm10": 1}[genome]
+    L = lib()
+    n = C.c_size_t()
+    L.check(L.L.mk_synth_host(seed, m, g, first, count, None, 0, C.byref(n)))
+    buf = C.create_string_buffer(n.value + 16)
+    L.check(L.L.mk_synth_host(seed, m, g, first, count, C.addressof(buf), n.value, C.byref(n)))
+    return buf.raw[:n.value]

@@ -1,0 +1,43 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads and exports what include/*.h declares."""
+import ctypes as C
+import os
+import re
+
+import microcket_b200 as mk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "microcket_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mk_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    mk.build()
+    L = C.CDLL(mk.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    L = mk.lib()
+    if L.device_count() > 0:
+        return
+    try:
+        mk.Sam2Pairs(mk.S2PConfig())
+    except mk.MkError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("a context was created without a GPU")
+
+
+def test_host_generator_is_deterministic_and_sharded():
+    a = mk.synth_host(42, "unc", "hg38", 0, 2000)
+    b = mk.synth_host(42, "unc", "hg38", 0, 1000) + mk.synth_host(42, "unc", "hg38", 1000, 1000)
+    assert a == b and a != mk.synth_host(43, "unc", "hg38", 0, 2000)
+    fq = mk.synth_host(42, "fastq", "mm10", 0, 100)
+    assert fq.count(b"\n") == 800

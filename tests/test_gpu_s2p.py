@@ -1,0 +1,119 @@
+"""Parity of the CUDA sam2pairs path (through the C ABI) with the oracle and the reference's golden vectors."""
+import os
+
+import pytest
+
+import microcket_b200 as mk
+from oracle_lib import sort_lines, sort_pairs
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rd(name):
+    return open(os.path.join(G, name), "rb").read()
+
+
+def gpu_s2p(sam, mode, ratio=0.5, q=10, threads=8, write_sam=True, chunk=None, window=0, names=None, packed=False):
+    s = mk.Sam2Pairs(mk.S2PConfig(mode=mode, ratio=ratio, min_mapq=q, threads=threads, write_sam=write_sam,
+                                  window_bytes=window, emit_packed=packed), names)
+    try:
+        p, so, st = s.run(sam, chunk)
+        pk = s.pull_packed() if packed else None
+        nm = s.chrom_names()
+    finally:
+        s.close()
+    return p, so, st, pk, nm
+
+
+@pytest.mark.parametrize("name,mode,ratio", [("appB_unc", "unc", 0.5), ("appB_flash_r05", "flash", 0.5), ("appB_flash_r08", "flash", 0.8)])
+def test_golden_vectors(name, mode, ratio):
+    p, so, st, _, _ = gpu_s2p(rd(name + ".sam"), mode, ratio=ratio, threads=2)
+    assert sort_pairs(p) == rd(name + ".pairs.sorted")
+    assert st.log_text() == rd(name + ".log")
+    assert sort_lines(so) == rd(name + ".samout.sorted")
+
+
+@pytest.mark.parametrize("mode,genome,seed,threads,ratio", [
+    ("unc", "hg38", 11, 8, 0.5), ("unc", "mm10", 12, 4, 0.8), ("flash", "hg38", 13, 8, 0.5), ("flash", "mm10", 14, 2, 0.8)])
+def test_synthetic_vs_oracle(oracle, mode, genome, seed, threads, ratio):
+    sam = mk.synth_host(seed, mode, genome, 0, 40000)
+    op, osam, ost = oracle.sam2pairs(sam, mode, ratio=ratio, threads=threads)
+    p, so, st, _, _ = gpu_s2p(sam, mode, ratio=ratio, threads=threads)
+    assert p == op                      # same order as the input (the oracle emits in group order)
+    assert so == osam
+    assert st.log_text() == ost.log_text()
+    assert (st.groups, st.selfCircle_true) == (ost.groups, ost.selfCircle_true)
+
+
+@pytest.mark.parametrize("mode", ["unc", "flash"])
+def test_many_small_windows_and_ragged_pushes(oracle, mode):
+    """Tiny windows + pushes cut at arbitrary bytes: partial lines and read groups are carried across windows."""
+    sam = mk.synth_host(5, mode, "hg38", 0, 20000)
+    op, osam, ost = oracle.sam2pairs(sam, mode, threads=8)
+    p, so, st, _, _ = gpu_s2p(sam, mode, chunk=77777, window=1 << 16)
+    assert p == op and so == osam and st.log_text() == ost.log_text()
+
+
+def test_selfcircle_quirk_multibatch(oracle):
+    sam = mk.synth_host(21, "unc", "hg38", 0, 300000)
+    for T in (2, 8):
+        op, _, ost = oracle.sam2pairs(sam, "unc", threads=T, write_sam=False)
+        p, _, st, _, _ = gpu_s2p(sam, "unc", threads=T, write_sam=False, window=32 << 20)
+        assert st.log_text() == ost.log_text()
+        assert p == op
+
+
+def test_header_and_names(oracle):
+    sam = rd("appB_unc.sam")
+    hg38 = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr2", "chr20",
+            "chr21", "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
+    p1, _, _, pk, nm = gpu_s2p(sam, "unc", threads=2, names=hg38, packed=True)
+    assert nm[:25] == hg38
+    p2, _, _, _, nm2 = gpu_s2p(sam, "unc", threads=2)        # names learnt from the RNAME column
+    assert p1 == p2 and set(nm2) <= set(hg38)
+    # packed records agree with the text
+    lines = p1.decode().splitlines()
+    assert len(lines) == len(pk)
+    for ln, r in zip(lines, pk):
+        f = ln.split("\t")
+        assert (f[1], int(f[2]), f[3], int(f[4])) == (nm[r["chr1"]], r["pos1"], nm[r["chr2"]], r["pos2"])
+        assert f[5] == "+-"[r["strands"] & 1] and f[6] == "+-"[(r["strands"] >> 1) & 1]
+
+
+def test_empty_and_degenerate_inputs():
+    for sam in (b"", b"@HD\tVN:1.0\n", b"\n\n", rd("appB_unc.sam").split(b"\n")[3] + b"\n"):
+        p, so, st, _, _ = gpu_s2p(sam, "unc", threads=2)
+        assert p == b"" and so == b"" and st.pairs == 0
+
+
+def test_no_trailing_newline(oracle):
+    sam = mk.synth_host(3, "unc", "hg38", 0, 500).rstrip(b"\n")
+    op, osam, ost = oracle.sam2pairs(sam, "unc", threads=8)
+    p, so, st, _, _ = gpu_s2p(sam, "unc")
+    assert p == op and st.log_text() == ost.log_text()
+
+
+def test_device_resident_path(oracle):
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    L = mk.lib()
+    n_groups = 60000
+    host = mk.synth_host(9, "unc", "hg38", 0, n_groups)
+    buf = torch.empty(len(host) + 64, dtype=torch.uint8, device="cuda")
+    n = C.c_size_t()
+    L.check(L.L.mk_synth_device(0, 9, 1, 0, 0, n_groups, buf.data_ptr(), len(host), C.byref(n), None))
+    assert n.value == len(host)
+    assert bytes(buf[:n.value].cpu().numpy().tobytes()) == host          # device generator == host generator
+    op, osam, ost = oracle.sam2pairs(host, "unc", threads=8)
+    s = mk.Sam2Pairs(mk.S2PConfig(mode="unc", threads=8, write_sam=True, emit_packed=True, window_bytes=8 << 20))
+    text = torch.empty(len(host), dtype=torch.uint8, device="cuda")
+    samo = torch.empty(len(host) + 64, dtype=torch.uint8, device="cuda")
+    pairs = torch.empty(n_groups * 16, dtype=torch.uint8, device="cuda")
+    io = s.run_device(buf.data_ptr(), n.value, True, text.data_ptr(), text.numel(), pairs.data_ptr(), n_groups, samo.data_ptr(), samo.numel())
+    st = s.finish()
+    assert io.consumed == n.value
+    assert bytes(text[:io.pairs_text_len].cpu().numpy().tobytes()) == op
+    assert bytes(samo[:io.sam_text_len].cpu().numpy().tobytes()) == osam
+    assert st.log_text() == ost.log_text() and io.n_pairs == st.pairs
+    s.close()
