@@ -1,0 +1,284 @@
+// pairs.cu — duplicate removal by sort + adjacent-unique, and contact binning to COO, over device-resident data.
+//
+//   mk_dedup_keys_device   64-bit keys (krmdup's 2-bit packed read bases, src/preprocess/krmdup.cpp:168-193):
+//                          stable radix sort of (key, index), first of every run is the occurrence the reference's
+//                          unordered_set keeps (krmdup.cpp:201-212)
+//   mk_pairs_dedup_device  mk_pair records sorted directly on (lane, chr1, pos1, chr2, pos2, strands), runs collapsed
+//   mk_pairs_bin_device    bin = offset[chr] + pos / res (util/analyze.EBV/calc.loop2EBV.pl:28), sort of (bin1,bin2)
+//                          keys, run-length encoding to COO triplets — stands in for `juicer_tools pre` (microcket:525-529)
+#include <algorithm>
+#include <vector>
+#include "mk_common.cuh"
+#include "radix_sort.cuh"
+
+struct K64 {                       // keys only
+    typedef u64 Key;
+    static constexpr int ITEMS = 16;
+    static constexpr bool HAS_VAL = false;
+    struct Bufs { u64 *k[2]; u32 *v[2]; };
+    __device__ static __forceinline__ u32 digit(const u64 &k, int byte) { return (u32)(k >> (8 * byte)) & 255u; }
+    __device__ static __forceinline__ u64 load_key(const Bufs &b, int which, u64 i) { return b.k[which][i]; }
+    __device__ static __forceinline__ void store_key(const Bufs &b, int which, u64 i, const u64 &k) { b.k[which][i] = k; }
+};
+
+// ------------------------------------------------------------------------------------------------ unique / compaction kernels
+#define UQ_T 256
+#define UQ_ITEMS 8
+
+// keep[idx] = first of run, for sorted (key, idx); counts uniques
+__global__ void __launch_bounds__(256) k_mark_first(const u64 *k0, const u64 *k1, const u32 *v0, const u32 *v1, const RadixPlan *plan,
+                                                    u64 n, u8 *keep, unsigned long long *n_unique) {
+    const u64 *k = plan->final_buf ? k1 : k0;
+    const u32 *v = plan->final_buf ? v1 : v0;
+    u32 local = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        bool first = i == 0 || k[i] != k[i - 1];
+        keep[plan->n_exec ? v[i] : (u32)i] = first ? 1 : 0;    // no pass ran (all keys equal): values are still the iota
+        local += first;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_unique, (unsigned long long)local);
+}
+
+__device__ __forceinline__ bool pair_key_differs(const uint4 &a, const uint4 &b) {
+    // identity = every field except cls (byte 13), which is a function of the others
+    return a.x != b.x || a.y != b.y || a.z != b.z || ((a.w ^ b.w) & 0xFFFF00FFu) != 0;
+}
+
+// stream compaction of the first record of every run (sorted records); single pass with look-back
+__global__ void __launch_bounds__(UQ_T) k_unique_rec16(const uint4 *b0, const uint4 *b1, const RadixPlan *plan, u64 n,
+                                                       uint4 *o0, uint4 *o1, u64 *desc, unsigned long long *n_out) {
+    __shared__ u32 s_scan[UQ_T / 32 + 1];
+    __shared__ u64 s_base;
+    const uint4 *in = plan->final_buf ? b1 : b0;
+    uint4 *out = plan->final_buf ? o0 : o1;                   // the other buffer
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
+        uint4 r[UQ_ITEMS]; u32 f = 0, cnt = 0;
+        uint4 prev = base > 0 && base <= n ? in[base - 1] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < UQ_ITEMS; ++k) {
+            if (base + k < n) {
+                r[k] = in[base + k];
+                bool first = (base + k == 0) || pair_key_differs(r[k], prev);
+                prev = r[k];
+                if (first) { f |= 1u << k; ++cnt; }
+            }
+        }
+        u32 tot;
+        u32 ex = block_excl_scan<UQ_T>(cnt, s_scan, &tot);
+        if (wid == 0) {
+            u64 b = lookback_exclusive(desc, tile, 0, tot, lane);
+            if (lane == 0) { s_base = b; if (tile == n_tiles - 1) *n_out = b + tot; }
+        }
+        __syncthreads();
+        u64 o = s_base + ex;
+#pragma unroll
+        for (int k = 0; k < UQ_ITEMS; ++k) if (f & (1u << k)) out[o++] = r[k];
+        __syncthreads();
+    }
+}
+
+// run heads of sorted 64-bit keys: head positions + keys, compacted (single pass with look-back)
+__global__ void __launch_bounds__(UQ_T) k_rle_heads(const u64 *k0, const u64 *k1, const RadixPlan *plan, u64 n,
+                                                    u64 *out_key, u32 *out_pos, u64 cap, u64 *desc, unsigned long long *n_out) {
+    __shared__ u32 s_scan[UQ_T / 32 + 1];
+    __shared__ u64 s_base;
+    const u64 *in = plan->final_buf ? k1 : k0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
+        u64 r[UQ_ITEMS]; u32 f = 0, cnt = 0;
+        u64 prev = base > 0 && base <= n ? in[base - 1] : 0;
+#pragma unroll
+        for (int k = 0; k < UQ_ITEMS; ++k) {
+            if (base + k < n) {
+                r[k] = in[base + k];
+                bool first = (base + k == 0) || r[k] != prev;
+                prev = r[k];
+                if (first) { f |= 1u << k; ++cnt; }
+            }
+        }
+        u32 tot;
+        u32 ex = block_excl_scan<UQ_T>(cnt, s_scan, &tot);
+        if (wid == 0) {
+            u64 b = lookback_exclusive(desc, tile, 0, tot, lane);
+            if (lane == 0) { s_base = b; if (tile == n_tiles - 1) *n_out = b + tot; }
+        }
+        __syncthreads();
+        u64 o = s_base + ex;
+#pragma unroll
+        for (int k = 0; k < UQ_ITEMS; ++k)
+            if (f & (1u << k)) { if (o < cap) { out_key[o] = r[k]; out_pos[o] = (u32)(base + k); } ++o; }
+        __syncthreads();
+    }
+}
+
+__global__ void k_rle_finish(const u64 *key, const u32 *pos, const unsigned long long *nnz_p, u64 n, u64 cap,
+                             u32 *bin1, u32 *bin2, u32 *cnt) {
+    const u64 nnz = *nnz_p < cap ? *nnz_p : cap;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) {
+        u64 k = key[i];
+        bin1[i] = (u32)(k >> 32); bin2[i] = (u32)k;
+        u32 nxt = (i + 1 < *nnz_p && i + 1 < cap) ? pos[i + 1] : (u32)n;
+        if (i + 1 < *nnz_p && i + 1 >= cap) nxt = pos[i] + 1;   // truncated output: count unknowable, caller gets an error
+        cnt[i] = nxt - pos[i];
+    }
+}
+
+// (bin1,bin2) key of every pair at one resolution
+__global__ void k_bin_keys(const mk_pair *p, u64 n, const u32 *chr_off /* per pair-chr id */, u32 res, u64 *key) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const uint4 r = ((const uint4 *)p)[i];
+        const u32 pos1 = r.x, pos2 = r.y, c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
+        u32 a = chr_off[c1] + pos1 / res, b = chr_off[c2] + pos2 / res;
+        if (a > b) { u32 t = a; a = b; b = t; }                 // upper triangle
+        key[i] = ((u64)a << 32) | b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct mk_pairs_ws {
+    int device = 0, sms = 148;
+    size_t max_pairs = 0;
+    RadixWs rws;
+    DevBuf alt;          // max_pairs * 16 B: second record buffer / key buffers
+    DevBuf keys2;        // max_pairs * 8 B
+    DevBuf heads_key, heads_pos;
+    DevBuf desc, counter, chr_off;
+    u64 launches = 0;
+};
+
+extern "C" int mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **out) {
+    if (!out || max_pairs == 0) { mk_set_error("mk_pairs_ws_create: bad argument"); return MK_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { mk_set_error("no CUDA device: microcket_b200 has no CPU fallback"); return MK_ERR_CUDA; }
+    MK_CUDA(cudaSetDevice(device));
+    mk_pairs_ws *w = new mk_pairs_ws();
+    w->device = device; w->sms = mk_sm_count(device); w->max_pairs = max_pairs;
+    int rc = w->rws.alloc(max_pairs);
+    if (rc == MK_OK) rc = w->alt.alloc(max_pairs * 16);
+    if (rc == MK_OK) rc = w->keys2.alloc(max_pairs * 8);
+    if (rc == MK_OK) rc = w->heads_key.alloc(max_pairs * 8);
+    if (rc == MK_OK) rc = w->heads_pos.alloc(max_pairs * 4);
+    if (rc == MK_OK) rc = w->desc.alloc((max_pairs / (UQ_T * UQ_ITEMS) + 4) * 8);
+    if (rc == MK_OK) rc = w->counter.alloc(64);
+    if (rc == MK_OK) rc = w->chr_off.alloc(65536 * 4);
+    if (rc != MK_OK) { delete w; return rc; }
+    *out = w;
+    return MK_OK;
+}
+extern "C" void mk_pairs_ws_destroy(mk_pairs_ws *w) { if (w) { cudaSetDevice(w->device); delete w; } }
+extern "C" uint64_t mk_pairs_launch_count(mk_pairs_ws *w) { return w ? w->launches : 0; }
+
+static int lookback_grid(const void *kernel, int threads, int sms) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0);
+    return sms * std::max(1, std::min(occ, 4));
+}
+
+extern "C" int mk_pairs_dedup_device(mk_pairs_ws *w, mk_pair *d_pairs, size_t n, size_t *n_kept, void *stream) {
+    if (!w || !n_kept) { mk_set_error("mk_pairs_dedup_device: bad argument"); return MK_ERR_ARG; }
+    if (n > w->max_pairs) { mk_set_error("mk_pairs_dedup_device: workspace holds %zu pairs, got %zu", w->max_pairs, n); return MK_ERR_CAPACITY; }
+    MK_CUDA(cudaSetDevice(w->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) { *n_kept = 0; return MK_OK; }
+    // LSD byte schedule over the mk_pair layout: strands(12) pos2(4..7) chr2(10,11) pos1(0..3) chr1(8,9) lane(14,15)
+    RadixSchedule sch; sch.n_pass = 15;
+    const int order[15] = {12, 4, 5, 6, 7, 10, 11, 0, 1, 2, 3, 8, 9, 14, 15};
+    for (int i = 0; i < 15; ++i) sch.byte_of[i] = order[i];
+    Rec16::Bufs b; b.k[0] = (uint4 *)d_pairs; b.k[1] = w->alt.as<uint4>(); b.v[0] = b.v[1] = nullptr;
+    MK_TRY(radix_sort<Rec16>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
+    const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
+    MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
+    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
+    k_unique_rec16<<<lookback_grid((const void *)k_unique_rec16, UQ_T, w->sms), UQ_T, 0, s>>>(
+        b.k[0], b.k[1], w->rws.plan.as<RadixPlan>(), n, b.k[0], b.k[1], w->desc.as<u64>(), w->counter.as<unsigned long long>());
+    w->launches += 1;
+    struct { unsigned long long kept; } hc;
+    u32 final_buf = 0;
+    MK_CUDA(cudaMemcpyAsync(&hc, w->counter.p, 8, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaMemcpyAsync(&final_buf, (char *)w->rws.plan.p + offsetof(RadixPlan, final_buf), 4, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    // sorted data sat in buffer final_buf, the compacted run heads went to the other one
+    if (final_buf == 0) MK_CUDA(cudaMemcpyAsync(d_pairs, w->alt.p, (size_t)hc.kept * 16, cudaMemcpyDeviceToDevice, s));
+    *n_kept = (size_t)hc.kept;
+    MK_CUDA(cudaStreamSynchronize(s));
+    return MK_OK;
+}
+
+extern "C" int mk_pairs_bin_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_t n, const uint32_t *chrom_len, int n_chrom,
+                                   const uint16_t *chrom_id_map, int n_map, uint32_t res, uint32_t *d_bin1, uint32_t *d_bin2,
+                                   uint32_t *d_cnt, size_t cap, size_t *nnz, void *stream) {
+    if (!w || !nnz || !chrom_len || n_chrom <= 0 || res == 0) { mk_set_error("mk_pairs_bin_device: bad argument"); return MK_ERR_ARG; }
+    if (n > w->max_pairs) { mk_set_error("mk_pairs_bin_device: workspace holds %zu pairs, got %zu", w->max_pairs, n); return MK_ERR_CAPACITY; }
+    MK_CUDA(cudaSetDevice(w->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) { *nnz = 0; return MK_OK; }
+    // bin offset of every chromosome in the given order; then per pair-chromosome-id through the map
+    std::vector<u64> off(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; ++c) off[c + 1] = off[c] + chrom_len[c] / res + 1;
+    if (off[n_chrom] >= (1ull << 32)) { mk_set_error("mk_pairs_bin_device: more than 2^32 bins"); return MK_ERR_CAPACITY; }
+    const int n_ids = chrom_id_map ? n_map : n_chrom;
+    if (n_ids > 65536) { mk_set_error("mk_pairs_bin_device: too many chromosome ids"); return MK_ERR_ARG; }
+    std::vector<u32> by_id(n_ids);
+    for (int i = 0; i < n_ids; ++i) {
+        int c = chrom_id_map ? chrom_id_map[i] : i;
+        if (c < 0 || c >= n_chrom) { mk_set_error("mk_pairs_bin_device: chromosome map entry %d out of range", i); return MK_ERR_ARG; }
+        by_id[i] = (u32)off[c];
+    }
+    MK_CUDA(cudaMemcpyAsync(w->chr_off.p, by_id.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice, s));
+    u64 *k0 = w->alt.as<u64>(), *k1 = w->keys2.as<u64>();
+    k_bin_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, w->chr_off.as<u32>(), res, k0);
+    w->launches += 1;
+    int nbytes = 1; while (nbytes < 4 && (off[n_chrom] >> (8 * nbytes))) ++nbytes;
+    RadixSchedule sch; sch.n_pass = 0;
+    for (int i = 0; i < nbytes; ++i) sch.byte_of[sch.n_pass++] = i;
+    for (int i = 0; i < nbytes; ++i) sch.byte_of[sch.n_pass++] = 4 + i;
+    K64::Bufs b; b.k[0] = k0; b.k[1] = k1; b.v[0] = b.v[1] = nullptr;
+    MK_TRY(radix_sort<K64>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
+    const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
+    MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
+    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
+    unsigned long long *cnt = w->counter.as<unsigned long long>();
+    k_rle_heads<<<lookback_grid((const void *)k_rle_heads, UQ_T, w->sms), UQ_T, 0, s>>>(
+        k0, k1, w->rws.plan.as<RadixPlan>(), n, w->heads_key.as<u64>(), w->heads_pos.as<u32>(), w->max_pairs, w->desc.as<u64>(), cnt);
+    k_rle_finish<<<w->sms * 4, 256, 0, s>>>(w->heads_key.as<u64>(), w->heads_pos.as<u32>(), cnt, n, cap, d_bin1, d_bin2, d_cnt);
+    w->launches += 2;
+    unsigned long long h = 0;
+    MK_CUDA(cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    *nnz = (size_t)h;
+    if (h > cap) { mk_set_error("mk_pairs_bin_device: %llu non-zero cells, output capacity %zu", h, cap); return MK_ERR_CAPACITY; }
+    return MK_OK;
+}
+
+extern "C" int mk_dedup_keys_device(int device, const uint64_t *d_keys, size_t n, uint8_t *d_keep, uint64_t *n_unique, void *stream) {
+    if (!d_keys || !d_keep || !n_unique) { mk_set_error("mk_dedup_keys_device: bad argument"); return MK_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { mk_set_error("no CUDA device: microcket_b200 has no CPU fallback"); return MK_ERR_CUDA; }
+    MK_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    *n_unique = 0;
+    if (n == 0) return MK_OK;
+    RadixWs rws; MK_TRY(rws.alloc(n));
+    DevBuf k0, k1, v0, v1, cnt;
+    MK_TRY(k0.alloc(n * 8)); MK_TRY(k1.alloc(n * 8)); MK_TRY(v0.alloc(n * 4)); MK_TRY(v1.alloc(n * 4)); MK_TRY(cnt.alloc(8));
+    MK_CUDA(cudaMemcpyAsync(k0.p, d_keys, n * 8, cudaMemcpyDeviceToDevice, s));
+    MK_CUDA(cudaMemsetAsync(cnt.p, 0, 8, s));
+    RadixSchedule sch; sch.n_pass = 8;
+    for (int i = 0; i < 8; ++i) sch.byte_of[i] = i;
+    KV64::Bufs b; b.k[0] = k0.as<u64>(); b.k[1] = k1.as<u64>(); b.v[0] = v0.as<u32>(); b.v[1] = v1.as<u32>();
+    u64 launches = 0;
+    const int sms = mk_sm_count(device);
+    MK_TRY(radix_sort<KV64>(b, n, sch, rws, 1, sms, s, &launches));
+    k_mark_first<<<sms * 8, 256, 0, s>>>(b.k[0], b.k[1], b.v[0], b.v[1], rws.plan.as<RadixPlan>(), n, d_keep, cnt.as<unsigned long long>());
+    unsigned long long h = 0;
+    MK_CUDA(cudaMemcpyAsync(&h, cnt.p, 8, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    *n_unique = h;
+    return MK_OK;
+}

@@ -92,7 +92,7 @@ struct S2PParams {
 };
 
 // ------------------------------------------------------------------------------------------------ begin / end
-__global__ void k_win_begin(S2PParams p, u32 n_desc) {
+static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_desc) { p.desc_scan[i] = 0; p.desc_emitA[i] = 0; p.desc_emitB[i] = 0; }
     if (i == 0) {
@@ -107,7 +107,7 @@ __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     }
 }
 
-__global__ void k_win_end(S2PParams p) {
+static __global__ void k_win_end(S2PParams p) {
     WinState *s = p.st;
     u64 ws = s->ws, we = s->we;
     u32 n = s->n_lines;
@@ -131,19 +131,18 @@ __global__ void k_win_end(S2PParams p) {
 // Tile = 32 KiB at absolute 32 KiB boundaries of the buffer.  Loads are coalesced 128-bit streaming
 // loads; the 16 newline flags of every 16-byte word go through shared memory so that each thread then
 // owns 128 CONTIGUOUS bytes (8 words), which makes ranks a single block scan.
-__global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
+// Shared by the SAM and FASTQ paths: positions (relative to ws) of every '\n' in [ws, we).
+__device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, const u64 we, const int first_tile,
+                                                u32 *nl_pos, const u32 cap_lines, u64 *desc, u32 *n_lines_out, u32 *err_out, u32 err_bit) {
     __shared__ __align__(16) u16 s_mask[S2P_TILE_BYTES / 16];
     __shared__ u32 s_scan[S2P_SCAN_THREADS / 32 + 1];
     __shared__ u32 s_base;
-    WinState *st = p.st;
-    const u64 ws = st->ws, we = st->we;
     if (we <= ws) return;
-    const int first_tile = (int)st->first_tile;
     const int last_tile = (int)((we - 1) / S2P_TILE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int tile = first_tile + blockIdx.x; tile <= last_tile; tile += gridDim.x) {
         const u64 tbase = (u64)tile * S2P_TILE_BYTES;
-        const uint4 *src = (const uint4 *)(p.buf + tbase);
+        const uint4 *src = (const uint4 *)(buf + tbase);
         uint4 w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -166,13 +165,13 @@ __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
         u32 total;
         u32 excl = block_excl_scan<S2P_SCAN_THREADS>(cnt, s_scan, &total);
         if (wid == 0) {
-            u64 b = lookback_exclusive(p.desc_scan - first_tile, tile, first_tile, total, lane);
+            u64 b = lookback_exclusive(desc - first_tile, tile, first_tile, total, lane);
             if (lane == 0) {
                 s_base = (u32)b;
                 if (tile == last_tile) {
                     u64 nl = b + total;
-                    if (nl > p.cap_lines) { atomicOr(&st->err, S2P_ERR_LINES); nl = p.cap_lines; }
-                    st->n_lines = (u32)nl;
+                    if (nl > cap_lines) { atomicOr(err_out, err_bit); nl = cap_lines; }
+                    *n_lines_out = (u32)nl;
                 }
             }
         }
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
             u32 m = parts[q];
             while (m) {
                 int b = __ffs(m) - 1; m &= m - 1;
-                if (idx < p.cap_lines) p.nl_pos[idx] = rel + q * 32 + b;
+                if (idx < cap_lines) nl_pos[idx] = rel + q * 32 + b;
                 ++idx;
             }
         }
@@ -193,11 +192,16 @@ __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
     }
 }
 
+static __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
+    WinState *st = p.st;
+    scan_lines_body(p.buf, st->ws, st->we, (int)st->first_tile, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
+}
+
 // ------------------------------------------------------------------------------------------------ chromosome table
 __device__ __forceinline__ u64 hash_step(u64 h, int c) { return (h ^ (u64)c) * 0x100000001B3ull; }
 
 // Returns the slot of the name; inserts it when unseen (lock-free; ids are published by the inserter).
-__device__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 name8, const char *buf, u64 name_off, u32 len) {
+static __device__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 name8, const char *buf, u64 name_off, u32 len) {
     if (h == 0) h = 0x9E3779B97F4A7C15ull;
     const u32 l = len < S2P_NAME_MAX ? len : S2P_NAME_MAX;
     u32 s = (u32)(h ^ (h >> 29)) & p.chr_mask;
@@ -238,7 +242,7 @@ __device__ __forceinline__ u32 parse_uint_tok(ByteReader &r, int &c) {
     return (bad || n == 0) ? 0u : v;
 }
 
-__global__ void __launch_bounds__(256) k_parse(S2PParams p) {
+static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
@@ -348,7 +352,7 @@ __device__ __forceinline__ bool mates(const Seg &lone, const Seg &c) {
 }
 __device__ __forceinline__ u32 distal_end(const Seg &s) { return (int)s.leftClip > (int)s.rightClip ? s.right0 : s.pos; }
 
-__device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
+static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
     ByteReader x, y;
     x.init(p.buf, ws + (a ? p.nl_pos[a - 1] + 1 : 0));
     y.init(p.buf, ws + (b ? p.nl_pos[b - 1] + 1 : 0));
@@ -360,7 +364,7 @@ __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
 }
 
 // bytewise order of two chromosome names (std::string::compare)
-__device__ int chr_name_cmp(const S2PParams &p, u16 sa, u16 sb) {
+static __device__ int chr_name_cmp(const S2PParams &p, u16 sa, u16 sb) {
     if (sa == sb) return 0;
     const ChrSlot *a = &p.chr[sa], *b = &p.chr[sb];
     u32 la = a->len, lb = b->len, m = la < lb ? la : lb;
@@ -376,7 +380,7 @@ __device__ __forceinline__ u32 dec_digits(u32 v) {
            v >= 10000u ? 5 : v >= 1000u ? 4 : v >= 100u ? 3 : v >= 10u ? 2 : 1;
 }
 
-__global__ void __launch_bounds__(256) k_group(S2PParams p) {
+static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
     if (threadIdx.x < ST_NCOUNTER) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -574,7 +578,7 @@ __device__ __forceinline__ void write_pair_line(const S2PParams &p, u64 ws, cons
 }
 struct PtrSink { char *p; __device__ __forceinline__ void put(char c) { *p++ = c; } };
 
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
+static __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
     __shared__ u32 s_scanA[EMIT_THREADS / 32 + 1], s_scanT[EMIT_THREADS / 32 + 1], s_scanS[EMIT_THREADS / 32 + 1];
     __shared__ u64 s_baseA, s_baseB;
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
 
 // ------------------------------------------------------------------------------------------------ K5: SAM passthrough
 // One warp per line: the lines of emitted groups are copied verbatim (with their '\n').
-__global__ void __launch_bounds__(256) k_copy_sam(S2PParams p) {
+static __global__ void __launch_bounds__(256) k_copy_sam(S2PParams p) {
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws, base = st->out_sam;
