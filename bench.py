@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py — valid pairs/s through SAM -> pairs -> dedup -> 5 kb bins on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU code (oracle/_ref), same workload
+
+Workload (BASELINE.json configs[1]): hg38 Micro-C 150-cycle stitched-read SAM ("flash" mode), 100 M read groups per
+GPU, synthetic (microcket_b200/csrc/synth.h), sam2pairs + coordinate dedup + 5 kb binning.  One step = one pass of
+that whole path over the GPU's shard.  `value` times the path with the SAM text already resident in HBM; `e2e` times
+the same path through the host-buffer C-ABI calls (pinned host SAM in, pairs text + COO counts out).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+HG38 = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr2", "chr20",
+        "chr21", "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
+HG38_LEN = [248956422, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616,
+            242193529, 64444167, 46709983, 50818468, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+            16569, 156040895, 57227415]
+RES = 5000
+SEED = 0x4D4B0002
+METRIC = "valid pairs/sec (SAM->dedup->binned)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def synth_to_device(torch, mk, first, count, device):
+    """→ (uint8 cuda tensor holding the SAM text, n_bytes)"""
+    L = mk.lib()
+    n = C.c_size_t()
+    L.check(L.L.mk_synth_device(device, SEED, 0, 0, first, count, None, 0, C.byref(n), None))
+    buf = torch.empty(n.value + 256, dtype=torch.uint8, device=f"cuda:{device}")
+    L.check(L.L.mk_synth_device(device, SEED, 0, 0, first, count, buf.data_ptr(), n.value, C.byref(n), None))
+    return buf, n.value
+
+
+def reference_sample(torch, mk, n_groups, device, tmpdir):
+    """Write the first n_groups of the workload to a file for the CPU arm."""
+    buf, nb = synth_to_device(torch, mk, 0, n_groups, device)
+    path = os.path.join(tmpdir, "sample.sam")
+    host = buf[:nb].cpu().numpy()
+    with open(path, "wb") as f:
+        f.write(host.tobytes())
+    del buf
+    return path, nb
+
+
+def cpu_pipeline_once(sam_path, tmpdir, threads):
+    """reference sam2pairs (oracle/_ref, its own sources) -> oracle coordinate dedup + 5 kb binning.  → (pairs, seconds, kind)"""
+    import oracle_lib
+    ref = os.path.join(ROOT, "oracle", "_ref", "sam2pairs")
+    pre = os.path.join(tmpdir, "cpu")
+    t0 = time.time()
+    if os.path.exists(ref):
+        kind = "reference"
+        out = subprocess.run([ref, sam_path, "flash", pre, str(threads), "0.5", "10", "0"], check=True, capture_output=True).stdout
+    else:
+        kind = "port"
+        cli = os.path.join(ROOT, "oracle", "_build", "oracle_cli")
+        if not os.path.exists(cli):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+        out = subprocess.run([cli, "sam2pairs", sam_path, "flash", pre, str(threads), "0.5", "10", "0"], check=True, capture_output=True).stdout
+    orc = oracle_lib.load()
+    pairs, n = orc.pairs_parse(out, HG38)
+    keep, kept = orc.coord_dedup(pairs, n)
+    orc.bin_coo(pairs, n, keep, HG38_LEN, RES)
+    return n, time.time() - t0, kind
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import microcket_b200 as mk
+    threads = max(2, min(host_cores(), 8))          # the driver passes sthread = 8 (microcket:461-466); the program does not scale further
+    sample_groups = args.cpu_groups
+    tmpdir = tempfile.mkdtemp(prefix="mkbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        path, nb = reference_sample(torch, mk, sample_groups, 0, tmpdir)
+        times, pairs, kind = [], 0, "reference"
+        for it in range(args.warmup + args.steps):
+            pairs, sec, kind = cpu_pipeline_once(path, tmpdir, threads)
+            if it >= args.warmup:
+                times.append(sec)
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+    ms = 1e3 * sum(times) / len(times)
+    val = pairs / (ms / 1e3)
+    sample = f"{sample_groups} read groups ({nb / 1e9:.2f} GB SAM) of the same synthetic workload per step, page-cache-warm file in /dev/shm"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(args, 1, sample_groups),
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, world, groups):
+    return {"workload": "BASELINE configs[1]: hg38 Micro-C 150-cycle stitched-read SAM (flash mode), sam2pairs + coordinate dedup + 5kb binning",
+            "read_groups_per_gpu": groups, "genome": "hg38", "mode": "flash", "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
+            "seed": SEED, "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
+            "parallelism": f"shard{world}: parse by read chunk, dedup keys all-to-all by hash(chr1,chr2,pos1/{RES}), COO owner-computes"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("MK_BENCH_GROUPS", 100_000_000)), help="read groups per GPU")
+    ap.add_argument("--e2e-groups", type=int, default=int(os.environ.get("MK_BENCH_E2E_GROUPS", 6_000_000)))
+    ap.add_argument("--cpu-groups", type=int, default=int(os.environ.get("MK_BENCH_CPU_GROUPS", 2_000_000)))
+    ap.add_argument("--window-mb", type=int, default=int(os.environ.get("MK_BENCH_WINDOW_MB", 1024)))
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import microcket_b200 as mk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    mk.lib().require_gpu()                            # no CPU fallback
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    G = args.groups
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- resident workload
+    sam, nbytes = synth_to_device(torch, mk, rank * G, G, local)
+    text = torch.empty(G * 100 + (1 << 20), dtype=torch.uint8, device=dev)
+    cap_pairs = int(G * (1.0 if world == 1 else 1.3)) + 4096
+    pairs = torch.empty(cap_pairs * 16, dtype=torch.uint8, device=dev)
+    ws = mk.PairsWorkspace(cap_pairs, device=local)
+    recv = torch.empty(cap_pairs * 16, dtype=torch.uint8, device=dev) if world > 1 else None
+    b1 = torch.empty(cap_pairs, dtype=torch.int32, device=dev); b2 = torch.empty_like(b1); cnt = torch.empty_like(b1)
+    s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local,
+                                    window_bytes=args.window_mb << 20, sharded=(world > 1)), HG38)
+
+    def step():
+        s2p.reset()
+        io = s2p.run_device(sam.data_ptr(), nbytes, True, text.data_ptr(), text.numel(), pairs.data_ptr(), cap_pairs, stream=stream)
+        n = io.n_pairs
+        src = pairs
+        if world > 1:
+            from microcket_b200 import shard
+            n, src = shard.exchange_pairs(mk, torch, dist, ws, pairs, n, recv, cap_pairs, RES, stream)
+        kept = ws.dedup(src.data_ptr(), n, stream=stream)
+        nnz = ws.bin(src.data_ptr(), kept, HG38_LEN, RES, b1.data_ptr(), b2.data_ptr(), cnt.data_ptr(), cap_pairs, stream=stream)
+        return io.n_pairs, kept, nnz
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    s2p.enable_timing(True)
+    clocks = ClockSampler(local)
+    launches0 = s2p.launches() + ws.launches()
+    kt0 = s2p.kernel_times()
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        n_pairs, kept, nnz = step()
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    kt1 = s2p.kernel_times()
+    launches = s2p.launches() + ws.launches() - launches0
+    s2p.enable_timing(False)
+    st = s2p.finish(0, 0) if world > 1 else s2p.finish()
+    t = torch.tensor([ms_total, float(n_pairs), float(kept), float(nnz)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, n_pairs_all, kept_all, nnz_all = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+    else:
+        n_pairs_all, kept_all, nnz_all = float(n_pairs), float(kept), float(nnz)
+    ms_step = ms_total / args.steps
+    value = n_pairs_all / (ms_step / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from CUDA events recorded on the launching stream during the timed region
+    peak, peak_src = measured_peak()
+    dk = {k: (kt1[k][0] - kt0[k][0], kt1[k][1] - kt0[k][1]) for k in kt1}
+    dom = max(dk, key=lambda k: dk[k][0])
+    dom_ms, dom_n = dk[dom]
+    lines = st.lines / max(1, 1)                       # lines of one pass (reset() clears the stream totals each step)
+    alg_bytes_step = {"k_scan_lines": nbytes + 4 * lines, "k_parse": nbytes, "k_group": nbytes, "k_emit": nbytes + 72.0 * n_pairs,
+                      "k_copy_sam": nbytes}[dom]
+    launches_per_step = max(1.0, dom_n / args.steps)
+    achieved = (alg_bytes_step / launches_per_step) / (dom_ms / max(dom_n, 1) / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    stage_ms = sum(v[0] for v in dk.values()) / args.steps
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "launches_per_step": launches_per_step, "avg_launch_ms": dom_ms / max(dom_n, 1),
+                "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
+                "s2p_stage": {"ms_per_step": stage_ms, "GBps": (nbytes + 72.0 * n_pairs) / (stage_ms / 1e3) / 1e9 if stage_ms else 0.0,
+                              "frac": ((nbytes + 72.0 * n_pairs) / (stage_ms / 1e3) / 1e9 / peak) if stage_ms else 0.0},
+                "kernels_ms_per_step": {k: v[0] / args.steps for k, v in dk.items()}}
+
+    # ---- end to end through the host-buffer C ABI (pinned host SAM in; pairs text, packed pairs and COO out)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        e2e = measure_e2e(torch, mk, np, args, local, ws)
+    # ---- reference CPU path beside it (bounded sample)
+    cpu = None
+    if not args.no_cpu and world == 1:
+        tmpdir = tempfile.mkdtemp(prefix="mkbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            path, nb = reference_sample(torch, mk, args.cpu_groups, local, tmpdir)
+            threads = max(2, min(host_cores(), 8))
+            p, sec, kind = cpu_pipeline_once(path, tmpdir, threads)
+            cpu = {"value": p / sec, "unit": "pairs/s", "cores": threads, "kind": kind, "host_cores": host_cores(),
+                   "sample": f"{args.cpu_groups} read groups ({nb / 1e9:.2f} GB SAM) of the same workload, one pass, {sec:.1f} s: "
+                             f"reference sam2pairs (T={threads}) + oracle dedup/binning (1 thread)"}
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
+
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": dict(workload_config(args, world, G), sam_bytes_per_gpu=nbytes, pairs_per_step=n_pairs_all, kept_after_dedup=kept_all,
+                           coo_cells=nnz_all, window_mb=args.window_mb),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def measure_e2e(torch, mk, np, args, local, ws):
+    E = min(args.e2e_groups, args.groups)
+    sam_d, nb = synth_to_device(torch, mk, 0, E, local)
+    host = torch.empty(nb, dtype=torch.uint8).pin_memory()
+    host.copy_(sam_d[:nb])
+    del sam_d
+    torch.cuda.synchronize()
+    out_text = torch.empty(E * 100 + (1 << 20), dtype=torch.uint8).pin_memory()
+    out_pairs = torch.empty((E + 1024) * 16, dtype=torch.uint8).pin_memory()
+    ob1 = torch.empty(E + 1024, dtype=torch.int32).pin_memory(); ob2 = torch.empty_like(ob1).pin_memory(); oc = torch.empty_like(ob1).pin_memory()
+    W = 256 << 20
+    s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W), HG38)
+
+    def once():
+        s2p.reset()
+        tl = pl = 0
+        off = 0
+        while off < nb:
+            m = min(W, nb - off)
+            s2p.push_ptr(host.data_ptr() + off, m, off + m == nb)
+            off += m
+            a, b = s2p.pull_into(out_text.data_ptr() + tl, out_text.numel() - tl, out_pairs.data_ptr() + pl * 16, E + 1024 - pl)
+            tl += a; pl += b
+        while True:
+            a, b = s2p.pull_into(out_text.data_ptr() + tl, out_text.numel() - tl, out_pairs.data_ptr() + pl * 16, E + 1024 - pl)
+            tl += a; pl += b
+            if a == 0 and b == 0:
+                break
+        st = s2p.finish()
+        assert st.pairs == pl
+        kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, HG38_LEN, RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), E + 1024)
+        return pl, tl, kept, nnz
+
+    for _ in range(2):
+        once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = max(2, min(args.steps, 5))
+    for _ in range(reps):
+        pl, tl, kept, nnz = once()
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / reps
+    s2p.close()
+    return {"value": pl / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(nb + pl * 16), "d2h_bytes_per_step": int(tl + pl * 16 + kept * 16 + nnz * 12),
+            "read_groups": E, "ms_per_step": sec * 1e3,
+            "api": "mk_s2p_push/pull/pull_packed/finish + mk_pairs_dedup_bin_host, host pinned buffers, wall clock incl. all copies"}
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,8 @@ int  mk_s2p_finish(mk_ctx *, mk_s2p_stats *);
 /* Sharded finish: this context processed groups [group_base, group_base + stats.groups) of a stream of
  * total_groups processed groups (multi-GPU: bases from an all-gather of per-rank group counts). */
 int  mk_s2p_finish_sharded(mk_ctx *, uint64_t group_base, uint64_t total_groups, mk_s2p_stats *);
+/* Start over on a new input with the same configuration, allocations and chromosome table. */
+int  mk_s2p_reset(mk_ctx *);
 /* Chromosome table after (or during) a run: id → name. */
 int  mk_s2p_chrom_count(mk_ctx *);
 int  mk_s2p_chrom_name(mk_ctx *, int id, char *buf, size_t cap);
@@ -116,6 +118,10 @@ typedef struct {
 int  mk_s2p_run_device(mk_ctx *, const char *d_sam, size_t n, int is_last, mk_s2p_dev_io *io, void *stream);
 /* number of kernel launches issued by this context so far (for bench accounting) */
 uint64_t mk_launch_count(mk_ctx *);
+/* Optional per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figure).
+ * ms[k] / count[k], k = 0 newline scan, 1 parse, 2 group, 3 emit, 4 SAM passthrough; arrays of 5. */
+int  mk_s2p_enable_timing(mk_ctx *, int on);
+int  mk_s2p_kernel_times(mk_ctx *, double *ms, uint64_t *count);
 
 /* ------------------------------------------------------------------ krmdup */
 typedef struct {
@@ -151,6 +157,17 @@ int  mk_pairs_bin_device(mk_pairs_ws *, const mk_pair *d_pairs, size_t n,
                          const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map,
                          uint32_t res, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
                          size_t *nnz, void *stream);
+/* Multi-GPU: group pairs by owner rank = mix(chr1, chr2, pos1 / res) mod world into d_out (segments in rank order;
+ * counts[r] pairs for rank r).  The caller moves the segments with an all-to-all (NCCL via torch.distributed in
+ * bench.py); afterwards equal keys and equal (bin1,bin2) cells at `res` are on one rank. */
+int  mk_pairs_partition_device(mk_pairs_ws *, const mk_pair *d_pairs, size_t n, int world, uint32_t res, mk_pair *d_out,
+                               uint64_t *counts, void *stream);
+uint32_t mk_pairs_owner(uint32_t chr1, uint32_t chr2, uint32_t pos1, uint32_t res, uint32_t world);
+/* Host-buffer form of the two calls above (pairs2bins CLI, end-to-end measurements): `pairs` is replaced by the kept
+ * pairs in key order when do_dedup != 0; COO triplets are written to bin1/bin2/cnt when res != 0. */
+int  mk_pairs_dedup_bin_host(mk_pairs_ws *, mk_pair *pairs, size_t n, int do_dedup,
+                             const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map, uint32_t res,
+                             uint32_t *bin1, uint32_t *bin2, uint32_t *cnt, size_t cap, size_t *n_kept, size_t *nnz);
 uint64_t mk_pairs_launch_count(mk_pairs_ws *);
 
 /* ------------------------------------------------------------------ synthetic inputs (tests / bench) */

@@ -93,6 +93,7 @@ class Lib:
         L.mk_s2p_pull_packed.argtypes = [vp, vp, sz, P(sz)]
         L.mk_s2p_finish.argtypes = [vp, P(S2PStats)]
         L.mk_s2p_finish_sharded.argtypes = [vp, u64, u64, P(S2PStats)]
+        L.mk_s2p_reset.argtypes = [vp]
         L.mk_s2p_chrom_count.argtypes = [vp]
         L.mk_s2p_chrom_name.argtypes = [vp, i, C.c_char_p, sz]
         L.mk_s2p_run_device.argtypes = [vp, vp, sz, i, P(S2PDevIO), vp]
@@ -107,9 +108,15 @@ class Lib:
                            ("mk_pairs_ws_create", [i, sz, P(vp)]), ("mk_pairs_ws_destroy", [vp]),
                            ("mk_pairs_dedup_device", [vp, vp, sz, P(sz), vp]),
                            ("mk_pairs_bin_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, vp, vp, vp, sz, P(sz), vp]),
+                           ("mk_pairs_dedup_bin_host", [vp, vp, sz, i, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, vp, vp, vp, sz, P(sz), P(sz)]),
+                           ("mk_s2p_enable_timing", [vp, i]), ("mk_s2p_kernel_times", [vp, P(C.c_double), P(u64)]),
+                           ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
                 getattr(L, name).argtypes = args
+        if hasattr(L, "mk_pairs_owner"):
+            L.mk_pairs_owner.argtypes = [C.c_uint32] * 5
+            L.mk_pairs_owner.restype = C.c_uint32
         if hasattr(L, "mk_pairs_launch_count"):
             L.mk_pairs_launch_count.restype = u64
 
@@ -214,6 +221,9 @@ class Sam2Pairs:
             self.lib.check(self.lib.L.mk_s2p_finish_sharded(self.h, group_base, total_groups, C.byref(st)))
         return st
 
+    def reset(self):
+        self.lib.check(self.lib.L.mk_s2p_reset(self.h))
+
     def chrom_names(self):
         n = self.lib.L.mk_s2p_chrom_count(self.h)
         buf = C.create_string_buffer(64)
@@ -241,6 +251,28 @@ class Sam2Pairs:
 
     def launches(self):
         return self.lib.L.mk_launch_count(self.h)
+
+    def enable_timing(self, on=True):
+        self.lib.check(self.lib.L.mk_s2p_enable_timing(self.h, int(on)))
+
+    def kernel_times(self):
+        """→ {name: (total_ms, launches)} measured with CUDA events on the launching stream."""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_uint64 * 5)()
+        self.lib.check(self.lib.L.mk_s2p_kernel_times(self.h, ms, cnt))
+        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_lines", "k_parse", "k_group", "k_emit", "k_copy_sam"))}
+
+    def push_ptr(self, ptr, n, is_last=False):
+        """push() from a raw host pointer (e.g. a pinned torch tensor): no Python-side copy."""
+        self.lib.check(self.lib.L.mk_s2p_push(self.h, C.cast(ptr, C.c_char_p), n, int(is_last)))
+
+    def pull_into(self, text_ptr, text_cap, pairs_ptr=0, pairs_cap=0):
+        """pull pair text (+ packed pairs) straight into caller memory → (text_bytes, n_pairs)"""
+        n, n2, npk = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self.lib.check(self.lib.L.mk_s2p_pull(self.h, text_ptr, text_cap, C.byref(n), None, 0, C.byref(n2)))
+        if pairs_ptr:
+            self.lib.check(self.lib.L.mk_s2p_pull_packed(self.h, pairs_ptr, pairs_cap, C.byref(npk)))
+        return n.value, npk.value
 
 
 class Krmdup:
@@ -338,6 +370,22 @@ class PairsWorkspace:
 
     def launches(self):
         return self.lib.L.mk_pairs_launch_count(self.h)
+
+    def partition(self, d_pairs, n, world, res, d_out, stream=0):
+        counts = (C.c_uint64 * world)()
+        self.lib.check(self.lib.L.mk_pairs_partition_device(self.h, d_pairs, n, world, res, d_out, counts, stream))
+        return list(counts)
+
+    def dedup_bin_host(self, pairs_ptr, n, chrom_len, res, b1_ptr, b2_ptr, c_ptr, cap, do_dedup=True, chrom_id_map=None):
+        cl = (C.c_uint32 * len(chrom_len))(*chrom_len)
+        if chrom_id_map is not None:
+            mp = (C.c_uint16 * len(chrom_id_map))(*chrom_id_map); nm = len(chrom_id_map)
+        else:
+            mp, nm = None, 0
+        kept, nnz = C.c_size_t(), C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_dedup_bin_host(self.h, pairs_ptr, n, int(do_dedup), cl, len(chrom_len), mp, nm, res,
+                                                          b1_ptr, b2_ptr, c_ptr, cap, C.byref(kept), C.byref(nnz)))
+        return kept.value, nnz.value
 
 
 def synth_host(seed, mode, genome, first, count) -> bytes:

@@ -149,6 +149,7 @@ struct mk_pairs_ws {
     DevBuf keys2;        // max_pairs * 8 B
     DevBuf heads_key, heads_pos;
     DevBuf desc, counter, chr_off;
+    DevBuf h_pairs, h_b1, h_b2, h_c;   // device staging of the host-buffer API, allocated on first use
     u64 launches = 0;
 };
 
@@ -164,7 +165,7 @@ extern "C" int mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **ou
     if (rc == MK_OK) rc = w->keys2.alloc(max_pairs * 8);
     if (rc == MK_OK) rc = w->heads_key.alloc(max_pairs * 8);
     if (rc == MK_OK) rc = w->heads_pos.alloc(max_pairs * 4);
-    if (rc == MK_OK) rc = w->desc.alloc((max_pairs / (UQ_T * UQ_ITEMS) + 4) * 8);
+    if (rc == MK_OK) rc = w->desc.alloc((max_pairs / (UQ_T * UQ_ITEMS) + 4) * 8 + 2048);
     if (rc == MK_OK) rc = w->counter.alloc(64);
     if (rc == MK_OK) rc = w->chr_off.alloc(65536 * 4);
     if (rc != MK_OK) { delete w; return rc; }
@@ -281,4 +282,104 @@ extern "C" int mk_dedup_keys_device(int device, const uint64_t *d_keys, size_t n
     MK_CUDA(cudaStreamSynchronize(s));
     *n_unique = h;
     return MK_OK;
+}
+
+// Host-buffer convenience over the two device entry points: packed pairs in host memory -> kept pairs (sorted, in place
+// in `pairs`) and COO counts at one resolution in host memory.  What the pairs2bins CLI and bench.py's e2e leg call.
+extern "C" int mk_pairs_dedup_bin_host(mk_pairs_ws *w, mk_pair *pairs, size_t n, int do_dedup, const uint32_t *chrom_len, int n_chrom,
+                                       const uint16_t *chrom_id_map, int n_map, uint32_t res,
+                                       uint32_t *bin1, uint32_t *bin2, uint32_t *cnt, size_t cap, size_t *n_kept, size_t *nnz) {
+    if (!w || !pairs || !n_kept || !nnz) { mk_set_error("mk_pairs_dedup_bin_host: bad argument"); return MK_ERR_ARG; }
+    if (n > w->max_pairs) { mk_set_error("mk_pairs_dedup_bin_host: workspace holds %zu pairs, got %zu", w->max_pairs, n); return MK_ERR_CAPACITY; }
+    MK_CUDA(cudaSetDevice(w->device));
+    *n_kept = n; *nnz = 0;
+    if (n == 0) return MK_OK;
+    DevBuf &d_pairs = w->h_pairs, &d_b1 = w->h_b1, &d_b2 = w->h_b2, &d_c = w->h_c;
+    if (!d_pairs.p) MK_TRY(d_pairs.alloc(w->max_pairs * sizeof(mk_pair)));
+    MK_CUDA(cudaMemcpy(d_pairs.p, pairs, n * sizeof(mk_pair), cudaMemcpyHostToDevice));
+    size_t kept = n;
+    if (do_dedup) {
+        MK_TRY(mk_pairs_dedup_device(w, d_pairs.as<mk_pair>(), n, &kept, nullptr));
+        MK_CUDA(cudaMemcpy(pairs, d_pairs.p, kept * sizeof(mk_pair), cudaMemcpyDeviceToHost));
+    }
+    *n_kept = kept;
+    if (res && bin1 && bin2 && cnt) {
+        const size_t ocap = std::min(cap, kept);
+        if (!d_b1.p) { MK_TRY(d_b1.alloc(w->max_pairs * 4)); MK_TRY(d_b2.alloc(w->max_pairs * 4)); MK_TRY(d_c.alloc(w->max_pairs * 4)); }
+        size_t z = 0;
+        MK_TRY(mk_pairs_bin_device(w, d_pairs.as<mk_pair>(), kept, chrom_len, n_chrom, chrom_id_map, n_map, res,
+                                   d_b1.as<u32>(), d_b2.as<u32>(), d_c.as<u32>(), ocap, &z, nullptr));
+        MK_CUDA(cudaMemcpy(bin1, d_b1.p, z * 4, cudaMemcpyDeviceToHost));
+        MK_CUDA(cudaMemcpy(bin2, d_b2.p, z * 4, cudaMemcpyDeviceToHost));
+        MK_CUDA(cudaMemcpy(cnt, d_c.p, z * 4, cudaMemcpyDeviceToHost));
+        *nnz = z;
+    }
+    return MK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU: owner partition
+// owner(pair) = mix(chr1, chr2, pos1 / res) mod world: equal keys and equal (bin1,bin2) cells at resolution `res` land on
+// one rank, so duplicate removal and COO counts need no further exchange after the all-to-all.
+__host__ __device__ __forceinline__ u32 mk_owner_hash(u32 chr1, u32 chr2, u32 pbin) {
+    u32 h = (chr1 * 0x9E3779B1u) ^ (chr2 * 0x85EBCA77u) ^ (pbin * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k_owner_count(const mk_pair *p, u64 n, u32 world, u32 res, unsigned long long *counts) {
+    __shared__ u32 s_c[64];
+    if (threadIdx.x < 64) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const u64 n_round = (n + 31) & ~(u64)31;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (u64)gridDim.x * blockDim.x) {
+        u32 d = 0xFFFFu + lane;
+        if (i < n) { const uint4 r = ((const uint4 *)p)[i]; d = mk_owner_hash(r.z & 0xFFFFu, r.z >> 16, r.x / res) % world; }
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        if (i < n && lane == __ffs(peers) - 1) atomicAdd(&s_c[d], (u32)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < world && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_owner_scatter(const mk_pair *p, u64 n, u32 world, u32 res, unsigned long long *cursor /* start offsets, advanced */,
+                                                       mk_pair *out) {
+    const int lane = threadIdx.x & 31;
+    const u64 n_round = (n + 31) & ~(u64)31;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (u64)gridDim.x * blockDim.x) {
+        u32 d = 0xFFFFu + lane; uint4 r = make_uint4(0, 0, 0, 0);
+        if (i < n) { r = ((const uint4 *)p)[i]; d = mk_owner_hash(r.z & 0xFFFFu, r.z >> 16, r.x / res) % world; }
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (i < n && lane == leader) base = atomicAdd(&cursor[d], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (i < n) ((uint4 *)out)[base + __popc(peers & ((1u << lane) - 1u))] = r;
+    }
+}
+
+// Groups `n` pairs by owner rank into d_out (contiguous segments in rank order); counts[r] = pairs destined to rank r.
+extern "C" int mk_pairs_partition_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_t n, int world, uint32_t res, mk_pair *d_out,
+                                         uint64_t *counts, void *stream) {
+    if (!w || !counts || world < 1 || world > 64 || res == 0) { mk_set_error("mk_pairs_partition_device: bad argument"); return MK_ERR_ARG; }
+    MK_CUDA(cudaSetDevice(w->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *dc = w->counter.as<unsigned long long>();        // 64 bytes... use the descriptor buffer for 2 x 64 counters
+    dc = (unsigned long long *)w->desc.p;
+    MK_CUDA(cudaMemsetAsync(dc, 0, 128 * 8, s));
+    if (n) k_owner_count<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, (u32)world, res, dc);
+    unsigned long long h[64];
+    MK_CUDA(cudaMemcpyAsync(h, dc, (size_t)world * 8, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    unsigned long long off[64], run = 0;
+    for (int r = 0; r < world; ++r) { counts[r] = h[r]; off[r] = run; run += h[r]; }
+    MK_CUDA(cudaMemcpyAsync(dc + 64, off, (size_t)world * 8, cudaMemcpyHostToDevice, s));
+    if (n) k_owner_scatter<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, (u32)world, res, dc + 64, d_out);
+    w->launches += 2;
+    MK_CUDA(cudaStreamSynchronize(s));
+    return MK_OK;
+}
+
+extern "C" uint32_t mk_pairs_owner(uint32_t chr1, uint32_t chr2, uint32_t pos1, uint32_t res, uint32_t world) {
+    return mk_owner_hash(chr1, chr2, pos1 / res) % world;
 }

@@ -18,8 +18,12 @@ struct S2PSlot {                                   // one in-flight window of th
     PinBuf h_state;
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_free = nullptr;   // ev_free: last reader of d_in has run
     bool free_pending = false;
-    bool busy = false;
+    bool busy = false;                             // kernels enqueued, results not yet looked at
     size_t n_in = 0;
+    // finished window whose outputs still sit in d_text / d_pairs / d_sam (pulled straight from there, or spilled)
+    size_t text_len = 0, text_off = 0, pairs_n = 0, pairs_off = 0, sam_len = 0, sam_off = 0;
+    u64 win_id = 0;
+    bool has_output() const { return text_off < text_len || pairs_off < pairs_n || sam_off < sam_len; }
 };
 
 struct S2PCtx : mk_ctx {
@@ -32,7 +36,8 @@ struct S2PCtx : mk_ctx {
     int grid_scan = 0, grid_emit = 0, grid_gs = 0;
     u64 launches = 0;
     // host streaming state
-    std::vector<char> pend;                        // bytes received but not yet sent to the device
+    size_t stage_fill = 0;                         // bytes staged in the next window's pinned buffer
+    PinBuf h_nl;                                   // a pinned '\n' (terminates a last line that lacks one)
     u64 windows = 0;
     int prev_slot = -1;
     bool finished_input = false;
@@ -43,10 +48,20 @@ struct S2PCtx : mk_ctx {
     u64 sc_full_rule = 0; std::vector<u64> sc_tail; u64 sc_true = 0;
     bool use_device_path = false;
     WinState last_state;
+    // optional per-kernel timing (bench.py roofline): events around every kernel of every window
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    std::vector<std::pair<int, size_t>> ev_marks;          // (kernel id, index of its start event); end = next event
+    double k_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; u64 k_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        return ev_pool[ev_used++];
+    }
     S2PCtx() { kind = MK_CTX_S2P; memset(&last_state, 0, sizeof last_state); }
     ~S2PCtx() override {
         cudaSetDevice(cfg.device);
         for (auto &s : slot) { if (s.ev_h2d) cudaEventDestroy(s.ev_h2d); if (s.ev_done) cudaEventDestroy(s.ev_done); if (s.ev_free) cudaEventDestroy(s.ev_free); }
+        for (auto e : ev_pool) cudaEventDestroy(e);
         if (s_comp) cudaStreamDestroy(s_comp);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
@@ -86,15 +101,51 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
 
 // enqueue the kernels of one window on the compute stream
 static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
+    const bool t = c->timing;
+    auto mark = [&](int id) { if (t) { cudaEvent_t e = c->next_event(); cudaEventRecord(e, s); c->ev_marks.emplace_back(id, c->ev_used - 1); } };
     k_win_begin<<<(c->n_desc + 255) / 256, 256, 0, s>>>(p, c->n_desc);
+    mark(0);
     k_scan_lines<<<c->grid_scan, S2P_SCAN_THREADS, 0, s>>>(p);
+    mark(1);
     k_parse<<<c->grid_gs, 256, 0, s>>>(p);
+    mark(2);
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
+    mark(3);
     k_emit<<<c->grid_emit, EMIT_THREADS, 0, s>>>(p);
+    mark(4);
     c->launches += 5;
     if (p.write_sam) { k_copy_sam<<<c->grid_gs, 256, 0, s>>>(p); c->launches += 1; }
+    mark(5);
     k_win_end<<<1, 1, 0, s>>>(p);
     c->launches += 1;
+}
+
+// fold the recorded events into per-kernel totals (call after the stream is idle)
+static void timing_collect(S2PCtx *c) {
+    for (size_t i = 0; i + 1 < c->ev_marks.size(); ++i) {
+        int id = c->ev_marks[i].first;
+        if (id == 5) continue;                                  // 5 closes a window
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[c->ev_marks[i].second], c->ev_pool[c->ev_marks[i + 1].second]) == cudaSuccess) { c->k_ms[id] += ms; c->k_cnt[id] += 1; }
+    }
+    c->ev_marks.clear(); c->ev_used = 0;
+}
+
+extern "C" int mk_s2p_enable_timing(mk_ctx *x, int on) {
+    if (!x || x->kind != MK_CTX_S2P) { mk_set_error("not a sam2pairs context"); return MK_ERR_ARG; }
+    ((S2PCtx *)x)->timing = on != 0;
+    return MK_OK;
+}
+
+// ms[k], count[k] for k = 0 scan_lines, 1 parse, 2 group, 3 emit, 4 copy_sam (accumulated since creation)
+extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
+    if (!x || x->kind != MK_CTX_S2P || !ms || !count) { mk_set_error("mk_s2p_kernel_times: bad argument"); return MK_ERR_ARG; }
+    S2PCtx *c = (S2PCtx *)x;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    timing_collect(c);
+    for (int k = 0; k < 5; ++k) { ms[k] = c->k_ms[k + 1]; count[k] = c->k_cnt[k + 1]; }
+    return MK_OK;
 }
 
 __global__ void k_set_stream(WinState *st, u64 cursor, u64 total, u32 is_last) { st->cursor = cursor; st->total = total; st->is_last = is_last; }
@@ -217,8 +268,8 @@ static void sc_absorb(S2PCtx *c, const u64 *list, u32 n, u64 groups_done_after) 
     c->sc_tail.resize(w);
 }
 
-// wait for a streaming window, fetch its outputs into the host queues
-static int s2p_retire(S2PCtx *c, int b) {
+// wait for a streaming window; its outputs stay on the device until pulled (or spilled)
+static int s2p_complete(S2PCtx *c, int b) {
     S2PSlot &s = c->slot[b];
     if (!s.busy) return MK_OK;
     MK_CUDA(cudaEventSynchronize(s.ev_done));
@@ -226,30 +277,40 @@ static int s2p_retire(S2PCtx *c, int b) {
     WinState st = *s.h_state.as<WinState>();
     c->last_state = st;
     MK_TRY(s2p_err_check(st.err));
-    if (st.w_text && c->cfg.emit_text) {
-        std::vector<char> v(st.w_text);
-        MK_CUDA(cudaMemcpyAsync(v.data(), s.d_text.p, st.w_text, cudaMemcpyDeviceToHost, c->s_out));
-        MK_CUDA(cudaStreamSynchronize(c->s_out));
-        c->q_text.emplace_back(std::move(v));
-    }
-    if (st.w_emit && c->cfg.emit_packed) {
-        std::vector<mk_pair> v(st.w_emit);
-        MK_CUDA(cudaMemcpyAsync(v.data(), s.d_pairs.p, (size_t)st.w_emit * sizeof(mk_pair), cudaMemcpyDeviceToHost, c->s_out));
-        MK_CUDA(cudaStreamSynchronize(c->s_out));
-        c->q_pairs.emplace_back(std::move(v));
-    }
-    if (st.w_sam && c->cfg.write_sam) {
-        std::vector<char> v(st.w_sam);
-        MK_CUDA(cudaMemcpyAsync(v.data(), s.d_sam.p, st.w_sam, cudaMemcpyDeviceToHost, c->s_out));
-        MK_CUDA(cudaStreamSynchronize(c->s_out));
-        c->q_sam.emplace_back(std::move(v));
-    }
+    s.text_len = c->cfg.emit_text ? st.w_text : 0; s.pairs_n = c->cfg.emit_packed ? st.w_emit : 0; s.sam_len = c->cfg.write_sam ? st.w_sam : 0;
+    s.text_off = s.pairs_off = s.sam_off = 0;
     if (st.sc_count) {
         std::vector<u64> l(st.sc_count);
         MK_CUDA(cudaMemcpyAsync(l.data(), s.d_sc.p, (size_t)st.sc_count * 8, cudaMemcpyDeviceToHost, c->s_out));
         MK_CUDA(cudaStreamSynchronize(c->s_out));
         sc_absorb(c, l.data(), st.sc_count, st.groups_done);
     } else sc_absorb(c, nullptr, 0, st.groups_done);
+    return MK_OK;
+}
+
+// move a finished window's un-pulled outputs to host queues so that the slot can be reused
+static int s2p_spill(S2PCtx *c, int b) {
+    S2PSlot &s = c->slot[b];
+    MK_TRY(s2p_complete(c, b));
+    if (s.text_off < s.text_len) {
+        std::vector<char> v(s.text_len - s.text_off);
+        MK_CUDA(cudaMemcpyAsync(v.data(), s.d_text.as<char>() + s.text_off, v.size(), cudaMemcpyDeviceToHost, c->s_out));
+        MK_CUDA(cudaStreamSynchronize(c->s_out));
+        c->q_text.emplace_back(std::move(v));
+    }
+    if (s.pairs_off < s.pairs_n) {
+        std::vector<mk_pair> v(s.pairs_n - s.pairs_off);
+        MK_CUDA(cudaMemcpyAsync(v.data(), s.d_pairs.as<mk_pair>() + s.pairs_off, v.size() * sizeof(mk_pair), cudaMemcpyDeviceToHost, c->s_out));
+        MK_CUDA(cudaStreamSynchronize(c->s_out));
+        c->q_pairs.emplace_back(std::move(v));
+    }
+    if (s.sam_off < s.sam_len) {
+        std::vector<char> v(s.sam_len - s.sam_off);
+        MK_CUDA(cudaMemcpyAsync(v.data(), s.d_sam.as<char>() + s.sam_off, v.size(), cudaMemcpyDeviceToHost, c->s_out));
+        MK_CUDA(cudaStreamSynchronize(c->s_out));
+        c->q_sam.emplace_back(std::move(v));
+    }
+    s.text_off = s.text_len; s.pairs_off = s.pairs_n; s.sam_off = s.sam_len;
     return MK_OK;
 }
 
@@ -266,20 +327,32 @@ static int s2p_slot_init(S2PCtx *c, S2PSlot &s) {
     MK_CUDA(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     MK_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     MK_CUDA(cudaEventCreateWithFlags(&s.ev_free, cudaEventDisableTiming));
+    if (!c->h_nl.p) { MK_TRY(c->h_nl.alloc(16)); c->h_nl.as<char>()[0] = '\n'; }
     return MK_OK;
 }
 
-// send one chunk (complete lines) to the device and enqueue its window
-static int s2p_submit(S2PCtx *c, const char *data, size_t n, bool final_chunk) {
+// The slot for the next window, ready to be filled: its previous window (k-2) is finished and its outputs are out.
+static int s2p_next_slot(S2PCtx *c, S2PSlot **out) {
     const int b = (int)(c->windows & 1);
     S2PSlot &s = c->slot[b];
     MK_TRY(s2p_slot_init(c, s));
-    MK_TRY(s2p_retire(c, b));                        // slot b last held window k-2
-    memcpy(s.h_in.p, data, n);
+    if (s.busy || s.has_output()) MK_TRY(s2p_spill(c, b));
+    *out = &s;
+    return MK_OK;
+}
+
+// Enqueue one window.  Its bytes are the first n_stage bytes of the slot's pinned buffer followed by n_direct bytes
+// DMA'd straight from `direct` (caller memory that is already pinned), plus a final '\n' when add_nl.
+static int s2p_submit(S2PCtx *c, size_t n_stage, const char *direct, size_t n_direct, bool add_nl, bool final_chunk) {
+    const int b = (int)(c->windows & 1);
+    S2PSlot &s = c->slot[b];
+    const size_t n = n_stage + n_direct + (add_nl ? 1 : 0);
     s.n_in = n;
     char *dst = s.d_in.as<char>() + S2P_CARRY;
     if (s.free_pending) { MK_CUDA(cudaStreamWaitEvent(c->s_in, s.ev_free, 0)); s.free_pending = false; }
-    MK_CUDA(cudaMemcpyAsync(dst, s.h_in.p, n, cudaMemcpyHostToDevice, c->s_in));
+    if (n_stage) MK_CUDA(cudaMemcpyAsync(dst, s.h_in.p, n_stage, cudaMemcpyHostToDevice, c->s_in));
+    if (n_direct) MK_CUDA(cudaMemcpyAsync(dst + n_stage, direct, n_direct, cudaMemcpyHostToDevice, c->s_in));
+    if (add_nl) MK_CUDA(cudaMemcpyAsync(dst + n_stage + n_direct, c->h_nl.p, 1, cudaMemcpyHostToDevice, c->s_in));
     MK_CUDA(cudaEventRecord(s.ev_h2d, c->s_in));
     MK_CUDA(cudaStreamWaitEvent(c->s_comp, s.ev_h2d, 0));
     const int pb = c->prev_slot;
@@ -295,36 +368,72 @@ static int s2p_submit(S2PCtx *c, const char *data, size_t n, bool final_chunk) {
     launch_window(c, p, c->s_comp);
     MK_CUDA(cudaMemcpyAsync(s.h_state.p, c->d_state.p, sizeof(WinState), cudaMemcpyDeviceToHost, c->s_comp));
     MK_CUDA(cudaEventRecord(s.ev_done, c->s_comp));
-    s.busy = true;
+    s.busy = true; s.win_id = c->windows;
     c->prev_slot = b;
     ++c->windows;
-    if (pb >= 0 && pb != b) MK_TRY(s2p_retire(c, pb));   // fetch window k-1's output while window k runs
     return MK_OK;
+}
+
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 extern "C" int mk_s2p_push(mk_ctx *x, const char *bytes, size_t n, int is_last) {
     S2PCtx *c; MK_TRY(s2p_check(x, &c));
     if (c->finished_input) { mk_set_error("mk_s2p_push after the last chunk"); return MK_ERR_STATE; }
     if (c->use_device_path) { mk_set_error("mk_s2p_push on a context used with mk_s2p_run_device"); return MK_ERR_STATE; }
-    if (n) c->pend.insert(c->pend.end(), bytes, bytes + n);
-    if (is_last && !c->pend.empty() && c->pend.back() != '\n') c->pend.push_back('\n');   // getline accepts a last line without '\n'
+    const bool pinned = n >= (1u << 20) && host_ptr_is_pinned(bytes);
+    cudaEvent_t last_direct = nullptr;
     size_t off = 0;
-    while (true) {
-        const size_t avail = c->pend.size() - off;
-        if (avail == 0 || (avail < c->W && !is_last)) break;
-        size_t take = std::min(avail, c->W);
-        const bool final_chunk = is_last && take == avail;
-        const char *base = c->pend.data() + off;
-        if (!final_chunk) {                          // cut at the last complete line
-            const void *nl = memrchr(base, '\n', take);
-            if (!nl) { mk_set_error("sam2pairs: a line longer than the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
-            take = (size_t)((const char *)nl - base) + 1;
+    while (off < n) {
+        S2PSlot *sp; MK_TRY(s2p_next_slot(c, &sp));
+        S2PSlot &s = *sp;
+        const size_t room = c->W - c->stage_fill, left = n - off;
+        if (pinned && left >= room / 2) {
+            // zero-copy: DMA a whole window straight from the caller's pinned memory, cut at its last complete line
+            size_t take = std::min(room, left);
+            const bool whole = is_last && take == left;
+            bool add_nl = false;
+            if (!whole) {
+                const void *nl = memrchr(bytes + off, '\n', take);
+                if (nl) take = (size_t)((const char *)nl - (bytes + off)) + 1; else take = 0;
+            } else add_nl = bytes[off + take - 1] != '\n';
+            if (take) {
+                MK_TRY(s2p_submit(c, c->stage_fill, bytes + off, take, add_nl, whole));
+                last_direct = s.ev_h2d;
+                c->stage_fill = 0; off += take;
+                if (whole) c->finished_input = true;
+                continue;
+            }
         }
-        MK_TRY(s2p_submit(c, base, take, final_chunk));
-        off += take;
+        // staged: gather bytes in the slot's pinned buffer until a window is full
+        const size_t take = std::min(room, left);
+        memcpy(s.h_in.as<char>() + c->stage_fill, bytes + off, take);
+        c->stage_fill += take; off += take;
+        if (c->stage_fill == c->W) {
+            const char *base = s.h_in.as<char>();
+            const void *nl = memrchr(base, '\n', c->stage_fill);
+            if (!nl) { mk_set_error("sam2pairs: a line longer than the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
+            const size_t cut = (size_t)((const char *)nl - base) + 1, rem = c->stage_fill - cut;
+            MK_TRY(s2p_submit(c, cut, nullptr, 0, false, false));
+            S2PSlot *np; MK_TRY(s2p_next_slot(c, &np));              // the partial last line opens the next window
+            memcpy(np->h_in.p, base + cut, rem);
+            c->stage_fill = rem;
+        }
     }
-    if (off) c->pend.erase(c->pend.begin(), c->pend.begin() + (long)off);
-    if (is_last) c->finished_input = true;
+    if (is_last && !c->finished_input) {
+        if (c->stage_fill) {
+            S2PSlot *sp; MK_TRY(s2p_next_slot(c, &sp));
+            char *base = sp->h_in.as<char>();
+            if (base[c->stage_fill - 1] != '\n') base[c->stage_fill++] = '\n';   // getline accepts a last line without '\n'
+            MK_TRY(s2p_submit(c, c->stage_fill, nullptr, 0, false, true));
+            c->stage_fill = 0;
+        }
+        c->finished_input = true;
+    }
+    if (last_direct) MK_CUDA(cudaEventSynchronize(last_direct));       // the caller may reuse its buffer when we return
     return MK_OK;
 }
 
@@ -341,10 +450,45 @@ static size_t drain(std::deque<std::vector<T>> &q, size_t &qoff, T *out, size_t 
     return n;
 }
 
+// slots in window order; windows still running are waited for only once the input is complete
+static int s2p_ready_slots(S2PCtx *c, int order[2], int *n) {
+    *n = 0;
+    if (c->windows == 0) return MK_OK;
+    int cand[2] = {(int)(c->windows & 1), (int)((c->windows + 1) & 1)};   // older (k-2 / k-1 ...) first
+    for (int i = 0; i < 2; ++i) {
+        S2PSlot &s = c->slot[cand[i]];
+        if (!s.d_in.p) continue;
+        if (s.busy) {
+            const bool newest = s.win_id + 1 == c->windows;
+            if (newest && !c->finished_input && cudaEventQuery(s.ev_done) != cudaSuccess) continue;   // let it run
+            MK_TRY(s2p_complete(c, cand[i]));
+        }
+        order[(*n)++] = cand[i];
+    }
+    if (*n == 2 && c->slot[order[0]].win_id > c->slot[order[1]].win_id) std::swap(order[0], order[1]);
+    return MK_OK;
+}
+
 extern "C" int mk_s2p_pull(mk_ctx *x, char *pairs_out, size_t cap, size_t *n_out, char *sam_out, size_t cap2, size_t *n_out2) {
     S2PCtx *c; MK_TRY(s2p_check(x, &c));
-    if (c->finished_input) { MK_TRY(s2p_retire(c, 0)); MK_TRY(s2p_retire(c, 1)); }
     size_t a = drain(c->q_text, c->q_text_off, pairs_out, cap), b = drain(c->q_sam, c->q_sam_off, sam_out, cap2);
+    int order[2], ns = 0;
+    MK_TRY(s2p_ready_slots(c, order, &ns));
+    bool text_blocked = !c->q_text.empty(), sam_blocked = !c->q_sam.empty();
+    for (int i = 0; i < ns; ++i) {
+        S2PSlot &s = c->slot[order[i]];
+        if (pairs_out && !text_blocked && s.text_off < s.text_len) {
+            size_t m = std::min(cap - a, s.text_len - s.text_off);
+            if (m) { MK_CUDA(cudaMemcpyAsync(pairs_out + a, s.d_text.as<char>() + s.text_off, m, cudaMemcpyDeviceToHost, c->s_out)); a += m; s.text_off += m; }
+        }
+        if (s.text_off < s.text_len) text_blocked = true;            // keep window order
+        if (sam_out && !sam_blocked && s.sam_off < s.sam_len) {
+            size_t m = std::min(cap2 - b, s.sam_len - s.sam_off);
+            if (m) { MK_CUDA(cudaMemcpyAsync(sam_out + b, s.d_sam.as<char>() + s.sam_off, m, cudaMemcpyDeviceToHost, c->s_out)); b += m; s.sam_off += m; }
+        }
+        if (s.sam_off < s.sam_len) sam_blocked = true;
+    }
+    MK_CUDA(cudaStreamSynchronize(c->s_out));
     if (n_out) *n_out = a;
     if (n_out2) *n_out2 = b;
     return MK_OK;
@@ -352,8 +496,19 @@ extern "C" int mk_s2p_pull(mk_ctx *x, char *pairs_out, size_t cap, size_t *n_out
 
 extern "C" int mk_s2p_pull_packed(mk_ctx *x, mk_pair *recs, size_t cap, size_t *n) {
     S2PCtx *c; MK_TRY(s2p_check(x, &c));
-    if (c->finished_input) { MK_TRY(s2p_retire(c, 0)); MK_TRY(s2p_retire(c, 1)); }
     size_t a = drain(c->q_pairs, c->q_pairs_off, recs, cap);
+    int order[2], ns = 0;
+    MK_TRY(s2p_ready_slots(c, order, &ns));
+    bool blocked = !c->q_pairs.empty();
+    for (int i = 0; i < ns && recs && !blocked; ++i) {
+        S2PSlot &s = c->slot[order[i]];
+        if (s.pairs_off < s.pairs_n) {
+            size_t m = std::min(cap - a, s.pairs_n - s.pairs_off);
+            if (m) { MK_CUDA(cudaMemcpyAsync(recs + a, s.d_pairs.as<mk_pair>() + s.pairs_off, m * sizeof(mk_pair), cudaMemcpyDeviceToHost, c->s_out)); a += m; s.pairs_off += m; }
+        }
+        if (s.pairs_off < s.pairs_n) blocked = true;
+    }
+    MK_CUDA(cudaStreamSynchronize(c->s_out));
     if (n) *n = a;
     return MK_OK;
 }
@@ -389,7 +544,8 @@ extern "C" int mk_s2p_finish(mk_ctx *x, mk_s2p_stats *out) {
     if (!out) { mk_set_error("mk_s2p_finish: null stats"); return MK_ERR_ARG; }
     if (!c->use_device_path) {
         if (!c->finished_input) MK_TRY(mk_s2p_push(x, nullptr, 0, 1));
-        MK_TRY(s2p_retire(c, 0)); MK_TRY(s2p_retire(c, 1));
+        const int o0 = (int)(c->windows & 1);
+        MK_TRY(s2p_complete(c, o0)); MK_TRY(s2p_complete(c, o0 ^ 1));
     }
     MK_CUDA(cudaStreamSynchronize(c->s_comp));
     WinState st;
@@ -402,11 +558,29 @@ extern "C" int mk_s2p_finish_sharded(mk_ctx *x, uint64_t group_base, uint64_t to
     if (!out) { mk_set_error("mk_s2p_finish_sharded: null stats"); return MK_ERR_ARG; }
     if (!c->use_device_path) {
         if (!c->finished_input) MK_TRY(mk_s2p_push(x, nullptr, 0, 1));
-        MK_TRY(s2p_retire(c, 0)); MK_TRY(s2p_retire(c, 1));
+        const int o0 = (int)(c->windows & 1);
+        MK_TRY(s2p_complete(c, o0)); MK_TRY(s2p_complete(c, o0 ^ 1));
     }
     MK_CUDA(cudaStreamSynchronize(c->s_comp));
     if (!c->cfg.sharded && group_base != 0) { mk_set_error("mk_s2p_finish_sharded: create the context with cfg.sharded = 1"); return MK_ERR_STATE; }
     return s2p_fill_stats(c, group_base, total_groups, out);
+}
+
+// Forget the stream (counters, carried group, pending output) but keep every allocation and the chromosome table:
+// the context can then process another input from the start.
+extern "C" int mk_s2p_reset(mk_ctx *x) {
+    S2PCtx *c; MK_TRY(s2p_check(x, &c));
+    MK_CUDA(cudaDeviceSynchronize());
+    WinState st;
+    MK_CUDA(cudaMemcpy(&st, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost));
+    u32 n_chrom = st.n_chrom;
+    memset(&st, 0, sizeof st); st.n_chrom = n_chrom;
+    MK_CUDA(cudaMemcpy(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice));
+    for (auto &s : c->slot) { s.busy = false; s.free_pending = false; s.text_len = s.text_off = s.pairs_n = s.pairs_off = s.sam_len = s.sam_off = 0; }
+    c->stage_fill = 0; c->windows = 0; c->prev_slot = -1; c->finished_input = false; c->use_device_path = false;
+    c->q_text.clear(); c->q_sam.clear(); c->q_pairs.clear(); c->q_text_off = c->q_sam_off = c->q_pairs_off = 0;
+    c->sc_full_rule = 0; c->sc_tail.clear(); c->sc_true = 0;
+    return MK_OK;
 }
 
 extern "C" int mk_s2p_chrom_count(mk_ctx *x) {
@@ -460,6 +634,7 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
         for (size_t w = 0; w < nwin; ++w) launch_window(c, p, s);
         MK_CUDA(cudaMemcpyAsync(&st, dst, sizeof st, cudaMemcpyDeviceToHost, s));
         MK_CUDA(cudaStreamSynchronize(s));
+        if (c->timing) timing_collect(c);
         MK_TRY(s2p_err_check(st.err));
         if (st.sc_count) {
             std::vector<u64> l(st.sc_count);
