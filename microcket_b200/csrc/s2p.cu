@@ -144,7 +144,7 @@ extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     timing_collect(c);
-    for (int k = 0; k < 5; ++k) { ms[k] = c->k_ms[k + 1]; count[k] = c->k_cnt[k + 1]; }
+    for (int k = 0; k < 5; ++k) { ms[k] = c->k_ms[k]; count[k] = c->k_cnt[k]; }
     return MK_OK;
 }
 

@@ -1,0 +1,100 @@
+"""The drop-in executables (argv / stdio / files / exit codes) against the reference's own programs (oracle/_ref)
+or, where those are absent, the oracle."""
+import os
+import subprocess
+
+import pytest
+
+import microcket_b200 as mk
+from oracle_lib import sort_lines, sort_pairs
+from refrun import ref_krmdup, ref_sam2pairs
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(os.path.dirname(mk.LIB_PATH), "bin")
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, **kw)
+
+
+@pytest.mark.parametrize("mode", ["unc", "flash"])
+def test_sam2pairs_cli_matches_reference(tmp_path, oracle, ref_bin, mode):
+    sam = mk.synth_host(51, mode, "hg38", 0, 30000)
+    src = tmp_path / "in.sam"; src.write_bytes(sam)
+    r = run([os.path.join(BIN, "sam2pairs"), str(src), mode, str(tmp_path / "g"), "8", "0.5", "10", "yes"])
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.decode() == "INFO: min_mapped_ratio is set to 0.5.\nINFO: min_mapQ is set to 10.\n"
+    if ref_bin:
+        rp, rlog, rsam = ref_sam2pairs(ref_bin, sam, mode, threads=8)
+    else:
+        op, osam, ost = oracle.sam2pairs(sam, mode, threads=8)
+        rp, rlog, rsam = sort_pairs(op), ost.log_text(), sort_lines(osam)
+    assert sort_pairs(r.stdout) == rp
+    assert (tmp_path / f"g.{mode}2pairs.log").read_bytes() == rlog
+    assert sort_lines((tmp_path / f"g.{mode}.sam").read_bytes()) == rsam
+
+
+def test_sam2pairs_cli_stdin_and_no_sam(tmp_path, oracle):
+    sam = mk.synth_host(52, "unc", "mm10", 0, 5000)
+    r = run([os.path.join(BIN, "sam2pairs"), "/dev/stdin", "unc", str(tmp_path / "g"), "4", "0.8", "20", "no"], input=sam)
+    assert r.returncode == 0
+    assert r.stderr.decode().endswith("WARN: sam output is skipped.\n")
+    op, _, ost = oracle.sam2pairs(sam, "unc", ratio=0.8, min_mapq=20, threads=4, write_sam=False)
+    assert r.stdout == op and (tmp_path / "g.unc2pairs.log").read_bytes() == ost.log_text()
+    assert not (tmp_path / "g.unc.sam").exists()
+
+
+def test_sam2pairs_cli_exit_codes(tmp_path):
+    b = os.path.join(BIN, "sam2pairs")
+    assert run([b]).returncode == 2
+    assert run([b, "x", "unc", "p", "1"]).returncode == 5
+    assert run([b, "x", "bad", "p"]).returncode == 6
+    assert run([b, str(tmp_path / "missing.sam"), "unc", str(tmp_path / "p")]).returncode == 10
+
+
+def test_krmdup_cli_appends_like_the_reference(tmp_path, oracle, ref_bin):
+    lanes = [mk.synth_host(53, "fastq", "hg38", k * 40000, 40000) for k in range(2)]
+    pre = str(tmp_path / "o")
+    for k, fq in enumerate(lanes):                                   # `microcket -b`: one process per lane, same prefix
+        src = tmp_path / f"l{k}.fq"; src.write_bytes(fq)
+        assert run([os.path.join(BIN, "krmdup"), "-i", str(src), "-o", pre]).returncode == 0
+    if ref_bin:
+        r1, r2, log = ref_krmdup(ref_bin, lanes)
+    else:
+        outs = [oracle.krmdup(l) for l in lanes]
+        r1, r2, log = b"".join(o[0] for o in outs), b"".join(o[1] for o in outs), b"".join(o[2].log_text() for o in outs)
+    assert open(pre + ".read1.fq", "rb").read() == r1
+    assert open(pre + ".read2.fq", "rb").read() == r2
+    assert open(pre + ".log", "rb").read() == log
+
+
+def test_krmdup_pipe_cli(tmp_path, oracle):
+    fq = mk.synth_host(54, "fastq", "hg38", 0, 70000)
+    r = run([os.path.join(BIN, "krmdup.pipe"), "-i", "-", "-o", str(tmp_path / "p")], input=fq)
+    assert r.returncode == 0
+    o1, o2, ost = oracle.krmdup(fq)
+    a, b = o1.split(b"\n")[:-1], o2.split(b"\n")[:-1]
+    exp = b"".join(b"\n".join(a[i:i + 4]) + b"\n" + b"\n".join(b[i:i + 4]) + b"\n" for i in range(0, len(a), 4))
+    assert r.stdout == exp                                            # interleaved records, deterministic bucket order
+    assert open(str(tmp_path / "p.log"), "rb").read() == ost.log_text()
+    assert run([os.path.join(BIN, "krmdup"), "-i", "x", "-o", "y", "-s", "20", "-S", "20"]).returncode == 1
+    assert run([os.path.join(BIN, "krmdup")]).returncode == 2
+
+
+def test_pairs2bins_cli(tmp_path, oracle):
+    sam = mk.synth_host(55, "unc", "hg38", 0, 20000)
+    op, _, _ = oracle.sam2pairs(sam, "unc", threads=8, write_sam=False)
+    op = op + op[:len(op) // 3].rsplit(b"\n", 1)[0] + b"\n"           # add duplicates
+    pf = tmp_path / "x.pairs"; pf.write_bytes(b"## pairs format v1.0\n#columns: readID chr1 position1 chr2 position2 strand1 strand2\n" + op)
+    names = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr2", "chr20", "chr21",
+             "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
+    from test_gpu_pairs import HG38_LEN
+    info = tmp_path / "hg38.info"; info.write_text("".join(f"{n}\t{l}\n" for n, l in zip(names, HG38_LEN)))
+    r = run([os.path.join(BIN, "pairs2bins"), "-d", "-r", "1000000,5000", str(pf), str(tmp_path / "out"), str(info)])
+    assert r.returncode == 0, r.stderr
+    pairs, n = oracle.pairs_parse(op, names)
+    keep, kept = oracle.coord_dedup(pairs, n)
+    for res in (1000000, 5000):
+        b1, b2, ct = oracle.bin_coo(pairs, n, keep, HG38_LEN, res)
+        exp = "".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1, b2, ct))
+        assert (tmp_path / f"out.{res}.coo").read_text() == exp
