@@ -216,8 +216,8 @@ def main():
         if world > 1:
             from microcket_b200 import shard
             n, src = shard.exchange_pairs(mk, torch, dist, ws, pairs, n, recv, cap_pairs, RES, stream)
-        kept = ws.dedup(src.data_ptr(), n, stream=stream)
-        nnz = ws.bin(src.data_ptr(), kept, HG38_LEN, RES, b1.data_ptr(), b2.data_ptr(), cnt.data_ptr(), cap_pairs, stream=stream)
+        # duplicate removal and 5 kb binning share one sort (mk_pairs_dedup_bin_device)
+        kept, nnz = ws.dedup_bin(src.data_ptr(), n, HG38_LEN, RES, b1.data_ptr(), b2.data_ptr(), cnt.data_ptr(), cap_pairs, stream=stream)
         return io.n_pairs, kept, nnz
 
     def barrier():

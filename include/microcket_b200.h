@@ -157,6 +157,13 @@ int  mk_pairs_bin_device(mk_pairs_ws *, const mk_pair *d_pairs, size_t n,
                          const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map,
                          uint32_t res, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
                          size_t *nnz, void *stream);
+/* Both steps with ONE sort: pairs are packed as (bin1, bin2, lane, pos1 % res, pos2 % res, strands) integers, so equal
+ * pairs are adjacent (dedup) and every (bin1,bin2) cell is contiguous (binning).  d_pairs is replaced by the kept pairs
+ * in that order; the COO counts are those of the kept pairs.  max_lane = largest mk_pair.lane present (0 if unused). */
+int  mk_pairs_dedup_bin_device(mk_pairs_ws *, mk_pair *d_pairs, size_t n,
+                               const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map,
+                               uint32_t res, uint16_t max_lane, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                               size_t *n_kept, size_t *nnz, void *stream);
 /* Multi-GPU: group pairs by owner rank = mix(chr1, chr2, pos1 / res) mod world into d_out (segments in rank order;
  * counts[r] pairs for rank r).  The caller moves the segments with an all-to-all (NCCL via torch.distributed in
  * bench.py); afterwards equal keys and equal (bin1,bin2) cells at `res` are on one rank. */

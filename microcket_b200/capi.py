@@ -110,6 +110,7 @@ class Lib:
                            ("mk_pairs_bin_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, vp, vp, vp, sz, P(sz), vp]),
                            ("mk_pairs_dedup_bin_host", [vp, vp, sz, i, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, vp, vp, vp, sz, P(sz), P(sz)]),
                            ("mk_s2p_enable_timing", [vp, i]), ("mk_s2p_kernel_times", [vp, P(C.c_double), P(u64)]),
+                           ("mk_pairs_dedup_bin_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, C.c_uint16, vp, vp, vp, sz, P(sz), P(sz), vp]),
                            ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
@@ -370,6 +371,18 @@ class PairsWorkspace:
 
     def launches(self):
         return self.lib.L.mk_pairs_launch_count(self.h)
+
+    def dedup_bin(self, d_pairs, n, chrom_len, res, d_bin1, d_bin2, d_cnt, cap, chrom_id_map=None, max_lane=0, stream=0):
+        """One-sort duplicate removal + binning → (n_kept, nnz)"""
+        cl = (C.c_uint32 * len(chrom_len))(*chrom_len)
+        if chrom_id_map is not None:
+            mp = (C.c_uint16 * len(chrom_id_map))(*chrom_id_map); nm = len(chrom_id_map)
+        else:
+            mp, nm = None, 0
+        kept, nnz = C.c_size_t(), C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_dedup_bin_device(self.h, d_pairs, n, cl, len(chrom_len), mp, nm, res, max_lane,
+                                                            d_bin1, d_bin2, d_cnt, cap, C.byref(kept), C.byref(nnz), stream))
+        return kept.value, nnz.value
 
     def partition(self, d_pairs, n, world, res, d_out, stream=0):
         counts = (C.c_uint64 * world)()

@@ -26,6 +26,7 @@ struct FqState {
     u64 out1, out2;
     unsigned long long uniq, dup, discard;
     u32 allones_seen[2], inserted[2];
+    u32 ticket, pad2;
 };
 
 struct FqParams {
@@ -43,11 +44,11 @@ struct FqParams {
 __global__ void k_fq_begin(FqParams p, u32 n_desc, u64 total, u32 is_last) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_desc) p.desc[i] = 0;
-    if (i == 0) { p.st->total = total; p.st->n_lines = 0; p.st->is_last = is_last; p.st->n_pairs = 0; p.st->consumed = 0; p.st->out1 = p.st->out2 = 0; }
+    if (i == 0) { p.st->total = total; p.st->n_lines = 0; p.st->is_last = is_last; p.st->n_pairs = 0; p.st->consumed = 0; p.st->out1 = p.st->out2 = 0; p.st->ticket = 0; }
 }
 
 __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_fq_scan(FqParams p) {
-    scan_lines_body(p.buf, 0, p.st->total, 0, p.nl_pos, p.cap_lines, p.desc, &p.st->n_lines, &p.st->err, FQ_ERR_LINES);
+    scan_lines_body(p.buf, 0, p.st->total, 0, p.nl_pos, p.cap_lines, p.desc, &p.st->n_lines, &p.st->err, FQ_ERR_LINES, &p.st->ticket);
 }
 
 __device__ __forceinline__ u32 fq_line_start(const u32 *nl, u32 line) { return line ? nl[line - 1] + 1 : 0; }

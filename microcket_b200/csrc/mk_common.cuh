@@ -116,6 +116,10 @@ __device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) {
 }
 // Called by ONE warp of the CTA that owns `tile`; returns the exclusive prefix of the tile
 // (sum of aggregates of tiles first_tile..tile-1) and publishes this tile's inclusive prefix.
+// Every round looks at LB_WIDE * 32 predecessors with all loads in flight at once: with a persistent grid the
+// nearest published inclusive prefix is typically one wave (several hundred tiles) back, and a narrow window
+// would turn that distance into a chain of dependent L2 round trips.
+#define LB_WIDE 1
 __device__ __forceinline__ u64 lookback_exclusive(u64 *desc, int tile, int first_tile, u64 aggregate, int lane) {
     if (tile == first_tile) {
         if (lane == 0) st_volatile_u64(&desc[tile], LB_INC | aggregate);
@@ -123,31 +127,84 @@ __device__ __forceinline__ u64 lookback_exclusive(u64 *desc, int tile, int first
     }
     if (lane == 0) st_volatile_u64(&desc[tile], LB_AGG | aggregate);
     u64 excl = 0;
-    int t = tile - 1;
+    int t = tile - 1;                                    // nearest predecessor not yet accounted for
     while (true) {
-        // lanes look at tiles t, t-1, ... t-31
-        int mine = t - lane;
-        u64 d = mine >= first_tile ? ld_volatile_u64(&desc[mine]) : LB_INC;   // virtual tile before the first: prefix 0
-        u32 st = (u32)(d >> 62);
-        if (__any_sync(0xffffffffu, st == 0)) continue;        // a predecessor has not published yet: poll again
-        u32 inc_mask = __ballot_sync(0xffffffffu, st == 2);
-        u64 v = LB_VAL(d);
-        if (inc_mask) {
-            int first_inc = __ffs(inc_mask) - 1;               // nearest tile with an inclusive prefix
-            if (lane > first_inc) v = 0;
+        u64 d[LB_WIDE];
+#pragma unroll
+        for (int j = 0; j < LB_WIDE; ++j) {
+            const int mine = t - lane - 32 * j;
+            d[j] = mine >= first_tile ? ld_volatile_u64(&desc[mine]) : LB_INC;   // virtual tiles before the first: prefix 0
+        }
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < LB_WIDE; ++j) {
+            const u32 st = (u32)(d[j] >> 62);
+            if (__any_sync(0xffffffffu, st == 0)) break;                         // not published yet: poll again from here
+            const u32 inc_mask = __ballot_sync(0xffffffffu, st == 2);
+            u64 v = LB_VAL(d[j]);
+            if (inc_mask) {
+                const int first_inc = __ffs(inc_mask) - 1;                       // nearest tile with an inclusive prefix
+                if (lane > first_inc) v = 0;
+            }
 #pragma unroll
             for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
             excl += v;
-            break;
+            t -= 32;
+            if (inc_mask) { done = true; break; }
         }
+        if (done) break;
+    }
+    if (lane == 0) st_volatile_u64(&desc[tile], LB_INC | (excl + aggregate));
+    return excl;
+}
+
+// Two-step form for kernels that have other work to do between publishing their aggregate and needing the prefix.
+__device__ __forceinline__ void lookback_publish(u64 *desc, int tile, int first_tile, u64 aggregate) {
+    st_volatile_u64(&desc[tile], (tile == first_tile ? LB_INC : LB_AGG) | aggregate);
+}
+__device__ __forceinline__ u64 lookback_resolve(u64 *desc, int tile, int first_tile, u64 aggregate, int lane) {
+    if (tile == first_tile) return 0;
+    u64 excl = 0;
+    int t = tile - 1;
+    while (true) {
+        const int mine = t - lane;
+        const u64 d = mine >= first_tile ? ld_volatile_u64(&desc[mine]) : LB_INC;
+        const u32 st = (u32)(d >> 62);
+        if (__any_sync(0xffffffffu, st == 0)) continue;
+        const u32 inc_mask = __ballot_sync(0xffffffffu, st == 2);
+        u64 v = LB_VAL(d);
+        if (inc_mask) { const int first_inc = __ffs(inc_mask) - 1; if (lane > first_inc) v = 0; }
 #pragma unroll
         for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
         excl += v;
+        if (inc_mask) break;
         t -= 32;
     }
     if (lane == 0) st_volatile_u64(&desc[tile], LB_INC | (excl + aggregate));
     return excl;
 }
+
+// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (sm_90+; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) {} }
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- forward byte reader over global memory using aligned 8-byte loads
 struct ByteReader {
@@ -163,6 +220,28 @@ struct ByteReader {
     }
     __device__ __forceinline__ int next() {
         if (left == 0) { cur = __ldg(base + (pos >> 3)); left = 8; }
+        int c = (int)(cur & 0xFF);
+        cur >>= 8; --left; ++pos;
+        return c;
+    }
+};
+
+// same interface, but bytes of [tlo, thi) (absolute offsets, 8-byte aligned bounds) come from a shared-memory copy
+struct TileReader {
+    const u64 *base; const char *sm; u64 tlo, thi;
+    u64 cur, pos; int left;
+    __device__ __forceinline__ u64 fetch(u64 a) const {       // a is 8-byte aligned
+        return (a >= tlo && a + 8 <= thi) ? *(const u64 *)(sm + (a - tlo)) : __ldg(base + (a >> 3));
+    }
+    __device__ __forceinline__ void setup(const char *buf, const char *smem_tile, u64 lo, u64 hi) { base = (const u64 *)buf; sm = smem_tile; tlo = lo; thi = hi; }
+    __device__ __forceinline__ void init(const char *, u64 off) {
+        pos = off;
+        int sh = (int)(off & 7);
+        cur = fetch(off & ~(u64)7) >> (sh * 8);
+        left = 8 - sh;
+    }
+    __device__ __forceinline__ int next() {
+        if (left == 0) { cur = fetch(pos); left = 8; }
         int c = (int)(cur & 0xFF);
         cur >>= 8; --left; ++pos;
         return c;

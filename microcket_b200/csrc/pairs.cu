@@ -167,7 +167,7 @@ extern "C" int mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **ou
     if (rc == MK_OK) rc = w->heads_pos.alloc(max_pairs * 4);
     if (rc == MK_OK) rc = w->desc.alloc((max_pairs / (UQ_T * UQ_ITEMS) + 4) * 8 + 2048);
     if (rc == MK_OK) rc = w->counter.alloc(64);
-    if (rc == MK_OK) rc = w->chr_off.alloc(65536 * 4);
+    if (rc == MK_OK) rc = w->chr_off.alloc(65536 * 4 + 16384 * 8);
     if (rc != MK_OK) { delete w; return rc; }
     *out = w;
     return MK_OK;
@@ -382,4 +382,196 @@ extern "C" int mk_pairs_partition_device(mk_pairs_ws *w, const mk_pair *d_pairs,
 
 extern "C" uint32_t mk_pairs_owner(uint32_t chr1, uint32_t chr2, uint32_t pos1, uint32_t res, uint32_t world) {
     return mk_owner_hash(chr1, chr2, pos1 / res) % world;
+}
+
+// ------------------------------------------------------------------------------------------------ fused dedup + binning
+// One sort serves both steps.  Every pair becomes a tightly packed integer, most significant field first:
+//   [ bin1 : nb ][ bin2 : nb ][ lane : nl ][ pos1 % res : nr ][ pos2 % res : nr ][ swapped : 1 ][ strands : 2 ]
+// Equal pairs are equal integers (duplicate removal = adjacent unique) and all pairs of one (bin1,bin2) cell are
+// contiguous (binning = run-length encoding of the top 2*nb bits), in ceil(bits/8) radix passes instead of the
+// 11 + 6 of the two separate sorts.  The packing is invertible, so the kept pairs are decoded back into mk_pair.
+struct PackCfg { u32 res, nb, nr, nl, total_bits, n_dec; };
+
+__device__ __forceinline__ void put_bits(u64 &lo, u64 &hi, u64 v, u32 width) {      // key = (key << width) | v
+    hi = width >= 64 ? lo << (width - 64) : (width ? (hi << width) | (lo >> (64 - width)) : hi);
+    lo = width >= 64 ? 0 : lo << width;
+    lo |= v;
+}
+__device__ __forceinline__ u64 take_bits(u64 &lo, u64 &hi, u32 width) {             // v = key & mask; key >>= width
+    const u64 v = width >= 64 ? lo : (lo & ((1ull << width) - 1));
+    lo = width >= 64 ? hi : (width ? (lo >> width) | (hi << (64 - width)) : lo);
+    hi = width >= 64 ? 0 : hi >> width;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, const u32 *off_by_id, PackCfg c, uint4 *key) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const uint4 r = ((const uint4 *)p)[i];
+        u32 pos1 = r.x, pos2 = r.y; const u32 c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
+        u32 st = r.w & 3u; const u32 lane = r.w >> 16;
+        u32 q1 = pos1 / c.res, q2 = pos2 / c.res;
+        u32 a = off_by_id[c1] + q1, b = off_by_id[c2] + q2;
+        u32 r1 = pos1 - q1 * c.res, r2 = pos2 - q2 * c.res;
+        u32 sw = 0;
+        if (a > b) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); sw = 1; }
+        u64 lo = 0, hi = 0;
+        put_bits(lo, hi, a, c.nb); put_bits(lo, hi, b, c.nb); put_bits(lo, hi, lane, c.nl);
+        put_bits(lo, hi, r1, c.nr); put_bits(lo, hi, r2, c.nr); put_bits(lo, hi, sw, 1); put_bits(lo, hi, st, 2);
+        key[i] = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+    }
+}
+
+__device__ __forceinline__ mk_pair unpack_key(uint4 k, const PackCfg &c, const u32 *dec_off, const u16 *dec_id) {
+    u64 lo = (u64)k.x | ((u64)k.y << 32), hi = (u64)k.z | ((u64)k.w << 32);
+    u32 st = (u32)take_bits(lo, hi, 2); const u32 sw = (u32)take_bits(lo, hi, 1);
+    u32 r2 = (u32)take_bits(lo, hi, c.nr), r1 = (u32)take_bits(lo, hi, c.nr);
+    const u32 lane = (u32)take_bits(lo, hi, c.nl);
+    u32 b = (u32)take_bits(lo, hi, c.nb), a = (u32)take_bits(lo, hi, c.nb);
+    if (sw) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); }
+    // chromosome of a bin: last entry of dec_off that is <= bin
+    u32 ka = 0, kb = 0;
+    { u32 l = 0, h = c.n_dec - 1; while (l < h) { u32 m = (l + h + 1) >> 1; if (dec_off[m] <= a) l = m; else h = m - 1; } ka = l; }
+    { u32 l = 0, h = c.n_dec - 1; while (l < h) { u32 m = (l + h + 1) >> 1; if (dec_off[m] <= b) l = m; else h = m - 1; } kb = l; }
+    mk_pair o;
+    o.pos1 = (a - dec_off[ka]) * c.res + r1; o.pos2 = (b - dec_off[kb]) * c.res + r2;
+    o.chr1 = dec_id[ka]; o.chr2 = dec_id[kb]; o.strands = (u8)st; o.lane = (u16)lane;
+    if (o.chr1 != o.chr2) o.cls = 0;
+    else { const u32 d = o.pos2 - o.pos1; o.cls = d >= 10000u ? 1 : (d >= 1000u ? 2 : 3); }
+    return o;
+}
+
+// sorted packed keys -> kept pairs (first of every run, decoded) + cell heads (bin1, bin2, rank of the cell's first kept pair)
+__global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint4 *b1, const RadixPlan *plan, u64 n, PackCfg c,
+                                                     const u32 *dec_off, const u16 *dec_id, mk_pair *out0, mk_pair *out1,
+                                                     u32 *cell_b1, u32 *cell_b2, u32 *cell_first, u64 cell_cap,
+                                                     u64 *desc, unsigned long long *counters /* [0] kept, [1] cells */, u32 *ticket) {
+    __shared__ u32 s_w[2][UQ_T / 32];
+    __shared__ u64 s_base;
+    __shared__ int s_tile;
+    const uint4 *in = plan->final_buf ? b1 : b0;
+    mk_pair *out = plan->final_buf ? out0 : out1;                 // the buffer the sorted keys are NOT in
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
+    const u32 cell_shift = c.total_bits - 2 * c.nb;               // bits below the (bin1,bin2) prefix
+    while (true) {
+        if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
+        const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
+        uint4 r[UQ_ITEMS]; u32 fk = 0, fc = 0, nk = 0, nc = 0;
+        uint4 prev = base > 0 && base <= n ? in[base - 1] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < UQ_ITEMS; ++k) {
+            if (base + k < n) {
+                r[k] = in[base + k];
+                const bool first = base + k == 0;
+                const bool dk = first || r[k].x != prev.x || r[k].y != prev.y || r[k].z != prev.z || r[k].w != prev.w;
+                bool dc = first;
+                if (!first && dk) {
+                    u64 lo = (u64)r[k].x | ((u64)r[k].y << 32), hi = (u64)r[k].z | ((u64)r[k].w << 32);
+                    u64 plo = (u64)prev.x | ((u64)prev.y << 32), phi = (u64)prev.z | ((u64)prev.w << 32);
+                    take_bits(lo, hi, cell_shift); take_bits(plo, phi, cell_shift);
+                    dc = lo != plo || hi != phi;
+                }
+                prev = r[k];
+                if (dk) { fk |= 1u << k; ++nk; }
+                if (dc) { fc |= 1u << k; ++nc; }
+            }
+        }
+        const u32 ik = warp_incl_scan(nk, lane), ic = warp_incl_scan(nc, lane);
+        if (lane == 31) { s_w[0][wid] = ik; s_w[1][wid] = ic; }
+        __syncthreads();
+        u32 bk = 0, bc = 0, tk = 0, tc = 0;
+#pragma unroll
+        for (int w = 0; w < UQ_T / 32; ++w) { const u32 x = s_w[0][w], y = s_w[1][w]; tk += x; tc += y; if (w < wid) { bk += x; bc += y; } }
+        if (wid == 0) {
+            const u64 agg = (u64)tk | ((u64)tc << 31);
+            const u64 b = lookback_exclusive(desc, tile, 0, agg, lane);
+            if (lane == 0) { s_base = b; if (tile == n_tiles - 1) { counters[0] = (b & 0x7FFFFFFFu) + tk; counters[1] = (b >> 31) + tc; } }
+        }
+        __syncthreads();
+        u64 ok = (s_base & 0x7FFFFFFFu) + bk + ik - nk, oc = (s_base >> 31) + bc + ic - nc;
+#pragma unroll
+        for (int k = 0; k < UQ_ITEMS; ++k) {
+            if (fc & (1u << k)) {
+                if (oc < cell_cap) {
+                    u64 lo = (u64)r[k].x | ((u64)r[k].y << 32), hi = (u64)r[k].z | ((u64)r[k].w << 32);
+                    take_bits(lo, hi, cell_shift);
+                    const u32 bb = (u32)take_bits(lo, hi, c.nb), aa = (u32)take_bits(lo, hi, c.nb);
+                    cell_b1[oc] = aa; cell_b2[oc] = bb; cell_first[oc] = (u32)ok;
+                }
+                ++oc;
+            }
+            if (fk & (1u << k)) { out[ok] = unpack_key(r[k], c, dec_off, dec_id); ++ok; }
+        }
+    }
+}
+
+__global__ void k_cell_counts(const u32 *cell_first, const unsigned long long *counters, u64 cap, u32 *cnt) {
+    const u64 kept = counters[0], cells = counters[1] < cap ? counters[1] : cap;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (u64)gridDim.x * blockDim.x)
+        cnt[i] = (i + 1 < counters[1] && i + 1 < cap ? cell_first[i + 1] : (u32)kept) - cell_first[i];
+}
+
+static u32 bits_for(u64 max_value) { u32 b = 1; while (b < 64 && (max_value >> b)) ++b; return b; }
+
+extern "C" int mk_pairs_dedup_bin_device(mk_pairs_ws *w, mk_pair *d_pairs, size_t n, const uint32_t *chrom_len, int n_chrom,
+                                         const uint16_t *chrom_id_map, int n_map, uint32_t res, uint16_t max_lane,
+                                         uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                                         size_t *n_kept, size_t *nnz, void *stream) {
+    if (!w || !n_kept || !nnz || !chrom_len || n_chrom <= 0 || res == 0 || !d_bin1 || !d_bin2 || !d_cnt) { mk_set_error("mk_pairs_dedup_bin_device: bad argument"); return MK_ERR_ARG; }
+    if (n > w->max_pairs) { mk_set_error("mk_pairs_dedup_bin_device: workspace holds %zu pairs, got %zu", w->max_pairs, n); return MK_ERR_CAPACITY; }
+    MK_CUDA(cudaSetDevice(w->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    *n_kept = 0; *nnz = 0;
+    if (n == 0) return MK_OK;
+    std::vector<u64> off(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; ++c) off[c + 1] = off[c] + chrom_len[c] / res + 1;
+    if (off[n_chrom] >= (1ull << 32)) { mk_set_error("mk_pairs_dedup_bin_device: more than 2^32 bins"); return MK_ERR_CAPACITY; }
+    const int n_ids = chrom_id_map ? n_map : n_chrom;
+    if (n_ids > 16384 || n_chrom > 16384) { mk_set_error("mk_pairs_dedup_bin_device: too many chromosomes"); return MK_ERR_ARG; }
+    std::vector<u32> by_id(n_ids), dec_off(n_chrom);
+    std::vector<u16> dec_id(n_chrom, 0xFFFF);
+    for (int i = 0; i < n_ids; ++i) {
+        int c = chrom_id_map ? chrom_id_map[i] : i;
+        if (c < 0 || c >= n_chrom) { mk_set_error("mk_pairs_dedup_bin_device: chromosome map entry %d out of range", i); return MK_ERR_ARG; }
+        by_id[i] = (u32)off[c];
+        if (dec_id[c] == 0xFFFF) dec_id[c] = (u16)i;
+    }
+    for (int c = 0; c < n_chrom; ++c) dec_off[c] = (u32)off[c];
+    PackCfg pc; pc.res = res; pc.nb = bits_for(off[n_chrom] - 1); pc.nr = bits_for(res - 1); pc.nl = max_lane ? bits_for(max_lane) : 0;
+    pc.total_bits = 2 * pc.nb + 2 * pc.nr + pc.nl + 3; pc.n_dec = (u32)n_chrom;
+    if (pc.total_bits > 128) { mk_set_error("mk_pairs_dedup_bin_device: key does not fit 128 bits"); return MK_ERR_CAPACITY; }
+    // small tables live in chr_off: [by_id (16384 u32)] [dec_off (16384 u32)] [dec_id (16384 u16)]
+    u32 *d_by_id = w->chr_off.as<u32>(), *d_dec_off = d_by_id + 16384; u16 *d_dec_id = (u16 *)(d_dec_off + 16384);
+    MK_CUDA(cudaMemcpyAsync(d_by_id, by_id.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice, s));
+    MK_CUDA(cudaMemcpyAsync(d_dec_off, dec_off.data(), (size_t)n_chrom * 4, cudaMemcpyHostToDevice, s));
+    MK_CUDA(cudaMemcpyAsync(d_dec_id, dec_id.data(), (size_t)n_chrom * 2, cudaMemcpyHostToDevice, s));
+    uint4 *k0 = w->alt.as<uint4>(), *k1 = (uint4 *)d_pairs;           // the pairs buffer doubles as the second sort buffer
+    k_pack_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, d_by_id, pc, k0);
+    w->launches += 1;
+    RadixSchedule sch; sch.n_pass = (int)((pc.total_bits + 7) / 8);
+    for (int i = 0; i < sch.n_pass; ++i) sch.byte_of[i] = i;
+    Rec16::Bufs b; b.k[0] = k0; b.k[1] = k1; b.v[0] = b.v[1] = nullptr;
+    MK_TRY(radix_sort<Rec16>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
+    const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
+    MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
+    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
+    unsigned long long *cnt = w->counter.as<unsigned long long>();
+    k_uniq_cells<<<lookback_grid((const void *)k_uniq_cells, UQ_T, w->sms), UQ_T, 0, s>>>(
+        k0, k1, w->rws.plan.as<RadixPlan>(), n, pc, d_dec_off, d_dec_id, (mk_pair *)k0, (mk_pair *)k1,
+        d_bin1, d_bin2, w->heads_pos.as<u32>(), cap, w->desc.as<u64>(), cnt, (u32 *)(cnt + 4));
+    k_cell_counts<<<w->sms * 4, 256, 0, s>>>(w->heads_pos.as<u32>(), cnt, cap, d_cnt);
+    w->launches += 2;
+    unsigned long long h[2]; u32 final_buf = 0;
+    MK_CUDA(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaMemcpyAsync(&final_buf, (char *)w->rws.plan.p + offsetof(RadixPlan, final_buf), 4, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    // sorted keys sat in buffer final_buf; the decoded pairs went to the other one
+    if (final_buf == 1) MK_CUDA(cudaMemcpyAsync(d_pairs, w->alt.p, (size_t)h[0] * 16, cudaMemcpyDeviceToDevice, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    *n_kept = (size_t)h[0]; *nnz = (size_t)h[1];
+    if (h[1] > cap) { mk_set_error("mk_pairs_dedup_bin_device: %llu non-zero cells, output capacity %zu", h[1], cap); return MK_ERR_CAPACITY; }
+    return MK_OK;
 }

@@ -33,7 +33,8 @@ struct S2PCtx : mk_ctx {
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
-    int grid_scan = 0, grid_emit = 0, grid_gs = 0;
+    int grid_scan = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0;
+    bool fused = true;
     u64 launches = 0;
     // host streaming state
     size_t stage_fill = 0;                         // bytes staged in the next window's pinned buffer
@@ -96,6 +97,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.mode = c->cfg.mode; p.min_mapq = c->cfg.min_mapq; p.ratio = c->cfg.min_mapped_ratio; p.lane = c->cfg.lane;
     p.write_sam = c->cfg.write_sam && out_sam; p.emit_text = c->cfg.emit_text && out_text; p.emit_packed = c->cfg.emit_packed && out_pairs;
     p.running_offsets = running;
+    p.dyn_tickets = getenv("MICROCKET_DYNAMIC_TILES") && atoi(getenv("MICROCKET_DYNAMIC_TILES"));   // measured slower on B200: default off
     return p;
 }
 
@@ -105,10 +107,16 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     auto mark = [&](int id) { if (t) { cudaEvent_t e = c->next_event(); cudaEventRecord(e, s); c->ev_marks.emplace_back(id, c->ev_used - 1); } };
     k_win_begin<<<(c->n_desc + 255) / 256, 256, 0, s>>>(p, c->n_desc);
     mark(0);
-    k_scan_lines<<<c->grid_scan, S2P_SCAN_THREADS, 0, s>>>(p);
-    mark(1);
-    k_parse<<<c->grid_gs, 256, 0, s>>>(p);
-    mark(2);
+    if (c->fused) {
+        k_scan_parse<<<c->grid_fused, FZ_THREADS, FZ_SMEM, s>>>(p);
+        mark(1); mark(2);                                        // reported under k_scan_lines; k_parse stays 0
+        c->launches -= 1;
+    } else {
+        k_scan_lines<<<c->grid_scan, S2P_SCAN_THREADS, 0, s>>>(p);
+        mark(1);
+        k_parse<<<c->grid_gs, 256, 0, s>>>(p);
+        mark(2);
+    }
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
     mark(3);
     k_emit<<<c->grid_emit, EMIT_THREADS, 0, s>>>(p);
@@ -180,7 +188,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     c->W = (c->W + 15) & ~(size_t)15;
     c->in_cap = S2P_CARRY + c->W + 64;
     c->cap_lines = (u32)((S2P_CARRY + c->W) / 32 + 1024);
-    c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->cap_lines / EMIT_THREADS + 4);
+    c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->cap_lines / EMIT_TILE + 4);
     c->sc_cap = c->cap_lines / 2 + 16; c->sc_cap_dev = 0;
     c->chr_cap = 16384; c->chr_slots = 32768;
     int rc = MK_OK;
@@ -226,6 +234,10 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, std::min(occ, 4));
     c->grid_gs = sms * 8;
+    cudaFuncSetAttribute(k_scan_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_parse, FZ_THREADS, FZ_SMEM);
+    c->grid_fused = sms * std::max(1, occ);
+    c->fused = !(getenv("MICROCKET_UNFUSED") && atoi(getenv("MICROCKET_UNFUSED")));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mk_set_error("mk_s2p_create: %s", cudaGetErrorString(e)); delete c; return MK_ERR_CUDA; }
     *out = c;

@@ -62,6 +62,7 @@ struct WinState {
     u64 groups_done, lines_done;
     unsigned long long counters[ST_NCOUNTER];
     u32 sc_count, n_chrom;
+    u32 tickets[4];                  // dynamic tile tickets of the look-back kernels (scan, emit), reset per window
 };
 
 #define S2P_ERR_LINES 1u
@@ -89,6 +90,7 @@ struct S2PParams {
     u64 window_bytes; u32 cap_lines;
     int mode, min_mapq, write_sam, emit_text, emit_packed; float ratio; u16 lane;
     int running_offsets;      // 1: append at st->out_* (device-resident runs); 0: every window writes at 0
+    int dyn_tickets;          // look-back kernels claim tiles with an atomic ticket (1) or round-robin (0)
 };
 
 // ------------------------------------------------------------------------------------------------ begin / end
@@ -103,6 +105,7 @@ static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
         s->n_lines = 0; s->carry_line = 0xFFFFFFFFu;
         s->first_tile = (u32)(s->ws / S2P_TILE_BYTES);
         s->w_groups = s->w_emit = s->w_text = s->w_sam = 0;
+        s->tickets[0] = s->tickets[1] = s->tickets[2] = s->tickets[3] = 0;
         if (!p.running_offsets) { s->out_text = s->out_pairs = s->out_sam = 0; s->sc_count = 0; }
     }
 }
@@ -132,42 +135,83 @@ static __global__ void k_win_end(S2PParams p) {
 // loads; the 16 newline flags of every 16-byte word go through shared memory so that each thread then
 // owns 128 CONTIGUOUS bytes (8 words), which makes ranks a single block scan.
 // Shared by the SAM and FASTQ paths: positions (relative to ws) of every '\n' in [ws, we).
+//
+// Per 16-byte word the four SWAR results are merged WITHOUT gathering: bit (8*j + k) of the word's flag mask is set
+// iff byte j of 32-bit lane k is '\n' (3 ALU ops per lane + 6 to merge).  The permuted order only matters for the rare
+// word that holds two newlines.  Shared-memory buffers are double-buffered so a tile costs three barriers, and the
+// next tile's loads are issued before the current tile's scan so HBM stays busy across the barriers.
+__device__ __forceinline__ u32 nl_y(u32 x) {
+    u32 t = ((x ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x) & 0x80808080u;
+}
+__device__ __forceinline__ u32 nl_flags16(const uint4 &w) { return (nl_y(w.x) >> 7) | (nl_y(w.y) >> 6) | (nl_y(w.z) >> 5) | (nl_y(w.w) >> 4); }
+__device__ __forceinline__ u32 perm_bit_of_byte(u32 q) { return 8u * (q & 3u) + (q >> 2); }       // byte q (0..15) -> bit
+__device__ __forceinline__ u32 byte_of_perm_bit(u32 b) { return ((b & 7u) << 2) | (b >> 3); }     // bit -> byte
+
+// Tiles go round-robin over a fully resident grid (tile = first + blockIdx + k * gridDim).  Claiming tiles with an
+// atomic ticket was measured on B200 and is slower here (14.9 ms vs 9.8 ms per 19.8 GB): kept only behind `dynamic`.
 __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, const u64 we, const int first_tile,
-                                                u32 *nl_pos, const u32 cap_lines, u64 *desc, u32 *n_lines_out, u32 *err_out, u32 err_bit) {
-    __shared__ __align__(16) u16 s_mask[S2P_TILE_BYTES / 16];
-    __shared__ u32 s_scan[S2P_SCAN_THREADS / 32 + 1];
-    __shared__ u32 s_base;
+                                                u32 *nl_pos, const u32 cap_lines, u64 *desc, u32 *n_lines_out, u32 *err_out, u32 err_bit,
+                                                u32 *ticket, const bool dynamic = true) {
+    __shared__ __align__(16) u32 s_z[2][S2P_TILE_BYTES / 16];
+    __shared__ u32 s_wtot[2][S2P_SCAN_THREADS / 32];
+    __shared__ u32 s_base[2];
+    __shared__ int s_next[2];
     if (we <= ws) return;
     const int last_tile = (int)((we - 1) / S2P_TILE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int tile = first_tile + blockIdx.x; tile <= last_tile; tile += gridDim.x) {
-        const u64 tbase = (u64)tile * S2P_TILE_BYTES;
+    if (tid == 0) s_next[0] = dynamic ? first_tile + (int)atomicAdd(ticket, 1u) : first_tile + (int)blockIdx.x;
+    __syncthreads();
+    int tile = s_next[0];
+    uint4 w[8];
+    auto load_tile = [&](int t) {
+        const u64 tbase = (u64)t * S2P_TILE_BYTES;
         const uint4 *src = (const uint4 *)(buf + tbase);
-        uint4 w[8];
+        const bool interior = tbase >= ws && tbase + S2P_TILE_BYTES <= we;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            u64 off = tbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
-            w[j] = (off < we && off + 16 > ws) ? ld_stream_v4(src + j * S2P_SCAN_THREADS + tid) : make_uint4(0, 0, 0, 0);
+            if (interior) w[j] = ld_stream_v4(src + j * S2P_SCAN_THREADS + tid);
+            else {
+                u64 off = tbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
+                w[j] = (off < we && off + 16 > ws) ? ld_stream_v4(src + j * S2P_SCAN_THREADS + tid) : make_uint4(0, 0, 0, 0);
+            }
         }
+    };
+    if (tile <= last_tile) load_tile(tile);
+    int pb = 0;
+    while (tile <= last_tile) {
+        const u64 tbase = (u64)tile * S2P_TILE_BYTES;
+        const bool interior = tbase >= ws && tbase + S2P_TILE_BYTES <= we;
+        if (tid == 0) s_next[pb ^ 1] = dynamic ? first_tile + (int)atomicAdd(ticket, 1u) : tile + (int)gridDim.x;   // read after the next barrier
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            u32 m = gather_flags4(byte_eq_mask(w[j].x, 0x0A0A0A0Au)) | (gather_flags4(byte_eq_mask(w[j].y, 0x0A0A0A0Au)) << 4) |
-                    (gather_flags4(byte_eq_mask(w[j].z, 0x0A0A0A0Au)) << 8) | (gather_flags4(byte_eq_mask(w[j].w, 0x0A0A0A0Au)) << 12);
-            u64 off = tbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
-            // partial words at the window edges
-            if (off < ws) { u64 d = ws - off; m = d >= 16 ? 0 : (m >> d) << d; }
-            if (off + 16 > we) { u64 keep = we > off ? we - off : 0; m = keep >= 16 ? m : (m & ((1u << keep) - 1)); }
-            s_mask[j * S2P_SCAN_THREADS + tid] = (u16)m;
+            u32 z = nl_flags16(w[j]);
+            if (!interior && z) {                                     // window edges: drop flags of bytes outside [ws, we)
+                const u64 off = tbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
+                u32 keep = 0;
+                for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
+                z &= keep;
+            }
+            s_z[pb][j * S2P_SCAN_THREADS + tid] = z;
         }
         __syncthreads();
-        uint4 mm = ((const uint4 *)s_mask)[tid];          // flags of bytes [tid*128, tid*128+128)
-        u32 cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
-        u32 total;
-        u32 excl = block_excl_scan<S2P_SCAN_THREADS>(cnt, s_scan, &total);
+        const int next_tile = s_next[pb ^ 1];
+        if (next_tile <= last_tile) load_tile(next_tile);             // prefetch this CTA's next tile
+        const uint4 za = ((const uint4 *)s_z[pb])[2 * tid], zb = ((const uint4 *)s_z[pb])[2 * tid + 1];   // bytes [tid*128, +128)
+        const u32 zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cnt += __popc(zz[i]);
+        const u32 inc = warp_incl_scan(cnt, lane);
+        if (lane == 31) s_wtot[pb][wid] = inc;
+        __syncthreads();
+        u32 before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < S2P_SCAN_THREADS / 32; ++k) { const u32 v = s_wtot[pb][k]; total += v; if (k < wid) before += v; }
         if (wid == 0) {
-            u64 b = lookback_exclusive(desc - first_tile, tile, first_tile, total, lane);
+            const u64 b = lookback_exclusive(desc - first_tile, tile, first_tile, total, lane);
             if (lane == 0) {
-                s_base = (u32)b;
+                s_base[pb] = (u32)b;
                 if (tile == last_tile) {
                     u64 nl = b + total;
                     if (nl > cap_lines) { atomicOr(err_out, err_bit); nl = cap_lines; }
@@ -176,25 +220,30 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
             }
         }
         __syncthreads();
-        u32 idx = s_base + excl;
-        u32 rel = (u32)(tbase + (u64)tid * 128 - ws);     // may wrap for bytes before ws: those have no flags
-        u32 parts[4] = {mm.x, mm.y, mm.z, mm.w};
+        if (cnt) {
+            u32 idx = s_base[pb] + before + inc - cnt;
+            const u32 rel = (u32)(tbase + (u64)tid * 128 - ws);        // may wrap for bytes before ws: those have no flags
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            u32 m = parts[q];
-            while (m) {
-                int b = __ffs(m) - 1; m &= m - 1;
-                if (idx < cap_lines) nl_pos[idx] = rel + q * 32 + b;
-                ++idx;
+            for (int i = 0; i < 8; ++i) {
+                u32 z = zz[i];
+                if (!z) continue;
+                if (z & (z - 1)) {                                    // several newlines in one 16-byte word: restore byte order
+                    u32 m = 0;
+                    while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
+                    while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (idx < cap_lines) nl_pos[idx] = rel + i * 16 + q; ++idx; }
+                } else {
+                    if (idx < cap_lines) nl_pos[idx] = rel + i * 16 + byte_of_perm_bit(__ffs(z) - 1);
+                    ++idx;
+                }
             }
         }
-        __syncthreads();
+        tile = next_tile; pb ^= 1;
     }
 }
 
 static __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
     WinState *st = p.st;
-    scan_lines_body(p.buf, st->ws, st->we, (int)st->first_tile, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
+    scan_lines_body(p.buf, st->ws, st->we, (int)st->first_tile, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES, &st->tickets[0], p.dyn_tickets != 0);
 }
 
 // ------------------------------------------------------------------------------------------------ chromosome table
@@ -235,11 +284,79 @@ static __device__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 name8, co
 }
 
 // ------------------------------------------------------------------------------------------------ K2: parse
-__device__ __forceinline__ u32 parse_uint_tok(ByteReader &r, int &c) {
+template <class R>
+__device__ __forceinline__ u32 parse_uint_tok(R &r, int &c) {
     while (is_blank(c)) c = r.next();
     u32 v = 0; bool bad = false; int n = 0;
     while (!is_ws(c)) { u32 d = (u32)(c - '0'); bad |= d > 9u; v = v * 10u + d; ++n; c = r.next(); }
     return (bad || n == 0) ? 0u : v;
+}
+
+#define LM_EQ_UNK 32u          // EQ not evaluated here (the previous line starts in another tile): K3 compares on demand
+
+// One SAM line: first six fields, record filter, CIGAR walk.  `r` is positioned at the line's first byte; when
+// cmp_prev, `q` is positioned at the previous line's first byte and the two QNAMEs are compared on the fly.
+// Returns the line's meta bits; `rec` is filled for kept lines.
+template <class R>
+__device__ __forceinline__ u32 parse_line(const S2PParams &p, R &r, R &q, const bool cmp_prev, const u64 line_abs, LineRec &rec) {
+    int c = r.next();
+    if (c == '@') return 0;                                   // header line (QNAME cannot contain '@')
+    while (is_blank(c)) c = r.next();
+    const u32 qoff = (u32)(r.pos - 1 - line_abs);
+    u32 meta = 0;
+    if (cmp_prev) {
+        int d = q.next();
+        while (is_blank(d)) d = q.next();
+        bool eq = true;
+        while (!is_ws(c)) { eq &= (c == d); if (!is_ws(d)) d = q.next(); c = r.next(); }
+        eq &= is_ws(d);
+        if (eq) meta |= LM_EQ;
+    } else {
+        while (!is_ws(c)) c = r.next();
+    }
+    const u32 qlen = (u32)(r.pos - 1 - line_abs) - qoff;
+    const u32 flag = parse_uint_tok(r, c);
+    while (is_blank(c)) c = r.next();
+    const u64 name_off = r.pos - 1;
+    u64 h = 0xCBF29CE484222325ull, name8 = 0;
+    u32 name_len = 0;
+    while (!is_ws(c)) { h = hash_step(h, c); if (name_len < 8) name8 |= (u64)c << (8 * name_len); ++name_len; c = r.next(); }
+    const u32 pos = parse_uint_tok(r, c);
+    const u32 mapq = parse_uint_tok(r, c);
+    if (mapq < (u32)p.min_mapq || (flag & 0x700u)) return meta;   // pairutil.h:157-161
+    meta |= LM_KEEP;
+    // CIGAR walk (pairutil.h:63-126)
+    while (is_blank(c)) c = r.next();
+    u32 val = 0, idx = 0, leftClip = 0, rightClip = 0, mappable = 0;
+    u32 cur = pos, right0 = 0, left1 = 0, right1 = 0, last_right = 0;
+    bool err = false;
+    while (!is_ws(c)) {
+        u32 d = (u32)(c - '0');
+        if (d <= 9u) { val = val * 10u + d; c = r.next(); continue; }
+        const int nxt = r.next();                       // one byte of look-ahead: is this op the last character?
+        if (c == 'H' || c == 'S') {
+            if (is_ws(nxt)) rightClip = val;
+            else if (idx == 0) leftClip = val;          // overwrites: 5H30S100M leaves leftClip = 30
+            else err = true;
+        } else if (c == 'M' || c == 'D') {
+            if (c == 'M') mappable += val;
+            cur += val; last_right = cur - 1;
+            if (idx == 0) right0 = last_right; else if (idx == 1) right1 = last_right;
+        } else if (c == 'N') {
+            cur += val; ++idx; last_right = 0;
+            if (idx == 1) left1 = cur;
+        } else if (c != 'I') err = true;
+        val = 0; c = nxt;
+    }
+    rec.pos = pos; rec.right0 = right0; rec.left1 = left1; rec.right1 = right1;
+    rec.leftClip = leftClip; rec.rightClip = rightClip; rec.mappable = mappable; rec.line_len = 0;
+    rec.flag = (u16)flag; rec.qname_len = (u16)qlen;
+    rec.chr_slot = (u16)chr_lookup_insert(p, h, name8, p.buf, name_off, name_len);
+    const u32 segCnt = idx + 1;
+    if (last_right == 0) err = true;                             // pairutil.h:119
+    rec.segCnt = err ? 0 : (u8)(segCnt > 2 ? 3 : segCnt);
+    rec.pad0 = 0; rec.qname_off = qoff; rec.pad1 = 0;
+    return meta;
 }
 
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
@@ -248,73 +365,207 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
     const u64 ws = st->ws;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += gridDim.x * blockDim.x) {
         const u32 start = i ? p.nl_pos[i - 1] + 1 : 0;
-        const u32 end = p.nl_pos[i];
         if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu;
-        ByteReader r; r.init(p.buf, ws + start);
-        int c = r.next();
-        if (c == '@') { p.lmeta[i] = 0; continue; }          // header line (QNAME cannot contain '@')
-        while (is_blank(c)) c = r.next();
-        const u32 qoff = (u32)(r.pos - 1 - (ws + start));
-        u32 meta = 0;
-        // QNAME, compared on the fly with the previous line's first token
-        if (i > 0) {
-            const u32 pstart = i > 1 ? p.nl_pos[i - 2] + 1 : 0;
-            ByteReader q; q.init(p.buf, ws + pstart);
-            int d = q.next();
-            while (is_blank(d)) d = q.next();
-            bool eq = true;
-            while (!is_ws(c)) { eq &= (c == d); if (!is_ws(d)) d = q.next(); c = r.next(); }
-            eq &= is_ws(d);
-            if (eq) meta |= LM_EQ;
-        } else {
-            while (!is_ws(c)) c = r.next();
-        }
-        const u32 qlen = (u32)(r.pos - 1 - (ws + start)) - qoff;
-        const u32 flag = parse_uint_tok(r, c);
-        // RNAME
-        while (is_blank(c)) c = r.next();
-        const u64 name_off = r.pos - 1;
-        u64 h = 0xCBF29CE484222325ull, name8 = 0;
-        u32 name_len = 0;
-        while (!is_ws(c)) { h = hash_step(h, c); if (name_len < 8) name8 |= (u64)c << (8 * name_len); ++name_len; c = r.next(); }
-        const u32 pos = parse_uint_tok(r, c);
-        const u32 mapq = parse_uint_tok(r, c);
-        if (mapq < (u32)p.min_mapq || (flag & 0x700u)) { p.lmeta[i] = (u8)meta; continue; }   // pairutil.h:157-161
-        meta |= LM_KEEP;
-        // CIGAR walk (pairutil.h:63-126)
-        while (is_blank(c)) c = r.next();
-        u32 val = 0, idx = 0, leftClip = 0, rightClip = 0, mappable = 0;
-        u32 cur = pos, right0 = 0, left1 = 0, right1 = 0, last_right = 0;
-        bool err = false;
-        while (!is_ws(c)) {
-            u32 d = (u32)(c - '0');
-            if (d <= 9u) { val = val * 10u + d; c = r.next(); continue; }
-            const int nxt = r.next();                       // one byte of look-ahead: is this op the last character?
-            if (c == 'H' || c == 'S') {
-                if (is_ws(nxt)) rightClip = val;
-                else if (idx == 0) leftClip = val;          // overwrites: 5H30S100M leaves leftClip = 30
-                else err = true;
-            } else if (c == 'M' || c == 'D') {
-                if (c == 'M') mappable += val;
-                cur += val; last_right = cur - 1;
-                if (idx == 0) right0 = last_right; else if (idx == 1) right1 = last_right;
-            } else if (c == 'N') {
-                cur += val; ++idx; last_right = 0;
-                if (idx == 1) left1 = cur;
-            } else if (c != 'I') err = true;
-            val = 0; c = nxt;
-        }
+        ByteReader r, q;
+        r.init(p.buf, ws + start);
+        if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
         LineRec rec;
-        rec.pos = pos; rec.right0 = right0; rec.left1 = left1; rec.right1 = right1;
-        rec.leftClip = leftClip; rec.rightClip = rightClip; rec.mappable = mappable; rec.line_len = end - start;
-        rec.flag = (u16)flag; rec.qname_len = (u16)qlen;
-        rec.chr_slot = (u16)chr_lookup_insert(p, h, name8, p.buf, name_off, name_len);
-        u32 segCnt = idx + 1;
-        if (last_right == 0) err = true;                             // pairutil.h:119
-        rec.segCnt = err ? 0 : (u8)(segCnt > 2 ? 3 : segCnt);
-        rec.pad0 = 0; rec.qname_off = qoff; rec.pad1 = 0;
-        p.rec[i] = rec;
+        const u32 meta = parse_line(p, r, q, i > 0, ws + start, rec);
+        if (meta & LM_KEEP) p.rec[i] = rec;
         p.lmeta[i] = (u8)meta;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1+K2 fused
+// One pass over the SAM bytes: 32 KiB tiles are brought into shared memory by TMA bulk copies (double buffered,
+// mbarrier completion), newline flags are computed from shared memory, and every line that STARTS in the tile is
+// parsed from shared memory by one thread (lines are compacted onto the low threads so warps are full).  The tile
+// publishes its newline count before parsing and resolves the decoupled look-back after it, so the wait for
+// predecessor tiles is hidden behind the parse.
+#define FZ_TILE 32768
+#define FZ_HALO 512
+#define FZ_THREADS 256
+#define FZ_LCAP 4096
+#define FZ_SMEM (2 * (FZ_TILE + FZ_HALO) + (FZ_TILE / 16) * 4 + FZ_LCAP * 2 + 64 + 32)
+
+#undef FZ_SMEM
+#define FZ_SMEM (2 * (FZ_TILE + FZ_HALO) + 2 * (FZ_TILE / 16) * 4 + FZ_LCAP * 2 + 128)
+
+// newline flags of one tile (from shared memory) -> s_z, per-thread masks of its 128-byte block, counts
+struct FzCount { u32 zz[8]; u32 cnt, my_first, total; };
+
+static __global__ void __launch_bounds__(FZ_THREADS) k_scan_parse(S2PParams p) {
+    extern __shared__ __align__(128) unsigned char fz_smem[];
+    char *s_tile0 = (char *)fz_smem, *s_tile1 = s_tile0 + FZ_TILE + FZ_HALO;
+    u32 *s_z = (u32 *)(fz_smem + 2 * (FZ_TILE + FZ_HALO));             // [2][2048]
+    u16 *s_nl = (u16 *)(s_z + 2 * (FZ_TILE / 16));
+    u32 *s_wtot = (u32 *)(s_nl + FZ_LCAP);                              // [2][8]
+    u32 *s_misc = s_wtot + 16;                                          // [0] excl, [1] claimed tile
+    u64 *s_bar = (u64 *)(s_misc + 8);
+    WinState *st = p.st;
+    const u64 ws = st->ws, we = st->we;
+    if (we <= ws) return;
+    const int first_tile = (int)st->first_tile;
+    const int last_tile = (int)((we - 1) / FZ_TILE);
+    const u64 readable = (st->total + 15) & ~(u64)15;                   // callers guarantee the buffer is readable up to here
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    u64 *desc = p.desc_scan - first_tile;
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](int t, int stage) {
+        const u64 tbase = (u64)t * FZ_TILE;
+        u64 n = readable - tbase;
+        if (n > FZ_TILE + FZ_HALO) n = FZ_TILE + FZ_HALO;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&s_bar[stage], (u32)n);
+        bulk_copy_g2s(stage ? s_tile1 : s_tile0, p.buf + tbase, (u32)n, &s_bar[stage]);
+    };
+    // claim (in order) and start loading a tile; every thread learns the tile id after the next barrier
+    auto claim = [&](int stage) {
+        if (tid == 0) {
+            const int t = first_tile + (int)atomicAdd(&st->tickets[0], 1u);
+            s_misc[1] = (u32)t;
+            if (t <= last_tile) issue(t, stage);
+        }
+    };
+    // count the newlines of a loaded tile and publish the aggregate (two barriers)
+    auto count_tile = [&](int t, int stage, u32 parity, FzCount &c) {
+        const u64 tbase = (u64)t * FZ_TILE;
+        const char *tl = stage ? s_tile1 : s_tile0;
+        u32 *z_out = s_z + stage * (FZ_TILE / 16);
+        mbar_wait(&s_bar[stage], parity);
+        const bool interior = tbase >= ws && tbase + FZ_TILE <= we;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 w = ((const uint4 *)tl)[j * FZ_THREADS + tid];
+            u32 z = nl_flags16(w);
+            if (!interior && z) {
+                const u64 off = tbase + ((u64)(j * FZ_THREADS + tid) << 4);
+                u32 keep = 0;
+                for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
+                z &= keep;
+            }
+            z_out[j * FZ_THREADS + tid] = z;
+        }
+        __syncthreads();
+        const uint4 za = ((const uint4 *)z_out)[2 * tid], zb = ((const uint4 *)z_out)[2 * tid + 1];
+        c.zz[0] = za.x; c.zz[1] = za.y; c.zz[2] = za.z; c.zz[3] = za.w; c.zz[4] = zb.x; c.zz[5] = zb.y; c.zz[6] = zb.z; c.zz[7] = zb.w;
+        c.cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c.cnt += __popc(c.zz[i]);
+        const u32 inc = warp_incl_scan(c.cnt, lane);
+        if (lane == 31) s_wtot[stage * 8 + wid] = inc;
+        __syncthreads();
+        u32 before = 0; c.total = 0;
+#pragma unroll
+        for (int k = 0; k < FZ_THREADS / 32; ++k) { const u32 v = s_wtot[stage * 8 + k]; c.total += v; if (k < wid) before += v; }
+        c.my_first = before + inc - c.cnt;
+        if (tid == 0) lookback_publish(desc, t, first_tile, c.total);    // EARLY: one whole parse phase before anyone needs it
+    };
+
+    claim(0);
+    __syncthreads();
+    int tile = (int)s_misc[1];
+    if (tile > last_tile) return;
+    __syncthreads();
+    claim(1);
+    FzCount cur;
+    count_tile(tile, 0, 0, cur);
+    int next_tile = (int)s_misc[1];                                     // visible after count_tile's barriers
+    for (int it = 0; tile <= last_tile; ++it) {
+        const int stage = it & 1;
+        const u64 tbase = (u64)tile * FZ_TILE;
+        const char *tl = stage ? s_tile1 : s_tile0;
+        u64 loaded = readable - tbase; if (loaded > FZ_TILE + FZ_HALO) loaded = FZ_TILE + FZ_HALO;
+        const u32 total = cur.total;
+        // Lines starting in this tile: local id 0 = the line that begins at the tile's first byte (or at ws), if any;
+        // local id r+1 = the line opened by the tile's r-th newline.  Global line index = excl + local id.
+        bool has_initial; u64 initial_abs;
+        if (tbase <= ws) { has_initial = true; initial_abs = ws; }
+        else { initial_abs = tbase; has_initial = p.buf[tbase - 1] == '\n'; }
+        // ---- a. parse the first batch of lines (all of them unless lines are very short)
+        u32 excl = 0;
+        FzCount nxt; nxt.total = 0; nxt.cnt = 0; nxt.my_first = 0;
+        for (u32 r0 = 0; r0 == 0 || r0 < total; r0 += FZ_LCAP) {
+            if (cur.cnt) {                                               // local newline offsets of ranks [r0, r0 + FZ_LCAP)
+                u32 rk = cur.my_first;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    u32 z = cur.zz[i];
+                    if (!z) continue;
+                    u32 m = 0;
+                    while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
+                    while (m) {
+                        const u32 q = __ffs(m) - 1; m &= m - 1;
+                        if (rk >= r0 && rk < r0 + FZ_LCAP) s_nl[rk - r0] = (u16)(tid * 128 + i * 16 + q);
+                        ++rk;
+                    }
+                }
+            }
+            __syncthreads();
+            const u32 n_here = total - r0 < FZ_LCAP ? total - r0 : FZ_LCAP;
+            for (u32 base_id = r0 ? r0 + 1 : 0; base_id <= r0 + n_here; base_id += FZ_THREADS) {
+                const u32 id = base_id + tid;
+                u32 meta = 0; LineRec rec; bool mine = false; u64 abs0 = 0;
+                if (id <= r0 + n_here) {
+                    bool exists = true;
+                    if (id == 0) { exists = has_initial; abs0 = initial_abs; }
+                    else { const u32 off = (u32)s_nl[id - 1 - r0] + 1; exists = off < FZ_TILE; abs0 = tbase + off; }
+                    if (exists && abs0 < we) {
+                        mine = true;
+                        bool cmp = false; u64 prev_abs = 0;              // previous line's start, when it is known here
+                        if (id >= 2 && id - 2 >= r0) { cmp = true; prev_abs = tbase + (u32)s_nl[id - 2 - r0] + 1; }
+                        else if (id == 1 && has_initial && r0 == 0) { cmp = true; prev_abs = initial_abs; }
+                        TileReader r, q;
+                        r.setup(p.buf, tl, tbase, tbase + loaded); q.setup(p.buf, tl, tbase, tbase + loaded);
+                        r.init(p.buf, abs0);
+                        if (cmp) q.init(p.buf, prev_abs);
+                        meta = parse_line(p, r, q, cmp, abs0, rec);
+                        if (!cmp && abs0 != ws) meta |= LM_EQ_UNK;
+                    }
+                }
+                if (base_id == 0) {
+                    // ---- b. count the NEXT tile and publish its aggregate, then c. resolve this tile's look-back
+                    if (next_tile <= last_tile) count_tile(next_tile, stage ^ 1, (u32)((it + 1) >> 1) & 1u, nxt);
+                    if (wid == 0) { const u64 e = lookback_resolve(desc, tile, first_tile, total, lane); if (lane == 0) s_misc[0] = (u32)e; }
+                    __syncthreads();
+                    excl = s_misc[0];
+                    if (tile == last_tile && tid == 0) {
+                        u64 nl = (u64)excl + total;
+                        if (nl > p.cap_lines) { atomicOr(&st->err, S2P_ERR_LINES); nl = p.cap_lines; }
+                        st->n_lines = (u32)nl;
+                    }
+                }
+                if (mine) {
+                    const u32 g = excl + id;
+                    if (g < p.cap_lines) {
+                        if (meta & LM_KEEP) p.rec[g] = rec;
+                        p.lmeta[g] = (u8)meta;
+                        if (p.write_sam) p.sam_dst[g] = 0xFFFFFFFFu;
+                    }
+                }
+            }
+            __syncthreads();                                             // s_nl is rewritten by the next round
+        }
+        // ---- newline positions (relative to ws) at their global ranks
+        if (cur.cnt) {
+            u32 idx = excl + cur.my_first;
+            const u32 rel = (u32)(tbase + (u64)tid * 128 - ws);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                u32 z = cur.zz[i];
+                if (!z) continue;
+                u32 m = 0;
+                while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
+                while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (idx < p.cap_lines) p.nl_pos[idx] = rel + i * 16 + q; ++idx; }
+            }
+        }
+        // ---- d. this tile's stage is free: claim and prefetch the tile after next
+        claim(stage);
+        __syncthreads();
+        tile = next_tile; next_tile = (int)s_misc[1];
+        cur = nxt;
+        __syncthreads();                                                 // s_misc[1] may be overwritten by the next claim
     }
 }
 
@@ -363,6 +614,13 @@ static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b
     return is_ws(c) && is_ws(d);
 }
 
+// EQ of line q (its QNAME equals line q-1's), evaluating it now when the fused kernel could not
+__device__ __forceinline__ bool line_eq(const S2PParams &p, u64 ws, u32 q, u32 mq) {
+    if (mq & LM_EQ_UNK) return q > 0 && qname_equal_slow(p, ws, q, q - 1);
+    return (mq & LM_EQ) != 0;
+}
+__device__ __forceinline__ u32 line_len_of(const S2PParams &p, u32 q) { return p.nl_pos[q] - (q ? p.nl_pos[q - 1] + 1 : 0); }
+
 // bytewise order of two chromosome names (std::string::compare)
 static __device__ int chr_name_cmp(const S2PParams &p, u16 sa, u16 sb) {
     if (sa == sb) return 0;
@@ -393,9 +651,9 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
         // ---- is this kept line the head of a group?  (pairutil.h:163-173: currId != lastId among kept records)
         bool head;
         {
-            bool chain = (mi & LM_EQ) != 0;
+            bool chain = line_eq(p, ws, i, mi);
             long j = (long)i - 1;
-            while (j >= 0) { u32 mj = p.lmeta[j]; if (mj & LM_KEEP) break; chain = chain && (mj & LM_EQ); --j; }
+            while (j >= 0) { u32 mj = p.lmeta[j]; if (mj & LM_KEEP) break; chain = chain && line_eq(p, ws, (u32)j, mj); --j; }
             if (j < 0) head = true;
             else if (chain) head = false;
             else if (j == (long)i - 1) head = true;
@@ -414,11 +672,11 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
             if (n < 2) first[n] = k;
             ++n;
             if (fl & 64u) { if (n1 < 2) r1[n1] = k; ++n1; } else if (fl & 128u) { if (n2 < 2) r2[n2] = k; ++n2; }
-            sam_len += rk->line_len + 1;
+            sam_len += line_len_of(p, k) + 1;
             prev = k;
             // next kept line
             u32 q = k + 1; chain = true;
-            while (q < n_lines) { u32 mq = p.lmeta[q]; chain = chain && (mq & LM_EQ); if (mq & LM_KEEP) break; ++q; }
+            while (q < n_lines) { u32 mq = p.lmeta[q]; chain = chain && line_eq(p, ws, q, mq); if (mq & LM_KEEP) break; ++q; }
             if (q >= n_lines) { off_end = true; break; }
             bool same = chain ? true : (q == prev + 1 ? false : qname_equal_slow(p, ws, q, prev));
             if (!same) break;
@@ -548,7 +806,9 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
 
 // ------------------------------------------------------------------------------------------------ K4: emit
 #define EMIT_THREADS 256
-#define EMIT_STAGE 24576
+#define EMIT_ITEMS 2
+#define EMIT_TILE (EMIT_THREADS * EMIT_ITEMS)
+#define EMIT_STAGE 40960
 
 __device__ __forceinline__ u32 put_uint(char *dst, u32 v) {
     u32 n = dec_digits(v);
@@ -556,111 +816,137 @@ __device__ __forceinline__ u32 put_uint(char *dst, u32 v) {
     return n;
 }
 
-template <class Sink>
-__device__ __forceinline__ void write_pair_line(const S2PParams &p, u64 ws, const GroupRes &g, Sink &out) {
+// rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347)
+__device__ __forceinline__ void write_pair_line(const S2PParams &p, u64 ws, const GroupRes &g, char *out) {
     const u32 rl = g.rid_line;
     const LineRec *rr = &p.rec[rl];
-    const u64 qsrc = ws + (rl ? p.nl_pos[rl - 1] + 1 : 0) + rr->qname_off;
     const u32 ql = rr->qname_len;
-    for (u32 i = 0; i < ql; ++i) out.put(p.buf[qsrc + i]);
-    out.put('\t');
+    ByteReader r; r.init(p.buf, ws + (rl ? p.nl_pos[rl - 1] + 1 : 0) + rr->qname_off);
+    for (u32 i = 0; i < ql; ++i) *out++ = (char)r.next();
+    *out++ = '\t';
     const ChrSlot *ca = &p.chr[p.id_to_slot[g.chrA]], *cb = &p.chr[p.id_to_slot[g.chrB]];
-    for (u32 i = 0; i < ca->len; ++i) out.put(ca->name[i]);
-    out.put('\t');
-    char tmp[10]; u32 n = put_uint(tmp, g.posA);
-    for (u32 i = 0; i < n; ++i) out.put(tmp[i]);
-    out.put('\t');
-    for (u32 i = 0; i < cb->len; ++i) out.put(cb->name[i]);
-    out.put('\t');
-    n = put_uint(tmp, g.posB);
-    for (u32 i = 0; i < n; ++i) out.put(tmp[i]);
-    out.put('\t'); out.put((g.strands & 1) ? '-' : '+'); out.put('\t'); out.put((g.strands & 2) ? '-' : '+'); out.put('\n');
+    for (u32 i = 0; i < ca->len; ++i) *out++ = ca->name[i];
+    *out++ = '\t';
+    out += put_uint(out, g.posA);
+    *out++ = '\t';
+    for (u32 i = 0; i < cb->len; ++i) *out++ = cb->name[i];
+    *out++ = '\t';
+    out += put_uint(out, g.posB);
+    *out++ = '\t'; *out++ = (g.strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (g.strands & 2) ? '-' : '+'; *out++ = '\n';
 }
-struct PtrSink { char *p; __device__ __forceinline__ void put(char c) { *p++ = c; } };
 
 static __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
-    __shared__ u32 s_scanA[EMIT_THREADS / 32 + 1], s_scanT[EMIT_THREADS / 32 + 1], s_scanS[EMIT_THREADS / 32 + 1];
-    __shared__ u64 s_baseA, s_baseB;
+    __shared__ u32 s_w[2][3][EMIT_THREADS / 32];
+    __shared__ u64 s_baseA[2], s_baseB[2];
     WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n_tiles = (int)((n_lines + EMIT_THREADS - 1) / EMIT_THREADS);
+    const int n_tiles = (int)((n_lines + EMIT_TILE - 1) / EMIT_TILE);
     const u64 base_text = st->out_text, base_pairs = st->out_pairs, base_sam = st->out_sam, base_groups = st->groups_done;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const u32 i = (u32)tile * EMIT_THREADS + tid;
-        u32 m = i < n_lines ? p.lmeta[i] : 0;
-        const bool proc = (m & LM_HEAD) && (m & LM_PROC);
-        const bool emit = proc && (m & LM_EMIT);
-        GroupRes g;
-        if (proc) g = p.res[i];
-        u32 vA = (proc ? 1u : 0u) | (emit ? 1u << 16 : 0u);
-        u32 vT = emit ? g.text_len : 0u, vS = (emit && p.write_sam) ? g.sam_len : 0u;
-        u32 totA, totT, totS;
-        u32 exA = block_excl_scan<EMIT_THREADS>(vA, s_scanA, &totA);
-        u32 exT = block_excl_scan<EMIT_THREADS>(vT, s_scanT, &totT);
-        u32 exS = block_excl_scan<EMIT_THREADS>(vS, s_scanS, &totS);
+    __shared__ int s_tk[2];
+    const bool dyn = p.dyn_tickets != 0;
+    if (tid == 0) s_tk[0] = dyn ? (int)atomicAdd(&st->tickets[1], 1u) : (int)blockIdx.x;
+    __syncthreads();
+    int pb = 0;
+    for (int tile = s_tk[0]; tile < n_tiles; tile = s_tk[pb ^= 1]) {
+        if (tid == 0) s_tk[pb ^ 1] = dyn ? (int)atomicAdd(&st->tickets[1], 1u) : tile + (int)gridDim.x;   // read after this tile's barriers
+        const u32 i0 = (u32)tile * EMIT_TILE + tid * EMIT_ITEMS;
+        GroupRes g[EMIT_ITEMS];
+        bool proc[EMIT_ITEMS], emit[EMIT_ITEMS];
+        u32 vA = 0, vT = 0, vS = 0;
+#pragma unroll
+        for (int k = 0; k < EMIT_ITEMS; ++k) {
+            const u32 i = i0 + k;
+            const u32 m = i < n_lines ? p.lmeta[i] : 0;
+            proc[k] = (m & LM_HEAD) && (m & LM_PROC);
+            emit[k] = proc[k] && (m & LM_EMIT);
+            if (proc[k]) g[k] = p.res[i];
+            vA += (proc[k] ? 1u : 0u) | (emit[k] ? 1u << 16 : 0u);
+            if (emit[k]) { vT += g[k].text_len; if (p.write_sam) vS += g[k].sam_len; }
+        }
+        // three block scans with one pair of barriers
+        const u32 iA = warp_incl_scan(vA, lane), iT = warp_incl_scan(vT, lane), iS = warp_incl_scan(vS, lane);
+        if (lane == 31) { s_w[pb][0][wid] = iA; s_w[pb][1][wid] = iT; s_w[pb][2][wid] = iS; }
+        __syncthreads();
+        u32 bA = 0, bT = 0, bS = 0, totA = 0, totT = 0, totS = 0;
+#pragma unroll
+        for (int k = 0; k < EMIT_THREADS / 32; ++k) {
+            const u32 a = s_w[pb][0][k], t = s_w[pb][1][k], s2 = s_w[pb][2][k];
+            totA += a; totT += t; totS += s2;
+            if (k < wid) { bA += a; bT += t; bS += s2; }
+        }
+        const u32 exA = bA + iA - vA, exT = bT + iT - vT, exS = bS + iS - vS;
         if (wid == 0) {
             u64 agg = (u64)(totA & 0xFFFFu) | ((u64)(totA >> 16) << 31);
             u64 b = lookback_exclusive(p.desc_emitA, tile, 0, agg, lane);
-            if (lane == 0) { s_baseA = b; if (tile == n_tiles - 1) { u64 t = b + agg; st->w_groups = (u32)(t & 0x7FFFFFFFu); st->w_emit = (u32)(t >> 31); } }
+            if (lane == 0) { s_baseA[pb] = b; if (tile == n_tiles - 1) { u64 t = b + agg; st->w_groups = (u32)(t & 0x7FFFFFFFu); st->w_emit = (u32)(t >> 31); } }
         } else if (wid == 1) {
             u64 agg = (u64)totT | ((u64)totS << 31);
             u64 b = lookback_exclusive(p.desc_emitB, tile, 0, agg, lane);
-            if (lane == 0) { s_baseB = b; if (tile == n_tiles - 1) { u64 t = b + agg; st->w_text = (u32)(t & 0x7FFFFFFFu); st->w_sam = (u32)(t >> 31); } }
+            if (lane == 0) { s_baseB[pb] = b; if (tile == n_tiles - 1) { u64 t = b + agg; st->w_text = (u32)(t & 0x7FFFFFFFu); st->w_sam = (u32)(t >> 31); } }
         }
         __syncthreads();
-        const u64 bA = s_baseA, bB = s_baseB;
-        const u32 g_idx = (u32)(bA & 0x7FFFFFFFu) + (exA & 0xFFFFu);          // processed-group index inside the window
-        const u32 e_idx = (u32)(bA >> 31) + (exA >> 16);
-        const u64 t_off = base_text + (bB & 0x7FFFFFFFu), s_off = base_sam + (bB >> 31);
-        if (proc && g.status == ST_SELFCIRCLE) {                               // for the thread-0-share emulation on the host
-            u32 slot = atomicAdd(&st->sc_count, 1u);
-            if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
-        }
-        if (emit && p.emit_packed) {
-            u64 o = base_pairs + e_idx;
-            if (o < p.out_pairs_cap) {
-                mk_pair r; r.pos1 = g.posA; r.pos2 = g.posB; r.chr1 = g.chrA; r.chr2 = g.chrB; r.strands = g.strands;
-                r.cls = (u8)(g.status - ST_TRANS); r.lane = p.lane;
-                p.out_pairs[o] = r;
-            } else atomicOr(&st->err, S2P_ERR_PAIRS);
-        }
-        if (p.emit_text && totT) {
-            if (t_off + totT > p.out_text_cap) { if (tid == 0) atomicOr(&st->err, S2P_ERR_TEXT); }
-            else if (totT <= EMIT_STAGE) {
-                // stage the tile's lines in shared memory with the destination's 16-byte phase, then flush with wide stores
-                const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);
-                if (emit) { PtrSink s{s_stage + phase + exT}; write_pair_line(p, ws, g, s); }
-                __syncthreads();
-                char *dst = p.out_text + t_off;
-                const u32 head = phase ? (16u - phase < totT ? 16u - phase : totT) : 0u;
-                if ((u32)tid < head) dst[tid] = s_stage[phase + tid];
-                const u32 body = (totT - head) >> 4;
-                for (u32 w = tid; w < body; w += EMIT_THREADS)
-                    *(uint4 *)(dst + head + ((u64)w << 4)) = *(const uint4 *)(s_stage + phase + head + (w << 4));
-                const u32 tail0 = head + (body << 4);
-                if (tail0 + tid < totT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
-            } else if (emit) {
-                PtrSink s{p.out_text + t_off + exT}; write_pair_line(p, ws, g, s);
+        const u64 gA = s_baseA[pb], gB = s_baseB[pb];
+        u32 g_idx = (u32)(gA & 0x7FFFFFFFu) + (exA & 0xFFFFu);          // processed-group index inside the window
+        u32 e_idx = (u32)(gA >> 31) + (exA >> 16);
+        const u64 t_off = base_text + (gB & 0x7FFFFFFFu);
+        u64 s_run = base_sam + (gB >> 31) + exS;
+        const bool text_fits = t_off + totT <= p.out_text_cap;
+        const bool staged = totT <= EMIT_STAGE;
+        const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);       // stage with the destination's 16-byte phase
+        if (p.emit_text && totT && !text_fits && tid == 0) atomicOr(&st->err, S2P_ERR_TEXT);
+        u32 t_run = exT;
+#pragma unroll
+        for (int k = 0; k < EMIT_ITEMS; ++k) {
+            if (!proc[k]) continue;
+            const u32 i = i0 + k;
+            if (g[k].status == ST_SELFCIRCLE) {                          // for the thread-0-share emulation on the host
+                u32 slot = atomicAdd(&st->sc_count, 1u);
+                if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
             }
-        }
-        if (p.write_sam && emit) {
-            // destination of every kept line of the group; K5 does the copying
-            u64 o = s_off + exS;
-            if (o + g.sam_len > p.out_sam_cap) atomicOr(&st->err, S2P_ERR_SAM);
-            else {
-                u32 k = i;
-                while (true) {
-                    p.sam_dst[k] = (u32)(o - base_sam);
-                    o += p.rec[k].line_len + 1;
-                    if (k == g.last_line) break;
-                    ++k; while (!(p.lmeta[k] & LM_KEEP)) ++k;
+            ++g_idx;
+            if (!emit[k]) continue;
+            if (p.emit_packed) {
+                u64 o = base_pairs + e_idx;
+                if (o < p.out_pairs_cap) {
+                    mk_pair r; r.pos1 = g[k].posA; r.pos2 = g[k].posB; r.chr1 = g[k].chrA; r.chr2 = g[k].chrB; r.strands = g[k].strands;
+                    r.cls = (u8)(g[k].status - ST_TRANS); r.lane = p.lane;
+                    p.out_pairs[o] = r;
+                } else atomicOr(&st->err, S2P_ERR_PAIRS);
+            }
+            ++e_idx;
+            if (p.emit_text && text_fits) {
+                write_pair_line(p, ws, g[k], staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
+                t_run += g[k].text_len;
+            }
+            if (p.write_sam) {                                           // destination of every kept line of the group; K5 copies
+                if (s_run + g[k].sam_len > p.out_sam_cap) atomicOr(&st->err, S2P_ERR_SAM);
+                else {
+                    u64 o = s_run; u32 q = i;
+                    while (true) {
+                        p.sam_dst[q] = (u32)(o - base_sam);
+                        o += line_len_of(p, q) + 1;
+                        if (q == g[k].last_line) break;
+                        ++q; while (!(p.lmeta[q] & LM_KEEP)) ++q;
+                    }
                 }
+                s_run += g[k].sam_len;
             }
         }
-        __syncthreads();
+        if (p.emit_text && totT && text_fits && staged) {
+            __syncthreads();
+            char *dst = p.out_text + t_off;
+            const u32 head = phase ? (16u - phase < totT ? 16u - phase : totT) : 0u;
+            if ((u32)tid < head) dst[tid] = s_stage[phase + tid];
+            const u32 body = (totT - head) >> 4;
+            for (u32 w = tid; w < body; w += EMIT_THREADS)
+                st_stream_v4((uint4 *)(dst + head + ((u64)w << 4)), *(const uint4 *)(s_stage + phase + head + (w << 4)));
+            const u32 tail0 = head + (body << 4);
+            if (tail0 + tid < totT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
+            __syncthreads();                                             // the stage is reused by the next tile
+        }
     }
 }
 

@@ -136,3 +136,25 @@ def test_key_dedup_all_equal_and_sorted_inputs():
         nu = C.c_uint64()
         L.check(L.L.mk_dedup_keys_device(0, d.data_ptr(), n, keep.data_ptr(), C.byref(nu), None))
         assert nu.value == len(first_idx) and np.array_equal(keep.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("n,seed,lanes,res", [(1, 1, 1, 5000), (300000, 3, 1, 5000), (1000003, 4, 3, 1000), (200000, 5, 1, 2500000)])
+def test_one_sort_dedup_bin_matches_oracle(oracle, n, seed, lanes, res):
+    """mk_pairs_dedup_bin_device: same kept set as the coordinate dedup, same COO as binning the kept pairs."""
+    p = random_pairs(n, seed, lanes=lanes)
+    op = as_oracle_pairs(p)
+    keep, kept = oracle.coord_dedup(op, n)
+    b1, b2, ct = oracle.bin_coo(op, n, keep, HG38_LEN, res)
+    ws = mk.PairsWorkspace(n)
+    d = to_dev(p)
+    o1 = torch.empty(n, dtype=torch.int32, device="cuda"); o2 = torch.empty_like(o1); oc = torch.empty_like(o1)
+    got, nnz = ws.dedup_bin(d.data_ptr(), n, HG38_LEN, res, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n, max_lane=lanes - 1)
+    assert got == kept and nnz == len(b1)
+    assert o1[:nnz].cpu().numpy().astype(np.uint32).tolist() == b1
+    assert o2[:nnz].cpu().numpy().astype(np.uint32).tolist() == b2
+    assert oc[:nnz].cpu().numpy().astype(np.uint32).tolist() == ct
+    out = np.frombuffer(d[:got * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+    exp = p[np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
+    key = lambda a: np.lexsort((a["strands"], a["pos2"], a["chr2"], a["pos1"], a["chr1"], a["lane"]))
+    assert np.array_equal(out[key(out)], exp[key(exp)])          # same set of kept pairs, fields restored exactly
+    ws.close()
