@@ -327,7 +327,10 @@ def measure_e2e(torch, mk, np, args, local, ws):
     W = 256 << 20
     s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W), HG38)
 
+    phases = {"stream_ms": 0.0, "drain_finish_ms": 0.0, "pairs_ms": 0.0}
+
     def once():
+        t_a = time.perf_counter()
         s2p.reset()
         tl = pl = 0
         off = 0
@@ -337,6 +340,7 @@ def measure_e2e(torch, mk, np, args, local, ws):
             off += m
             a, b = s2p.pull_into(out_text.data_ptr() + tl, out_text.numel() - tl, out_pairs.data_ptr() + pl * 16, E + 1024 - pl)
             tl += a; pl += b
+        t_b = time.perf_counter()
         while True:
             a, b = s2p.pull_into(out_text.data_ptr() + tl, out_text.numel() - tl, out_pairs.data_ptr() + pl * 16, E + 1024 - pl)
             tl += a; pl += b
@@ -344,12 +348,17 @@ def measure_e2e(torch, mk, np, args, local, ws):
                 break
         st = s2p.finish()
         assert st.pairs == pl
+        t_c = time.perf_counter()
         kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, HG38_LEN, RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), E + 1024)
+        t_d = time.perf_counter()
+        phases["stream_ms"] += (t_b - t_a) * 1e3; phases["drain_finish_ms"] += (t_c - t_b) * 1e3; phases["pairs_ms"] += (t_d - t_c) * 1e3
         return pl, tl, kept, nnz
 
     for _ in range(2):
         once()
     torch.cuda.synchronize()
+    for k in phases:
+        phases[k] = 0.0
     t0 = time.perf_counter()
     reps = max(2, min(args.steps, 5))
     for _ in range(reps):
@@ -358,7 +367,7 @@ def measure_e2e(torch, mk, np, args, local, ws):
     sec = (time.perf_counter() - t0) / reps
     s2p.close()
     return {"value": pl / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(nb + pl * 16), "d2h_bytes_per_step": int(tl + pl * 16 + kept * 16 + nnz * 12),
-            "read_groups": E, "ms_per_step": sec * 1e3,
+            "read_groups": E, "ms_per_step": sec * 1e3, "phases_ms": {k: v / reps for k, v in phases.items()},
             "api": "mk_s2p_push/pull/pull_packed/finish + mk_pairs_dedup_bin_host, host pinned buffers, wall clock incl. all copies"}
 
 

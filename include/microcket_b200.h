@@ -88,7 +88,9 @@ void mk_s2p_default_cfg(mk_s2p_cfg *);
  * order is bytewise like std::string::compare).  Pre-registered names get ids 0..n-1. */
 int  mk_s2p_create(const mk_s2p_cfg *, const char *const *chrom_names, int n_chrom, mk_ctx **);
 /* Host streaming API (what the sam2pairs CLI uses).  `sam_bytes` may be split anywhere; the
- * library carries partial lines and the trailing read group over to the next call. */
+ * library carries partial lines and the trailing read group over to the next call.  Pageable memory is copied before
+ * the call returns.  Memory that is already pinned (cudaHostAlloc / cudaHostRegister) is DMA'd straight from the
+ * caller's buffer, asynchronously: it must stay valid and unchanged until mk_s2p_finish (or mk_s2p_reset) returns. */
 int  mk_s2p_push(mk_ctx *, const char *sam_bytes, size_t n, int is_last);
 /* Drains produced output; *n_out == 0 and *n_out2 == 0 when nothing is pending.  Either buffer may be NULL. */
 int  mk_s2p_pull(mk_ctx *, char *pairs_out, size_t cap, size_t *n_out,

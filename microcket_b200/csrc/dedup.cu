@@ -48,7 +48,7 @@ __global__ void k_fq_begin(FqParams p, u32 n_desc, u64 total, u32 is_last) {
 }
 
 __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_fq_scan(FqParams p) {
-    scan_lines_body(p.buf, 0, p.st->total, 0, p.nl_pos, p.cap_lines, p.desc, &p.st->n_lines, &p.st->err, FQ_ERR_LINES, &p.st->ticket);
+    scan_lines_body<4>(p.buf, 0, p.st->total, p.nl_pos, p.cap_lines, p.desc, &p.st->n_lines, &p.st->err, FQ_ERR_LINES);
 }
 
 __device__ __forceinline__ u32 fq_line_start(const u32 *nl, u32 line) { return line ? nl[line - 1] + 1 : 0; }
@@ -337,8 +337,8 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     p.hskip1 = c->cfg.hskip1; p.klen1 = c->cfg.klen1; p.hskip2 = c->cfg.hskip2; p.klen2 = c->cfg.klen2;
     MK_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, n, cudaMemcpyHostToDevice, s));
     k_fq_begin<<<(c->n_desc + 255) / 256, 256, 0, s>>>(p, c->n_desc, n, is_last ? 1u : 0u);
-    int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fq_scan, S2P_SCAN_THREADS, 0);
-    k_fq_scan<<<c->sms * std::max(1, std::min(occ, 4)), S2P_SCAN_THREADS, 0, s>>>(p);
+    int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fq_scan, S2P_SCAN_THREADS, 4 * 8192);
+    k_fq_scan<<<c->sms * std::max(1, std::min(occ, 4)), S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
     k_fq_keys<<<c->sms * 8, 256, 0, s>>>(p);
     c->launches_generic += 3;
     // the pair count lives on the device; the sort is sized by a host read of it (one small sync per window)

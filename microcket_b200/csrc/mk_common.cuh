@@ -158,6 +158,38 @@ __device__ __forceinline__ u64 lookback_exclusive(u64 *desc, int tile, int first
     return excl;
 }
 
+// ---- wave scan: exclusive prefix for a persistent grid that walks tiles round-robin (tile = first + blockIdx + k * grid).
+// All CTAs are on wave k together, so a chained look-back degenerates into an INC that crawls 32 tiles per L2 round trip
+// across the wave.  Here every tile sums the aggregates of its predecessors INSIDE the wave with all loads in flight at
+// once (one round trip) and adds the wave's base, which the wave's last CTA publishes for the next wave.
+// agg[rel] : per-tile aggregate descriptors (rel = tile - first_tile), base[w] : per-wave exclusive prefix; both zeroed.
+#define WS_MAX_PER_LANE 16        // supports grids of up to 512 CTAs
+__device__ __forceinline__ u64 wave_scan_exclusive(u64 *agg, u64 *base, int rel, int grid, u64 aggregate, int lane, bool last_of_wave) {
+    const int w = rel / grid, b = rel - w * grid;
+    if (lane == 0) st_volatile_u64(&agg[rel], LB_AGG | aggregate);
+    const u64 *row = agg + (u64)w * grid;
+    u64 d[WS_MAX_PER_LANE];
+#pragma unroll
+    for (int k = 0; k < WS_MAX_PER_LANE; ++k) { const int j = lane + 32 * k; d[k] = j < b ? ld_volatile_u64(&row[j]) : LB_AGG; }
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < WS_MAX_PER_LANE; ++k) {
+        const int j = lane + 32 * k;
+        while ((d[k] >> 62) == 0) d[k] = ld_volatile_u64(&row[j]);     // that predecessor has not counted yet
+        sum += LB_VAL(d[k]);
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    u64 wb = 0;
+    if (w > 0) {
+        if (lane == 0) { u64 x; do { x = ld_volatile_u64(&base[w]); } while ((x >> 62) == 0); wb = LB_VAL(x); }
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+    }
+    const u64 excl = wb + sum;
+    if (last_of_wave && lane == 0) st_volatile_u64(&base[w + 1], LB_INC | (excl + aggregate));
+    return excl;
+}
+
 // Two-step form for kernels that have other work to do between publishing their aggregate and needing the prefix.
 __device__ __forceinline__ void lookback_publish(u64 *desc, int tile, int first_tile, u64 aggregate) {
     st_volatile_u64(&desc[tile], (tile == first_tile ? LB_INC : LB_AGG) | aggregate);

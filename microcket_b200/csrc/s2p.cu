@@ -33,8 +33,8 @@ struct S2PCtx : mk_ctx {
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
-    int grid_scan = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0;
-    bool fused = true;
+    int grid_scan = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0, scan_nt = 4;
+    bool fused = false;
     u64 launches = 0;
     // host streaming state
     size_t stage_fill = 0;                         // bytes staged in the next window's pinned buffer
@@ -88,6 +88,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
     p.rec = c->d_rec.as<LineRec>(); p.res = c->d_res.as<GroupRes>(); p.sam_dst = c->d_samdst.as<u32>();
     p.desc_scan = c->d_desc.as<u64>(); p.desc_emitA = p.desc_scan + c->n_desc; p.desc_emitB = p.desc_emitA + c->n_desc;
+    p.wave_scan = p.desc_emitB + c->n_desc; p.wave_emitA = p.wave_scan + c->n_desc; p.wave_emitB = p.wave_emitA + c->n_desc;
     p.chr = c->d_chr.as<ChrSlot>(); p.chr_mask = c->chr_slots - 1; p.id_to_slot = c->d_id2slot.as<int>(); p.chr_cap = c->chr_cap;
     p.sc_list = sc_list; p.sc_cap = sc_cap;
     p.out_text = out_text; p.out_text_cap = out_text ? text_cap : 0;
@@ -112,7 +113,8 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
         mark(1); mark(2);                                        // reported under k_scan_lines; k_parse stays 0
         c->launches -= 1;
     } else {
-        k_scan_lines<<<c->grid_scan, S2P_SCAN_THREADS, 0, s>>>(p);
+        if (c->scan_nt == 8) k_scan_lines<8><<<c->grid_scan8, S2P_SCAN_THREADS, 8 * 8192, s>>>(p);
+        else k_scan_lines<4><<<c->grid_scan, S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
         mark(1);
         k_parse<<<c->grid_gs, 256, 0, s>>>(p);
         mark(2);
@@ -188,7 +190,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     c->W = (c->W + 15) & ~(size_t)15;
     c->in_cap = S2P_CARRY + c->W + 64;
     c->cap_lines = (u32)((S2P_CARRY + c->W) / 32 + 1024);
-    c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->cap_lines / EMIT_TILE + 4);
+    c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->cap_lines / EMIT_BIG + 4);
     c->sc_cap = c->cap_lines / 2 + 16; c->sc_cap_dev = 0;
     c->chr_cap = 16384; c->chr_slots = 32768;
     int rc = MK_OK;
@@ -197,7 +199,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_nl.alloc((size_t)c->cap_lines * 4)); A(c->d_lmeta.alloc(c->cap_lines)); A(c->d_rec.alloc((size_t)c->cap_lines * sizeof(LineRec)));
     A(c->d_res.alloc((size_t)c->cap_lines * sizeof(GroupRes)));
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
-    A(c->d_desc.alloc((size_t)c->n_desc * 3 * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
+    A(c->d_desc.alloc((size_t)c->n_desc * 6 * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
@@ -229,15 +231,19 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaMemcpy(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice);
     // grids: the two look-back kernels need every CTA resident
     int sms = mk_sm_count(cfg->device), occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines, S2P_SCAN_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<4>, S2P_SCAN_THREADS, 4 * 8192);
     c->grid_scan = sms * std::max(1, std::min(occ, 4));
+    cudaFuncSetAttribute(k_scan_lines<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<8>, S2P_SCAN_THREADS, 8 * 8192);
+    c->grid_scan8 = sms * std::max(1, std::min(occ, 4));
+    if (getenv("MICROCKET_SCAN_NT")) c->scan_nt = atoi(getenv("MICROCKET_SCAN_NT"));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, std::min(occ, 4));
     c->grid_gs = sms * 8;
     cudaFuncSetAttribute(k_scan_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_parse, FZ_THREADS, FZ_SMEM);
     c->grid_fused = sms * std::max(1, occ);
-    c->fused = !(getenv("MICROCKET_UNFUSED") && atoi(getenv("MICROCKET_UNFUSED")));
+    c->fused = getenv("MICROCKET_FUSED") && atoi(getenv("MICROCKET_FUSED"));   // single-pass scan+parse: correct, but latency-bound so far
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mk_set_error("mk_s2p_create: %s", cudaGetErrorString(e)); delete c; return MK_ERR_CUDA; }
     *out = c;
@@ -445,7 +451,7 @@ extern "C" int mk_s2p_push(mk_ctx *x, const char *bytes, size_t n, int is_last) 
         }
         c->finished_input = true;
     }
-    if (last_direct) MK_CUDA(cudaEventSynchronize(last_direct));       // the caller may reuse its buffer when we return
+    (void)last_direct;   // pinned caller memory is read asynchronously: it must stay valid until the window's output was pulled (or finish)
     return MK_OK;
 }
 

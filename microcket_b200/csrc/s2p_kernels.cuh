@@ -82,6 +82,7 @@ struct S2PParams {
     GroupRes *res;
     u32 *sam_dst;
     u64 *desc_scan, *desc_emitA, *desc_emitB;
+    u64 *wave_scan, *wave_emitA, *wave_emitB;   // per-wave bases of the wave scans
     ChrSlot *chr; u32 chr_mask; int *id_to_slot; u32 chr_cap;
     u64 *sc_list; u32 sc_cap;
     char *out_text; u64 out_text_cap;
@@ -96,7 +97,7 @@ struct S2PParams {
 // ------------------------------------------------------------------------------------------------ begin / end
 static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_desc) { p.desc_scan[i] = 0; p.desc_emitA[i] = 0; p.desc_emitB[i] = 0; }
+    if (i < n_desc) { p.desc_scan[i] = 0; p.desc_emitA[i] = 0; p.desc_emitB[i] = 0; p.wave_scan[i] = 0; p.wave_emitA[i] = 0; p.wave_emitB[i] = 0; }
     if (i == 0) {
         WinState *s = p.st;
         s->ws = s->cursor;
@@ -148,68 +149,79 @@ __device__ __forceinline__ u32 nl_flags16(const uint4 &w) { return (nl_y(w.x) >>
 __device__ __forceinline__ u32 perm_bit_of_byte(u32 q) { return 8u * (q & 3u) + (q >> 2); }       // byte q (0..15) -> bit
 __device__ __forceinline__ u32 byte_of_perm_bit(u32 b) { return ((b & 7u) << 2) | (b >> 3); }     // bit -> byte
 
-// Tiles go round-robin over a fully resident grid (tile = first + blockIdx + k * gridDim).  Claiming tiles with an
-// atomic ticket was measured on B200 and is slower here (14.9 ms vs 9.8 ms per 19.8 GB): kept only behind `dynamic`.
-__device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, const u64 we, const int first_tile,
-                                                u32 *nl_pos, const u32 cap_lines, u64 *desc, u32 *n_lines_out, u32 *err_out, u32 err_bit,
-                                                u32 *ticket, const bool dynamic = true) {
-    __shared__ __align__(16) u32 s_z[2][S2P_TILE_BYTES / 16];
-    __shared__ u32 s_wtot[2][S2P_SCAN_THREADS / 32];
+// Tiles go round-robin over a fully resident grid (tile = first + blockIdx + k * gridDim); a tile is S2P_NT sub-tiles of
+// 32 KiB = 128 KiB, so the grid-wide dependency of the look-back (every wave waits for its slowest CTA) and the three
+// block barriers are paid once per 128 KiB, and the sub-tiles' loads are software-pipelined so HBM stays busy.
+// (Measured on B200: 32 KiB tiles 2.0 TB/s; atomic tickets and a wave-parallel prefix were both slower.)
+template <int S2P_NT>
+__device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, const u64 we,
+                                                u32 *nl_pos, const u32 cap_lines, u64 *desc, u32 *n_lines_out, u32 *err_out, u32 err_bit) {
+    extern __shared__ __align__(16) u32 s_z_dyn[];                     // S2P_NT * 2048 words (dynamic: 64 KiB for NT = 8)
+    u32 (*s_z)[S2P_TILE_BYTES / 16] = (u32 (*)[S2P_TILE_BYTES / 16])s_z_dyn;
+    __shared__ u32 s_wtot[2][S2P_NT][S2P_SCAN_THREADS / 32];
     __shared__ u32 s_base[2];
-    __shared__ int s_next[2];
+    constexpr u64 S2P_SUPER = (u64)S2P_NT * S2P_TILE_BYTES;
     if (we <= ws) return;
-    const int last_tile = (int)((we - 1) / S2P_TILE_BYTES);
+    const int first_tile = (int)(ws / S2P_SUPER), last_tile = (int)((we - 1) / S2P_SUPER);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_next[0] = dynamic ? first_tile + (int)atomicAdd(ticket, 1u) : first_tile + (int)blockIdx.x;
-    __syncthreads();
-    int tile = s_next[0];
+    u64 *dsc = desc - first_tile;
     uint4 w[8];
-    auto load_tile = [&](int t) {
-        const u64 tbase = (u64)t * S2P_TILE_BYTES;
-        const uint4 *src = (const uint4 *)(buf + tbase);
-        const bool interior = tbase >= ws && tbase + S2P_TILE_BYTES <= we;
+    auto load_sub = [&](u64 sbase) {                                   // one 32 KiB sub-tile into registers
+        const uint4 *src = (const uint4 *)(buf + sbase);
+        const bool interior = sbase >= ws && sbase + S2P_TILE_BYTES <= we;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (interior) w[j] = ld_stream_v4(src + j * S2P_SCAN_THREADS + tid);
             else {
-                u64 off = tbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
+                const u64 off = sbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
                 w[j] = (off < we && off + 16 > ws) ? ld_stream_v4(src + j * S2P_SCAN_THREADS + tid) : make_uint4(0, 0, 0, 0);
             }
         }
     };
-    if (tile <= last_tile) load_tile(tile);
-    int pb = 0;
-    while (tile <= last_tile) {
-        const u64 tbase = (u64)tile * S2P_TILE_BYTES;
-        const bool interior = tbase >= ws && tbase + S2P_TILE_BYTES <= we;
-        if (tid == 0) s_next[pb ^ 1] = dynamic ? first_tile + (int)atomicAdd(ticket, 1u) : tile + (int)gridDim.x;   // read after the next barrier
+    int tile = first_tile + (int)blockIdx.x;
+    if (tile <= last_tile) load_sub((u64)tile * S2P_SUPER);
+    for (int pb = 0; tile <= last_tile; tile += gridDim.x, pb ^= 1) {
+        const u64 tbase = (u64)tile * S2P_SUPER;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            u32 z = nl_flags16(w[j]);
-            if (!interior && z) {                                     // window edges: drop flags of bytes outside [ws, we)
-                const u64 off = tbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
-                u32 keep = 0;
-                for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
-                z &= keep;
+        for (int k = 0; k < S2P_NT; ++k) {
+            const u64 sbase = tbase + (u64)k * S2P_TILE_BYTES;
+            const bool interior = sbase >= ws && sbase + S2P_TILE_BYTES <= we;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                u32 z = nl_flags16(w[j]);
+                if (!interior && z) {                                 // window edges: drop flags of bytes outside [ws, we)
+                    const u64 off = sbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
+                    u32 keep = 0;
+                    for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
+                    z &= keep;
+                }
+                s_z[k][j * S2P_SCAN_THREADS + tid] = z;
             }
-            s_z[pb][j * S2P_SCAN_THREADS + tid] = z;
+            // next sub-tile (of this tile, or the first one of this CTA's next tile) while the flags are being used
+            if (k + 1 < S2P_NT) load_sub(sbase + S2P_TILE_BYTES);
+            else if (tile + (int)gridDim.x <= last_tile) load_sub((u64)(tile + gridDim.x) * S2P_SUPER);
         }
         __syncthreads();
-        const int next_tile = s_next[pb ^ 1];
-        if (next_tile <= last_tile) load_tile(next_tile);             // prefetch this CTA's next tile
-        const uint4 za = ((const uint4 *)s_z[pb])[2 * tid], zb = ((const uint4 *)s_z[pb])[2 * tid + 1];   // bytes [tid*128, +128)
-        const u32 zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-        u32 cnt = 0;
+        u32 cnt[S2P_NT], inc[S2P_NT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cnt += __popc(zz[i]);
-        const u32 inc = warp_incl_scan(cnt, lane);
-        if (lane == 31) s_wtot[pb][wid] = inc;
+        for (int k = 0; k < S2P_NT; ++k) {
+            const uint4 za = ((const uint4 *)s_z[k])[2 * tid], zb = ((const uint4 *)s_z[k])[2 * tid + 1];   // bytes [tid*128, +128) of sub-tile k
+            cnt[k] = __popc(za.x) + __popc(za.y) + __popc(za.z) + __popc(za.w) + __popc(zb.x) + __popc(zb.y) + __popc(zb.z) + __popc(zb.w);
+            inc[k] = warp_incl_scan(cnt[k], lane);
+            if (lane == 31) s_wtot[pb][k][wid] = inc[k];
+        }
         __syncthreads();
-        u32 before = 0, total = 0;
+        u32 pre[S2P_NT], total = 0;                                     // exclusive prefix of this thread's block in sub-tile k, inside the tile
 #pragma unroll
-        for (int k = 0; k < S2P_SCAN_THREADS / 32; ++k) { const u32 v = s_wtot[pb][k]; total += v; if (k < wid) before += v; }
+        for (int k = 0; k < S2P_NT; ++k) {
+            u32 before = 0, sub = 0;
+#pragma unroll
+            for (int q = 0; q < S2P_SCAN_THREADS / 32; ++q) { const u32 v = s_wtot[pb][k][q]; sub += v; if (q < wid) before += v; }
+            pre[k] = total + before + inc[k] - cnt[k];
+            total += sub;
+        }
         if (wid == 0) {
-            const u64 b = lookback_exclusive(desc - first_tile, tile, first_tile, total, lane);
+            const u64 b = lookback_exclusive(dsc, tile, first_tile, total, lane);
             if (lane == 0) {
                 s_base[pb] = (u32)b;
                 if (tile == last_tile) {
@@ -220,9 +232,14 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
             }
         }
         __syncthreads();
-        if (cnt) {
-            u32 idx = s_base[pb] + before + inc - cnt;
-            const u32 rel = (u32)(tbase + (u64)tid * 128 - ws);        // may wrap for bytes before ws: those have no flags
+        const u32 base = s_base[pb];
+#pragma unroll
+        for (int k = 0; k < S2P_NT; ++k) {
+            if (!cnt[k]) continue;
+            const uint4 za = ((const uint4 *)s_z[k])[2 * tid], zb = ((const uint4 *)s_z[k])[2 * tid + 1];
+            const u32 zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+            u32 idx = base + pre[k];
+            const u32 rel = (u32)(tbase + (u64)k * S2P_TILE_BYTES + (u64)tid * 128 - ws);   // may wrap for bytes before ws: those have no flags
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 u32 z = zz[i];
@@ -237,13 +254,14 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
                 }
             }
         }
-        tile = next_tile; pb ^= 1;
+        __syncthreads();                                               // s_z is rewritten by the next tile
     }
 }
 
-static __global__ void __launch_bounds__(S2P_SCAN_THREADS) k_scan_lines(S2PParams p) {
+template <int NT>
+static __global__ void __launch_bounds__(S2P_SCAN_THREADS, 3) k_scan_lines(S2PParams p) {
     WinState *st = p.st;
-    scan_lines_body(p.buf, st->ws, st->we, (int)st->first_tile, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES, &st->tickets[0], p.dyn_tickets != 0);
+    scan_lines_body<NT>(p.buf, st->ws, st->we, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
 }
 
 // ------------------------------------------------------------------------------------------------ chromosome table
@@ -359,18 +377,221 @@ __device__ __forceinline__ u32 parse_line(const S2PParams &p, R &r, R &q, const 
     return meta;
 }
 
+static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b);
+
+// ---- word-at-a-time fast path -------------------------------------------------------------------------------------
+// Well-formed lines (single tabs between the first six fields, nothing else below 0x21, digits where numbers belong,
+// RNAME <= 8 bytes) are tokenised with SWAR on 16-byte words instead of byte loops; anything else returns false and goes
+// through parse_line, so the result is identical by construction.
+__device__ __forceinline__ u32 lt21_y(u32 x) {                       // 0x80 in every byte < 0x21
+    const u32 t = (x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu;
+    return ~(t | x) & 0x80808080u;
+}
+__device__ __forceinline__ u32 lt21_mask16(const uint4 &w) {         // bit q set iff byte q of the word is < 0x21 (byte order)
+    return gather_flags4(lt21_y(w.x)) | (gather_flags4(lt21_y(w.y)) << 4) | (gather_flags4(lt21_y(w.z)) << 8) | (gather_flags4(lt21_y(w.w)) << 12);
+}
+// Fetchers: aligned 16- and 8-byte loads from global memory, or from the shared-memory copy of a tile where it covers them
+struct GlobalFetch {
+    const char *buf;
+    __device__ __forceinline__ uint4 ld16(u64 a) const { return __ldg((const uint4 *)(buf + a)); }
+    __device__ __forceinline__ u64 ld8(u64 a) const { return __ldg((const u64 *)(buf + a)); }
+    __device__ __forceinline__ int byte(u64 a) const { return (int)(unsigned char)buf[a]; }
+};
+struct TileFetch {
+    const char *buf, *sm; u64 tlo, thi;
+    __device__ __forceinline__ uint4 ld16(u64 a) const { return (a >= tlo && a + 16 <= thi) ? *(const uint4 *)(sm + (a - tlo)) : __ldg((const uint4 *)(buf + a)); }
+    __device__ __forceinline__ u64 ld8(u64 a) const { return (a >= tlo && a + 8 <= thi) ? *(const u64 *)(sm + (a - tlo)) : __ldg((const u64 *)(buf + a)); }
+    __device__ __forceinline__ int byte(u64 a) const { return (a >= tlo && a < thi) ? (int)(unsigned char)sm[a - tlo] : (int)(unsigned char)buf[a]; }
+};
+// the thread's own line prefix (7 x 16 bytes from A) staged in a shared-memory column: field extraction at data-dependent
+// offsets without going back to L1/L2
+struct LineFetch {
+    const char *buf; const uint4 *col; u64 A;                           // col[j * 256] = bytes [A + 16 j, A + 16 j + 16)
+    __device__ __forceinline__ uint4 ld16(u64 a) const { return (a >= A && a + 16 <= A + 112) ? col[((a - A) >> 4) * 256] : __ldg((const uint4 *)(buf + a)); }
+    __device__ __forceinline__ u64 ld8(u64 a) const {
+        return (a >= A && a + 8 <= A + 112) ? ((const u64 *)&col[((a - A) >> 4) * 256])[(a >> 3) & 1] : __ldg((const u64 *)(buf + a));
+    }
+    __device__ __forceinline__ int byte(u64 a) const { return (int)((ld8(a & ~(u64)7) >> (8 * (a & 7))) & 0xFF); }
+};
+template <class F>
+__device__ __forceinline__ u64 fetch8(const F &f, u64 abs) {          // 8 bytes at any offset, from aligned loads
+    const u64 a8 = abs & ~(u64)7;
+    const u32 sh = (u32)(abs & 7) * 8;
+    const u64 lo = f.ld8(a8);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (f.ld8(a8 + 8) << (64 - sh));
+}
+// QNAME of the line at `a` (length t0, already tokenised) equal to the first token of the line at `pa`?
+template <class F>
+__device__ __forceinline__ bool qname_eq_fetch(const F &f, u64 a, u64 pa, u32 t0) {
+    bool eq = true;
+    for (u32 k = 0; k < t0 && eq; k += 8) {
+        u64 x = fetch8(f, a + k), y = fetch8(f, pa + k);
+        if (t0 - k < 8) { const u64 m = (1ull << (8 * (t0 - k))) - 1; x &= m; y &= m; }
+        eq = x == y;
+    }
+    return eq && is_ws(f.byte(pa + t0));
+}
+__device__ __forceinline__ u32 pop_lowest128(u32 &m0, u32 &m1, u32 &m2, u32 &m3) {
+    if (m0) { const u32 b = __ffs(m0) - 1; m0 &= m0 - 1; return b; }
+    if (m1) { const u32 b = __ffs(m1) - 1; m1 &= m1 - 1; return 32 + b; }
+    if (m2) { const u32 b = __ffs(m2) - 1; m2 &= m2 - 1; return 64 + b; }
+    if (m3) { const u32 b = __ffs(m3) - 1; m3 &= m3 - 1; return 96 + b; }
+    return 255;
+}
+// decimal field of `len` (1..10) characters starting at abs; false if a non-digit is found
+template <class F>
+__device__ __forceinline__ bool dec_field(const F &buf, u64 abs, u32 len, u32 &out) {
+    u64 x = fetch8(buf, abs);
+    u32 v = 0; bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if ((u32)k < len) { const u32 d = (u32)((x >> (8 * k)) & 0xFF) - '0'; ok &= d <= 9u; v = v * 10u + d; }
+    }
+    if (len > 8) {
+        x = fetch8(buf, abs + 8);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if ((u32)(8 + k) < len) { const u32 d = (u32)((x >> (8 * k)) & 0xFF) - '0'; ok &= d <= 9u; v = v * 10u + d; }
+        }
+    }
+    out = v;
+    return ok;
+}
+
+struct FastTok { u32 t0; u64 q[5]; bool ok; };                       // QNAME length and its first 40 bytes (zero padded)
+
+template <class F, bool WANT_Q>
+__device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, const u64 a, const u64 limit, FastTok &tok, LineRec &rec, u32 &meta) {
+    tok.ok = false;
+    if (a + 144 > limit) return false;
+    const u64 A = a & ~(u64)15;
+    const u32 s = (u32)(a - A);
+    uint4 w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = f.ld16(A + 16 * j);
+    if ((char)((w[0].x >> 0) & 0xFF) == '@' && s == 0) return false;   // cheap early-out; the exact test is below
+    u32 m0 = lt21_mask16(w[0]) | (lt21_mask16(w[1]) << 16), m1 = lt21_mask16(w[2]) | (lt21_mask16(w[3]) << 16);
+    u32 m2 = lt21_mask16(w[4]) | (lt21_mask16(w[5]) << 16), m3 = lt21_mask16(w[6]);
+    if (s) {                                                          // bit j <-> byte a + j
+        m0 = __funnelshift_r(m0, m1, s); m1 = __funnelshift_r(m1, m2, s); m2 = __funnelshift_r(m2, m3, s); m3 >>= s;
+    }
+    const u32 t0 = pop_lowest128(m0, m1, m2, m3), t1 = pop_lowest128(m0, m1, m2, m3), t2 = pop_lowest128(m0, m1, m2, m3);
+    const u32 t3 = pop_lowest128(m0, m1, m2, m3), t4 = pop_lowest128(m0, m1, m2, m3), t5 = pop_lowest128(m0, m1, m2, m3);
+    if (t5 >= 112 - s) return false;                                  // six separators inside the words we looked at
+    // every separator must be a single TAB, every field non-empty
+    if (t0 == 0 || t1 == t0 + 1 || t2 == t1 + 1 || t3 == t2 + 1 || t4 == t3 + 1 || t5 == t4 + 1) return false;
+    if (f.byte(a + t0) != '\t' || f.byte(a + t1) != '\t' || f.byte(a + t2) != '\t' || f.byte(a + t3) != '\t' || f.byte(a + t4) != '\t' ||
+        f.byte(a + t5) != '\t') return false;
+    if (f.byte(a) == '@') return false;
+    const u32 l_flag = t1 - t0 - 1, l_name = t2 - t1 - 1, l_pos = t3 - t2 - 1, l_mapq = t4 - t3 - 1;
+    if (l_flag > 5 || l_name > 8 || l_pos > 10 || l_mapq > 3) return false;
+    u32 flag, pos, mapq;
+    if (!dec_field(f, a + t0 + 1, l_flag, flag)) return false;
+    if (!dec_field(f, a + t2 + 1, l_pos, pos)) return false;
+    if (!dec_field(f, a + t3 + 1, l_mapq, mapq)) return false;
+    tok.t0 = t0;
+    if (WANT_Q) {                                                      // QNAME words for the neighbour-lane comparison
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            u64 x = (u32)(8 * k) < t0 ? fetch8(f, a + 8 * k) : 0;
+            if (t0 < (u32)(8 * k + 8) && t0 > (u32)(8 * k)) x &= (1ull << (8 * (t0 - 8 * k))) - 1;
+            tok.q[k] = x;
+        }
+    }
+    tok.ok = t0 <= 40;
+    meta = 0;
+    if (mapq < (u32)p.min_mapq || (flag & 0x700u)) return true;       // pairutil.h:157-161
+    meta = LM_KEEP;
+    // RNAME: FNV-1a over its bytes, same as the byte loop
+    u64 name8 = fetch8(f, a + t1 + 1);
+    if (l_name < 8) name8 &= (1ull << (8 * l_name)) - 1;
+    u64 h = 0xCBF29CE484222325ull;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if ((u32)k < l_name) h = hash_step(h, (int)((name8 >> (8 * k)) & 0xFF));
+    // CIGAR walk (pairutil.h:63-126), 8 characters per fetch
+    u32 val = 0, idx = 0, leftClip = 0, rightClip = 0, mappable = 0;
+    u32 cur = pos, right0 = 0, left1 = 0, right1 = 0, last_right = 0;
+    bool err = false;
+    const u32 l_cig = t5 - t4 - 1;
+    u64 x = 0;
+    for (u32 k = 0; k < l_cig; ++k) {
+        if ((k & 7) == 0) x = fetch8(f, a + t4 + 1 + k);
+        const int c = (int)(x & 0xFF); x >>= 8;
+        const u32 d = (u32)(c - '0');
+        if (d <= 9u) { val = val * 10u + d; continue; }
+        if (c == 'H' || c == 'S') {
+            if (k + 1 == l_cig) rightClip = val;
+            else if (idx == 0) leftClip = val;
+            else err = true;
+        } else if (c == 'M' || c == 'D') {
+            if (c == 'M') mappable += val;
+            cur += val; last_right = cur - 1;
+            if (idx == 0) right0 = last_right; else if (idx == 1) right1 = last_right;
+        } else if (c == 'N') {
+            cur += val; ++idx; last_right = 0;
+            if (idx == 1) left1 = cur;
+        } else if (c != 'I') err = true;
+        val = 0;
+    }
+    rec.pos = pos; rec.right0 = right0; rec.left1 = left1; rec.right1 = right1;
+    rec.leftClip = leftClip; rec.rightClip = rightClip; rec.mappable = mappable; rec.line_len = 0;
+    rec.flag = (u16)flag; rec.qname_len = (u16)t0;
+    rec.chr_slot = (u16)chr_lookup_insert(p, h, name8, p.buf, a + t1 + 1, l_name);
+    const u32 segCnt = idx + 1;
+    if (last_right == 0) err = true;
+    rec.segCnt = err ? 0 : (u8)(segCnt > 2 ? 3 : segCnt);
+    rec.pad0 = 0; rec.qname_off = 0; rec.pad1 = 0;
+    return true;
+}
+
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
+    __shared__ uint4 s_line[7][256];
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += gridDim.x * blockDim.x) {
-        const u32 start = i ? p.nl_pos[i - 1] + 1 : 0;
-        if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu;
-        ByteReader r, q;
-        r.init(p.buf, ws + start);
-        if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
-        LineRec rec;
-        const u32 meta = parse_line(p, r, q, i > 0, ws + start, rec);
+    const u64 limit = st->total;
+    const int lane = threadIdx.x & 31;
+    const u32 n_round = (n_lines + 31u) & ~31u;                       // whole warps stay in the loop (shuffles below)
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool active = i < n_lines;
+        u32 start = 0;
+        if (active) { start = i ? p.nl_pos[i - 1] + 1 : 0; if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu; }
+        LineRec rec; u32 meta = 0;
+        FastTok tok; tok.ok = false; tok.t0 = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tok.q[k] = 0;
+        bool fast = false;
+        if (active && ws + start + 144 <= limit) {
+            LineFetch lf; lf.buf = p.buf; lf.col = &s_line[0][threadIdx.x]; lf.A = (ws + start) & ~(u64)15;
+            const uint4 *src = (const uint4 *)(p.buf + lf.A);
+            uint4 w[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) w[j] = __ldg(src + j);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) s_line[j][threadIdx.x] = w[j];
+            fast = parse_line_fast<LineFetch, true>(p, lf, ws + start, limit, tok, rec, meta);
+        }
+        // QNAME equal to the previous line's?  Neighbouring lanes hold neighbouring lines: compare in registers.
+        const u32 pt0 = __shfl_up_sync(0xffffffffu, tok.t0, 1);
+        const int pok = __shfl_up_sync(0xffffffffu, (int)tok.ok, 1);
+        bool same = pt0 == tok.t0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { const u64 pq = __shfl_up_sync(0xffffffffu, tok.q[k], 1); same &= pq == tok.q[k]; }
+        if (!active) continue;
+        if (fast) {
+            if (i > 0) {
+                bool eq;
+                if (lane > 0 && tok.ok && pok) eq = same;
+                else eq = qname_equal_slow(p, ws, i, i - 1);
+                if (eq) meta |= LM_EQ;
+            }
+        } else {
+            ByteReader r, q;
+            r.init(p.buf, ws + start);
+            if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
+            meta = parse_line(p, r, q, i > 0, ws + start, rec);
+        }
         if (meta & LM_KEEP) p.rec[i] = rec;
         p.lmeta[i] = (u8)meta;
     }
@@ -505,7 +726,9 @@ static __global__ void __launch_bounds__(FZ_THREADS) k_scan_parse(S2PParams p) {
             __syncthreads();
             const u32 n_here = total - r0 < FZ_LCAP ? total - r0 : FZ_LCAP;
             for (u32 base_id = r0 ? r0 + 1 : 0; base_id <= r0 + n_here; base_id += FZ_THREADS) {
-                const u32 id = base_id + tid;
+                // consecutive lines go to different warps (8 lanes of every warp for a typical 64-line tile): the parse is a
+                // dependent chain per line, so its latency is hidden by warps, not by lanes
+                const u32 id = base_id + (u32)((tid & 7) * 32 + (tid >> 3));
                 u32 meta = 0; LineRec rec; bool mine = false; u64 abs0 = 0;
                 if (id <= r0 + n_here) {
                     bool exists = true;
@@ -516,11 +739,17 @@ static __global__ void __launch_bounds__(FZ_THREADS) k_scan_parse(S2PParams p) {
                         bool cmp = false; u64 prev_abs = 0;              // previous line's start, when it is known here
                         if (id >= 2 && id - 2 >= r0) { cmp = true; prev_abs = tbase + (u32)s_nl[id - 2 - r0] + 1; }
                         else if (id == 1 && has_initial && r0 == 0) { cmp = true; prev_abs = initial_abs; }
-                        TileReader r, q;
-                        r.setup(p.buf, tl, tbase, tbase + loaded); q.setup(p.buf, tl, tbase, tbase + loaded);
-                        r.init(p.buf, abs0);
-                        if (cmp) q.init(p.buf, prev_abs);
-                        meta = parse_line(p, r, q, cmp, abs0, rec);
+                        TileFetch tf; tf.buf = p.buf; tf.sm = tl; tf.tlo = tbase; tf.thi = tbase + loaded;
+                        FastTok tok;
+                        if (parse_line_fast<TileFetch, false>(p, tf, abs0, st->total, tok, rec, meta)) {
+                            if (cmp && qname_eq_fetch(tf, abs0, prev_abs, tok.t0)) meta |= LM_EQ;
+                        } else {
+                            TileReader r, q;
+                            r.setup(p.buf, tl, tbase, tbase + loaded); q.setup(p.buf, tl, tbase, tbase + loaded);
+                            r.init(p.buf, abs0);
+                            if (cmp) q.init(p.buf, prev_abs);
+                            meta = parse_line(p, r, q, cmp, abs0, rec);
+                        }
                         if (!cmp && abs0 != ws) meta |= LM_EQ_UNK;
                     }
                 }
@@ -835,117 +1064,134 @@ __device__ __forceinline__ void write_pair_line(const S2PParams &p, u64 ws, cons
     *out++ = '\t'; *out++ = (g.strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (g.strands & 2) ? '-' : '+'; *out++ = '\n';
 }
 
+// A tile is EMIT_NT sub-tiles of 512 lines: the sizes of all sub-tiles are scanned first, ONE look-back pair covers the
+// tile (the look-back makes every wave of the persistent grid wait for its slowest CTA, so it is amortised over 2048
+// lines), then the sub-tiles are written one after the other through the shared-memory text stage.
+#define EMIT_NT 4
+#define EMIT_BIG (EMIT_NT * EMIT_TILE)
+
 static __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
-    __shared__ u32 s_w[2][3][EMIT_THREADS / 32];
+    __shared__ u32 s_w[2][EMIT_NT][3][EMIT_THREADS / 32];
     __shared__ u64 s_baseA[2], s_baseB[2];
     WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n_tiles = (int)((n_lines + EMIT_TILE - 1) / EMIT_TILE);
+    const int n_tiles = (int)((n_lines + EMIT_BIG - 1) / EMIT_BIG);
     const u64 base_text = st->out_text, base_pairs = st->out_pairs, base_sam = st->out_sam, base_groups = st->groups_done;
-    __shared__ int s_tk[2];
-    const bool dyn = p.dyn_tickets != 0;
-    if (tid == 0) s_tk[0] = dyn ? (int)atomicAdd(&st->tickets[1], 1u) : (int)blockIdx.x;
-    __syncthreads();
     int pb = 0;
-    for (int tile = s_tk[0]; tile < n_tiles; tile = s_tk[pb ^= 1]) {
-        if (tid == 0) s_tk[pb ^ 1] = dyn ? (int)atomicAdd(&st->tickets[1], 1u) : tile + (int)gridDim.x;   // read after this tile's barriers
-        const u32 i0 = (u32)tile * EMIT_TILE + tid * EMIT_ITEMS;
-        GroupRes g[EMIT_ITEMS];
-        bool proc[EMIT_ITEMS], emit[EMIT_ITEMS];
-        u32 vA = 0, vT = 0, vS = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, pb ^= 1) {
+        // ---- phase 1: per-thread sizes of every sub-tile (groups | emitted << 16, text bytes, passthrough bytes)
+        u32 lA[EMIT_NT], lT[EMIT_NT], lS[EMIT_NT];                      // become thread-exclusive prefixes inside the sub-tile
 #pragma unroll
-        for (int k = 0; k < EMIT_ITEMS; ++k) {
-            const u32 i = i0 + k;
-            const u32 m = i < n_lines ? p.lmeta[i] : 0;
-            proc[k] = (m & LM_HEAD) && (m & LM_PROC);
-            emit[k] = proc[k] && (m & LM_EMIT);
-            if (proc[k]) g[k] = p.res[i];
-            vA += (proc[k] ? 1u : 0u) | (emit[k] ? 1u << 16 : 0u);
-            if (emit[k]) { vT += g[k].text_len; if (p.write_sam) vS += g[k].sam_len; }
+        for (int k = 0; k < EMIT_NT; ++k) {
+            const u32 i0 = (u32)tile * EMIT_BIG + k * EMIT_TILE + tid * EMIT_ITEMS;
+            u32 vA = 0, vT = 0, vS = 0;
+#pragma unroll
+            for (int q = 0; q < EMIT_ITEMS; ++q) {
+                const u32 i = i0 + q;
+                const u32 m = i < n_lines ? p.lmeta[i] : 0;
+                const bool proc = (m & LM_HEAD) && (m & LM_PROC), emit = proc && (m & LM_EMIT);
+                vA += (proc ? 1u : 0u) | (emit ? 1u << 16 : 0u);
+                if (emit) { vT += p.res[i].text_len; if (p.write_sam) vS += p.res[i].sam_len; }
+            }
+            const u32 iA = warp_incl_scan(vA, lane), iT = warp_incl_scan(vT, lane), iS = warp_incl_scan(vS, lane);
+            if (lane == 31) { s_w[pb][k][0][wid] = iA; s_w[pb][k][1][wid] = iT; s_w[pb][k][2][wid] = iS; }
+            lA[k] = iA - vA; lT[k] = iT - vT; lS[k] = iS - vS;
         }
-        // three block scans with one pair of barriers
-        const u32 iA = warp_incl_scan(vA, lane), iT = warp_incl_scan(vT, lane), iS = warp_incl_scan(vS, lane);
-        if (lane == 31) { s_w[pb][0][wid] = iA; s_w[pb][1][wid] = iT; s_w[pb][2][wid] = iS; }
         __syncthreads();
-        u32 bA = 0, bT = 0, bS = 0, totA = 0, totT = 0, totS = 0;
+        // ---- phase 2: sub-tile totals, tile totals, one look-back per chain
+        u32 sG[EMIT_NT], sE[EMIT_NT], sT[EMIT_NT], sS[EMIT_NT], tG = 0, tE = 0, tT = 0, tS = 0;
 #pragma unroll
-        for (int k = 0; k < EMIT_THREADS / 32; ++k) {
-            const u32 a = s_w[pb][0][k], t = s_w[pb][1][k], s2 = s_w[pb][2][k];
-            totA += a; totT += t; totS += s2;
-            if (k < wid) { bA += a; bT += t; bS += s2; }
+        for (int k = 0; k < EMIT_NT; ++k) {
+            u32 a = 0, t = 0, s2 = 0;
+#pragma unroll
+            for (int q = 0; q < EMIT_THREADS / 32; ++q) {
+                const u32 xa = s_w[pb][k][0][q], xt = s_w[pb][k][1][q], xs = s_w[pb][k][2][q];
+                a += xa; t += xt; s2 += xs;
+                if (q < wid) { lA[k] += xa; lT[k] += xt; lS[k] += xs; }
+            }
+            sG[k] = a & 0xFFFFu; sE[k] = a >> 16; sT[k] = t; sS[k] = s2;
+            tG += sG[k]; tE += sE[k]; tT += t; tS += s2;
         }
-        const u32 exA = bA + iA - vA, exT = bT + iT - vT, exS = bS + iS - vS;
         if (wid == 0) {
-            u64 agg = (u64)(totA & 0xFFFFu) | ((u64)(totA >> 16) << 31);
-            u64 b = lookback_exclusive(p.desc_emitA, tile, 0, agg, lane);
-            if (lane == 0) { s_baseA[pb] = b; if (tile == n_tiles - 1) { u64 t = b + agg; st->w_groups = (u32)(t & 0x7FFFFFFFu); st->w_emit = (u32)(t >> 31); } }
+            const u64 agg = (u64)tG | ((u64)tE << 31);
+            const u64 b = lookback_exclusive(p.desc_emitA, tile, 0, agg, lane);
+            if (lane == 0) { s_baseA[pb] = b; if (tile == n_tiles - 1) { const u64 t = b + agg; st->w_groups = (u32)(t & 0x7FFFFFFFu); st->w_emit = (u32)(t >> 31); } }
         } else if (wid == 1) {
-            u64 agg = (u64)totT | ((u64)totS << 31);
-            u64 b = lookback_exclusive(p.desc_emitB, tile, 0, agg, lane);
-            if (lane == 0) { s_baseB[pb] = b; if (tile == n_tiles - 1) { u64 t = b + agg; st->w_text = (u32)(t & 0x7FFFFFFFu); st->w_sam = (u32)(t >> 31); } }
+            const u64 agg = (u64)tT | ((u64)tS << 31);
+            const u64 b = lookback_exclusive(p.desc_emitB, tile, 0, agg, lane);
+            if (lane == 0) { s_baseB[pb] = b; if (tile == n_tiles - 1) { const u64 t = b + agg; st->w_text = (u32)(t & 0x7FFFFFFFu); st->w_sam = (u32)(t >> 31); } }
         }
         __syncthreads();
-        const u64 gA = s_baseA[pb], gB = s_baseB[pb];
-        u32 g_idx = (u32)(gA & 0x7FFFFFFFu) + (exA & 0xFFFFu);          // processed-group index inside the window
-        u32 e_idx = (u32)(gA >> 31) + (exA >> 16);
-        const u64 t_off = base_text + (gB & 0x7FFFFFFFu);
-        u64 s_run = base_sam + (gB >> 31) + exS;
-        const bool text_fits = t_off + totT <= p.out_text_cap;
-        const bool staged = totT <= EMIT_STAGE;
-        const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);       // stage with the destination's 16-byte phase
-        if (p.emit_text && totT && !text_fits && tid == 0) atomicOr(&st->err, S2P_ERR_TEXT);
-        u32 t_run = exT;
+        // ---- phase 3: outputs, sub-tile by sub-tile
+        u32 pG = (u32)(s_baseA[pb] & 0x7FFFFFFFu), pE = (u32)(s_baseA[pb] >> 31);   // running prefixes at the sub-tile's start
+        u64 pT = base_text + (s_baseB[pb] & 0x7FFFFFFFu), pS = base_sam + (s_baseB[pb] >> 31);
 #pragma unroll
-        for (int k = 0; k < EMIT_ITEMS; ++k) {
-            if (!proc[k]) continue;
-            const u32 i = i0 + k;
-            if (g[k].status == ST_SELFCIRCLE) {                          // for the thread-0-share emulation on the host
-                u32 slot = atomicAdd(&st->sc_count, 1u);
-                if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
-            }
-            ++g_idx;
-            if (!emit[k]) continue;
-            if (p.emit_packed) {
-                u64 o = base_pairs + e_idx;
-                if (o < p.out_pairs_cap) {
-                    mk_pair r; r.pos1 = g[k].posA; r.pos2 = g[k].posB; r.chr1 = g[k].chrA; r.chr2 = g[k].chrB; r.strands = g[k].strands;
-                    r.cls = (u8)(g[k].status - ST_TRANS); r.lane = p.lane;
-                    p.out_pairs[o] = r;
-                } else atomicOr(&st->err, S2P_ERR_PAIRS);
-            }
-            ++e_idx;
-            if (p.emit_text && text_fits) {
-                write_pair_line(p, ws, g[k], staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
-                t_run += g[k].text_len;
-            }
-            if (p.write_sam) {                                           // destination of every kept line of the group; K5 copies
-                if (s_run + g[k].sam_len > p.out_sam_cap) atomicOr(&st->err, S2P_ERR_SAM);
-                else {
-                    u64 o = s_run; u32 q = i;
-                    while (true) {
-                        p.sam_dst[q] = (u32)(o - base_sam);
-                        o += line_len_of(p, q) + 1;
-                        if (q == g[k].last_line) break;
-                        ++q; while (!(p.lmeta[q] & LM_KEEP)) ++q;
-                    }
+        for (int k = 0; k < EMIT_NT; ++k) {
+            const u32 i0 = (u32)tile * EMIT_BIG + k * EMIT_TILE + tid * EMIT_ITEMS;
+            u32 g_idx = pG + (lA[k] & 0xFFFFu), e_idx = pE + (lA[k] >> 16);
+            const u64 t_off = pT;                                        // first text byte of the sub-tile
+            u64 s_run = pS + lS[k];
+            const u32 totT = sT[k];
+            const bool text_fits = t_off + totT <= p.out_text_cap;
+            const bool staged = totT <= EMIT_STAGE;
+            const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);   // stage with the destination's 16-byte phase
+            if (p.emit_text && totT && !text_fits && tid == 0) atomicOr(&st->err, S2P_ERR_TEXT);
+            u32 t_run = lT[k];
+#pragma unroll
+            for (int q = 0; q < EMIT_ITEMS; ++q) {
+                const u32 i = i0 + q;
+                const u32 m = i < n_lines ? p.lmeta[i] : 0;
+                if (!((m & LM_HEAD) && (m & LM_PROC))) continue;
+                const GroupRes g = p.res[i];
+                if (g.status == ST_SELFCIRCLE) {                         // for the thread-0-share emulation on the host
+                    u32 slot = atomicAdd(&st->sc_count, 1u);
+                    if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
                 }
-                s_run += g[k].sam_len;
+                ++g_idx;
+                if (!(m & LM_EMIT)) continue;
+                if (p.emit_packed) {
+                    const u64 o = base_pairs + e_idx;
+                    if (o < p.out_pairs_cap) {
+                        mk_pair r; r.pos1 = g.posA; r.pos2 = g.posB; r.chr1 = g.chrA; r.chr2 = g.chrB; r.strands = g.strands;
+                        r.cls = (u8)(g.status - ST_TRANS); r.lane = p.lane;
+                        p.out_pairs[o] = r;
+                    } else atomicOr(&st->err, S2P_ERR_PAIRS);
+                }
+                ++e_idx;
+                if (p.emit_text && text_fits) {
+                    write_pair_line(p, ws, g, staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
+                    t_run += g.text_len;
+                }
+                if (p.write_sam) {                                       // destination of every kept line of the group; K5 copies
+                    if (s_run + g.sam_len > p.out_sam_cap) atomicOr(&st->err, S2P_ERR_SAM);
+                    else {
+                        u64 o = s_run; u32 ql = i;
+                        while (true) {
+                            p.sam_dst[ql] = (u32)(o - base_sam);
+                            o += line_len_of(p, ql) + 1;
+                            if (ql == g.last_line) break;
+                            ++ql; while (!(p.lmeta[ql] & LM_KEEP)) ++ql;
+                        }
+                    }
+                    s_run += g.sam_len;
+                }
             }
-        }
-        if (p.emit_text && totT && text_fits && staged) {
-            __syncthreads();
-            char *dst = p.out_text + t_off;
-            const u32 head = phase ? (16u - phase < totT ? 16u - phase : totT) : 0u;
-            if ((u32)tid < head) dst[tid] = s_stage[phase + tid];
-            const u32 body = (totT - head) >> 4;
-            for (u32 w = tid; w < body; w += EMIT_THREADS)
-                st_stream_v4((uint4 *)(dst + head + ((u64)w << 4)), *(const uint4 *)(s_stage + phase + head + (w << 4)));
-            const u32 tail0 = head + (body << 4);
-            if (tail0 + tid < totT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
-            __syncthreads();                                             // the stage is reused by the next tile
+            if (p.emit_text && totT && text_fits && staged) {
+                __syncthreads();
+                char *dst = p.out_text + t_off;
+                const u32 head = phase ? (16u - phase < totT ? 16u - phase : totT) : 0u;
+                if ((u32)tid < head) dst[tid] = s_stage[phase + tid];
+                const u32 body = (totT - head) >> 4;
+                for (u32 w = tid; w < body; w += EMIT_THREADS)
+                    st_stream_v4((uint4 *)(dst + head + ((u64)w << 4)), *(const uint4 *)(s_stage + phase + head + (w << 4)));
+                const u32 tail0 = head + (body << 4);
+                if (tail0 + tid < totT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
+                __syncthreads();                                         // the stage is reused by the next sub-tile
+            }
+            pG += sG[k]; pE += sE[k]; pT += sT[k]; pS += sS[k];
         }
     }
 }

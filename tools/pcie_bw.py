@@ -1,0 +1,15 @@
+"""Raw pinned host<->device copy bandwidth of the box (context for bench.py's e2e figure)."""
+import time
+import torch
+n = 1 << 30
+h = torch.empty(n, dtype=torch.uint8).pin_memory()
+d = torch.empty(n, dtype=torch.uint8, device="cuda")
+for name, a, b in (("h2d", d, h), ("d2h", h, d)):
+    for _ in range(2):
+        a.copy_(b, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        a.copy_(b, non_blocking=True)
+    torch.cuda.synchronize()
+    print(name, f"{5 * n / (time.perf_counter() - t0) / 1e9:.1f} GB/s")
