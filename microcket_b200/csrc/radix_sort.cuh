@@ -65,10 +65,13 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(typename P::Bu
         const bool valid = i < n;
         typename P::Key k;
         if (valid) k = P::load_key(bufs, 0, i);
+        const u32 vmask = __ballot_sync(0xffffffffu, valid);
         for (int p = 0; p < sch.n_pass; ++p) {
-            u32 d = valid ? P::digit(k, sch.byte_of[p]) : 0x100u + lane;   // invalid lanes never match anyone
-            u32 peers = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + d], (u32)__popc(peers));
+            const u32 d = valid ? P::digit(k, sch.byte_of[p]) : 0u;
+            // constant digits (high bytes, unused fields) would serialise 32 ways on one counter: one add per warp instead
+            const u32 d0 = __shfl_sync(0xffffffffu, d, __ffs(vmask) - 1);
+            if (__all_sync(0xffffffffu, !valid || d == d0)) { if (lane == __ffs(vmask) - 1) atomicAdd(&s_hist[p * 256 + d0], (u32)__popc(vmask)); }
+            else if (valid) atomicAdd(&s_hist[p * 256 + d], 1u);
         }
     }
     __syncthreads();

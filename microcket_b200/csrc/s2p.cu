@@ -37,7 +37,7 @@ struct S2PCtx : mk_ctx {
     bool fused = false;
     u64 launches = 0;
     // host streaming state
-    size_t stage_fill = 0;                         // bytes staged in the next window's pinned buffer
+    std::vector<char> tail;                        // input not yet part of a window (a partial last line, or small pushes)
     PinBuf h_nl;                                   // a pinned '\n' (terminates a last line that lacks one)
     u64 windows = 0;
     int prev_slot = -1;
@@ -403,55 +403,49 @@ extern "C" int mk_s2p_push(mk_ctx *x, const char *bytes, size_t n, int is_last) 
     if (c->finished_input) { mk_set_error("mk_s2p_push after the last chunk"); return MK_ERR_STATE; }
     if (c->use_device_path) { mk_set_error("mk_s2p_push on a context used with mk_s2p_run_device"); return MK_ERR_STATE; }
     const bool pinned = n >= (1u << 20) && host_ptr_is_pinned(bytes);
-    cudaEvent_t last_direct = nullptr;
+    std::vector<char> &tail = c->tail;                   // bytes received but not yet part of a window (partial line, small pushes)
     size_t off = 0;
-    while (off < n) {
-        S2PSlot *sp; MK_TRY(s2p_next_slot(c, &sp));
-        S2PSlot &s = *sp;
-        const size_t room = c->W - c->stage_fill, left = n - off;
-        if (pinned && left >= room / 2) {
-            // zero-copy: DMA a whole window straight from the caller's pinned memory, cut at its last complete line
-            size_t take = std::min(room, left);
-            const bool whole = is_last && take == left;
-            bool add_nl = false;
-            if (!whole) {
-                const void *nl = memrchr(bytes + off, '\n', take);
-                if (nl) take = (size_t)((const char *)nl - (bytes + off)) + 1; else take = 0;
-            } else add_nl = bytes[off + take - 1] != '\n';
-            if (take) {
-                MK_TRY(s2p_submit(c, c->stage_fill, bytes + off, take, add_nl, whole));
-                last_direct = s.ev_h2d;
-                c->stage_fill = 0; off += take;
-                if (whole) c->finished_input = true;
+    while (true) {
+        const size_t left = n - off, have = tail.size() + left;
+        if (have == 0) break;
+        if (have < c->W && !is_last) { tail.insert(tail.end(), bytes + off, bytes + off + left); off = n; break; }
+        // a window of at most W bytes: the tail followed by the first `take` new bytes, cut after its last complete line
+        size_t take = std::min(left, c->W - std::min(c->W, tail.size()));
+        const bool whole = is_last && take == left;
+        size_t cut = take;
+        if (!whole) {
+            const void *nl = take ? memrchr(bytes + off, '\n', take) : nullptr;
+            if (nl) cut = (size_t)((const char *)nl - (bytes + off)) + 1;
+            else {                                         // no line end in the new bytes: the window ends inside the tail
+                tail.insert(tail.end(), bytes + off, bytes + off + take); off += take;
+                const void *tn = memrchr(tail.data(), '\n', tail.size());
+                if (!tn) { mk_set_error("sam2pairs: a line longer than the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
+                const size_t keep_from = (size_t)((const char *)tn - tail.data()) + 1;
+                S2PSlot *sp; MK_TRY(s2p_next_slot(c, &sp));
+                memcpy(sp->h_in.p, tail.data(), keep_from);
+                MK_TRY(s2p_submit(c, keep_from, nullptr, 0, false, false));
+                tail.erase(tail.begin(), tail.begin() + (long)keep_from);
                 continue;
             }
         }
-        // staged: gather bytes in the slot's pinned buffer until a window is full
-        const size_t take = std::min(room, left);
-        memcpy(s.h_in.as<char>() + c->stage_fill, bytes + off, take);
-        c->stage_fill += take; off += take;
-        if (c->stage_fill == c->W) {
-            const char *base = s.h_in.as<char>();
-            const void *nl = memrchr(base, '\n', c->stage_fill);
-            if (!nl) { mk_set_error("sam2pairs: a line longer than the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
-            const size_t cut = (size_t)((const char *)nl - base) + 1, rem = c->stage_fill - cut;
-            MK_TRY(s2p_submit(c, cut, nullptr, 0, false, false));
-            S2PSlot *np; MK_TRY(s2p_next_slot(c, &np));              // the partial last line opens the next window
-            memcpy(np->h_in.p, base + cut, rem);
-            c->stage_fill = rem;
+        S2PSlot *sp; MK_TRY(s2p_next_slot(c, &sp));
+        char *stage = sp->h_in.as<char>();
+        const size_t n_tail = tail.size();
+        if (n_tail) memcpy(stage, tail.data(), n_tail);
+        tail.clear();
+        const bool add_nl = whole && (cut ? bytes[off + cut - 1] != '\n' : (n_tail && stage[n_tail - 1] != '\n'));   // getline accepts a last line without '\n'
+        if (pinned && cut >= (1u << 20)) {
+            MK_TRY(s2p_submit(c, n_tail, bytes + off, cut, add_nl, whole));   // DMA straight from the caller's pinned memory
+        } else {
+            memcpy(stage + n_tail, bytes + off, cut);
+            size_t tot = n_tail + cut;
+            if (add_nl) stage[tot++] = '\n';
+            MK_TRY(s2p_submit(c, tot, nullptr, 0, false, whole));
         }
+        off += cut;
+        if (whole) { c->finished_input = true; break; }
     }
-    if (is_last && !c->finished_input) {
-        if (c->stage_fill) {
-            S2PSlot *sp; MK_TRY(s2p_next_slot(c, &sp));
-            char *base = sp->h_in.as<char>();
-            if (base[c->stage_fill - 1] != '\n') base[c->stage_fill++] = '\n';   // getline accepts a last line without '\n'
-            MK_TRY(s2p_submit(c, c->stage_fill, nullptr, 0, false, true));
-            c->stage_fill = 0;
-        }
-        c->finished_input = true;
-    }
-    (void)last_direct;   // pinned caller memory is read asynchronously: it must stay valid until the window's output was pulled (or finish)
+    if (is_last) c->finished_input = true;
     return MK_OK;
 }
 
@@ -595,7 +589,7 @@ extern "C" int mk_s2p_reset(mk_ctx *x) {
     memset(&st, 0, sizeof st); st.n_chrom = n_chrom;
     MK_CUDA(cudaMemcpy(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice));
     for (auto &s : c->slot) { s.busy = false; s.free_pending = false; s.text_len = s.text_off = s.pairs_n = s.pairs_off = s.sam_len = s.sam_off = 0; }
-    c->stage_fill = 0; c->windows = 0; c->prev_slot = -1; c->finished_input = false; c->use_device_path = false;
+    c->tail.clear(); c->windows = 0; c->prev_slot = -1; c->finished_input = false; c->use_device_path = false;
     c->q_text.clear(); c->q_sam.clear(); c->q_pairs.clear(); c->q_text_off = c->q_sam_off = c->q_pairs_off = 0;
     c->sc_full_rule = 0; c->sc_tail.clear(); c->sc_true = 0;
     return MK_OK;

@@ -546,54 +546,65 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
 }
 
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
-    __shared__ uint4 s_line[7][256];
+    __shared__ uint4 s_line[7][256];                                  // every thread's line prefix, one column per thread
+    __shared__ u64 s_A[256];                                          // its 16-byte aligned base, or ~0 when not staged
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const u64 limit = st->total;
-    const int lane = threadIdx.x & 31;
-    const u32 n_round = (n_lines + 31u) & ~31u;                       // whole warps stay in the loop (shuffles below)
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const int tid = threadIdx.x;
+    const u32 n_round = (n_lines + 255u) & ~255u;                     // whole CTAs stay in the loop (barriers below)
+    for (u32 i = blockIdx.x * blockDim.x + tid; i < n_round; i += gridDim.x * blockDim.x) {
         const bool active = i < n_lines;
         u32 start = 0;
         if (active) { start = i ? p.nl_pos[i - 1] + 1 : 0; if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu; }
-        LineRec rec; u32 meta = 0;
-        FastTok tok; tok.ok = false; tok.t0 = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) tok.q[k] = 0;
-        bool fast = false;
-        if (active && ws + start + 144 <= limit) {
-            LineFetch lf; lf.buf = p.buf; lf.col = &s_line[0][threadIdx.x]; lf.A = (ws + start) & ~(u64)15;
+        const u64 a = ws + start;
+        LineFetch lf; lf.buf = p.buf; lf.col = &s_line[0][tid]; lf.A = a & ~(u64)15;
+        const bool staged = active && a + 144 <= limit;
+        if (staged) {
             const uint4 *src = (const uint4 *)(p.buf + lf.A);
             uint4 w[7];
 #pragma unroll
             for (int j = 0; j < 7; ++j) w[j] = __ldg(src + j);
 #pragma unroll
-            for (int j = 0; j < 7; ++j) s_line[j][threadIdx.x] = w[j];
-            fast = parse_line_fast<LineFetch, true>(p, lf, ws + start, limit, tok, rec, meta);
+            for (int j = 0; j < 7; ++j) s_line[j][tid] = w[j];
         }
-        // QNAME equal to the previous line's?  Neighbouring lanes hold neighbouring lines: compare in registers.
-        const u32 pt0 = __shfl_up_sync(0xffffffffu, tok.t0, 1);
-        const int pok = __shfl_up_sync(0xffffffffu, (int)tok.ok, 1);
-        bool same = pt0 == tok.t0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { const u64 pq = __shfl_up_sync(0xffffffffu, tok.q[k], 1); same &= pq == tok.q[k]; }
-        if (!active) continue;
-        if (fast) {
-            if (i > 0) {
-                bool eq;
-                if (lane > 0 && tok.ok && pok) eq = same;
-                else eq = qname_equal_slow(p, ws, i, i - 1);
-                if (eq) meta |= LM_EQ;
+        s_A[tid] = staged ? lf.A : ~(u64)0;
+        __syncthreads();                                               // neighbours read each other's columns
+        if (active) {
+            LineRec rec; u32 meta = 0;
+            FastTok tok;
+            if (staged && parse_line_fast<LineFetch, false>(p, lf, a, limit, tok, rec, meta)) {
+                if (i > 0) {
+                    // QNAME equal to the previous line's?  That line's prefix sits in the neighbouring column.
+                    const u64 pa = ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0);
+                    bool eq;
+                    if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_slow(p, ws, i, i - 1);   // operator>> skips leading blanks
+                    else if (tid > 0 && s_A[tid - 1] != ~(u64)0) {
+                        LineFetch lp; lp.buf = p.buf; lp.col = &s_line[0][tid - 1]; lp.A = s_A[tid - 1];
+                        eq = true;
+                        for (u32 k = 0; k < tok.t0 && eq; k += 8) {
+                            u64 x = fetch8(lf, a + k), y = fetch8(lp, pa + k);
+                            if (tok.t0 - k < 8) { const u64 m = (1ull << (8 * (tok.t0 - k))) - 1; x &= m; y &= m; }
+                            eq = x == y;
+                        }
+                        eq = eq && is_ws(lp.byte(pa + tok.t0));
+                    } else {
+                        GlobalFetch gf; gf.buf = p.buf;
+                        eq = qname_eq_fetch(gf, a, pa, tok.t0);
+                    }
+                    if (eq) meta |= LM_EQ;
+                }
+            } else {
+                ByteReader r, q;
+                r.init(p.buf, a);
+                if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
+                meta = parse_line(p, r, q, i > 0, a, rec);
             }
-        } else {
-            ByteReader r, q;
-            r.init(p.buf, ws + start);
-            if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
-            meta = parse_line(p, r, q, i > 0, ws + start, rec);
+            if (meta & LM_KEEP) p.rec[i] = rec;
+            p.lmeta[i] = (u8)meta;
         }
-        if (meta & LM_KEEP) p.rec[i] = rec;
-        p.lmeta[i] = (u8)meta;
+        __syncthreads();                                               // columns are rewritten by the next round
     }
 }
 
