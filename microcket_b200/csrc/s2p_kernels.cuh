@@ -1057,19 +1057,33 @@ __device__ __forceinline__ u32 put_uint(char *dst, u32 v) {
 }
 
 // rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347)
-__device__ __forceinline__ void write_pair_line(const S2PParams &p, u64 ws, const GroupRes &g, char *out) {
+__device__ __forceinline__ char *put_bytes8(char *out, u64 x, u32 n) {       // the low n (<= 8) bytes of x
+#pragma unroll
+    for (int b = 0; b < 8; ++b) if ((u32)b < n) out[b] = (char)(x >> (8 * b));
+    return out + n;
+}
+__device__ __forceinline__ char *put_name(char *out, const ChrSlot *c) {
+    const u32 l = c->len;
+    if (l <= 8) return put_bytes8(out, c->name8, l);
+    for (u32 i = 0; i < l; ++i) out[i] = c->name[i];
+    return out + l;
+}
+struct RidInfo { u64 abs; u32 len; };                                          // where the group's read id sits in the SAM text
+__device__ __forceinline__ RidInfo rid_info(const S2PParams &p, u64 ws, const GroupRes &g) {
     const u32 rl = g.rid_line;
     const LineRec *rr = &p.rec[rl];
-    const u32 ql = rr->qname_len;
-    ByteReader r; r.init(p.buf, ws + (rl ? p.nl_pos[rl - 1] + 1 : 0) + rr->qname_off);
-    for (u32 i = 0; i < ql; ++i) *out++ = (char)r.next();
+    RidInfo r; r.len = rr->qname_len; r.abs = ws + (rl ? p.nl_pos[rl - 1] + 1 : 0) + rr->qname_off;
+    return r;
+}
+__device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInfo &rid, const GroupRes &g, char *out) {
+    GlobalFetch gf; gf.buf = p.buf;
+    for (u32 k = 0; k < rid.len; k += 8) { const u32 n = rid.len - k < 8 ? rid.len - k : 8; out = put_bytes8(out, fetch8(gf, rid.abs + k), n); }
     *out++ = '\t';
-    const ChrSlot *ca = &p.chr[p.id_to_slot[g.chrA]], *cb = &p.chr[p.id_to_slot[g.chrB]];
-    for (u32 i = 0; i < ca->len; ++i) *out++ = ca->name[i];
+    out = put_name(out, &p.chr[p.id_to_slot[g.chrA]]);
     *out++ = '\t';
     out += put_uint(out, g.posA);
     *out++ = '\t';
-    for (u32 i = 0; i < cb->len; ++i) *out++ = cb->name[i];
+    out = put_name(out, &p.chr[p.id_to_slot[g.chrB]]);
     *out++ = '\t';
     out += put_uint(out, g.posB);
     *out++ = '\t'; *out++ = (g.strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (g.strands & 2) ? '-' : '+'; *out++ = '\n';
@@ -1081,7 +1095,7 @@ __device__ __forceinline__ void write_pair_line(const S2PParams &p, u64 ws, cons
 #define EMIT_NT 4
 #define EMIT_BIG (EMIT_NT * EMIT_TILE)
 
-static __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
+static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
     __shared__ u32 s_w[2][EMIT_NT][3][EMIT_THREADS / 32];
     __shared__ u64 s_baseA[2], s_baseB[2];
@@ -1151,12 +1165,21 @@ static __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
             const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);   // stage with the destination's 16-byte phase
             if (p.emit_text && totT && !text_fits && tid == 0) atomicOr(&st->err, S2P_ERR_TEXT);
             u32 t_run = lT[k];
+            u32 mm[EMIT_ITEMS]; GroupRes gg[EMIT_ITEMS]; RidInfo rid[EMIT_ITEMS];
+#pragma unroll
+            for (int q = 0; q < EMIT_ITEMS; ++q) {                       // all loads first: the chain lmeta -> res -> rec -> nl_pos is latency bound
+                const u32 i = i0 + q;
+                mm[q] = i < n_lines ? p.lmeta[i] : 0;
+                if ((mm[q] & LM_HEAD) && (mm[q] & LM_PROC)) gg[q] = p.res[i];
+            }
+#pragma unroll
+            for (int q = 0; q < EMIT_ITEMS; ++q) if ((mm[q] & LM_EMIT) && p.emit_text) rid[q] = rid_info(p, ws, gg[q]);
 #pragma unroll
             for (int q = 0; q < EMIT_ITEMS; ++q) {
                 const u32 i = i0 + q;
-                const u32 m = i < n_lines ? p.lmeta[i] : 0;
+                const u32 m = mm[q];
                 if (!((m & LM_HEAD) && (m & LM_PROC))) continue;
-                const GroupRes g = p.res[i];
+                const GroupRes &g = gg[q];
                 if (g.status == ST_SELFCIRCLE) {                         // for the thread-0-share emulation on the host
                     u32 slot = atomicAdd(&st->sc_count, 1u);
                     if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
@@ -1173,7 +1196,7 @@ static __global__ void __launch_bounds__(EMIT_THREADS) k_emit(S2PParams p) {
                 }
                 ++e_idx;
                 if (p.emit_text && text_fits) {
-                    write_pair_line(p, ws, g, staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
+                    write_pair_line(p, rid[q], g, staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
                     t_run += g.text_len;
                 }
                 if (p.write_sam) {                                       // destination of every kept line of the group; K5 copies
