@@ -182,8 +182,8 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
     if (tile <= last_tile) load_sub((u64)tile * S2P_SUPER);
     for (int pb = 0; tile <= last_tile; tile += gridDim.x, pb ^= 1) {
         const u64 tbase = (u64)tile * S2P_SUPER;
-#pragma unroll
-        for (int k = 0; k < S2P_NT; ++k) {
+#pragma unroll 1
+        for (int k = 0; k < S2P_NT; ++k) {                              // rolled: the kernel must fit the instruction cache
             const u64 sbase = tbase + (u64)k * S2P_TILE_BYTES;
             const bool interior = sbase >= ws && sbase + S2P_TILE_BYTES <= we;
 #pragma unroll
@@ -192,6 +192,7 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
                 if (!interior && z) {                                 // window edges: drop flags of bytes outside [ws, we)
                     const u64 off = sbase + ((u64)(j * S2P_SCAN_THREADS + tid) << 4);
                     u32 keep = 0;
+#pragma unroll 1
                     for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
                     z &= keep;
                 }
@@ -234,17 +235,16 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
         __syncthreads();
         const u32 base = s_base[pb];
 #pragma unroll
-        for (int k = 0; k < S2P_NT; ++k) {
+        for (int k = 0; k < S2P_NT; ++k) {                              // (cnt / pre are registers: static indices)
             if (!cnt[k]) continue;
-            const uint4 za = ((const uint4 *)s_z[k])[2 * tid], zb = ((const uint4 *)s_z[k])[2 * tid + 1];
-            const u32 zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
             u32 idx = base + pre[k];
             const u32 rel = (u32)(tbase + (u64)k * S2P_TILE_BYTES + (u64)tid * 128 - ws);   // may wrap for bytes before ws: those have no flags
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < 8; ++i) {
-                u32 z = zz[i];
+                u32 z = s_z[k][8 * tid + i];
                 if (!z) continue;
                 if (z & (z - 1)) {                                    // several newlines in one 16-byte word: restore byte order
+#pragma unroll 1
                     u32 m = 0;
                     while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
                     while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (idx < cap_lines) nl_pos[idx] = rel + i * 16 + q; ++idx; }
@@ -268,7 +268,7 @@ static __global__ void __launch_bounds__(S2P_SCAN_THREADS, 3) k_scan_lines(S2PPa
 __device__ __forceinline__ u64 hash_step(u64 h, int c) { return (h ^ (u64)c) * 0x100000001B3ull; }
 
 // Returns the slot of the name; inserts it when unseen (lock-free; ids are published by the inserter).
-static __device__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 name8, const char *buf, u64 name_off, u32 len) {
+static __device__ __noinline__ int chr_lookup_insert_slow(const S2PParams &p, u64 h, u64 name8, const char *buf, u64 name_off, u32 len) {
     if (h == 0) h = 0x9E3779B97F4A7C15ull;
     const u32 l = len < S2P_NAME_MAX ? len : S2P_NAME_MAX;
     u32 s = (u32)(h ^ (h >> 29)) & p.chr_mask;
@@ -299,6 +299,15 @@ static __device__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 name8, co
     }
     atomicOr(&p.st->err, S2P_ERR_CHRTABLE);
     return 0;
+}
+
+// Hot path: the name is already in the table (published by an earlier launch or earlier in this one) and is short.
+// Plain cached loads are enough here: a stale view can only look "absent", which falls through to the exact slow path.
+__device__ __forceinline__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 name8, const char *buf, u64 name_off, u32 len) {
+    const u64 hh = h ? h : 0x9E3779B97F4A7C15ull;
+    const ChrSlot *sl = &p.chr[(u32)(hh ^ (hh >> 29)) & p.chr_mask];
+    if (len <= 8 && sl->key == hh && sl->id >= 0 && sl->len == len && sl->name8 == name8) return (int)(sl - p.chr);
+    return chr_lookup_insert_slow(p, h, name8, buf, name_off, len);
 }
 
 // ------------------------------------------------------------------------------------------------ K2: parse
@@ -545,6 +554,14 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     return true;
 }
 
+// the generic byte-loop parser, out of line: it is the rare path and would otherwise triple the hot loop's code size
+static __device__ __noinline__ u32 parse_line_slow(const S2PParams &p, u64 ws, u32 i, u64 a, LineRec &rec) {
+    ByteReader r, q;
+    r.init(p.buf, a);
+    if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
+    return parse_line(p, r, q, i > 0, a, rec);
+}
+
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
     __shared__ uint4 s_line[7][256];                                  // every thread's line prefix, one column per thread
     __shared__ u64 s_A[256];                                          // its 16-byte aligned base, or ~0 when not staged
@@ -595,12 +612,7 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
                     }
                     if (eq) meta |= LM_EQ;
                 }
-            } else {
-                ByteReader r, q;
-                r.init(p.buf, a);
-                if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
-                meta = parse_line(p, r, q, i > 0, a, rec);
-            }
+            } else meta = parse_line_slow(p, ws, i, a, rec);
             if (meta & LM_KEEP) p.rec[i] = rec;
             p.lmeta[i] = (u8)meta;
         }
