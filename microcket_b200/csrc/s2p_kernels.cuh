@@ -386,16 +386,16 @@ __device__ __forceinline__ u32 parse_line(const S2PParams &p, R &r, R &q, const 
     return meta;
 }
 
+__device__ __forceinline__ u32 lt21_y(u32 x) {                       // 0x80 in every byte < 0x21
+    const u32 t = (x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu;
+    return ~(t | x) & 0x80808080u;
+}
 static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b);
 
 // ---- word-at-a-time fast path -------------------------------------------------------------------------------------
 // Well-formed lines (single tabs between the first six fields, nothing else below 0x21, digits where numbers belong,
 // RNAME <= 8 bytes) are tokenised with SWAR on 16-byte words instead of byte loops; anything else returns false and goes
 // through parse_line, so the result is identical by construction.
-__device__ __forceinline__ u32 lt21_y(u32 x) {                       // 0x80 in every byte < 0x21
-    const u32 t = (x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu;
-    return ~(t | x) & 0x80808080u;
-}
 __device__ __forceinline__ u32 lt21_mask16(const uint4 &w) {         // bit q set iff byte q of the word is < 0x21 (byte order)
     return gather_flags4(lt21_y(w.x)) | (gather_flags4(lt21_y(w.y)) << 4) | (gather_flags4(lt21_y(w.z)) << 8) | (gather_flags4(lt21_y(w.w)) << 12);
 }
@@ -855,15 +855,39 @@ __device__ __forceinline__ bool mates(const Seg &lone, const Seg &c) {
 }
 __device__ __forceinline__ u32 distal_end(const Seg &s) { return (int)s.leftClip > (int)s.rightClip ? s.right0 : s.pos; }
 
-static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
+// first byte < 0x21 in the 8 bytes of x (0..7), or 8 when there is none
+__device__ __forceinline__ u32 first_ws8(u64 x) {
+    const u32 lo = lt21_y((u32)x), hi = lt21_y((u32)(x >> 32));
+    if (lo) return (u32)(__ffs(lo) - 1) >> 3;
+    if (hi) return 4u + ((u32)(__ffs(hi) - 1) >> 3);
+    return 8u;
+}
+// Exact comparison of the first tokens (QNAMEs) of lines a and b, 8 bytes at a time.  Bytes below 0x21 that are not
+// white space, and leading blanks, are left to the byte loop so that the result is operator>>'s in every case.
+static __device__ __noinline__ bool qname_equal_bytes(const S2PParams &p, u64 pa, u64 pb) {
     ByteReader x, y;
-    x.init(p.buf, ws + (a ? p.nl_pos[a - 1] + 1 : 0));
-    y.init(p.buf, ws + (b ? p.nl_pos[b - 1] + 1 : 0));
+    x.init(p.buf, pa); y.init(p.buf, pb);
     int c = x.next(), d = y.next();
     while (is_blank(c)) c = x.next();
     while (is_blank(d)) d = y.next();
     while (!is_ws(c) && !is_ws(d)) { if (c != d) return false; c = x.next(); d = y.next(); }
     return is_ws(c) && is_ws(d);
+}
+static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
+    const u64 pa = ws + (a ? p.nl_pos[a - 1] + 1 : 0), pb = ws + (b ? p.nl_pos[b - 1] + 1 : 0);
+    GlobalFetch gf; gf.buf = p.buf;
+    for (u32 k = 0;; k += 8) {
+        const u64 x = fetch8(gf, pa + k), y = fetch8(gf, pb + k);
+        const u32 tx = first_ws8(x), ty = first_ws8(y);
+        if (tx == 8 && ty == 8) { if (x != y) return false; continue; }
+        // a token ends inside this word: both must end at the same byte, on real white space, after equal bytes
+        const u32 t = tx < ty ? tx : ty;
+        const int cx = tx < 8 ? (int)((x >> (8 * tx)) & 0xFF) : 'x', cy = ty < 8 ? (int)((y >> (8 * ty)) & 0xFF) : 'x';
+        if ((tx < 8 && !is_ws(cx)) || (ty < 8 && !is_ws(cy)) || (k == 0 && t == 0)) return qname_equal_bytes(p, pa, pb);
+        if (tx != ty) return false;
+        const u64 m = t ? ((1ull << (8 * t)) - 1) : 0;
+        return (x & m) == (y & m);
+    }
 }
 
 // EQ of line q (its QNAME equals line q-1's), evaluating it now when the fused kernel could not
