@@ -117,3 +117,50 @@ def test_device_resident_path(oracle):
     assert bytes(samo[:io.sam_text_len].cpu().numpy().tobytes()) == osam
     assert st.log_text() == ost.log_text() and io.n_pairs == st.pairs
     s.close()
+
+
+def test_sharded_contexts_reproduce_the_selfcircle_log_value(oracle):
+    """Two contexts, each over one shard of whole read groups (multi-GPU layout): counters add up and the thread-0-share
+    self-circle value is settled from the global group indices (mk_s2p_finish_sharded)."""
+    n = 290000                                   # > 2^18 groups: one full reference batch + a final one
+    sam = mk.synth_host(21, "unc", "hg38", 0, n)
+    _, _, ost = oracle.sam2pairs(sam, "unc", threads=8, write_sam=False)
+    cut = n // 2 + 7
+    a = mk.synth_host(21, "unc", "hg38", 0, cut)
+    b = mk.synth_host(21, "unc", "hg38", cut, n - cut)
+    assert a + b == sam
+    # shard 0 must not drop its last group (only the stream's last group is dropped): give it the first group of shard 1
+    first_b = b[:b.index(b"\n", b.index(b"\n") + 1) + 1]
+    ctxs, outs = [], []
+    for data, last in ((a + first_b, False), (b, True)):
+        s = mk.Sam2Pairs(mk.S2PConfig(mode="unc", threads=8, write_sam=False, sharded=True, window_bytes=16 << 20))
+        s.push(data, True)
+        outs.append(s.pull()[0])
+        ctxs.append(s)
+    counts = []
+    for s in ctxs:                               # per-shard group counts (an all-gather in the multi-GPU run)
+        counts.append(s.finish(0, 0).groups)
+    total = sum(counts)
+    stats = [ctxs[0].finish(0, total), ctxs[1].finish(counts[0], total)]
+    assert total == ost.groups
+    for f in ("lowMap", "manyHits", "unpaired", "selfCircle", "trans", "cis10K", "cis1K", "cis0"):
+        assert sum(getattr(x, f) for x in stats) == getattr(ost, f), f
+    op, _, _ = oracle.sam2pairs(sam, "unc", threads=8, write_sam=False)
+    assert outs[0] + outs[1] == op
+    for s in ctxs:
+        s.close()
+
+
+def test_reset_and_kernel_timing(oracle):
+    sam = mk.synth_host(8, "flash", "hg38", 0, 5000)
+    op, _, ost = oracle.sam2pairs(sam, "flash", threads=8, write_sam=False)
+    s = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False))
+    s.enable_timing(True)
+    for _ in range(3):                           # the same context processes the input three times
+        s.reset()
+        p, _, st = s.run(sam)
+        assert p == op and st.log_text() == ost.log_text()
+    t = s.kernel_times()
+    assert t["k_scan_lines"][1] >= 3 and t["k_scan_lines"][0] > 0 and t["k_emit"][1] >= 3
+    assert s.launches() > 0
+    s.close()
