@@ -447,17 +447,12 @@ __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint
                                                      u64 *desc, unsigned long long *counters /* [0] kept, [1] cells */, u32 *ticket) {
     __shared__ u32 s_w[2][UQ_T / 32];
     __shared__ u64 s_base;
-    __shared__ int s_tile;
     const uint4 *in = plan->final_buf ? b1 : b0;
     mk_pair *out = plan->final_buf ? out0 : out1;                 // the buffer the sorted keys are NOT in
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
     const u32 cell_shift = c.total_bits - 2 * c.nb;               // bits below the (bin1,bin2) prefix
-    while (true) {
-        if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= n_tiles) break;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {   // round-robin over a resident grid (tickets measured slower)
         const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
         uint4 r[UQ_ITEMS]; u32 fk = 0, fc = 0, nk = 0, nc = 0;
         uint4 prev = base > 0 && base <= n ? in[base - 1] : make_uint4(0, 0, 0, 0);
@@ -505,6 +500,7 @@ __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint
             }
             if (fk & (1u << k)) { out[ok] = unpack_key(r[k], c, dec_off, dec_id); ++ok; }
         }
+        __syncthreads();                                                // s_w / s_base are reused by the next tile
     }
 }
 

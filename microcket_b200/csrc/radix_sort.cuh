@@ -69,9 +69,10 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(typename P::Bu
         for (int p = 0; p < sch.n_pass; ++p) {
             const u32 d = valid ? P::digit(k, sch.byte_of[p]) : 0u;
             // constant digits (high bytes, unused fields) would serialise 32 ways on one counter: one add per warp instead
-            const u32 d0 = __shfl_sync(0xffffffffu, d, __ffs(vmask) - 1);
-            if (__all_sync(0xffffffffu, !valid || d == d0)) { if (lane == __ffs(vmask) - 1) atomicAdd(&s_hist[p * 256 + d0], (u32)__popc(vmask)); }
-            else if (valid) atomicAdd(&s_hist[p * 256 + d], 1u);
+            if (vmask == 0xffffffffu) {
+                if (__reduce_and_sync(0xffffffffu, d) == __reduce_or_sync(0xffffffffu, d)) { if (lane == 0) atomicAdd(&s_hist[p * 256 + d], 32u); }
+                else atomicAdd(&s_hist[p * 256 + d], 1u);
+            } else if (valid) atomicAdd(&s_hist[p * 256 + d], 1u);
         }
     }
     __syncthreads();

@@ -37,8 +37,8 @@ struct __align__(16) LineRec {       // 48 B, written by K2 for kept lines
 struct __align__(16) GroupRes {      // 32 B, written by K3 for group heads
     u32 posA, posB;
     u16 chrA, chrB;                  // chromosome ids
-    u8 status, strands; u16 n_kept;
-    u32 rid_line, last_line, text_len, sam_len;
+    u8 status, strands; u16 rid_len;   // length of the read id (QNAME of the group's last kept record)
+    u32 rid_off, last_line, text_len, sam_len;   // rid_off: offset of that QNAME from the window start
 };
 
 struct __align__(64) ChrSlot {       // open-addressing table keyed by a 64-bit hash of the name
@@ -401,13 +401,19 @@ __device__ __forceinline__ u32 lt21_mask16(const uint4 &w) {         // bit q se
 }
 // Fetchers: aligned 16- and 8-byte loads from global memory, or from the shared-memory copy of a tile where it covers them
 struct GlobalFetch {
-    const char *buf;
+    const char *buf; u64 A;                                             // A: 16-byte aligned base of the relative accessors
+    __device__ __forceinline__ uint4 ld16r(u32 r) const { return __ldg((const uint4 *)(buf + A + r)); }
+    __device__ __forceinline__ u64 ld8r(u32 r) const { return __ldg((const u64 *)(buf + A + r)); }
+    __device__ __forceinline__ int byter(u32 r) const { return (int)(unsigned char)buf[A + r]; }
     __device__ __forceinline__ uint4 ld16(u64 a) const { return __ldg((const uint4 *)(buf + a)); }
     __device__ __forceinline__ u64 ld8(u64 a) const { return __ldg((const u64 *)(buf + a)); }
     __device__ __forceinline__ int byte(u64 a) const { return (int)(unsigned char)buf[a]; }
 };
 struct TileFetch {
-    const char *buf, *sm; u64 tlo, thi;
+    const char *buf, *sm; u64 tlo, thi, A;
+    __device__ __forceinline__ uint4 ld16r(u32 r) const { return ld16(A + r); }
+    __device__ __forceinline__ u64 ld8r(u32 r) const { return ld8(A + r); }
+    __device__ __forceinline__ int byter(u32 r) const { return byte(A + r); }
     __device__ __forceinline__ uint4 ld16(u64 a) const { return (a >= tlo && a + 16 <= thi) ? *(const uint4 *)(sm + (a - tlo)) : __ldg((const uint4 *)(buf + a)); }
     __device__ __forceinline__ u64 ld8(u64 a) const { return (a >= tlo && a + 8 <= thi) ? *(const u64 *)(sm + (a - tlo)) : __ldg((const u64 *)(buf + a)); }
     __device__ __forceinline__ int byte(u64 a) const { return (a >= tlo && a < thi) ? (int)(unsigned char)sm[a - tlo] : (int)(unsigned char)buf[a]; }
@@ -416,12 +422,23 @@ struct TileFetch {
 // offsets without going back to L1/L2
 struct LineFetch {
     const char *buf; const uint4 *col; u64 A;                           // col[j * 256] = bytes [A + 16 j, A + 16 j + 16)
+    // offsets relative to A: 32-bit arithmetic on the hot path
+    __device__ __forceinline__ uint4 ld16r(u32 r) const { return r + 16 <= 112 ? col[(r >> 4) * 256] : __ldg((const uint4 *)(buf + A + r)); }
+    __device__ __forceinline__ u64 ld8r(u32 r) const { return r + 8 <= 112 ? ((const u64 *)&col[(r >> 4) * 256])[(r >> 3) & 1] : __ldg((const u64 *)(buf + A + r)); }
+    __device__ __forceinline__ int byter(u32 r) const { return (int)((ld8r(r & ~7u) >> (8 * (r & 7u))) & 0xFF); }
     __device__ __forceinline__ uint4 ld16(u64 a) const { return (a >= A && a + 16 <= A + 112) ? col[((a - A) >> 4) * 256] : __ldg((const uint4 *)(buf + a)); }
     __device__ __forceinline__ u64 ld8(u64 a) const {
         return (a >= A && a + 8 <= A + 112) ? ((const u64 *)&col[((a - A) >> 4) * 256])[(a >> 3) & 1] : __ldg((const u64 *)(buf + a));
     }
     __device__ __forceinline__ int byte(u64 a) const { return (int)((ld8(a & ~(u64)7) >> (8 * (a & 7))) & 0xFF); }
 };
+template <class F>
+__device__ __forceinline__ u64 fetch8r(const F &f, u32 r) {           // 8 bytes at any offset relative to f.A
+    const u32 a8 = r & ~7u, sh = (r & 7u) * 8;
+    const u64 lo = f.ld8r(a8);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (f.ld8r(a8 + 8) << (64 - sh));
+}
 template <class F>
 __device__ __forceinline__ u64 fetch8(const F &f, u64 abs) {          // 8 bytes at any offset, from aligned loads
     const u64 a8 = abs & ~(u64)7;
@@ -450,15 +467,15 @@ __device__ __forceinline__ u32 pop_lowest128(u32 &m0, u32 &m1, u32 &m2, u32 &m3)
 }
 // decimal field of `len` (1..10) characters starting at abs; false if a non-digit is found
 template <class F>
-__device__ __forceinline__ bool dec_field(const F &buf, u64 abs, u32 len, u32 &out) {
-    u64 x = fetch8(buf, abs);
+__device__ __forceinline__ bool dec_field(const F &buf, u32 abs, u32 len, u32 &out) {
+    u64 x = fetch8r(buf, abs);
     u32 v = 0; bool ok = true;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if ((u32)k < len) { const u32 d = (u32)((x >> (8 * k)) & 0xFF) - '0'; ok &= d <= 9u; v = v * 10u + d; }
     }
     if (len > 8) {
-        x = fetch8(buf, abs + 8);
+        x = fetch8r(buf, abs + 8);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if ((u32)(8 + k) < len) { const u32 d = (u32)((x >> (8 * k)) & 0xFF) - '0'; ok &= d <= 9u; v = v * 10u + d; }
@@ -478,7 +495,7 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     const u32 s = (u32)(a - A);
     uint4 w[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) w[j] = f.ld16(A + 16 * j);
+    for (int j = 0; j < 7; ++j) w[j] = f.ld16r(16 * j);
     if ((char)((w[0].x >> 0) & 0xFF) == '@' && s == 0) return false;   // cheap early-out; the exact test is below
     u32 m0 = lt21_mask16(w[0]) | (lt21_mask16(w[1]) << 16), m1 = lt21_mask16(w[2]) | (lt21_mask16(w[3]) << 16);
     u32 m2 = lt21_mask16(w[4]) | (lt21_mask16(w[5]) << 16), m3 = lt21_mask16(w[6]);
@@ -490,20 +507,20 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     if (t5 >= 112 - s) return false;                                  // six separators inside the words we looked at
     // every separator must be a single TAB, every field non-empty
     if (t0 == 0 || t1 == t0 + 1 || t2 == t1 + 1 || t3 == t2 + 1 || t4 == t3 + 1 || t5 == t4 + 1) return false;
-    if (f.byte(a + t0) != '\t' || f.byte(a + t1) != '\t' || f.byte(a + t2) != '\t' || f.byte(a + t3) != '\t' || f.byte(a + t4) != '\t' ||
-        f.byte(a + t5) != '\t') return false;
-    if (f.byte(a) == '@') return false;
+    if (f.byter(s + t0) != '\t' || f.byter(s + t1) != '\t' || f.byter(s + t2) != '\t' || f.byter(s + t3) != '\t' || f.byter(s + t4) != '\t' ||
+        f.byter(s + t5) != '\t') return false;
+    if (f.byter(s) == '@') return false;
     const u32 l_flag = t1 - t0 - 1, l_name = t2 - t1 - 1, l_pos = t3 - t2 - 1, l_mapq = t4 - t3 - 1;
     if (l_flag > 5 || l_name > 8 || l_pos > 10 || l_mapq > 3) return false;
     u32 flag, pos, mapq;
-    if (!dec_field(f, a + t0 + 1, l_flag, flag)) return false;
-    if (!dec_field(f, a + t2 + 1, l_pos, pos)) return false;
-    if (!dec_field(f, a + t3 + 1, l_mapq, mapq)) return false;
+    if (!dec_field(f, s + t0 + 1, l_flag, flag)) return false;
+    if (!dec_field(f, s + t2 + 1, l_pos, pos)) return false;
+    if (!dec_field(f, s + t3 + 1, l_mapq, mapq)) return false;
     tok.t0 = t0;
     if (WANT_Q) {                                                      // QNAME words for the neighbour-lane comparison
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            u64 x = (u32)(8 * k) < t0 ? fetch8(f, a + 8 * k) : 0;
+            u64 x = (u32)(8 * k) < t0 ? fetch8r(f, s + 8 * k) : 0;
             if (t0 < (u32)(8 * k + 8) && t0 > (u32)(8 * k)) x &= (1ull << (8 * (t0 - 8 * k))) - 1;
             tok.q[k] = x;
         }
@@ -513,7 +530,7 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     if (mapq < (u32)p.min_mapq || (flag & 0x700u)) return true;       // pairutil.h:157-161
     meta = LM_KEEP;
     // RNAME: FNV-1a over its bytes, same as the byte loop
-    u64 name8 = fetch8(f, a + t1 + 1);
+    u64 name8 = fetch8r(f, s + t1 + 1);
     if (l_name < 8) name8 &= (1ull << (8 * l_name)) - 1;
     u64 h = 0xCBF29CE484222325ull;
 #pragma unroll
@@ -525,7 +542,7 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     const u32 l_cig = t5 - t4 - 1;
     u64 x = 0;
     for (u32 k = 0; k < l_cig; ++k) {
-        if ((k & 7) == 0) x = fetch8(f, a + t4 + 1 + k);
+        if ((k & 7) == 0) x = fetch8r(f, s + t4 + 1 + k);
         const int c = (int)(x & 0xFF); x >>= 8;
         const u32 d = (u32)(c - '0');
         if (d <= 9u) { val = val * 10u + d; continue; }
@@ -599,15 +616,16 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
                     if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_slow(p, ws, i, i - 1);   // operator>> skips leading blanks
                     else if (tid > 0 && s_A[tid - 1] != ~(u64)0) {
                         LineFetch lp; lp.buf = p.buf; lp.col = &s_line[0][tid - 1]; lp.A = s_A[tid - 1];
+                        const u32 so = (u32)(a - lf.A), sp = (u32)(pa - lp.A);
                         eq = true;
                         for (u32 k = 0; k < tok.t0 && eq; k += 8) {
-                            u64 x = fetch8(lf, a + k), y = fetch8(lp, pa + k);
+                            u64 x = fetch8r(lf, so + k), y = fetch8r(lp, sp + k);
                             if (tok.t0 - k < 8) { const u64 m = (1ull << (8 * (tok.t0 - k))) - 1; x &= m; y &= m; }
                             eq = x == y;
                         }
-                        eq = eq && is_ws(lp.byte(pa + tok.t0));
+                        eq = eq && is_ws(lp.byter(sp + tok.t0));
                     } else {
-                        GlobalFetch gf; gf.buf = p.buf;
+                        GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
                         eq = qname_eq_fetch(gf, a, pa, tok.t0);
                     }
                     if (eq) meta |= LM_EQ;
@@ -762,7 +780,7 @@ static __global__ void __launch_bounds__(FZ_THREADS) k_scan_parse(S2PParams p) {
                         bool cmp = false; u64 prev_abs = 0;              // previous line's start, when it is known here
                         if (id >= 2 && id - 2 >= r0) { cmp = true; prev_abs = tbase + (u32)s_nl[id - 2 - r0] + 1; }
                         else if (id == 1 && has_initial && r0 == 0) { cmp = true; prev_abs = initial_abs; }
-                        TileFetch tf; tf.buf = p.buf; tf.sm = tl; tf.tlo = tbase; tf.thi = tbase + loaded;
+                        TileFetch tf; tf.buf = p.buf; tf.sm = tl; tf.tlo = tbase; tf.thi = tbase + loaded; tf.A = abs0 & ~(u64)15;
                         FastTok tok;
                         if (parse_line_fast<TileFetch, false>(p, tf, abs0, st->total, tok, rec, meta)) {
                             if (cmp && qname_eq_fetch(tf, abs0, prev_abs, tok.t0)) meta |= LM_EQ;
@@ -875,7 +893,7 @@ static __device__ __noinline__ bool qname_equal_bytes(const S2PParams &p, u64 pa
 }
 static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
     const u64 pa = ws + (a ? p.nl_pos[a - 1] + 1 : 0), pb = ws + (b ? p.nl_pos[b - 1] + 1 : 0);
-    GlobalFetch gf; gf.buf = p.buf;
+    GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
     for (u32 k = 0;; k += 8) {
         const u64 x = fetch8(gf, pa + k), y = fetch8(gf, pb + k);
         const u32 tx = first_ws8(x), ty = first_ws8(y);
@@ -965,7 +983,11 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
         }
         // ---- resolve
         GroupRes g; g.status = ST_NONE; g.posA = g.posB = 0; g.chrA = g.chrB = 0; g.strands = 0;
-        g.n_kept = (u16)(n > 65535u ? 65535u : n); g.rid_line = prev; g.last_line = prev; g.text_len = 0; g.sam_len = sam_len;
+        {
+            const LineRec *rp = &p.rec[prev];
+            g.rid_len = rp->qname_len; g.rid_off = (prev ? p.nl_pos[prev - 1] + 1 : 0) + rp->qname_off;
+        }
+        g.last_line = prev; g.text_len = 0; g.sam_len = sam_len;
         u32 p1 = 0, p2 = 0; u16 c1 = 0, c2 = 0; bool m1 = false, m2 = false; bool have = false, ordered = false;
         const float ratio = p.ratio;
         if (p.mode == 0) {                   // flash2pairs.h:25-154
@@ -1068,7 +1090,7 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
             g.chrA = (u16)ca->id; g.chrB = (u16)cb->id;
             if (g.status != ST_SELFCIRCLE) {
                 meta |= LM_EMIT;
-                g.text_len = (u32)p.rec[prev].qname_len + ca->len + cb->len + dec_digits(p1) + dec_digits(p2) + 9u;
+                g.text_len = (u32)g.rid_len + ca->len + cb->len + dec_digits(p1) + dec_digits(p2) + 9u;
             }
         }
         if (!(meta & LM_EMIT)) g.sam_len = 0;
@@ -1106,13 +1128,11 @@ __device__ __forceinline__ char *put_name(char *out, const ChrSlot *c) {
 }
 struct RidInfo { u64 abs; u32 len; };                                          // where the group's read id sits in the SAM text
 __device__ __forceinline__ RidInfo rid_info(const S2PParams &p, u64 ws, const GroupRes &g) {
-    const u32 rl = g.rid_line;
-    const LineRec *rr = &p.rec[rl];
-    RidInfo r; r.len = rr->qname_len; r.abs = ws + (rl ? p.nl_pos[rl - 1] + 1 : 0) + rr->qname_off;
+    RidInfo r; r.len = g.rid_len; r.abs = ws + g.rid_off;
     return r;
 }
 __device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInfo &rid, const GroupRes &g, char *out) {
-    GlobalFetch gf; gf.buf = p.buf;
+    GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
     for (u32 k = 0; k < rid.len; k += 8) { const u32 n = rid.len - k < 8 ? rid.len - k : 8; out = put_bytes8(out, fetch8(gf, rid.abs + k), n); }
     *out++ = '\t';
     out = put_name(out, &p.chr[p.id_to_slot[g.chrA]]);
