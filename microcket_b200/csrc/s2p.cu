@@ -33,7 +33,7 @@ struct S2PCtx : mk_ctx {
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
-    int grid_scan = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0, scan_nt = 4;
+    int grid_scan = 0, grid_scan4 = 0, scan_occ4 = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0, scan_nt = 4;
     bool fused = false;
     u64 launches = 0;
     // host streaming state
@@ -114,6 +114,7 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
         c->launches -= 1;
     } else {
         if (c->scan_nt == 8) k_scan_lines<8><<<c->grid_scan8, S2P_SCAN_THREADS, 8 * 8192, s>>>(p);
+        else if (c->scan_occ4) k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
         else k_scan_lines<4><<<c->grid_scan, S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
         mark(1);
         k_parse<<<c->grid_gs, 256, 0, s>>>(p);
@@ -237,6 +238,9 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<8>, S2P_SCAN_THREADS, 8 * 8192);
     c->grid_scan8 = sms * std::max(1, std::min(occ, 4));
     if (getenv("MICROCKET_SCAN_NT")) c->scan_nt = atoi(getenv("MICROCKET_SCAN_NT"));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<4, 4>, S2P_SCAN_THREADS, 4 * 8192);
+    c->grid_scan4 = sms * std::max(1, std::min(occ, 4));
+    c->scan_occ4 = !(getenv("MICROCKET_SCAN_OCC4") && !atoi(getenv("MICROCKET_SCAN_OCC4")));   // 4 CTAs/SM (64 registers): 5.6 vs 6.3 ms per 19.8 GB
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, std::min(occ, 4));
     c->grid_gs = sms * 8;

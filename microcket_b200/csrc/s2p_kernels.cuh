@@ -258,8 +258,8 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
     }
 }
 
-template <int NT>
-static __global__ void __launch_bounds__(S2P_SCAN_THREADS, 3) k_scan_lines(S2PParams p) {
+template <int NT, int MINB = 3>
+static __global__ void __launch_bounds__(S2P_SCAN_THREADS, MINB) k_scan_lines(S2PParams p) {
     WinState *st = p.st;
     scan_lines_body<NT>(p.buf, st->ws, st->we, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
 }
