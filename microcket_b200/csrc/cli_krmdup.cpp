@@ -3,6 +3,7 @@
 // src/preprocess/krmdup.pipe.cpp).  Built twice: -DKRMDUP_PIPE writes interleaved FASTQ to stdout instead of
 // <prefix>.read1.fq / <prefix>.read2.fq.
 #include <getopt.h>
+#include <time.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,7 +83,11 @@ int main(int argc, char *argv[]) {
     FILE *fin = (readx[0] == '-' && readx[1] == '\0') ? fopen("/dev/stdin", "rb") : fopen(readx, "rb");
     if (!fin) { cerr << "Error: read fastq failed!\n"; return 10; }
     mk_ctx *ctx = NULL;
+    const bool trace = getenv("MICROCKET_TRACE") != NULL;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto since = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - ts0.tv_sec) + 1e-9 * (t.tv_nsec - ts0.tv_nsec); };
     if (mk_dedup_create(&cfg, &ctx) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
+    if (trace) fprintf(stderr, "[krmdup] context ready after %.3f s\n", since());
     const size_t IN = 64u << 20, OUT = 32u << 20;
     vector<char> in(IN), o1(OUT), o2(OUT);
     auto drain = [&]() -> int {
@@ -111,6 +116,7 @@ int main(int argc, char *argv[]) {
 #else
     fflush(stdout);
 #endif
+    if (trace) fprintf(stderr, "[krmdup] streaming done after %.3f s\n", since());
     ofstream flog((string(prefix) + ".log").c_str(), ios::app);
     if (flog.fail()) { cerr << "Error: write log failed!\n"; return 10; }
     flog << "Total\t" << st.uniq + st.dup + st.discard << "\nUniq\t" << st.uniq << "\nDup\t" << st.dup << "\nDiscard\t" << st.discard << '\n';

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <deque>
 #include <vector>
+#include <chrono>
 #include "ctx.h"
 #include "s2p_kernels.cuh"
 #include "radix_sort.cuh"
@@ -318,8 +319,12 @@ static int dd_check(mk_ctx *x, DedupCtx **c) {
 }
 
 // one window: `n` bytes of complete lines already in h_in; returns bytes consumed (whole batches unless last)
+static double dd_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     cudaStream_t s = c->s;
+    const bool trace = getenv("MICROCKET_TRACE") != nullptr;
+    const double t0 = dd_now();
     // the window can insert at most one key per pair: keep the table at most ~60 % full
     const u64 bound = n / 40 + 16;                       // a pair of records needs at least 8 newlines + ids + bases
     for (int w = 0; w < 2; ++w) {
@@ -346,6 +351,7 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     MK_CUDA(cudaMemcpyAsync(&hst, c->d_state.p, sizeof hst, cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
     if (hst.err & FQ_ERR_LINES) { mk_set_error("krmdup: too many lines in one window"); return MK_ERR_CAPACITY; }
+    const double t1 = dd_now();
     const u64 np = hst.n_pairs;
     *consumed = (size_t)hst.consumed;
     if (np == 0) return MK_OK;
@@ -363,11 +369,14 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     MK_CUDA(cudaMemcpyAsync(&hst, c->d_state.p, sizeof hst, cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
     if (hst.err & FQ_ERR_OUT) { mk_set_error("krmdup: output buffer too small"); return MK_ERR_CAPACITY; }
+    const double t2 = dd_now();
     c->hcount[0] += hst.inserted[0]; c->hcount[1] += hst.inserted[1];
     MK_CUDA(cudaMemsetAsync((char *)c->d_state.p + offsetof(FqState, inserted), 0, 8, s));
     c->pairs_total += np;
     if (hst.out1) { std::vector<char> v(hst.out1); MK_CUDA(cudaMemcpyAsync(v.data(), c->d_out1.p, hst.out1, cudaMemcpyDeviceToHost, s)); MK_CUDA(cudaStreamSynchronize(s)); c->q1.emplace_back(std::move(v)); }
     if (hst.out2) { std::vector<char> v(hst.out2); MK_CUDA(cudaMemcpyAsync(v.data(), c->d_out2.p, hst.out2, cudaMemcpyDeviceToHost, s)); MK_CUDA(cudaStreamSynchronize(s)); c->q2.emplace_back(std::move(v)); }
+    if (trace) fprintf(stderr, "[krmdup window] %zu bytes, %llu pairs: h2d+scan+keys %.1f ms, sort+mark+layout+copy %.1f ms, d2h %.1f ms\n",
+                       n, (unsigned long long)np, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (dd_now() - t2) * 1e3);
     return MK_OK;
 }
 

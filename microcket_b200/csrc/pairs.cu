@@ -14,6 +14,7 @@
 struct K64 {                       // keys only
     typedef u64 Key;
     static constexpr int ITEMS = 16;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr bool HAS_VAL = false;
     struct Bufs { u64 *k[2]; u32 *v[2]; };
     __device__ static __forceinline__ u32 digit(const u64 &k, int byte) { return (u32)(k >> (8 * byte)) & 255u; }

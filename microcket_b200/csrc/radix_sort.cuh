@@ -33,6 +33,7 @@ struct RadixSchedule { int n_pass; int byte_of[RS_MAX_PASSES]; };   // LSD order
 struct KV64 {
     typedef u64 Key;
     static constexpr int ITEMS = 16;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr bool HAS_VAL = true;
     struct Bufs { u64 *k[2]; u32 *v[2]; };
     __device__ static __forceinline__ u32 digit(const u64 &k, int byte) { return (u32)(k >> (8 * byte)) & 255u; }
@@ -42,6 +43,7 @@ struct KV64 {
 struct Rec16 {
     typedef uint4 Key;
     static constexpr int ITEMS = 8;
+    static constexpr int MIN_BLOCKS = 4;          // 64 registers: four resident tiles per SM hide the look-back and scatter latency
     static constexpr bool HAS_VAL = false;
     struct Bufs { uint4 *k[2]; u32 *v[2]; };
     __device__ static __forceinline__ u32 digit(const uint4 &k, int byte) {
@@ -115,7 +117,7 @@ static __global__ void __launch_bounds__(256) k_radix_plan(RadixPlan *plan, u64 
 #define RS_VAL(x) ((x) & 0x3FFFFFFFu)
 
 template <class P>
-static __global__ void __launch_bounds__(RS_THREADS) k_radix_pass(typename P::Bufs bufs, u64 n, int pass, int byte, RadixPlan *plan,
+static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass(typename P::Bufs bufs, u64 n, int pass, int byte, RadixPlan *plan,
                                                           u32 *desc /* n_tiles * 256 */, int iota_vals) {
     constexpr int ITEMS = P::ITEMS;
     constexpr int TILE = RS_THREADS * ITEMS;
