@@ -266,9 +266,22 @@ def main():
     dk = {k: (kt1[k][0] - kt0[k][0], kt1[k][1] - kt0[k][1]) for k in kt1}
     dom = max(dk, key=lambda k: dk[k][0])
     dom_ms, dom_n = dk[dom]
-    lines = st.lines / max(1, 1)                       # lines of one pass (reset() clears the stream totals each step)
-    alg_bytes_step = {"k_scan_lines": nbytes + 4 * lines, "k_parse": nbytes, "k_group": nbytes, "k_emit": nbytes + 72.0 * n_pairs,
-                      "k_copy_sam": nbytes}[dom]
+    lines = float(st.lines)                            # lines of one pass (reset() clears the stream totals each step)
+    groups = float(st.groups)
+    # Algorithmic bytes per step of every kernel: what the kernel has to read and write, not what it
+    # happens to move.  Only the newline scan touches every SAM byte; the parser needs the head of each line (the 112 bytes
+    # it fetches cover QNAME..CIGAR), its newline offset and flag byte, and writes one 48-byte record per line (an upper
+    # bound is avoided by counting one record per read group only); the group kernel reads those records and writes a
+    # 32-byte result per group; emit reads the results and the read id (~40 B) and writes ~72 B of text + 16 B packed.
+    alg = {"k_scan_chunks": nbytes + 4 * lines, "k_chunk_index": 8 * lines,
+           "k_parse": 117.0 * lines + 48.0 * groups, "k_group": lines + 80.0 * groups,
+           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 0.0}
+    per_kernel = {}
+    for k, (ms_k, n_k) in dk.items():
+        if ms_k > 0 and n_k > 0:
+            gbs = alg[k] * args.steps / (ms_k / 1e3) / 1e9
+            per_kernel[k] = {"ms_per_step": ms_k / args.steps, "launches_per_step": n_k / args.steps, "algorithmic_GBps": gbs, "frac": gbs / peak}
+    alg_bytes_step = alg[dom]
     launches_per_step = max(1.0, dom_n / args.steps)
     achieved = (alg_bytes_step / launches_per_step) / (dom_ms / max(dom_n, 1) / 1e3) / 1e9 if dom_ms > 0 else 0.0
     stage_ms = sum(v[0] for v in dk.values()) / args.steps
@@ -284,7 +297,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
                 "s2p_stage": {"ms_per_step": stage_ms, "GBps": (nbytes + 72.0 * n_pairs) / (stage_ms / 1e3) / 1e9 if stage_ms else 0.0,
                               "frac": ((nbytes + 72.0 * n_pairs) / (stage_ms / 1e3) / 1e9 / peak) if stage_ms else 0.0},
-                "kernels_ms_per_step": {k: v[0] / args.steps for k, v in dk.items()}}
+                "kernels": per_kernel}
 
     # ---- end to end through the host-buffer C ABI (pinned host SAM in; pairs text, packed pairs and COO out)
     e2e = None

@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "microcket_b200.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
         return LIB_PATH
-    r = subprocess.run(["make", "-C", CSRC, "all"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j8", "-C", CSRC, "all"], capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode:
@@ -258,10 +258,10 @@ class Sam2Pairs:
 
     def kernel_times(self):
         """→ {name: (total_ms, launches)} measured with CUDA events on the launching stream."""
-        ms = (C.c_double * 5)()
-        cnt = (C.c_uint64 * 5)()
+        ms = (C.c_double * 6)()
+        cnt = (C.c_uint64 * 6)()
         self.lib.check(self.lib.L.mk_s2p_kernel_times(self.h, ms, cnt))
-        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_lines", "k_parse", "k_group", "k_emit", "k_copy_sam"))}
+        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index"))}
 
     def push_ptr(self, ptr, n, is_last=False):
         """push() from a raw host pointer (e.g. a pinned torch tensor): no Python-side copy."""

@@ -121,6 +121,8 @@ int main(int argc, char *argv[]) {
     if (flog.fail()) { cerr << "Error: write log failed!\n"; return 10; }
     flog << "Total\t" << st.uniq + st.dup + st.discard << "\nUniq\t" << st.uniq << "\nDup\t" << st.dup << "\nDiscard\t" << st.discard << '\n';
     flog.close();
+    if (trace) fprintf(stderr, "[krmdup] log written after %.3f s\n", since());
     mk_destroy(ctx);
+    if (trace) fprintf(stderr, "[krmdup] context destroyed after %.3f s\n", since());
     return 0;
 }

@@ -244,14 +244,17 @@ struct DedupCtx : mk_ctx {
     DevBuf d_in, d_state, d_nl, d_desc, d_rec0, d_rec1, d_cls, d_eoff, d_btab, d_ldesc, d_out1, d_out2;
     DevBuf d_hset[2]; u64 hslots[2] = {0, 0}; u64 hcount[2] = {0, 0};
     RadixWs rws;
-    PinBuf h_in;
-    std::vector<char> pend;
+    PinBuf h_in, h_out1, h_out2;                   // pinned: the window being filled by push(); the last window's kept records
+    size_t fill = 0;                               // bytes of h_in filled so far
+    size_t ho_len[2] = {0, 0}, ho_off[2] = {0, 0}; // undrained part of h_out1 / h_out2
     bool finished = false;
     std::deque<std::vector<char>> q1, q2; size_t q1_off = 0, q2_off = 0;
     u64 pairs_total = 0;
     DedupCtx() { kind = MK_CTX_DEDUP; }
     ~DedupCtx() override { cudaSetDevice(cfg.device); if (s) cudaStreamDestroy(s); }
 };
+
+static double dd_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" void mk_dedup_default_cfg(mk_dedup_cfg *c) {
     memset(c, 0, sizeof *c);
@@ -280,7 +283,11 @@ extern "C" int mk_dedup_create(const mk_dedup_cfg *cfg, mk_ctx **out) {
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { mk_set_error("no CUDA device: microcket_b200 has no CPU fallback"); return MK_ERR_CUDA; }
+    const bool trace = getenv("MICROCKET_TRACE") != nullptr;
+    const double t_start = dd_now();
     MK_CUDA(cudaSetDevice(cfg->device));
+    MK_CUDA(cudaFree(0));
+    if (trace) fprintf(stderr, "[krmdup create] CUDA context %.3f s\n", dd_now() - t_start);
     DedupCtx *c = new DedupCtx();
     c->cfg = *cfg;
     c->W = cfg->window_bytes ? cfg->window_bytes : (size_t)256 << 20;
@@ -298,7 +305,10 @@ extern "C" int mk_dedup_create(const mk_dedup_cfg *cfg, mk_ctx **out) {
     A(c->d_desc.alloc((size_t)c->n_desc * 8)); A(c->d_rec0.alloc((size_t)c->cap_pairs * 16)); A(c->d_rec1.alloc((size_t)c->cap_pairs * 16));
     A(c->d_cls.alloc(c->cap_pairs)); A(c->d_eoff.alloc((size_t)c->cap_pairs * 8)); A(c->d_btab.alloc((size_t)(c->cap_pairs / FQ_BATCH + 4) * 32));
     A(c->d_ldesc.alloc((size_t)c->n_tiles_cap * 4 * 8)); A(c->d_out1.alloc(c->W + 64)); A(c->d_out2.alloc(c->W + 64));
-    A(c->rws.alloc(c->cap_pairs)); A(c->h_in.alloc(c->W + 64));
+    A(c->rws.alloc(c->cap_pairs));
+    if (trace) fprintf(stderr, "[krmdup create] + device buffers %.3f s\n", dd_now() - t_start);
+    A(c->h_in.alloc(c->W + 64)); A(c->h_out1.alloc(c->W + 64)); A(c->h_out2.alloc(c->W + 64));
+    if (trace) fprintf(stderr, "[krmdup create] + pinned buffers %.3f s\n", dd_now() - t_start);
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
     cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking);
@@ -319,8 +329,6 @@ static int dd_check(mk_ctx *x, DedupCtx **c) {
 }
 
 // one window: `n` bytes of complete lines already in h_in; returns bytes consumed (whole batches unless last)
-static double dd_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
 static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     cudaStream_t s = c->s;
     const bool trace = getenv("MICROCKET_TRACE") != nullptr;
@@ -373,8 +381,19 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     c->hcount[0] += hst.inserted[0]; c->hcount[1] += hst.inserted[1];
     MK_CUDA(cudaMemsetAsync((char *)c->d_state.p + offsetof(FqState, inserted), 0, 8, s));
     c->pairs_total += np;
-    if (hst.out1) { std::vector<char> v(hst.out1); MK_CUDA(cudaMemcpyAsync(v.data(), c->d_out1.p, hst.out1, cudaMemcpyDeviceToHost, s)); MK_CUDA(cudaStreamSynchronize(s)); c->q1.emplace_back(std::move(v)); }
-    if (hst.out2) { std::vector<char> v(hst.out2); MK_CUDA(cudaMemcpyAsync(v.data(), c->d_out2.p, hst.out2, cudaMemcpyDeviceToHost, s)); MK_CUDA(cudaStreamSynchronize(s)); c->q2.emplace_back(std::move(v)); }
+    // kept records: DMA into the pinned output buffers; whatever the caller has not pulled from the previous window is
+    // moved to the overflow queues first (only when several windows are pushed between two pulls)
+    for (int w = 0; w < 2; ++w) {
+        if (c->ho_off[w] < c->ho_len[w]) {
+            const char *src = (w ? c->h_out2 : c->h_out1).as<char>() + c->ho_off[w];
+            (w ? c->q2 : c->q1).emplace_back(src, src + (c->ho_len[w] - c->ho_off[w]));
+        }
+        c->ho_len[w] = c->ho_off[w] = 0;
+    }
+    if (hst.out1) MK_CUDA(cudaMemcpyAsync(c->h_out1.p, c->d_out1.p, hst.out1, cudaMemcpyDeviceToHost, s));
+    if (hst.out2) MK_CUDA(cudaMemcpyAsync(c->h_out2.p, c->d_out2.p, hst.out2, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    c->ho_len[0] = hst.out1; c->ho_len[1] = hst.out2;
     if (trace) fprintf(stderr, "[krmdup window] %zu bytes, %llu pairs: h2d+scan+keys %.1f ms, sort+mark+layout+copy %.1f ms, d2h %.1f ms\n",
                        n, (unsigned long long)np, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (dd_now() - t2) * 1e3);
     return MK_OK;
@@ -383,31 +402,28 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
 extern "C" int mk_dedup_push(mk_ctx *x, const char *bytes, size_t n, int is_last) {
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     if (c->finished) { mk_set_error("mk_dedup_push after the last chunk"); return MK_ERR_STATE; }
-    if (n) c->pend.insert(c->pend.end(), bytes, bytes + n);
-    if (is_last && !c->pend.empty() && c->pend.back() != '\n') c->pend.push_back('\n');
+    char *h = c->h_in.as<char>();
     size_t off = 0;
     while (true) {
-        const size_t avail = c->pend.size() - off;
-        if (avail == 0 || (avail < c->W && !is_last)) break;
-        size_t take = std::min(avail, c->W);
-        const bool final_chunk = is_last && take == avail;
-        const char *base = c->pend.data() + off;
+        const size_t take = std::min(c->W - c->fill, n - off);
+        if (take) { memcpy(h + c->fill, bytes + off, take); c->fill += take; off += take; }
+        const bool final_chunk = is_last && off == n;
+        if (c->fill < c->W && !final_chunk) break;                       // wait for more input
+        if (c->fill == 0) break;
+        if (final_chunk && h[c->fill - 1] != '\n') h[c->fill++] = '\n';   // getline accepts a last line without '\n' (room: W + 64)
+        size_t len = c->fill;
         if (!final_chunk) {
-            const void *nl = memrchr(base, '\n', take);
+            const void *nl = memrchr(h, '\n', len);
             if (!nl) { mk_set_error("krmdup: a line longer than the window"); return MK_ERR_CAPACITY; }
-            take = (size_t)((const char *)nl - base) + 1;
+            len = (size_t)((const char *)nl - h) + 1;
         }
-        memcpy(c->h_in.p, base, take);
         size_t consumed = 0;
-        MK_TRY(dd_window(c, take, final_chunk, &consumed));
-        if (final_chunk) { off += take; break; }
-        if (consumed == 0) {
-            if (take < c->W / 2 && !is_last) break;                  // not even one batch yet: wait for more input
-            mk_set_error("krmdup: one 65 536-pair batch does not fit the window (%zu bytes)", c->W); return MK_ERR_CAPACITY;
-        }
-        off += consumed;
+        MK_TRY(dd_window(c, len, final_chunk, &consumed));
+        if (final_chunk) { c->fill = 0; break; }
+        if (consumed == 0) { mk_set_error("krmdup: one 65 536-pair batch does not fit the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
+        memmove(h, h + consumed, c->fill - consumed);                    // whole batches only: the rest opens the next window
+        c->fill -= consumed;
     }
-    if (off) c->pend.erase(c->pend.begin(), c->pend.begin() + (long)off);
     if (is_last) c->finished = true;
     return MK_OK;
 }
@@ -427,6 +443,9 @@ static size_t dd_drain(std::deque<std::vector<char>> &q, size_t &qoff, char *out
 extern "C" int mk_dedup_pull(mk_ctx *x, char *r1, size_t cap1, size_t *n1, char *r2, size_t cap2, size_t *n2) {
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     size_t a = dd_drain(c->q1, c->q1_off, r1, cap1), b = dd_drain(c->q2, c->q2_off, r2, cap2);
+    // then the last window's records, straight from the pinned buffers
+    if (r1 && c->q1.empty() && a < cap1) { const size_t m = std::min(cap1 - a, c->ho_len[0] - c->ho_off[0]); memcpy(r1 + a, c->h_out1.as<char>() + c->ho_off[0], m); a += m; c->ho_off[0] += m; }
+    if (r2 && c->q2.empty() && b < cap2) { const size_t m = std::min(cap2 - b, c->ho_len[1] - c->ho_off[1]); memcpy(r2 + b, c->h_out2.as<char>() + c->ho_off[1], m); b += m; c->ho_off[1] += m; }
     if (n1) *n1 = a;
     if (n2) *n2 = b;
     return MK_OK;

@@ -31,6 +31,8 @@ struct S2PCtx : mk_ctx {
     size_t W = 0, in_cap = 0; u32 cap_lines = 0, n_desc = 0, sc_cap = 0;
     u32 chr_slots = 0, chr_cap = 0, sc_cap_dev = 0;
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
+    u32 n_chunks_cap = 0; bool scan_chunks = true;
+    DevBuf d_cklist, d_ckcnt;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
     int grid_scan = 0, grid_scan4 = 0, scan_occ4 = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0, scan_nt = 4;
@@ -86,6 +88,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     S2PParams p;
     memset(&p, 0, sizeof p);
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
+    p.ck_list = c->d_cklist.as<u32>(); p.ck_cnt = c->d_ckcnt.as<u32>(); p.ck_pre = p.ck_cnt + c->n_chunks_cap; p.n_chunks_cap = c->n_chunks_cap;
     p.rec = c->d_rec.as<LineRec>(); p.res = c->d_res.as<GroupRes>(); p.sam_dst = c->d_samdst.as<u32>();
     p.desc_scan = c->d_desc.as<u64>(); p.desc_emitA = p.desc_scan + c->n_desc; p.desc_emitB = p.desc_emitA + c->n_desc;
     p.wave_scan = p.desc_emitB + c->n_desc; p.wave_emitA = p.wave_scan + c->n_desc; p.wave_emitB = p.wave_emitA + c->n_desc;
@@ -113,9 +116,18 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
         mark(1); mark(2);                                        // reported under k_scan_lines; k_parse stays 0
         c->launches -= 1;
     } else {
-        if (c->scan_nt == 8) k_scan_lines<8><<<c->grid_scan8, S2P_SCAN_THREADS, 8 * 8192, s>>>(p);
-        else if (c->scan_occ4) k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
-        else k_scan_lines<4><<<c->grid_scan, S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
+        if (c->scan_chunks) {
+            // chunked scan (no look-back); the look-back kernel only does work when a chunk overflowed its slot list
+            k_scan_chunks<<<(c->n_chunks_cap + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, s>>>(p);
+            mark(6);
+            k_chunk_prefix<<<1, 1024, 0, s>>>(p);
+            k_chunk_compact<<<(c->n_chunks_cap + 7) / 8, 256, 0, s>>>(p);
+            k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 1);
+            c->launches += 3;
+        }
+        else if (c->scan_nt == 8) k_scan_lines<8><<<c->grid_scan8, S2P_SCAN_THREADS, 8 * 8192, s>>>(p, 0);
+        else if (c->scan_occ4) k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 0);
+        else k_scan_lines<4><<<c->grid_scan, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 0);
         mark(1);
         k_parse<<<c->grid_gs, 256, 0, s>>>(p);
         mark(2);
@@ -148,7 +160,8 @@ extern "C" int mk_s2p_enable_timing(mk_ctx *x, int on) {
     return MK_OK;
 }
 
-// ms[k], count[k] for k = 0 scan_lines, 1 parse, 2 group, 3 emit, 4 copy_sam (accumulated since creation)
+// ms[k], count[k] for k = 0 newline scan, 1 parse, 2 group, 3 emit, 4 copy_sam, 5 scan index (prefix + compaction + the
+// look-back fallback's early exit) (accumulated since creation)
 extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
     if (!x || x->kind != MK_CTX_S2P || !ms || !count) { mk_set_error("mk_s2p_kernel_times: bad argument"); return MK_ERR_ARG; }
     S2PCtx *c = (S2PCtx *)x;
@@ -156,6 +169,7 @@ extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
     cudaDeviceSynchronize();
     timing_collect(c);
     for (int k = 0; k < 5; ++k) { ms[k] = c->k_ms[k]; count[k] = c->k_cnt[k]; }
+    ms[5] = c->k_ms[6]; count[5] = c->k_cnt[6];
     return MK_OK;
 }
 
@@ -193,6 +207,8 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     c->cap_lines = (u32)((S2P_CARRY + c->W) / 32 + 1024);
     c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->cap_lines / EMIT_BIG + 4);
     c->sc_cap = c->cap_lines / 2 + 16; c->sc_cap_dev = 0;
+    c->n_chunks_cap = (u32)((S2P_CARRY + c->W) / SC_CHUNK + 8) & ~3u;       // multiple of 4: counts and prefixes are read as uint4
+    c->scan_chunks = !(getenv("MICROCKET_SCAN_CHUNKS") && !atoi(getenv("MICROCKET_SCAN_CHUNKS")));   // 0: look-back scan only (A/B)
     c->chr_cap = 16384; c->chr_slots = 32768;
     int rc = MK_OK;
 #define A(x) do { if (rc == MK_OK) rc = (x); } while (0)
@@ -202,6 +218,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
     A(c->d_desc.alloc((size_t)c->n_desc * 6 * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
+    A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4));
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
     cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);

@@ -53,7 +53,7 @@ struct WinState {
     u64 cursor, total;               // next window start; bytes available
     u64 ws, we;                      // this window
     u32 n_lines, carry_line, first_tile, is_last;
-    u32 err, pad;
+    u32 err, scan_ovf;               // scan_ovf: a 16 KiB chunk held more newlines than its slot list (the look-back scan redoes the window)
     // per-window emit totals
     u32 w_groups, w_emit, w_text, w_sam;
     // running output offsets (device-resident multi-window runs)
@@ -77,6 +77,8 @@ struct S2PParams {
     const char *buf;          // SAM text base (16-byte aligned)
     WinState *st;
     u32 *nl_pos;              // newline offsets relative to ws
+    u32 *ck_list, *ck_cnt, *ck_pre;   // chunked scan: per-chunk newline lists (SC_CAP slots each), counts, exclusive prefixes
+    u32 n_chunks_cap;
     u8 *lmeta;
     LineRec *rec;
     GroupRes *res;
@@ -103,7 +105,7 @@ static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
         s->ws = s->cursor;
         u64 we = s->cursor + p.window_bytes;
         s->we = we < s->total ? we : s->total;
-        s->n_lines = 0; s->carry_line = 0xFFFFFFFFu;
+        s->n_lines = 0; s->carry_line = 0xFFFFFFFFu; s->scan_ovf = 0;
         s->first_tile = (u32)(s->ws / S2P_TILE_BYTES);
         s->w_groups = s->w_emit = s->w_text = s->w_sam = 0;
         s->tickets[0] = s->tickets[1] = s->tickets[2] = s->tickets[3] = 0;
@@ -259,9 +261,167 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
 }
 
 template <int NT, int MINB = 3>
-static __global__ void __launch_bounds__(S2P_SCAN_THREADS, MINB) k_scan_lines(S2PParams p) {
+static __global__ void __launch_bounds__(S2P_SCAN_THREADS, MINB) k_scan_lines(S2PParams p, int only_if_ovf) {
     WinState *st = p.st;
+    if (only_if_ovf && !st->scan_ovf) return;          // fallback of the chunked scan: runs only for windows with very short lines
     scan_lines_body<NT>(p.buf, st->ws, st->we, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 (default): chunked newline index
+// No inter-CTA dependency and no barrier: every WARP owns one 16 KiB chunk (absolute 16 KiB boundaries of the buffer), streams it
+// with coalesced 128-bit loads (lane l reads word 32 * it + l), and appends the positions of its newlines, in byte order, to the
+// chunk's own slot list; ranks inside the warp come from one ballot.  k_chunk_prefix then turns the 64 Ki chunk counts of a window
+// into exclusive prefixes (one CTA) and k_chunk_compact copies the lists to the dense nl_pos[] the other kernels index.  The
+// look-back scan above was held at ~0.5 of the HBM peak by its grid-wide dependency (every wave waits for its slowest CTA) and by
+// 73 instructions per 16-byte word; this one needs ~40.  A chunk with more than SC_CAP newlines (average line < 32 B) raises
+// scan_ovf and the look-back kernel redoes that window, so any input is still handled.
+#define SC_CHUNK 16384u
+#define SC_CAP 512u
+#define SC_UNROLL 8
+#define SC_WARPS 8
+
+__device__ __forceinline__ u32 nl_raw(u32 x) {          // bit 7 of byte k set iff that byte is '\n'; other bits are garbage (mask with 0x80808080)
+    const u32 t = x ^ 0x0A0A0A0Au;
+    return (t - 0x01010101u) & ~t & ~(t << 7);            // borrow false positives (a 0x0B right above a newline) have bit 0 set
+}
+
+static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PParams p) {
+    const WinState *st = p.st;
+    const u64 ws = st->ws, we = st->we;
+    if (we <= ws) return;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const u64 first_chunk = ws / SC_CHUNK, last_chunk = (we - 1) / SC_CHUNK;
+    const u64 lc = (u64)blockIdx.x * SC_WARPS + wid;               // chunk index inside the window
+    const u64 chunk = first_chunk + lc;
+    if (chunk > last_chunk || lc >= p.n_chunks_cap) return;
+    const u64 cbase = chunk * SC_CHUNK;
+    const bool edge = cbase < ws || cbase + SC_CHUNK > we;
+    const uint4 *src = (const uint4 *)(p.buf + cbase) + lane;
+    u32 *list = p.ck_list + lc * SC_CAP;
+    const u32 rel0 = (u32)(cbase - ws) + lane * 16u;                 // wraps for bytes before ws: those are filtered below
+    const u32 lt = (1u << lane) - 1u;
+    u32 n = 0;
+#pragma unroll 1
+    for (u32 it = 0; it < SC_CHUNK / 512u; it += SC_UNROLL) {
+        uint4 w[SC_UNROLL];
+        if (!edge) {
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) w[u] = ld_stream_v4(src + (it + u) * 32u);
+        } else {
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; ++u) {
+                const u64 off = cbase + (u64)((it + u) * 32u + lane) * 16u;
+                w[u] = (off < we && off + 16 > ws) ? ld_stream_v4(src + (it + u) * 32u) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SC_UNROLL; ++u) {
+            const u32 e0 = nl_raw(w[u].x), e1 = nl_raw(w[u].y), e2 = nl_raw(w[u].z), e3 = nl_raw(w[u].w);
+            const u32 any = (e0 | e1 | e2 | e3) & 0x80808080u;
+            const u32 bal0 = __ballot_sync(0xFFFFFFFFu, any != 0);
+            if (bal0 == 0) continue;                                 // warp-uniform
+            // bit (8 * j + k) <- byte j of 32-bit lane k (the permuted order of nl_flags16)
+            u32 z = ((e0 >> 7) & 0x01010101u) | ((e1 >> 6) & 0x02020202u) | ((e2 >> 5) & 0x04040404u) | ((e3 >> 4) & 0x08080808u);
+            const u32 rel = rel0 + (it + u) * 512u;
+            if (edge && z) {
+                const u64 off = cbase + (u64)((it + u) * 32u + lane) * 16u;
+                u32 keep = 0;
+#pragma unroll 1
+                for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
+                z &= keep;
+            }
+            const u32 c = __popc(z);
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, c != 0);
+            const u32 multi = __ballot_sync(0xFFFFFFFFu, c > 1);
+            u32 pre, tot;
+            if (multi == 0) { pre = __popc(bal & lt); tot = __popc(bal); }
+            else { const u32 inc = warp_incl_scan(c, (int)lane); pre = inc - c; tot = __shfl_sync(0xFFFFFFFFu, inc, 31); }
+            if (c == 1) {
+                const u32 idx = n + pre;
+                if (idx < SC_CAP) list[idx] = rel + byte_of_perm_bit(__ffs(z) - 1);
+            } else if (c > 1) {                                      // several newlines in one 16-byte word: restore byte order
+                u32 m = 0, idx = n + pre;
+#pragma unroll 1
+                while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
+#pragma unroll 1
+                while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (idx < SC_CAP) list[idx] = rel + q; ++idx; }
+            }
+            n += tot;
+        }
+    }
+    if (lane == 0) p.ck_cnt[lc] = n;
+}
+
+// exclusive prefixes of the chunk counts of one window (<= ~128 Ki values): one CTA, 128-bit loads (all of a thread's loads in
+// flight at once), the second pass re-reads the counts from L1/L2
+static __global__ void __launch_bounds__(1024) k_chunk_prefix(S2PParams p) {
+    __shared__ u32 s_w[32];
+    __shared__ u32 s_ovf;
+    WinState *st = p.st;
+    const u64 ws = st->ws, we = st->we;
+    if (we <= ws) { if (threadIdx.x == 0) st->n_lines = 0; return; }
+    const u64 nc64 = (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1;
+    const u32 nc = (u32)(nc64 < p.n_chunks_cap ? nc64 : p.n_chunks_cap);
+    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (tid == 0) s_ovf = nc64 > p.n_chunks_cap ? 1u : 0u;
+    __syncthreads();
+    const u32 nq = (nc + 3u) / 4u, per = (nq + 1023u) / 1024u;       // groups of four counts; groups per thread
+    const u32 lo = tid * per < nq ? tid * per : nq, hi = lo + per < nq ? lo + per : nq;
+    const uint4 *c4 = (const uint4 *)p.ck_cnt;
+    uint4 *p4 = (uint4 *)p.ck_pre;
+    auto masked = [&](u32 i) {                                       // counts past the window's last chunk are stale
+        uint4 v = c4[i];
+        if (4u * i + 3u >= nc) { if (4u * i + 1u >= nc) v.y = 0; if (4u * i + 2u >= nc) v.z = 0; v.w = 0; }
+        return v;
+    };
+    u32 sum = 0, big = 0;
+#pragma unroll 8
+    for (u32 i = lo; i < hi; ++i) {
+        const uint4 v = masked(i);
+        sum += v.x + v.y + v.z + v.w;
+        big |= (v.x > SC_CAP) | (v.y > SC_CAP) | (v.z > SC_CAP) | (v.w > SC_CAP);
+    }
+    if (big) s_ovf = 1u;
+    const u32 inc = warp_incl_scan(sum, (int)lane);
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) { const u32 v = s_w[lane]; const u32 vi = warp_incl_scan(v, (int)lane); s_w[lane] = vi - v; }
+    __syncthreads();
+    u32 base = s_w[wid] + inc - sum;
+#pragma unroll 8
+    for (u32 i = lo; i < hi; ++i) {
+        const uint4 v = masked(i);
+        uint4 o; o.x = base; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+        p4[i] = o;
+        base = o.w + v.w;
+    }
+    if (tid == 1023) {
+        if (s_ovf) st->scan_ovf = 1u;
+        else {
+            u32 nl = base;
+            if (nl > p.cap_lines) { atomicOr(&st->err, S2P_ERR_LINES); nl = p.cap_lines; }
+            st->n_lines = nl;
+        }
+    }
+}
+
+// chunk lists -> dense nl_pos[]: one warp per chunk; every load is issued before the first use (one round trip for chunks of
+// up to 64 lines)
+static __global__ void __launch_bounds__(256) k_chunk_compact(S2PParams p) {
+    const WinState *st = p.st;
+    const u64 lc = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (lc >= p.n_chunks_cap) return;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 *list = p.ck_list + lc * SC_CAP;
+    const u32 ovf = st->scan_ovf;
+    const u64 ws = st->ws, we = st->we;
+    const u32 cnt = p.ck_cnt[lc], base = p.ck_pre[lc];
+    const u32 a = list[lane], b = list[lane + 32];                     // in bounds (SC_CAP >= 64); stale past cnt
+    if (ovf || we <= ws) return;
+    if (lc >= (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1) return;
+    if (lane < cnt && base + lane < p.cap_lines) p.nl_pos[base + lane] = a;
+    if (lane + 32 < cnt && base + lane + 32 < p.cap_lines) p.nl_pos[base + lane + 32] = b;
+    for (u32 i = lane + 64; i < cnt; i += 32) if (base + i < p.cap_lines) p.nl_pos[base + i] = list[i];
 }
 
 // ------------------------------------------------------------------------------------------------ chromosome table

@@ -161,6 +161,19 @@ def test_reset_and_kernel_timing(oracle):
         p, _, st = s.run(sam)
         assert p == op and st.log_text() == ost.log_text()
     t = s.kernel_times()
-    assert t["k_scan_lines"][1] >= 3 and t["k_scan_lines"][0] > 0 and t["k_emit"][1] >= 3
+    assert t["k_scan_chunks"][1] >= 3 and t["k_scan_chunks"][0] > 0 and t["k_emit"][1] >= 3
     assert s.launches() > 0
     s.close()
+
+
+@pytest.mark.parametrize("window", [0, 1 << 16])
+def test_short_lines_take_the_lookback_scan(oracle, window):
+    """Chunks with more newlines than the chunked scan's slot list (average line < 32 B: here thousands of 4-byte header
+    lines, also in the middle of the stream) make the window fall back to the look-back scan; results must not change."""
+    a = mk.synth_host(31, "unc", "hg38", 0, 6000)
+    b = mk.synth_host(32, "unc", "hg38", 6000, 6000)
+    sam = b"@CO\n" * 30000 + a + b"@x\n" * 50000 + b
+    ref = a + b
+    op, osam, ost = oracle.sam2pairs(ref, "unc", threads=8)
+    p, so, st, _, _ = gpu_s2p(sam, "unc", window=window)
+    assert p == op and so == osam and st.log_text() == ost.log_text()
