@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box pass that produces everything profiles/ cites: full-size bench line (+ reference arm), ncu launch list of the
+# bench command at a size ncu can replay, and one `ncu --set full` capture of the sam2pairs kernels.
+# usage: tools/profile_round.sh <tag>        (outputs under gpurun_out/<tag>_*)
+set -x
+TAG=${1:-rXX}
+O=gpurun_out
+python bench.py > $O/${TAG}_bench_full.json 2> $O/${TAG}_bench_full.err || exit 1
+python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err
+SMALL="--groups 6000000 --steps 2 --warmup 1 --no-cpu --no-e2e"
+python bench.py $SMALL > $O/${TAG}_bench_small.json 2> $O/${TAG}_bench_small.err || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${TAG}_launches.csv \
+    python bench.py $SMALL > $O/${TAG}_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_scan_chunks|k_chunk_prefix|k_chunk_compact|k_parse|k_group|k_emit' \
+    -s 12 -c 6 -f -o $O/${TAG}_s2p python bench.py $SMALL > $O/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_radix_pass|k_radix_hist|k_uniq_cells|k_pack_keys' \
+    -s 12 -c 5 -f -o $O/${TAG}_sort python bench.py $SMALL > $O/${TAG}_ncu_sort.log 2>&1
+tail -c 600 $O/${TAG}_bench_full.json
