@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--groups", type=int, default=int(os.environ.get("MK_BENCH_GROUPS", 100_000_000)), help="read groups per GPU")
     ap.add_argument("--e2e-groups", type=int, default=int(os.environ.get("MK_BENCH_E2E_GROUPS", 6_000_000)))
     ap.add_argument("--cpu-groups", type=int, default=int(os.environ.get("MK_BENCH_CPU_GROUPS", 2_000_000)))
-    ap.add_argument("--window-mb", type=int, default=int(os.environ.get("MK_BENCH_WINDOW_MB", 1024)))
+    ap.add_argument("--window-mb", type=int, default=int(os.environ.get("MK_BENCH_WINDOW_MB", 2040)))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

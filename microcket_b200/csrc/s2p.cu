@@ -88,7 +88,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     S2PParams p;
     memset(&p, 0, sizeof p);
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
-    p.ck_list = c->d_cklist.as<u32>(); p.ck_cnt = c->d_ckcnt.as<u32>(); p.ck_pre = p.ck_cnt + c->n_chunks_cap; p.n_chunks_cap = c->n_chunks_cap;
+    p.ck_list = c->d_cklist.as<u32>(); p.ck_cnt = c->d_ckcnt.as<u32>(); p.ck_pre = p.ck_cnt + c->n_chunks_cap; p.ck_bsum = p.ck_pre + c->n_chunks_cap; p.n_chunks_cap = c->n_chunks_cap;
     p.rec = c->d_rec.as<LineRec>(); p.res = c->d_res.as<GroupRes>(); p.sam_dst = c->d_samdst.as<u32>();
     p.desc_scan = c->d_desc.as<u64>(); p.desc_emitA = p.desc_scan + c->n_desc; p.desc_emitB = p.desc_emitA + c->n_desc;
     p.wave_scan = p.desc_emitB + c->n_desc; p.wave_emitA = p.wave_scan + c->n_desc; p.wave_emitB = p.wave_emitA + c->n_desc;
@@ -120,7 +120,7 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
             // chunked scan (no look-back); the look-back kernel only does work when a chunk overflowed its slot list
             k_scan_chunks<<<(c->n_chunks_cap + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, s>>>(p);
             mark(6);
-            k_chunk_prefix<<<1, 1024, 0, s>>>(p);
+            k_chunk_prefix<<<(c->n_chunks_cap + SC_PFX_BLOCK - 1) / SC_PFX_BLOCK, 256, 0, s>>>(p);
             k_chunk_compact<<<(c->n_chunks_cap + 7) / 8, 256, 0, s>>>(p);
             k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 1);
             c->launches += 3;
@@ -218,7 +218,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
     A(c->d_desc.alloc((size_t)c->n_desc * 6 * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
-    A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4));
+    A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4 + 160 * 4));   // counts, prefixes, 160 block sums (W <= 2040 MiB: <= 130 blocks of 1024 chunks)
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
     cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);

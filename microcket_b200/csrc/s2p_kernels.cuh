@@ -77,7 +77,7 @@ struct S2PParams {
     const char *buf;          // SAM text base (16-byte aligned)
     WinState *st;
     u32 *nl_pos;              // newline offsets relative to ws
-    u32 *ck_list, *ck_cnt, *ck_pre;   // chunked scan: per-chunk newline lists (SC_CAP slots each), counts, exclusive prefixes
+    u32 *ck_list, *ck_cnt, *ck_pre, *ck_bsum;   // chunked scan: per-chunk newline lists (SC_CAP slots each), counts, in-block exclusive prefixes, block sums
     u32 n_chunks_cap;
     u8 *lmeta;
     LineRec *rec;
@@ -352,75 +352,65 @@ static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PPara
     if (lane == 0) p.ck_cnt[lc] = n;
 }
 
-// exclusive prefixes of the chunk counts of one window (<= ~128 Ki values): one CTA, 128-bit loads (all of a thread's loads in
-// flight at once), the second pass re-reads the counts from L1/L2
-static __global__ void __launch_bounds__(1024) k_chunk_prefix(S2PParams p) {
-    __shared__ u32 s_w[32];
-    __shared__ u32 s_ovf;
+// Chunk counts -> positions in nl_pos[], in two small kernels without a serial pass:
+//   k_chunk_prefix  one CTA per 1024 chunks: exclusive prefix inside the block (one uint4 of counts per thread) + the block's sum
+//   k_chunk_compact one warp per chunk: base = sum of the earlier blocks' sums (<= 128, one REDUX) + the in-block prefix;
+//                   copies the chunk's slot list into the dense nl_pos[]; the last chunk's warp publishes n_lines
+#define SC_PFX_BLOCK 1024u                                              // chunks per k_chunk_prefix CTA
+static __global__ void __launch_bounds__(256) k_chunk_prefix(S2PParams p) {
+    __shared__ u32 s_w[8];
     WinState *st = p.st;
     const u64 ws = st->ws, we = st->we;
-    if (we <= ws) { if (threadIdx.x == 0) st->n_lines = 0; return; }
+    if (we <= ws) return;
     const u64 nc64 = (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1;
     const u32 nc = (u32)(nc64 < p.n_chunks_cap ? nc64 : p.n_chunks_cap);
     const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    if (tid == 0) s_ovf = nc64 > p.n_chunks_cap ? 1u : 0u;
-    __syncthreads();
-    const u32 nq = (nc + 3u) / 4u, per = (nq + 1023u) / 1024u;       // groups of four counts; groups per thread
-    const u32 lo = tid * per < nq ? tid * per : nq, hi = lo + per < nq ? lo + per : nq;
-    const uint4 *c4 = (const uint4 *)p.ck_cnt;
-    uint4 *p4 = (uint4 *)p.ck_pre;
-    auto masked = [&](u32 i) {                                       // counts past the window's last chunk are stale
-        uint4 v = c4[i];
-        if (4u * i + 3u >= nc) { if (4u * i + 1u >= nc) v.y = 0; if (4u * i + 2u >= nc) v.z = 0; v.w = 0; }
-        return v;
-    };
-    u32 sum = 0, big = 0;
-#pragma unroll 8
-    for (u32 i = lo; i < hi; ++i) {
-        const uint4 v = masked(i);
-        sum += v.x + v.y + v.z + v.w;
-        big |= (v.x > SC_CAP) | (v.y > SC_CAP) | (v.z > SC_CAP) | (v.w > SC_CAP);
+    const u32 i = blockIdx.x * (SC_PFX_BLOCK / 4) + tid;             // uint4 index
+    if (blockIdx.x * SC_PFX_BLOCK >= nc) return;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (4u * i < nc) {
+        v = ((const uint4 *)p.ck_cnt)[i];
+        if (4u * i + 3u >= nc) { if (4u * i + 1u >= nc) v.y = 0; if (4u * i + 2u >= nc) v.z = 0; v.w = 0; }   // stale counts past the window
     }
-    if (big) s_ovf = 1u;
+    if ((v.x > SC_CAP) | (v.y > SC_CAP) | (v.z > SC_CAP) | (v.w > SC_CAP) | (nc64 > p.n_chunks_cap)) st->scan_ovf = 1u;
+    const u32 sum = v.x + v.y + v.z + v.w;
     const u32 inc = warp_incl_scan(sum, (int)lane);
     if (lane == 31) s_w[wid] = inc;
     __syncthreads();
-    if (wid == 0) { const u32 v = s_w[lane]; const u32 vi = warp_incl_scan(v, (int)lane); s_w[lane] = vi - v; }
-    __syncthreads();
-    u32 base = s_w[wid] + inc - sum;
-#pragma unroll 8
-    for (u32 i = lo; i < hi; ++i) {
-        const uint4 v = masked(i);
-        uint4 o; o.x = base; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
-        p4[i] = o;
-        base = o.w + v.w;
-    }
-    if (tid == 1023) {
-        if (s_ovf) st->scan_ovf = 1u;
-        else {
-            u32 nl = base;
-            if (nl > p.cap_lines) { atomicOr(&st->err, S2P_ERR_LINES); nl = p.cap_lines; }
-            st->n_lines = nl;
-        }
-    }
+    u32 before = 0, total = 0;
+#pragma unroll
+    for (u32 q = 0; q < 8; ++q) { const u32 x = s_w[q]; total += x; if (q < wid) before += x; }
+    uint4 o; o.x = before + inc - sum; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+    if (4u * i < nc) ((uint4 *)p.ck_pre)[i] = o;
+    if (tid == 0) p.ck_bsum[blockIdx.x] = total;
 }
 
-// chunk lists -> dense nl_pos[]: one warp per chunk; every load is issued before the first use (one round trip for chunks of
-// up to 64 lines)
 static __global__ void __launch_bounds__(256) k_chunk_compact(S2PParams p) {
-    const WinState *st = p.st;
+    WinState *st = p.st;
     const u64 lc = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (lc >= p.n_chunks_cap) return;
     const u32 lane = threadIdx.x & 31u;
     const u32 *list = p.ck_list + lc * SC_CAP;
+    // every load is issued before the first use: one memory round trip for chunks of up to 64 lines
     const u32 ovf = st->scan_ovf;
     const u64 ws = st->ws, we = st->we;
-    const u32 cnt = p.ck_cnt[lc], base = p.ck_pre[lc];
-    const u32 a = list[lane], b = list[lane + 32];                     // in bounds (SC_CAP >= 64); stale past cnt
+    const u32 cnt = p.ck_cnt[lc], pre = p.ck_pre[lc];
+    const u32 blk = (u32)(lc / SC_PFX_BLOCK);
+    u32 bs = 0;
+#pragma unroll
+    for (u32 q = 0; q < 5; ++q) { const u32 b = lane + 32u * q; const u32 x = p.ck_bsum[b]; if (b < blk) bs += x; }   // ck_bsum has 160 slots
+    const u32 a = list[lane], b2 = list[lane + 32];                    // in bounds (SC_CAP >= 64); stale past cnt
     if (ovf || we <= ws) return;
-    if (lc >= (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1) return;
+    const u64 nc = (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1;
+    if (lc >= nc) return;
+    const u32 base = __reduce_add_sync(0xFFFFFFFFu, bs) + pre;
+    if (lc == nc - 1 && lane == 0) {
+        u32 nl = base + cnt;
+        if (nl > p.cap_lines) { atomicOr(&st->err, S2P_ERR_LINES); nl = p.cap_lines; }
+        st->n_lines = nl;
+    }
     if (lane < cnt && base + lane < p.cap_lines) p.nl_pos[base + lane] = a;
-    if (lane + 32 < cnt && base + lane + 32 < p.cap_lines) p.nl_pos[base + lane + 32] = b;
+    if (lane + 32 < cnt && base + lane + 32 < p.cap_lines) p.nl_pos[base + lane + 32] = b2;
     for (u32 i = lane + 64; i < cnt; i += 32) if (base + i < p.cap_lines) p.nl_pos[base + i] = list[i];
 }
 
