@@ -32,7 +32,8 @@ struct S2PCtx : mk_ctx {
     u32 chr_slots = 0, chr_cap = 0, sc_cap_dev = 0;
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     u32 n_chunks_cap = 0; bool scan_chunks = true;
-    DevBuf d_cklist, d_ckcnt;
+    DevBuf d_cklist, d_ckcnt, d_tiletot;
+    u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
     int grid_scan = 0, grid_scan4 = 0, scan_occ4 = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0, scan_nt = 4;
@@ -89,6 +90,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     memset(&p, 0, sizeof p);
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
     p.ck_list = c->d_cklist.as<u32>(); p.ck_cnt = c->d_ckcnt.as<u32>(); p.ck_pre = p.ck_cnt + c->n_chunks_cap; p.ck_bsum = p.ck_pre + c->n_chunks_cap; p.n_chunks_cap = c->n_chunks_cap;
+    p.tile_tot = c->d_tiletot.as<uint4>(); p.tile_pre = p.tile_tot + c->n_sub_cap; p.n_sub_cap = c->n_sub_cap;
     p.rec = c->d_rec.as<LineRec>(); p.res = c->d_res.as<GroupRes>(); p.sam_dst = c->d_samdst.as<u32>();
     p.desc_scan = c->d_desc.as<u64>(); p.desc_emitA = p.desc_scan + c->n_desc; p.desc_emitB = p.desc_emitA + c->n_desc;
     p.wave_scan = p.desc_emitB + c->n_desc; p.wave_emitA = p.wave_scan + c->n_desc; p.wave_emitB = p.wave_emitA + c->n_desc;
@@ -134,9 +136,10 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     }
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
     mark(3);
+    k_emit_prefix<<<1, 1024, 0, s>>>(p);
     k_emit<<<c->grid_emit, EMIT_THREADS, 0, s>>>(p);
     mark(4);
-    c->launches += 5;
+    c->launches += 6;
     if (p.write_sam) { k_copy_sam<<<c->grid_gs, 256, 0, s>>>(p); c->launches += 1; }
     mark(5);
     k_win_end<<<1, 1, 0, s>>>(p);
@@ -205,7 +208,8 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     c->W = (c->W + 15) & ~(size_t)15;
     c->in_cap = S2P_CARRY + c->W + 64;
     c->cap_lines = (u32)((S2P_CARRY + c->W) / 32 + 1024);
-    c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->cap_lines / EMIT_BIG + 4);
+    c->n_sub_cap = c->cap_lines / EMIT_TILE + 4;
+    c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->n_sub_cap);   // k_win_begin's grid covers both
     c->sc_cap = c->cap_lines / 2 + 16; c->sc_cap_dev = 0;
     c->n_chunks_cap = (u32)((S2P_CARRY + c->W) / SC_CHUNK + 8) & ~3u;       // multiple of 4: counts and prefixes are read as uint4
     c->scan_chunks = !(getenv("MICROCKET_SCAN_CHUNKS") && !atoi(getenv("MICROCKET_SCAN_CHUNKS")));   // 0: look-back scan only (A/B)
@@ -218,6 +222,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
     A(c->d_desc.alloc((size_t)c->n_desc * 6 * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
+    A(c->d_tiletot.alloc((size_t)c->n_sub_cap * 2 * sizeof(uint4)));
     A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4 + 160 * 4));   // counts, prefixes, 160 block sums (W <= 2040 MiB: <= 130 blocks of 1024 chunks)
 #undef A
     if (rc != MK_OK) { delete c; return rc; }

@@ -84,6 +84,7 @@ struct S2PParams {
     GroupRes *res;
     u32 *sam_dst;
     u64 *desc_scan, *desc_emitA, *desc_emitB;
+    uint4 *tile_tot, *tile_pre; u32 n_sub_cap;  // per 512 lines: (groups | emitted << 16, text bytes, passthrough bytes) summed by K3; exclusive prefixes (groups, emitted, text, passthrough)
     u64 *wave_scan, *wave_emitA, *wave_emitB;   // per-wave bases of the wave scans
     ChrSlot *chr; u32 chr_mask; int *id_to_slot; u32 chr_cap;
     u64 *sc_list; u32 sc_cap;
@@ -99,6 +100,7 @@ struct S2PParams {
 // ------------------------------------------------------------------------------------------------ begin / end
 static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n_sub_cap) p.tile_tot[i] = make_uint4(0, 0, 0, 0);
     if (i < n_desc) { p.desc_scan[i] = 0; p.desc_emitA[i] = 0; p.desc_emitB[i] = 0; p.wave_scan[i] = 0; p.wave_emitA[i] = 0; p.wave_emitB[i] = 0; }
     if (i == 0) {
         WinState *s = p.st;
@@ -1089,7 +1091,10 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += gridDim.x * blockDim.x) {
+    const u32 n_round = (n_lines + 31u) & ~31u;                        // whole warps stay in the loop (warp reduction at its end)
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+      u32 vA = 0, vT = 0, vS = 0;                                      // this line's contribution to its 512-line tile's sizes (K4)
+      if (i < n_lines) do {                                            // `continue` below leaves this block
         const u32 mi = p.lmeta[i];
         if (!(mi & LM_KEEP)) continue;
         // ---- is this kept line the head of a group?  (pairutil.h:163-173: currId != lastId among kept records)
@@ -1247,6 +1252,17 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
         if (g.status != ST_NONE) atomicAdd(&s_cnt[g.status], 1u);
         p.res[i] = g;
         p.lmeta[i] = (u8)meta;
+        vA = 1u | ((meta & LM_EMIT) ? 1u << 16 : 0u);
+        if (meta & LM_EMIT) { vT = g.text_len; if (p.write_sam) vS = g.sam_len; }
+      } while (0);
+      // sizes per 512 lines for K4, which then needs no look-back: one reduction per warp (its 32 lines share a tile)
+      vA = __reduce_add_sync(0xFFFFFFFFu, vA); vT = __reduce_add_sync(0xFFFFFFFFu, vT); vS = __reduce_add_sync(0xFFFFFFFFu, vS);
+      if ((threadIdx.x & 31u) == 0 && vA) {
+          u32 *tt = (u32 *)&p.tile_tot[i >> 9];
+          atomicAdd(tt, vA);
+          if (vT) atomicAdd(tt + 1, vT);
+          if (vS) atomicAdd(tt + 2, vS);
+      }
     }
     __syncthreads();
     if (threadIdx.x < ST_NCOUNTER && s_cnt[threadIdx.x]) atomicAdd(&st->counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
@@ -1295,16 +1311,43 @@ __device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInf
     *out++ = '\t'; *out++ = (g.strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (g.strands & 2) ? '-' : '+'; *out++ = '\n';
 }
 
-// A tile is EMIT_NT sub-tiles of 512 lines: the sizes of all sub-tiles are scanned first, ONE look-back pair covers the
-// tile (the look-back makes every wave of the persistent grid wait for its slowest CTA, so it is amortised over 2048
-// lines), then the sub-tiles are written one after the other through the shared-memory text stage.
-#define EMIT_NT 4
+// Tiles of 512 lines.  K3 has already summed every tile's sizes (tile_tot), k_emit_prefix turns them into exclusive prefixes
+// (one CTA, a few microseconds), so a tile here depends on no other tile: no look-back, no grid-wide dependency, and the
+// small tiles leave no idle tail (the look-back version needed 2048-line tiles to amortise its chain: 5.1 tiles per CTA
+// per 2 GiB window, i.e. a sixth round that was 90 % idle).
+#define EMIT_NT 1
 #define EMIT_BIG (EMIT_NT * EMIT_TILE)
+
+static __global__ void __launch_bounds__(1024) k_emit_prefix(S2PParams p) {
+    __shared__ u32 s_w[4][32];
+    WinState *st = p.st;
+    const u32 n_sub = (st->n_lines + EMIT_TILE - 1) / EMIT_TILE;
+    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const u32 per = (n_sub + 1023u) / 1024u;
+    const u32 lo = tid * per < n_sub ? tid * per : n_sub, hi = lo + per < n_sub ? lo + per : n_sub;
+    const uint4 *__restrict__ tot = p.tile_tot;
+    uint4 *__restrict__ pre = p.tile_pre;
+    u32 G = 0, E = 0, T = 0, S = 0;
+#pragma unroll 4
+    for (u32 i = lo; i < hi; ++i) { const uint4 v = tot[i]; G += v.x & 0xFFFFu; E += v.x >> 16; T += v.y; S += v.z; }
+    const u32 iG = warp_incl_scan(G, (int)lane), iE = warp_incl_scan(E, (int)lane), iT = warp_incl_scan(T, (int)lane), iS = warp_incl_scan(S, (int)lane);
+    if (lane == 31) { s_w[0][wid] = iG; s_w[1][wid] = iE; s_w[2][wid] = iT; s_w[3][wid] = iS; }
+    __syncthreads();
+    if (wid < 4) { const u32 v = s_w[wid][lane]; const u32 vi = warp_incl_scan(v, (int)lane); s_w[wid][lane] = vi - v; }
+    __syncthreads();
+    u32 bG = s_w[0][wid] + iG - G, bE = s_w[1][wid] + iE - E, bT = s_w[2][wid] + iT - T, bS = s_w[3][wid] + iS - S;
+#pragma unroll 4
+    for (u32 i = lo; i < hi; ++i) {
+        const uint4 v = tot[i];
+        pre[i] = make_uint4(bG, bE, bT, bS);
+        bG += v.x & 0xFFFFu; bE += v.x >> 16; bT += v.y; bS += v.z;
+    }
+    if (tid == 1023) { st->w_groups = bG; st->w_emit = bE; st->w_text = bT; st->w_sam = bS; }
+}
 
 static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
     __shared__ u32 s_w[2][EMIT_NT][3][EMIT_THREADS / 32];
-    __shared__ u64 s_baseA[2], s_baseB[2];
     WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
@@ -1313,8 +1356,9 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
     const u64 base_text = st->out_text, base_pairs = st->out_pairs, base_sam = st->out_sam, base_groups = st->groups_done;
     int pb = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, pb ^= 1) {
-        // ---- phase 1: per-thread sizes of every sub-tile (groups | emitted << 16, text bytes, passthrough bytes)
-        u32 lA[EMIT_NT], lT[EMIT_NT], lS[EMIT_NT];                      // become thread-exclusive prefixes inside the sub-tile
+        const uint4 tbase = p.tile_pre[tile];                           // (groups, emitted, text, passthrough) before this tile
+        // ---- phase 1: per-thread sizes (groups | emitted << 16, text bytes, passthrough bytes)
+        u32 lA[EMIT_NT], lT[EMIT_NT], lS[EMIT_NT];                      // become thread-exclusive prefixes inside the tile
 #pragma unroll
         for (int k = 0; k < EMIT_NT; ++k) {
             const u32 i0 = (u32)tile * EMIT_BIG + k * EMIT_TILE + tid * EMIT_ITEMS;
@@ -1332,8 +1376,8 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
             lA[k] = iA - vA; lT[k] = iT - vT; lS[k] = iS - vS;
         }
         __syncthreads();
-        // ---- phase 2: sub-tile totals, tile totals, one look-back per chain
-        u32 sG[EMIT_NT], sE[EMIT_NT], sT[EMIT_NT], sS[EMIT_NT], tG = 0, tE = 0, tT = 0, tS = 0;
+        // ---- phase 2: tile totals and this thread's prefix inside the tile
+        u32 sG[EMIT_NT], sE[EMIT_NT], sT[EMIT_NT], sS[EMIT_NT];
 #pragma unroll
         for (int k = 0; k < EMIT_NT; ++k) {
             u32 a = 0, t = 0, s2 = 0;
@@ -1344,21 +1388,10 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
                 if (q < wid) { lA[k] += xa; lT[k] += xt; lS[k] += xs; }
             }
             sG[k] = a & 0xFFFFu; sE[k] = a >> 16; sT[k] = t; sS[k] = s2;
-            tG += sG[k]; tE += sE[k]; tT += t; tS += s2;
         }
-        if (wid == 0) {
-            const u64 agg = (u64)tG | ((u64)tE << 31);
-            const u64 b = lookback_exclusive(p.desc_emitA, tile, 0, agg, lane);
-            if (lane == 0) { s_baseA[pb] = b; if (tile == n_tiles - 1) { const u64 t = b + agg; st->w_groups = (u32)(t & 0x7FFFFFFFu); st->w_emit = (u32)(t >> 31); } }
-        } else if (wid == 1) {
-            const u64 agg = (u64)tT | ((u64)tS << 31);
-            const u64 b = lookback_exclusive(p.desc_emitB, tile, 0, agg, lane);
-            if (lane == 0) { s_baseB[pb] = b; if (tile == n_tiles - 1) { const u64 t = b + agg; st->w_text = (u32)(t & 0x7FFFFFFFu); st->w_sam = (u32)(t >> 31); } }
-        }
-        __syncthreads();
-        // ---- phase 3: outputs, sub-tile by sub-tile
-        u32 pG = (u32)(s_baseA[pb] & 0x7FFFFFFFu), pE = (u32)(s_baseA[pb] >> 31);   // running prefixes at the sub-tile's start
-        u64 pT = base_text + (s_baseB[pb] & 0x7FFFFFFFu), pS = base_sam + (s_baseB[pb] >> 31);
+        u32 pG = tbase.x, pE = tbase.y;                                 // running prefixes at the sub-tile's start
+        u64 pT = base_text + tbase.z, pS = base_sam + tbase.w;
+        // ---- phase 3: outputs
 #pragma unroll
         for (int k = 0; k < EMIT_NT; ++k) {
             const u32 i0 = (u32)tile * EMIT_BIG + k * EMIT_TILE + tid * EMIT_ITEMS;
