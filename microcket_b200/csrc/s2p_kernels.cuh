@@ -319,12 +319,9 @@ static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PPara
 #pragma unroll
         for (int u = 0; u < SC_UNROLL; ++u) {
             const u32 e0 = nl_raw(w[u].x), e1 = nl_raw(w[u].y), e2 = nl_raw(w[u].z), e3 = nl_raw(w[u].w);
-            const u32 any = (e0 | e1 | e2 | e3) & 0x80808080u;
-            const u32 bal0 = __ballot_sync(0xFFFFFFFFu, any != 0);
-            if (bal0 == 0) continue;                                 // warp-uniform
-            // bit (8 * j + k) <- byte j of 32-bit lane k (the permuted order of nl_flags16)
+            // bit (8 * j + k) <- byte j of 32-bit lane k (the permuted order of nl_flags16); built on every row so that a row
+            // with newlines costs one more ballot, two popcounts and the store
             u32 z = ((e0 >> 7) & 0x01010101u) | ((e1 >> 6) & 0x02020202u) | ((e2 >> 5) & 0x04040404u) | ((e3 >> 4) & 0x08080808u);
-            const u32 rel = rel0 + (it + u) * 512u;
             if (edge && z) {
                 const u64 off = cbase + (u64)((it + u) * 32u + lane) * 16u;
                 u32 keep = 0;
@@ -332,17 +329,23 @@ static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PPara
                 for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
                 z &= keep;
             }
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, z != 0);
+            if (bal == 0) continue;                                  // warp-uniform
+            const u32 multi = __ballot_sync(0xFFFFFFFFu, (z & (z - 1u)) != 0);
+            const u32 rel = rel0 + (it + u) * 512u;
+            if (multi == 0) {                                        // at most one newline per 16-byte word: ranks from the ballot
+                if (z) {
+                    const u32 idx = n + __popc(bal & lt);
+                    if (idx < SC_CAP) list[idx] = rel + byte_of_perm_bit(__ffs(z) - 1);
+                }
+                n += __popc(bal);
+                continue;
+            }
             const u32 c = __popc(z);
-            const u32 bal = __ballot_sync(0xFFFFFFFFu, c != 0);
-            const u32 multi = __ballot_sync(0xFFFFFFFFu, c > 1);
-            u32 pre, tot;
-            if (multi == 0) { pre = __popc(bal & lt); tot = __popc(bal); }
-            else { const u32 inc = warp_incl_scan(c, (int)lane); pre = inc - c; tot = __shfl_sync(0xFFFFFFFFu, inc, 31); }
-            if (c == 1) {
-                const u32 idx = n + pre;
-                if (idx < SC_CAP) list[idx] = rel + byte_of_perm_bit(__ffs(z) - 1);
-            } else if (c > 1) {                                      // several newlines in one 16-byte word: restore byte order
-                u32 m = 0, idx = n + pre;
+            const u32 inc = warp_incl_scan(c, (int)lane);
+            const u32 tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            if (c) {                                                 // restore byte order inside the word
+                u32 m = 0, idx = n + inc - c;
 #pragma unroll 1
                 while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
 #pragma unroll 1
