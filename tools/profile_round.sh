@@ -12,7 +12,7 @@ python bench.py $SMALL > $O/${TAG}_bench_small.json 2> $O/${TAG}_bench_small.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py $SMALL > $O/${TAG}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_scan_chunks|k_chunk_prefix|k_chunk_compact|k_parse|k_group|k_emit' \
-    -s 12 -c 6 -f -o $O/${TAG}_s2p python bench.py $SMALL > $O/${TAG}_ncu_full.log 2>&1
+    -s 21 -c 7 -f -o $O/${TAG}_s2p python bench.py $SMALL > $O/${TAG}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_radix_pass|k_radix_hist|k_uniq_cells|k_pack_keys' \
     -s 12 -c 5 -f -o $O/${TAG}_sort python bench.py $SMALL > $O/${TAG}_ncu_sort.log 2>&1
 tail -c 600 $O/${TAG}_bench_full.json
