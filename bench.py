@@ -149,7 +149,8 @@ def run_reference(args):
     sample = f"{sample_groups} read groups ({nb / 1e9:.2f} GB SAM) of the same synthetic workload per step, page-cache-warm file in /dev/shm"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": workload_config(args, 1, sample_groups),
+            "data": "synthetic", "config": dict(workload_config(args, max(1, args.gpus), args.groups), window_mb=args.window_mb,
+                                                  reference_sample_read_groups=sample_groups),
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -573,20 +573,23 @@ struct TileFetch {
     __device__ __forceinline__ u64 ld8(u64 a) const { return (a >= tlo && a + 8 <= thi) ? *(const u64 *)(sm + (a - tlo)) : __ldg((const u64 *)(buf + a)); }
     __device__ __forceinline__ int byte(u64 a) const { return (a >= tlo && a < thi) ? (int)(unsigned char)sm[a - tlo] : (int)(unsigned char)buf[a]; }
 };
-// the thread's own line prefix (7 x 16 bytes from A) staged in a shared-memory column: field extraction at data-dependent
-// offsets without going back to L1/L2
+// the thread's own line prefix (7 x 16 bytes from A) staged in a shared-memory column of 32-bit words (word w of the prefix
+// at col[w * 256]: consecutive threads hit consecutive banks whatever w is), followed by four zero words, so that eight
+// bytes at ANY offset below 112 are three conflict-free 32-bit loads and two funnel shifts, with no bounds test (ncu: the
+// 64-bit accessor with its bounds test and 64-bit shifts was 31 % of k_parse's instructions)
+#define LF_WORDS 32
 struct LineFetch {
-    const char *buf; const uint4 *col; u64 A;                           // col[j * 256] = bytes [A + 16 j, A + 16 j + 16)
-    // offsets relative to A: 32-bit arithmetic on the hot path
-    __device__ __forceinline__ uint4 ld16r(u32 r) const { return r + 16 <= 112 ? col[(r >> 4) * 256] : __ldg((const uint4 *)(buf + A + r)); }
-    __device__ __forceinline__ u64 ld8r(u32 r) const { return r + 8 <= 112 ? ((const u64 *)&col[(r >> 4) * 256])[(r >> 3) & 1] : __ldg((const u64 *)(buf + A + r)); }
-    __device__ __forceinline__ int byter(u32 r) const { return (int)((ld8r(r & ~7u) >> (8 * (r & 7u))) & 0xFF); }
-    __device__ __forceinline__ uint4 ld16(u64 a) const { return (a >= A && a + 16 <= A + 112) ? col[((a - A) >> 4) * 256] : __ldg((const uint4 *)(buf + a)); }
-    __device__ __forceinline__ u64 ld8(u64 a) const {
-        return (a >= A && a + 8 <= A + 112) ? ((const u64 *)&col[((a - A) >> 4) * 256])[(a >> 3) & 1] : __ldg((const u64 *)(buf + a));
+    const char *buf; const u32 *col; u64 A;                            // col[w * 256] = bytes [A + 4 w, A + 4 w + 4)
+    uint4 w[7];                                                        // the same prefix in registers (own line only)
+    __device__ __forceinline__ uint4 ld16r(u32 r) const { return w[r >> 4]; }          // r = 16 j, j a compile-time constant
+    __device__ __forceinline__ int byter(u32 r) const { return (int)((col[(r >> 2) * 256] >> (8 * (r & 3u))) & 0xFFu); }
+    __device__ __forceinline__ u64 f8(u32 r) const {                   // r + 8 <= 120
+        const u32 *q = col + (r >> 2) * 256; const u32 sh = (r & 3u) * 8u;
+        const u32 a = q[0], b = q[256], c = q[512];
+        return (u64)__funnelshift_r(a, b, sh) | ((u64)__funnelshift_r(b, c, sh) << 32);
     }
-    __device__ __forceinline__ int byte(u64 a) const { return (int)((ld8(a & ~(u64)7) >> (8 * (a & 7))) & 0xFF); }
 };
+__device__ __forceinline__ u64 fetch8r(const LineFetch &f, u32 r) { return f.f8(r); }   // preferred over the template below
 template <class F>
 __device__ __forceinline__ u64 fetch8r(const F &f, u32 r) {           // 8 bytes at any offset relative to f.A
     const u32 a8 = r & ~7u, sh = (r & 7u) * 8;
@@ -735,13 +738,15 @@ static __device__ __noinline__ u32 parse_line_slow(const S2PParams &p, u64 ws, u
 }
 
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
-    __shared__ uint4 s_line[7][256];                                  // every thread's line prefix, one column per thread
+    __shared__ u32 s_line[LF_WORDS][256];                             // every thread's line prefix, one column of words per thread
     __shared__ u64 s_A[256];                                          // its 16-byte aligned base, or ~0 when not staged
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const u64 limit = st->total;
     const int tid = threadIdx.x;
+#pragma unroll
+    for (int j = 28; j < LF_WORDS; ++j) s_line[j][tid] = 0;           // the pad words behind the 112 staged bytes (never rewritten)
     const u32 n_round = (n_lines + 255u) & ~255u;                     // whole CTAs stay in the loop (barriers below)
     for (u32 i = blockIdx.x * blockDim.x + tid; i < n_round; i += gridDim.x * blockDim.x) {
         const bool active = i < n_lines;
@@ -756,7 +761,10 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
 #pragma unroll
             for (int j = 0; j < 7; ++j) w[j] = __ldg(src + j);
 #pragma unroll
-            for (int j = 0; j < 7; ++j) s_line[j][tid] = w[j];
+            for (int j = 0; j < 7; ++j) {
+                s_line[4 * j][tid] = w[j].x; s_line[4 * j + 1][tid] = w[j].y; s_line[4 * j + 2][tid] = w[j].z; s_line[4 * j + 3][tid] = w[j].w;
+                lf.w[j] = w[j];
+            }
         }
         s_A[tid] = staged ? lf.A : ~(u64)0;
         __syncthreads();                                               // neighbours read each other's columns
@@ -769,7 +777,7 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
                     const u64 pa = ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0);
                     bool eq;
                     if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_slow(p, ws, i, i - 1);   // operator>> skips leading blanks
-                    else if (tid > 0 && s_A[tid - 1] != ~(u64)0) {
+                    else if (tid > 0 && s_A[tid - 1] != ~(u64)0 && (u32)(pa - s_A[tid - 1]) + tok.t0 + 1 <= 112) {   // inside the neighbour's staged bytes
                         LineFetch lp; lp.buf = p.buf; lp.col = &s_line[0][tid - 1]; lp.A = s_A[tid - 1];
                         const u32 so = (u32)(a - lf.A), sp = (u32)(pa - lp.A);
                         eq = true;
