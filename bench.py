@@ -247,6 +247,16 @@ def main():
     launches = s2p.launches() + ws.launches() - launches0
     s2p.enable_timing(False)
     st = s2p.finish(0, 0) if world > 1 else s2p.finish()
+    # size-independent properties of the last timed step, at full size (reported, not asserted: the parity tests are tests/):
+    # every emitted pair is counted in exactly one class counter; the COO counts add up to the pairs kept by the dedup
+    checks = None
+    try:
+        cls_sum = int(st.trans) + int(st.cis10K) + int(st.cis1K) + int(st.cis0)
+        coo_sum = int(cnt[:int(nnz)].to(torch.int64).sum().item())
+        checks = {"pairs_equal_class_counters": cls_sum == int(n_pairs), "coo_counts_sum_to_kept_pairs": coo_sum == int(kept),
+                  "scope": "rank 0, last timed step"}
+    except Exception as e:                                    # never let the report break the bench line
+        checks = {"error": str(e)}
     t = torch.tensor([ms_total, float(n_pairs), float(kept), float(nnz)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -322,7 +332,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": dict(workload_config(args, world, G), sam_bytes_per_gpu=nbytes, pairs_per_step=n_pairs_all, kept_after_dedup=kept_all,
                            coo_cells=nnz_all, window_mb=args.window_mb),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checks": checks}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
