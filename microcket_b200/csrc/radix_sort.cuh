@@ -120,6 +120,7 @@ static __global__ void __launch_bounds__(256) k_radix_plan(RadixPlan *plan, u64 
 #define RS_ST_AGG (1u << 30)
 #define RS_ST_INC (2u << 30)
 #define RS_VAL(x) ((x) & 0x3FFFFFFFu)
+#define RS_LB 4                                  // look-back descriptor loads in flight per digit thread
 
 template <class P>
 static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass(typename P::Bufs bufs, u64 n, int pass, int byte, RadixPlan *plan,
@@ -139,7 +140,7 @@ static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass
     const bool use_iota = P::HAS_VAL && iota_vals && plan->first[pass];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_scan[16] = atomicAdd(&plan->ticket[pass], 1u);
-    for (int i = tid; i < (RS_THREADS / 32) * 256; i += RS_THREADS) s_wcnt[i] = 0;
+    for (int i = tid; i < (RS_THREADS / 32) * 256 + 256; i += RS_THREADS) s_wcnt[i] = 0;       // warp counters and s_dig_excl (tile histogram below)
     __syncthreads();
     const u32 tile = s_scan[16];
     const u64 tile_base = (u64)tile * TILE;
@@ -153,6 +154,16 @@ static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass
             if (P::HAS_VAL) val[j] = use_iota ? (u32)i : bufs.v[which][i];
             dig[j] = P::digit(key[j], byte);
         } else dig[j] = 255u;                                            // padding sorts last inside the last tile
+    }
+    // ---- the tile's digit counts first (plain shared-memory atomics), so that its aggregate is published BEFORE the slow
+    // stable ranking: the successors' look-back then finds it ready instead of spinning (ncu: 29 % of the stall samples)
+    u32 *my = desc + (u64)tile * 256 + tid;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) atomicAdd(&s_dig_excl[dig[j]], 1u);
+    __syncthreads();
+    {
+        const u32 c0 = s_dig_excl[tid];
+        atomicExch(my, (tile == 0 ? RS_ST_INC : RS_ST_AGG) | c0);
     }
     // ---- stable rank inside the warp, digit by digit
     u32 *wc = s_wcnt + wid * 256;
@@ -178,20 +189,27 @@ static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass
         u32 tot;
         const u32 ex = block_excl_scan<RS_THREADS>(cnt, s_scan, &tot);
         s_dig_excl[d] = ex;
-        // decoupled look-back for this digit
-        u32 *my = desc + (u64)tile * 256 + d;
+        // decoupled look-back for this digit (the aggregate was published above)
         u32 excl = 0;
-        if (tile == 0) { atomicExch(my, RS_ST_INC | cnt); }
-        else {
-            atomicExch(my, RS_ST_AGG | cnt);
+        if (tile != 0) {
+            // Walk back over the predecessors with RS_LB descriptor loads in flight: the tiles in flight publish their aggregates
+            // at about the same time, so a walk is tens of steps long, and one dependent L2 round trip per step was 35 % of
+            // this kernel's stall samples (ncu).
             long t = (long)tile - 1;
-            while (true) {
-                u32 v = *(volatile u32 *)(desc + (u64)t * 256 + d);
-                u32 st = v >> 30;
-                if (st == 0) continue;
-                excl += RS_VAL(v);
-                if (st == 2) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                u32 v[RS_LB];
+#pragma unroll
+                for (int q = 0; q < RS_LB; ++q) v[q] = t - q >= 0 ? *(volatile u32 *)(desc + (u64)(t - q) * 256 + d) : 0u;
+                int used = 0;
+#pragma unroll
+                for (int q = 0; q < RS_LB; ++q) {
+                    const u32 st = v[q] >> 30;
+                    if (done || used != q || st == 0) continue;         // consume in order; stop at the first one that is not ready
+                    excl += RS_VAL(v[q]); ++used;
+                    if (st == 2) done = true;
+                }
+                t -= used;
             }
             atomicExch(my, RS_ST_INC | (excl + cnt));
         }
