@@ -120,7 +120,7 @@ static __global__ void __launch_bounds__(256) k_radix_plan(RadixPlan *plan, u64 
 #define RS_ST_AGG (1u << 30)
 #define RS_ST_INC (2u << 30)
 #define RS_VAL(x) ((x) & 0x3FFFFFFFu)
-#define RS_LB 4                                  // look-back descriptor loads in flight per digit thread
+#define RS_LB 8                                  // look-back descriptor loads in flight per digit thread
 
 template <class P>
 static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass(typename P::Bufs bufs, u64 n, int pass, int byte, RadixPlan *plan,
@@ -192,7 +192,7 @@ static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass
         // decoupled look-back for this digit (the aggregate was published above)
         u32 excl = 0;
         if (tile != 0) {
-            // Walk back over the predecessors with RS_LB descriptor loads in flight: the tiles in flight publish their aggregates
+            // Walk back over the predecessors with RS_LB descriptor loads in flight (8: A/B 4 / 8 / 16 -> stage 5.19 / 4.98 / 5.08 ms): the tiles in flight publish their aggregates
             // at about the same time, so a walk is tens of steps long, and one dependent L2 round trip per step was 35 % of
             // this kernel's stall samples (ncu).
             long t = (long)tile - 1;
