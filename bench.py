@@ -213,6 +213,7 @@ def main():
         s2p.reset()
         io = s2p.run_device(sam.data_ptr(), nbytes, True, text.data_ptr(), text.numel(), pairs.data_ptr(), cap_pairs, stream=stream)
         n = io.n_pairs
+        text_len[0] = io.pairs_text_len
         src = pairs
         if world > 1:
             from microcket_b200 import shard
@@ -226,6 +227,7 @@ def main():
         return io.n_pairs, kept, nnz
 
     pair_events = []
+    text_len = [0]
 
     def barrier():
         if dist is not None:
@@ -279,6 +281,7 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
 
+    io_text_len = text_len[0]
     # ---- roofline of the dominant kernel, from CUDA events recorded on the launching stream during the timed region
     peak, peak_src = measured_peak()
     dk = {k: (kt1[k][0] - kt0[k][0], kt1[k][1] - kt0[k][1]) for k in kt1}
@@ -291,9 +294,13 @@ def main():
     # it fetches cover QNAME..CIGAR), its newline offset and flag byte, and writes one 48-byte record per line (an upper
     # bound is avoided by counting one record per read group only); the group kernel reads those records and writes a
     # 32-byte result per group; emit reads the results and the read id (~40 B) and writes ~72 B of text + 16 B packed.
+    text_b = float(io_text_len)                        # bytes of pair text of one pass
     alg = {"k_scan_chunks": nbytes + 4 * lines, "k_chunk_index": 8 * lines,
            "k_parse": 117.0 * lines + 48.0 * groups, "k_group": lines + 80.0 * groups,
-           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 0.0}
+           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 0.0,
+           # single-pass tile path: every SAM byte once, pair text + packed pairs written to the tile scratch;
+           # gather: the scratch read once and written once to the dense outputs
+           "k_ft_tile": nbytes + text_b + 16.0 * n_pairs, "k_ft_gather": 2.0 * (text_b + 16.0 * n_pairs)}
     per_kernel = {}
     for k, (ms_k, n_k) in dk.items():
         if ms_k > 0 and n_k > 0:
@@ -313,8 +320,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches_per_step": launches_per_step, "avg_launch_ms": dom_ms / max(dom_n, 1),
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
-                "s2p_stage": {"ms_per_step": stage_ms, "GBps": (nbytes + 72.0 * n_pairs) / (stage_ms / 1e3) / 1e9 if stage_ms else 0.0,
-                              "frac": ((nbytes + 72.0 * n_pairs) / (stage_ms / 1e3) / 1e9 / peak) if stage_ms else 0.0},
+                "s2p_stage": {"ms_per_step": stage_ms, "GBps": (nbytes + text_b) / (stage_ms / 1e3) / 1e9 if stage_ms else 0.0,
+                              "frac": ((nbytes + text_b) / (stage_ms / 1e3) / 1e9 / peak) if stage_ms else 0.0,
+                              "bytes": "SAM text in + pair text out (SURVEY 8d B_s2p)"},
                 "kernels": per_kernel}
     # the dedup + binning stage (pack, one radix sort of 16-byte records, unique/cell compaction), CUDA events around the call
     # on the launching stream: algorithmic = 16 B per pair in + 16 B per kept pair + 12 B per cell out; what the sort really

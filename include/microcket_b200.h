@@ -121,8 +121,9 @@ int  mk_s2p_run_device(mk_ctx *, const char *d_sam, size_t n, int is_last, mk_s2
 /* number of kernel launches issued by this context so far (for bench accounting) */
 uint64_t mk_launch_count(mk_ctx *);
 /* Optional per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figure).
- * ms[k] / count[k], k = 0 newline scan, 1 parse, 2 group, 3 emit, 4 SAM passthrough, 5 scan index (chunk prefix +
- * compaction); arrays of 6. */
+ * ms[k] / count[k]; arrays of 8.  k = 6 single-pass tile kernel (scan + parse + group + emit of one 128 KiB tile), 7 its
+ * tile prefix + gather; the multi-kernel path (MICROCKET_FUSED=0, or a window the tile path gives up): k = 0 newline
+ * scan, 1 parse, 2 group, 3 emit, 4 SAM passthrough, 5 scan index (chunk prefix + compaction). */
 int  mk_s2p_enable_timing(mk_ctx *, int on);
 int  mk_s2p_kernel_times(mk_ctx *, double *ms, uint64_t *count);
 

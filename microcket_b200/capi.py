@@ -258,10 +258,11 @@ class Sam2Pairs:
 
     def kernel_times(self):
         """→ {name: (total_ms, launches)} measured with CUDA events on the launching stream."""
-        ms = (C.c_double * 6)()
-        cnt = (C.c_uint64 * 6)()
+        ms = (C.c_double * 8)()
+        cnt = (C.c_uint64 * 8)()
         self.lib.check(self.lib.L.mk_s2p_kernel_times(self.h, ms, cnt))
-        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index"))}
+        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index",
+                                                           "k_ft_tile", "k_ft_gather"))}
 
     def push_ptr(self, ptr, n, is_last=False):
         """push() from a raw host pointer (e.g. a pinned torch tensor): no Python-side copy."""

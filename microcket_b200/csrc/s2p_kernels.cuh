@@ -63,6 +63,14 @@ struct WinState {
     unsigned long long counters[ST_NCOUNTER];
     u32 sc_count, n_chrom;
     u32 tickets[4];                  // dynamic tile tickets of the look-back kernels (scan, emit), reset per window
+    // single-pass tile path (s2p_fused.cuh)
+    u32 path_old;                    // 1: this window goes through the multi-kernel path (tile path disabled or overflowed)
+    u32 halt;                        // a window overflowed the tile path and no inline fallback was enqueued: nothing advances until the host redoes it
+    u32 sc_count0;                   // sc_count at the start of the window (restored when the tile path gives the window up)
+    u32 ft_carry_tile, ft_carry_nl;  // tile (window-local) of the carried group's first line, newlines of that tile before it
+    u32 ft_lines_before_carry, ft_pad;
+    u64 ft_carry_pos, ft_last_end;   // absolute offset of the carried group's first line (~0: none); end of the window's last complete line
+    unsigned long long w_counters[ST_NCOUNTER];   // this window's class counters, committed by k_ft_prefix
 };
 
 #define S2P_ERR_LINES 1u
@@ -95,6 +103,10 @@ struct S2PParams {
     int mode, min_mapq, write_sam, emit_text, emit_packed; float ratio; u16 lane;
     int running_offsets;      // 1: append at st->out_* (device-resident runs); 0: every window writes at 0
     int dyn_tickets;          // look-back kernels claim tiles with an atomic ticket (1) or round-robin (0)
+    // single-pass tile path: per-tile scratch (text bytes, packed pairs, passthrough copy entries), indexed by window-local tile
+    int fused;                // 1: windows go through k_ft_tile first
+    int old_inline;           // 1: the multi-kernel path is enqueued behind it and takes over a window the tile path gives up
+    char *ft_text; mk_pair *ft_pairs; uint4 *ft_sam, *ft_tot, *ft_pre; u32 *ft_nent; u32 n_tiles_cap;
 };
 
 // ------------------------------------------------------------------------------------------------ begin / end
@@ -104,6 +116,7 @@ static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     if (i < n_desc) { p.desc_scan[i] = 0; p.desc_emitA[i] = 0; p.desc_emitB[i] = 0; p.wave_scan[i] = 0; p.wave_emitA[i] = 0; p.wave_emitB[i] = 0; }
     if (i == 0) {
         WinState *s = p.st;
+        if (s->halt) return;
         s->ws = s->cursor;
         u64 we = s->cursor + p.window_bytes;
         s->we = we < s->total ? we : s->total;
@@ -112,25 +125,39 @@ static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
         s->w_groups = s->w_emit = s->w_text = s->w_sam = 0;
         s->tickets[0] = s->tickets[1] = s->tickets[2] = s->tickets[3] = 0;
         if (!p.running_offsets) { s->out_text = s->out_pairs = s->out_sam = 0; s->sc_count = 0; }
+        s->path_old = p.fused ? 0u : 1u; s->sc_count0 = s->sc_count;
+        s->ft_carry_tile = 0; s->ft_carry_nl = 0; s->ft_lines_before_carry = 0; s->ft_carry_pos = ~(u64)0; s->ft_last_end = 0;
+        for (int k = 0; k < ST_NCOUNTER; ++k) s->w_counters[k] = 0;
     }
 }
 
 static __global__ void k_win_end(S2PParams p) {
     WinState *s = p.st;
+    if (s->halt) return;                                   // the host redoes this window through the multi-kernel path
+    if (s->path_old && !p.old_inline && p.fused) { s->halt = 1; return; }
     u64 ws = s->ws, we = s->we;
     u32 n = s->n_lines;
     u64 next;
-    if (s->carry_line != 0xFFFFFFFFu) {
-        u32 c = s->carry_line;
-        next = ws + (c ? (u64)p.nl_pos[c - 1] + 1 : 0);
+    bool carried; u32 lines_before;
+    if (!s->path_old) {                                    // tile path: positions instead of line indices
+        carried = s->ft_carry_pos != ~(u64)0;
+        next = carried ? s->ft_carry_pos : (s->ft_last_end ? s->ft_last_end : ws);
+        lines_before = s->ft_lines_before_carry;
     } else {
-        next = ws + (n ? (u64)p.nl_pos[n - 1] + 1 : 0);   // no kept record: everything up to the last complete line is consumed
+        carried = s->carry_line != 0xFFFFFFFFu;
+        if (carried) {
+            u32 c = s->carry_line;
+            next = ws + (c ? (u64)p.nl_pos[c - 1] + 1 : 0);
+        } else {
+            next = ws + (n ? (u64)p.nl_pos[n - 1] + 1 : 0);   // no kept record: everything up to the last complete line is consumed
+        }
+        lines_before = s->carry_line;
     }
     bool final_win = (we == s->total) && s->is_last;
     if (final_win) next = s->total;                        // the stream's last group is never processed (pairutil.h:176)
     else if (next == ws && we > ws && we - ws >= p.window_bytes) s->err |= S2P_ERR_NOPROGRESS;  // one group (or line) fills the window
     s->cursor = next;
-    s->lines_done += (s->carry_line != 0xFFFFFFFFu && !final_win) ? s->carry_line : n;
+    s->lines_done += (carried && !final_win) ? lines_before : n;
     s->groups_done += s->w_groups;
     s->out_text += s->w_text; s->out_pairs += s->w_emit; s->out_sam += s->w_sam;
 }
@@ -265,6 +292,7 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
 template <int NT, int MINB = 3>
 static __global__ void __launch_bounds__(S2P_SCAN_THREADS, MINB) k_scan_lines(S2PParams p, int only_if_ovf) {
     WinState *st = p.st;
+    if (!st->path_old) return;
     if (only_if_ovf && !st->scan_ovf) return;          // fallback of the chunked scan: runs only for windows with very short lines
     scan_lines_body<NT>(p.buf, st->ws, st->we, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
 }
@@ -289,6 +317,7 @@ __device__ __forceinline__ u32 nl_raw(u32 x) {          // bit 7 of byte k set i
 
 static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PParams p) {
     const WinState *st = p.st;
+    if (!st->path_old) return;
     const u64 ws = st->ws, we = st->we;
     if (we <= ws) return;
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -365,6 +394,7 @@ static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PPara
 static __global__ void __launch_bounds__(256) k_chunk_prefix(S2PParams p) {
     __shared__ u32 s_w[8];
     WinState *st = p.st;
+    if (!st->path_old) return;
     const u64 ws = st->ws, we = st->we;
     if (we <= ws) return;
     const u64 nc64 = (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1;
@@ -392,6 +422,7 @@ static __global__ void __launch_bounds__(256) k_chunk_prefix(S2PParams p) {
 
 static __global__ void __launch_bounds__(256) k_chunk_compact(S2PParams p) {
     WinState *st = p.st;
+    if (!st->path_old) return;
     const u64 lc = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (lc >= p.n_chunks_cap) return;
     const u32 lane = threadIdx.x & 31u;
@@ -545,6 +576,7 @@ __device__ __forceinline__ u32 lt21_y(u32 x) {                       // 0x80 in 
     const u32 t = (x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu;
     return ~(t | x) & 0x80808080u;
 }
+static __device__ bool qname_equal_abs(const S2PParams &p, u64 pa, u64 pb);
 static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b);
 
 // ---- word-at-a-time fast path -------------------------------------------------------------------------------------
@@ -730,17 +762,21 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
 }
 
 // the generic byte-loop parser, out of line: it is the rare path and would otherwise triple the hot loop's code size
-static __device__ __noinline__ u32 parse_line_slow(const S2PParams &p, u64 ws, u32 i, u64 a, LineRec &rec) {
+static __device__ __noinline__ u32 parse_line_slow_abs(const S2PParams &p, u64 a, bool has_prev, u64 pa, LineRec &rec) {
     ByteReader r, q;
     r.init(p.buf, a);
-    if (i > 0) q.init(p.buf, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0));
-    return parse_line(p, r, q, i > 0, a, rec);
+    if (has_prev) q.init(p.buf, pa);
+    return parse_line(p, r, q, has_prev, a, rec);
+}
+static __device__ __forceinline__ u32 parse_line_slow(const S2PParams &p, u64 ws, u32 i, u64 a, LineRec &rec) {
+    return parse_line_slow_abs(p, a, i > 0, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0), rec);
 }
 
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
     __shared__ u32 s_line[LF_WORDS][256];                             // every thread's line prefix, one column of words per thread
     __shared__ u64 s_A[256];                                          // its 16-byte aligned base, or ~0 when not staged
     const WinState *st = p.st;
+    if (!st->path_old) return;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const u64 limit = st->total;
@@ -801,207 +837,6 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K1+K2 fused
-// One pass over the SAM bytes: 32 KiB tiles are brought into shared memory by TMA bulk copies (double buffered,
-// mbarrier completion), newline flags are computed from shared memory, and every line that STARTS in the tile is
-// parsed from shared memory by one thread (lines are compacted onto the low threads so warps are full).  The tile
-// publishes its newline count before parsing and resolves the decoupled look-back after it, so the wait for
-// predecessor tiles is hidden behind the parse.
-#define FZ_TILE 32768
-#define FZ_HALO 512
-#define FZ_THREADS 256
-#define FZ_LCAP 4096
-#define FZ_SMEM (2 * (FZ_TILE + FZ_HALO) + (FZ_TILE / 16) * 4 + FZ_LCAP * 2 + 64 + 32)
-
-#undef FZ_SMEM
-#define FZ_SMEM (2 * (FZ_TILE + FZ_HALO) + 2 * (FZ_TILE / 16) * 4 + FZ_LCAP * 2 + 128)
-
-// newline flags of one tile (from shared memory) -> s_z, per-thread masks of its 128-byte block, counts
-struct FzCount { u32 zz[8]; u32 cnt, my_first, total; };
-
-static __global__ void __launch_bounds__(FZ_THREADS) k_scan_parse(S2PParams p) {
-    extern __shared__ __align__(128) unsigned char fz_smem[];
-    char *s_tile0 = (char *)fz_smem, *s_tile1 = s_tile0 + FZ_TILE + FZ_HALO;
-    u32 *s_z = (u32 *)(fz_smem + 2 * (FZ_TILE + FZ_HALO));             // [2][2048]
-    u16 *s_nl = (u16 *)(s_z + 2 * (FZ_TILE / 16));
-    u32 *s_wtot = (u32 *)(s_nl + FZ_LCAP);                              // [2][8]
-    u32 *s_misc = s_wtot + 16;                                          // [0] excl, [1] claimed tile
-    u64 *s_bar = (u64 *)(s_misc + 8);
-    WinState *st = p.st;
-    const u64 ws = st->ws, we = st->we;
-    if (we <= ws) return;
-    const int first_tile = (int)st->first_tile;
-    const int last_tile = (int)((we - 1) / FZ_TILE);
-    const u64 readable = (st->total + 15) & ~(u64)15;                   // callers guarantee the buffer is readable up to here
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    u64 *desc = p.desc_scan - first_tile;
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    auto issue = [&](int t, int stage) {
-        const u64 tbase = (u64)t * FZ_TILE;
-        u64 n = readable - tbase;
-        if (n > FZ_TILE + FZ_HALO) n = FZ_TILE + FZ_HALO;
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&s_bar[stage], (u32)n);
-        bulk_copy_g2s(stage ? s_tile1 : s_tile0, p.buf + tbase, (u32)n, &s_bar[stage]);
-    };
-    // claim (in order) and start loading a tile; every thread learns the tile id after the next barrier
-    auto claim = [&](int stage) {
-        if (tid == 0) {
-            const int t = first_tile + (int)atomicAdd(&st->tickets[0], 1u);
-            s_misc[1] = (u32)t;
-            if (t <= last_tile) issue(t, stage);
-        }
-    };
-    // count the newlines of a loaded tile and publish the aggregate (two barriers)
-    auto count_tile = [&](int t, int stage, u32 parity, FzCount &c) {
-        const u64 tbase = (u64)t * FZ_TILE;
-        const char *tl = stage ? s_tile1 : s_tile0;
-        u32 *z_out = s_z + stage * (FZ_TILE / 16);
-        mbar_wait(&s_bar[stage], parity);
-        const bool interior = tbase >= ws && tbase + FZ_TILE <= we;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint4 w = ((const uint4 *)tl)[j * FZ_THREADS + tid];
-            u32 z = nl_flags16(w);
-            if (!interior && z) {
-                const u64 off = tbase + ((u64)(j * FZ_THREADS + tid) << 4);
-                u32 keep = 0;
-                for (u32 q = 0; q < 16; ++q) if (off + q >= ws && off + q < we) keep |= 1u << perm_bit_of_byte(q);
-                z &= keep;
-            }
-            z_out[j * FZ_THREADS + tid] = z;
-        }
-        __syncthreads();
-        const uint4 za = ((const uint4 *)z_out)[2 * tid], zb = ((const uint4 *)z_out)[2 * tid + 1];
-        c.zz[0] = za.x; c.zz[1] = za.y; c.zz[2] = za.z; c.zz[3] = za.w; c.zz[4] = zb.x; c.zz[5] = zb.y; c.zz[6] = zb.z; c.zz[7] = zb.w;
-        c.cnt = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) c.cnt += __popc(c.zz[i]);
-        const u32 inc = warp_incl_scan(c.cnt, lane);
-        if (lane == 31) s_wtot[stage * 8 + wid] = inc;
-        __syncthreads();
-        u32 before = 0; c.total = 0;
-#pragma unroll
-        for (int k = 0; k < FZ_THREADS / 32; ++k) { const u32 v = s_wtot[stage * 8 + k]; c.total += v; if (k < wid) before += v; }
-        c.my_first = before + inc - c.cnt;
-        if (tid == 0) lookback_publish(desc, t, first_tile, c.total);    // EARLY: one whole parse phase before anyone needs it
-    };
-
-    claim(0);
-    __syncthreads();
-    int tile = (int)s_misc[1];
-    if (tile > last_tile) return;
-    __syncthreads();
-    claim(1);
-    FzCount cur;
-    count_tile(tile, 0, 0, cur);
-    int next_tile = (int)s_misc[1];                                     // visible after count_tile's barriers
-    for (int it = 0; tile <= last_tile; ++it) {
-        const int stage = it & 1;
-        const u64 tbase = (u64)tile * FZ_TILE;
-        const char *tl = stage ? s_tile1 : s_tile0;
-        u64 loaded = readable - tbase; if (loaded > FZ_TILE + FZ_HALO) loaded = FZ_TILE + FZ_HALO;
-        const u32 total = cur.total;
-        // Lines starting in this tile: local id 0 = the line that begins at the tile's first byte (or at ws), if any;
-        // local id r+1 = the line opened by the tile's r-th newline.  Global line index = excl + local id.
-        bool has_initial; u64 initial_abs;
-        if (tbase <= ws) { has_initial = true; initial_abs = ws; }
-        else { initial_abs = tbase; has_initial = p.buf[tbase - 1] == '\n'; }
-        // ---- a. parse the first batch of lines (all of them unless lines are very short)
-        u32 excl = 0;
-        FzCount nxt; nxt.total = 0; nxt.cnt = 0; nxt.my_first = 0;
-        for (u32 r0 = 0; r0 == 0 || r0 < total; r0 += FZ_LCAP) {
-            if (cur.cnt) {                                               // local newline offsets of ranks [r0, r0 + FZ_LCAP)
-                u32 rk = cur.my_first;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    u32 z = cur.zz[i];
-                    if (!z) continue;
-                    u32 m = 0;
-                    while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
-                    while (m) {
-                        const u32 q = __ffs(m) - 1; m &= m - 1;
-                        if (rk >= r0 && rk < r0 + FZ_LCAP) s_nl[rk - r0] = (u16)(tid * 128 + i * 16 + q);
-                        ++rk;
-                    }
-                }
-            }
-            __syncthreads();
-            const u32 n_here = total - r0 < FZ_LCAP ? total - r0 : FZ_LCAP;
-            for (u32 base_id = r0 ? r0 + 1 : 0; base_id <= r0 + n_here; base_id += FZ_THREADS) {
-                // consecutive lines go to different warps (8 lanes of every warp for a typical 64-line tile): the parse is a
-                // dependent chain per line, so its latency is hidden by warps, not by lanes
-                const u32 id = base_id + (u32)((tid & 7) * 32 + (tid >> 3));
-                u32 meta = 0; LineRec rec; bool mine = false; u64 abs0 = 0;
-                if (id <= r0 + n_here) {
-                    bool exists = true;
-                    if (id == 0) { exists = has_initial; abs0 = initial_abs; }
-                    else { const u32 off = (u32)s_nl[id - 1 - r0] + 1; exists = off < FZ_TILE; abs0 = tbase + off; }
-                    if (exists && abs0 < we) {
-                        mine = true;
-                        bool cmp = false; u64 prev_abs = 0;              // previous line's start, when it is known here
-                        if (id >= 2 && id - 2 >= r0) { cmp = true; prev_abs = tbase + (u32)s_nl[id - 2 - r0] + 1; }
-                        else if (id == 1 && has_initial && r0 == 0) { cmp = true; prev_abs = initial_abs; }
-                        TileFetch tf; tf.buf = p.buf; tf.sm = tl; tf.tlo = tbase; tf.thi = tbase + loaded; tf.A = abs0 & ~(u64)15;
-                        FastTok tok;
-                        if (parse_line_fast<TileFetch, false>(p, tf, abs0, st->total, tok, rec, meta)) {
-                            if (cmp && qname_eq_fetch(tf, abs0, prev_abs, tok.t0)) meta |= LM_EQ;
-                        } else {
-                            TileReader r, q;
-                            r.setup(p.buf, tl, tbase, tbase + loaded); q.setup(p.buf, tl, tbase, tbase + loaded);
-                            r.init(p.buf, abs0);
-                            if (cmp) q.init(p.buf, prev_abs);
-                            meta = parse_line(p, r, q, cmp, abs0, rec);
-                        }
-                        if (!cmp && abs0 != ws) meta |= LM_EQ_UNK;
-                    }
-                }
-                if (base_id == 0) {
-                    // ---- b. count the NEXT tile and publish its aggregate, then c. resolve this tile's look-back
-                    if (next_tile <= last_tile) count_tile(next_tile, stage ^ 1, (u32)((it + 1) >> 1) & 1u, nxt);
-                    if (wid == 0) { const u64 e = lookback_resolve(desc, tile, first_tile, total, lane); if (lane == 0) s_misc[0] = (u32)e; }
-                    __syncthreads();
-                    excl = s_misc[0];
-                    if (tile == last_tile && tid == 0) {
-                        u64 nl = (u64)excl + total;
-                        if (nl > p.cap_lines) { atomicOr(&st->err, S2P_ERR_LINES); nl = p.cap_lines; }
-                        st->n_lines = (u32)nl;
-                    }
-                }
-                if (mine) {
-                    const u32 g = excl + id;
-                    if (g < p.cap_lines) {
-                        if (meta & LM_KEEP) p.rec[g] = rec;
-                        p.lmeta[g] = (u8)meta;
-                        if (p.write_sam) p.sam_dst[g] = 0xFFFFFFFFu;
-                    }
-                }
-            }
-            __syncthreads();                                             // s_nl is rewritten by the next round
-        }
-        // ---- newline positions (relative to ws) at their global ranks
-        if (cur.cnt) {
-            u32 idx = excl + cur.my_first;
-            const u32 rel = (u32)(tbase + (u64)tid * 128 - ws);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                u32 z = cur.zz[i];
-                if (!z) continue;
-                u32 m = 0;
-                while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
-                while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (idx < p.cap_lines) p.nl_pos[idx] = rel + i * 16 + q; ++idx; }
-            }
-        }
-        // ---- d. this tile's stage is free: claim and prefetch the tile after next
-        claim(stage);
-        __syncthreads();
-        tile = next_tile; next_tile = (int)s_misc[1];
-        cur = nxt;
-        __syncthreads();                                                 // s_misc[1] may be overwritten by the next claim
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ K3: groups
 struct Seg { u32 pos, right0, left1, right1, leftClip, rightClip, mappable; int segCnt; bool minus; u16 chr; };
 
@@ -1055,7 +890,10 @@ static __device__ __noinline__ bool qname_equal_bytes(const S2PParams &p, u64 pa
     return is_ws(c) && is_ws(d);
 }
 static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
-    const u64 pa = ws + (a ? p.nl_pos[a - 1] + 1 : 0), pb = ws + (b ? p.nl_pos[b - 1] + 1 : 0);
+    return qname_equal_abs(p, ws + (a ? p.nl_pos[a - 1] + 1 : 0), ws + (b ? p.nl_pos[b - 1] + 1 : 0));
+}
+// first tokens of the lines that start at absolute offsets pa and pb
+static __device__ bool qname_equal_abs(const S2PParams &p, u64 pa, u64 pb) {
     GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
     for (u32 k = 0;; k += 8) {
         const u64 x = fetch8(gf, pa + k), y = fetch8(gf, pb + k);
@@ -1095,11 +933,120 @@ __device__ __forceinline__ u32 dec_digits(u32 v) {
            v >= 10000u ? 5 : v >= 1000u ? 4 : v >= 100u ? 3 : v >= 10u ? 2 : 1;
 }
 
+// Resolution of one read group from the records of its kept lines (flash2pairs.h:25-154, unc2pairs.h:29-358): n kept records,
+// n1 / n2 of them flagged first / second in pair; f0, f1 = the first two kept records, a1, b1 / a2, b2 = the first two R1 / R2
+// records (pointers beyond the counts are never dereferenced).  Shared by the multi-kernel path and the single-pass tile path.
+struct Resolved { u32 p1, p2; u16 sA, sB; u8 status, strands; bool have; };
+__device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32 n1, u32 n2, const LineRec *f0, const LineRec *f1,
+                                                  const LineRec *a1, const LineRec *b1, const LineRec *a2, const LineRec *b2) {
+    Resolved o; o.p1 = o.p2 = 0; o.sA = o.sB = 0; o.status = ST_NONE; o.strands = 0; o.have = false;
+    u32 p1 = 0, p2 = 0; u16 c1 = 0, c2 = 0; bool m1 = false, m2 = false; bool have = false, ordered = false;
+    const float ratio = p.ratio;
+    if (p.mode == 0) {                   // flash2pairs.h:25-154
+        if (n == 1) {
+            Seg a = seg_of(*f0);
+            if (a.segCnt == 0) o.status = ST_CIGARERR;
+            else if (a.segCnt > 2) o.status = ST_MANYHITS;
+            else if (!integrity1(a, ratio)) o.status = ST_LOWMAP;
+            else {
+                p1 = a.pos; p2 = a.segCnt == 2 ? a.right1 : a.right0;
+                u32 d = p2 - p1;
+                o.status = d >= 10000u ? ST_CIS10K : (d >= 1000u ? ST_CIS1K : ST_CIS0);
+                c1 = c2 = a.chr; m1 = false; m2 = true; have = true; ordered = true;   // always "+ -", never swapped
+            }
+        } else if (n == 2) {
+            Seg a = seg_of(*f0), b = seg_of(*f1);
+            if (a.segCnt == 0 || b.segCnt == 0) o.status = ST_CIGARERR;
+            else if (a.segCnt != 1 || b.segCnt != 1) o.status = ST_MANYHITS;
+            else if (!integrity2(a, b, ratio)) o.status = ST_LOWMAP;
+            else {
+                p1 = (int)a.leftClip > (int)a.rightClip ? a.right0 : a.pos;
+                p2 = (int)b.leftClip > (int)b.rightClip ? b.right0 : b.pos;
+                c1 = a.chr; c2 = b.chr; m1 = a.minus; m2 = b.minus; have = true;
+            }
+        } else o.status = ST_MANYHITS;
+    } else {                             // unc2pairs.h:29-358
+        if (n1 == 0 || n2 == 0 || n1 + n2 > 3) o.status = ST_NONE;        // silent drops, unc2pairs.h:52-59
+        else if (n1 == 1 && n2 == 1) {
+            Seg a = seg_of(*a1), b = seg_of(*a2);
+            if (a.segCnt == 0) o.status = ST_CIGARERR;
+            else if (!integrity1(a, ratio)) o.status = ST_LOWMAP;
+            else if (b.segCnt == 0) o.status = ST_CIGARERR;
+            else if (!integrity1(b, ratio)) o.status = ST_LOWMAP;
+            else if (a.segCnt + b.segCnt > 3) o.status = ST_MANYHITS;
+            else {
+                c1 = a.chr; c2 = b.chr; m1 = a.minus; m2 = b.minus; have = true;
+                if (a.segCnt == 1 && b.segCnt == 1) {
+                    p1 = a.minus ? a.right0 : a.pos; p2 = b.minus ? b.right0 : b.pos;
+                } else if (a.segCnt == 2) {                                   // unc2pairs.h:146-167
+                    if (!a.minus) {
+                        if (b.minus && a.chr == b.chr && (int)a.left1 < (int)b.pos && (int)b.right0 - (int)a.left1 <= 1000) { p1 = a.pos; p2 = b.right0; }
+                        else { o.status = ST_UNPAIRED; have = false; }
+                    } else {
+                        if (!b.minus && a.chr == b.chr && (int)b.pos < (int)a.pos && (int)a.right0 - (int)b.pos <= 1000) { p1 = a.right1; p2 = b.pos; }
+                        else { o.status = ST_UNPAIRED; have = false; }
+                    }
+                } else {                                                      // unc2pairs.h:168-189
+                    if (!a.minus) {
+                        if (b.minus && a.chr == b.chr && (int)a.pos < (int)b.pos && (int)b.right0 - (int)a.pos <= 1000) { p1 = a.pos; p2 = b.right1; }
+                        else { o.status = ST_UNPAIRED; have = false; }
+                    } else {
+                        if (!b.minus && a.chr == b.chr && (int)b.left1 < (int)a.pos && (int)a.right0 - (int)b.left1 <= 1000) { p1 = a.right0; p2 = b.pos; }
+                        else { o.status = ST_UNPAIRED; have = false; }
+                    }
+                }
+            }
+        } else if (n1 == 1) {            // 1 + 2
+            Seg a = seg_of(*a1), b = seg_of(*a2), c = seg_of(*b2);
+            if (a.segCnt == 0) o.status = ST_CIGARERR;
+            else if (!integrity1(a, ratio)) o.status = ST_LOWMAP;
+            else if (b.segCnt == 0 || c.segCnt == 0) o.status = ST_CIGARERR;
+            else if (!integrity2(b, c, ratio)) o.status = ST_LOWMAP;
+            else if (a.segCnt != 1 || b.segCnt != 1 || c.segCnt != 1) o.status = ST_MANYHITS;
+            else {
+                c1 = a.chr; m1 = a.minus; p1 = a.minus ? a.right0 : a.pos;
+                if (mates(a, b)) { c2 = c.chr; m2 = c.minus; p2 = distal_end(c); have = true; }
+                else if (mates(a, c)) { c2 = b.chr; m2 = b.minus; p2 = distal_end(b); have = true; }
+                else o.status = ST_UNPAIRED;
+            }
+        } else {                         // 2 + 1
+            Seg a = seg_of(*a1), b = seg_of(*b1), c = seg_of(*a2);
+            if (a.segCnt == 0 || b.segCnt == 0) o.status = ST_CIGARERR;
+            else if (!integrity2(a, b, ratio)) o.status = ST_LOWMAP;
+            else if (c.segCnt == 0) o.status = ST_CIGARERR;
+            else if (!integrity1(c, ratio)) o.status = ST_LOWMAP;
+            else if (a.segCnt != 1 || b.segCnt != 1 || c.segCnt != 1) o.status = ST_MANYHITS;
+            else {
+                c2 = c.chr; m2 = c.minus; p2 = c.minus ? c.right0 : c.pos;
+                if (mates(c, a)) { c1 = b.chr; m1 = b.minus; p1 = distal_end(b); have = true; }
+                else if (mates(c, b)) { c1 = a.chr; m1 = a.minus; p1 = distal_end(a); have = true; }
+                else o.status = ST_UNPAIRED;
+            }
+        }
+    }
+    if (have) {
+        u16 sA = c1, sB = c2;
+        if (!ordered) {                  // unc2pairs.h:310-348
+            int cc = chr_name_cmp(p, c1, c2);
+            if (!(cc < 0 || (cc == 0 && p1 < p2))) {
+                u32 t = p1; p1 = p2; p2 = t; sA = c2; sB = c1; bool tm = m1; m1 = m2; m2 = tm;
+            }
+            if (cc == 0) {
+                u32 d = p2 - p1;
+                o.status = d <= 10u ? ST_SELFCIRCLE : (d >= 10000u ? ST_CIS10K : (d >= 1000u ? ST_CIS1K : ST_CIS0));
+            } else o.status = ST_TRANS;
+        }
+        o.p1 = p1; o.p2 = p2; o.sA = sA; o.sB = sB; o.strands = (u8)((m1 ? 1 : 0) | (m2 ? 2 : 0)); o.have = true;
+    }
+    return o;
+}
+
 static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
+    WinState *st = p.st;
+    if (!st->path_old) return;
     if (threadIdx.x < ST_NCOUNTER) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const u32 n_round = (n_lines + 31u) & ~31u;                        // whole warps stay in the loop (warp reduction at its end)
@@ -1148,115 +1095,22 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
             continue;
         }
         // ---- resolve
-        GroupRes g; g.status = ST_NONE; g.posA = g.posB = 0; g.chrA = g.chrB = 0; g.strands = 0;
+        GroupRes g; g.posA = g.posB = 0; g.chrA = g.chrB = 0; g.strands = 0;
         {
             const LineRec *rp = &p.rec[prev];
             g.rid_len = rp->qname_len; g.rid_off = (prev ? p.nl_pos[prev - 1] + 1 : 0) + rp->qname_off;
         }
         g.last_line = prev; g.text_len = 0; g.sam_len = sam_len;
-        u32 p1 = 0, p2 = 0; u16 c1 = 0, c2 = 0; bool m1 = false, m2 = false; bool have = false, ordered = false;
-        const float ratio = p.ratio;
-        if (p.mode == 0) {                   // flash2pairs.h:25-154
-            if (n == 1) {
-                Seg a = seg_of(p.rec[first[0]]);
-                if (a.segCnt == 0) g.status = ST_CIGARERR;
-                else if (a.segCnt > 2) g.status = ST_MANYHITS;
-                else if (!integrity1(a, ratio)) g.status = ST_LOWMAP;
-                else {
-                    p1 = a.pos; p2 = a.segCnt == 2 ? a.right1 : a.right0;
-                    u32 d = p2 - p1;
-                    g.status = d >= 10000u ? ST_CIS10K : (d >= 1000u ? ST_CIS1K : ST_CIS0);
-                    c1 = c2 = a.chr; m1 = false; m2 = true; have = true; ordered = true;   // always "+ -", never swapped
-                }
-            } else if (n == 2) {
-                Seg a = seg_of(p.rec[first[0]]), b = seg_of(p.rec[first[1]]);
-                if (a.segCnt == 0 || b.segCnt == 0) g.status = ST_CIGARERR;
-                else if (a.segCnt != 1 || b.segCnt != 1) g.status = ST_MANYHITS;
-                else if (!integrity2(a, b, ratio)) g.status = ST_LOWMAP;
-                else {
-                    p1 = (int)a.leftClip > (int)a.rightClip ? a.right0 : a.pos;
-                    p2 = (int)b.leftClip > (int)b.rightClip ? b.right0 : b.pos;
-                    c1 = a.chr; c2 = b.chr; m1 = a.minus; m2 = b.minus; have = true;
-                }
-            } else g.status = ST_MANYHITS;
-        } else {                             // unc2pairs.h:29-358
-            if (n1 == 0 || n2 == 0 || n1 + n2 > 3) g.status = ST_NONE;        // silent drops, unc2pairs.h:52-59
-            else if (n1 == 1 && n2 == 1) {
-                Seg a = seg_of(p.rec[r1[0]]), b = seg_of(p.rec[r2[0]]);
-                if (a.segCnt == 0) g.status = ST_CIGARERR;
-                else if (!integrity1(a, ratio)) g.status = ST_LOWMAP;
-                else if (b.segCnt == 0) g.status = ST_CIGARERR;
-                else if (!integrity1(b, ratio)) g.status = ST_LOWMAP;
-                else if (a.segCnt + b.segCnt > 3) g.status = ST_MANYHITS;
-                else {
-                    c1 = a.chr; c2 = b.chr; m1 = a.minus; m2 = b.minus; have = true;
-                    if (a.segCnt == 1 && b.segCnt == 1) {
-                        p1 = a.minus ? a.right0 : a.pos; p2 = b.minus ? b.right0 : b.pos;
-                    } else if (a.segCnt == 2) {                                   // unc2pairs.h:146-167
-                        if (!a.minus) {
-                            if (b.minus && a.chr == b.chr && (int)a.left1 < (int)b.pos && (int)b.right0 - (int)a.left1 <= 1000) { p1 = a.pos; p2 = b.right0; }
-                            else { g.status = ST_UNPAIRED; have = false; }
-                        } else {
-                            if (!b.minus && a.chr == b.chr && (int)b.pos < (int)a.pos && (int)a.right0 - (int)b.pos <= 1000) { p1 = a.right1; p2 = b.pos; }
-                            else { g.status = ST_UNPAIRED; have = false; }
-                        }
-                    } else {                                                      // unc2pairs.h:168-189
-                        if (!a.minus) {
-                            if (b.minus && a.chr == b.chr && (int)a.pos < (int)b.pos && (int)b.right0 - (int)a.pos <= 1000) { p1 = a.pos; p2 = b.right1; }
-                            else { g.status = ST_UNPAIRED; have = false; }
-                        } else {
-                            if (!b.minus && a.chr == b.chr && (int)b.left1 < (int)a.pos && (int)a.right0 - (int)b.left1 <= 1000) { p1 = a.right0; p2 = b.pos; }
-                            else { g.status = ST_UNPAIRED; have = false; }
-                        }
-                    }
-                }
-            } else if (n1 == 1) {            // 1 + 2
-                Seg a = seg_of(p.rec[r1[0]]), b = seg_of(p.rec[r2[0]]), c = seg_of(p.rec[r2[1]]);
-                if (a.segCnt == 0) g.status = ST_CIGARERR;
-                else if (!integrity1(a, ratio)) g.status = ST_LOWMAP;
-                else if (b.segCnt == 0 || c.segCnt == 0) g.status = ST_CIGARERR;
-                else if (!integrity2(b, c, ratio)) g.status = ST_LOWMAP;
-                else if (a.segCnt != 1 || b.segCnt != 1 || c.segCnt != 1) g.status = ST_MANYHITS;
-                else {
-                    c1 = a.chr; m1 = a.minus; p1 = a.minus ? a.right0 : a.pos;
-                    if (mates(a, b)) { c2 = c.chr; m2 = c.minus; p2 = distal_end(c); have = true; }
-                    else if (mates(a, c)) { c2 = b.chr; m2 = b.minus; p2 = distal_end(b); have = true; }
-                    else g.status = ST_UNPAIRED;
-                }
-            } else {                         // 2 + 1
-                Seg a = seg_of(p.rec[r1[0]]), b = seg_of(p.rec[r1[1]]), c = seg_of(p.rec[r2[0]]);
-                if (a.segCnt == 0 || b.segCnt == 0) g.status = ST_CIGARERR;
-                else if (!integrity2(a, b, ratio)) g.status = ST_LOWMAP;
-                else if (c.segCnt == 0) g.status = ST_CIGARERR;
-                else if (!integrity1(c, ratio)) g.status = ST_LOWMAP;
-                else if (a.segCnt != 1 || b.segCnt != 1 || c.segCnt != 1) g.status = ST_MANYHITS;
-                else {
-                    c2 = c.chr; m2 = c.minus; p2 = c.minus ? c.right0 : c.pos;
-                    if (mates(c, a)) { c1 = b.chr; m1 = b.minus; p1 = distal_end(b); have = true; }
-                    else if (mates(c, b)) { c1 = a.chr; m1 = a.minus; p1 = distal_end(a); have = true; }
-                    else g.status = ST_UNPAIRED;
-                }
-            }
-        }
+        const Resolved rs = resolve_group(p, n, n1, n2, &p.rec[first[0]], &p.rec[first[1]], &p.rec[r1[0]], &p.rec[r1[1]], &p.rec[r2[0]], &p.rec[r2[1]]);
+        g.status = rs.status;
         u32 meta = mi | LM_HEAD | LM_PROC;
-        if (have) {
-            u16 sA = c1, sB = c2;
-            if (!ordered) {                  // unc2pairs.h:310-348
-                int cc = chr_name_cmp(p, c1, c2);
-                if (!(cc < 0 || (cc == 0 && p1 < p2))) {
-                    u32 t = p1; p1 = p2; p2 = t; sA = c2; sB = c1; bool tm = m1; m1 = m2; m2 = tm;
-                }
-                if (cc == 0) {
-                    u32 d = p2 - p1;
-                    g.status = d <= 10u ? ST_SELFCIRCLE : (d >= 10000u ? ST_CIS10K : (d >= 1000u ? ST_CIS1K : ST_CIS0));
-                } else g.status = ST_TRANS;
-            }
-            g.posA = p1; g.posB = p2; g.strands = (u8)((m1 ? 1 : 0) | (m2 ? 2 : 0));
-            const ChrSlot *ca = &p.chr[sA], *cb = &p.chr[sB];
+        if (rs.have) {
+            g.posA = rs.p1; g.posB = rs.p2; g.strands = rs.strands;
+            const ChrSlot *ca = &p.chr[rs.sA], *cb = &p.chr[rs.sB];
             g.chrA = (u16)ca->id; g.chrB = (u16)cb->id;
             if (g.status != ST_SELFCIRCLE) {
                 meta |= LM_EMIT;
-                g.text_len = (u32)g.rid_len + ca->len + cb->len + dec_digits(p1) + dec_digits(p2) + 9u;
+                g.text_len = (u32)g.rid_len + ca->len + cb->len + dec_digits(rs.p1) + dec_digits(rs.p2) + 9u;
             }
         }
         if (!(meta & LM_EMIT)) g.sam_len = 0;
@@ -1308,18 +1162,22 @@ __device__ __forceinline__ RidInfo rid_info(const S2PParams &p, u64 ws, const Gr
     RidInfo r; r.len = g.rid_len; r.abs = ws + g.rid_off;
     return r;
 }
-__device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInfo &rid, const GroupRes &g, char *out) {
+__device__ __forceinline__ void write_pair_line_slots(const S2PParams &p, const RidInfo &rid, const ChrSlot *ca, const ChrSlot *cb,
+                                                      u32 posA, u32 posB, u32 strands, char *out) {
     GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
     for (u32 k = 0; k < rid.len; k += 8) { const u32 n = rid.len - k < 8 ? rid.len - k : 8; out = put_bytes8(out, fetch8(gf, rid.abs + k), n); }
     *out++ = '\t';
-    out = put_name(out, &p.chr[p.id_to_slot[g.chrA]]);
+    out = put_name(out, ca);
     *out++ = '\t';
-    out += put_uint(out, g.posA);
+    out += put_uint(out, posA);
     *out++ = '\t';
-    out = put_name(out, &p.chr[p.id_to_slot[g.chrB]]);
+    out = put_name(out, cb);
     *out++ = '\t';
-    out += put_uint(out, g.posB);
-    *out++ = '\t'; *out++ = (g.strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (g.strands & 2) ? '-' : '+'; *out++ = '\n';
+    out += put_uint(out, posB);
+    *out++ = '\t'; *out++ = (strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (strands & 2) ? '-' : '+'; *out++ = '\n';
+}
+__device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInfo &rid, const GroupRes &g, char *out) {
+    write_pair_line_slots(p, rid, &p.chr[p.id_to_slot[g.chrA]], &p.chr[p.id_to_slot[g.chrB]], g.posA, g.posB, g.strands, out);
 }
 
 // Tiles of 512 lines.  K3 has already summed every tile's sizes (tile_tot), k_emit_prefix turns them into exclusive prefixes
@@ -1332,6 +1190,7 @@ __device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInf
 static __global__ void __launch_bounds__(1024) k_emit_prefix(S2PParams p) {
     __shared__ u32 s_w[4][32];
     WinState *st = p.st;
+    if (!st->path_old) return;
     const u32 n_sub = (st->n_lines + EMIT_TILE - 1) / EMIT_TILE;
     const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const u32 per = (n_sub + 1023u) / 1024u;
@@ -1360,6 +1219,7 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
     __shared__ u32 s_w[2][EMIT_NT][3][EMIT_THREADS / 32];
     WinState *st = p.st;
+    if (!st->path_old) return;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1484,6 +1344,7 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
 // One warp per line: the lines of emitted groups are copied verbatim (with their '\n').
 static __global__ void __launch_bounds__(256) k_copy_sam(S2PParams p) {
     const WinState *st = p.st;
+    if (!st->path_old) return;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws, base = st->out_sam;
     const int lane = threadIdx.x & 31;

@@ -10,6 +10,19 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+@pytest.fixture(autouse=True, params=["tile", "multi"])
+def s2p_path(request):
+    """Every test runs through the single-pass tile path (default) and through the multi-kernel path alone (MICROCKET_FUSED=0,
+    read at context creation): the second is also what takes over a window the tile path gives up."""
+    old = os.environ.get("MICROCKET_FUSED")
+    os.environ["MICROCKET_FUSED"] = "1" if request.param == "tile" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("MICROCKET_FUSED", None)
+    else:
+        os.environ["MICROCKET_FUSED"] = old
+
+
 def rd(name):
     return open(os.path.join(G, name), "rb").read()
 
@@ -151,7 +164,7 @@ def test_sharded_contexts_reproduce_the_selfcircle_log_value(oracle):
         s.close()
 
 
-def test_reset_and_kernel_timing(oracle):
+def test_reset_and_kernel_timing(oracle, s2p_path):
     sam = mk.synth_host(8, "flash", "hg38", 0, 5000)
     op, _, ost = oracle.sam2pairs(sam, "flash", threads=8, write_sam=False)
     s = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False))
@@ -161,7 +174,10 @@ def test_reset_and_kernel_timing(oracle):
         p, _, st = s.run(sam)
         assert p == op and st.log_text() == ost.log_text()
     t = s.kernel_times()
-    assert t["k_scan_chunks"][1] >= 3 and t["k_scan_chunks"][0] > 0 and t["k_emit"][1] >= 3
+    if s2p_path == "tile":
+        assert t["k_ft_tile"][1] >= 3 and t["k_ft_tile"][0] > 0 and t["k_ft_gather"][1] >= 3
+    else:
+        assert t["k_scan_chunks"][1] >= 3 and t["k_scan_chunks"][0] > 0 and t["k_emit"][1] >= 3
     assert s.launches() > 0
     s.close()
 
@@ -177,3 +193,76 @@ def test_short_lines_take_the_lookback_scan(oracle, window):
     op, osam, ost = oracle.sam2pairs(ref, "unc", threads=8)
     p, so, st, _, _ = gpu_s2p(sam, "unc", window=window)
     assert p == op and so == osam and st.log_text() == ost.log_text()
+
+
+# ---------------------------------------------------------------------------------------------- tile-path geometry cases
+def _line(q, flag, chrom, pos, mapq, cigar, seqlen=100, tail=b""):
+    return b"\t".join([q, str(flag).encode(), chrom, str(pos).encode(), str(mapq).encode(), cigar, b"*", b"0", b"0",
+                       b"A" * seqlen, b"F" * seqlen]) + tail + b"\n"
+
+
+def _check(oracle, sam, mode, window=0, chunk=None):
+    op, osam, ost = oracle.sam2pairs(sam, mode, threads=8)
+    p, so, st, _, _ = gpu_s2p(sam, mode, window=window, chunk=chunk)
+    assert p == op and so == osam and st.log_text() == ost.log_text()
+    assert (st.groups, st.selfCircle_true, st.lines) == (ost.groups, ost.selfCircle_true, sam.count(b"\n") if not hasattr(ost, "lines") else ost.lines)
+    return st
+
+
+def test_long_lines_cross_halos_and_tiles(oracle):
+    """Lines of 3 KiB (longer than the 2 KiB halos), 40 KiB and 300 KiB (longer than a 128 KiB tile): tiles without any line
+    start, heads whose predecessor / successor lies outside the scanned halo (byte-level walks)."""
+    import random
+    rnd = random.Random(5)
+    out = []
+    for i in range(1500):
+        q = b"L%d" % i
+        L = rnd.choice([100, 100, 100, 3000, 3000, 40000, 300000 if i % 300 == 7 else 100])
+        out.append(_line(q, 65, b"chr1", 1000 + 13 * i, 60, b"100M", L))
+        if i % 3:
+            out.append(_line(q, 129, b"chr2", 9000 + 17 * i, 60, b"100M", rnd.choice([100, 3000])))
+        else:
+            out.append(_line(q, 145, b"chr1", 5000 + 13 * i, 60, b"50M50S", 100))
+    sam = b"".join(out)
+    _check(oracle, sam, "unc", window=0)
+    _check(oracle, sam, "unc", window=4 << 20, chunk=1234567)
+
+
+def test_groups_with_many_dropped_and_many_kept_lines(oracle):
+    """Filtered records between the mates (beyond the look-ahead of a round), groups of hundreds of kept records (manyHits /
+    silent drops spanning rounds and tiles), kept records that are neither first nor second in pair (passed through)."""
+    out = []
+    for i in range(4000):
+        q = b"G%d" % i
+        out.append(_line(q, 65, b"chr3", 2000 + 11 * i, 60, b"100M"))
+        k = i % 9
+        if k == 1:
+            out += [_line(q, 385, b"chr4", 77, 0, b"100M")] * 25            # secondary, MAPQ 0: dropped
+        elif k == 2:
+            out += [_line(q, 65, b"chr5", 100 + j, 60, b"100M") for j in range(300)]   # 301 R1 records
+        elif k == 3:
+            out += [_line(q, 1, b"chr5", 100 + j, 60, b"100M") for j in range(40)]     # kept, neither 64 nor 128
+        elif k == 4:
+            out += [_line(b"other%d" % i, 65, b"chr4", 77, 3, b"100M")] * 12           # dropped lines of ANOTHER name inside the group
+        out.append(_line(q, 145, b"chr3", 900000 + 7 * i, 60, b"100M"))
+    sam = b"".join(out)
+    _check(oracle, sam, "unc")
+    _check(oracle, sam, "unc", window=1 << 20, chunk=999983)
+    _check(oracle, sam, "flash")
+
+
+def test_tile_text_overflow_falls_back(oracle):
+    """Read ids of 220 bytes on minimal lines: more pair text per 128 KiB tile than the tile scratch holds, so the window is
+    handed to the multi-kernel path; the output must not change."""
+    out = []
+    for i in range(6000):
+        q = (b"Q%06d" % i) + b"x" * 213
+        out.append(_line(q, 65, b"chr1", 1000 + i, 60, b"10M", 10))
+        out.append(_line(q, 129, b"chr2", 5000 + i, 60, b"10M", 10))
+    _check(oracle, b"".join(out), "unc")
+
+
+def test_big_synthetic_both_modes(oracle):
+    for mode, seed in (("flash", 41), ("unc", 42)):
+        sam = mk.synth_host(seed, mode, "hg38", 0, 250000)
+        _check(oracle, sam, mode, window=64 << 20)
