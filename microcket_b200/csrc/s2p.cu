@@ -34,6 +34,7 @@ struct S2PCtx : mk_ctx {
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
     u32 n_chunks_cap = 0; bool scan_chunks = true;
     DevBuf d_cklist, d_ckcnt, d_tiletot;
+    DevBuf d_params;                               // device copies of the kernels' parameter blocks (S2PParams.self)
     DevBuf d_fttext, d_ftpairs, d_ftsam, d_fttot, d_ftnent; u32 n_tiles_cap = 0;   // single-pass tile path: per-tile scratch
     u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
@@ -109,7 +110,16 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.fused = c->fused ? 1 : 0; p.old_inline = old_inline;
     p.ft_text = c->d_fttext.as<char>(); p.ft_pairs = c->d_ftpairs.as<mk_pair>(); p.ft_sam = c->d_ftsam.as<uint4>();
     p.ft_tot = c->d_fttot.as<uint4>(); p.ft_pre = p.ft_tot + c->n_tiles_cap; p.ft_nent = c->d_ftnent.as<u32>(); p.n_tiles_cap = c->n_tiles_cap;
+    p.self = nullptr;
     return p;
+}
+
+// The parameter block also lives in device memory (slot 0..3 of d_params): out-of-line device functions take it by
+// reference from there, so no kernel copies its parameters to local memory.
+static int upload_params(S2PCtx *c, S2PParams &p, int slot, cudaStream_t s) {
+    p.self = c->d_params.as<S2PParams>() + slot;
+    MK_CUDA(cudaMemcpyAsync((void *)p.self, &p, sizeof p, cudaMemcpyHostToDevice, s));
+    return MK_OK;
 }
 
 // enqueue the kernels of one window on the compute stream: the single-pass tile path first (p.fused), the multi-kernel
@@ -122,7 +132,7 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     c->launches += 1;
     if (p.fused) {
         mark(7);
-        k_ft_tile<<<c->n_tiles_cap, FT_THREADS, FT_SMEM, s>>>(p);
+        k_ft_strip<<<c->grid_fused, FS_THREADS, FS_SMEM, s>>>(p);
         mark(8);
         k_ft_prefix<<<1, 1024, 0, s>>>(p);
         k_ft_gather<<<c->n_tiles_cap, 256, 0, s>>>(p);
@@ -224,6 +234,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     int rc = MK_OK;
 #define A(x) do { if (rc == MK_OK) rc = (x); } while (0)
     A(c->d_state.alloc(sizeof(WinState)));
+    A(c->d_params.alloc(4 * sizeof(S2PParams)));
     A(c->d_nl.alloc((size_t)c->cap_lines * 4)); A(c->d_lmeta.alloc(c->cap_lines)); A(c->d_rec.alloc((size_t)c->cap_lines * sizeof(LineRec)));
     A(c->d_res.alloc((size_t)c->cap_lines * sizeof(GroupRes)));
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
@@ -280,7 +291,10 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, std::min(occ, 4));
     c->grid_gs = sms * 8;
-    cudaFuncSetAttribute(k_ft_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    cudaFuncSetAttribute(k_ft_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ft_strip, FS_THREADS, FS_SMEM);
+    c->grid_fused = sms * std::max(1, occ);
+    if (getenv("MICROCKET_FT_GRID")) c->grid_fused = atoi(getenv("MICROCKET_FT_GRID"));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mk_set_error("mk_s2p_create: %s", cudaGetErrorString(e)); delete c; return MK_ERR_CUDA; }
     *out = c;
@@ -420,6 +434,7 @@ static int s2p_submit(S2PCtx *c, size_t n_stage, const char *direct, size_t n_di
     }
     S2PParams p = make_params(c, s.d_in.as<char>(), s.d_sc.as<u64>(), c->sc_cap, s.d_text.as<char>(), s.d_text.n,
                               s.d_pairs.as<mk_pair>(), c->cap_lines, s.d_sam.as<char>(), s.d_sam.n, S2P_CARRY + c->W + 64, 0, 1);
+    MK_TRY(upload_params(c, p, b, c->s_comp));
     launch_window(c, p, c->s_comp);
     MK_CUDA(cudaMemcpyAsync(s.h_state.p, c->d_state.p, sizeof(WinState), cudaMemcpyDeviceToHost, c->s_comp));
     MK_CUDA(cudaEventRecord(s.ev_done, c->s_comp));
@@ -672,6 +687,7 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
     c->launches += 1;
     S2PParams p = make_params(c, d_sam, c->d_sclist.as<u64>(), c->sc_cap_dev, io->d_pairs_text, io->pairs_text_cap, io->d_pairs, io->pairs_cap, io->d_sam_text, io->sam_text_cap, c->W, 1, 0);
     S2PParams p_old = p; p_old.fused = 0;                     // the multi-kernel path, for a window the tile path gave up
+    MK_TRY(upload_params(c, p, 2, s)); MK_TRY(upload_params(c, p_old, 3, s));
     // running output offsets restart at 0 for every call
     MK_CUDA(cudaMemsetAsync((char *)dst + offsetof(WinState, out_text), 0, 3 * sizeof(u64), s));
     // every window consumes at least W - (largest read group) bytes; enqueue an upper bound and top up if needed

@@ -1,48 +1,50 @@
 // s2p_fused.cuh — the single-pass sam2pairs path: every SAM byte is read from HBM once.
 //
-//   k_ft_tile    one CTA per 128 KiB tile of the window (absolute 128 KiB boundaries).  Eight warps stream the tile (16 KiB
-//                each, the same 128-bit SWAR newline test as k_scan_chunks) plus 2 KiB on either side; the newline positions
-//                go to shared memory, never to HBM.  The lines that start in the tile are then parsed one per thread out of L2
-//                (their first 112 bytes, staged in shared memory like k_parse), grouped by QNAME, resolved (resolve_group) and
-//                turned into .pairs text, packed pairs and passthrough copy entries in the tile's own scratch segment — no
-//                per-line record, line index or group result ever goes to HBM.  A tile depends on no other tile: the group that
-//                starts in it is followed into the next tile (halo lines, then a byte-level walk), and whether its first kept
-//                line continues a group of the previous tile is decided by looking back the same way.
-//   k_ft_prefix  one CTA: exclusive prefixes of the tiles' sizes, window totals, counters committed, self-circle group indices
-//   k_ft_gather  one CTA per tile: the scratch segments copied to their final, dense positions (128-bit stores at any
+//   k_ft_strip   warp-private pipelines, no block barrier, no dependency between warps.  A warp claims a 128 KiB strip of the
+//                window (absolute 128 KiB boundaries, atomic ticket) and streams it with the same coalesced 128-bit loads and
+//                SWAR newline test as k_scan_chunks, eight 512-byte rows in flight.  Line starts go to a ring in shared memory,
+//                never to HBM.  Whenever 32 complete lines are pending, the warp parses them one per lane (their first 112
+//                bytes come back out of L2, staged in shared-memory columns so that unaligned 8-byte fetches are conflict-free
+//                32-bit loads), keeps the 52-byte records of the last 64 lines in shared memory, resolves the read groups whose
+//                eight-line look-ahead is complete (resolve_group) and writes .pairs text, packed pairs and passthrough copy
+//                entries into the strip's own scratch segment.  No per-line record, line index or group result goes to HBM.
+//                A strip depends on no other strip: the group that starts in it is followed into the next strip (2 KiB halo,
+//                then a byte-level walk from global memory), and whether its first kept line continues a group of the previous
+//                strip is decided by looking back the same way.
+//   k_ft_prefix  one CTA: exclusive prefixes of the strips' sizes, window totals, counters committed, self-circle group indices
+//   k_ft_gather  one CTA per strip: the scratch segments copied to their final, dense positions (128-bit stores at any
 //                source/destination alignment), passthrough lines copied straight from the SAM text
 //
-// Replaces pairutil.h:136-177 (load_batch: getline, filter, grouping) + flash2pairs.h / unc2pairs.h bodies + the string
-// appends of unc2pairs.h:311-356 in one pass.  Anything the tile geometry cannot hold (more than FT_WCAP newlines in a 16 KiB
-// chunk, more than FT_LMAX lines or FT_TEXT_CAP bytes of pair text per tile) gives the WINDOW back to the multi-kernel path
-// (k_scan_chunks ... k_emit), which handles any input; results are identical by construction (same parsers, same resolver).
+// Replaces pairutil.h:136-177 (load_batch: getline, filter, grouping) + the flash2pairs.h / unc2pairs.h bodies + the string
+// appends of unc2pairs.h:311-356 in one pass.  Anything the geometry cannot hold (more than ~160 newlines in 4 KiB, more than
+// FT_LMAX emitted pairs / passthrough lines or FT_TEXT_CAP bytes of pair text per strip) gives the WINDOW back to the
+// multi-kernel path (k_scan_chunks ... k_emit), which handles any input; results are identical by construction (same
+// tokenisation rules, same generic parser for anything unusual, same resolver).
 #pragma once
 #include "s2p_kernels.cuh"
 
-#define FT_THREADS 256
-#define FT_WARPS 8
-#define FT_CHUNK 16384u
-#define FT_TILE (FT_WARPS * FT_CHUNK)
-#define FT_HALO 2048u                 // bytes scanned on either side of the tile (4 rows of 512 B)
-#define FT_WCAP 384u                  // newline slots per 16 KiB chunk (lines of >= 43 B on average)
-#define FT_HCAP 32u                   // newline slots per 512-byte halo row
-#define FT_LMAX 1024u                 // line starts per tile (halo included)
-#define FT_LOOKBACK 2u                // lines parsed before / after the heads a round resolves
-#define FT_LOOKAHEAD 6u
-#define FT_TEXT_CAP 49152u            // bytes of pair text per tile in the scratch
-#define FT_STAGE_CAP 32752u           // text of one round staged in shared memory (the line-head columns are dead by then)
-#define FT_M_END 0x80u                // s_meta: no (complete, parsed) line here
+#define FT_TILE 131072u               // strip size; ft_tot / ft_pre / scratch segments are indexed by window-local strip
+#define FT_LMAX 1024u                 // emitted pairs / passthrough entries per strip
+#define FT_TEXT_CAP 49152u            // bytes of pair text per strip in the scratch
+#define FS_THREADS 256
+#define FS_WARPS 8
+#define FS_HALO 2048u                 // bytes scanned on either side of the strip (4 rows of 512 B)
+#define FS_RING 256u                  // line starts (relative to the strip's scan origin) known to the warp
+#define FS_RECS 64u                   // records / meta bytes of the last 64 parsed lines
+#define FS_LOOKAHEAD 8u               // lines parsed beyond the heads a round resolves
+#define FS_STAGE 4064u                // pair text of one round staged in the (then dead) line-head columns
 
-#define FT_OFF_LINE 0
-#define FT_OFF_REC 32768
-#define FT_OFF_START (FT_OFF_REC + 12288)
-#define FT_OFF_A (FT_OFF_START + 4 * (FT_LMAX + 4))
-#define FT_OFF_META (FT_OFF_A + 2048)
-#define FT_OFF_MISC (FT_OFF_META + 256)
-#define FT_SMEM (FT_OFF_MISC + 512)
-
-static_assert(FT_WARPS * FT_WCAP * 2 + FT_WARPS * FT_HCAP * 2 <= 12288, "newline lists alias the record array");
-static_assert(sizeof(LineRec) * 256 == 12288, "record array");
+struct __align__(4) FtRec {           // LineRec's fields at a 13-word stride: conflict-free across the lanes of a warp
+    u32 pos, right0, left1, right1, leftClip, rightClip, mappable, line_len;
+    u16 flag, qname_len, chr_slot; u8 segCnt, pad0;
+    u32 qname_off, pad1, pad2;
+};
+static_assert(sizeof(FtRec) == 52, "record stride");
+#define FS_OFF_REC 4096
+#define FS_OFF_RING (FS_OFF_REC + 52 * FS_RECS)
+#define FS_OFF_META (FS_OFF_RING + 4 * FS_RING)
+#define FS_WARP_SMEM (FS_OFF_META + FS_RECS)
+#define FS_SMEM (FS_WARPS * FS_WARP_SMEM + 64)
 
 // ---------------------------------------------------------------------------------------------- byte-level helpers (rare paths)
 #define FT_NONE (~(u64)0)
@@ -78,7 +80,7 @@ static __device__ __noinline__ bool ft_head_slow(const S2PParams &p, u64 ws, u64
     return true;
 }
 
-struct FtGroup { Resolved r; u32 sam_len, n_members; bool off_end; };
+struct FtGroup { Resolved r; u32 sam_len, n_members, qname_len, qname_off; bool off_end, kept; };
 // The whole group of the head line at `a_head`, line by line from global memory (any number of lines, any line length).
 // entries != nullptr: also writes one passthrough copy entry per member (src relative to ws, length with '\n', destination).
 static __device__ __noinline__ void ft_group_slow(const S2PParams &p, u64 ws, u64 we, u64 a_head, FtGroup &out, uint4 *entries, u32 ent_cap, u32 dst0) {
@@ -87,8 +89,10 @@ static __device__ __noinline__ void ft_group_slow(const S2PParams &p, u64 ws, u6
     out.off_end = false;
     u64 cur = a_head;
     u64 e = ft_find_nl(p.buf, cur, we);
-    u32 meta = parse_line_slow_abs(p, cur, false, 0, rec);
-    (void)meta;
+    const u32 meta = parse_line_slow_abs(p, cur, false, 0, rec);
+    out.kept = (meta & LM_KEEP) != 0; out.qname_len = rec.qname_len; out.qname_off = rec.qname_off;
+    out.sam_len = 0; out.n_members = 0;
+    if (!out.kept || e == FT_NONE) { out.off_end = true; return; }
     while (true) {
         // `rec` (line [cur, e]) is a member
         if (n < 2) f[n] = rec;
@@ -116,14 +120,13 @@ static __device__ __noinline__ void ft_group_slow(const S2PParams &p, u64 ws, u6
 }
 
 // ---------------------------------------------------------------------------------------------- scan of 512-byte rows
-// Newline offsets (relative to rbase) of `nrows` rows appended, in byte order, to a shared-memory list; returns their number
-// (which may exceed cap: the caller gives the window up).  Same tests as k_scan_chunks.
+// Line starts (newline offset + 1, relative to the scan origin; rel0 = offset of rbase from it) of `nrows` rows appended, in byte
+// order, to the warp's ring; returns the new number of known starts.  Same tests as k_scan_chunks.
 template <int U>
-__device__ __forceinline__ u32 ft_scan_rows(const char *buf, long long rbase, u32 nrows, u64 ws, u64 we, u16 *list, u32 cap, u32 lane) {
+__device__ __forceinline__ u32 fs_scan_push(const char *buf, long long rbase, u32 nrows, u32 rel0, u64 ws, u64 we, u32 *ring, u32 n, u32 lane) {
     const bool edge = rbase < (long long)ws || rbase + (long long)nrows * 512 > (long long)we;
     const uint4 *src = (const uint4 *)(buf + rbase) + lane;
     const u32 lt = (1u << lane) - 1u;
-    u32 n = 0;
 #pragma unroll 1
     for (u32 it = 0; it < nrows; it += U) {
         uint4 w[U];
@@ -151,12 +154,9 @@ __device__ __forceinline__ u32 ft_scan_rows(const char *buf, long long rbase, u3
             const u32 bal = __ballot_sync(0xFFFFFFFFu, z != 0);
             if (bal == 0) continue;
             const u32 multi = __ballot_sync(0xFFFFFFFFu, (z & (z - 1u)) != 0);
-            const u32 rel = (it + u) * 512u + lane * 16u;
+            const u32 rel = rel0 + (it + u) * 512u + lane * 16u + 1u;
             if (multi == 0) {
-                if (z) {
-                    const u32 idx = n + __popc(bal & lt);
-                    if (idx < cap) list[idx] = (u16)(rel + byte_of_perm_bit(__ffs(z) - 1));
-                }
+                if (z) ring[(n + __popc(bal & lt)) & (FS_RING - 1u)] = rel + byte_of_perm_bit(__ffs(z) - 1);
                 n += __popc(bal);
                 continue;
             }
@@ -168,7 +168,7 @@ __device__ __forceinline__ u32 ft_scan_rows(const char *buf, long long rbase, u3
 #pragma unroll 1
                 while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
 #pragma unroll 1
-                while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (idx < cap) list[idx] = (u16)(rel + q); ++idx; }
+                while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; ring[idx & (FS_RING - 1u)] = rel + q; ++idx; }
             }
             n += tot;
         }
@@ -176,328 +176,505 @@ __device__ __forceinline__ u32 ft_scan_rows(const char *buf, long long rbase, u3
     return n;
 }
 
-// ---------------------------------------------------------------------------------------------- the tile kernel
-// s_misc layout
-#define FM_OVF 0
-#define FM_GROUPS 1
-#define FM_EMIT 2
-#define FM_TEXT 3
-#define FM_SAM 4
-#define FM_NENT 5
-#define FM_CNT 8          // ST_NCOUNTER counters
-#define FM_SEG 24         // 16 segment counts
-#define FM_SCAN 40        // 4 x 8 warp totals
+// ---------------------------------------------------------------------------------------------- lean per-line parser
+// The lane's line head sits in a shared-memory column of 32-bit words, word w at col[32 * w]; four zero words follow the
+// 28 staged ones, so eight bytes at any offset below 112 are three conflict-free loads and two funnel shifts.
+struct ColFetch {
+    const u32 *col;
+    __device__ __forceinline__ u32 byter(u32 r) const { return (col[(r >> 2) * 32] >> (8 * (r & 3u))) & 0xFFu; }
+    __device__ __forceinline__ void f8(u32 r, u32 &lo, u32 &hi) const {
+        const u32 *q = col + (r >> 2) * 32; const u32 sh = (r & 3u) * 8u;
+        const u32 a = q[0], b = q[32], c = q[64];
+        lo = __funnelshift_r(a, b, sh); hi = __funnelshift_r(b, c, sh);
+    }
+};
+// `len` (1..8) decimal characters in the low bytes of hi:lo, first character lowest; ok is cleared on a non-digit
+__device__ __forceinline__ u32 dec8(u32 lo, u32 hi, u32 len, bool &ok) {
+    // right-align: the last character goes to byte 7
+    const u32 sh = (8u - len) * 8u;
+    u32 l2, h2, ml, mh;                                                // ml / mh: 0xFF in the real characters' bytes
+    if (sh >= 32u) { h2 = lo << (sh - 32u); l2 = 0; mh = 0xFFFFFFFFu << (sh - 32u); ml = 0; }
+    else { h2 = __funnelshift_l(lo, hi, sh); l2 = lo << sh; mh = 0xFFFFFFFFu; ml = 0xFFFFFFFFu << sh; }
+    l2 = (l2 ^ 0x30303030u) & ml; h2 = (h2 ^ 0x30303030u) & mh;         // digit values; anything else has a byte > 9
+    const u32 bad = ((((l2 & 0x7F7F7F7Fu) + 0x76767676u) | l2) | (((h2 & 0x7F7F7F7Fu) + 0x76767676u) | h2)) & 0x80808080u;
+    ok = ok && bad == 0;
+    u32 t = (l2 * 10u + (l2 >> 8)) & 0x00FF00FFu;
+    const u32 vl = (t & 0xFFu) * 100u + (t >> 16);
+    t = (h2 * 10u + (h2 >> 8)) & 0x00FF00FFu;
+    const u32 vh = (t & 0xFFu) * 100u + (t >> 16);
+    return vl * 10000u + vh;
+}
+// decimal field of 1..10 characters at offset r of the column
+__device__ __forceinline__ u32 fs_dec_field(const ColFetch &f, u32 r, u32 len, bool &ok) {
+    u32 lo, hi;
+    f.f8(r, lo, hi);
+    if (len <= 8u) return dec8(lo, hi, len, ok);
+    const u32 head = dec8(lo, hi, len - 8u, ok);                         // one or two leading characters
+    f.f8(r + len - 8u, lo, hi);
+    return head * 100000000u + dec8(lo, hi, 8u, ok);
+}
 
-static __global__ void __launch_bounds__(FT_THREADS, 3) k_ft_tile(S2PParams p) {
-    extern __shared__ __align__(16) unsigned char ft_smem[];
-    u32 (*s_line)[256] = (u32 (*)[256])(ft_smem + FT_OFF_LINE);       // line heads, one column of 32-bit words per thread; text stage later
-    LineRec *s_rec = (LineRec *)(ft_smem + FT_OFF_REC);               // this round's records; the newline lists before the first round
-    u16 *s_own = (u16 *)(ft_smem + FT_OFF_REC);
-    u16 *s_halo = s_own + FT_WARPS * FT_WCAP;
-    u32 *s_start = (u32 *)(ft_smem + FT_OFF_START);                   // line starts relative to ebase, ascending
-    u64 *s_A = (u64 *)(ft_smem + FT_OFF_A);
-    u8 *s_meta = (u8 *)(ft_smem + FT_OFF_META);
-    u32 *s_misc = (u32 *)(ft_smem + FT_OFF_MISC);
+// Well-formed lines only (single tabs between the first six fields, nothing else below 0x21 in front of them, digits where
+// numbers belong, RNAME <= 8 bytes); anything else returns false and goes through the generic byte parser, so the result is
+// identical by construction.  m0..m3: bit j set iff byte j of the line is below 0x21 (the first 112 - s bytes).
+__device__ __forceinline__ bool fs_parse_fast(const S2PParams &p, const ColFetch &f, const u32 s, u32 m0, u32 m1, u32 m2, u32 m3,
+                                              const u64 a, FtRec &rec, u32 &meta, u32 &t0_out) {
+    const u32 t0 = pop_lowest128(m0, m1, m2, m3), t1 = pop_lowest128(m0, m1, m2, m3), t2 = pop_lowest128(m0, m1, m2, m3);
+    const u32 t3 = pop_lowest128(m0, m1, m2, m3), t4 = pop_lowest128(m0, m1, m2, m3), t5 = pop_lowest128(m0, m1, m2, m3);
+    if (t5 >= 112u - s) return false;                                 // six separators inside the bytes we looked at
+    if (t0 == 0 || t1 == t0 + 1 || t2 == t1 + 1 || t3 == t2 + 1 || t4 == t3 + 1 || t5 == t4 + 1) return false;
+    if (f.byter(s + t0) != '\t' || f.byter(s + t1) != '\t' || f.byter(s + t2) != '\t' || f.byter(s + t3) != '\t' || f.byter(s + t4) != '\t' ||
+        f.byter(s + t5) != '\t') return false;
+    if (f.byter(s) == '@') return false;
+    const u32 l_flag = t1 - t0 - 1, l_name = t2 - t1 - 1, l_pos = t3 - t2 - 1, l_mapq = t4 - t3 - 1;
+    if (l_flag > 5 || l_name > 8 || l_pos > 10 || l_mapq > 3) return false;
+    bool ok = true;
+    const u32 flag = fs_dec_field(f, s + t0 + 1, l_flag, ok);
+    const u32 pos = fs_dec_field(f, s + t2 + 1, l_pos, ok);
+    const u32 mapq = fs_dec_field(f, s + t3 + 1, l_mapq, ok);
+    if (!ok) return false;
+    t0_out = t0;
+    meta = 0;
+    if (mapq < (u32)p.min_mapq || (flag & 0x700u)) return true;       // pairutil.h:157-161
+    meta = LM_KEEP;
+    // RNAME: FNV-1a over its bytes, same as the byte loop
+    u32 nlo, nhi;
+    f.f8(s + t1 + 1, nlo, nhi);
+    u64 name8 = (u64)nlo | ((u64)nhi << 32);
+    if (l_name < 8) name8 &= (1ull << (8 * l_name)) - 1;
+    u64 h = 0xCBF29CE484222325ull;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if ((u32)k < l_name) h = hash_step(h, (int)((name8 >> (8 * k)) & 0xFF));
+    // CIGAR walk (pairutil.h:63-126), 8 characters per fetch
+    u32 val = 0, idx = 0, leftClip = 0, rightClip = 0, mappable = 0;
+    u32 cur = pos, right0 = 0, left1 = 0, right1 = 0, last_right = 0;
+    bool err = false;
+    const u32 l_cig = t5 - t4 - 1;
+    u32 xlo = 0, xhi = 0;
+    for (u32 k = 0; k < l_cig; ++k) {
+        if ((k & 7u) == 0) f.f8(s + t4 + 1 + k, xlo, xhi);
+        const u32 c = xlo & 0xFFu; xlo = __funnelshift_r(xlo, xhi, 8); xhi >>= 8;
+        const u32 d = c - '0';
+        if (d <= 9u) { val = val * 10u + d; continue; }
+        if (c == 'H' || c == 'S') {
+            if (k + 1 == l_cig) rightClip = val;
+            else if (idx == 0) leftClip = val;
+            else err = true;
+        } else if (c == 'M' || c == 'D') {
+            if (c == 'M') mappable += val;
+            cur += val; last_right = cur - 1;
+            if (idx == 0) right0 = last_right; else if (idx == 1) right1 = last_right;
+        } else if (c == 'N') {
+            cur += val; ++idx; last_right = 0;
+            if (idx == 1) left1 = cur;
+        } else if (c != 'I') err = true;
+        val = 0;
+    }
+    rec.pos = pos; rec.right0 = right0; rec.left1 = left1; rec.right1 = right1;
+    rec.leftClip = leftClip; rec.rightClip = rightClip; rec.mappable = mappable;
+    rec.flag = (u16)flag; rec.qname_len = (u16)t0;
+    rec.chr_slot = (u16)chr_lookup_insert(p, h, name8, p.buf, a + t1 + 1, l_name);
+    const u32 segCnt = idx + 1;
+    if (last_right == 0) err = true;
+    rec.segCnt = err ? 0 : (u8)(segCnt > 2 ? 3 : segCnt);
+    rec.qname_off = 0;
+    return true;
+}
+// the generic parser, out of line, into a shared-memory record
+static __device__ __noinline__ u32 fs_parse_slow(const S2PParams &p, u64 a, bool has_prev, u64 pa, FtRec *out) {
+    LineRec r;
+    const u32 meta = parse_line_slow_abs(p, a, has_prev, pa, r);
+    if (meta & LM_KEEP) {
+        out->pos = r.pos; out->right0 = r.right0; out->left1 = r.left1; out->right1 = r.right1; out->leftClip = r.leftClip; out->rightClip = r.rightClip;
+        out->mappable = r.mappable; out->flag = r.flag; out->qname_len = r.qname_len; out->chr_slot = r.chr_slot; out->segCnt = r.segCnt; out->qname_off = r.qname_off;
+    }
+    return meta;
+}
+
+// ---------------------------------------------------------------------------------------------- lean text writer
+// Bytes are collected in a 64-bit accumulator and stored as aligned 32-bit words; the first and last word of a line are
+// shared with the neighbouring lines (written by other lanes), so their bytes go out one by one.
+struct TextW { u32 *w; u32 lo, hi, fill, skip; };
+__device__ __forceinline__ void tw_init(TextW &t, char *dst) {
+    t.w = (u32 *)((size_t)dst & ~(size_t)3); t.skip = (u32)((size_t)dst & 3u); t.fill = t.skip; t.lo = t.hi = 0;
+}
+__device__ __forceinline__ void tw_flush(TextW &t) {
+    if (t.skip) { unsigned char *b = (unsigned char *)t.w; for (u32 k = t.skip; k < 4u; ++k) b[k] = (unsigned char)(t.lo >> (8 * k)); t.skip = 0; }
+    else *t.w = t.lo;
+    ++t.w; t.lo = t.hi; t.hi = 0; t.fill -= 4u;
+}
+__device__ __forceinline__ void tw_put(TextW &t, u32 x, u32 n) {     // the low n (1..4) bytes of x; the bytes above them must be zero
+    const u32 sh = t.fill * 8u;
+    t.lo |= x << sh; t.hi |= __funnelshift_l(x, 0u, sh);
+    t.fill += n;
+    if (t.fill >= 4u) tw_flush(t);
+}
+__device__ __forceinline__ void tw_end(TextW &t) {
+    unsigned char *b = (unsigned char *)t.w;
+    for (u32 k = t.skip; k < t.fill; ++k) b[k] = (unsigned char)(t.lo >> (8 * k));
+}
+// four decimal digits of v (< 10000) as characters, most significant in the lowest byte
+__device__ __forceinline__ u32 dig4(u32 v) {
+    const u32 hi2 = (v * 5243u) >> 19, lo2 = v - hi2 * 100u;           // v / 100 for v < 10000
+    const u32 a = (hi2 * 103u) >> 10, b = (lo2 * 103u) >> 10;          // x / 10 for x < 100
+    return (a | ((hi2 - a * 10u) << 8) | (b << 16) | ((lo2 - b * 10u) << 24)) + 0x30303030u;
+}
+__device__ __forceinline__ void tw_put_uint(TextW &t, u32 v) {
+    const u32 q1 = v / 10000u, r1 = v - q1 * 10000u;
+    if (q1 == 0) {
+        const u32 n = v >= 1000u ? 4u : v >= 100u ? 3u : v >= 10u ? 2u : 1u;
+        tw_put(t, dig4(r1) >> (8u * (4u - n)), n);
+        return;
+    }
+    const u32 q2 = q1 / 10000u, r2 = q1 - q2 * 10000u;
+    if (q2 == 0) {
+        const u32 n = q1 >= 1000u ? 4u : q1 >= 100u ? 3u : q1 >= 10u ? 2u : 1u;
+        tw_put(t, dig4(r2) >> (8u * (4u - n)), n);
+    } else {
+        const u32 n = q2 >= 10u ? 2u : 1u;
+        tw_put(t, dig4(q2) >> (8u * (4u - n)), n);
+        tw_put(t, dig4(r2), 4u);
+    }
+    tw_put(t, dig4(r1), 4u);
+}
+__device__ __forceinline__ void tw_put_name_tab(TextW &t, const ChrSlot *c) {   // chromosome name followed by a tab
+    const u32 l = c->len;
+    if (l < 8) {
+        const u64 x = c->name8 | ((u64)'\t' << (8 * l));
+        const u32 n = l + 1;
+        if (n <= 4) tw_put(t, (u32)x, n);
+        else { tw_put(t, (u32)x, 4u); tw_put(t, (u32)(x >> 32), n - 4u); }
+        return;
+    }
+    if (l == 8) { tw_put(t, (u32)c->name8, 4u); tw_put(t, (u32)(c->name8 >> 32), 4u); }
+    else for (u32 i = 0; i < l; ++i) tw_put(t, (u32)(unsigned char)c->name[i], 1u);
+    tw_put(t, '\t', 1u);
+}
+// rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347); the read id comes back out of L2
+__device__ __forceinline__ void fs_write_pair_line(const char *buf, u64 rid_abs, u32 rid_len, const ChrSlot *ca, const ChrSlot *cb,
+                                                   u32 posA, u32 posB, u32 strands, char *out) {
+    TextW t; tw_init(t, out);
+    const u64 a8 = rid_abs & ~(u64)7; const u32 sh = (u32)(rid_abs & 7u) * 8u;
+    const u64 *src = (const u64 *)(buf + a8);
+    u64 cur = __ldg(src);
+    for (u32 k = 0; k < rid_len; k += 8) {
+        const u64 nxt = __ldg(src + (k >> 3) + 1);
+        const u64 x = sh ? (cur >> sh) | (nxt << (64u - sh)) : cur;
+        cur = nxt;
+        const u32 n = rid_len - k < 8u ? rid_len - k : 8u;
+        const u32 xl = (u32)x, xh = (u32)(x >> 32);
+        if (n >= 4u) { tw_put(t, xl, 4u); if (n > 4u) tw_put(t, n == 8u ? xh : xh & ((1u << (8u * (n - 4u))) - 1u), n - 4u); }
+        else tw_put(t, xl & ((1u << (8u * n)) - 1u), n);
+    }
+    tw_put(t, '\t', 1u);
+    tw_put_name_tab(t, ca);
+    tw_put_uint(t, posA);
+    tw_put(t, '\t', 1u);
+    tw_put_name_tab(t, cb);
+    tw_put_uint(t, posB);
+    // \t s1 \t s2 \n
+    tw_put(t, (u32)'\t' | ((strands & 1u) ? (u32)'-' << 8 : (u32)'+' << 8) | ((u32)'\t' << 16) | ((strands & 2u) ? (u32)'-' << 24 : (u32)'+' << 24), 4u);
+    tw_put(t, '\n', 1u);
+    tw_end(t);
+}
+
+// ---------------------------------------------------------------------------------------------- the strip kernel
+static __global__ void __launch_bounds__(FS_THREADS, 3) k_ft_strip(S2PParams p) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    unsigned char *wb = fs_smem + wid * FS_WARP_SMEM;
+    u32 *col = (u32 *)wb + lane;                                      // this lane's column of line-head words (word w at col[32 w])
+    FtRec *recs = (FtRec *)(wb + FS_OFF_REC);
+    u32 *ring = (u32 *)(wb + FS_OFF_RING);
+    u8 *metas = (u8 *)(wb + FS_OFF_META);
+    u32 *s_cnt = (u32 *)(fs_smem + FS_WARPS * FS_WARP_SMEM);
     WinState *st = p.st;
     if (st->halt || st->path_old) return;
     const u64 ws = st->ws, we = st->we;
     if (we <= ws) return;
-    const u64 tile = ws / FT_TILE + blockIdx.x;
-    if (tile > (we - 1) / FT_TILE || blockIdx.x >= p.n_tiles_cap) return;
     const u64 limit = st->total;
-    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const u64 tbase = tile * FT_TILE, tend = tbase + FT_TILE;
-    const long long ebase = (long long)tbase - (long long)FT_HALO;    // positions below are relative to ebase
-    if (tid < 128) s_misc[tid] = 0;
+    const u64 strip0 = ws / FT_TILE;
+    const u32 n_strips = (u32)((we - 1) / FT_TILE - strip0 + 1);
+    if (tid < 16) s_cnt[tid] = 0;
 #pragma unroll
-    for (int j = 28; j < LF_WORDS; ++j) s_line[j][tid] = 0;           // pad words behind the 112 staged bytes
+    for (int j = 28; j < 32; ++j) col[32 * j] = 0;                    // pad words behind the 112 staged bytes
     __syncthreads();
+    const S2PParams &ps = *p.self;                                     // what out-of-line callees get
+    const u32 ltmask = (1u << lane) - 1u;
+    u64 last_end = 0;
 
-    // ---- 1. newline scan: own 16 KiB chunk, then one halo row per warp (warps 0-3 before the tile, 4-7 behind it)
-    {
-        const u32 n_own = ft_scan_rows<8>(p.buf, (long long)tbase + (long long)wid * FT_CHUNK, FT_CHUNK / 512u, ws, we, s_own + wid * FT_WCAP, FT_WCAP, lane);
-        const long long hb = wid < 4 ? ebase + (long long)wid * 512 : (long long)tend + (long long)(wid - 4) * 512;
-        const u32 n_halo = ft_scan_rows<1>(p.buf, hb, 1u, ws, we, s_halo + wid * FT_HCAP, FT_HCAP, lane);
-        if (lane == 0) {
-            s_misc[FM_SEG + 4 + wid] = n_own;
-            s_misc[FM_SEG + (wid < 4 ? wid : 8 + wid)] = n_halo;
-            if (n_own > FT_WCAP || n_halo > FT_HCAP) s_misc[FM_OVF] = 1;
+    while (true) {
+        u32 sl = 0;
+        if (lane == 0) sl = atomicAdd(&st->tickets[0], 1u);
+        sl = __shfl_sync(0xFFFFFFFFu, sl, 0);
+        if (sl >= n_strips || sl >= p.n_tiles_cap) break;
+        if (*(volatile u32 *)&st->path_old) break;
+        const u64 sbase = (strip0 + sl) * FT_TILE, send = sbase + FT_TILE;
+        const long long ebase = (long long)sbase - (long long)FS_HALO; // line starts below are relative to ebase
+        const bool has_initial = ebase <= (long long)ws;                // the window's first line starts inside the scanned range
+        char *sc_text = p.ft_text + (size_t)sl * FT_TEXT_CAP;
+        mk_pair *sc_pairs = p.ft_pairs + (size_t)sl * FT_LMAX;
+        uint4 *sc_sam = p.ft_sam + (size_t)sl * FT_LMAX;
+        u32 n_known = 0;
+        if (has_initial) { if (lane == 0) ring[0] = (u32)((long long)ws - ebase); n_known = 1; }
+        // the four rows in front of the strip: only the last lines matter (look-back of the strip's first group)
+        n_known = fs_scan_push<4>(p.buf, ebase, 4u, 0u, ws, we, ring, n_known, lane);
+        if (n_known > FS_RING - 64u) { if (lane == 0) atomicOr(&st->path_old, 1u); break; }
+        const u32 n_main0 = n_known;                                   // lines from here on start behind a newline of this strip
+        const u32 n_drop = n_known > 3u ? n_known - 3u : 0u;           // lines below are never parsed
+        u32 n_parsed = n_drop, n_res = n_drop, n_main1 = n_known;
+        u32 run_g = 0, run_e = 0, run_t = 0, run_s = 0, run_n = 0;     // strip totals so far (warp-uniform)
+        u32 stage = 0;                                                  // 0..31 main batches of 8 rows, 32 the rows behind the strip, 33 done
+        bool ovf = false;
+        while (true) {
+            const u32 pending = n_known - n_parsed;                    // starts not parsed yet (the last one has no known end)
+            if (stage <= 32u && pending <= 32u) {                      // not enough for a full round of 32 complete lines: scan on
+                if (stage < 32u) {
+                    n_known = fs_scan_push<8>(p.buf, (long long)sbase + (long long)stage * 4096, 8u, FS_HALO + stage * 4096u, ws, we, ring, n_known, lane);
+                    n_main1 = n_known;
+                } else n_known = fs_scan_push<4>(p.buf, (long long)send, 4u, FS_HALO + FT_TILE, ws, we, ring, n_known, lane);
+                ++stage;
+                if (n_known - n_parsed > FS_RING - 64u) { ovf = true; break; }
+                if (stage == 32u && n_main1 > n_main0) {               // end of the strip's last complete line (a window without kept records ends there)
+                    __syncwarp();
+                    const u64 e = (u64)(ebase + (long long)ring[(n_main1 - 1u) & (FS_RING - 1u)]);
+                    if (e > last_end) last_end = e;
+                }
+                continue;
+            }
+            const bool final = stage > 32u;
+            const u32 cnt = pending > 32u ? 32u : (pending ? pending - 1u : 0u);
+            __syncwarp();
+            // ---- parse `cnt` lines, one per lane.  A start is a complete line iff it has a successor in the ring.
+            if (cnt) {
+                const u32 line = n_parsed + lane;
+                const bool act = lane < cnt;
+                u64 a = 0, A = ~(u64)0;
+                u32 m0 = 0, m1 = 0, m2 = 0, m3 = 0, s = 0;
+                if (act) {
+                    a = (u64)(ebase + (long long)ring[line & (FS_RING - 1u)]);
+                    if (a + 144 <= limit) {
+                        A = a & ~(u64)15; s = (u32)(a - A);
+                        const uint4 *src = (const uint4 *)(p.buf + A);
+                        uint4 w[7];
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) w[j] = __ldg(src + j);
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) { col[32 * (4 * j)] = w[j].x; col[32 * (4 * j + 1)] = w[j].y; col[32 * (4 * j + 2)] = w[j].z; col[32 * (4 * j + 3)] = w[j].w; }
+                        m0 = lt21_mask16(w[0]) | (lt21_mask16(w[1]) << 16); m1 = lt21_mask16(w[2]) | (lt21_mask16(w[3]) << 16);
+                        m2 = lt21_mask16(w[4]) | (lt21_mask16(w[5]) << 16); m3 = lt21_mask16(w[6]);
+                        if (s) { m0 = __funnelshift_r(m0, m1, s); m1 = __funnelshift_r(m1, m2, s); m2 = __funnelshift_r(m2, m3, s); m3 >>= s; }
+                    }
+                }
+                const u64 An = __shfl_up_sync(0xFFFFFFFFu, A, 1);       // the previous line's staged base (lane - 1)
+                __syncwarp();
+                if (act) {
+                    const bool has_prev = line > 0;
+                    const u64 pa = has_prev ? (u64)(ebase + (long long)ring[(line - 1u) & (FS_RING - 1u)]) : 0;
+                    FtRec &rec = recs[line & (FS_RECS - 1u)];
+                    ColFetch f; f.col = col;
+                    u32 meta = 0, t0 = 0;
+                    if (A != ~(u64)0 && fs_parse_fast(p, f, s, m0, m1, m2, m3, a, rec, meta, t0)) {
+                        if (has_prev) {
+                            bool eq;
+                            if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_abs(ps, a, pa);   // operator>> skips leading blanks
+                            else if (lane > 0 && An != ~(u64)0 && (u32)(pa - An) + t0 + 1 <= 112) {        // inside the neighbour's staged bytes
+                                ColFetch fp; fp.col = col - 1;
+                                const u32 sp = (u32)(pa - An);
+                                eq = true;
+                                for (u32 k = 0; k < t0 && eq; k += 8) {
+                                    u32 xl, xh, yl, yh;
+                                    f.f8(s + k, xl, xh); fp.f8(sp + k, yl, yh);
+                                    xl ^= yl; xh ^= yh;
+                                    const u32 r = t0 - k;
+                                    if (r < 8u) { if (r <= 4u) { xh = 0; if (r < 4u) xl &= (1u << (8u * r)) - 1u; } else xh &= (1u << (8u * (r - 4u))) - 1u; }
+                                    eq = (xl | xh) == 0;
+                                }
+                                eq = eq && is_ws((int)fp.byter(sp + t0));
+                            } else {
+                                GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
+                                eq = qname_eq_fetch(gf, a, pa, t0);
+                            }
+                            if (eq) meta |= LM_EQ;
+                        }
+                    } else meta = fs_parse_slow(ps, a, has_prev, pa, &rec);
+                    if (!has_prev && !has_initial) meta |= LM_EQ_UNK;   // the line before the first one we know of
+                    metas[line & (FS_RECS - 1u)] = (u8)meta;
+                }
+                n_parsed += cnt;
+                __syncwarp();
+            }
+            // ---- resolve the heads whose look-ahead is parsed, 32 lines per step
+            const bool last = final && (n_known - n_parsed <= 1u);
+            const u32 R = last ? n_known : (n_parsed > FS_LOOKAHEAD ? n_parsed - FS_LOOKAHEAD : 0u);
+            while (n_res < R && !ovf) {
+                const u32 line = n_res + lane;
+                const u32 step = R - n_res < 32u ? R - n_res : 32u;
+                bool proc = false, emit = false, use_slow = false;
+                Resolved rs; rs.status = ST_NONE; rs.have = false; rs.p1 = rs.p2 = 0; rs.sA = rs.sB = 0; rs.strands = 0;
+                u32 text_len = 0, sam_len = 0, n_mem = 0, rid_len = 0, rid_off = 0;
+                u64 a = 0;
+                if (lane < step) {
+                    const u32 rel = ring[line & (FS_RING - 1u)];
+                    a = (u64)(ebase + (long long)rel);
+                    const bool own = rel >= FS_HALO && rel < FS_HALO + FT_TILE && a < we;
+                    const bool parsed = line < n_parsed;
+                    u32 meta = parsed ? metas[line & (FS_RECS - 1u)] : 0u;
+                    bool kept = own && (meta & LM_KEEP);
+                    if (own && !parsed) {                              // the last start we know: a line only if it ends before `we`
+                        use_slow = true;
+                        kept = false;
+                        if (ft_find_nl(p.buf, a, we) != FT_NONE) {
+                            FtRec tmp;
+                            const bool has_prev = line > 0;
+                            meta = fs_parse_slow(ps, a, has_prev, has_prev ? (u64)(ebase + (long long)ring[(line - 1u) & (FS_RING - 1u)]) : 0, &tmp);
+                            if (!has_prev && !has_initial) meta |= LM_EQ_UNK;
+                            kept = (meta & LM_KEEP) != 0;
+                        }
+                    }
+                    if (kept) {
+                        // head?  (pairutil.h:163-173: currId != lastId among kept records)
+                        int head = (meta & LM_EQ_UNK) ? 2 : -1;        // 0 no, 1 yes, 2 walk the bytes
+                        {
+                            bool chain = (meta & LM_EQ) != 0;
+                            const u32 low = n_parsed > FS_RECS ? max(n_drop, n_parsed - FS_RECS) : n_drop;   // oldest line whose meta is still held
+                            u32 j = line;
+                            while (head < 0 && j > low) {
+                                --j;
+                                const u32 mj = metas[j & (FS_RECS - 1u)];
+                                if (mj & LM_KEEP) {
+                                    if (chain) head = 0;
+                                    else if (j + 1 == line) head = 1;
+                                    else head = qname_equal_abs(ps, a, (u64)(ebase + (long long)ring[j & (FS_RING - 1u)])) ? 0 : 1;
+                                    break;
+                                }
+                                if (mj & LM_EQ_UNK) { head = 2; break; }
+                                chain = chain && (mj & LM_EQ);
+                            }
+                            if (head < 0) head = (low == 0 && has_initial) ? 1 : 2;   // nothing kept before it in the window / out of sight
+                            if (head == 2) head = ft_head_slow(ps, ws, a) ? 1 : 0;
+                        }
+                        if (head) {
+                            u32 f0 = line, f1 = line, r1a = line, r1b = line, r2a = line, r2b = line;
+                            u32 n = 0, n1 = 0, n2 = 0;
+                            if (!use_slow) {
+                                u32 k = line;
+                                while (true) {
+                                    const u32 fl = recs[k & (FS_RECS - 1u)].flag;
+                                    if (n == 0) f0 = k; else if (n == 1) f1 = k;
+                                    ++n;
+                                    if (fl & 64u) { if (n1 == 0) r1a = k; else if (n1 == 1) r1b = k; ++n1; }
+                                    else if (fl & 128u) { if (n2 == 0) r2a = k; else if (n2 == 1) r2b = k; ++n2; }
+                                    sam_len += ring[(k + 1u) & (FS_RING - 1u)] - ring[k & (FS_RING - 1u)];
+                                    u32 q = k + 1; bool chain = true; u32 mq = 0;
+                                    while (q < n_parsed) { mq = metas[q & (FS_RECS - 1u)]; chain = chain && (mq & LM_EQ); if (mq & LM_KEEP) break; ++q; }
+                                    if (q >= n_parsed) { use_slow = true; break; }
+                                    const bool same = chain ? true : (q == k + 1 ? false :
+                                        qname_equal_abs(ps, (u64)(ebase + (long long)ring[q & (FS_RING - 1u)]), (u64)(ebase + (long long)ring[k & (FS_RING - 1u)])));
+                                    if (!same) break;
+                                    k = q;
+                                }
+                                n_mem = n;
+                            }
+                            if (use_slow) {
+                                FtGroup g;
+                                ft_group_slow(ps, ws, we, a, g, nullptr, 0, 0);
+                                if (g.off_end) {                       // the window's last group: carried to the next window (or dropped at EOF)
+                                    st->ft_carry_pos = a; st->ft_carry_tile = sl;
+                                    st->ft_carry_nl = line >= n_main0 ? line - n_main0 + 1u : 0u;   // newlines of this strip before the line
+                                } else { proc = true; rs = g.r; sam_len = g.sam_len; n_mem = g.n_members; rid_len = g.qname_len; rid_off = g.qname_off; }
+                            } else {
+                                proc = true;
+                                rs = resolve_group(p, n, n1, n2, &recs[f0 & (FS_RECS - 1u)], &recs[f1 & (FS_RECS - 1u)], &recs[r1a & (FS_RECS - 1u)],
+                                                   &recs[r1b & (FS_RECS - 1u)], &recs[r2a & (FS_RECS - 1u)], &recs[r2b & (FS_RECS - 1u)]);
+                                rid_len = recs[line & (FS_RECS - 1u)].qname_len; rid_off = recs[line & (FS_RECS - 1u)].qname_off;
+                            }
+                            if (proc) {
+                                if (rs.status != ST_NONE) atomicAdd(&s_cnt[rs.status], 1u);
+                                if (rs.have && rs.status != ST_SELFCIRCLE) {
+                                    emit = true;
+                                    text_len = rid_len + p.chr[rs.sA].len + p.chr[rs.sB].len + dec_digits(rs.p1) + dec_digits(rs.p2) + 9u;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (!emit || !p.write_sam) { sam_len = 0; n_mem = 0; }   // (also the partial sums of a walk that went to the byte level)
+                // -- offsets inside the step
+                const u32 vT = p.emit_text ? text_len : 0u;
+                const u32 bal_p = __ballot_sync(0xFFFFFFFFu, proc), bal_e = __ballot_sync(0xFFFFFFFFu, emit);
+                const u32 iT = warp_incl_scan(vT, (int)lane);
+                const u32 tT = __shfl_sync(0xFFFFFFFFu, iT, 31), bT = iT - vT;
+                u32 bS = 0, bE = 0, tS = 0, tE = 0;
+                if (p.write_sam) {
+                    const u32 iS = warp_incl_scan(sam_len, (int)lane), iE = warp_incl_scan(n_mem, (int)lane);
+                    tS = __shfl_sync(0xFFFFFFFFu, iS, 31); tE = __shfl_sync(0xFFFFFFFFu, iE, 31); bS = iS - sam_len; bE = iE - n_mem;
+                }
+                const u32 bG = __popc(bal_p & ltmask), bP = __popc(bal_e & ltmask), tG = __popc(bal_p), tP = __popc(bal_e);
+                if (run_t + tT > FT_TEXT_CAP || run_n + tE > FT_LMAX || run_e + tP > FT_LMAX) { ovf = true; break; }
+                const bool staged = tT <= FS_STAGE;
+                const u32 phase = (u32)((size_t)(sc_text + run_t) & 15u);
+                char *s_stage = (char *)wb;                            // the line-head columns are dead until the next parse round
+                if (proc) {
+                    if (rs.status == ST_SELFCIRCLE) {                  // (strip, group index inside the strip): k_ft_prefix makes it global
+                        const u32 slot = atomicAdd(&st->sc_count, 1u);
+                        if (slot < p.sc_cap) p.sc_list[slot] = ((u64)sl << 32) | (u64)(run_g + bG); else atomicOr(&st->err, S2P_ERR_SCLIST);
+                    }
+                    if (emit) {
+                        const ChrSlot *ca = &p.chr[rs.sA], *cb = &p.chr[rs.sB];
+                        if (p.emit_packed) {
+                            uint4 r;
+                            r.x = rs.p1; r.y = rs.p2; r.z = (u32)(u16)ca->id | ((u32)(u16)cb->id << 16);
+                            r.w = (u32)rs.strands | ((u32)(rs.status - ST_TRANS) << 8) | ((u32)p.lane << 16);
+                            ((uint4 *)sc_pairs)[run_e + bP] = r;
+                        }
+                        if (p.emit_text) fs_write_pair_line(p.buf, a + rid_off, rid_len, ca, cb, rs.p1, rs.p2, rs.strands,
+                                                            staged ? s_stage + phase + bT : sc_text + run_t + bT);
+                        if (p.write_sam) {                             // one copy entry per kept line of the group
+                            uint4 *ent = sc_sam + run_n + bE;
+                            if (use_slow) { FtGroup g; ft_group_slow(ps, ws, we, a, g, ent, n_mem, run_s + bS); }
+                            else {
+                                u32 k = line, d = run_s + bS, c = 0;
+                                while (true) {
+                                    const u32 r0 = ring[k & (FS_RING - 1u)], len = ring[(k + 1u) & (FS_RING - 1u)] - r0;
+                                    ent[c++] = make_uint4((u32)((u64)(ebase + (long long)r0) - ws), len, d, 0u);
+                                    d += len;
+                                    if (c == n_mem) break;
+                                    ++k; while (!(metas[k & (FS_RECS - 1u)] & LM_KEEP)) ++k;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (p.emit_text && tT && staged) {
+                    __syncwarp();
+                    char *dst = sc_text + run_t;
+                    const u32 head = phase ? (16u - phase < tT ? 16u - phase : tT) : 0u;
+                    if (lane < head) dst[lane] = s_stage[phase + lane];
+                    const u32 body = (tT - head) >> 4;
+                    for (u32 w = lane; w < body; w += 32u)
+                        *(uint4 *)(dst + head + ((size_t)w << 4)) = *(const uint4 *)(s_stage + phase + head + (w << 4));
+                    const u32 tail0 = head + (body << 4);
+                    if (tail0 + lane < tT) dst[tail0 + lane] = s_stage[phase + tail0 + lane];
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 28; j < 32; ++j) col[32 * j] = 0;     // the stage covered the pad words of the columns
+                }
+                run_g += tG; run_e += tP; run_t += tT; run_s += tS; run_n += tE;
+                n_res += step;
+                __syncwarp();
+            }
+            if (last || ovf) break;
+        }
+        if (ovf) { if (lane == 0) atomicOr(&st->path_old, 1u); break; }
+        if (lane == 0) {                                               // (groups | emitted << 16, text bytes, passthrough bytes, newlines of the strip)
+            p.ft_tot[sl] = make_uint4(run_g | (run_e << 16), run_t, run_s, n_main1 - n_main0);
+            p.ft_nent[sl] = run_n;
         }
     }
     __syncthreads();
-    // ---- 2. dense, ascending list of line starts (a start at `we` is kept as the end marker of the last complete line)
-    const u32 has_initial = ebase <= (long long)ws ? 1u : 0u;           // the window's first line starts at ws
-    u32 Ltot, n_own_nl = 0;
-    {
-        u32 pre[17]; pre[0] = has_initial;
-#pragma unroll
-        for (int s = 0; s < 16; ++s) { const u32 c = s_misc[FM_SEG + s]; pre[s + 1] = pre[s] + c; if (s >= 4 && s < 12) n_own_nl += c; }
-        Ltot = pre[16];
-        if (Ltot > FT_LMAX) { if (tid == 0) s_misc[FM_OVF] = 1; }
-        else if (!s_misc[FM_OVF]) {
-            if (tid == 0 && has_initial) s_start[0] = (u32)((long long)ws - ebase);
-            // every warp copies the two lists it produced
-            const u32 so = 4 + wid, sh = wid < 4 ? wid : 8 + wid;
-            const u32 bo = FT_HALO + wid * FT_CHUNK, bh = wid < 4 ? wid * 512u : FT_HALO + FT_TILE + (wid - 4) * 512u;
-            u32 po = 0, ph = 0, co = 0, ch = 0;
-#pragma unroll
-            for (int s = 0; s < 16; ++s) { if ((u32)s == so) { po = pre[s]; co = pre[s + 1] - pre[s]; } if ((u32)s == sh) { ph = pre[s]; ch = pre[s + 1] - pre[s]; } }
-            for (u32 i = lane; i < co; i += 32) s_start[po + i] = bo + s_own[wid * FT_WCAP + i] + 1u;
-            for (u32 i = lane; i < ch; i += 32) s_start[ph + i] = bh + s_halo[wid * FT_HCAP + i] + 1u;
-        }
-        if (tid == 0 && n_own_nl) {                                    // end of the window's last complete line (a window without kept records)
-            u32 s = 11; while (s_misc[FM_SEG + s] == 0) --s;
-            const u64 x = tbase + (u64)(s - 4) * FT_CHUNK + s_own[(s - 4) * FT_WCAP + (s_misc[FM_SEG + s] <= FT_WCAP ? s_misc[FM_SEG + s] - 1 : 0)];
-            if (!s_misc[FM_OVF]) atomicMax((unsigned long long *)&st->ft_last_end, (unsigned long long)(x + 1));
-        }
-    }
-    __syncthreads();
-    if (s_misc[FM_OVF]) { if (tid == 0) atomicOr(&st->path_old, 1u); return; }
-    // own lines = starts in [tbase, tend): dense indices [j0, j1)
-    u32 j0, j1;
-    {
-        u32 lo = 0, hi = Ltot;
-        while (lo < hi) { const u32 m = (lo + hi) >> 1; if (s_start[m] < FT_HALO) lo = m + 1; else hi = m; }
-        j0 = lo; hi = Ltot;
-        while (lo < hi) { const u32 m = (lo + hi) >> 1; if (s_start[m] < FT_HALO + FT_TILE) lo = m + 1; else hi = m; }
-        j1 = lo;
-    }
-    const u32 tl = blockIdx.x;                                         // window-local tile index
-    char *sc_text = p.ft_text + (size_t)tl * FT_TEXT_CAP;
-    mk_pair *sc_pairs = p.ft_pairs + (size_t)tl * FT_LMAX;
-    uint4 *sc_sam = p.ft_sam + (size_t)tl * FT_LMAX;
-    __syncthreads();                                                   // the newline lists (aliasing s_rec) are dead from here
-
-    // ---- 3. rounds: 256 lines parsed (one per thread), heads in [lo, hi) resolved and emitted
-    u32 base = j0 >= FT_LOOKBACK ? j0 - FT_LOOKBACK : 0u;
-    u32 lo = j0;
-    while (lo < j1) {
-        const bool last_round = base + 256u >= Ltot;
-        const u32 hi = last_round ? j1 : min(j1, base + 256u - FT_LOOKAHEAD);
-        const u32 li = base + tid;
-        // -- parse.  A dense entry is a complete line iff it has a successor; the last entry is only known to be a line start.
-        const bool parsed = li + 1 < Ltot;
-        u64 a = 0;
-        LineFetch lf; lf.buf = p.buf; lf.col = &s_line[0][tid]; lf.A = 0;
-        bool staged = false;
-        if (parsed) {
-            a = (u64)(ebase + (long long)s_start[li]);
-            lf.A = a & ~(u64)15;
-            staged = a + 144 <= limit;
-            if (staged) {
-                const uint4 *src = (const uint4 *)(p.buf + lf.A);
-                uint4 w[7];
-#pragma unroll
-                for (int j = 0; j < 7; ++j) w[j] = __ldg(src + j);
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    s_line[4 * j][tid] = w[j].x; s_line[4 * j + 1][tid] = w[j].y; s_line[4 * j + 2][tid] = w[j].z; s_line[4 * j + 3][tid] = w[j].w;
-                    lf.w[j] = w[j];
-                }
-            }
-        }
-        s_A[tid] = staged ? lf.A : ~(u64)0;
-        __syncthreads();
-        u32 meta = FT_M_END;
-        LineRec rec;
-        if (parsed) {
-            const bool has_prev = li > 0;
-            const u64 pa = has_prev ? (u64)(ebase + (long long)s_start[li - 1]) : 0;
-            FastTok tok;
-            meta = 0;
-            if (staged && parse_line_fast<LineFetch, false>(p, lf, a, limit, tok, rec, meta)) {
-                if (has_prev) {
-                    bool eq;
-                    if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_abs(p, a, pa);
-                    else if (tid > 0 && s_A[tid - 1] != ~(u64)0 && (u32)(pa - s_A[tid - 1]) + tok.t0 + 1 <= 112) {
-                        LineFetch lp; lp.buf = p.buf; lp.col = &s_line[0][tid - 1]; lp.A = s_A[tid - 1];
-                        const u32 so = (u32)(a - lf.A), sp = (u32)(pa - lp.A);
-                        eq = true;
-                        for (u32 k = 0; k < tok.t0 && eq; k += 8) {
-                            u64 x = fetch8r(lf, so + k), y = fetch8r(lp, sp + k);
-                            if (tok.t0 - k < 8) { const u64 m = (1ull << (8 * (tok.t0 - k))) - 1; x &= m; y &= m; }
-                            eq = x == y;
-                        }
-                        eq = eq && is_ws(lp.byter(sp + tok.t0));
-                    } else {
-                        GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
-                        eq = qname_eq_fetch(gf, a, pa, tok.t0);
-                    }
-                    if (eq) meta |= LM_EQ;
-                }
-            } else meta = parse_line_slow_abs(p, a, has_prev, pa, rec);
-            if (!has_prev && !has_initial) meta |= LM_EQ_UNK;          // the line before the first one we know of
-            if (meta & LM_KEEP) s_rec[tid] = rec;
-        }
-        s_meta[tid] = (u8)meta;
-        __syncthreads();
-
-        // -- group: is this line the head of a read group, and what does the group resolve to?
-        bool proc = false, emit = false, use_slow = false;
-        Resolved rs; rs.status = ST_NONE; rs.have = false; rs.p1 = rs.p2 = 0; rs.sA = rs.sB = 0; rs.strands = 0;
-        u32 text_len = 0, sam_len = 0, n_mem = 0, rid_len = 0, rid_off = 0;
-        if (li >= lo && li < hi) {
-            bool kept = (meta & LM_KEEP) != 0 && parsed;
-            if (!parsed && li < Ltot) {                                // the list's last entry: a line only if it ends before `we`
-                a = (u64)(ebase + (long long)s_start[li]);
-                if (a < we && ft_find_nl(p.buf, a, we) != FT_NONE) {
-                    const bool has_prev = li > 0;
-                    meta = parse_line_slow_abs(p, a, has_prev, has_prev ? (u64)(ebase + (long long)s_start[li - 1]) : 0, rec);
-                    if (!has_prev && !has_initial) meta |= LM_EQ_UNK;
-                    kept = (meta & LM_KEEP) != 0;
-                    use_slow = true;
-                }
-            }
-            if (kept) {
-                // head?  (pairutil.h:163-173: currId != lastId among kept records)
-                int head;                                              // 0 no, 1 yes, 2 walk the bytes
-                {
-                    bool chain = (meta & LM_EQ) != 0;
-                    head = (meta & LM_EQ_UNK) ? 2 : -1;
-                    int j = (int)tid - 1;
-                    while (head < 0 && j >= 0) {
-                        const u32 mj = s_meta[j];
-                        if (mj & LM_KEEP) break;
-                        if (mj & LM_EQ_UNK) { head = 2; break; }
-                        chain = chain && (mj & LM_EQ);
-                        --j;
-                    }
-                    if (head < 0) {
-                        if (j < 0) head = (base == 0 && has_initial) ? 1 : 2;
-                        else if (chain) head = 0;
-                        else if (j == (int)tid - 1) head = 1;
-                        else head = qname_equal_abs(p, a, (u64)(ebase + (long long)s_start[base + j])) ? 0 : 1;
-                    }
-                    if (head == 2) head = ft_head_slow(p, ws, a) ? 1 : 0;
-                }
-                if (head) {
-                    u32 first[2] = {tid, tid}, r1[2] = {tid, tid}, r2[2] = {tid, tid};
-                    u32 n = 0, n1 = 0, n2 = 0;
-                    if (!use_slow) {
-                        u32 k = tid;
-                        while (true) {
-                            const u32 fl = s_rec[k].flag;
-                            if (n < 2) first[n] = k;
-                            ++n;
-                            if (fl & 64u) { if (n1 < 2) r1[n1] = k; ++n1; } else if (fl & 128u) { if (n2 < 2) r2[n2] = k; ++n2; }
-                            sam_len += s_start[base + k + 1] - s_start[base + k];
-                            u32 q = k + 1; bool chain = true; u32 mq = FT_M_END;
-                            while (q < 256u) { mq = s_meta[q]; if (mq & FT_M_END) break; chain = chain && (mq & LM_EQ); if (mq & LM_KEEP) break; ++q; }
-                            if (q >= 256u || (mq & FT_M_END)) { use_slow = true; break; }
-                            const bool same = chain ? true : (q == k + 1 ? false :
-                                qname_equal_abs(p, (u64)(ebase + (long long)s_start[base + q]), (u64)(ebase + (long long)s_start[base + k])));
-                            if (!same) break;
-                            k = q;
-                        }
-                        n_mem = n;
-                    }
-                    if (use_slow) {
-                        FtGroup g;
-                        ft_group_slow(p, ws, we, a, g, nullptr, 0, 0);
-                        if (g.off_end) {                               // the window's last group: carried to the next window (or dropped at EOF)
-                            st->ft_carry_pos = a; st->ft_carry_tile = tl;
-                            u32 c = 0;                                 // newlines of this tile before the line
-                            for (u32 k = has_initial; k <= li; ++k) if (s_start[k] > FT_HALO) ++c;
-                            st->ft_carry_nl = c;
-                        } else { proc = true; rs = g.r; sam_len = g.sam_len; n_mem = g.n_members; }
-                    } else {
-                        proc = true;
-                        rs = resolve_group(p, n, n1, n2, &s_rec[first[0]], &s_rec[first[1]], &s_rec[r1[0]], &s_rec[r1[1]], &s_rec[r2[0]], &s_rec[r2[1]]);
-                    }
-                    if (proc) {
-                        rid_len = parsed ? s_rec[tid].qname_len : rec.qname_len;
-                        rid_off = parsed ? s_rec[tid].qname_off : rec.qname_off;
-                        if (rs.status != ST_NONE) atomicAdd(&s_misc[FM_CNT + rs.status], 1u);
-                        if (rs.have && rs.status != ST_SELFCIRCLE) {
-                            emit = true;
-                            text_len = rid_len + p.chr[rs.sA].len + p.chr[rs.sB].len + dec_digits(rs.p1) + dec_digits(rs.p2) + 9u;
-                        }
-                    }
-                }
-            }
-        }
-        if (!emit || !p.write_sam) { sam_len = 0; n_mem = 0; }           // (also the partial sums of a walk that went to the byte level)
-        // -- offsets inside the round: (groups | emitted << 16), text bytes, passthrough bytes, passthrough entries
-        u32 vA = (proc ? 1u : 0u) | (emit ? 1u << 16 : 0u), vT = p.emit_text ? text_len : 0u, vS = sam_len, vE = n_mem;
-        const u32 iA = warp_incl_scan(vA, (int)lane), iT = warp_incl_scan(vT, (int)lane), iS = warp_incl_scan(vS, (int)lane), iE = warp_incl_scan(vE, (int)lane);
-        __syncthreads();                                               // every thread is done with s_line / s_rec of this round
-        if (lane == 31) { s_misc[FM_SCAN + wid] = iA; s_misc[FM_SCAN + 8 + wid] = iT; s_misc[FM_SCAN + 16 + wid] = iS; s_misc[FM_SCAN + 24 + wid] = iE; }
-        __syncthreads();
-        u32 bA = iA - vA, bT = iT - vT, bS = iS - vS, bE = iE - vE, tA = 0, tT = 0, tS = 0, tE = 0;
-#pragma unroll
-        for (u32 w = 0; w < 8; ++w) {
-            const u32 xa = s_misc[FM_SCAN + w], xt = s_misc[FM_SCAN + 8 + w], xs = s_misc[FM_SCAN + 16 + w], xe = s_misc[FM_SCAN + 24 + w];
-            tA += xa; tT += xt; tS += xs; tE += xe;
-            if (w < wid) { bA += xa; bT += xt; bS += xs; bE += xe; }
-        }
-        const u32 run_g = s_misc[FM_GROUPS], run_e = s_misc[FM_EMIT], run_t = s_misc[FM_TEXT], run_s = s_misc[FM_SAM], run_n = s_misc[FM_NENT];
-        const bool fits = run_t + tT <= FT_TEXT_CAP && run_n + tE <= FT_LMAX && run_e + (tA >> 16) <= FT_LMAX;
-        if (!fits) { if (tid == 0) atomicOr(&st->path_old, 1u); return; }   // uniform: the window goes to the multi-kernel path
-        const bool stage = tT <= FT_STAGE_CAP;
-        const u32 phase = (u32)((size_t)(sc_text + run_t) & 15u);
-        char *s_stage = (char *)ft_smem;
-        if (proc) {
-            if (rs.status == ST_SELFCIRCLE) {                          // (tile, group index inside the tile): k_ft_prefix makes it global
-                const u32 slot = atomicAdd(&st->sc_count, 1u);
-                if (slot < p.sc_cap) p.sc_list[slot] = ((u64)tl << 32) | (u64)(run_g + (bA & 0xFFFFu)); else atomicOr(&st->err, S2P_ERR_SCLIST);
-            }
-            if (emit) {
-                const ChrSlot *ca = &p.chr[rs.sA], *cb = &p.chr[rs.sB];
-                if (p.emit_packed) {
-                    mk_pair r; r.pos1 = rs.p1; r.pos2 = rs.p2; r.chr1 = (u16)ca->id; r.chr2 = (u16)cb->id; r.strands = rs.strands;
-                    r.cls = (u8)(rs.status - ST_TRANS); r.lane = p.lane;
-                    sc_pairs[run_e + (bA >> 16)] = r;
-                }
-                if (p.emit_text) {
-                    RidInfo rid; rid.abs = a + rid_off; rid.len = rid_len;
-                    write_pair_line_slots(p, rid, ca, cb, rs.p1, rs.p2, rs.strands, stage ? s_stage + phase + bT : sc_text + run_t + bT);
-                }
-                if (p.write_sam) {                                     // one copy entry per kept line of the group
-                    uint4 *ent = sc_sam + run_n + bE;
-                    if (use_slow) { FtGroup g; ft_group_slow(p, ws, we, a, g, ent, n_mem, run_s + bS); }
-                    else {
-                        u32 k = tid, d = run_s + bS, c = 0;
-                        while (true) {
-                            const u32 len = s_start[base + k + 1] - s_start[base + k];
-                            ent[c++] = make_uint4((u32)((u64)(ebase + (long long)s_start[base + k]) - ws), len, d, 0u);
-                            d += len;
-                            if (c == n_mem) break;
-                            ++k; while (!(s_meta[k] & LM_KEEP)) ++k;
-                        }
-                    }
-                }
-            }
-        }
-        if (p.emit_text && tT && stage) {
-            __syncthreads();
-            char *dst = sc_text + run_t;
-            const u32 head = phase ? (16u - phase < tT ? 16u - phase : tT) : 0u;
-            if (tid < head) dst[tid] = s_stage[phase + tid];
-            const u32 body = (tT - head) >> 4;
-            for (u32 w = tid; w < body; w += FT_THREADS)
-                *(uint4 *)(dst + head + ((size_t)w << 4)) = *(const uint4 *)(s_stage + phase + head + (w << 4));
-            const u32 tail0 = head + (body << 4);
-            if (tail0 + tid < tT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            s_misc[FM_GROUPS] = run_g + (tA & 0xFFFFu); s_misc[FM_EMIT] = run_e + (tA >> 16); s_misc[FM_TEXT] = run_t + tT;
-            s_misc[FM_SAM] = run_s + tS; s_misc[FM_NENT] = run_n + tE;
-        }
-        if (stage && tT) {                                             // the stage overwrote the pad words of the line columns
-#pragma unroll
-            for (int j = 28; j < LF_WORDS; ++j) s_line[j][tid] = 0;
-        }
-        __syncthreads();
-        lo = hi;
-        base = hi - FT_LOOKBACK;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        p.ft_tot[tl] = make_uint4(s_misc[FM_GROUPS] | (s_misc[FM_EMIT] << 16), s_misc[FM_TEXT], s_misc[FM_SAM], n_own_nl);
-        p.ft_nent[tl] = s_misc[FM_NENT];
-    }
-    if (tid < ST_NCOUNTER && s_misc[FM_CNT + tid]) atomicAdd(&st->w_counters[tid], (unsigned long long)s_misc[FM_CNT + tid]);
+    if (tid < ST_NCOUNTER && s_cnt[tid]) atomicAdd(&st->w_counters[tid], (unsigned long long)s_cnt[tid]);
+    if (lane == 0 && last_end) atomicMax((unsigned long long *)&st->ft_last_end, (unsigned long long)last_end);
 }
 
 // ---------------------------------------------------------------------------------------------- prefixes over the tiles

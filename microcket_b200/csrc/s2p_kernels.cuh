@@ -106,6 +106,7 @@ struct S2PParams {
     // single-pass tile path: per-tile scratch (text bytes, packed pairs, passthrough copy entries), indexed by window-local tile
     int fused;                // 1: windows go through k_ft_tile first
     int old_inline;           // 1: the multi-kernel path is enqueued behind it and takes over a window the tile path gives up
+    const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
     char *ft_text; mk_pair *ft_pairs; uint4 *ft_sam, *ft_tot, *ft_pre; u32 *ft_nent; u32 n_tiles_cap;
 };
 
@@ -493,7 +494,7 @@ __device__ __forceinline__ int chr_lookup_insert(const S2PParams &p, u64 h, u64 
     const u64 hh = h ? h : 0x9E3779B97F4A7C15ull;
     const ChrSlot *sl = &p.chr[(u32)(hh ^ (hh >> 29)) & p.chr_mask];
     if (len <= 8 && sl->key == hh && sl->id >= 0 && sl->len == len && sl->name8 == name8) return (int)(sl - p.chr);
-    return chr_lookup_insert_slow(p, h, name8, buf, name_off, len);
+    return chr_lookup_insert_slow(*p.self, h, name8, buf, name_off, len);
 }
 
 // ------------------------------------------------------------------------------------------------ K2: parse
@@ -576,8 +577,8 @@ __device__ __forceinline__ u32 lt21_y(u32 x) {                       // 0x80 in 
     const u32 t = (x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu;
     return ~(t | x) & 0x80808080u;
 }
-static __device__ bool qname_equal_abs(const S2PParams &p, u64 pa, u64 pb);
-static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b);
+static __device__ __noinline__ bool qname_equal_abs(const S2PParams &p, u64 pa, u64 pb);
+static __device__ __forceinline__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b);
 
 // ---- word-at-a-time fast path -------------------------------------------------------------------------------------
 // Well-formed lines (single tabs between the first six fields, nothing else below 0x21, digits where numbers belong,
@@ -677,8 +678,8 @@ __device__ __forceinline__ bool dec_field(const F &buf, u32 abs, u32 len, u32 &o
 
 struct FastTok { u32 t0; u64 q[5]; bool ok; };                       // QNAME length and its first 40 bytes (zero padded)
 
-template <class F, bool WANT_Q>
-__device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, const u64 a, const u64 limit, FastTok &tok, LineRec &rec, u32 &meta) {
+template <class F, bool WANT_Q, class RT>
+__device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, const u64 a, const u64 limit, FastTok &tok, RT &rec, u32 &meta) {
     tok.ok = false;
     if (a + 144 > limit) return false;
     const u64 A = a & ~(u64)15;
@@ -769,7 +770,7 @@ static __device__ __noinline__ u32 parse_line_slow_abs(const S2PParams &p, u64 a
     return parse_line(p, r, q, has_prev, a, rec);
 }
 static __device__ __forceinline__ u32 parse_line_slow(const S2PParams &p, u64 ws, u32 i, u64 a, LineRec &rec) {
-    return parse_line_slow_abs(p, a, i > 0, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0), rec);
+    return parse_line_slow_abs(*p.self, a, i > 0, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0), rec);
 }
 
 static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
@@ -840,7 +841,8 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
 // ------------------------------------------------------------------------------------------------ K3: groups
 struct Seg { u32 pos, right0, left1, right1, leftClip, rightClip, mappable; int segCnt; bool minus; u16 chr; };
 
-__device__ __forceinline__ Seg seg_of(const LineRec &r) {
+template <class RT>
+__device__ __forceinline__ Seg seg_of(const RT &r) {
     Seg s; s.pos = r.pos; s.right0 = r.right0; s.left1 = r.left1; s.right1 = r.right1;
     s.leftClip = r.leftClip; s.rightClip = r.rightClip; s.mappable = r.mappable; s.segCnt = r.segCnt;
     s.minus = (r.flag & 16u) != 0; s.chr = r.chr_slot;
@@ -889,11 +891,11 @@ static __device__ __noinline__ bool qname_equal_bytes(const S2PParams &p, u64 pa
     while (!is_ws(c) && !is_ws(d)) { if (c != d) return false; c = x.next(); d = y.next(); }
     return is_ws(c) && is_ws(d);
 }
-static __device__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
-    return qname_equal_abs(p, ws + (a ? p.nl_pos[a - 1] + 1 : 0), ws + (b ? p.nl_pos[b - 1] + 1 : 0));
+static __device__ __forceinline__ bool qname_equal_slow(const S2PParams &p, u64 ws, u32 a, u32 b) {
+    return qname_equal_abs(*p.self, ws + (a ? p.nl_pos[a - 1] + 1 : 0), ws + (b ? p.nl_pos[b - 1] + 1 : 0));
 }
 // first tokens of the lines that start at absolute offsets pa and pb
-static __device__ bool qname_equal_abs(const S2PParams &p, u64 pa, u64 pb) {
+static __device__ __noinline__ bool qname_equal_abs(const S2PParams &p, u64 pa, u64 pb) {
     GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
     for (u32 k = 0;; k += 8) {
         const u64 x = fetch8(gf, pa + k), y = fetch8(gf, pb + k);
@@ -917,15 +919,25 @@ __device__ __forceinline__ bool line_eq(const S2PParams &p, u64 ws, u32 q, u32 m
 __device__ __forceinline__ u32 line_len_of(const S2PParams &p, u32 q) { return p.nl_pos[q] - (q ? p.nl_pos[q - 1] + 1 : 0); }
 
 // bytewise order of two chromosome names (std::string::compare)
-static __device__ int chr_name_cmp(const S2PParams &p, u16 sa, u16 sb) {
-    if (sa == sb) return 0;
-    const ChrSlot *a = &p.chr[sa], *b = &p.chr[sb];
+static __device__ __noinline__ int chr_name_cmp_slow(const ChrSlot *a, const ChrSlot *b) {
     u32 la = a->len, lb = b->len, m = la < lb ? la : lb;
     for (u32 i = 0; i < m; ++i) {
         int d = (int)(u8)a->name[i] - (int)(u8)b->name[i];
         if (d) return d;
     }
     return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+// names of up to 8 bytes (name8 = the bytes, little endian, zero padded) compare as big-endian integers
+__device__ __forceinline__ int chr_name_cmp(const S2PParams &p, u16 sa, u16 sb) {
+    if (sa == sb) return 0;
+    const ChrSlot *a = &p.chr[sa], *b = &p.chr[sb];
+    if (a->len <= 8 && b->len <= 8) {
+        const u64 x = a->name8, y = b->name8;
+        const u32 xh = __byte_perm((u32)x, 0, 0x0123), xl = __byte_perm((u32)(x >> 32), 0, 0x0123);
+        const u32 yh = __byte_perm((u32)y, 0, 0x0123), yl = __byte_perm((u32)(y >> 32), 0, 0x0123);
+        return xh != yh ? (xh < yh ? -1 : 1) : (xl != yl ? (xl < yl ? -1 : 1) : 0);   // zero padding: a proper prefix sorts first
+    }
+    return chr_name_cmp_slow(a, b);
 }
 
 __device__ __forceinline__ u32 dec_digits(u32 v) {
@@ -937,8 +949,9 @@ __device__ __forceinline__ u32 dec_digits(u32 v) {
 // n1 / n2 of them flagged first / second in pair; f0, f1 = the first two kept records, a1, b1 / a2, b2 = the first two R1 / R2
 // records (pointers beyond the counts are never dereferenced).  Shared by the multi-kernel path and the single-pass tile path.
 struct Resolved { u32 p1, p2; u16 sA, sB; u8 status, strands; bool have; };
-__device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32 n1, u32 n2, const LineRec *f0, const LineRec *f1,
-                                                  const LineRec *a1, const LineRec *b1, const LineRec *a2, const LineRec *b2) {
+template <class RT>
+__device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32 n1, u32 n2, const RT *f0, const RT *f1,
+                                                  const RT *a1, const RT *b1, const RT *a2, const RT *b2) {
     Resolved o; o.p1 = o.p2 = 0; o.sA = o.sB = 0; o.status = ST_NONE; o.strands = 0; o.have = false;
     u32 p1 = 0, p2 = 0; u16 c1 = 0, c2 = 0; bool m1 = false, m2 = false; bool have = false, ordered = false;
     const float ratio = p.ratio;
