@@ -242,7 +242,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
     A(c->d_tiletot.alloc((size_t)c->n_sub_cap * 2 * sizeof(uint4)));
     c->n_tiles_cap = (u32)((S2P_CARRY + c->W) / FT_TILE + 2);
-    c->fused = !(getenv("MICROCKET_FUSED") && !atoi(getenv("MICROCKET_FUSED")));   // 0: multi-kernel path only (A/B, parity of both paths)
+    c->fused = getenv("MICROCKET_FUSED") && atoi(getenv("MICROCKET_FUSED"));   // 1: single-pass strip path first (half the DRAM traffic, but instruction-fetch bound so far: see DESIGN.md); default: multi-kernel path
     if (c->fused) {
         A(c->d_fttext.alloc((size_t)c->n_tiles_cap * FT_TEXT_CAP + 64)); A(c->d_ftpairs.alloc((size_t)c->n_tiles_cap * FT_LMAX * sizeof(mk_pair)));
         A(c->d_ftsam.alloc(cfg->write_sam ? (size_t)c->n_tiles_cap * FT_LMAX * sizeof(uint4) : 16));

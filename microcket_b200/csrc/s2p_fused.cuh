@@ -28,7 +28,7 @@
 #define FT_TEXT_CAP 49152u            // bytes of pair text per strip in the scratch
 #define FS_THREADS 256
 #define FS_WARPS 8
-#define FS_HALO 2048u                 // bytes scanned on either side of the strip (4 rows of 512 B)
+#define FS_HALO 4096u                 // bytes scanned on either side of the strip (8 rows of 512 B, one scan step)
 #define FS_RING 256u                  // line starts (relative to the strip's scan origin) known to the warp
 #define FS_RECS 64u                   // records / meta bytes of the last 64 parsed lines
 #define FS_LOOKAHEAD 8u               // lines parsed beyond the heads a round resolves
@@ -80,16 +80,33 @@ static __device__ __noinline__ bool ft_head_slow(const S2PParams &p, u64 ws, u64
     return true;
 }
 
+// the generic parser, out of line, into a shared-memory record
+static __device__ __noinline__ u32 fs_parse_slow(const S2PParams &p, u64 a, bool has_prev, u64 pa, FtRec *out) {
+    LineRec r;
+    const u32 meta = parse_line_slow_abs(p, a, has_prev, pa, r);
+    if (meta & LM_KEEP) {
+        out->pos = r.pos; out->right0 = r.right0; out->left1 = r.left1; out->right1 = r.right1; out->leftClip = r.leftClip; out->rightClip = r.rightClip;
+        out->mappable = r.mappable; out->flag = r.flag; out->qname_len = r.qname_len; out->chr_slot = r.chr_slot; out->segCnt = r.segCnt; out->qname_off = r.qname_off;
+    }
+    return meta;
+}
+
+// one out-of-line copy of the resolver for this path (records in shared or local memory)
+static __device__ __noinline__ Resolved fs_resolve(const S2PParams &p, u32 n, u32 n1, u32 n2, const FtRec *f0, const FtRec *f1,
+                                                   const FtRec *a1, const FtRec *b1, const FtRec *a2, const FtRec *b2) {
+    return resolve_group(p, n, n1, n2, f0, f1, a1, b1, a2, b2);
+}
 struct FtGroup { Resolved r; u32 sam_len, n_members, qname_len, qname_off; bool off_end, kept; };
 // The whole group of the head line at `a_head`, line by line from global memory (any number of lines, any line length).
 // entries != nullptr: also writes one passthrough copy entry per member (src relative to ws, length with '\n', destination).
 static __device__ __noinline__ void ft_group_slow(const S2PParams &p, u64 ws, u64 we, u64 a_head, FtGroup &out, uint4 *entries, u32 ent_cap, u32 dst0) {
-    LineRec f[2], r1[2], r2[2], rec;
+    FtRec f[2], r1[2], r2[2], rec;
     u32 n = 0, n1 = 0, n2 = 0, sam_len = 0;
     out.off_end = false;
     u64 cur = a_head;
     u64 e = ft_find_nl(p.buf, cur, we);
-    const u32 meta = parse_line_slow_abs(p, cur, false, 0, rec);
+    rec.qname_len = 0; rec.qname_off = 0;
+    const u32 meta = fs_parse_slow(p, cur, false, 0, &rec);
     out.kept = (meta & LM_KEEP) != 0; out.qname_len = rec.qname_len; out.qname_off = rec.qname_off;
     out.sam_len = 0; out.n_members = 0;
     if (!out.kept || e == FT_NONE) { out.off_end = true; return; }
@@ -107,7 +124,7 @@ static __device__ __noinline__ void ft_group_slow(const S2PParams &p, u64 ws, u6
             if (nxt >= we) { out.off_end = true; break; }
             const u64 e2 = ft_find_nl(p.buf, nxt, we);
             if (e2 == FT_NONE) { out.off_end = true; break; }
-            const u32 m2 = parse_line_slow_abs(p, nxt, true, a_head, rec);
+            const u32 m2 = fs_parse_slow(p, nxt, true, a_head, &rec);
             cur = nxt; e = e2;
             if (!(m2 & LM_KEEP)) continue;
             more = (m2 & LM_EQ) != 0;
@@ -116,12 +133,24 @@ static __device__ __noinline__ void ft_group_slow(const S2PParams &p, u64 ws, u6
         if (out.off_end || !more) break;
     }
     out.sam_len = sam_len; out.n_members = n;
-    if (!out.off_end) out.r = resolve_group(p, n, n1, n2, &f[0], &f[1], &r1[0], &r1[1], &r2[0], &r2[1]);
+    if (!out.off_end) out.r = fs_resolve(p, n, n1, n2, &f[0], &f[1], &r1[0], &r1[1], &r2[0], &r2[1]);
 }
 
 // ---------------------------------------------------------------------------------------------- scan of 512-byte rows
 // Line starts (newline offset + 1, relative to the scan origin; rel0 = offset of rbase from it) of `nrows` rows appended, in byte
 // order, to the warp's ring; returns the new number of known starts.  Same tests as k_scan_chunks.
+// a 512-byte row in which some 16-byte word holds several newlines (empty or very short lines): ranks by a warp scan
+static __device__ __noinline__ u32 fs_push_multi(u32 *ring, u32 n, u32 z, u32 rel, u32 lane) {
+    const u32 c = __popc(z);
+    const u32 inc = warp_incl_scan(c, (int)lane);
+    const u32 tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    if (c) {
+        u32 m = 0, idx = n + inc - c;
+        while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
+        while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; ring[idx & (FS_RING - 1u)] = rel + q; ++idx; }
+    }
+    return n + tot;
+}
 template <int U>
 __device__ __forceinline__ u32 fs_scan_push(const char *buf, long long rbase, u32 nrows, u32 rel0, u64 ws, u64 we, u32 *ring, u32 n, u32 lane) {
     const bool edge = rbase < (long long)ws || rbase + (long long)nrows * 512 > (long long)we;
@@ -160,17 +189,7 @@ __device__ __forceinline__ u32 fs_scan_push(const char *buf, long long rbase, u3
                 n += __popc(bal);
                 continue;
             }
-            const u32 c = __popc(z);
-            const u32 inc = warp_incl_scan(c, (int)lane);
-            const u32 tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            if (c) {
-                u32 m = 0, idx = n + inc - c;
-#pragma unroll 1
-                while (z) { const u32 b = __ffs(z) - 1; z &= z - 1; m |= 1u << byte_of_perm_bit(b); }
-#pragma unroll 1
-                while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; ring[idx & (FS_RING - 1u)] = rel + q; ++idx; }
-            }
-            n += tot;
+            n = fs_push_multi(ring, n, z, rel, lane);
         }
     }
     return n;
@@ -280,104 +299,6 @@ __device__ __forceinline__ bool fs_parse_fast(const S2PParams &p, const ColFetch
     rec.qname_off = 0;
     return true;
 }
-// the generic parser, out of line, into a shared-memory record
-static __device__ __noinline__ u32 fs_parse_slow(const S2PParams &p, u64 a, bool has_prev, u64 pa, FtRec *out) {
-    LineRec r;
-    const u32 meta = parse_line_slow_abs(p, a, has_prev, pa, r);
-    if (meta & LM_KEEP) {
-        out->pos = r.pos; out->right0 = r.right0; out->left1 = r.left1; out->right1 = r.right1; out->leftClip = r.leftClip; out->rightClip = r.rightClip;
-        out->mappable = r.mappable; out->flag = r.flag; out->qname_len = r.qname_len; out->chr_slot = r.chr_slot; out->segCnt = r.segCnt; out->qname_off = r.qname_off;
-    }
-    return meta;
-}
-
-// ---------------------------------------------------------------------------------------------- lean text writer
-// Bytes are collected in a 64-bit accumulator and stored as aligned 32-bit words; the first and last word of a line are
-// shared with the neighbouring lines (written by other lanes), so their bytes go out one by one.
-struct TextW { u32 *w; u32 lo, hi, fill, skip; };
-__device__ __forceinline__ void tw_init(TextW &t, char *dst) {
-    t.w = (u32 *)((size_t)dst & ~(size_t)3); t.skip = (u32)((size_t)dst & 3u); t.fill = t.skip; t.lo = t.hi = 0;
-}
-__device__ __forceinline__ void tw_flush(TextW &t) {
-    if (t.skip) { unsigned char *b = (unsigned char *)t.w; for (u32 k = t.skip; k < 4u; ++k) b[k] = (unsigned char)(t.lo >> (8 * k)); t.skip = 0; }
-    else *t.w = t.lo;
-    ++t.w; t.lo = t.hi; t.hi = 0; t.fill -= 4u;
-}
-__device__ __forceinline__ void tw_put(TextW &t, u32 x, u32 n) {     // the low n (1..4) bytes of x; the bytes above them must be zero
-    const u32 sh = t.fill * 8u;
-    t.lo |= x << sh; t.hi |= __funnelshift_l(x, 0u, sh);
-    t.fill += n;
-    if (t.fill >= 4u) tw_flush(t);
-}
-__device__ __forceinline__ void tw_end(TextW &t) {
-    unsigned char *b = (unsigned char *)t.w;
-    for (u32 k = t.skip; k < t.fill; ++k) b[k] = (unsigned char)(t.lo >> (8 * k));
-}
-// four decimal digits of v (< 10000) as characters, most significant in the lowest byte
-__device__ __forceinline__ u32 dig4(u32 v) {
-    const u32 hi2 = (v * 5243u) >> 19, lo2 = v - hi2 * 100u;           // v / 100 for v < 10000
-    const u32 a = (hi2 * 103u) >> 10, b = (lo2 * 103u) >> 10;          // x / 10 for x < 100
-    return (a | ((hi2 - a * 10u) << 8) | (b << 16) | ((lo2 - b * 10u) << 24)) + 0x30303030u;
-}
-__device__ __forceinline__ void tw_put_uint(TextW &t, u32 v) {
-    const u32 q1 = v / 10000u, r1 = v - q1 * 10000u;
-    if (q1 == 0) {
-        const u32 n = v >= 1000u ? 4u : v >= 100u ? 3u : v >= 10u ? 2u : 1u;
-        tw_put(t, dig4(r1) >> (8u * (4u - n)), n);
-        return;
-    }
-    const u32 q2 = q1 / 10000u, r2 = q1 - q2 * 10000u;
-    if (q2 == 0) {
-        const u32 n = q1 >= 1000u ? 4u : q1 >= 100u ? 3u : q1 >= 10u ? 2u : 1u;
-        tw_put(t, dig4(r2) >> (8u * (4u - n)), n);
-    } else {
-        const u32 n = q2 >= 10u ? 2u : 1u;
-        tw_put(t, dig4(q2) >> (8u * (4u - n)), n);
-        tw_put(t, dig4(r2), 4u);
-    }
-    tw_put(t, dig4(r1), 4u);
-}
-__device__ __forceinline__ void tw_put_name_tab(TextW &t, const ChrSlot *c) {   // chromosome name followed by a tab
-    const u32 l = c->len;
-    if (l < 8) {
-        const u64 x = c->name8 | ((u64)'\t' << (8 * l));
-        const u32 n = l + 1;
-        if (n <= 4) tw_put(t, (u32)x, n);
-        else { tw_put(t, (u32)x, 4u); tw_put(t, (u32)(x >> 32), n - 4u); }
-        return;
-    }
-    if (l == 8) { tw_put(t, (u32)c->name8, 4u); tw_put(t, (u32)(c->name8 >> 32), 4u); }
-    else for (u32 i = 0; i < l; ++i) tw_put(t, (u32)(unsigned char)c->name[i], 1u);
-    tw_put(t, '\t', 1u);
-}
-// rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347); the read id comes back out of L2
-__device__ __forceinline__ void fs_write_pair_line(const char *buf, u64 rid_abs, u32 rid_len, const ChrSlot *ca, const ChrSlot *cb,
-                                                   u32 posA, u32 posB, u32 strands, char *out) {
-    TextW t; tw_init(t, out);
-    const u64 a8 = rid_abs & ~(u64)7; const u32 sh = (u32)(rid_abs & 7u) * 8u;
-    const u64 *src = (const u64 *)(buf + a8);
-    u64 cur = __ldg(src);
-    for (u32 k = 0; k < rid_len; k += 8) {
-        const u64 nxt = __ldg(src + (k >> 3) + 1);
-        const u64 x = sh ? (cur >> sh) | (nxt << (64u - sh)) : cur;
-        cur = nxt;
-        const u32 n = rid_len - k < 8u ? rid_len - k : 8u;
-        const u32 xl = (u32)x, xh = (u32)(x >> 32);
-        if (n >= 4u) { tw_put(t, xl, 4u); if (n > 4u) tw_put(t, n == 8u ? xh : xh & ((1u << (8u * (n - 4u))) - 1u), n - 4u); }
-        else tw_put(t, xl & ((1u << (8u * n)) - 1u), n);
-    }
-    tw_put(t, '\t', 1u);
-    tw_put_name_tab(t, ca);
-    tw_put_uint(t, posA);
-    tw_put(t, '\t', 1u);
-    tw_put_name_tab(t, cb);
-    tw_put_uint(t, posB);
-    // \t s1 \t s2 \n
-    tw_put(t, (u32)'\t' | ((strands & 1u) ? (u32)'-' << 8 : (u32)'+' << 8) | ((u32)'\t' << 16) | ((strands & 2u) ? (u32)'-' << 24 : (u32)'+' << 24), 4u);
-    tw_put(t, '\n', 1u);
-    tw_end(t);
-}
-
 // ---------------------------------------------------------------------------------------------- the strip kernel
 static __global__ void __launch_bounds__(FS_THREADS, 3) k_ft_strip(S2PParams p) {
     extern __shared__ __align__(16) unsigned char fs_smem[];
@@ -417,32 +338,32 @@ static __global__ void __launch_bounds__(FS_THREADS, 3) k_ft_strip(S2PParams p) 
         uint4 *sc_sam = p.ft_sam + (size_t)sl * FT_LMAX;
         u32 n_known = 0;
         if (has_initial) { if (lane == 0) ring[0] = (u32)((long long)ws - ebase); n_known = 1; }
-        // the four rows in front of the strip: only the last lines matter (look-back of the strip's first group)
-        n_known = fs_scan_push<4>(p.buf, ebase, 4u, 0u, ws, we, ring, n_known, lane);
-        if (n_known > FS_RING - 64u) { if (lane == 0) atomicOr(&st->path_old, 1u); break; }
-        const u32 n_main0 = n_known;                                   // lines from here on start behind a newline of this strip
-        const u32 n_drop = n_known > 3u ? n_known - 3u : 0u;           // lines below are never parsed
-        u32 n_parsed = n_drop, n_res = n_drop, n_main1 = n_known;
+        // scan steps of 8 rows (4 KiB): step 0 in front of the strip (only its last lines matter: look-back of the strip's first
+        // group), steps 1..32 the strip, step 33 behind it (look-ahead of its last group)
+        u32 n_main0 = n_known, n_drop = 0, n_main1 = n_known;
+        u32 n_parsed = 0, n_res = 0;
         u32 run_g = 0, run_e = 0, run_t = 0, run_s = 0, run_n = 0;     // strip totals so far (warp-uniform)
-        u32 stage = 0;                                                  // 0..31 main batches of 8 rows, 32 the rows behind the strip, 33 done
+        u32 stage = 0;
         bool ovf = false;
         while (true) {
             const u32 pending = n_known - n_parsed;                    // starts not parsed yet (the last one has no known end)
-            if (stage <= 32u && pending <= 32u) {                      // not enough for a full round of 32 complete lines: scan on
-                if (stage < 32u) {
-                    n_known = fs_scan_push<8>(p.buf, (long long)sbase + (long long)stage * 4096, 8u, FS_HALO + stage * 4096u, ws, we, ring, n_known, lane);
-                    n_main1 = n_known;
-                } else n_known = fs_scan_push<4>(p.buf, (long long)send, 4u, FS_HALO + FT_TILE, ws, we, ring, n_known, lane);
+            if (stage <= 33u && (pending <= 32u || stage == 0u)) {     // not enough for a full round of 32 complete lines: scan on
+                n_known = fs_scan_push<8>(p.buf, ebase + (long long)stage * 4096, 8u, stage * 4096u, ws, we, ring, n_known, lane);
                 ++stage;
                 if (n_known - n_parsed > FS_RING - 64u) { ovf = true; break; }
-                if (stage == 32u && n_main1 > n_main0) {               // end of the strip's last complete line (a window without kept records ends there)
+                if (stage == 1u) {                                     // lines from here on start behind a newline of this strip
+                    n_main0 = n_known; n_drop = n_known > 3u ? n_known - 3u : 0u;   // lines below n_drop are never parsed
+                    n_parsed = n_res = n_drop;
+                }
+                if (stage <= 33u) n_main1 = n_known;
+                if (stage == 33u && n_main1 > n_main0) {               // end of the strip's last complete line (a window without kept records ends there)
                     __syncwarp();
                     const u64 e = (u64)(ebase + (long long)ring[(n_main1 - 1u) & (FS_RING - 1u)]);
                     if (e > last_end) last_end = e;
                 }
                 continue;
             }
-            const bool final = stage > 32u;
+            const bool final = stage > 33u;
             const u32 cnt = pending > 32u ? 32u : (pending ? pending - 1u : 0u);
             __syncwarp();
             // ---- parse `cnt` lines, one per lane.  A start is a complete line iff it has a successor in the ring.
@@ -585,7 +506,7 @@ static __global__ void __launch_bounds__(FS_THREADS, 3) k_ft_strip(S2PParams p) 
                                 } else { proc = true; rs = g.r; sam_len = g.sam_len; n_mem = g.n_members; rid_len = g.qname_len; rid_off = g.qname_off; }
                             } else {
                                 proc = true;
-                                rs = resolve_group(p, n, n1, n2, &recs[f0 & (FS_RECS - 1u)], &recs[f1 & (FS_RECS - 1u)], &recs[r1a & (FS_RECS - 1u)],
+                                rs = fs_resolve(ps, n, n1, n2, &recs[f0 & (FS_RECS - 1u)], &recs[f1 & (FS_RECS - 1u)], &recs[r1a & (FS_RECS - 1u)],
                                                    &recs[r1b & (FS_RECS - 1u)], &recs[r2a & (FS_RECS - 1u)], &recs[r2b & (FS_RECS - 1u)]);
                                 rid_len = recs[line & (FS_RECS - 1u)].qname_len; rid_off = recs[line & (FS_RECS - 1u)].qname_off;
                             }
@@ -615,6 +536,11 @@ static __global__ void __launch_bounds__(FS_THREADS, 3) k_ft_strip(S2PParams p) 
                 const bool staged = tT <= FS_STAGE;
                 const u32 phase = (u32)((size_t)(sc_text + run_t) & 15u);
                 char *s_stage = (char *)wb;                            // the line-head columns are dead until the next parse round
+                if (p.emit_text && tT && staged) {                     // the text is OR-ed into a zeroed stage
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ((uint4 *)wb)[j * 32 + lane] = make_uint4(0, 0, 0, 0);
+                    __syncwarp();
+                }
                 if (proc) {
                     if (rs.status == ST_SELFCIRCLE) {                  // (strip, group index inside the strip): k_ft_prefix makes it global
                         const u32 slot = atomicAdd(&st->sc_count, 1u);
@@ -628,8 +554,10 @@ static __global__ void __launch_bounds__(FS_THREADS, 3) k_ft_strip(S2PParams p) 
                             r.w = (u32)rs.strands | ((u32)(rs.status - ST_TRANS) << 8) | ((u32)p.lane << 16);
                             ((uint4 *)sc_pairs)[run_e + bP] = r;
                         }
-                        if (p.emit_text) fs_write_pair_line(p.buf, a + rid_off, rid_len, ca, cb, rs.p1, rs.p2, rs.strands,
-                                                            staged ? s_stage + phase + bT : sc_text + run_t + bT);
+                        if (p.emit_text) {
+                            if (staged && ca->len <= 8 && cb->len <= 8) fs_write_pair_line(p.buf, a + rid_off, rid_len, ca, cb, rs.p1, rs.p2, rs.strands, s_stage + phase + bT);
+                            else fs_write_pair_line_bytes(p.buf, a + rid_off, rid_len, ca, cb, rs.p1, rs.p2, rs.strands, staged ? s_stage + phase + bT : sc_text + run_t + bT, staged);
+                        }
                         if (p.write_sam) {                             // one copy entry per kept line of the group
                             uint4 *ent = sc_sam + run_n + bE;
                             if (use_slow) { FtGroup g; ft_group_slow(ps, ws, we, a, g, ent, n_mem, run_s + bS); }

@@ -1193,6 +1193,137 @@ __device__ __forceinline__ void write_pair_line(const S2PParams &p, const RidInf
     write_pair_line_slots(p, rid, &p.chr[p.id_to_slot[g.chrA]], &p.chr[p.id_to_slot[g.chrB]], g.posA, g.posB, g.strands, out);
 }
 
+// ---------------------------------------------------------------------------------------------- lean text writer
+// A line is a sequence of pieces of at most four bytes.  They are collected in a 64-bit accumulator and OR-ed into the
+// (zeroed) shared-memory stage as aligned 32-bit words: the first and last word of a line are shared with the neighbouring
+// lines, which other lanes write, and OR makes that safe without any byte-level special case.
+// (red.shared on a 32-bit shared address: a generic-pointer atomicOr compiles to the slow generic ATOM path)
+__device__ __forceinline__ void sts_or(u32 saddr, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+struct TextW { u32 w; u32 lo, hi, fill; };                            // w: shared-memory byte address of the current word
+__device__ __forceinline__ void tw_init(TextW &t, char *dst) {
+    const u32 sa = smem_u32(dst);
+    t.w = sa & ~3u; t.fill = sa & 3u; t.lo = t.hi = 0;
+}
+__device__ __forceinline__ void tw_put(TextW &t, u32 x, u32 n) {     // the low n (0..4) bytes of x; the bytes above them must be zero
+    const u32 sh = t.fill * 8u;
+    t.lo |= x << sh; t.hi |= __funnelshift_l(x, 0u, sh);
+    t.fill += n;
+    if (t.fill >= 4u) { sts_or(t.w, t.lo); t.w += 4u; t.lo = t.hi; t.hi = 0; t.fill -= 4u; }
+}
+__device__ __forceinline__ void tw_end(TextW &t) { if (t.fill) sts_or(t.w, t.lo); }
+// four decimal digits of v (< 10000) as characters, most significant in the lowest byte
+__device__ __forceinline__ u32 dig4(u32 v) {
+    const u32 hi2 = (v * 5243u) >> 19, lo2 = v - hi2 * 100u;           // v / 100 for v < 10000
+    const u32 a = (hi2 * 103u) >> 10, b = (lo2 * 103u) >> 10;          // x / 10 for x < 100
+    return (a | ((hi2 - a * 10u) << 8) | (b << 16) | ((lo2 - b * 10u) << 24)) + 0x30303030u;
+}
+// the nd decimal characters of v, left-aligned in three words (first character in the lowest byte of d0)
+__device__ __forceinline__ void dec_chars(u32 v, u32 nd, u32 &d0, u32 &d1, u32 &d2) {
+    const u32 q1 = v / 10000u, r1 = v - q1 * 10000u, q2 = q1 / 10000u, r2 = q1 - q2 * 10000u;
+    const u32 w0 = dig4(q2), w1 = dig4(r2), w2 = dig4(r1);             // "00dddddddddd": twelve characters, 12 - nd leading zeros
+    const u32 k = 12u - nd, i = k >> 2, sh = (k & 3u) * 8u;
+    const u32 a = i == 0 ? w0 : (i == 1 ? w1 : w2), b = i == 0 ? w1 : (i == 1 ? w2 : 0u), c = i == 0 ? w2 : 0u;
+    d0 = __funnelshift_r(a, b, sh); d1 = __funnelshift_r(b, c, sh); d2 = c >> sh;
+}
+__device__ __forceinline__ u32 piece_len(u32 total, u32 j) { return total > 4u * j ? (total - 4u * j > 4u ? 4u : total - 4u * j) : 0u; }
+// rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347) into the zeroed stage; the read id comes back out of
+// L2.  Chromosome names of up to 8 bytes (ChrSlot.name8); longer ones take the byte-wise writer.
+__device__ __forceinline__ void fs_write_pair_line(const char *buf, u64 rid_abs, u32 rid_len, const ChrSlot *ca, const ChrSlot *cb,
+                                                   u32 posA, u32 posB, u32 strands, char *out) {
+    TextW t; tw_init(t, out);
+    {
+        // the first 48 bytes of the read id: seven aligned 8-byte loads issued together (they come from L2 or DRAM), then
+        // realigned in registers; longer ids continue with one dependent load per 8 bytes
+        const u64 a8 = rid_abs & ~(u64)7; const u32 sh = (u32)(rid_abs & 7u) * 8u;
+        const u64 *src = (const u64 *)(buf + a8);
+        const u32 span = rid_len + (sh >> 3);
+        u64 r[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) r[j] = (u32)(8 * j) < span ? __ldg(src + j) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            if ((u32)(8 * j) < rid_len) {
+                const u64 x = sh ? (r[j] >> sh) | (r[j + 1] << (64u - sh)) : r[j];
+                const u32 n = rid_len - 8u * j < 8u ? rid_len - 8u * j : 8u;
+                u32 xl = (u32)x, xh = (u32)(x >> 32);
+                if (n < 8u) { if (n <= 4u) { xh = 0; if (n < 4u) xl &= (1u << (8u * n)) - 1u; } else xh &= (1u << (8u * (n - 4u))) - 1u; }
+                tw_put(t, xl, n < 4u ? n : 4u);
+                tw_put(t, xh, n > 4u ? n - 4u : 0u);
+            }
+        }
+        if (rid_len > 48u) {
+            u64 cur = r[6];
+#pragma unroll 1
+            for (u32 k = 48; k < rid_len; k += 8) {
+                const u64 nxt = __ldg(src + (k >> 3) + 1);
+                const u64 x = sh ? (cur >> sh) | (nxt << (64u - sh)) : cur;
+                cur = nxt;
+                const u32 n = rid_len - k < 8u ? rid_len - k : 8u;
+                u32 xl = (u32)x, xh = (u32)(x >> 32);
+                if (n < 8u) { if (n <= 4u) { xh = 0; if (n < 4u) xl &= (1u << (8u * n)) - 1u; } else xh &= (1u << (8u * (n - 4u))) - 1u; }
+                tw_put(t, xl, n < 4u ? n : 4u);
+                tw_put(t, xh, n > 4u ? n - 4u : 0u);
+            }
+        }
+    }
+    // the fourteen pieces behind the read id, through ONE tw_put site (code size)
+    const u32 la = ca->len, lb = cb->len;
+    const u64 na = ca->name8, nb = cb->name8;
+    const u32 nda = dec_digits(posA), ndb = dec_digits(posB);
+    u32 a0, a1, a2, b0, b1, b2;
+    dec_chars(posA, nda, a0, a1, a2); dec_chars(posB, ndb, b0, b1, b2);
+    // "\t" name "\t" as up to ten bytes in three words
+    const u64 ta = (u64)'\t' | (na << 8) | (la < 7u ? (u64)'\t' << (8u * (la + 1u)) : 0ull), tb = (u64)'\t' | (nb << 8) | (lb < 7u ? (u64)'\t' << (8u * (lb + 1u)) : 0ull);
+    const u32 ta2 = (u32)(na >> 56) | (la == 7u ? (u32)'\t' : 0u) | (la == 8u ? (u32)'\t' << 8 : 0u);
+    const u32 tb2 = (u32)(nb >> 56) | (lb == 7u ? (u32)'\t' : 0u) | (lb == 8u ? (u32)'\t' << 8 : 0u);
+    const u32 tail = (u32)'\t' | ((strands & 1u) ? (u32)'-' << 8 : (u32)'+' << 8) | ((u32)'\t' << 16) | ((strands & 2u) ? (u32)'-' << 24 : (u32)'+' << 24);
+#pragma unroll 1
+    for (u32 step = 0; step < 14u; ++step) {
+        u32 x, n;
+        switch (step) {
+        case 0: x = (u32)ta; n = piece_len(la + 2u, 0); break;
+        case 1: x = (u32)(ta >> 32); n = piece_len(la + 2u, 1); break;
+        case 2: x = ta2; n = piece_len(la + 2u, 2); break;
+        case 3: x = a0; n = piece_len(nda, 0); break;
+        case 4: x = a1; n = piece_len(nda, 1); break;
+        case 5: x = a2; n = piece_len(nda, 2); break;
+        case 6: x = (u32)tb; n = piece_len(lb + 2u, 0); break;
+        case 7: x = (u32)(tb >> 32); n = piece_len(lb + 2u, 1); break;
+        case 8: x = tb2; n = piece_len(lb + 2u, 2); break;
+        case 9: x = b0; n = piece_len(ndb, 0); break;
+        case 10: x = b1; n = piece_len(ndb, 1); break;
+        case 11: x = b2; n = piece_len(ndb, 2); break;
+        case 12: x = tail; n = 4u; break;
+        default: x = (u32)'\n'; n = 1u; break;
+        }
+        tw_put(t, x, n);
+    }
+    tw_end(t);
+}
+// byte-wise writer: long chromosome names, or a round whose text does not fit the stage (rare).  or_mode: the destination is the
+// zeroed shared-memory stage that neighbouring lines are OR-ed into, so every byte is OR-ed into its word as well.
+__device__ __forceinline__ void put_byte_mode(char *out, char c, bool or_mode) {
+    if (or_mode) { const u32 sa = smem_u32(out); sts_or(sa & ~3u, (u32)(unsigned char)c << (8u * (sa & 3u))); }
+    else *out = c;
+}
+static __device__ __noinline__ void fs_write_pair_line_bytes(const char *buf, u64 rid_abs, u32 rid_len, const ChrSlot *ca, const ChrSlot *cb,
+                                                              u32 posA, u32 posB, u32 strands, char *out, bool or_mode) {
+    for (u32 k = 0; k < rid_len; ++k) put_byte_mode(out++, buf[rid_abs + k], or_mode);
+    put_byte_mode(out++, '\t', or_mode);
+    for (u32 k = 0; k < ca->len; ++k) put_byte_mode(out++, ca->name[k], or_mode);
+    put_byte_mode(out++, '\t', or_mode);
+    for (int pass = 0; pass < 2; ++pass) {
+        u32 v = pass ? posB : posA;
+        const u32 n = dec_digits(v);
+        for (int i = (int)n - 1; i >= 0; --i) { put_byte_mode(out + i, (char)('0' + v % 10u), or_mode); v /= 10u; }
+        out += n;
+        put_byte_mode(out++, '\t', or_mode);
+        if (pass == 0) { for (u32 k = 0; k < cb->len; ++k) put_byte_mode(out++, cb->name[k], or_mode); put_byte_mode(out++, '\t', or_mode); }
+    }
+    put_byte_mode(out++, (strands & 1) ? '-' : '+', or_mode); put_byte_mode(out++, '\t', or_mode);
+    put_byte_mode(out++, (strands & 2) ? '-' : '+', or_mode); put_byte_mode(out++, '\n', or_mode);
+}
+
 // Tiles of 512 lines.  K3 has already summed every tile's sizes (tile_tot), k_emit_prefix turns them into exclusive prefixes
 // (one CTA, a few microseconds), so a tile here depends on no other tile: no look-back, no grid-wide dependency, and the
 // small tiles leave no idle tail (the look-back version needed 2048-line tiles to amortise its chain: 5.1 tiles per CTA
@@ -1241,6 +1372,7 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
     int pb = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, pb ^= 1) {
         const uint4 tbase = p.tile_pre[tile];                           // (groups, emitted, text, passthrough) before this tile
+
         // ---- phase 1: per-thread sizes (groups | emitted << 16, text bytes, passthrough bytes)
         u32 lA[EMIT_NT], lT[EMIT_NT], lS[EMIT_NT];                      // become thread-exclusive prefixes inside the tile
 #pragma unroll
@@ -1319,6 +1451,8 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
                 }
                 ++e_idx;
                 if (p.emit_text && text_fits) {
+                    // (byte-wise on purpose: the word-wise OR writer of the strip path is a dependent chain through its accumulator and
+                    // measured slower here, 4.8 vs 3.2 ms per 19.8 GB; these stores are independent)
                     write_pair_line(p, rid[q], g, staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
                     t_run += g.text_len;
                 }
