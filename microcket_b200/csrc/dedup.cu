@@ -102,10 +102,11 @@ __device__ __forceinline__ u64 hs_hash(u64 k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return k;
 }
-// returns true when the key was not in the set (and inserts it)
-__device__ __forceinline__ bool hs_insert(u64 *tab, u64 mask, u64 key) {
+// returns true when the key was not in the set (and inserts it).  The probe is bounded by the table size: a full table
+// raises *full instead of spinning (the host sizes the tables so that this cannot happen; it is the safety net).
+__device__ __forceinline__ bool hs_insert(u64 *tab, u64 mask, u64 key, u32 *full) {
     u64 s = hs_hash(key) & mask;
-    while (true) {
+    for (u64 probe = 0; probe <= mask; ++probe) {
         u64 cur = tab[s];
         if (cur == key) return false;
         if (cur == HS_EMPTY) {
@@ -115,6 +116,8 @@ __device__ __forceinline__ bool hs_insert(u64 *tab, u64 mask, u64 key) {
         }
         s = (s + 1) & mask;
     }
+    atomicOr(full, FQ_ERR_TABLE);
+    return false;
 }
 
 // sorted records: the first of every (key, tag) run is this window's earliest occurrence; it survives iff the key was
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) k_fq_mark(FqParams p, const RadixPlan *pl
         if (first) {
             const u64 key = (u64)a.x | ((u64)a.y << 32);
             if (key == HS_EMPTY) keep = atomicExch(&st->allones_seen[a.w], 1u) == 0u;      // poly-G key: the table's empty marker
-            else { keep = hs_insert(p.hset[a.w], p.hmask[a.w], key); if (keep) atomicAdd(&st->inserted[a.w], 1u); }
+            else { keep = hs_insert(p.hset[a.w], p.hmask[a.w], key, &st->err); if (keep) atomicAdd(&st->inserted[a.w], 1u); }
         }
         if (keep) { p.cls[a.z] |= 8u; ++n_uniq; } else ++n_dup;
     }
@@ -141,10 +144,10 @@ __global__ void __launch_bounds__(256) k_fq_mark(FqParams p, const RadixPlan *pl
     if ((threadIdx.x & 31) == 0) { if (n_uniq) atomicAdd(&st->uniq, (unsigned long long)n_uniq); if (n_dup) atomicAdd(&st->dup, (unsigned long long)n_dup); }
 }
 
-__global__ void k_hs_rehash(const u64 *old_tab, u64 old_slots, u64 *new_tab, u64 new_mask) {
+__global__ void k_hs_rehash(const u64 *old_tab, u64 old_slots, u64 *new_tab, u64 new_mask, u32 *err) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < old_slots; i += (u64)gridDim.x * blockDim.x) {
         u64 k = old_tab[i];
-        if (k != HS_EMPTY) hs_insert(new_tab, new_mask, k);
+        if (k != HS_EMPTY) hs_insert(new_tab, new_mask, k, err);
     }
 }
 
@@ -266,7 +269,7 @@ static int hs_alloc(DedupCtx *c, int which, u64 slots) {
     MK_TRY(nb.alloc(slots * 8));
     MK_CUDA(cudaMemsetAsync(nb.p, 0xFF, slots * 8, c->s));
     if (c->d_hset[which].p && c->hcount[which]) {
-        k_hs_rehash<<<c->sms * 8, 256, 0, c->s>>>(c->d_hset[which].as<u64>(), c->hslots[which], nb.as<u64>(), slots - 1);
+        k_hs_rehash<<<c->sms * 8, 256, 0, c->s>>>(c->d_hset[which].as<u64>(), c->hslots[which], nb.as<u64>(), slots - 1, &c->d_state.as<FqState>()->err);
         c->launches_generic += 1;
     }
     MK_CUDA(cudaStreamSynchronize(c->s));
@@ -333,10 +336,11 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     cudaStream_t s = c->s;
     const bool trace = getenv("MICROCKET_TRACE") != nullptr;
     const double t0 = dd_now();
-    // the window can insert at most one key per pair: keep the table at most ~60 % full
+    // the window can insert at most one key per pair into EITHER set (tag 1 = lower-case first key base, e.g. soft-masked
+    // reads: every pair of such a file lands there): keep both tables at most ~60 % full for the same bound
     const u64 bound = n / 40 + 16;                       // a pair of records needs at least 8 newlines + ids + bases
     for (int w = 0; w < 2; ++w) {
-        u64 need = c->hcount[w] + (w == 0 ? bound : std::min<u64>(bound, 1 << 14));
+        u64 need = c->hcount[w] + bound;
         u64 slots = c->hslots[w];
         while (need * 10 > slots * 6) slots *= 2;
         if (slots != c->hslots[w]) MK_TRY(hs_alloc(c, w, slots));
@@ -377,6 +381,7 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     MK_CUDA(cudaMemcpyAsync(&hst, c->d_state.p, sizeof hst, cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
     if (hst.err & FQ_ERR_OUT) { mk_set_error("krmdup: output buffer too small"); return MK_ERR_CAPACITY; }
+    if (hst.err & FQ_ERR_TABLE) { mk_set_error("krmdup: key set full (device hash table)"); return MK_ERR_CAPACITY; }
     const double t2 = dd_now();
     c->hcount[0] += hst.inserted[0]; c->hcount[1] += hst.inserted[1];
     MK_CUDA(cudaMemsetAsync((char *)c->d_state.p + offsetof(FqState, inserted), 0, 8, s));

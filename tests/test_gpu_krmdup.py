@@ -74,3 +74,15 @@ def test_degenerate_inputs(oracle):
 def test_bad_key_sizes_are_rejected():
     with pytest.raises(mk.MkError):
         mk.Krmdup(5, 20, 5, 20)          # krmdup.cpp:259-262
+
+
+def test_all_lowercase_reads_fill_the_second_key_set(oracle):
+    """Soft-masked / lower-cased reads: every key lands in the T bucket's set (tag 1).  200 k pairs in one window used to
+    overflow that set's table (sized for 2^14 new keys per window) and spin forever; it is sized like the main one now
+    and the probe is bounded."""
+    fq = mk.synth_host(36, "fastq", "hg38", 0, 200000)
+    low = fq.lower().replace(b"@sim", b"@SIM")
+    o1, o2, ost = oracle.krmdup(low)
+    r1, r2, st = gpu_krmdup(low)
+    assert r1 == o1 and r2 == o2 and st.log_text() == ost.log_text()
+    assert st.uniq > 100000
