@@ -168,6 +168,17 @@ int  mk_pairs_dedup_bin_device(mk_pairs_ws *, mk_pair *d_pairs, size_t n,
                                const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map,
                                uint32_t res, uint16_t max_lane, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
                                size_t *n_kept, size_t *nnz, void *stream);
+/* The same call, also reporting WHICH input pairs survive (what a deduplicated .pairs file needs, SURVEY.md §8a D3: the
+ * first occurrence in input order wins, like the reference's unordered_set probe, krmdup.cpp:201-212):
+ *   d_keep      n bytes (device, may be NULL): keep[i] = 1 iff input pair i is the first of its key
+ *   d_kept_idx  n x u32 (device, may be NULL): input index of every kept pair, in the key order of the kept pairs
+ * Pairs that cannot be keyed (chromosome id outside the table, position past the chromosome end, lane > max_lane) are
+ * left out of both outputs and counted: mk_pairs_dropped() returns the count of the last call. */
+int  mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *, mk_pair *d_pairs, size_t n,
+                               const uint32_t *chrom_len, int n_chrom, const uint16_t *chrom_id_map, int n_map,
+                               uint32_t res, uint16_t max_lane, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                               uint8_t *d_keep, uint32_t *d_kept_idx, size_t *n_kept, size_t *nnz, void *stream);
+uint64_t mk_pairs_dropped(mk_pairs_ws *);
 /* Multi-GPU: group pairs by owner rank = mix(chr1, chr2, pos1 / res) mod world into d_out (segments in rank order;
  * counts[r] pairs for rank r).  The caller moves the segments with an all-to-all (NCCL via torch.distributed in
  * bench.py); afterwards equal keys and equal (bin1,bin2) cells at `res` are on one rank. */
@@ -188,6 +199,22 @@ int  mk_synth_host(uint64_t seed, int mode, int genome, uint64_t first, uint64_t
                    char *buf, size_t cap, size_t *n_out);
 int  mk_synth_device(int device, uint64_t seed, int mode, int genome, uint64_t first, uint64_t count,
                      char *d_buf, size_t cap, size_t *n_out, void *stream);
+
+/* The same generators with the workload mixture exposed (BASELINE configs[2..4]): per-1024 weights, -1 =
+ * default.  dup_per_1024 > 0: a read group (or FASTQ pair) re-uses the fragment of group `hash % dup_universe` — a PCR
+ * duplicate with its own read id; set dup_universe to the job's total group count so duplicates cross shards. */
+typedef struct {
+    int      dup_per_1024;
+    uint64_t dup_universe;
+    int      chimeric_per_1024;    /* groups with a split alignment (default: unc 256, flash 358) */
+    int      noise_per_1024;       /* low MAPQ / unmapped / secondary / odd clips / introns (default 51) */
+    int      selfcircle_per_1024;  /* default 5 */
+} mk_synth_opts;
+void mk_synth_default_opts(mk_synth_opts *);
+int  mk_synth_host_ex(uint64_t seed, int mode, int genome, const mk_synth_opts *, uint64_t first, uint64_t count,
+                      char *buf, size_t cap, size_t *n_out);
+int  mk_synth_device_ex(int device, uint64_t seed, int mode, int genome, const mk_synth_opts *, uint64_t first, uint64_t count,
+                        char *d_buf, size_t cap, size_t *n_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,15 @@ class S2PDevIO(C.Structure):
                 ("pairs_text_len", C.c_size_t), ("n_pairs", C.c_size_t), ("sam_text_len", C.c_size_t), ("consumed", C.c_size_t)]
 
 
+class SynthOpts(C.Structure):
+    _fields_ = [("dup_per_1024", C.c_int), ("dup_universe", C.c_uint64), ("chimeric_per_1024", C.c_int),
+                ("noise_per_1024", C.c_int), ("selfcircle_per_1024", C.c_int)]
+
+
+def synth_opts(dup_per_1024=0, dup_universe=0, chimeric_per_1024=-1, noise_per_1024=-1, selfcircle_per_1024=-1):
+    return SynthOpts(dup_per_1024, dup_universe, chimeric_per_1024, noise_per_1024, selfcircle_per_1024)
+
+
 class DedupCfg(C.Structure):
     _fields_ = [("hskip1", C.c_int), ("klen1", C.c_int), ("hskip2", C.c_int), ("klen2", C.c_int), ("device", C.c_int),
                 ("window_bytes", C.c_size_t)]
@@ -101,6 +110,8 @@ class Lib:
         L.mk_launch_count.restype = u64
         L.mk_synth_host.argtypes = [u64, i, i, u64, u64, vp, sz, P(sz)]
         L.mk_synth_device.argtypes = [i, u64, i, i, u64, u64, vp, sz, P(sz), vp]
+        L.mk_synth_host_ex.argtypes = [u64, i, i, P(SynthOpts), u64, u64, vp, sz, P(sz)]
+        L.mk_synth_device_ex.argtypes = [i, u64, i, i, P(SynthOpts), u64, u64, vp, sz, P(sz), vp]
         for name, args in (("mk_dedup_default_cfg", [P(DedupCfg)]), ("mk_dedup_create", [P(DedupCfg), P(vp)]),
                            ("mk_dedup_push", [vp, C.c_char_p, sz, i]), ("mk_dedup_pull", [vp, vp, sz, P(sz), vp, sz, P(sz)]),
                            ("mk_dedup_finish", [vp, P(DedupStats)]),
@@ -111,6 +122,8 @@ class Lib:
                            ("mk_pairs_dedup_bin_host", [vp, vp, sz, i, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, vp, vp, vp, sz, P(sz), P(sz)]),
                            ("mk_s2p_enable_timing", [vp, i]), ("mk_s2p_kernel_times", [vp, P(C.c_double), P(u64)]),
                            ("mk_pairs_dedup_bin_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, C.c_uint16, vp, vp, vp, sz, P(sz), P(sz), vp]),
+                           ("mk_pairs_dedup_bin_indexed_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, C.c_uint16, vp, vp, vp, sz, vp, vp, P(sz), P(sz), vp]),
+                           ("mk_pairs_dropped", [vp]),
                            ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
@@ -120,6 +133,8 @@ class Lib:
             L.mk_pairs_owner.restype = C.c_uint32
         if hasattr(L, "mk_pairs_launch_count"):
             L.mk_pairs_launch_count.restype = u64
+        if hasattr(L, "mk_pairs_dropped"):
+            L.mk_pairs_dropped.restype = u64
 
     def check(self, rc):
         if rc != 0:
@@ -373,17 +388,22 @@ class PairsWorkspace:
     def launches(self):
         return self.lib.L.mk_pairs_launch_count(self.h)
 
-    def dedup_bin(self, d_pairs, n, chrom_len, res, d_bin1, d_bin2, d_cnt, cap, chrom_id_map=None, max_lane=0, stream=0):
-        """One-sort duplicate removal + binning → (n_kept, nnz)"""
+    def dedup_bin(self, d_pairs, n, chrom_len, res, d_bin1, d_bin2, d_cnt, cap, chrom_id_map=None, max_lane=0, stream=0,
+                  d_keep=0, d_kept_idx=0):
+        """One-sort duplicate removal + binning → (n_kept, nnz); d_keep / d_kept_idx: which input pairs survive"""
         cl = (C.c_uint32 * len(chrom_len))(*chrom_len)
         if chrom_id_map is not None:
             mp = (C.c_uint16 * len(chrom_id_map))(*chrom_id_map); nm = len(chrom_id_map)
         else:
             mp, nm = None, 0
         kept, nnz = C.c_size_t(), C.c_size_t()
-        self.lib.check(self.lib.L.mk_pairs_dedup_bin_device(self.h, d_pairs, n, cl, len(chrom_len), mp, nm, res, max_lane,
-                                                            d_bin1, d_bin2, d_cnt, cap, C.byref(kept), C.byref(nnz), stream))
+        self.lib.check(self.lib.L.mk_pairs_dedup_bin_indexed_device(self.h, d_pairs, n, cl, len(chrom_len), mp, nm, res, max_lane,
+                                                                    d_bin1, d_bin2, d_cnt, cap, d_keep, d_kept_idx,
+                                                                    C.byref(kept), C.byref(nnz), stream))
         return kept.value, nnz.value
+
+    def dropped(self):
+        return self.lib.L.mk_pairs_dropped(self.h)
 
     def partition(self, d_pairs, n, world, res, d_out, stream=0):
         counts = (C.c_uint64 * world)()
@@ -402,13 +422,27 @@ class PairsWorkspace:
         return kept.value, nnz.value
 
 
-def synth_host(seed, mode, genome, first, count) -> bytes:
+def synth_host(seed, mode, genome, first, count, opts=None) -> bytes:
     """Synthetic SAM ('flash'/'unc') or interleaved FASTQ ('fastq') for groups/pairs [first, first+count) — host side."""
     m = {"flash": 0, "unc": 1, "fastq": 2}[mode]
     g = {"hg38": 0, "mm10": 1}[genome]
     L = lib()
     n = C.c_size_t()
-    L.check(L.L.mk_synth_host(seed, m, g, first, count, None, 0, C.byref(n)))
+    o = C.byref(opts) if opts is not None else None
+    L.check(L.L.mk_synth_host_ex(seed, m, g, o, first, count, None, 0, C.byref(n)))
     buf = C.create_string_buffer(n.value + 16)
-    L.check(L.L.mk_synth_host(seed, m, g, first, count, C.addressof(buf), n.value, C.byref(n)))
+    L.check(L.L.mk_synth_host_ex(seed, m, g, o, first, count, C.addressof(buf), n.value, C.byref(n)))
     return buf.raw[:n.value]
+
+
+def synth_device(torch, seed, mode, genome, first, count, device=0, opts=None):
+    """The same bytes generated on the GPU → (uint8 cuda tensor, n_bytes); the tensor has 64 spare bytes behind the text."""
+    m = {"flash": 0, "unc": 1, "fastq": 2}[mode]
+    g = {"hg38": 0, "mm10": 1}[genome]
+    L = lib()
+    n = C.c_size_t()
+    o = C.byref(opts) if opts is not None else None
+    L.check(L.L.mk_synth_device_ex(device, seed, m, g, o, first, count, None, 0, C.byref(n), None))
+    buf = torch.empty(n.value + 64, dtype=torch.uint8, device=f"cuda:{device}")
+    L.check(L.L.mk_synth_device_ex(device, seed, m, g, o, first, count, buf.data_ptr(), n.value, C.byref(n), None))
+    return buf, n.value

@@ -118,8 +118,15 @@ __global__ void __launch_bounds__(UQ_T) k_rle_heads(const u64 *k0, const u64 *k1
     }
 }
 
-__global__ void k_rle_finish(const u64 *key, const u32 *pos, const unsigned long long *nnz_p, u64 n, u64 cap,
+// the run of sentinel keys (pairs that failed validation), if any, is the last one: it is not a cell
+__global__ void k_rle_trim(const u64 *key, const u32 *pos, unsigned long long *counters /* [0] runs -> cells, [2] <- valid elements */, u64 n, u64 cap) {
+    const u64 runs = counters[0];
+    counters[2] = n;
+    if (runs && runs <= cap && key[runs - 1] == 0xFFFFFFFFFFFFFFFFull) { counters[0] = runs - 1; counters[2] = pos[runs - 1]; }
+}
+__global__ void k_rle_finish(const u64 *key, const u32 *pos, const unsigned long long *nnz_p, u64 n_unused, u64 cap,
                              u32 *bin1, u32 *bin2, u32 *cnt) {
+    const u64 n = nnz_p[2];
     const u64 nnz = *nnz_p < cap ? *nnz_p : cap;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) {
         u64 k = key[i];
@@ -130,15 +137,30 @@ __global__ void k_rle_finish(const u64 *key, const u32 *pos, const unsigned long
     }
 }
 
-// (bin1,bin2) key of every pair at one resolution
-__global__ void k_bin_keys(const mk_pair *p, u64 n, const u32 *chr_off /* per pair-chr id */, u32 res, u64 *key) {
+// (bin1,bin2) key of every pair at one resolution.  Every field is checked (chromosome id inside the table, position inside
+// the chromosome's bins): an offender is counted in *bad, the host turns that into MK_ERR_INPUT, and its key is the all-ones
+// sentinel (sorted last, dropped by the run-length step) so that nothing is read or counted out of range.
+#define BIN_BAD_KEY 0xFFFFFFFFFFFFFFFFull
+__global__ void k_bin_keys(const mk_pair *p, u64 n, const u32 *chr_off /* per pair-chr id */, const u32 *chr_nb /* bins per id */, u32 n_ids,
+                           u32 res, u64 *key, unsigned long long *bad) {
+    u32 nbad = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const uint4 r = ((const uint4 *)p)[i];
         const u32 pos1 = r.x, pos2 = r.y, c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
-        u32 a = chr_off[c1] + pos1 / res, b = chr_off[c2] + pos2 / res;
-        if (a > b) { u32 t = a; a = b; b = t; }                 // upper triangle
-        key[i] = ((u64)a << 32) | b;
+        u64 k = BIN_BAD_KEY;
+        if (c1 < n_ids && c2 < n_ids) {
+            const u32 q1 = pos1 / res, q2 = pos2 / res;
+            if (q1 < chr_nb[c1] && q2 < chr_nb[c2]) {
+                u32 a = chr_off[c1] + q1, b = chr_off[c2] + q2;
+                if (a > b) { u32 t = a; a = b; b = t; }          // upper triangle
+                k = ((u64)a << 32) | b;
+            }
+        }
+        nbad += k == BIN_BAD_KEY;
+        key[i] = k;
     }
+    nbad = __reduce_add_sync(0xffffffffu, nbad);
+    if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
@@ -152,6 +174,7 @@ struct mk_pairs_ws {
     DevBuf desc, counter, chr_off;
     DevBuf h_pairs, h_b1, h_b2, h_c;   // device staging of the host-buffer API, allocated on first use
     u64 launches = 0;
+    u64 dropped = 0;     // pairs the last dedup / binning call left out (unknown chromosome id, position past the chromosome end, lane > max_lane)
 };
 
 extern "C" int mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **out) {
@@ -168,13 +191,15 @@ extern "C" int mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **ou
     if (rc == MK_OK) rc = w->heads_pos.alloc(max_pairs * 4);
     if (rc == MK_OK) rc = w->desc.alloc((max_pairs / (UQ_T * UQ_ITEMS) + 4) * 8 + 2048);
     if (rc == MK_OK) rc = w->counter.alloc(64);
-    if (rc == MK_OK) rc = w->chr_off.alloc(65536 * 4 + 16384 * 8);
+    if (rc == MK_OK) rc = w->chr_off.alloc(65536 * 8 + 16384 * 8);
+    if (rc == MK_OK && cudaMemset(w->chr_off.p, 0, w->chr_off.n) != cudaSuccess) rc = MK_ERR_CUDA;
     if (rc != MK_OK) { delete w; return rc; }
     *out = w;
     return MK_OK;
 }
 extern "C" void mk_pairs_ws_destroy(mk_pairs_ws *w) { if (w) { cudaSetDevice(w->device); delete w; } }
 extern "C" uint64_t mk_pairs_launch_count(mk_pairs_ws *w) { return w ? w->launches : 0; }
+extern "C" uint64_t mk_pairs_dropped(mk_pairs_ws *w) { return w ? w->dropped : 0; }
 
 static int lookback_grid(const void *kernel, int threads, int sms) {
     int occ = 1;
@@ -226,15 +251,17 @@ extern "C" int mk_pairs_bin_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_
     if (off[n_chrom] >= (1ull << 32)) { mk_set_error("mk_pairs_bin_device: more than 2^32 bins"); return MK_ERR_CAPACITY; }
     const int n_ids = chrom_id_map ? n_map : n_chrom;
     if (n_ids > 65536) { mk_set_error("mk_pairs_bin_device: too many chromosome ids"); return MK_ERR_ARG; }
-    std::vector<u32> by_id(n_ids);
+    std::vector<u32> by_id(2 * (size_t)n_ids);                          // [offsets | bins per id], one upload
     for (int i = 0; i < n_ids; ++i) {
         int c = chrom_id_map ? chrom_id_map[i] : i;
         if (c < 0 || c >= n_chrom) { mk_set_error("mk_pairs_bin_device: chromosome map entry %d out of range", i); return MK_ERR_ARG; }
-        by_id[i] = (u32)off[c];
+        by_id[i] = (u32)off[c]; by_id[n_ids + i] = chrom_len[c] / res + 1;
     }
-    MK_CUDA(cudaMemcpyAsync(w->chr_off.p, by_id.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice, s));
+    MK_CUDA(cudaMemcpyAsync(w->chr_off.p, by_id.data(), by_id.size() * 4, cudaMemcpyHostToDevice, s));
+    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
+    unsigned long long *cnt = w->counter.as<unsigned long long>();
     u64 *k0 = w->alt.as<u64>(), *k1 = w->keys2.as<u64>();
-    k_bin_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, w->chr_off.as<u32>(), res, k0);
+    k_bin_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, w->chr_off.as<u32>(), w->chr_off.as<u32>() + n_ids, (u32)n_ids, res, k0, cnt + 3);
     w->launches += 1;
     int nbytes = 1; while (nbytes < 4 && (off[n_chrom] >> (8 * nbytes))) ++nbytes;
     RadixSchedule sch; sch.n_pass = 0;
@@ -244,16 +271,16 @@ extern "C" int mk_pairs_bin_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_
     MK_TRY(radix_sort<K64>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
     MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
-    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
-    unsigned long long *cnt = w->counter.as<unsigned long long>();
     k_rle_heads<<<lookback_grid((const void *)k_rle_heads, UQ_T, w->sms), UQ_T, 0, s>>>(
         k0, k1, w->rws.plan.as<RadixPlan>(), n, w->heads_key.as<u64>(), w->heads_pos.as<u32>(), w->max_pairs, w->desc.as<u64>(), cnt);
+    k_rle_trim<<<1, 1, 0, s>>>(w->heads_key.as<u64>(), w->heads_pos.as<u32>(), cnt, n, w->max_pairs);
     k_rle_finish<<<w->sms * 4, 256, 0, s>>>(w->heads_key.as<u64>(), w->heads_pos.as<u32>(), cnt, n, cap, d_bin1, d_bin2, d_cnt);
-    w->launches += 2;
-    unsigned long long h = 0;
-    MK_CUDA(cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, s));
+    w->launches += 3;
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    MK_CUDA(cudaMemcpyAsync(hc, cnt, 32, cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
-    *nnz = (size_t)h;
+    const unsigned long long h = hc[0];
+    *nnz = (size_t)h; w->dropped = hc[3];
     if (h > cap) { mk_set_error("mk_pairs_bin_device: %llu non-zero cells, output capacity %zu", h, cap); return MK_ERR_CAPACITY; }
     return MK_OK;
 }
@@ -359,25 +386,32 @@ __global__ void __launch_bounds__(256) k_owner_scatter(const mk_pair *p, u64 n, 
     }
 }
 
+// counts -> start offsets of the segments (exclusive prefix), in place behind the counts
+__global__ void k_owner_prefix(unsigned long long *dc, u32 world) {
+    unsigned long long run = 0;
+    for (u32 r = 0; r < world; ++r) { dc[64 + r] = run; run += dc[r]; }
+}
+
 // Groups `n` pairs by owner rank into d_out (contiguous segments in rank order); counts[r] = pairs destined to rank r.
+// Count, prefix and scatter are enqueued back to back; the only host round trip is the read-back of the counts.
 extern "C" int mk_pairs_partition_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_t n, int world, uint32_t res, mk_pair *d_out,
                                          uint64_t *counts, void *stream) {
-    if (!w || !counts || world < 1 || world > 64 || res == 0) { mk_set_error("mk_pairs_partition_device: bad argument"); return MK_ERR_ARG; }
+    if (!w || !counts || world < 1 || world > 64 || res == 0 || (n && (!d_pairs || !d_out))) { mk_set_error("mk_pairs_partition_device: bad argument"); return MK_ERR_ARG; }
+    if (n > w->max_pairs) { mk_set_error("mk_pairs_partition_device: workspace holds %zu pairs, got %zu", w->max_pairs, n); return MK_ERR_CAPACITY; }
     MK_CUDA(cudaSetDevice(w->device));
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long *dc = w->counter.as<unsigned long long>();        // 64 bytes... use the descriptor buffer for 2 x 64 counters
-    dc = (unsigned long long *)w->desc.p;
+    unsigned long long *dc = (unsigned long long *)w->desc.p;           // 2 x 64 counters: counts, then cursors
     MK_CUDA(cudaMemsetAsync(dc, 0, 128 * 8, s));
-    if (n) k_owner_count<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, (u32)world, res, dc);
+    if (n) {
+        k_owner_count<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, (u32)world, res, dc);
+        k_owner_prefix<<<1, 1, 0, s>>>(dc, (u32)world);
+    }
     unsigned long long h[64];
     MK_CUDA(cudaMemcpyAsync(h, dc, (size_t)world * 8, cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaStreamSynchronize(s));
-    unsigned long long off[64], run = 0;
-    for (int r = 0; r < world; ++r) { counts[r] = h[r]; off[r] = run; run += h[r]; }
-    MK_CUDA(cudaMemcpyAsync(dc + 64, off, (size_t)world * 8, cudaMemcpyHostToDevice, s));
     if (n) k_owner_scatter<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, (u32)world, res, dc + 64, d_out);
-    w->launches += 2;
+    w->launches += n ? 3 : 0;
     MK_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < world; ++r) counts[r] = h[r];
     return MK_OK;
 }
 
@@ -387,13 +421,18 @@ extern "C" uint32_t mk_pairs_owner(uint32_t chr1, uint32_t chr2, uint32_t pos1, 
 
 // ------------------------------------------------------------------------------------------------ fused dedup + binning
 // One sort serves both steps.  Every pair becomes a tightly packed integer, most significant field first:
-//   [ bin1 : nb ][ bin2 : nb ][ lane : nl ][ pos1 % res : nr ][ pos2 % res : nr ][ swapped : 1 ][ strands : 2 ]
-// Equal pairs are equal integers (duplicate removal = adjacent unique) and all pairs of one (bin1,bin2) cell are
-// contiguous (binning = run-length encoding of the top 2*nb bits), in ceil(bits/8) radix passes instead of the
-// 11 + 6 of the two separate sorts.  The packing is invertible, so the kept pairs are decoded back into mk_pair.
-struct PackCfg { u32 res, nb, nr, nl, total_bits, n_dec; };
+//   [ bin1 : nb ][ bin2 : nb ][ lane : nl ][ pos1 % res : nr ][ pos2 % res : nr ][ swapped : 1 ][ strands : 2 ]   (<= 96 bits)
+// with the pair's INPUT INDEX in bits 96..127 of the 16-byte record, which the sort never looks at.  Equal pairs are equal
+// integers (duplicate removal = adjacent unique) and all pairs of one (bin1,bin2) cell are contiguous (binning = run-length
+// encoding of the top 2*nb bits), in ceil(bits/8) radix passes instead of the 11 + 6 of the two separate sorts.  The sort
+// is stable, so the head of every run is the pair that came FIRST in the input — the occurrence the reference's
+// unordered_set keeps (src/preprocess/krmdup.cpp:201-212) — and its index says which emitted .pairs line survives.
+// The packing is invertible, so the kept pairs are decoded back into mk_pair.
+// A pair that cannot be keyed (chromosome id outside the table, position past the chromosome's last bin, lane > max_lane)
+// gets the all-ones key: it sorts last, is dropped from both outputs and is counted (mk_pairs_dropped).
+struct PackCfg { u32 res, nb, nr, nl, total_bits, n_dec, n_ids, max_lane; };
 
-__device__ __forceinline__ void put_bits(u64 &lo, u64 &hi, u64 v, u32 width) {      // key = (key << width) | v
+__device__ __forceinline__ void put_bits(u64 &lo, u64 &hi, u64 v, u32 width) {      // key = (key << width) | v;  v < 2^width
     hi = width >= 64 ? lo << (width - 64) : (width ? (hi << width) | (lo >> (64 - width)) : hi);
     lo = width >= 64 ? 0 : lo << width;
     lo |= v;
@@ -405,25 +444,38 @@ __device__ __forceinline__ u64 take_bits(u64 &lo, u64 &hi, u32 width) {         
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, const u32 *off_by_id, PackCfg c, uint4 *key) {
+__global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, const u32 *off_by_id, const u32 *nb_by_id, PackCfg c, uint4 *key,
+                                                   unsigned long long *bad) {
+    u32 nbad = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const uint4 r = ((const uint4 *)p)[i];
         u32 pos1 = r.x, pos2 = r.y; const u32 c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
         u32 st = r.w & 3u; const u32 lane = r.w >> 16;
-        u32 q1 = pos1 / c.res, q2 = pos2 / c.res;
-        u32 a = off_by_id[c1] + q1, b = off_by_id[c2] + q2;
-        u32 r1 = pos1 - q1 * c.res, r2 = pos2 - q2 * c.res;
-        u32 sw = 0;
-        if (a > b) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); sw = 1; }
-        u64 lo = 0, hi = 0;
-        put_bits(lo, hi, a, c.nb); put_bits(lo, hi, b, c.nb); put_bits(lo, hi, lane, c.nl);
-        put_bits(lo, hi, r1, c.nr); put_bits(lo, hi, r2, c.nr); put_bits(lo, hi, sw, 1); put_bits(lo, hi, st, 2);
-        key[i] = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+        uint4 k = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, (u32)i);
+        bool ok = c1 < c.n_ids && c2 < c.n_ids && lane <= c.max_lane;
+        if (ok) {
+            const u32 q1 = pos1 / c.res, q2 = pos2 / c.res;
+            ok = q1 < nb_by_id[c1] && q2 < nb_by_id[c2];
+            if (ok) {
+                u32 a = off_by_id[c1] + q1, b = off_by_id[c2] + q2;
+                u32 r1 = pos1 - q1 * c.res, r2 = pos2 - q2 * c.res;
+                u32 sw = 0;
+                if (a > b) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); sw = 1; }
+                u64 lo = 0, hi = 0;
+                put_bits(lo, hi, a, c.nb); put_bits(lo, hi, b, c.nb); put_bits(lo, hi, lane, c.nl);
+                put_bits(lo, hi, r1, c.nr); put_bits(lo, hi, r2, c.nr); put_bits(lo, hi, sw, 1); put_bits(lo, hi, st, 2);
+                k.x = (u32)lo; k.y = (u32)(lo >> 32); k.z = (u32)hi;
+            }
+        }
+        nbad += !ok;
+        key[i] = k;
     }
+    nbad = __reduce_add_sync(0xffffffffu, nbad);
+    if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
 }
 
 __device__ __forceinline__ mk_pair unpack_key(uint4 k, const PackCfg &c, const u32 *dec_off, const u16 *dec_id) {
-    u64 lo = (u64)k.x | ((u64)k.y << 32), hi = (u64)k.z | ((u64)k.w << 32);
+    u64 lo = (u64)k.x | ((u64)k.y << 32), hi = (u64)k.z;
     u32 st = (u32)take_bits(lo, hi, 2); const u32 sw = (u32)take_bits(lo, hi, 1);
     u32 r2 = (u32)take_bits(lo, hi, c.nr), r1 = (u32)take_bits(lo, hi, c.nr);
     const u32 lane = (u32)take_bits(lo, hi, c.nl);
@@ -442,18 +494,26 @@ __device__ __forceinline__ mk_pair unpack_key(uint4 k, const PackCfg &c, const u
 }
 
 // sorted packed keys -> kept pairs (first of every run, decoded) + cell heads (bin1, bin2, rank of the cell's first kept pair)
+// + optionally keep[input index] = 1 and kept_idx[rank] = input index of every kept pair
 __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint4 *b1, const RadixPlan *plan, u64 n, PackCfg c,
                                                      const u32 *dec_off, const u16 *dec_id, mk_pair *out0, mk_pair *out1,
-                                                     u32 *cell_b1, u32 *cell_b2, u32 *cell_first, u64 cell_cap,
+                                                     u32 *cell_b1, u32 *cell_b2, u32 *cell_first, u64 cell_cap, u8 *keep, u32 *kept_idx,
                                                      u64 *desc, unsigned long long *counters /* [0] kept, [1] cells */, u32 *ticket) {
     __shared__ u32 s_w[2][UQ_T / 32];
     __shared__ u64 s_base;
+    __shared__ u32 s_tile;
     const uint4 *in = plan->final_buf ? b1 : b0;
     mk_pair *out = plan->final_buf ? out0 : out1;                 // the buffer the sorted keys are NOT in
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
     const u32 cell_shift = c.total_bits - 2 * c.nb;               // bits below the (bin1,bin2) prefix
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {   // round-robin over a resident grid (tickets measured slower)
+    while (true) {
+        // tiles are claimed with a ticket: a tile's predecessors are then always owned by CTAs that are already running, so the
+        // look-back cannot wait on a CTA that was never scheduled (other streams may share the device)
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int tile = (int)s_tile;
+        if (tile >= n_tiles) break;
         const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
         uint4 r[UQ_ITEMS]; u32 fk = 0, fc = 0, nk = 0, nc = 0;
         uint4 prev = base > 0 && base <= n ? in[base - 1] : make_uint4(0, 0, 0, 0);
@@ -462,11 +522,11 @@ __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint
             if (base + k < n) {
                 r[k] = in[base + k];
                 const bool first = base + k == 0;
-                const bool dk = first || r[k].x != prev.x || r[k].y != prev.y || r[k].z != prev.z || r[k].w != prev.w;
+                const bool dk = first || r[k].x != prev.x || r[k].y != prev.y || r[k].z != prev.z;   // .w is the input index
                 bool dc = first;
                 if (!first && dk) {
-                    u64 lo = (u64)r[k].x | ((u64)r[k].y << 32), hi = (u64)r[k].z | ((u64)r[k].w << 32);
-                    u64 plo = (u64)prev.x | ((u64)prev.y << 32), phi = (u64)prev.z | ((u64)prev.w << 32);
+                    u64 lo = (u64)r[k].x | ((u64)r[k].y << 32), hi = (u64)r[k].z;
+                    u64 plo = (u64)prev.x | ((u64)prev.y << 32), phi = (u64)prev.z;
                     take_bits(lo, hi, cell_shift); take_bits(plo, phi, cell_shift);
                     dc = lo != plo || hi != phi;
                 }
@@ -492,16 +552,33 @@ __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint
         for (int k = 0; k < UQ_ITEMS; ++k) {
             if (fc & (1u << k)) {
                 if (oc < cell_cap) {
-                    u64 lo = (u64)r[k].x | ((u64)r[k].y << 32), hi = (u64)r[k].z | ((u64)r[k].w << 32);
+                    u64 lo = (u64)r[k].x | ((u64)r[k].y << 32), hi = (u64)r[k].z;
                     take_bits(lo, hi, cell_shift);
                     const u32 bb = (u32)take_bits(lo, hi, c.nb), aa = (u32)take_bits(lo, hi, c.nb);
                     cell_b1[oc] = aa; cell_b2[oc] = bb; cell_first[oc] = (u32)ok;
                 }
                 ++oc;
             }
-            if (fk & (1u << k)) { out[ok] = unpack_key(r[k], c, dec_off, dec_id); ++ok; }
+            if (fk & (1u << k)) {
+                out[ok] = unpack_key(r[k], c, dec_off, dec_id);
+                if (keep) keep[r[k].w] = 1;
+                if (kept_idx) kept_idx[ok] = r[k].w;
+                ++ok;
+            }
         }
-        __syncthreads();                                                // s_w / s_base are reused by the next tile
+        __syncthreads();                                                // s_w / s_base / s_tile are reused by the next tile
+    }
+}
+
+// pairs that could not be keyed form the last run (all-ones key): it is neither a kept pair nor a cell
+__global__ void k_uniq_trim(const uint4 *b0, const uint4 *b1, const RadixPlan *plan, u64 n, u8 *keep, unsigned long long *counters) {
+    const uint4 *in = plan->final_buf ? b1 : b0;
+    if (!counters[3]) return;
+    const u64 first_bad = n - counters[3];
+    const uint4 k = in[first_bad];
+    if (k.x == 0xFFFFFFFFu && k.y == 0xFFFFFFFFu && k.z == 0xFFFFFFFFu) {
+        counters[0] -= 1; counters[1] -= 1;
+        if (keep) keep[k.w] = 0;
     }
 }
 
@@ -511,42 +588,51 @@ __global__ void k_cell_counts(const u32 *cell_first, const unsigned long long *c
         cnt[i] = (i + 1 < counters[1] && i + 1 < cap ? cell_first[i + 1] : (u32)kept) - cell_first[i];
 }
 
+// decoded pairs landed in the sort's other buffer: bring them home when that is not the caller's
+__global__ void k_copy_if_alt(const RadixPlan *plan, const uint4 *alt, uint4 *home, const unsigned long long *counters) {
+    if (plan->final_buf != 1) return;                                  // keys ended in `home`'s twin: the pairs are already in `home`
+    const u64 n = counters[0];
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) home[i] = alt[i];
+}
+
 static u32 bits_for(u64 max_value) { u32 b = 1; while (b < 64 && (max_value >> b)) ++b; return b; }
 
-extern "C" int mk_pairs_dedup_bin_device(mk_pairs_ws *w, mk_pair *d_pairs, size_t n, const uint32_t *chrom_len, int n_chrom,
-                                         const uint16_t *chrom_id_map, int n_map, uint32_t res, uint16_t max_lane,
-                                         uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
-                                         size_t *n_kept, size_t *nnz, void *stream) {
+extern "C" int mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *w, mk_pair *d_pairs, size_t n, const uint32_t *chrom_len, int n_chrom,
+                                                 const uint16_t *chrom_id_map, int n_map, uint32_t res, uint16_t max_lane,
+                                                 uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                                                 uint8_t *d_keep, uint32_t *d_kept_idx, size_t *n_kept, size_t *nnz, void *stream) {
     if (!w || !n_kept || !nnz || !chrom_len || n_chrom <= 0 || res == 0 || !d_bin1 || !d_bin2 || !d_cnt) { mk_set_error("mk_pairs_dedup_bin_device: bad argument"); return MK_ERR_ARG; }
     if (n > w->max_pairs) { mk_set_error("mk_pairs_dedup_bin_device: workspace holds %zu pairs, got %zu", w->max_pairs, n); return MK_ERR_CAPACITY; }
     MK_CUDA(cudaSetDevice(w->device));
     cudaStream_t s = (cudaStream_t)stream;
-    *n_kept = 0; *nnz = 0;
+    *n_kept = 0; *nnz = 0; w->dropped = 0;
     if (n == 0) return MK_OK;
     std::vector<u64> off(n_chrom + 1, 0);
     for (int c = 0; c < n_chrom; ++c) off[c + 1] = off[c] + chrom_len[c] / res + 1;
     if (off[n_chrom] >= (1ull << 32)) { mk_set_error("mk_pairs_dedup_bin_device: more than 2^32 bins"); return MK_ERR_CAPACITY; }
     const int n_ids = chrom_id_map ? n_map : n_chrom;
     if (n_ids > 16384 || n_chrom > 16384) { mk_set_error("mk_pairs_dedup_bin_device: too many chromosomes"); return MK_ERR_ARG; }
-    std::vector<u32> by_id(n_ids), dec_off(n_chrom);
-    std::vector<u16> dec_id(n_chrom, 0xFFFF);
+    // one upload: [by_id offsets (16384 u32)] [bins per id (16384 u32)] [dec_off (16384 u32)] [dec_id (16384 u16)]
+    std::vector<u32> tab(3 * 16384 + 8192, 0);
+    u32 *by_id = tab.data(), *nb_id = by_id + 16384, *dec_off = nb_id + 16384; u16 *dec_id = (u16 *)(dec_off + 16384);
+    for (int c = 0; c < n_chrom; ++c) { dec_off[c] = (u32)off[c]; dec_id[c] = 0xFFFF; }
     for (int i = 0; i < n_ids; ++i) {
         int c = chrom_id_map ? chrom_id_map[i] : i;
         if (c < 0 || c >= n_chrom) { mk_set_error("mk_pairs_dedup_bin_device: chromosome map entry %d out of range", i); return MK_ERR_ARG; }
-        by_id[i] = (u32)off[c];
+        by_id[i] = (u32)off[c]; nb_id[i] = chrom_len[c] / res + 1;
         if (dec_id[c] == 0xFFFF) dec_id[c] = (u16)i;
     }
-    for (int c = 0; c < n_chrom; ++c) dec_off[c] = (u32)off[c];
-    PackCfg pc; pc.res = res; pc.nb = bits_for(off[n_chrom] - 1); pc.nr = bits_for(res - 1); pc.nl = max_lane ? bits_for(max_lane) : 0;
-    pc.total_bits = 2 * pc.nb + 2 * pc.nr + pc.nl + 3; pc.n_dec = (u32)n_chrom;
-    if (pc.total_bits > 128) { mk_set_error("mk_pairs_dedup_bin_device: key does not fit 128 bits"); return MK_ERR_CAPACITY; }
-    // small tables live in chr_off: [by_id (16384 u32)] [dec_off (16384 u32)] [dec_id (16384 u16)]
-    u32 *d_by_id = w->chr_off.as<u32>(), *d_dec_off = d_by_id + 16384; u16 *d_dec_id = (u16 *)(d_dec_off + 16384);
-    MK_CUDA(cudaMemcpyAsync(d_by_id, by_id.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice, s));
-    MK_CUDA(cudaMemcpyAsync(d_dec_off, dec_off.data(), (size_t)n_chrom * 4, cudaMemcpyHostToDevice, s));
-    MK_CUDA(cudaMemcpyAsync(d_dec_id, dec_id.data(), (size_t)n_chrom * 2, cudaMemcpyHostToDevice, s));
+    PackCfg pc; pc.res = res; pc.nb = bits_for(off[n_chrom]) /* one value past the last bin stays free for the all-ones key */;
+    pc.nr = bits_for(res - 1); pc.nl = max_lane ? bits_for(max_lane) : 0;
+    pc.total_bits = 2 * pc.nb + 2 * pc.nr + pc.nl + 3; pc.n_dec = (u32)n_chrom; pc.n_ids = (u32)n_ids; pc.max_lane = max_lane;
+    if (pc.total_bits > 96) { mk_set_error("mk_pairs_dedup_bin_device: key needs %u bits, 96 available", pc.total_bits); return MK_ERR_CAPACITY; }
+    u32 *d_by_id = w->chr_off.as<u32>(), *d_nb_id = d_by_id + 16384, *d_dec_off = d_nb_id + 16384; u16 *d_dec_id = (u16 *)(d_dec_off + 16384);
+    MK_CUDA(cudaMemcpyAsync(d_by_id, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));    // (pageable source: staged before the call returns)
+    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
+    unsigned long long *cnt = w->counter.as<unsigned long long>();
+    if (d_keep) MK_CUDA(cudaMemsetAsync(d_keep, 0, n, s));
     uint4 *k0 = w->alt.as<uint4>(), *k1 = (uint4 *)d_pairs;           // the pairs buffer doubles as the second sort buffer
-    k_pack_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, d_by_id, pc, k0);
+    k_pack_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, d_by_id, d_nb_id, pc, k0, cnt + 3);
     w->launches += 1;
     RadixSchedule sch; sch.n_pass = (int)((pc.total_bits + 7) / 8);
     for (int i = 0; i < sch.n_pass; ++i) sch.byte_of[i] = i;
@@ -554,21 +640,27 @@ extern "C" int mk_pairs_dedup_bin_device(mk_pairs_ws *w, mk_pair *d_pairs, size_
     MK_TRY(radix_sort<Rec16>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
     MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
-    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
-    unsigned long long *cnt = w->counter.as<unsigned long long>();
+    const RadixPlan *plan = w->rws.plan.as<RadixPlan>();
     k_uniq_cells<<<lookback_grid((const void *)k_uniq_cells, UQ_T, w->sms), UQ_T, 0, s>>>(
-        k0, k1, w->rws.plan.as<RadixPlan>(), n, pc, d_dec_off, d_dec_id, (mk_pair *)k0, (mk_pair *)k1,
-        d_bin1, d_bin2, w->heads_pos.as<u32>(), cap, w->desc.as<u64>(), cnt, (u32 *)(cnt + 4));
+        k0, k1, plan, n, pc, d_dec_off, d_dec_id, (mk_pair *)k0, (mk_pair *)k1,
+        d_bin1, d_bin2, w->heads_pos.as<u32>(), cap, d_keep, d_kept_idx, w->desc.as<u64>(), cnt, (u32 *)(cnt + 4));
+    k_uniq_trim<<<1, 1, 0, s>>>(k0, k1, plan, n, d_keep, cnt);
     k_cell_counts<<<w->sms * 4, 256, 0, s>>>(w->heads_pos.as<u32>(), cnt, cap, d_cnt);
-    w->launches += 2;
-    unsigned long long h[2]; u32 final_buf = 0;
-    MK_CUDA(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaMemcpyAsync(&final_buf, (char *)w->rws.plan.p + offsetof(RadixPlan, final_buf), 4, cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaStreamSynchronize(s));
     // sorted keys sat in buffer final_buf; the decoded pairs went to the other one
-    if (final_buf == 1) MK_CUDA(cudaMemcpyAsync(d_pairs, w->alt.p, (size_t)h[0] * 16, cudaMemcpyDeviceToDevice, s));
-    MK_CUDA(cudaStreamSynchronize(s));
-    *n_kept = (size_t)h[0]; *nnz = (size_t)h[1];
+    k_copy_if_alt<<<w->sms * 4, 256, 0, s>>>(plan, k0, k1, cnt);
+    w->launches += 4;
+    unsigned long long h[4];
+    MK_CUDA(cudaMemcpyAsync(h, cnt, 32, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));                                  // the one host round trip: the two result counts
+    *n_kept = (size_t)h[0]; *nnz = (size_t)h[1]; w->dropped = h[3];
     if (h[1] > cap) { mk_set_error("mk_pairs_dedup_bin_device: %llu non-zero cells, output capacity %zu", h[1], cap); return MK_ERR_CAPACITY; }
     return MK_OK;
+}
+
+extern "C" int mk_pairs_dedup_bin_device(mk_pairs_ws *w, mk_pair *d_pairs, size_t n, const uint32_t *chrom_len, int n_chrom,
+                                         const uint16_t *chrom_id_map, int n_map, uint32_t res, uint16_t max_lane,
+                                         uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                                         size_t *n_kept, size_t *nnz, void *stream) {
+    return mk_pairs_dedup_bin_indexed_device(w, d_pairs, n, chrom_len, n_chrom, chrom_id_map, n_map, res, max_lane, d_bin1, d_bin2, d_cnt, cap,
+                                             nullptr, nullptr, n_kept, nnz, stream);
 }

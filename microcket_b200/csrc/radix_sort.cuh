@@ -278,9 +278,9 @@ static int radix_sort(typename P::Bufs bufs, u64 n, const RadixSchedule &sch, Ra
     *launches += 2;
     const int TILE = RS_THREADS * P::ITEMS;
     const u64 tiles = (n + TILE - 1) / TILE;
-    static bool attr_set = false;
     const size_t smem = radix_pass_smem<P>();
-    if (!attr_set) { cudaFuncSetAttribute(k_radix_pass<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    // per device, not per process: set on every call (a cheap driver call; a static flag would leave a second device unset)
+    MK_CUDA(cudaFuncSetAttribute(k_radix_pass<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int p = 0; p < sch.n_pass && tiles; ++p) {
         MK_CUDA(cudaMemsetAsync(ws.desc.p, 0, tiles * 256 * 4, s));
         k_radix_pass<P><<<(unsigned)tiles, RS_THREADS, smem, s>>>(bufs, n, p, sch.byte_of[p], plan, ws.desc.as<u32>(), iota_vals);

@@ -46,13 +46,31 @@ __global__ void k_synth_write(mk_synth_cfg cfg, int mode, u64 first, u64 count, 
     }
 }
 
-static void synth_cfg(mk_synth_cfg *c, uint64_t seed, int mode, int genome) {
+static void synth_cfg(mk_synth_cfg *c, uint64_t seed, int mode, int genome, const mk_synth_opts *o = nullptr) {
     mk_synth_init(c, seed, mode == 0 ? 0 : 1, genome);
+    if (!o) return;
+    if (o->dup_per_1024 > 0) { c->sam_dup_per_1024 = o->dup_per_1024; c->sam_dup_universe = o->dup_universe; c->dup_per_1024 = o->dup_per_1024; }
+    if (o->chimeric_per_1024 >= 0) c->w_chimeric = o->chimeric_per_1024;
+    if (o->noise_per_1024 >= 0) c->w_noise = o->noise_per_1024;
+    if (o->selfcircle_per_1024 >= 0) c->w_selfcircle = o->selfcircle_per_1024;
 }
 
+extern "C" void mk_synth_default_opts(mk_synth_opts *o) {
+    if (!o) return;
+    o->dup_per_1024 = 0; o->dup_universe = 0; o->chimeric_per_1024 = -1; o->noise_per_1024 = -1; o->selfcircle_per_1024 = -1;
+}
 extern "C" int mk_synth_host(uint64_t seed, int mode, int genome, uint64_t first, uint64_t count, char *buf, size_t cap, size_t *n_out) {
+    return mk_synth_host_ex(seed, mode, genome, nullptr, first, count, buf, cap, n_out);
+}
+extern "C" int mk_synth_device(int device, uint64_t seed, int mode, int genome, uint64_t first, uint64_t count,
+                               char *d_buf, size_t cap, size_t *n_out, void *stream) {
+    return mk_synth_device_ex(device, seed, mode, genome, nullptr, first, count, d_buf, cap, n_out, stream);
+}
+
+extern "C" int mk_synth_host_ex(uint64_t seed, int mode, int genome, const mk_synth_opts *opts, uint64_t first, uint64_t count,
+                                char *buf, size_t cap, size_t *n_out) {
     if (mode < 0 || mode > 2 || !n_out) { mk_set_error("mk_synth_host: bad argument"); return MK_ERR_ARG; }
-    mk_synth_cfg c; synth_cfg(&c, seed, mode, genome);
+    mk_synth_cfg c; synth_cfg(&c, seed, mode, genome, opts);
     mk_sink w; w.p = nullptr; w.n = 0;
     for (uint64_t i = 0; i < count; ++i) { if (mode == 2) mk_gen_fastq_pair(&c, first + i, &w); else mk_gen_group(&c, first + i, &w); }
     size_t need = w.n;
@@ -64,12 +82,12 @@ extern "C" int mk_synth_host(uint64_t seed, int mode, int genome, uint64_t first
     return MK_OK;
 }
 
-extern "C" int mk_synth_device(int device, uint64_t seed, int mode, int genome, uint64_t first, uint64_t count,
-                               char *d_buf, size_t cap, size_t *n_out, void *stream) {
+extern "C" int mk_synth_device_ex(int device, uint64_t seed, int mode, int genome, const mk_synth_opts *opts, uint64_t first, uint64_t count,
+                                  char *d_buf, size_t cap, size_t *n_out, void *stream) {
     if (mode < 0 || mode > 2 || !n_out) { mk_set_error("mk_synth_device: bad argument"); return MK_ERR_ARG; }
     MK_CUDA(cudaSetDevice(device));
     cudaStream_t s = (cudaStream_t)stream;
-    mk_synth_cfg c; synth_cfg(&c, seed, mode, genome);
+    mk_synth_cfg c; synth_cfg(&c, seed, mode, genome, opts);
     if (count == 0) { *n_out = 0; return MK_OK; }
     DevBuf d_len, d_off, d_desc, d_total;
     const int n_tiles = (int)((count + SCAN_T * SCAN_ITEMS - 1) / (SCAN_T * SCAN_ITEMS));

@@ -40,6 +40,11 @@ typedef struct {
     int w_selfcircle;
     int dup_per_1024;         /* FASTQ generator: fraction of pairs that re-use an earlier fragment */
     int n_lanes;
+    /* SAM generator: a group re-uses the fragment (loci, strands, CIGARs, bases) of group `hash % sam_dup_universe` with
+       probability sam_dup_per_1024/1024 — PCR duplicates with their own read ids.  The source is anywhere in the universe
+       (the whole job, all shards), so duplicates cross shard boundaries in both directions.  0 = off. */
+    int sam_dup_per_1024;
+    uint64_t sam_dup_universe;
 } mk_synth_cfg;
 
 MK_HD uint64_t mk_mix64(uint64_t x) {
@@ -193,8 +198,15 @@ MK_HD void mk_plain_cigar(mk_aln *a, mk_rng *r, int len, int noisy) {
  *      supplementary `aHbM` (bwa mem -5 without -Y), noise as configured.
  * flash: single-end records (flags 0/16/2048/2064).
  */
+MK_HD uint64_t mk_sam_fragment(const mk_synth_cfg *c, uint64_t idx) {
+    if (c->sam_dup_per_1024 <= 0 || c->sam_dup_universe == 0) return idx;
+    mk_rng d; d.s = mk_mix64(c->seed ^ 0xD0B1E5ULL ^ (idx * 0xA24BAED4963EE407ULL));
+    if (mk_below(&d, 1024) < (uint32_t)c->sam_dup_per_1024) return mk_next(&d) % c->sam_dup_universe;
+    return idx;
+}
+
 MK_HD int mk_gen_group(const mk_synth_cfg *c, uint64_t idx, mk_sink *w) {
-    mk_rng r; r.s = mk_mix64(c->seed ^ (idx * 0xD1342543DE82EF95ULL));
+    mk_rng r; r.s = mk_mix64(c->seed ^ (mk_sam_fragment(c, idx) * 0xD1342543DE82EF95ULL));
     int sc;
     mk_locus A = mk_pick_locus(c, &r, 4000);
     mk_locus B = mk_pick_partner(c, &r, A, &sc);
@@ -406,6 +418,7 @@ static inline void mk_synth_init(mk_synth_cfg *c, uint64_t seed, int mode, int m
     c->w_trans = 256; c->w_far = 236; c->w_mid = 20; c->w_selfcircle = 5;
     c->w_noise = 51;                        /* 5 % */
     c->dup_per_1024 = 205; c->n_lanes = 1;
+    c->sam_dup_per_1024 = 0; c->sam_dup_universe = 0;
 }
 
 #endif

@@ -158,3 +158,108 @@ def test_one_sort_dedup_bin_matches_oracle(oracle, n, seed, lanes, res):
     key = lambda a: np.lexsort((a["strands"], a["pos2"], a["chr2"], a["pos1"], a["chr1"], a["lane"]))
     assert np.array_equal(out[key(out)], exp[key(exp)])          # same set of kept pairs, fields restored exactly
     ws.close()
+
+
+@pytest.mark.parametrize("n,seed,lanes", [(1, 1, 1), (77777, 6, 1), (1000003, 4, 3)])
+def test_dedup_bin_reports_first_occurrences(oracle, n, seed, lanes):
+    """keep[] is the oracle's first-in-input-order mask (krmdup.cpp:201-212 semantics) and kept_idx[] names, for every
+    kept pair in output order, the input pair it came from."""
+    p = random_pairs(n, seed, dup_frac=0.4, lanes=lanes)
+    keep, kept = oracle.coord_dedup(as_oracle_pairs(p), n)
+    exp_keep = np.frombuffer(bytes(keep), dtype=np.uint8)[:n]
+    ws = mk.PairsWorkspace(n)
+    d = to_dev(p)
+    o1 = torch.empty(n, dtype=torch.int32, device="cuda"); o2 = torch.empty_like(o1); oc = torch.empty_like(o1)
+    d_keep = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    d_idx = torch.empty(n, dtype=torch.int32, device="cuda")
+    got, nnz = ws.dedup_bin(d.data_ptr(), n, HG38_LEN, 5000, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n, max_lane=lanes - 1,
+                            d_keep=d_keep.data_ptr(), d_kept_idx=d_idx.data_ptr())
+    assert got == kept and ws.dropped() == 0
+    assert np.array_equal(d_keep.cpu().numpy(), exp_keep)
+    idx = d_idx[:got].cpu().numpy().astype(np.uint32)
+    out = np.frombuffer(d[:got * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+    assert np.array_equal(out, p[idx])                         # every kept pair is the input pair kept_idx points at
+    assert np.array_equal(np.sort(idx), np.flatnonzero(exp_keep))
+    ws.close()
+
+
+def test_unkeyable_pairs_are_dropped_and_counted(oracle):
+    """Unknown chromosome ids (sam2pairs learns RNAMEs absent from the .info list), positions past the chromosome end and
+    lanes above max_lane never index out of range: they are left out and counted."""
+    n = 100000
+    p = random_pairs(n, 11, lanes=2)
+    bad = np.zeros(n, dtype=bool)
+    rng = np.random.default_rng(3)
+    i1, i2, i3, i4 = (rng.choice(n, 50, replace=False) for _ in range(4))
+    q = p.copy()
+    q["chr1"][i1] = 25; q["chr2"][i2] = 60000                 # ids outside the 25-entry table
+    q["pos2"][i3] = np.array(HG38_LEN)[q["chr2"][i3] % 25] + 5000 * 3   # past the last bin of its chromosome
+    q["lane"][i4] = 9                                          # > max_lane
+    bad[i1] = bad[i2] = bad[i3] = bad[i4] = True
+    good = q[~bad]
+    ng = len(good)
+    keep, kept = oracle.coord_dedup(as_oracle_pairs(good), ng)
+    b1, b2, ct = oracle.bin_coo(as_oracle_pairs(good), ng, keep, HG38_LEN, 5000)
+    ws = mk.PairsWorkspace(n)
+    d = to_dev(q)
+    o1 = torch.empty(n, dtype=torch.int32, device="cuda"); o2 = torch.empty_like(o1); oc = torch.empty_like(o1)
+    d_keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+    got, nnz = ws.dedup_bin(d.data_ptr(), n, HG38_LEN, 5000, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n, max_lane=1,
+                            d_keep=d_keep.data_ptr())
+    assert ws.dropped() == int(bad.sum())
+    assert got == kept and nnz == len(b1)
+    assert oc[:nnz].cpu().numpy().astype(np.uint32).tolist() == ct and o1[:nnz].cpu().numpy().astype(np.uint32).tolist() == b1
+    k = d_keep.cpu().numpy()
+    assert not k[bad].any() and np.array_equal(k[~bad], np.frombuffer(bytes(keep), dtype=np.uint8)[:ng])
+    # plain binning: same rule
+    d2 = to_dev(q)
+    # (lane is not part of a bin: only the three coordinate offenders are dropped there)
+    coord_bad = np.isin(np.arange(n), np.concatenate([i1, i2, i3]))
+    good_b = q[~coord_bad]
+    b1b, b2b, ctb = oracle.bin_coo(as_oracle_pairs(good_b), len(good_b), None, HG38_LEN, 5000)
+    nnz2 = ws.bin(d2.data_ptr(), n, HG38_LEN, 5000, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n)
+    assert ws.dropped() == n - len(good_b)
+    assert nnz2 == len(b1b) and oc[:nnz2].cpu().numpy().astype(np.uint32).tolist() == ctb
+    assert int(oc[:nnz2].sum()) == len(good_b)
+    ws.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_owner_partition_then_dedup_bin_equals_unsharded(oracle, world):
+    """The multi-GPU data path on one GPU: mk_pairs_partition_device groups the pairs by owner rank; duplicate removal + binning
+    per segment, concatenated over the owners, equals the unsharded result (kept set, COO) — including duplicates that sit
+    in different positions of the input and lanes (equal keys and equal cells land on one owner)."""
+    from test_shard_gloo import owner_np
+    n = 300007                                                  # not a multiple of 32
+    res = 5000
+    p = random_pairs(n, 21 + world, dup_frac=0.3, lanes=2)
+    keep, kept = oracle.coord_dedup(as_oracle_pairs(p), n)
+    b1, b2, ct = oracle.bin_coo(as_oracle_pairs(p), n, keep, HG38_LEN, res)
+    ws = mk.PairsWorkspace(n)
+    d = to_dev(p)
+    part = torch.empty(n * 16 + 16, dtype=torch.uint8, device="cuda")
+    counts = ws.partition(d.data_ptr(), n, world, res, part.data_ptr())
+    own = owner_np(p["chr1"], p["chr2"], p["pos1"], res, world)
+    assert counts == np.bincount(own, minlength=world).tolist()
+    seg = np.frombuffer(part[:n * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+    o1 = torch.empty(n, dtype=torch.int32, device="cuda"); o2 = torch.empty_like(o1); oc = torch.empty_like(o1)
+    all_kept, all_coo = [], []
+    off = 0
+    for r in range(world):
+        s = seg[off:off + counts[r]]
+        assert sorted(s.tobytes()[i:i + 16] for i in range(0, len(s) * 16, 16)) == \
+            sorted(p[own == r].tobytes()[i:i + 16] for i in range(0, counts[r] * 16, 16))
+        ds = to_dev(s) if len(s) else torch.empty(16, dtype=torch.uint8, device="cuda")
+        got, nnz = ws.dedup_bin(ds.data_ptr(), len(s), HG38_LEN, res, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n, max_lane=1)
+        all_kept.append(np.frombuffer(ds[:got * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE))
+        all_coo.append(np.stack([o1[:nnz].cpu().numpy().astype(np.uint32), o2[:nnz].cpu().numpy().astype(np.uint32),
+                                 oc[:nnz].cpu().numpy().astype(np.uint32)], axis=1))
+        off += counts[r]
+    out = np.concatenate(all_kept)
+    exp = p[np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
+    key = lambda a: np.lexsort((a["strands"], a["pos2"], a["chr2"], a["pos1"], a["chr1"], a["lane"]))
+    assert len(out) == kept and np.array_equal(out[key(out)], exp[key(exp)])
+    coo = np.concatenate(all_coo)
+    coo = coo[np.lexsort((coo[:, 1], coo[:, 0]))]
+    assert coo[:, 0].tolist() == b1 and coo[:, 1].tolist() == b2 and coo[:, 2].tolist() == ct   # every cell on exactly one owner
+    ws.close()
