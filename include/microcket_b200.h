@@ -114,6 +114,9 @@ typedef struct {
     char    *d_pairs_text;  size_t pairs_text_cap;   /* may be NULL when emit_text == 0 */
     mk_pair *d_pairs;       size_t pairs_cap;        /* may be NULL when emit_packed == 0 */
     char    *d_sam_text;    size_t sam_text_cap;     /* may be NULL when write_sam == 0 */
+    uint64_t *d_line_off;   size_t line_off_cap;     /* optional (NULL): d_line_off[e] = offset in d_pairs_text of emitted pair e's
+                                                        line, d_line_off[n_pairs] = pairs_text_len; needs cap >= n_pairs + 1.
+                                                        Input of mk_pairs_sort_text_device / mk_pairs_filter_text_device */
     /* results (host values, valid after the call returns) */
     size_t   pairs_text_len, n_pairs, sam_text_len, consumed;
 } mk_s2p_dev_io;
@@ -179,6 +182,19 @@ int  mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *, mk_pair *d_pairs, size_t n
                                uint32_t res, uint16_t max_lane, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
                                uint8_t *d_keep, uint32_t *d_kept_idx, size_t *n_kept, size_t *nnz, void *stream);
 uint64_t mk_pairs_dropped(mk_pairs_ws *);
+/* .pairs text of the kept pairs in the order the driver's `LANG=C sort -k2,2d -k4,4d -k3,3n -k5,5n` (microcket:480,484,502,
+ * 506,514) produces: chromosome names under sort's dictionary rule (chrom_rank[id], from mk_pairs_chrom_ranks), positions
+ * numerically, ties by whole-line bytewise comparison (GNU sort's last resort).  d_pairs / d_pairs_text / d_line_off are the
+ * outputs of one mk_s2p_run_device call (emission order); d_keep (may be NULL = all) is mk_pairs_dedup_bin_indexed_device's
+ * mask.  max_pos: largest position present (chromosome length bound; 0 = 32 bits).  Replaces that sort process. */
+int  mk_pairs_sort_text_device(mk_pairs_ws *, const mk_pair *d_pairs, size_t n, const uint8_t *d_keep,
+                               const char *d_pairs_text, const uint64_t *d_line_off, const uint16_t *chrom_rank, int n_ids,
+                               uint32_t max_pos, char *d_out, size_t out_cap, size_t *out_len, size_t *n_lines, void *stream);
+/* The lines of the kept pairs in input order (deduplicated, unsorted). */
+int  mk_pairs_filter_text_device(mk_pairs_ws *, size_t n, const uint8_t *d_keep, const char *d_pairs_text,
+                                 const uint64_t *d_line_off, char *d_out, size_t out_cap, size_t *out_len, void *stream);
+/* rank[i] of names[i] under `sort -d` in the C locale (only blanks and alphanumerics compare); equal keys share a rank */
+int  mk_pairs_chrom_ranks(const char *const *names, int n, uint16_t *rank);
 /* Multi-GPU: group pairs by owner rank = mix(chr1, chr2, pos1 / res) mod world into d_out (segments in rank order;
  * counts[r] pairs for rank r).  The caller moves the segments with an all-to-all (NCCL via torch.distributed in
  * bench.py); afterwards equal keys and equal (bin1,bin2) cells at `res` are on one rank. */

@@ -40,7 +40,7 @@ class S2PStats(C.Structure):
 
 class S2PDevIO(C.Structure):
     _fields_ = [("d_pairs_text", C.c_void_p), ("pairs_text_cap", C.c_size_t), ("d_pairs", C.c_void_p), ("pairs_cap", C.c_size_t),
-                ("d_sam_text", C.c_void_p), ("sam_text_cap", C.c_size_t),
+                ("d_sam_text", C.c_void_p), ("sam_text_cap", C.c_size_t), ("d_line_off", C.c_void_p), ("line_off_cap", C.c_size_t),
                 ("pairs_text_len", C.c_size_t), ("n_pairs", C.c_size_t), ("sam_text_len", C.c_size_t), ("consumed", C.c_size_t)]
 
 
@@ -124,6 +124,9 @@ class Lib:
                            ("mk_pairs_dedup_bin_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, C.c_uint16, vp, vp, vp, sz, P(sz), P(sz), vp]),
                            ("mk_pairs_dedup_bin_indexed_device", [vp, vp, sz, P(C.c_uint32), i, P(C.c_uint16), i, C.c_uint32, C.c_uint16, vp, vp, vp, sz, vp, vp, P(sz), P(sz), vp]),
                            ("mk_pairs_dropped", [vp]),
+                           ("mk_pairs_sort_text_device", [vp, vp, sz, vp, vp, vp, P(C.c_uint16), i, C.c_uint32, vp, sz, P(sz), P(sz), vp]),
+                           ("mk_pairs_filter_text_device", [vp, sz, vp, vp, vp, vp, sz, P(sz), vp]),
+                           ("mk_pairs_chrom_ranks", [P(C.c_char_p), i, P(C.c_uint16)]),
                            ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
@@ -260,8 +263,9 @@ class Sam2Pairs:
         p, s = self.pull()
         return p, s, self.finish()
 
-    def run_device(self, d_ptr, n, is_last, d_text=0, text_cap=0, d_pairs=0, pairs_cap=0, d_sam=0, sam_cap=0, stream=0):
-        io = S2PDevIO(d_text, text_cap, d_pairs, pairs_cap, d_sam, sam_cap, 0, 0, 0, 0)
+    def run_device(self, d_ptr, n, is_last, d_text=0, text_cap=0, d_pairs=0, pairs_cap=0, d_sam=0, sam_cap=0, stream=0,
+                   d_line_off=0, line_off_cap=0):
+        io = S2PDevIO(d_text, text_cap, d_pairs, pairs_cap, d_sam, sam_cap, d_line_off, line_off_cap, 0, 0, 0, 0)
         self.lib.check(self.lib.L.mk_s2p_run_device(self.h, d_ptr, n, int(is_last), C.byref(io), stream))
         return io
 
@@ -276,8 +280,7 @@ class Sam2Pairs:
         ms = (C.c_double * 8)()
         cnt = (C.c_uint64 * 8)()
         self.lib.check(self.lib.L.mk_s2p_kernel_times(self.h, ms, cnt))
-        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index",
-                                                           "k_ft_tile", "k_ft_gather"))}
+        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index"))}
 
     def push_ptr(self, ptr, n, is_last=False):
         """push() from a raw host pointer (e.g. a pinned torch tensor): no Python-side copy."""
@@ -405,6 +408,19 @@ class PairsWorkspace:
     def dropped(self):
         return self.lib.L.mk_pairs_dropped(self.h)
 
+    def sort_text(self, d_pairs, n, d_keep, d_text, d_line_off, chrom_rank, max_pos, d_out, out_cap, stream=0):
+        """Lines of the kept pairs in `sort -k2,2d -k4,4d -k3,3n -k5,5n` order → (bytes, lines)"""
+        rk = (C.c_uint16 * len(chrom_rank))(*chrom_rank)
+        ol, nl = C.c_size_t(), C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_sort_text_device(self.h, d_pairs, n, d_keep, d_text, d_line_off, rk, len(chrom_rank), max_pos,
+                                                            d_out, out_cap, C.byref(ol), C.byref(nl), stream))
+        return ol.value, nl.value
+
+    def filter_text(self, n, d_keep, d_text, d_line_off, d_out, out_cap, stream=0):
+        ol = C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_filter_text_device(self.h, n, d_keep, d_text, d_line_off, d_out, out_cap, C.byref(ol), stream))
+        return ol.value
+
     def partition(self, d_pairs, n, world, res, d_out, stream=0):
         counts = (C.c_uint64 * world)()
         self.lib.check(self.lib.L.mk_pairs_partition_device(self.h, d_pairs, n, world, res, d_out, counts, stream))
@@ -420,6 +436,15 @@ class PairsWorkspace:
         self.lib.check(self.lib.L.mk_pairs_dedup_bin_host(self.h, pairs_ptr, n, int(do_dedup), cl, len(chrom_len), mp, nm, res,
                                                           b1_ptr, b2_ptr, c_ptr, cap, C.byref(kept), C.byref(nnz)))
         return kept.value, nnz.value
+
+
+def chrom_ranks(names):
+    """rank of every chromosome name under `sort -d` (C locale), as mk_pairs_sort_text_device wants them"""
+    arr = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+    out = (C.c_uint16 * max(len(names), 1))()
+    L = lib()
+    L.check(L.L.mk_pairs_chrom_ranks(arr, len(names), out))
+    return list(out)[:len(names)]
 
 
 def synth_host(seed, mode, genome, first, count, opts=None) -> bytes:

@@ -158,38 +158,6 @@ __device__ __forceinline__ u64 lookback_exclusive(u64 *desc, int tile, int first
     return excl;
 }
 
-// ---- wave scan: exclusive prefix for a persistent grid that walks tiles round-robin (tile = first + blockIdx + k * grid).
-// All CTAs are on wave k together, so a chained look-back degenerates into an INC that crawls 32 tiles per L2 round trip
-// across the wave.  Here every tile sums the aggregates of its predecessors INSIDE the wave with all loads in flight at
-// once (one round trip) and adds the wave's base, which the wave's last CTA publishes for the next wave.
-// agg[rel] : per-tile aggregate descriptors (rel = tile - first_tile), base[w] : per-wave exclusive prefix; both zeroed.
-#define WS_MAX_PER_LANE 16        // supports grids of up to 512 CTAs
-__device__ __forceinline__ u64 wave_scan_exclusive(u64 *agg, u64 *base, int rel, int grid, u64 aggregate, int lane, bool last_of_wave) {
-    const int w = rel / grid, b = rel - w * grid;
-    if (lane == 0) st_volatile_u64(&agg[rel], LB_AGG | aggregate);
-    const u64 *row = agg + (u64)w * grid;
-    u64 d[WS_MAX_PER_LANE];
-#pragma unroll
-    for (int k = 0; k < WS_MAX_PER_LANE; ++k) { const int j = lane + 32 * k; d[k] = j < b ? ld_volatile_u64(&row[j]) : LB_AGG; }
-    u64 sum = 0;
-#pragma unroll
-    for (int k = 0; k < WS_MAX_PER_LANE; ++k) {
-        const int j = lane + 32 * k;
-        while ((d[k] >> 62) == 0) d[k] = ld_volatile_u64(&row[j]);     // that predecessor has not counted yet
-        sum += LB_VAL(d[k]);
-    }
-#pragma unroll
-    for (int s = 16; s; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-    u64 wb = 0;
-    if (w > 0) {
-        if (lane == 0) { u64 x; do { x = ld_volatile_u64(&base[w]); } while ((x >> 62) == 0); wb = LB_VAL(x); }
-        wb = __shfl_sync(0xffffffffu, wb, 0);
-    }
-    const u64 excl = wb + sum;
-    if (last_of_wave && lane == 0) st_volatile_u64(&base[w + 1], LB_INC | (excl + aggregate));
-    return excl;
-}
-
 // Two-step form for kernels that have other work to do between publishing their aggregate and needing the prefix.
 __device__ __forceinline__ void lookback_publish(u64 *desc, int tile, int first_tile, u64 aggregate) {
     st_volatile_u64(&desc[tile], (tile == first_tile ? LB_INC : LB_AGG) | aggregate);
@@ -252,28 +220,6 @@ struct ByteReader {
     }
     __device__ __forceinline__ int next() {
         if (left == 0) { cur = __ldg(base + (pos >> 3)); left = 8; }
-        int c = (int)(cur & 0xFF);
-        cur >>= 8; --left; ++pos;
-        return c;
-    }
-};
-
-// same interface, but bytes of [tlo, thi) (absolute offsets, 8-byte aligned bounds) come from a shared-memory copy
-struct TileReader {
-    const u64 *base; const char *sm; u64 tlo, thi;
-    u64 cur, pos; int left;
-    __device__ __forceinline__ u64 fetch(u64 a) const {       // a is 8-byte aligned
-        return (a >= tlo && a + 8 <= thi) ? *(const u64 *)(sm + (a - tlo)) : __ldg(base + (a >> 3));
-    }
-    __device__ __forceinline__ void setup(const char *buf, const char *smem_tile, u64 lo, u64 hi) { base = (const u64 *)buf; sm = smem_tile; tlo = lo; thi = hi; }
-    __device__ __forceinline__ void init(const char *, u64 off) {
-        pos = off;
-        int sh = (int)(off & 7);
-        cur = fetch(off & ~(u64)7) >> (sh * 8);
-        left = 8 - sh;
-    }
-    __device__ __forceinline__ int next() {
-        if (left == 0) { cur = fetch(pos); left = 8; }
         int c = (int)(cur & 0xFF);
         cur >>= 8; --left; ++pos;
         return c;

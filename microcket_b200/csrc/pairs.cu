@@ -10,6 +10,7 @@
 #include <vector>
 #include "mk_common.cuh"
 #include "radix_sort.cuh"
+#include "pairs_ws.h"
 
 struct K64 {                       // keys only
     typedef u64 Key;
@@ -163,20 +164,7 @@ __global__ void k_bin_keys(const mk_pair *p, u64 n, const u32 *chr_off /* per pa
     if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
 }
 
-// ------------------------------------------------------------------------------------------------ workspace
-struct mk_pairs_ws {
-    int device = 0, sms = 148;
-    size_t max_pairs = 0;
-    RadixWs rws;
-    DevBuf alt;          // max_pairs * 16 B: second record buffer / key buffers
-    DevBuf keys2;        // max_pairs * 8 B
-    DevBuf heads_key, heads_pos;
-    DevBuf desc, counter, chr_off;
-    DevBuf h_pairs, h_b1, h_b2, h_c;   // device staging of the host-buffer API, allocated on first use
-    u64 launches = 0;
-    u64 dropped = 0;     // pairs the last dedup / binning call left out (unknown chromosome id, position past the chromosome end, lane > max_lane)
-};
-
+// ------------------------------------------------------------------------------------------------ workspace (pairs_ws.h)
 extern "C" int mk_pairs_ws_create(int device, size_t max_pairs, mk_pairs_ws **out) {
     if (!out || max_pairs == 0) { mk_set_error("mk_pairs_ws_create: bad argument"); return MK_ERR_ARG; }
     int ndev = 0;

@@ -7,7 +7,6 @@
 #include <vector>
 #include "ctx.h"
 #include "s2p_kernels.cuh"
-#include "s2p_fused.cuh"
 
 static const size_t S2P_CARRY = 8u << 20;          // room in front of every window for the previous window's last group
 static const u32 S2P_BATCH = 1u << 18;             // pairutil.h:48
@@ -35,12 +34,10 @@ struct S2PCtx : mk_ctx {
     u32 n_chunks_cap = 0; bool scan_chunks = true;
     DevBuf d_cklist, d_ckcnt, d_tiletot;
     DevBuf d_params;                               // device copies of the kernels' parameter blocks (S2PParams.self)
-    DevBuf d_fttext, d_ftpairs, d_ftsam, d_fttot, d_ftnent; u32 n_tiles_cap = 0;   // single-pass tile path: per-tile scratch
     u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
-    int grid_scan = 0, grid_scan4 = 0, scan_occ4 = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_fused = 0, scan_nt = 4;
-    bool fused = false;
+    int grid_scan = 0, grid_scan4 = 0, scan_occ4 = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0, scan_nt = 4;
     u64 launches = 0, fallback_windows = 0;
     // host streaming state
     std::vector<char> tail;                        // input not yet part of a window (a partial last line, or small pushes)
@@ -88,28 +85,24 @@ extern "C" void mk_s2p_default_cfg(mk_s2p_cfg *c) {
 }
 
 static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_cap, char *out_text, u64 text_cap, mk_pair *out_pairs, u64 pairs_cap,
-                             char *out_sam, u64 sam_cap, u64 window_bytes, int running, int old_inline) {
+                             char *out_sam, u64 sam_cap, u64 window_bytes, int running, u64 *line_off = nullptr, u64 line_off_cap = 0) {
     S2PParams p;
     memset(&p, 0, sizeof p);
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
     p.ck_list = c->d_cklist.as<u32>(); p.ck_cnt = c->d_ckcnt.as<u32>(); p.ck_pre = p.ck_cnt + c->n_chunks_cap; p.ck_bsum = p.ck_pre + c->n_chunks_cap; p.n_chunks_cap = c->n_chunks_cap;
     p.tile_tot = c->d_tiletot.as<uint4>(); p.tile_pre = p.tile_tot + c->n_sub_cap; p.n_sub_cap = c->n_sub_cap;
     p.rec = c->d_rec.as<LineRec>(); p.res = c->d_res.as<GroupRes>(); p.sam_dst = c->d_samdst.as<u32>();
-    p.desc_scan = c->d_desc.as<u64>(); p.desc_emitA = p.desc_scan + c->n_desc; p.desc_emitB = p.desc_emitA + c->n_desc;
-    p.wave_scan = p.desc_emitB + c->n_desc; p.wave_emitA = p.wave_scan + c->n_desc; p.wave_emitB = p.wave_emitA + c->n_desc;
+    p.desc_scan = c->d_desc.as<u64>();
     p.chr = c->d_chr.as<ChrSlot>(); p.chr_mask = c->chr_slots - 1; p.id_to_slot = c->d_id2slot.as<int>(); p.chr_cap = c->chr_cap;
     p.sc_list = sc_list; p.sc_cap = sc_cap;
     p.out_text = out_text; p.out_text_cap = out_text ? text_cap : 0;
     p.out_pairs = out_pairs; p.out_pairs_cap = out_pairs ? pairs_cap : 0;
     p.out_sam = out_sam; p.out_sam_cap = out_sam ? sam_cap : 0;
+    p.out_line_off = line_off; p.out_line_off_cap = line_off ? line_off_cap : 0;
     p.window_bytes = window_bytes; p.cap_lines = c->cap_lines;
     p.mode = c->cfg.mode; p.min_mapq = c->cfg.min_mapq; p.ratio = c->cfg.min_mapped_ratio; p.lane = c->cfg.lane;
     p.write_sam = c->cfg.write_sam && out_sam; p.emit_text = c->cfg.emit_text && out_text; p.emit_packed = c->cfg.emit_packed && out_pairs;
     p.running_offsets = running;
-    p.dyn_tickets = getenv("MICROCKET_DYNAMIC_TILES") && atoi(getenv("MICROCKET_DYNAMIC_TILES"));   // measured slower on B200: default off
-    p.fused = c->fused ? 1 : 0; p.old_inline = old_inline;
-    p.ft_text = c->d_fttext.as<char>(); p.ft_pairs = c->d_ftpairs.as<mk_pair>(); p.ft_sam = c->d_ftsam.as<uint4>();
-    p.ft_tot = c->d_fttot.as<uint4>(); p.ft_pre = p.ft_tot + c->n_tiles_cap; p.ft_nent = c->d_ftnent.as<u32>(); p.n_tiles_cap = c->n_tiles_cap;
     p.self = nullptr;
     return p;
 }
@@ -122,41 +115,28 @@ static int upload_params(S2PCtx *c, S2PParams &p, int slot, cudaStream_t s) {
     return MK_OK;
 }
 
-// enqueue the kernels of one window on the compute stream: the single-pass tile path first (p.fused), the multi-kernel
-// path behind it when this launch carries the fallback (p.old_inline, or p.fused == 0); every kernel of the path that
-// does not own the window returns at once (WinState.path_old)
+// enqueue the kernels of one window on the compute stream
 static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     const bool t = c->timing;
     auto mark = [&](int id) { if (t) { cudaEvent_t e = c->next_event(); cudaEventRecord(e, s); c->ev_marks.emplace_back(id, c->ev_used - 1); } };
     k_win_begin<<<(c->n_desc + 255) / 256, 256, 0, s>>>(p, c->n_desc);
-    c->launches += 1;
-    if (p.fused) {
-        mark(7);
-        k_ft_strip<<<c->grid_fused, FS_THREADS, FS_SMEM, s>>>(p);
-        mark(8);
-        k_ft_prefix<<<1, 1024, 0, s>>>(p);
-        k_ft_gather<<<c->n_tiles_cap, 256, 0, s>>>(p);
-        c->launches += 3;
-    }
-    if (!p.fused || p.old_inline) {
-        mark(0);
-        // chunked scan (no look-back); the look-back kernel only does work when a chunk overflowed its slot list
-        k_scan_chunks<<<(c->n_chunks_cap + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, s>>>(p);
-        mark(6);
-        k_chunk_prefix<<<(c->n_chunks_cap + SC_PFX_BLOCK - 1) / SC_PFX_BLOCK, 256, 0, s>>>(p);
-        k_chunk_compact<<<(c->n_chunks_cap + 7) / 8, 256, 0, s>>>(p);
-        k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 1);
-        mark(1);
-        k_parse<<<c->grid_gs, 256, 0, s>>>(p);
-        mark(2);
-        k_group<<<c->grid_gs, 256, 0, s>>>(p);
-        mark(3);
-        k_emit_prefix<<<1, 1024, 0, s>>>(p);
-        k_emit<<<c->grid_emit, EMIT_THREADS, 0, s>>>(p);
-        mark(4);
-        c->launches += 8;
-        if (p.write_sam) { k_copy_sam<<<c->grid_gs, 256, 0, s>>>(p); c->launches += 1; }
-    }
+    mark(0);
+    // chunked scan (no look-back); the look-back kernel only does work when a chunk overflowed its slot list
+    k_scan_chunks<<<(c->n_chunks_cap + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, s>>>(p);
+    mark(6);
+    k_chunk_prefix<<<(c->n_chunks_cap + SC_PFX_BLOCK - 1) / SC_PFX_BLOCK, 256, 0, s>>>(p);
+    k_chunk_compact<<<(c->n_chunks_cap + 7) / 8, 256, 0, s>>>(p);
+    k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 1);
+    mark(1);
+    k_parse<<<c->grid_parse, 256, PR_SMEM, s>>>(p);
+    mark(2);
+    k_group<<<c->grid_gs, 256, 0, s>>>(p);
+    mark(3);
+    k_emit_prefix<<<1, 1024, 0, s>>>(p);
+    k_emit<<<c->grid_emit, EMIT_THREADS, 0, s>>>(p);
+    mark(4);
+    c->launches += 9;
+    if (p.write_sam) { k_copy_sam<<<c->grid_gs, 256, 0, s>>>(p); c->launches += 1; }
     mark(5);
     k_win_end<<<1, 1, 0, s>>>(p);
     c->launches += 1;
@@ -180,7 +160,7 @@ extern "C" int mk_s2p_enable_timing(mk_ctx *x, int on) {
 }
 
 // ms[k], count[k] for k = 0 newline scan, 1 parse, 2 group, 3 emit, 4 copy_sam, 5 scan index (prefix + compaction + the
-// look-back fallback's early exit), 6 single-pass tile kernel, 7 its prefix + gather (accumulated since creation); arrays of 8
+// look-back fallback's early exit); 6, 7 unused (accumulated since creation); arrays of 8
 extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
     if (!x || x->kind != MK_CTX_S2P || !ms || !count) { mk_set_error("mk_s2p_kernel_times: bad argument"); return MK_ERR_ARG; }
     S2PCtx *c = (S2PCtx *)x;
@@ -189,7 +169,7 @@ extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
     timing_collect(c);
     for (int k = 0; k < 5; ++k) { ms[k] = c->k_ms[k]; count[k] = c->k_cnt[k]; }
     ms[5] = c->k_ms[6]; count[5] = c->k_cnt[6];
-    ms[6] = c->k_ms[7]; count[6] = c->k_cnt[7]; ms[7] = c->k_ms[8]; count[7] = c->k_cnt[8];
+    ms[6] = ms[7] = 0; count[6] = count[7] = 0;
     return MK_OK;
 }
 
@@ -238,16 +218,9 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_nl.alloc((size_t)c->cap_lines * 4)); A(c->d_lmeta.alloc(c->cap_lines)); A(c->d_rec.alloc((size_t)c->cap_lines * sizeof(LineRec)));
     A(c->d_res.alloc((size_t)c->cap_lines * sizeof(GroupRes)));
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
-    A(c->d_desc.alloc((size_t)c->n_desc * 6 * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
+    A(c->d_desc.alloc((size_t)c->n_desc * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
     A(c->d_tiletot.alloc((size_t)c->n_sub_cap * 2 * sizeof(uint4)));
-    c->n_tiles_cap = (u32)((S2P_CARRY + c->W) / FT_TILE + 2);
-    c->fused = getenv("MICROCKET_FUSED") && atoi(getenv("MICROCKET_FUSED"));   // 1: single-pass strip path first (half the DRAM traffic, but instruction-fetch bound so far: see DESIGN.md); default: multi-kernel path
-    if (c->fused) {
-        A(c->d_fttext.alloc((size_t)c->n_tiles_cap * FT_TEXT_CAP + 64)); A(c->d_ftpairs.alloc((size_t)c->n_tiles_cap * FT_LMAX * sizeof(mk_pair)));
-        A(c->d_ftsam.alloc(cfg->write_sam ? (size_t)c->n_tiles_cap * FT_LMAX * sizeof(uint4) : 16));
-        A(c->d_fttot.alloc((size_t)c->n_tiles_cap * 2 * sizeof(uint4))); A(c->d_ftnent.alloc((size_t)c->n_tiles_cap * 4));
-    }
     A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4 + 160 * 4));   // counts, prefixes, 160 block sums (W <= 2040 MiB: <= 130 blocks of 1024 chunks)
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
@@ -291,10 +264,9 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, std::min(occ, 4));
     c->grid_gs = sms * 8;
-    cudaFuncSetAttribute(k_ft_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ft_strip, FS_THREADS, FS_SMEM);
-    c->grid_fused = sms * std::max(1, occ);
-    if (getenv("MICROCKET_FT_GRID")) c->grid_fused = atoi(getenv("MICROCKET_FT_GRID"));
+    cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parse, 256, PR_SMEM);
+    c->grid_parse = sms * std::max(1, occ);                 // one resident wave: every CTA then pipelines many rounds
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mk_set_error("mk_s2p_create: %s", cudaGetErrorString(e)); delete c; return MK_ERR_CUDA; }
     *out = c;
@@ -433,7 +405,7 @@ static int s2p_submit(S2PCtx *c, size_t n_stage, const char *direct, size_t n_di
         c->slot[pb].free_pending = true;
     }
     S2PParams p = make_params(c, s.d_in.as<char>(), s.d_sc.as<u64>(), c->sc_cap, s.d_text.as<char>(), s.d_text.n,
-                              s.d_pairs.as<mk_pair>(), c->cap_lines, s.d_sam.as<char>(), s.d_sam.n, S2P_CARRY + c->W + 64, 0, 1);
+                              s.d_pairs.as<mk_pair>(), c->cap_lines, s.d_sam.as<char>(), s.d_sam.n, S2P_CARRY + c->W + 64, 0);
     MK_TRY(upload_params(c, p, b, c->s_comp));
     launch_window(c, p, c->s_comp);
     MK_CUDA(cudaMemcpyAsync(s.h_state.p, c->d_state.p, sizeof(WinState), cudaMemcpyDeviceToHost, c->s_comp));
@@ -685,9 +657,8 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
     WinState *dst = c->d_state.as<WinState>();
     k_set_stream<<<1, 1, 0, s>>>(dst, 0, n, is_last ? 1u : 0u);
     c->launches += 1;
-    S2PParams p = make_params(c, d_sam, c->d_sclist.as<u64>(), c->sc_cap_dev, io->d_pairs_text, io->pairs_text_cap, io->d_pairs, io->pairs_cap, io->d_sam_text, io->sam_text_cap, c->W, 1, 0);
-    S2PParams p_old = p; p_old.fused = 0;                     // the multi-kernel path, for a window the tile path gave up
-    MK_TRY(upload_params(c, p, 2, s)); MK_TRY(upload_params(c, p_old, 3, s));
+    S2PParams p = make_params(c, d_sam, c->d_sclist.as<u64>(), c->sc_cap_dev, io->d_pairs_text, io->pairs_text_cap, io->d_pairs, io->pairs_cap, io->d_sam_text, io->sam_text_cap, c->W, 1, (u64 *)io->d_line_off, io->line_off_cap);
+    MK_TRY(upload_params(c, p, 2, s));
     // running output offsets restart at 0 for every call
     MK_CUDA(cudaMemsetAsync((char *)dst + offsetof(WinState, out_text), 0, 3 * sizeof(u64), s));
     // every window consumes at least W - (largest read group) bytes; enqueue an upper bound and top up if needed
@@ -700,13 +671,6 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
         for (size_t w = 0; w < nwin; ++w) launch_window(c, p, s);
         MK_CUDA(cudaMemcpyAsync(&st, dst, sizeof st, cudaMemcpyDeviceToHost, s));
         MK_CUDA(cudaStreamSynchronize(s));
-        while (st.halt && !st.err) {                          // nothing has advanced since that window: redo it, then carry on
-            MK_CUDA(cudaMemsetAsync((char *)dst + offsetof(WinState, halt), 0, 4, s));
-            launch_window(c, p_old, s);
-            c->fallback_windows += 1;
-            MK_CUDA(cudaMemcpyAsync(&st, dst, sizeof st, cudaMemcpyDeviceToHost, s));
-            MK_CUDA(cudaStreamSynchronize(s));
-        }
         if (c->timing) timing_collect(c);
         MK_TRY(s2p_err_check(st.err));
         if (st.sc_count) {

@@ -62,15 +62,7 @@ struct WinState {
     u64 groups_done, lines_done;
     unsigned long long counters[ST_NCOUNTER];
     u32 sc_count, n_chrom;
-    u32 tickets[4];                  // dynamic tile tickets of the look-back kernels (scan, emit), reset per window
-    // single-pass tile path (s2p_fused.cuh)
-    u32 path_old;                    // 1: this window goes through the multi-kernel path (tile path disabled or overflowed)
-    u32 halt;                        // a window overflowed the tile path and no inline fallback was enqueued: nothing advances until the host redoes it
-    u32 sc_count0;                   // sc_count at the start of the window (restored when the tile path gives the window up)
-    u32 ft_carry_tile, ft_carry_nl;  // tile (window-local) of the carried group's first line, newlines of that tile before it
-    u32 ft_lines_before_carry, ft_pad;
-    u64 ft_carry_pos, ft_last_end;   // absolute offset of the carried group's first line (~0: none); end of the window's last complete line
-    unsigned long long w_counters[ST_NCOUNTER];   // this window's class counters, committed by k_ft_prefix
+    u32 tickets[4];                  // dynamic tile tickets of look-back kernels, reset per window
 };
 
 #define S2P_ERR_LINES 1u
@@ -91,33 +83,27 @@ struct S2PParams {
     LineRec *rec;
     GroupRes *res;
     u32 *sam_dst;
-    u64 *desc_scan, *desc_emitA, *desc_emitB;
+    u64 *desc_scan;
     uint4 *tile_tot, *tile_pre; u32 n_sub_cap;  // per 512 lines: (groups | emitted << 16, text bytes, passthrough bytes) summed by K3; exclusive prefixes (groups, emitted, text, passthrough)
-    u64 *wave_scan, *wave_emitA, *wave_emitB;   // per-wave bases of the wave scans
     ChrSlot *chr; u32 chr_mask; int *id_to_slot; u32 chr_cap;
     u64 *sc_list; u32 sc_cap;
     char *out_text; u64 out_text_cap;
     mk_pair *out_pairs; u64 out_pairs_cap;
+    u64 *out_line_off; u64 out_line_off_cap;   // optional: offset (in out_text) of every emitted pair's line, plus the end of the last one
     char *out_sam; u64 out_sam_cap;
     u64 window_bytes; u32 cap_lines;
     int mode, min_mapq, write_sam, emit_text, emit_packed; float ratio; u16 lane;
     int running_offsets;      // 1: append at st->out_* (device-resident runs); 0: every window writes at 0
-    int dyn_tickets;          // look-back kernels claim tiles with an atomic ticket (1) or round-robin (0)
-    // single-pass tile path: per-tile scratch (text bytes, packed pairs, passthrough copy entries), indexed by window-local tile
-    int fused;                // 1: windows go through k_ft_tile first
-    int old_inline;           // 1: the multi-kernel path is enqueued behind it and takes over a window the tile path gives up
     const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
-    char *ft_text; mk_pair *ft_pairs; uint4 *ft_sam, *ft_tot, *ft_pre; u32 *ft_nent; u32 n_tiles_cap;
 };
 
 // ------------------------------------------------------------------------------------------------ begin / end
 static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p.n_sub_cap) p.tile_tot[i] = make_uint4(0, 0, 0, 0);
-    if (i < n_desc) { p.desc_scan[i] = 0; p.desc_emitA[i] = 0; p.desc_emitB[i] = 0; p.wave_scan[i] = 0; p.wave_emitA[i] = 0; p.wave_emitB[i] = 0; }
+    if (i < n_desc) p.desc_scan[i] = 0;                        // look-back descriptors of the fallback scan
     if (i == 0) {
         WinState *s = p.st;
-        if (s->halt) return;
         s->ws = s->cursor;
         u64 we = s->cursor + p.window_bytes;
         s->we = we < s->total ? we : s->total;
@@ -126,41 +112,29 @@ static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
         s->w_groups = s->w_emit = s->w_text = s->w_sam = 0;
         s->tickets[0] = s->tickets[1] = s->tickets[2] = s->tickets[3] = 0;
         if (!p.running_offsets) { s->out_text = s->out_pairs = s->out_sam = 0; s->sc_count = 0; }
-        s->path_old = p.fused ? 0u : 1u; s->sc_count0 = s->sc_count;
-        s->ft_carry_tile = 0; s->ft_carry_nl = 0; s->ft_lines_before_carry = 0; s->ft_carry_pos = ~(u64)0; s->ft_last_end = 0;
-        for (int k = 0; k < ST_NCOUNTER; ++k) s->w_counters[k] = 0;
     }
 }
 
 static __global__ void k_win_end(S2PParams p) {
     WinState *s = p.st;
-    if (s->halt) return;                                   // the host redoes this window through the multi-kernel path
-    if (s->path_old && !p.old_inline && p.fused) { s->halt = 1; return; }
     u64 ws = s->ws, we = s->we;
     u32 n = s->n_lines;
     u64 next;
-    bool carried; u32 lines_before;
-    if (!s->path_old) {                                    // tile path: positions instead of line indices
-        carried = s->ft_carry_pos != ~(u64)0;
-        next = carried ? s->ft_carry_pos : (s->ft_last_end ? s->ft_last_end : ws);
-        lines_before = s->ft_lines_before_carry;
+    const bool carried = s->carry_line != 0xFFFFFFFFu;
+    if (carried) {
+        u32 c = s->carry_line;
+        next = ws + (c ? (u64)p.nl_pos[c - 1] + 1 : 0);
     } else {
-        carried = s->carry_line != 0xFFFFFFFFu;
-        if (carried) {
-            u32 c = s->carry_line;
-            next = ws + (c ? (u64)p.nl_pos[c - 1] + 1 : 0);
-        } else {
-            next = ws + (n ? (u64)p.nl_pos[n - 1] + 1 : 0);   // no kept record: everything up to the last complete line is consumed
-        }
-        lines_before = s->carry_line;
+        next = ws + (n ? (u64)p.nl_pos[n - 1] + 1 : 0);       // no kept record: everything up to the last complete line is consumed
     }
     bool final_win = (we == s->total) && s->is_last;
     if (final_win) next = s->total;                        // the stream's last group is never processed (pairutil.h:176)
     else if (next == ws && we > ws && we - ws >= p.window_bytes) s->err |= S2P_ERR_NOPROGRESS;  // one group (or line) fills the window
     s->cursor = next;
-    s->lines_done += (carried && !final_win) ? lines_before : n;
+    s->lines_done += (carried && !final_win) ? s->carry_line : n;
     s->groups_done += s->w_groups;
     s->out_text += s->w_text; s->out_pairs += s->w_emit; s->out_sam += s->w_sam;
+    if (p.out_line_off && s->out_pairs < p.out_line_off_cap) p.out_line_off[s->out_pairs] = s->out_text;   // end of the last line so far
 }
 
 // ------------------------------------------------------------------------------------------------ K1: newline index
@@ -293,7 +267,6 @@ __device__ __forceinline__ void scan_lines_body(const char *buf, const u64 ws, c
 template <int NT, int MINB = 3>
 static __global__ void __launch_bounds__(S2P_SCAN_THREADS, MINB) k_scan_lines(S2PParams p, int only_if_ovf) {
     WinState *st = p.st;
-    if (!st->path_old) return;
     if (only_if_ovf && !st->scan_ovf) return;          // fallback of the chunked scan: runs only for windows with very short lines
     scan_lines_body<NT>(p.buf, st->ws, st->we, p.nl_pos, p.cap_lines, p.desc_scan, &st->n_lines, &st->err, S2P_ERR_LINES);
 }
@@ -318,7 +291,6 @@ __device__ __forceinline__ u32 nl_raw(u32 x) {          // bit 7 of byte k set i
 
 static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PParams p) {
     const WinState *st = p.st;
-    if (!st->path_old) return;
     const u64 ws = st->ws, we = st->we;
     if (we <= ws) return;
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -395,7 +367,6 @@ static __global__ void __launch_bounds__(SC_WARPS * 32, 4) k_scan_chunks(S2PPara
 static __global__ void __launch_bounds__(256) k_chunk_prefix(S2PParams p) {
     __shared__ u32 s_w[8];
     WinState *st = p.st;
-    if (!st->path_old) return;
     const u64 ws = st->ws, we = st->we;
     if (we <= ws) return;
     const u64 nc64 = (we - 1) / SC_CHUNK - ws / SC_CHUNK + 1;
@@ -423,7 +394,6 @@ static __global__ void __launch_bounds__(256) k_chunk_prefix(S2PParams p) {
 
 static __global__ void __launch_bounds__(256) k_chunk_compact(S2PParams p) {
     WinState *st = p.st;
-    if (!st->path_old) return;
     const u64 lc = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (lc >= p.n_chunks_cap) return;
     const u32 lane = threadIdx.x & 31u;
@@ -505,8 +475,6 @@ __device__ __forceinline__ u32 parse_uint_tok(R &r, int &c) {
     while (!is_ws(c)) { u32 d = (u32)(c - '0'); bad |= d > 9u; v = v * 10u + d; ++n; c = r.next(); }
     return (bad || n == 0) ? 0u : v;
 }
-
-#define LM_EQ_UNK 32u          // EQ not evaluated here (the previous line starts in another tile): K3 compares on demand
 
 // One SAM line: first six fields, record filter, CIGAR walk.  `r` is positioned at the line's first byte; when
 // cmp_prev, `q` is positioned at the previous line's first byte and the two QNAMEs are compared on the fly.
@@ -597,32 +565,6 @@ struct GlobalFetch {
     __device__ __forceinline__ u64 ld8(u64 a) const { return __ldg((const u64 *)(buf + a)); }
     __device__ __forceinline__ int byte(u64 a) const { return (int)(unsigned char)buf[a]; }
 };
-struct TileFetch {
-    const char *buf, *sm; u64 tlo, thi, A;
-    __device__ __forceinline__ uint4 ld16r(u32 r) const { return ld16(A + r); }
-    __device__ __forceinline__ u64 ld8r(u32 r) const { return ld8(A + r); }
-    __device__ __forceinline__ int byter(u32 r) const { return byte(A + r); }
-    __device__ __forceinline__ uint4 ld16(u64 a) const { return (a >= tlo && a + 16 <= thi) ? *(const uint4 *)(sm + (a - tlo)) : __ldg((const uint4 *)(buf + a)); }
-    __device__ __forceinline__ u64 ld8(u64 a) const { return (a >= tlo && a + 8 <= thi) ? *(const u64 *)(sm + (a - tlo)) : __ldg((const u64 *)(buf + a)); }
-    __device__ __forceinline__ int byte(u64 a) const { return (a >= tlo && a < thi) ? (int)(unsigned char)sm[a - tlo] : (int)(unsigned char)buf[a]; }
-};
-// the thread's own line prefix (7 x 16 bytes from A) staged in a shared-memory column of 32-bit words (word w of the prefix
-// at col[w * 256]: consecutive threads hit consecutive banks whatever w is), followed by four zero words, so that eight
-// bytes at ANY offset below 112 are three conflict-free 32-bit loads and two funnel shifts, with no bounds test (ncu: the
-// 64-bit accessor with its bounds test and 64-bit shifts was 31 % of k_parse's instructions)
-#define LF_WORDS 32
-struct LineFetch {
-    const char *buf; const u32 *col; u64 A;                            // col[w * 256] = bytes [A + 4 w, A + 4 w + 4)
-    uint4 w[7];                                                        // the same prefix in registers (own line only)
-    __device__ __forceinline__ uint4 ld16r(u32 r) const { return w[r >> 4]; }          // r = 16 j, j a compile-time constant
-    __device__ __forceinline__ int byter(u32 r) const { return (int)((col[(r >> 2) * 256] >> (8 * (r & 3u))) & 0xFFu); }
-    __device__ __forceinline__ u64 f8(u32 r) const {                   // r + 8 <= 120
-        const u32 *q = col + (r >> 2) * 256; const u32 sh = (r & 3u) * 8u;
-        const u32 a = q[0], b = q[256], c = q[512];
-        return (u64)__funnelshift_r(a, b, sh) | ((u64)__funnelshift_r(b, c, sh) << 32);
-    }
-};
-__device__ __forceinline__ u64 fetch8r(const LineFetch &f, u32 r) { return f.f8(r); }   // preferred over the template below
 template <class F>
 __device__ __forceinline__ u64 fetch8r(const F &f, u32 r) {           // 8 bytes at any offset relative to f.A
     const u32 a8 = r & ~7u, sh = (r & 7u) * 8;
@@ -773,60 +715,103 @@ static __device__ __forceinline__ u32 parse_line_slow(const S2PParams &p, u64 ws
     return parse_line_slow_abs(*p.self, a, i > 0, ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0), rec);
 }
 
-static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
-    __shared__ u32 s_line[LF_WORDS][256];                             // every thread's line prefix, one column of words per thread
-    __shared__ u64 s_A[256];                                          // its 16-byte aligned base, or ~0 when not staged
+// ---- K2 staging: every thread's line prefix (7 x 16 bytes from the line's 16-byte aligned base) is copied global -> shared
+// with cp.async (LDGSTS: no register staging, no store instructions) into the thread's own 144-byte row, one round AHEAD
+// of the round being parsed, so the DRAM latency of a round's scattered 112-byte reads is covered by the previous round's
+// parsing.  (The first version loaded into registers, transposed into shared-memory word columns and parsed in the same
+// round: ncu showed 4.3 long-scoreboard stalls per issue at 24 resident warps.)  Row stride 144 = 9 x 16 bytes: the eight
+// lanes of a quarter-warp start 36 words apart, so 16-byte row reads are conflict-free; bytes 112..127 of a row are a zero
+// pad that is never rewritten, so eight bytes at ANY offset below 112 are three 32-bit loads and two funnel shifts with
+// no bounds test.
+#define PR_ROW 144
+#define PR_STAGES 2
+__device__ __forceinline__ void cp_async16(u32 saddr, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+struct RowFetch {
+    const char *row;                                                    // this line's 144-byte row in shared memory
+    __device__ __forceinline__ uint4 ld16r(u32 r) const { return *(const uint4 *)(row + r); }      // r = 16 j
+    __device__ __forceinline__ int byter(u32 r) const { return (int)(unsigned char)row[r]; }
+    __device__ __forceinline__ u64 f8(u32 r) const {                   // r + 8 <= 120
+        const u32 *q = (const u32 *)(row + (r & ~3u)); const u32 sh = (r & 3u) * 8u;
+        const u32 a = q[0], b = q[1], c = q[2];
+        return (u64)__funnelshift_r(a, b, sh) | ((u64)__funnelshift_r(b, c, sh) << 32);
+    }
+};
+__device__ __forceinline__ u64 fetch8r(const RowFetch &f, u32 r) { return f.f8(r); }
+
+static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
+    extern __shared__ __align__(16) char s_rows[];                     // [PR_STAGES][256][PR_ROW]
+    __shared__ u32 s_st[PR_STAGES][256];                               // the staged line's start (relative to ws), or ~0 when not staged
     const WinState *st = p.st;
-    if (!st->path_old) return;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const u64 limit = st->total;
     const int tid = threadIdx.x;
 #pragma unroll
-    for (int j = 28; j < LF_WORDS; ++j) s_line[j][tid] = 0;           // the pad words behind the 112 staged bytes (never rewritten)
+    for (int b = 0; b < PR_STAGES; ++b) *(uint4 *)(s_rows + ((size_t)b * 256 + tid) * PR_ROW + 112) = make_uint4(0, 0, 0, 0);
     const u32 n_round = (n_lines + 255u) & ~255u;                     // whole CTAs stay in the loop (barriers below)
-    for (u32 i = blockIdx.x * blockDim.x + tid; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool active = i < n_lines;
-        u32 start = 0;
-        if (active) { start = i ? p.nl_pos[i - 1] + 1 : 0; if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu; }
-        const u64 a = ws + start;
-        LineFetch lf; lf.buf = p.buf; lf.col = &s_line[0][tid]; lf.A = a & ~(u64)15;
-        const bool staged = active && a + 144 <= limit;
-        if (staged) {
-            const uint4 *src = (const uint4 *)(p.buf + lf.A);
-            uint4 w[7];
+    const u32 stride = gridDim.x * 256u;
+    u32 i = blockIdx.x * 256u + tid;
+    // start offset of a line (relative to ws); ~0 for a slot past the last line
+    auto line_start = [&](u32 k) -> u32 { return k < n_lines ? (k ? p.nl_pos[k - 1] + 1 : 0u) : 0xFFFFFFFFu; };
+    auto stage = [&](int b, u32 start) {                               // issue the copies of one line's prefix
+        u32 staged = 0xFFFFFFFFu;
+        if (start != 0xFFFFFFFFu) {
+            const u64 a = ws + start;
+            if (a + 144 <= limit) {
+                staged = start;
+                const u32 sa = smem_u32(s_rows + ((size_t)b * 256 + tid) * PR_ROW);
+                const char *g = p.buf + (a & ~(u64)15);
 #pragma unroll
-            for (int j = 0; j < 7; ++j) w[j] = __ldg(src + j);
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                s_line[4 * j][tid] = w[j].x; s_line[4 * j + 1][tid] = w[j].y; s_line[4 * j + 2][tid] = w[j].z; s_line[4 * j + 3][tid] = w[j].w;
-                lf.w[j] = w[j];
+                for (int j = 0; j < 7; ++j) cp_async16(sa + 16 * j, g + 16 * j);
             }
         }
-        s_A[tid] = staged ? lf.A : ~(u64)0;
-        __syncthreads();                                               // neighbours read each other's columns
+        s_st[b][tid] = staged;
+        cp_async_commit();
+    };
+    u32 start_cur = i < n_round ? line_start(i) : 0xFFFFFFFFu;
+    u32 start_nxt = i + stride < n_round ? line_start(i + stride) : 0xFFFFFFFFu;
+    if (i < n_round) stage(0, start_cur);
+    int b = 0;
+    for (; i < n_round; i += stride, b ^= 1) {
+        const bool active = i < n_lines;
+        // next round's copies go out first, then the start offset of the round after it is fetched
+        const bool more = i + stride < n_round;
+        if (more) stage(b ^ 1, start_nxt);
+        const u32 start_nn = (more && i + 2 * stride < n_round) ? line_start(i + 2 * stride) : 0xFFFFFFFFu;
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();                                               // neighbours read each other's rows
         if (active) {
+            if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu;
+            const u64 a = ws + start_cur;
+            RowFetch lf; lf.row = s_rows + ((size_t)b * 256 + tid) * PR_ROW;
+            const bool staged = s_st[b][tid] != 0xFFFFFFFFu;
             LineRec rec; u32 meta = 0;
             FastTok tok;
-            if (staged && parse_line_fast<LineFetch, false>(p, lf, a, limit, tok, rec, meta)) {
+            if (staged && parse_line_fast<RowFetch, false>(p, lf, a, limit, tok, rec, meta)) {
                 if (i > 0) {
-                    // QNAME equal to the previous line's?  That line's prefix sits in the neighbouring column.
-                    const u64 pa = ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0);
+                    // QNAME equal to the previous line's?  That line's prefix sits in the neighbouring row.
+                    const u32 pst = tid > 0 ? s_st[b][tid - 1] : 0xFFFFFFFFu;
+                    const u32 sp = (u32)((ws + pst) & 15u);            // the previous line's first byte inside its row
                     bool eq;
-                    if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_slow(p, ws, i, i - 1);   // operator>> skips leading blanks
-                    else if (tid > 0 && s_A[tid - 1] != ~(u64)0 && (u32)(pa - s_A[tid - 1]) + tok.t0 + 1 <= 112) {   // inside the neighbour's staged bytes
-                        LineFetch lp; lp.buf = p.buf; lp.col = &s_line[0][tid - 1]; lp.A = s_A[tid - 1];
-                        const u32 so = (u32)(a - lf.A), sp = (u32)(pa - lp.A);
-                        eq = true;
-                        for (u32 k = 0; k < tok.t0 && eq; k += 8) {
-                            u64 x = fetch8r(lf, so + k), y = fetch8r(lp, sp + k);
-                            if (tok.t0 - k < 8) { const u64 m = (1ull << (8 * (tok.t0 - k))) - 1; x &= m; y &= m; }
-                            eq = x == y;
+                    if (pst != 0xFFFFFFFFu && sp + tok.t0 + 1 <= 112) {
+                        RowFetch lp; lp.row = lf.row - PR_ROW;
+                        if (is_blank(lp.byter(sp))) eq = qname_equal_slow(p, ws, i, i - 1);   // operator>> skips leading blanks
+                        else {
+                            const u32 so = (u32)(a & 15u);
+                            eq = true;
+                            for (u32 k = 0; k < tok.t0 && eq; k += 8) {
+                                u64 x = fetch8r(lf, so + k), y = fetch8r(lp, sp + k);
+                                if (tok.t0 - k < 8) { const u64 m = (1ull << (8 * (tok.t0 - k))) - 1; x &= m; y &= m; }
+                                eq = x == y;
+                            }
+                            eq = eq && is_ws(lp.byter(sp + tok.t0));
                         }
-                        eq = eq && is_ws(lp.byter(sp + tok.t0));
-                    } else {
-                        GlobalFetch gf; gf.buf = p.buf; gf.A = 0;
-                        eq = qname_eq_fetch(gf, a, pa, tok.t0);
+                    } else {                                           // first thread of the CTA, or a line the staging skipped
+                        const u64 pa = ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0);
+                        if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_slow(p, ws, i, i - 1);
+                        else { GlobalFetch gf; gf.buf = p.buf; gf.A = 0; eq = qname_eq_fetch(gf, a, pa, tok.t0); }
                     }
                     if (eq) meta |= LM_EQ;
                 }
@@ -834,9 +819,11 @@ static __global__ void __launch_bounds__(256) k_parse(S2PParams p) {
             if (meta & LM_KEEP) p.rec[i] = rec;
             p.lmeta[i] = (u8)meta;
         }
-        __syncthreads();                                               // columns are rewritten by the next round
+        __syncthreads();                                               // this round's rows are the target of the next round's copies
+        start_cur = start_nxt; start_nxt = start_nn;
     }
 }
+#define PR_SMEM (PR_STAGES * 256 * PR_ROW)
 
 // ------------------------------------------------------------------------------------------------ K3: groups
 struct Seg { u32 pos, right0, left1, right1, leftClip, rightClip, mappable; int segCnt; bool minus; u16 chr; };
@@ -911,11 +898,8 @@ static __device__ __noinline__ bool qname_equal_abs(const S2PParams &p, u64 pa, 
     }
 }
 
-// EQ of line q (its QNAME equals line q-1's), evaluating it now when the fused kernel could not
-__device__ __forceinline__ bool line_eq(const S2PParams &p, u64 ws, u32 q, u32 mq) {
-    if (mq & LM_EQ_UNK) return q > 0 && qname_equal_slow(p, ws, q, q - 1);
-    return (mq & LM_EQ) != 0;
-}
+// EQ of line q: its QNAME equals line q-1's (evaluated by K2)
+__device__ __forceinline__ bool line_eq(const S2PParams &, u64, u32, u32 mq) { return (mq & LM_EQ) != 0; }
 __device__ __forceinline__ u32 line_len_of(const S2PParams &p, u32 q) { return p.nl_pos[q] - (q ? p.nl_pos[q - 1] + 1 : 0); }
 
 // bytewise order of two chromosome names (std::string::compare)
@@ -1057,7 +1041,6 @@ __device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32
 static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
     WinState *st = p.st;
-    if (!st->path_old) return;
     if (threadIdx.x < ST_NCOUNTER) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const u32 n_lines = st->n_lines;
@@ -1334,7 +1317,6 @@ static __device__ __noinline__ void fs_write_pair_line_bytes(const char *buf, u6
 static __global__ void __launch_bounds__(1024) k_emit_prefix(S2PParams p) {
     __shared__ u32 s_w[4][32];
     WinState *st = p.st;
-    if (!st->path_old) return;
     const u32 n_sub = (st->n_lines + EMIT_TILE - 1) / EMIT_TILE;
     const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const u32 per = (n_sub + 1023u) / 1024u;
@@ -1363,7 +1345,6 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
     __shared__ u32 s_w[2][EMIT_NT][3][EMIT_THREADS / 32];
     WinState *st = p.st;
-    if (!st->path_old) return;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1449,6 +1430,7 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
                         p.out_pairs[o] = r;
                     } else atomicOr(&st->err, S2P_ERR_PAIRS);
                 }
+                if (p.out_line_off && p.emit_text && base_pairs + e_idx < p.out_line_off_cap) p.out_line_off[base_pairs + e_idx] = t_off + t_run;
                 ++e_idx;
                 if (p.emit_text && text_fits) {
                     // (byte-wise on purpose: the word-wise OR writer of the strip path is a dependent chain through its accumulator and
@@ -1491,7 +1473,6 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
 // One warp per line: the lines of emitted groups are copied verbatim (with their '\n').
 static __global__ void __launch_bounds__(256) k_copy_sam(S2PParams p) {
     const WinState *st = p.st;
-    if (!st->path_old) return;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws, base = st->out_sam;
     const int lane = threadIdx.x & 31;

@@ -247,8 +247,8 @@ def test_owner_partition_then_dedup_bin_equals_unsharded(oracle, world):
     off = 0
     for r in range(world):
         s = seg[off:off + counts[r]]
-        assert sorted(s.tobytes()[i:i + 16] for i in range(0, len(s) * 16, 16)) == \
-            sorted(p[own == r].tobytes()[i:i + 16] for i in range(0, counts[r] * 16, 16))
+        as_rows = lambda a: np.sort(np.frombuffer(a.tobytes(), dtype="V16"))      # the segment as a multiset of 16-byte records
+        assert np.array_equal(as_rows(s), as_rows(p[own == r]))
         ds = to_dev(s) if len(s) else torch.empty(16, dtype=torch.uint8, device="cuda")
         got, nnz = ws.dedup_bin(ds.data_ptr(), len(s), HG38_LEN, res, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n, max_lane=1)
         all_kept.append(np.frombuffer(ds[:got * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE))

@@ -10,19 +10,6 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(autouse=True, params=["tile", "multi"])
-def s2p_path(request):
-    """Every test runs through the single-pass tile path (default) and through the multi-kernel path alone (MICROCKET_FUSED=0,
-    read at context creation): the second is also what takes over a window the tile path gives up."""
-    old = os.environ.get("MICROCKET_FUSED")
-    os.environ["MICROCKET_FUSED"] = "1" if request.param == "tile" else "0"
-    yield request.param
-    if old is None:
-        os.environ.pop("MICROCKET_FUSED", None)
-    else:
-        os.environ["MICROCKET_FUSED"] = old
-
-
 def rd(name):
     return open(os.path.join(G, name), "rb").read()
 
@@ -164,7 +151,7 @@ def test_sharded_contexts_reproduce_the_selfcircle_log_value(oracle):
         s.close()
 
 
-def test_reset_and_kernel_timing(oracle, s2p_path):
+def test_reset_and_kernel_timing(oracle):
     sam = mk.synth_host(8, "flash", "hg38", 0, 5000)
     op, _, ost = oracle.sam2pairs(sam, "flash", threads=8, write_sam=False)
     s = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False))
@@ -174,10 +161,7 @@ def test_reset_and_kernel_timing(oracle, s2p_path):
         p, _, st = s.run(sam)
         assert p == op and st.log_text() == ost.log_text()
     t = s.kernel_times()
-    if s2p_path == "tile":
-        assert t["k_ft_tile"][1] >= 3 and t["k_ft_tile"][0] > 0 and t["k_ft_gather"][1] >= 3
-    else:
-        assert t["k_scan_chunks"][1] >= 3 and t["k_scan_chunks"][0] > 0 and t["k_emit"][1] >= 3
+    assert t["k_scan_chunks"][1] >= 3 and t["k_scan_chunks"][0] > 0 and t["k_emit"][1] >= 3 and t["k_parse"][0] > 0
     assert s.launches() > 0
     s.close()
 
@@ -195,7 +179,7 @@ def test_short_lines_take_the_lookback_scan(oracle, window):
     assert p == op and so == osam and st.log_text() == ost.log_text()
 
 
-# ---------------------------------------------------------------------------------------------- tile-path geometry cases
+# ---------------------------------------------------------------------------------------------- geometry cases
 def _line(q, flag, chrom, pos, mapq, cigar, seqlen=100, tail=b""):
     return b"\t".join([q, str(flag).encode(), chrom, str(pos).encode(), str(mapq).encode(), cigar, b"*", b"0", b"0",
                        b"A" * seqlen, b"F" * seqlen]) + tail + b"\n"
@@ -210,8 +194,7 @@ def _check(oracle, sam, mode, window=0, chunk=None):
 
 
 def test_long_lines_cross_halos_and_tiles(oracle):
-    """Lines of 3 KiB (longer than the 2 KiB halos), 40 KiB and 300 KiB (longer than a 128 KiB tile): tiles without any line
-    start, heads whose predecessor / successor lies outside the scanned halo (byte-level walks)."""
+    """Lines of 3 KiB, 40 KiB and 300 KiB: scan chunks without any line start, line prefixes far apart."""
     import random
     rnd = random.Random(5)
     out = []
@@ -251,9 +234,9 @@ def test_groups_with_many_dropped_and_many_kept_lines(oracle):
     _check(oracle, sam, "flash")
 
 
-def test_tile_text_overflow_falls_back(oracle):
-    """Read ids of 220 bytes on minimal lines: more pair text per 128 KiB tile than the tile scratch holds, so the window is
-    handed to the multi-kernel path; the output must not change."""
+def test_long_read_ids_on_minimal_lines(oracle):
+    """Read ids of 220 bytes on minimal lines: QNAMEs longer than the staged line prefix (comparison and read-id copy go back
+    to global memory), more pair text per emit tile than its shared-memory stage holds."""
     out = []
     for i in range(6000):
         q = (b"Q%06d" % i) + b"x" * 213
