@@ -32,6 +32,12 @@ HG38_LEN = [248956422, 133797422, 135086622, 133275309, 114364328, 107043718, 10
 RES = 5000
 SEED = 0x4D4B0002
 METRIC = "valid pairs/sec (SAM->dedup->binned)"
+DUP_PER_1024 = 128          # 12.5 % of the read groups re-use the fragment of another group anywhere in the job (PCR duplicates
+                            # with their own read ids, crossing shard boundaries): ~11 % of the pairs are removed by the dedup
+
+
+def synth_opts(mk, universe):
+    return mk.synth_opts(dup_per_1024=DUP_PER_1024, dup_universe=universe)
 
 
 def measured_peak():
@@ -75,19 +81,14 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def synth_to_device(torch, mk, first, count, device):
+def synth_to_device(torch, mk, first, count, device, universe):
     """→ (uint8 cuda tensor holding the SAM text, n_bytes)"""
-    L = mk.lib()
-    n = C.c_size_t()
-    L.check(L.L.mk_synth_device(device, SEED, 0, 0, first, count, None, 0, C.byref(n), None))
-    buf = torch.empty(n.value + 256, dtype=torch.uint8, device=f"cuda:{device}")
-    L.check(L.L.mk_synth_device(device, SEED, 0, 0, first, count, buf.data_ptr(), n.value, C.byref(n), None))
-    return buf, n.value
+    return mk.synth_device(torch, SEED, "flash", "hg38", first, count, device=device, opts=synth_opts(mk, universe))
 
 
-def reference_sample(torch, mk, n_groups, device, tmpdir):
+def reference_sample(torch, mk, n_groups, device, tmpdir, universe):
     """Write the first n_groups of the workload to a file for the CPU arm."""
-    buf, nb = synth_to_device(torch, mk, 0, n_groups, device)
+    buf, nb = synth_to_device(torch, mk, 0, n_groups, device, universe)
     path = os.path.join(tmpdir, "sample.sam")
     host = buf[:nb].cpu().numpy()
     with open(path, "wb") as f:
@@ -136,8 +137,9 @@ def run_reference(args):
     sample_groups = args.cpu_groups
     tmpdir = tempfile.mkdtemp(prefix="mkbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
-        path, nb = reference_sample(torch, mk, sample_groups, 0, tmpdir)
+        path, nb = reference_sample(torch, mk, sample_groups, 0, tmpdir, args.groups * max(1, args.gpus))
         times, pairs, kind = [], 0, "reference"
+        args.warmup = min(args.warmup, 1)              # one pass warms the page cache; every further pass costs ~30 s
         for it in range(args.warmup + args.steps):
             pairs, sec, kind = cpu_pipeline_once(path, tmpdir, threads)
             if it >= args.warmup:
@@ -159,8 +161,116 @@ def run_reference(args):
 def workload_config(args, world, groups):
     return {"workload": "BASELINE configs[1]: hg38 Micro-C 150-cycle stitched-read SAM (flash mode), sam2pairs + coordinate dedup + 5kb binning",
             "read_groups_per_gpu": groups, "genome": "hg38", "mode": "flash", "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
-            "seed": SEED, "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
+            "seed": SEED, "duplicates": f"{DUP_PER_1024}/1024 of the read groups copy the fragment of another group of the whole job (all shards)", "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
             "parallelism": f"shard{world}: parse by read chunk, dedup keys all-to-all by hash(chr1,chr2,pos1/{RES}), COO owner-computes"}
+
+
+class Pipeline:
+    """The timed path on one rank: sam2pairs over the rank's resident shard -> (N > 1: owner partition + all-to-all) ->
+    coordinate dedup + 5 kb binning with one sort.  Used by the timed loop and by the reduced-size verification."""
+
+    def __init__(self, torch, mk, dist, groups, world, local, window_bytes):
+        self.torch, self.mk, self.dist, self.world = torch, mk, dist, world
+        dev = torch.device(f"cuda:{local}")
+        self.cap_pairs = int(groups * (1.0 if world == 1 else 1.3)) + 4096
+        self.text = torch.empty(groups * 100 + (1 << 20), dtype=torch.uint8, device=dev)
+        self.pairs = torch.empty(self.cap_pairs * 16, dtype=torch.uint8, device=dev)
+        self.ws = mk.PairsWorkspace(self.cap_pairs, device=local)
+        self.recv = torch.empty(self.cap_pairs * 16, dtype=torch.uint8, device=dev) if world > 1 else None
+        self.b1 = torch.empty(self.cap_pairs, dtype=torch.int32, device=dev); self.b2 = torch.empty_like(self.b1); self.cnt = torch.empty_like(self.b1)
+        self.s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local,
+                                             window_bytes=window_bytes, sharded=(world > 1)), HG38)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.src = self.pairs
+
+    def run(self, sam, nbytes, pair_events=None, text_len=None):
+        torch = self.torch
+        self.s2p.reset()
+        io = self.s2p.run_device(sam.data_ptr(), nbytes, True, self.text.data_ptr(), self.text.numel(), self.pairs.data_ptr(), self.cap_pairs,
+                                 stream=self.stream)
+        n = io.n_pairs
+        if text_len is not None:
+            text_len[0] = io.pairs_text_len
+        src = self.pairs
+        if self.world > 1:
+            from microcket_b200 import shard
+            n, src = shard.exchange_pairs(self.mk, torch, self.dist, self.ws, self.pairs, n, self.recv, self.cap_pairs, RES, self.stream)
+        # duplicate removal and 5 kb binning share one sort (mk_pairs_dedup_bin_device)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        kept, nnz = self.ws.dedup_bin(src.data_ptr(), n, HG38_LEN, RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
+                                      stream=self.stream)
+        eb.record()
+        if pair_events is not None:
+            pair_events.append((ea, eb, n))
+        self.src = src
+        return io.n_pairs, kept, nnz
+
+    def close(self):
+        self.s2p.close(); self.ws.close()
+
+
+def verify_sharded(torch, mk, np, dist, args, world, rank, local):
+    """Untimed and ASSERTED: the N-GPU path (shard by read chunk -> sam2pairs -> owner partition -> all-to-all -> dedup + binning
+    per owner) at reduced size.  Every rank's kept pairs and COO triplets are gathered; rank 0 compares their union with (a) the
+    CPU oracle (sam2pairs + coordinate dedup + binning over the whole input) and (b) the single-GPU path over the whole input."""
+    import oracle_lib
+    V = args.verify_groups
+    universe = V * world
+    dev = torch.device(f"cuda:{local}")
+    sam, nb = synth_to_device(torch, mk, rank * V, V + (1 if rank + 1 < world else 0), local, universe)   # + the next shard's first group:
+    pipe = Pipeline(torch, mk, dist, V + 1, world, local, 64 << 20)                                        # only the stream's last group is dropped
+    n_pairs, kept, nnz = pipe.run(sam, nb)
+    st = pipe.s2p.finish(0, 0)
+    # gather (padded to the largest rank)
+    sizes = torch.tensor([kept, nnz, n_pairs, int(st.groups)], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [x.tolist() for x in all_sizes]
+    mk_, mz = max(x[0] for x in all_sizes), max(x[1] for x in all_sizes)
+    kp = torch.zeros(mk_ * 16, dtype=torch.uint8, device=dev); kp[:kept * 16] = pipe.src[:kept * 16]
+    coo = torch.zeros(mz * 3, dtype=torch.int32, device=dev)
+    coo[:nnz] = pipe.b1[:nnz]; coo[mz:mz + nnz] = pipe.b2[:nnz]; coo[2 * mz:2 * mz + nnz] = pipe.cnt[:nnz]
+    kps = [torch.empty_like(kp) for _ in range(world)]; coos = [torch.empty_like(coo) for _ in range(world)]
+    dist.all_gather(kps, kp); dist.all_gather(coos, coo)
+    pipe.close()
+    ok, why = True, ""
+    if rank == 0:
+        got_pairs = np.concatenate([np.frombuffer(kps[r][:all_sizes[r][0] * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE) for r in range(world)])
+        got_coo = np.concatenate([np.stack([coos[r][k * mz:k * mz + all_sizes[r][1]].cpu().numpy().astype(np.uint32) for k in range(3)], axis=1)
+                                  for r in range(world)])
+        got_coo = got_coo[np.lexsort((got_coo[:, 1], got_coo[:, 0]))]
+        key = lambda a: np.lexsort((a["strands"], a["pos2"], a["chr2"], a["pos1"], a["chr1"], a["lane"]))
+        # (a) the CPU oracle over the whole input
+        sam1, nb1 = synth_to_device(torch, mk, 0, universe, local, universe)
+        host = sam1[:nb1].cpu().numpy().tobytes()                        # (the device generator's bytes equal the host generator's: tests/)
+        orc = oracle_lib.load()
+        op, _, ost = orc.sam2pairs(host, "flash", threads=8, write_sam=False)
+        arr, n = orc.pairs_parse(op, HG38)
+        keep, n_keep = orc.coord_dedup(arr, n)
+        b1, b2, ct = orc.bin_coo(arr, n, keep, HG38_LEN, RES)
+        exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n][np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
+        checks = {"groups": sum(x[3] for x in all_sizes) == ost.groups, "pairs": sum(x[2] for x in all_sizes) == n,
+                  "kept": len(got_pairs) == n_keep and np.array_equal(got_pairs[key(got_pairs)], exp[key(exp)]),
+                  "coo": got_coo[:, 0].tolist() == b1 and got_coo[:, 1].tolist() == b2 and got_coo[:, 2].tolist() == ct,
+                  "duplicates_removed": n - n_keep > 0.05 * n}
+        # (b) the single-GPU path over the whole input
+        one = Pipeline(torch, mk, None, universe, 1, local, 64 << 20)
+        p1, k1, z1 = one.run(sam1, nb1)
+        single = np.frombuffer(one.src[:k1 * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+        checks["equals_single_gpu"] = (p1 == n and k1 == n_keep and z1 == len(b1) and np.array_equal(single[key(single)], got_pairs[key(got_pairs)])
+                                       and one.cnt[:z1].cpu().numpy().astype(np.uint32).tolist() == got_coo[:, 2].tolist())
+        one.close()
+        ok = all(checks.values()); why = json.dumps(checks)
+        print(f"[bench] verified {world}-GPU path on {universe} read groups: {why}", file=sys.stderr)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.broadcast(flag, 0)
+    if int(flag.item()) != 1:
+        raise SystemExit(f"bench.py: the {world}-GPU result differs from the oracle / single-GPU result: {why}")
+    VERIFY["result"] = {"read_groups": universe, "asserted": True, "against": "CPU oracle and single-GPU path, kept pairs + COO of all ranks gathered"}
+
+
+VERIFY = {}
 
 
 def main():
@@ -170,11 +280,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--groups", type=int, default=int(os.environ.get("MK_BENCH_GROUPS", 100_000_000)), help="read groups per GPU")
-    ap.add_argument("--e2e-groups", type=int, default=int(os.environ.get("MK_BENCH_E2E_GROUPS", 6_000_000)))
-    ap.add_argument("--cpu-groups", type=int, default=int(os.environ.get("MK_BENCH_CPU_GROUPS", 2_000_000)))
+    ap.add_argument("--e2e-groups", type=int, default=int(os.environ.get("MK_BENCH_E2E_GROUPS", 0)), help="read groups of the end-to-end leg (0 = --groups)")
+    ap.add_argument("--cpu-groups", type=int, default=int(os.environ.get("MK_BENCH_CPU_GROUPS", 10_000_000)))
     ap.add_argument("--window-mb", type=int, default=int(os.environ.get("MK_BENCH_WINDOW_MB", 2040)))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed, asserted reduced-size verification of the N-GPU path")
+    ap.add_argument("--verify-groups", type=int, default=200_000, help="read groups per GPU of that verification")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -199,32 +311,15 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- resident workload
-    sam, nbytes = synth_to_device(torch, mk, rank * G, G, local)
-    text = torch.empty(G * 100 + (1 << 20), dtype=torch.uint8, device=dev)
-    cap_pairs = int(G * (1.0 if world == 1 else 1.3)) + 4096
-    pairs = torch.empty(cap_pairs * 16, dtype=torch.uint8, device=dev)
-    ws = mk.PairsWorkspace(cap_pairs, device=local)
-    recv = torch.empty(cap_pairs * 16, dtype=torch.uint8, device=dev) if world > 1 else None
-    b1 = torch.empty(cap_pairs, dtype=torch.int32, device=dev); b2 = torch.empty_like(b1); cnt = torch.empty_like(b1)
-    s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local,
-                                    window_bytes=args.window_mb << 20, sharded=(world > 1)), HG38)
+    universe = G * world
+    if world > 1 and not args.no_verify:
+        verify_sharded(torch, mk, np, dist, args, world, rank, local)      # raises (non-zero exit) when the N-GPU result is wrong
+    sam, nbytes = synth_to_device(torch, mk, rank * G, G, local, universe)
+    pipe = Pipeline(torch, mk, dist, G, world, local, args.window_mb << 20)
+    s2p, ws, cnt = pipe.s2p, pipe.ws, pipe.cnt
 
     def step():
-        s2p.reset()
-        io = s2p.run_device(sam.data_ptr(), nbytes, True, text.data_ptr(), text.numel(), pairs.data_ptr(), cap_pairs, stream=stream)
-        n = io.n_pairs
-        text_len[0] = io.pairs_text_len
-        src = pairs
-        if world > 1:
-            from microcket_b200 import shard
-            n, src = shard.exchange_pairs(mk, torch, dist, ws, pairs, n, recv, cap_pairs, RES, stream)
-        # duplicate removal and 5 kb binning share one sort (mk_pairs_dedup_bin_device)
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        kept, nnz = ws.dedup_bin(src.data_ptr(), n, HG38_LEN, RES, b1.data_ptr(), b2.data_ptr(), cnt.data_ptr(), cap_pairs, stream=stream)
-        eb.record()
-        pair_events.append((ea, eb, n))
-        return io.n_pairs, kept, nnz
+        return pipe.run(sam, nbytes, pair_events, text_len)
 
     pair_events = []
     text_len = [0]
@@ -276,6 +371,14 @@ def main():
     ms_step = ms_total / args.steps
     value = n_pairs_all / (ms_step / 1e3)
 
+    # ---- end to end through the host-buffer C ABI (pinned host SAM in; pairs text, kept pairs and COO out), every rank its shard
+    e2e_res = None
+    if not args.no_e2e:
+        del sam
+        pipe.text = pipe.pairs = pipe.recv = None
+        torch.cuda.empty_cache()
+        e2e_res = measure_e2e(torch, mk, np, dist, args, world, rank, local)
+
     if rank != 0:
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
@@ -297,10 +400,7 @@ def main():
     text_b = float(io_text_len)                        # bytes of pair text of one pass
     alg = {"k_scan_chunks": nbytes + 4 * lines, "k_chunk_index": 8 * lines,
            "k_parse": 117.0 * lines + 48.0 * groups, "k_group": lines + 80.0 * groups,
-           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 0.0,
-           # single-pass tile path: every SAM byte once, pair text + packed pairs written to the tile scratch;
-           # gather: the scratch read once and written once to the dense outputs
-           "k_ft_tile": nbytes + text_b + 16.0 * n_pairs, "k_ft_gather": 2.0 * (text_b + 16.0 * n_pairs)}
+           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 0.0}
     per_kernel = {}
     for k, (ms_k, n_k) in dk.items():
         if ms_k > 0 and n_k > 0:
@@ -338,15 +438,13 @@ def main():
         roofline["pairs_stage"] = {"error": str(e)}
 
     # ---- end to end through the host-buffer C ABI (pinned host SAM in; pairs text, packed pairs and COO out)
-    e2e = None
-    if not args.no_e2e and world == 1:
-        e2e = measure_e2e(torch, mk, np, args, local, ws)
+    e2e = e2e_res
     # ---- reference CPU path beside it (bounded sample)
     cpu = None
     if not args.no_cpu and world == 1:
         tmpdir = tempfile.mkdtemp(prefix="mkbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
-            path, nb = reference_sample(torch, mk, args.cpu_groups, local, tmpdir)
+            path, nb = reference_sample(torch, mk, args.cpu_groups, local, tmpdir, universe)
             threads = max(2, min(host_cores(), 8))
             p, sec, kind = cpu_pipeline_once(path, tmpdir, threads)
             cpu = {"value": p / sec, "unit": "pairs/s", "cores": threads, "kind": kind, "host_cores": host_cores(),
@@ -359,25 +457,58 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": dict(workload_config(args, world, G), sam_bytes_per_gpu=nbytes, pairs_per_step=n_pairs_all, kept_after_dedup=kept_all,
                            coo_cells=nnz_all, window_mb=args.window_mb),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checks": checks}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checks": checks,
+            "parity": "sam2pairs pinned by the reference binary (tests/); coordinate dedup + binning UNPINNED (no reference implementation "
+                      "exists: checked against oracle/pairs_oracle.c + numpy only) - that stage is %.1f of the %.1f ms step" % (
+                          roofline.get("pairs_stage", {}).get("ms_per_step", 0.0), ms_step),
+            "verify_sharded": VERIFY.get("result")}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
 
 
-def measure_e2e(torch, mk, np, args, local, ws):
-    E = min(args.e2e_groups, args.groups)
-    sam_d, nb = synth_to_device(torch, mk, 0, E, local)
-    host = torch.empty(nb, dtype=torch.uint8).pin_memory()
-    host.copy_(sam_d[:nb])
-    del sam_d
-    torch.cuda.synchronize()
-    out_text = torch.empty(E * 100 + (1 << 20), dtype=torch.uint8).pin_memory()
-    out_pairs = torch.empty((E + 1024) * 16, dtype=torch.uint8).pin_memory()
-    ob1 = torch.empty(E + 1024, dtype=torch.int32).pin_memory(); ob2 = torch.empty_like(ob1).pin_memory(); oc = torch.empty_like(ob1).pin_memory()
+def measure_e2e(torch, mk, np, dist, args, world, rank, local):
+    """The same path through the host-buffer C ABI: pinned host SAM pushed window by window (H2D inside), pair text and packed
+    pairs pulled to host memory (D2H inside), then duplicate removal + binning with the kept pairs and COO triplets brought back
+    to the host.  N > 1: every rank streams its own shard and the packed pairs cross NVLink (owner partition + all-to-all)
+    before the dedup.  Wall clock between barriers, max over ranks."""
+    E = min(args.e2e_groups or args.groups, args.groups)
+    dev = torch.device(f"cuda:{local}")
+    host = out_text = out_pairs = None
+    while True:                                    # the full-size leg needs ~75 GB of pinned host memory per rank: back off if the box cannot pin it
+        try:
+            sam_d, nb = synth_to_device(torch, mk, rank * E, E, local, E * world)
+            host = torch.empty(nb, dtype=torch.uint8).pin_memory()
+            host.copy_(sam_d[:nb])
+            del sam_d
+            torch.cuda.synchronize(); torch.cuda.empty_cache()
+            out_text = torch.empty(E * 56 + (1 << 20), dtype=torch.uint8).pin_memory()
+            out_pairs = torch.empty((E + 1024) * 16, dtype=torch.uint8).pin_memory()
+            ok = 1
+        except (RuntimeError, MemoryError) as e:
+            print(f"[bench] e2e: cannot stage {E} read groups in pinned memory ({str(e)[:80]}); halving", file=sys.stderr)
+            host = out_text = out_pairs = None
+            ok = 0
+        if dist is not None:                       # every rank runs the same size
+            f = torch.tensor([ok], dtype=torch.int32, device=dev); dist.all_reduce(f, op=dist.ReduceOp.MIN); ok = int(f.item())
+        if ok:
+            break
+        host = out_text = out_pairs = None
+        E //= 2
+        if E < 1_000_000:
+            return {"error": "pinned host memory"}
+    cap = int(E * (1.0 if world == 1 else 1.3)) + 4096
+    ob1 = torch.empty(cap, dtype=torch.int32).pin_memory(); ob2 = torch.empty_like(ob1).pin_memory(); oc = torch.empty_like(ob1).pin_memory()
+    ws = mk.PairsWorkspace(cap, device=local)
     W = 256 << 20
-    s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W), HG38)
-
+    s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W,
+                                    sharded=(world > 1)), HG38)
+    if world > 1:
+        from microcket_b200 import shard
+        d_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev); d_recv = torch.empty_like(d_pairs)
+        db1 = torch.empty(cap, dtype=torch.int32, device=dev); db2 = torch.empty_like(db1); dbc = torch.empty_like(db1)
+        kept_host = torch.empty(cap * 16, dtype=torch.uint8).pin_memory()
+        stream = torch.cuda.current_stream().cuda_stream
     phases = {"stream_ms": 0.0, "drain_finish_ms": 0.0, "pairs_ms": 0.0}
 
     def once():
@@ -397,29 +528,53 @@ def measure_e2e(torch, mk, np, args, local, ws):
             tl += a; pl += b
             if a == 0 and b == 0:
                 break
-        st = s2p.finish()
+        st = s2p.finish(0, 0) if world > 1 else s2p.finish()
         assert st.pairs == pl
         t_c = time.perf_counter()
-        kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, HG38_LEN, RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), E + 1024)
+        if world == 1:
+            kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, HG38_LEN, RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), cap)
+            moved = pl
+        else:
+            d_pairs[:pl * 16].copy_(out_pairs[:pl * 16], non_blocking=True)
+            n, src = shard.exchange_pairs(mk, torch, dist, ws, d_pairs, pl, d_recv, cap, RES, stream)
+            kept, nnz = ws.dedup_bin(src.data_ptr(), n, HG38_LEN, RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
+            kept_host[:kept * 16].copy_(src[:kept * 16], non_blocking=True)
+            ob1[:nnz].copy_(db1[:nnz], non_blocking=True); ob2[:nnz].copy_(db2[:nnz], non_blocking=True); oc[:nnz].copy_(dbc[:nnz], non_blocking=True)
+            torch.cuda.synchronize()
+            moved = pl
         t_d = time.perf_counter()
         phases["stream_ms"] += (t_b - t_a) * 1e3; phases["drain_finish_ms"] += (t_c - t_b) * 1e3; phases["pairs_ms"] += (t_d - t_c) * 1e3
-        return pl, tl, kept, nnz
+        return pl, tl, kept, nnz, moved
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(2):
         once()
-    torch.cuda.synchronize()
     for k in phases:
         phases[k] = 0.0
+    reps = max(2, min(args.steps, 3))
+    barrier()
     t0 = time.perf_counter()
-    reps = max(2, min(args.steps, 5))
     for _ in range(reps):
-        pl, tl, kept, nnz = once()
-    torch.cuda.synchronize()
+        pl, tl, kept, nnz, moved = once()
+    barrier()
     sec = (time.perf_counter() - t0) / reps
-    s2p.close()
-    return {"value": pl / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(nb + pl * 16), "d2h_bytes_per_step": int(tl + pl * 16 + kept * 16 + nnz * 12),
-            "read_groups": E, "ms_per_step": sec * 1e3, "phases_ms": {k: v / reps for k, v in phases.items()},
-            "api": "mk_s2p_push/pull/pull_packed/finish + mk_pairs_dedup_bin_host, host pinned buffers, wall clock incl. all copies"}
+    s2p.close(); ws.close()
+    t = torch.tensor([sec, float(pl), float(nb + moved * 16), float(tl + pl * 16 + kept * 16 + nnz * 12)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        sec, pl_all, h2d, d2h = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+    else:
+        pl_all, h2d, d2h = float(pl), float(t[2]), float(t[3])
+    return {"value": pl_all / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "read_groups_per_gpu": E, "ms_per_step": sec * 1e3, "phases_ms_rank0": {k: v / reps for k, v in phases.items()},
+            "api": "mk_s2p_push/pull/pull_packed/finish from pinned host buffers" +
+                   (" + mk_pairs_dedup_bin_host" if world == 1 else " + H2D of the packed pairs, owner partition, NCCL all-to-all, mk_pairs_dedup_bin_device, D2H of kept pairs and COO") +
+                   "; wall clock incl. all copies, max over ranks"}
 
 
 if __name__ == "__main__":

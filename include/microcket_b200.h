@@ -208,6 +208,28 @@ int  mk_pairs_dedup_bin_host(mk_pairs_ws *, mk_pair *pairs, size_t n, int do_ded
                              uint32_t *bin1, uint32_t *bin2, uint32_t *cnt, size_t cap, size_t *n_kept, size_t *nnz);
 uint64_t mk_pairs_launch_count(mk_pairs_ws *);
 
+/* ------------------------------------------------------------------ dense multi-resolution histogram */
+/* Contact counts of every requested resolution from ONE read of the packed pairs (the `-r` list of microcket:98,176-180 as
+ * consumed by `juicer_tools pre`, microcket:525-529): per resolution an upper-triangle u32 matrix in HBM, the diagonals
+ * privatised in shared memory, off-diagonal cells as global atomics.  For resolutions whose triangle fits in memory
+ * (mk_hist_cells; hg38 at 100 kb: 1.9 GB); finer ones use mk_pairs_bin_device.  d_cells (may be NULL, or hold NULLs):
+ * caller-owned, ZEROED matrices — e.g. torch tensors that an NCCL reduce sums across GPUs before mk_hist_coo_device. */
+typedef struct mk_hist mk_hist;
+int  mk_hist_cells(const uint32_t *chrom_len, int n_chrom, uint32_t res, uint64_t *n_bins, uint64_t *n_cells);
+int  mk_hist_create(int device, const uint32_t *chrom_len, int n_chrom, const uint32_t *res, int n_res,
+                    uint32_t *const *d_cells, mk_hist **);
+void mk_hist_destroy(mk_hist *);
+int  mk_hist_reset(mk_hist *, void *stream);                       /* zero every matrix */
+/* Adds n pairs to every matrix (may be called once per window).  Pairs with an unknown chromosome id or a position past
+ * the chromosome end are left out of EVERY resolution and counted (mk_hist_dropped). */
+int  mk_hist_add_device(mk_hist *, const mk_pair *d_pairs, size_t n, const uint16_t *chrom_id_map, int n_map, void *stream);
+int  mk_hist_matrix(mk_hist *, int res_idx, uint32_t **d_cells, uint64_t *n_cells, uint64_t *n_bins);
+/* Non-zero cells of one resolution as COO triplets sorted by (bin1, bin2), bin1 <= bin2; *total = sum of the counts. */
+int  mk_hist_coo_device(mk_hist *, int res_idx, uint32_t *d_bin1, uint32_t *d_bin2, uint32_t *d_cnt, size_t cap,
+                        size_t *nnz, uint64_t *total, void *stream);
+uint64_t mk_hist_dropped(mk_hist *);
+uint64_t mk_hist_launch_count(mk_hist *);
+
 /* ------------------------------------------------------------------ synthetic inputs (tests / bench) */
 /* Same bytes on host and device for a given (seed, mode, genome, first, count).  mode: 0 flash, 1 unc,
  * 2 interleaved FASTQ.  genome: 0 hg38, 1 mm10.  Returns bytes written in *n_out (or needed when buf == NULL). */

@@ -127,6 +127,13 @@ class Lib:
                            ("mk_pairs_sort_text_device", [vp, vp, sz, vp, vp, vp, P(C.c_uint16), i, C.c_uint32, vp, sz, P(sz), P(sz), vp]),
                            ("mk_pairs_filter_text_device", [vp, sz, vp, vp, vp, vp, sz, P(sz), vp]),
                            ("mk_pairs_chrom_ranks", [P(C.c_char_p), i, P(C.c_uint16)]),
+                           ("mk_hist_cells", [P(C.c_uint32), i, C.c_uint32, P(u64), P(u64)]),
+                           ("mk_hist_create", [i, P(C.c_uint32), i, P(C.c_uint32), i, P(vp), P(vp)]),
+                           ("mk_hist_destroy", [vp]), ("mk_hist_reset", [vp, vp]),
+                           ("mk_hist_add_device", [vp, vp, sz, P(C.c_uint16), i, vp]),
+                           ("mk_hist_matrix", [vp, i, P(vp), P(u64), P(u64)]),
+                           ("mk_hist_coo_device", [vp, i, vp, vp, vp, sz, P(sz), P(u64), vp]),
+                           ("mk_hist_dropped", [vp]), ("mk_hist_launch_count", [vp]),
                            ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
@@ -138,6 +145,9 @@ class Lib:
             L.mk_pairs_launch_count.restype = u64
         if hasattr(L, "mk_pairs_dropped"):
             L.mk_pairs_dropped.restype = u64
+        for name in ("mk_hist_dropped", "mk_hist_launch_count"):
+            if hasattr(L, name):
+                getattr(L, name).restype = u64
 
     def check(self, rc):
         if rc != 0:
@@ -436,6 +446,71 @@ class PairsWorkspace:
         self.lib.check(self.lib.L.mk_pairs_dedup_bin_host(self.h, pairs_ptr, n, int(do_dedup), cl, len(chrom_len), mp, nm, res,
                                                           b1_ptr, b2_ptr, c_ptr, cap, C.byref(kept), C.byref(nnz)))
         return kept.value, nnz.value
+
+
+class Hist:
+    """Dense multi-resolution contact histogram (csrc/hist.cu): add() packed pairs, then coo() per resolution."""
+
+    def __init__(self, chrom_len, resolutions, device=0, cells_ptrs=None):
+        self.lib = lib()
+        self.lib.require_gpu()
+        self.res = list(resolutions)
+        self.chrom_len = list(chrom_len)
+        cl = (C.c_uint32 * len(chrom_len))(*chrom_len)
+        rs = (C.c_uint32 * len(self.res))(*self.res)
+        ptrs = None
+        if cells_ptrs is not None:
+            ptrs = (C.c_void_p * len(self.res))(*cells_ptrs)
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.mk_hist_create(device, cl, len(chrom_len), rs, len(self.res), ptrs, C.byref(self.h)))
+
+    @staticmethod
+    def cells(chrom_len, res):
+        """→ (bins, cells of the upper triangle) at one resolution"""
+        cl = (C.c_uint32 * len(chrom_len))(*chrom_len)
+        nb, nc = C.c_uint64(), C.c_uint64()
+        L = lib()
+        L.check(L.L.mk_hist_cells(cl, len(chrom_len), res, C.byref(nb), C.byref(nc)))
+        return nb.value, nc.value
+
+    def close(self):
+        if self.h:
+            self.lib.L.mk_hist_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, d_pairs, n, chrom_id_map=None, stream=0):
+        if chrom_id_map is not None:
+            mp = (C.c_uint16 * len(chrom_id_map))(*chrom_id_map); nm = len(chrom_id_map)
+        else:
+            mp, nm = None, 0
+        self.lib.check(self.lib.L.mk_hist_add_device(self.h, d_pairs, n, mp, nm, stream))
+
+    def reset(self, stream=0):
+        self.lib.check(self.lib.L.mk_hist_reset(self.h, stream))
+
+    def matrix(self, k):
+        """→ (device pointer, cells, bins) of resolution k's upper-triangle matrix"""
+        p, nc, nb = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self.lib.check(self.lib.L.mk_hist_matrix(self.h, k, C.byref(p), C.byref(nc), C.byref(nb)))
+        return p.value, nc.value, nb.value
+
+    def coo(self, k, d_bin1, d_bin2, d_cnt, cap, stream=0):
+        """→ (nnz, sum of counts)"""
+        nnz, tot = C.c_size_t(), C.c_uint64()
+        self.lib.check(self.lib.L.mk_hist_coo_device(self.h, k, d_bin1, d_bin2, d_cnt, cap, C.byref(nnz), C.byref(tot), stream))
+        return nnz.value, tot.value
+
+    def dropped(self):
+        return self.lib.L.mk_hist_dropped(self.h)
+
+    def launches(self):
+        return self.lib.L.mk_hist_launch_count(self.h)
 
 
 def chrom_ranks(names):

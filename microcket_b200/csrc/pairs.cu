@@ -138,24 +138,21 @@ __global__ void k_rle_finish(const u64 *key, const u32 *pos, const unsigned long
     }
 }
 
-// (bin1,bin2) key of every pair at one resolution.  Every field is checked (chromosome id inside the table, position inside
-// the chromosome's bins): an offender is counted in *bad, the host turns that into MK_ERR_INPUT, and its key is the all-ones
+// (bin1,bin2) key of every pair at one resolution.  Every field is checked (chromosome id inside the table, position not
+// past the chromosome's end — one rule for every resolution, so a pair is in all matrices or in none): an offender is counted in *bad, the host turns that into MK_ERR_INPUT, and its key is the all-ones
 // sentinel (sorted last, dropped by the run-length step) so that nothing is read or counted out of range.
 #define BIN_BAD_KEY 0xFFFFFFFFFFFFFFFFull
-__global__ void k_bin_keys(const mk_pair *p, u64 n, const u32 *chr_off /* per pair-chr id */, const u32 *chr_nb /* bins per id */, u32 n_ids,
+__global__ void k_bin_keys(const mk_pair *p, u64 n, const u32 *chr_off /* per pair-chr id */, const u32 *chr_len /* length per id */, u32 n_ids,
                            u32 res, u64 *key, unsigned long long *bad) {
     u32 nbad = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const uint4 r = ((const uint4 *)p)[i];
         const u32 pos1 = r.x, pos2 = r.y, c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
         u64 k = BIN_BAD_KEY;
-        if (c1 < n_ids && c2 < n_ids) {
-            const u32 q1 = pos1 / res, q2 = pos2 / res;
-            if (q1 < chr_nb[c1] && q2 < chr_nb[c2]) {
-                u32 a = chr_off[c1] + q1, b = chr_off[c2] + q2;
-                if (a > b) { u32 t = a; a = b; b = t; }          // upper triangle
-                k = ((u64)a << 32) | b;
-            }
+        if (c1 < n_ids && c2 < n_ids && pos1 <= chr_len[c1] && pos2 <= chr_len[c2]) {
+            u32 a = chr_off[c1] + pos1 / res, b = chr_off[c2] + pos2 / res;
+            if (a > b) { u32 t = a; a = b; b = t; }              // upper triangle
+            k = ((u64)a << 32) | b;
         }
         nbad += k == BIN_BAD_KEY;
         key[i] = k;
@@ -239,11 +236,11 @@ extern "C" int mk_pairs_bin_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_
     if (off[n_chrom] >= (1ull << 32)) { mk_set_error("mk_pairs_bin_device: more than 2^32 bins"); return MK_ERR_CAPACITY; }
     const int n_ids = chrom_id_map ? n_map : n_chrom;
     if (n_ids > 65536) { mk_set_error("mk_pairs_bin_device: too many chromosome ids"); return MK_ERR_ARG; }
-    std::vector<u32> by_id(2 * (size_t)n_ids);                          // [offsets | bins per id], one upload
+    std::vector<u32> by_id(2 * (size_t)n_ids);                          // [offsets | lengths per id], one upload
     for (int i = 0; i < n_ids; ++i) {
         int c = chrom_id_map ? chrom_id_map[i] : i;
         if (c < 0 || c >= n_chrom) { mk_set_error("mk_pairs_bin_device: chromosome map entry %d out of range", i); return MK_ERR_ARG; }
-        by_id[i] = (u32)off[c]; by_id[n_ids + i] = chrom_len[c] / res + 1;
+        by_id[i] = (u32)off[c]; by_id[n_ids + i] = chrom_len[c];
     }
     MK_CUDA(cudaMemcpyAsync(w->chr_off.p, by_id.data(), by_id.size() * 4, cudaMemcpyHostToDevice, s));
     MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
@@ -432,7 +429,7 @@ __device__ __forceinline__ u64 take_bits(u64 &lo, u64 &hi, u32 width) {         
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, const u32 *off_by_id, const u32 *nb_by_id, PackCfg c, uint4 *key,
+__global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, const u32 *off_by_id, const u32 *len_by_id, PackCfg c, uint4 *key,
                                                    unsigned long long *bad) {
     u32 nbad = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
@@ -443,7 +440,7 @@ __global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, cons
         bool ok = c1 < c.n_ids && c2 < c.n_ids && lane <= c.max_lane;
         if (ok) {
             const u32 q1 = pos1 / c.res, q2 = pos2 / c.res;
-            ok = q1 < nb_by_id[c1] && q2 < nb_by_id[c2];
+            ok = pos1 <= len_by_id[c1] && pos2 <= len_by_id[c2];
             if (ok) {
                 u32 a = off_by_id[c1] + q1, b = off_by_id[c2] + q2;
                 u32 r1 = pos1 - q1 * c.res, r2 = pos2 - q2 * c.res;
@@ -600,14 +597,14 @@ extern "C" int mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *w, mk_pair *d_pair
     if (off[n_chrom] >= (1ull << 32)) { mk_set_error("mk_pairs_dedup_bin_device: more than 2^32 bins"); return MK_ERR_CAPACITY; }
     const int n_ids = chrom_id_map ? n_map : n_chrom;
     if (n_ids > 16384 || n_chrom > 16384) { mk_set_error("mk_pairs_dedup_bin_device: too many chromosomes"); return MK_ERR_ARG; }
-    // one upload: [by_id offsets (16384 u32)] [bins per id (16384 u32)] [dec_off (16384 u32)] [dec_id (16384 u16)]
+    // one upload: [by_id offsets (16384 u32)] [length per id (16384 u32)] [dec_off (16384 u32)] [dec_id (16384 u16)]
     std::vector<u32> tab(3 * 16384 + 8192, 0);
     u32 *by_id = tab.data(), *nb_id = by_id + 16384, *dec_off = nb_id + 16384; u16 *dec_id = (u16 *)(dec_off + 16384);
     for (int c = 0; c < n_chrom; ++c) { dec_off[c] = (u32)off[c]; dec_id[c] = 0xFFFF; }
     for (int i = 0; i < n_ids; ++i) {
         int c = chrom_id_map ? chrom_id_map[i] : i;
         if (c < 0 || c >= n_chrom) { mk_set_error("mk_pairs_dedup_bin_device: chromosome map entry %d out of range", i); return MK_ERR_ARG; }
-        by_id[i] = (u32)off[c]; nb_id[i] = chrom_len[c] / res + 1;
+        by_id[i] = (u32)off[c]; nb_id[i] = chrom_len[c];
         if (dec_id[c] == 0xFFFF) dec_id[c] = (u16)i;
     }
     PackCfg pc; pc.res = res; pc.nb = bits_for(off[n_chrom]) /* one value past the last bin stays free for the all-ones key */;

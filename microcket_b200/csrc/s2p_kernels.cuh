@@ -753,11 +753,19 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
     const u32 n_round = (n_lines + 255u) & ~255u;                     // whole CTAs stay in the loop (barriers below)
     const u32 stride = gridDim.x * 256u;
     u32 i = blockIdx.x * 256u + tid;
-    // start offset of a line (relative to ws); ~0 for a slot past the last line
-    auto line_start = [&](u32 k) -> u32 { return k < n_lines ? (k ? p.nl_pos[k - 1] + 1 : 0u) : 0xFFFFFFFFu; };
-    auto stage = [&](int b, u32 start) {                               // issue the copies of one line's prefix
+    // start offset of a line (relative to ws) is the previous newline + 1.  The RAW newline position is what is prefetched two
+    // rounds ahead (0xFFFFFFFE for a slot past the last line, 0xFFFFFFFF for line 0): no arithmetic touches the loaded value
+    // before the round that uses it, so the load's latency is never waited for (ncu: 11 % of the stall samples sat on the
+    // `+ 1` right behind the load)
+    auto line_nl = [&](u32 k) -> u32 {
+        u32 v = 0xFFFFFFFEu;
+        if (k < n_lines) { v = 0xFFFFFFFFu; if (k) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p.nl_pos + (k - 1))); }
+        return v;
+    };
+    auto stage = [&](int b, u32 nl) {                                  // issue the copies of one line's prefix
         u32 staged = 0xFFFFFFFFu;
-        if (start != 0xFFFFFFFFu) {
+        const u32 start = nl + 1u;
+        if (nl != 0xFFFFFFFEu) {
             const u64 a = ws + start;
             if (a + 144 <= limit) {
                 staged = start;
@@ -770,21 +778,21 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
         s_st[b][tid] = staged;
         cp_async_commit();
     };
-    u32 start_cur = i < n_round ? line_start(i) : 0xFFFFFFFFu;
-    u32 start_nxt = i + stride < n_round ? line_start(i + stride) : 0xFFFFFFFFu;
-    if (i < n_round) stage(0, start_cur);
+    u32 nl_cur = i < n_round ? line_nl(i) : 0xFFFFFFFEu;
+    u32 nl_nxt = i + stride < n_round ? line_nl(i + stride) : 0xFFFFFFFEu;
+    if (i < n_round) stage(0, nl_cur);
     int b = 0;
     for (; i < n_round; i += stride, b ^= 1) {
         const bool active = i < n_lines;
         // next round's copies go out first, then the start offset of the round after it is fetched
         const bool more = i + stride < n_round;
-        if (more) stage(b ^ 1, start_nxt);
-        const u32 start_nn = (more && i + 2 * stride < n_round) ? line_start(i + 2 * stride) : 0xFFFFFFFFu;
+        if (more) stage(b ^ 1, nl_nxt);
+        const u32 nl_nn = (more && i + 2 * stride < n_round) ? line_nl(i + 2 * stride) : 0xFFFFFFFEu;
         if (more) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();                                               // neighbours read each other's rows
         if (active) {
             if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu;
-            const u64 a = ws + start_cur;
+            const u64 a = ws + (u64)(nl_cur + 1u);
             RowFetch lf; lf.row = s_rows + ((size_t)b * 256 + tid) * PR_ROW;
             const bool staged = s_st[b][tid] != 0xFFFFFFFFu;
             LineRec rec; u32 meta = 0;
@@ -820,7 +828,7 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
             p.lmeta[i] = (u8)meta;
         }
         __syncthreads();                                               // this round's rows are the target of the next round's copies
-        start_cur = start_nxt; start_nxt = start_nn;
+        nl_cur = nl_nxt; nl_nxt = nl_nn;
     }
 }
 #define PR_SMEM (PR_STAGES * 256 * PR_ROW)
@@ -1038,6 +1046,11 @@ __device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32
     return o;
 }
 
+#define EMIT_THREADS 256
+#define EMIT_ITEMS 1
+#define EMIT_TILE (EMIT_THREADS * EMIT_ITEMS)
+#define EMIT_STAGE 20480
+
 static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
     WinState *st = p.st;
@@ -1116,10 +1129,10 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
         vA = 1u | ((meta & LM_EMIT) ? 1u << 16 : 0u);
         if (meta & LM_EMIT) { vT = g.text_len; if (p.write_sam) vS = g.sam_len; }
       } while (0);
-      // sizes per 512 lines for K4, which then needs no look-back: one reduction per warp (its 32 lines share a tile)
+      // sizes per EMIT_TILE lines for K4, which then needs no look-back: one reduction per warp (its 32 lines share a tile)
       vA = __reduce_add_sync(0xFFFFFFFFu, vA); vT = __reduce_add_sync(0xFFFFFFFFu, vT); vS = __reduce_add_sync(0xFFFFFFFFu, vS);
       if ((threadIdx.x & 31u) == 0 && vA) {
-          u32 *tt = (u32 *)&p.tile_tot[i >> 9];
+          u32 *tt = (u32 *)&p.tile_tot[i / EMIT_TILE];
           atomicAdd(tt, vA);
           if (vT) atomicAdd(tt + 1, vT);
           if (vS) atomicAdd(tt + 2, vS);
@@ -1130,10 +1143,6 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ K4: emit
-#define EMIT_THREADS 256
-#define EMIT_ITEMS 2
-#define EMIT_TILE (EMIT_THREADS * EMIT_ITEMS)
-#define EMIT_STAGE 40960
 
 __device__ __forceinline__ u32 put_uint(char *dst, u32 v) {
     u32 n = dec_digits(v);
@@ -1341,130 +1350,135 @@ static __global__ void __launch_bounds__(1024) k_emit_prefix(S2PParams p) {
     if (tid == 1023) { st->w_groups = bG; st->w_emit = bE; st->w_text = bT; st->w_sam = bS; }
 }
 
-static __global__ void __launch_bounds__(EMIT_THREADS, 3) k_emit(S2PParams p) {
+// the nd (1..10) decimal characters of v as byte stores, without a division chain
+__device__ __forceinline__ char *put_uint_fast(char *out, u32 v, u32 nd) {
+    u32 d0, d1, d2;
+    dec_chars(v, nd, d0, d1, d2);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) if ((u32)b < nd) out[b] = (char)(d0 >> (8 * b));
+#pragma unroll
+    for (int b = 0; b < 4; ++b) if ((u32)(4 + b) < nd) out[4 + b] = (char)(d1 >> (8 * b));
+#pragma unroll
+    for (int b = 0; b < 2; ++b) if ((u32)(8 + b) < nd) out[8 + b] = (char)(d2 >> (8 * b));
+    return out + nd;
+}
+
+// One line per thread, tiles of 256 lines.  Every global load of a tile's round — line flags, the group's resolution, and the
+// read id's bytes out of the SAM text (seven aligned 8-byte words, realigned in registers) — is issued before the first
+// byte is formatted: ncu had the read-id fetch, one dependent load per 8 bytes inside the formatting loop, at 25 % of this
+// kernel's stall samples.  64 registers and a 20 KiB stage leave room for five CTAs per SM (was three).
+static __global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
-    __shared__ u32 s_w[2][EMIT_NT][3][EMIT_THREADS / 32];
+    __shared__ u32 s_w[2][3][EMIT_THREADS / 32];
     WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n_tiles = (int)((n_lines + EMIT_BIG - 1) / EMIT_BIG);
+    const int n_tiles = (int)((n_lines + EMIT_TILE - 1) / EMIT_TILE);
     const u64 base_text = st->out_text, base_pairs = st->out_pairs, base_sam = st->out_sam, base_groups = st->groups_done;
     int pb = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, pb ^= 1) {
         const uint4 tbase = p.tile_pre[tile];                           // (groups, emitted, text, passthrough) before this tile
-
-        // ---- phase 1: per-thread sizes (groups | emitted << 16, text bytes, passthrough bytes)
-        u32 lA[EMIT_NT], lT[EMIT_NT], lS[EMIT_NT];                      // become thread-exclusive prefixes inside the tile
+        const u32 i = (u32)tile * EMIT_TILE + tid;
+        // ---- loads
+        const u32 m = i < n_lines ? p.lmeta[i] : 0;
+        const bool proc = (m & LM_HEAD) && (m & LM_PROC), emit = proc && (m & LM_EMIT);
+        GroupRes g; g.text_len = 0; g.sam_len = 0; g.rid_len = 0; g.rid_off = 0; g.status = ST_NONE;
+        if (proc) g = p.res[i];
+        const bool want_text = emit && p.emit_text;
+        const u64 rid_abs = ws + g.rid_off;
+        const u32 rsh = (u32)(rid_abs & 7u) * 8u;
+        u64 rw[7];
+        {
+            const u64 *src = (const u64 *)(p.buf + (rid_abs & ~(u64)7));
+            const u32 span = g.rid_len + (rsh >> 3);
 #pragma unroll
-        for (int k = 0; k < EMIT_NT; ++k) {
-            const u32 i0 = (u32)tile * EMIT_BIG + k * EMIT_TILE + tid * EMIT_ITEMS;
-            u32 vA = 0, vT = 0, vS = 0;
-#pragma unroll
-            for (int q = 0; q < EMIT_ITEMS; ++q) {
-                const u32 i = i0 + q;
-                const u32 m = i < n_lines ? p.lmeta[i] : 0;
-                const bool proc = (m & LM_HEAD) && (m & LM_PROC), emit = proc && (m & LM_EMIT);
-                vA += (proc ? 1u : 0u) | (emit ? 1u << 16 : 0u);
-                if (emit) { vT += p.res[i].text_len; if (p.write_sam) vS += p.res[i].sam_len; }
-            }
-            const u32 iA = warp_incl_scan(vA, lane), iT = warp_incl_scan(vT, lane), iS = warp_incl_scan(vS, lane);
-            if (lane == 31) { s_w[pb][k][0][wid] = iA; s_w[pb][k][1][wid] = iT; s_w[pb][k][2][wid] = iS; }
-            lA[k] = iA - vA; lT[k] = iT - vT; lS[k] = iS - vS;
+            for (int j = 0; j < 7; ++j) rw[j] = (want_text && (u32)(8 * j) < span) ? __ldg(src + j) : 0ull;
         }
+        const ChrSlot *ca = nullptr, *cb = nullptr;
+        if (want_text) { ca = &p.chr[p.id_to_slot[g.chrA]]; cb = &p.chr[p.id_to_slot[g.chrB]]; }
+        // ---- sizes: (groups | emitted << 16, text bytes, passthrough bytes), scanned over the tile
+        const u32 vA = (proc ? 1u : 0u) | (emit ? 1u << 16 : 0u), vT = emit ? g.text_len : 0u, vS = (emit && p.write_sam) ? g.sam_len : 0u;
+        const u32 iA = warp_incl_scan(vA, lane), iT = warp_incl_scan(vT, lane), iS = warp_incl_scan(vS, lane);
+        if (lane == 31) { s_w[pb][0][wid] = iA; s_w[pb][1][wid] = iT; s_w[pb][2][wid] = iS; }
         __syncthreads();
-        // ---- phase 2: tile totals and this thread's prefix inside the tile
-        u32 sG[EMIT_NT], sE[EMIT_NT], sT[EMIT_NT], sS[EMIT_NT];
+        u32 lA = iA - vA, lT = iT - vT, lS = iS - vS, totT = 0;
 #pragma unroll
-        for (int k = 0; k < EMIT_NT; ++k) {
-            u32 a = 0, t = 0, s2 = 0;
-#pragma unroll
-            for (int q = 0; q < EMIT_THREADS / 32; ++q) {
-                const u32 xa = s_w[pb][k][0][q], xt = s_w[pb][k][1][q], xs = s_w[pb][k][2][q];
-                a += xa; t += xt; s2 += xs;
-                if (q < wid) { lA[k] += xa; lT[k] += xt; lS[k] += xs; }
-            }
-            sG[k] = a & 0xFFFFu; sE[k] = a >> 16; sT[k] = t; sS[k] = s2;
+        for (int q = 0; q < EMIT_THREADS / 32; ++q) {
+            const u32 xa = s_w[pb][0][q], xt = s_w[pb][1][q], xs = s_w[pb][2][q];
+            totT += xt;
+            if (q < wid) { lA += xa; lT += xt; lS += xs; }
         }
-        u32 pG = tbase.x, pE = tbase.y;                                 // running prefixes at the sub-tile's start
-        u64 pT = base_text + tbase.z, pS = base_sam + tbase.w;
-        // ---- phase 3: outputs
-#pragma unroll
-        for (int k = 0; k < EMIT_NT; ++k) {
-            const u32 i0 = (u32)tile * EMIT_BIG + k * EMIT_TILE + tid * EMIT_ITEMS;
-            u32 g_idx = pG + (lA[k] & 0xFFFFu), e_idx = pE + (lA[k] >> 16);
-            const u64 t_off = pT;                                        // first text byte of the sub-tile
-            u64 s_run = pS + lS[k];
-            const u32 totT = sT[k];
-            const bool text_fits = t_off + totT <= p.out_text_cap;
-            const bool staged = totT <= EMIT_STAGE;
-            const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);   // stage with the destination's 16-byte phase
-            if (p.emit_text && totT && !text_fits && tid == 0) atomicOr(&st->err, S2P_ERR_TEXT);
-            u32 t_run = lT[k];
-            u32 mm[EMIT_ITEMS]; GroupRes gg[EMIT_ITEMS]; RidInfo rid[EMIT_ITEMS];
-#pragma unroll
-            for (int q = 0; q < EMIT_ITEMS; ++q) {                       // all loads first: the chain lmeta -> res -> rec -> nl_pos is latency bound
-                const u32 i = i0 + q;
-                mm[q] = i < n_lines ? p.lmeta[i] : 0;
-                if ((mm[q] & LM_HEAD) && (mm[q] & LM_PROC)) gg[q] = p.res[i];
+        const u32 g_idx = tbase.x + (lA & 0xFFFFu), e_idx = tbase.y + (lA >> 16);
+        const u64 t_off = base_text + tbase.z;                           // first text byte of the tile
+        const u64 s_run = base_sam + tbase.w + lS;
+        const bool text_fits = t_off + totT <= p.out_text_cap;
+        const bool staged = totT <= EMIT_STAGE;
+        const u32 phase = (u32)((u64)(p.out_text + t_off) & 15u);       // stage with the destination's 16-byte phase
+        if (p.emit_text && totT && !text_fits && tid == 0) atomicOr(&st->err, S2P_ERR_TEXT);
+        // ---- outputs
+        if (proc) {
+            if (g.status == ST_SELFCIRCLE) {                             // for the thread-0-share emulation on the host
+                u32 slot = atomicAdd(&st->sc_count, 1u);
+                if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
             }
-#pragma unroll
-            for (int q = 0; q < EMIT_ITEMS; ++q) if ((mm[q] & LM_EMIT) && p.emit_text) rid[q] = rid_info(p, ws, gg[q]);
-#pragma unroll
-            for (int q = 0; q < EMIT_ITEMS; ++q) {
-                const u32 i = i0 + q;
-                const u32 m = mm[q];
-                if (!((m & LM_HEAD) && (m & LM_PROC))) continue;
-                const GroupRes &g = gg[q];
-                if (g.status == ST_SELFCIRCLE) {                         // for the thread-0-share emulation on the host
-                    u32 slot = atomicAdd(&st->sc_count, 1u);
-                    if (slot < p.sc_cap) p.sc_list[slot] = base_groups + g_idx; else atomicOr(&st->err, S2P_ERR_SCLIST);
-                }
-                ++g_idx;
-                if (!(m & LM_EMIT)) continue;
+            if (emit) {
+                const u64 o = base_pairs + e_idx;
                 if (p.emit_packed) {
-                    const u64 o = base_pairs + e_idx;
                     if (o < p.out_pairs_cap) {
                         mk_pair r; r.pos1 = g.posA; r.pos2 = g.posB; r.chr1 = g.chrA; r.chr2 = g.chrB; r.strands = g.strands;
                         r.cls = (u8)(g.status - ST_TRANS); r.lane = p.lane;
                         p.out_pairs[o] = r;
                     } else atomicOr(&st->err, S2P_ERR_PAIRS);
                 }
-                if (p.out_line_off && p.emit_text && base_pairs + e_idx < p.out_line_off_cap) p.out_line_off[base_pairs + e_idx] = t_off + t_run;
-                ++e_idx;
+                if (p.out_line_off && p.emit_text && o < p.out_line_off_cap) p.out_line_off[o] = t_off + lT;
                 if (p.emit_text && text_fits) {
-                    // (byte-wise on purpose: the word-wise OR writer of the strip path is a dependent chain through its accumulator and
-                    // measured slower here, 4.8 vs 3.2 ms per 19.8 GB; these stores are independent)
-                    write_pair_line(p, rid[q], g, staged ? s_stage + phase + t_run : p.out_text + t_off + t_run);
-                    t_run += g.text_len;
+                    // rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347)
+                    char *out = staged ? s_stage + phase + lT : p.out_text + t_off + lT;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        if ((u32)(8 * j) < g.rid_len) {
+                            const u64 x = rsh ? (rw[j] >> rsh) | (rw[j + 1] << (64u - rsh)) : rw[j];
+                            const u32 nb = g.rid_len - 8u * j < 8u ? g.rid_len - 8u * j : 8u;
+                            out = put_bytes8(out, x, nb);
+                        }
+                    }
+                    for (u32 k = 48; k < g.rid_len; ++k) *out++ = p.buf[rid_abs + k];    // read ids beyond 48 bytes: rare
+                    *out++ = '\t';
+                    out = put_name(out, ca);
+                    *out++ = '\t';
+                    out = put_uint_fast(out, g.posA, dec_digits(g.posA));
+                    *out++ = '\t';
+                    out = put_name(out, cb);
+                    *out++ = '\t';
+                    out = put_uint_fast(out, g.posB, dec_digits(g.posB));
+                    *out++ = '\t'; *out++ = (g.strands & 1) ? '-' : '+'; *out++ = '\t'; *out++ = (g.strands & 2) ? '-' : '+'; *out++ = '\n';
                 }
                 if (p.write_sam) {                                       // destination of every kept line of the group; K5 copies
                     if (s_run + g.sam_len > p.out_sam_cap) atomicOr(&st->err, S2P_ERR_SAM);
                     else {
-                        u64 o = s_run; u32 ql = i;
+                        u64 o2 = s_run; u32 ql = i;
                         while (true) {
-                            p.sam_dst[ql] = (u32)(o - base_sam);
-                            o += line_len_of(p, ql) + 1;
+                            p.sam_dst[ql] = (u32)(o2 - base_sam);
+                            o2 += line_len_of(p, ql) + 1;
                             if (ql == g.last_line) break;
                             ++ql; while (!(p.lmeta[ql] & LM_KEEP)) ++ql;
                         }
                     }
-                    s_run += g.sam_len;
                 }
             }
-            if (p.emit_text && totT && text_fits && staged) {
-                __syncthreads();
-                char *dst = p.out_text + t_off;
-                const u32 head = phase ? (16u - phase < totT ? 16u - phase : totT) : 0u;
-                if ((u32)tid < head) dst[tid] = s_stage[phase + tid];
-                const u32 body = (totT - head) >> 4;
-                for (u32 w = tid; w < body; w += EMIT_THREADS)
-                    st_stream_v4((uint4 *)(dst + head + ((u64)w << 4)), *(const uint4 *)(s_stage + phase + head + (w << 4)));
-                const u32 tail0 = head + (body << 4);
-                if (tail0 + tid < totT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
-                __syncthreads();                                         // the stage is reused by the next sub-tile
-            }
-            pG += sG[k]; pE += sE[k]; pT += sT[k]; pS += sS[k];
+        }
+        if (p.emit_text && totT && text_fits && staged) {
+            __syncthreads();
+            char *dst = p.out_text + t_off;
+            const u32 head = phase ? (16u - phase < totT ? 16u - phase : totT) : 0u;
+            if ((u32)tid < head) dst[tid] = s_stage[phase + tid];
+            const u32 body = (totT - head) >> 4;
+            for (u32 w = tid; w < body; w += EMIT_THREADS)
+                st_stream_v4((uint4 *)(dst + head + ((u64)w << 4)), *(const uint4 *)(s_stage + phase + head + (w << 4)));
+            const u32 tail0 = head + (body << 4);
+            if (tail0 + tid < totT) dst[tail0 + tid] = s_stage[phase + tail0 + tid];
+            __syncthreads();                                             // the stage is reused by the next tile
         }
     }
 }
