@@ -32,6 +32,8 @@ HG38_LEN = [248956422, 133797422, 135086622, 133275309, 114364328, 107043718, 10
 RES = 5000
 SEED = 0x4D4B0002
 METRIC = "valid pairs/sec (SAM->dedup->binned)"
+PART_RES = 5_000_000        # owner = hash(chr1, chr2, pos1 / 5 Mb): the least common multiple of the driver's default resolutions
+                            # (microcket:98), so every duplicate and every cell of every resolution has exactly one owner
 DUP_PER_1024 = 128          # 12.5 % of the read groups re-use the fragment of another group anywhere in the job (PCR duplicates
                             # with their own read ids, crossing shard boundaries): ~11 % of the pairs are removed by the dedup
 
@@ -162,7 +164,7 @@ def workload_config(args, world, groups):
     return {"workload": "BASELINE configs[1]: hg38 Micro-C 150-cycle stitched-read SAM (flash mode), sam2pairs + coordinate dedup + 5kb binning",
             "read_groups_per_gpu": groups, "genome": "hg38", "mode": "flash", "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
             "seed": SEED, "duplicates": f"{DUP_PER_1024}/1024 of the read groups copy the fragment of another group of the whole job (all shards)", "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
-            "parallelism": f"shard{world}: parse by read chunk, dedup keys all-to-all by hash(chr1,chr2,pos1/{RES}), COO owner-computes"}
+            "parallelism": f"shard{world}: parse by read chunk, packed pairs to their owner hash(chr1,chr2,pos1/{PART_RES}) by the library's own NVLink peer-memory kernel (MICROCKET_XCHG=nccl: partition + NCCL all-to-all), dedup + COO owner-computes"}
 
 
 class Pipeline:
@@ -182,6 +184,14 @@ class Pipeline:
                                              window_bytes=window_bytes, sharded=(world > 1)), HG38)
         self.stream = torch.cuda.current_stream().cuda_stream
         self.src = self.pairs
+        self.src_ptr = self.pairs.data_ptr()
+        # N > 1: the library's NVLink peer-memory exchange (csrc/xchg.cu); MICROCKET_XCHG=nccl: partition + NCCL all-to-all
+        self.xchg = None
+        if world > 1 and os.environ.get("MICROCKET_XCHG", "p2p") != "nccl":
+            from microcket_b200 import shard
+            self.xchg = mk.Xchg(world, dist.get_rank(), self.cap_pairs, device=local)
+            shard.connect_xchg(torch, dist, self.xchg, dev)
+            self.recv = None
 
     def run(self, sam, nbytes, pair_events=None, text_len=None):
         torch = self.torch
@@ -191,23 +201,36 @@ class Pipeline:
         n = io.n_pairs
         if text_len is not None:
             text_len[0] = io.pairs_text_len
-        src = self.pairs
-        if self.world > 1:
+        src_ptr = self.pairs.data_ptr()
+        if self.xchg is not None:
+            self.xchg.scatter(self.pairs.data_ptr(), n, PART_RES, stream=self.stream)
+            src_ptr, n = self.xchg.finish(stream=self.stream)
+        elif self.world > 1:
             from microcket_b200 import shard
-            n, src = shard.exchange_pairs(self.mk, torch, self.dist, self.ws, self.pairs, n, self.recv, self.cap_pairs, RES, self.stream)
+            n, src = shard.exchange_pairs(self.mk, torch, self.dist, self.ws, self.pairs, n, self.recv, self.cap_pairs, PART_RES, self.stream)
+            src_ptr = src.data_ptr()
         # duplicate removal and 5 kb binning share one sort (mk_pairs_dedup_bin_device)
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
-        kept, nnz = self.ws.dedup_bin(src.data_ptr(), n, HG38_LEN, RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
+        kept, nnz = self.ws.dedup_bin(src_ptr, n, HG38_LEN, RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
                                       stream=self.stream)
         eb.record()
         if pair_events is not None:
             pair_events.append((ea, eb, n))
-        self.src = src
+        self.src_ptr = src_ptr
         return io.n_pairs, kept, nnz
+
+    def kept_pairs(self, kept):
+        """the kept pairs of the last run as a uint8 cuda tensor (copied out of wherever the exchange left them)"""
+        out = self.torch.empty(max(kept, 1) * 16, dtype=self.torch.uint8, device=self.b1.device)
+        if kept:
+            self.mk.lib().check_cuda_copy(out.data_ptr(), self.src_ptr, kept * 16)
+        return out[:kept * 16]
 
     def close(self):
         self.s2p.close(); self.ws.close()
+        if self.xchg is not None:
+            self.xchg.close()
 
 
 def verify_sharded(torch, mk, np, dist, args, world, rank, local):
@@ -228,7 +251,7 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
     dist.all_gather(all_sizes, sizes)
     all_sizes = [x.tolist() for x in all_sizes]
     mk_, mz = max(x[0] for x in all_sizes), max(x[1] for x in all_sizes)
-    kp = torch.zeros(mk_ * 16, dtype=torch.uint8, device=dev); kp[:kept * 16] = pipe.src[:kept * 16]
+    kp = torch.zeros(mk_ * 16, dtype=torch.uint8, device=dev); kp[:kept * 16] = pipe.kept_pairs(kept)
     coo = torch.zeros(mz * 3, dtype=torch.int32, device=dev)
     coo[:nnz] = pipe.b1[:nnz]; coo[mz:mz + nnz] = pipe.b2[:nnz]; coo[2 * mz:2 * mz + nnz] = pipe.cnt[:nnz]
     kps = [torch.empty_like(kp) for _ in range(world)]; coos = [torch.empty_like(coo) for _ in range(world)]
@@ -257,7 +280,7 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
         # (b) the single-GPU path over the whole input
         one = Pipeline(torch, mk, None, universe, 1, local, 64 << 20)
         p1, k1, z1 = one.run(sam1, nb1)
-        single = np.frombuffer(one.src[:k1 * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+        single = np.frombuffer(one.kept_pairs(k1).cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
         checks["equals_single_gpu"] = (p1 == n and k1 == n_keep and z1 == len(b1) and np.array_equal(single[key(single)], got_pairs[key(got_pairs)])
                                        and one.cnt[:z1].cpu().numpy().astype(np.uint32).tolist() == got_coo[:, 2].tolist())
         one.close()

@@ -47,6 +47,7 @@ const char *mk_last_error(void);
 int  mk_version(void);
 int  mk_device_count(void);          /* CUDA devices visible; 0 when there is no GPU (no error) */
 void mk_destroy(mk_ctx *);
+int  mk_copy_device(void *d_dst, const void *d_src, size_t nbytes);   /* synchronous device-to-device copy between raw pointers */
 
 /* ------------------------------------------------------------------ packed pair record (16 B) */
 typedef struct {
@@ -229,6 +230,28 @@ int  mk_hist_coo_device(mk_hist *, int res_idx, uint32_t *d_bin1, uint32_t *d_bi
                         size_t *nnz, uint64_t *total, void *stream);
 uint64_t mk_hist_dropped(mk_hist *);
 uint64_t mk_hist_launch_count(mk_hist *);
+
+/* ------------------------------------------------------------------ multi-GPU exchange over NVLink peer memory */
+/* One object per rank (one process per GPU, or several ranks in one process).  Owner bucketing and the all-to-all are ONE
+ * kernel: owner = mix(chr1, chr2, pos1 / res) mod world (mk_pairs_owner); every rank writes its pairs straight into the
+ * owners' receive buffers through peer pointers and publishes an epoch flag there; the consumer waits on the device.
+ * Bootstrap: every rank calls mk_xchg_handle, the 128-byte handles are all-gathered by whatever the host program has
+ * (torch.distributed, MPI, a file), then mk_xchg_connect.  Ranks inside one process use mk_xchg_connect_local.
+ * Choose res = least common multiple of the binning resolutions (5 Mb for microcket:98's default list): every duplicate and
+ * every cell of every resolution then has one owner, and nothing else has to cross GPUs.  Arrival order is not
+ * deterministic: which of several IDENTICAL packed pairs survives the dedup is not defined across ranks. */
+typedef struct mk_xchg mk_xchg;
+int  mk_xchg_create(int device, int world, int rank, size_t cap_pairs /* most pairs this rank can own per exchange */, mk_xchg **);
+void mk_xchg_destroy(mk_xchg *);
+int  mk_xchg_handle(mk_xchg *, void *handle128);
+int  mk_xchg_connect(mk_xchg *, const void *all_handles /* world x 128 bytes, rank order */);
+int  mk_xchg_connect_local(mk_xchg *const *all /* rank order */, int world);
+/* enqueue: this rank's n pairs go to their owners (returns at once; d_pairs may be reused when the stream has passed it) */
+int  mk_xchg_scatter_device(mk_xchg *, const mk_pair *d_pairs, size_t n, uint32_t res, void *stream);
+/* wait on the device until all ranks have delivered; *d_recv / *n_recv: the pairs this rank owns (inside the object's
+ * buffer, valid until the scatter after next; may be modified in place, e.g. by mk_pairs_dedup_bin_device) */
+int  mk_xchg_finish_device(mk_xchg *, mk_pair **d_recv, size_t *n_recv, void *stream);
+uint64_t mk_xchg_launch_count(mk_xchg *);
 
 /* ------------------------------------------------------------------ synthetic inputs (tests / bench) */
 /* Same bytes on host and device for a given (seed, mode, genome, first, count).  mode: 0 flash, 1 unc,

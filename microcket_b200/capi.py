@@ -95,6 +95,7 @@ class Lib:
         L.mk_version.restype = i
         L.mk_device_count.restype = i
         L.mk_destroy.argtypes = [vp]
+        L.mk_copy_device.argtypes = [vp, vp, sz]
         L.mk_s2p_default_cfg.argtypes = [P(S2PCfg)]
         L.mk_s2p_create.argtypes = [P(S2PCfg), P(C.c_char_p), i, P(vp)]
         L.mk_s2p_push.argtypes = [vp, C.c_char_p, sz, i]
@@ -134,6 +135,10 @@ class Lib:
                            ("mk_hist_matrix", [vp, i, P(vp), P(u64), P(u64)]),
                            ("mk_hist_coo_device", [vp, i, vp, vp, vp, sz, P(sz), P(u64), vp]),
                            ("mk_hist_dropped", [vp]), ("mk_hist_launch_count", [vp]),
+                           ("mk_xchg_create", [i, i, i, sz, P(vp)]), ("mk_xchg_destroy", [vp]), ("mk_xchg_handle", [vp, vp]),
+                           ("mk_xchg_connect", [vp, vp]), ("mk_xchg_connect_local", [P(vp), i]),
+                           ("mk_xchg_scatter_device", [vp, vp, sz, C.c_uint32, vp]), ("mk_xchg_finish_device", [vp, P(vp), P(sz), vp]),
+                           ("mk_xchg_launch_count", [vp]),
                            ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
@@ -145,7 +150,7 @@ class Lib:
             L.mk_pairs_launch_count.restype = u64
         if hasattr(L, "mk_pairs_dropped"):
             L.mk_pairs_dropped.restype = u64
-        for name in ("mk_hist_dropped", "mk_hist_launch_count"):
+        for name in ("mk_hist_dropped", "mk_hist_launch_count", "mk_xchg_launch_count"):
             if hasattr(L, name):
                 getattr(L, name).restype = u64
 
@@ -155,6 +160,10 @@ class Lib:
 
     def device_count(self):
         return self.L.mk_device_count()
+
+    def check_cuda_copy(self, dst, src, nbytes):
+        """device-to-device copy between raw pointers (library-owned buffers have no torch tensor)"""
+        self.check(self.L.mk_copy_device(dst, src, nbytes))
 
     def require_gpu(self):
         if self.device_count() < 1:
@@ -511,6 +520,55 @@ class Hist:
 
     def launches(self):
         return self.lib.L.mk_hist_launch_count(self.h)
+
+
+class Xchg:
+    """One rank of the NVLink peer-memory exchange of packed pairs (csrc/xchg.cu)."""
+
+    def __init__(self, world, rank, cap_pairs, device=0):
+        self.lib = lib()
+        self.lib.require_gpu()
+        self.world, self.rank = world, rank
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.mk_xchg_create(device, world, rank, cap_pairs, C.byref(self.h)))
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.lib.check(self.lib.L.mk_xchg_handle(self.h, buf))
+        return buf.raw
+
+    def connect(self, all_handles: bytes):
+        assert len(all_handles) == 128 * self.world
+        self.lib.check(self.lib.L.mk_xchg_connect(self.h, all_handles))
+
+    @staticmethod
+    def connect_local(xs):
+        arr = (C.c_void_p * len(xs))(*[x.h for x in xs])
+        L = lib()
+        L.check(L.L.mk_xchg_connect_local(arr, len(xs)))
+
+    def scatter(self, d_pairs, n, res, stream=0):
+        self.lib.check(self.lib.L.mk_xchg_scatter_device(self.h, d_pairs, n, res, stream))
+
+    def finish(self, stream=0):
+        """→ (device pointer of the pairs this rank owns, their number)"""
+        p, n = C.c_void_p(), C.c_size_t()
+        self.lib.check(self.lib.L.mk_xchg_finish_device(self.h, C.byref(p), C.byref(n), stream))
+        return p.value or 0, n.value
+
+    def launches(self):
+        return self.lib.L.mk_xchg_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.L.mk_xchg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def chrom_ranks(names):

@@ -28,3 +28,10 @@ int mk_sm_count(int device) {
 }
 
 extern "C" void mk_destroy(mk_ctx *c) { delete c; }
+
+// device-to-device copy between raw pointers (buffers owned by this library have no tensor on the host side)
+extern "C" int mk_copy_device(void *d_dst, const void *d_src, size_t nbytes) {
+    if (nbytes && (!d_dst || !d_src)) { mk_set_error("mk_copy_device: null pointer"); return MK_ERR_ARG; }
+    MK_CUDA(cudaMemcpy(d_dst, d_src, nbytes, cudaMemcpyDeviceToDevice));
+    return MK_OK;
+}

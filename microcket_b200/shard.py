@@ -1,10 +1,19 @@
-"""Multi-GPU plumbing of the dedup/binning exchange (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+"""Multi-GPU plumbing of the dedup/binning exchange.
 
-The data path has ONE exchange step: packed pairs are grouped by owner rank on the device
-(mk_pairs_partition_device), the per-destination counts are exchanged, then the segments move with a single
-all_to_all_single.  Parsing needs no collective (shards are cut at read-group boundaries) and the COO counts are
-owner-computed, so nothing else crosses NVLink.
+The data path has ONE exchange step.  On GPUs it is the library's own kernel over NVLink peer memory
+(mk_xchg_*, csrc/xchg.cu): torch.distributed only carries the 128-byte cudaIpc handles at start-up (connect_xchg).
+The collective form below (owner partition on the device, counts exchanged, one all_to_all_single) is kept for boxes
+without peer access (MICROCKET_XCHG=nccl) and is what the CPU tests drive with gloo.  Parsing needs no collective
+(shards are cut at read-group boundaries) and the COO counts are owner-computed, so nothing else crosses NVLink.
 """
+
+
+def connect_xchg(torch, dist, xchg, device):
+    """Bootstrap of the NVLink peer-memory exchange (csrc/xchg.cu): all-gather the ranks' 128-byte cudaIpc handles."""
+    mine = torch.frombuffer(bytearray(xchg.handle()), dtype=torch.uint8).to(device)
+    allh = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(allh, mine)
+    xchg.connect(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
 
 
 def exchange_counts(torch, dist, counts, device):
