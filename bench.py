@@ -528,10 +528,14 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
                                     sharded=(world > 1)), HG38)
     if world > 1:
         from microcket_b200 import shard
-        d_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev); d_recv = torch.empty_like(d_pairs)
+        d_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev); d_kept = torch.empty_like(d_pairs)
         db1 = torch.empty(cap, dtype=torch.int32, device=dev); db2 = torch.empty_like(db1); dbc = torch.empty_like(db1)
         kept_host = torch.empty(cap * 16, dtype=torch.uint8).pin_memory()
         stream = torch.cuda.current_stream().cuda_stream
+        use_p2p = os.environ.get("MICROCKET_XCHG", "p2p") != "nccl"
+        if use_p2p:
+            xchg = mk.Xchg(world, rank, cap, device=local)
+            shard.connect_xchg(torch, dist, xchg, dev)
     phases = {"stream_ms": 0.0, "drain_finish_ms": 0.0, "pairs_ms": 0.0}
 
     def once():
@@ -559,9 +563,15 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
             moved = pl
         else:
             d_pairs[:pl * 16].copy_(out_pairs[:pl * 16], non_blocking=True)
-            n, src = shard.exchange_pairs(mk, torch, dist, ws, d_pairs, pl, d_recv, cap, RES, stream)
-            kept, nnz = ws.dedup_bin(src.data_ptr(), n, HG38_LEN, RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
-            kept_host[:kept * 16].copy_(src[:kept * 16], non_blocking=True)
+            if use_p2p:
+                xchg.scatter(d_pairs.data_ptr(), pl, PART_RES, stream=stream)
+                src_ptr, n = xchg.finish(stream=stream)
+            else:
+                n, src = shard.exchange_pairs(mk, torch, dist, ws, d_pairs, pl, d_kept, cap, PART_RES, stream)
+                src_ptr = src.data_ptr()
+            kept, nnz = ws.dedup_bin(src_ptr, n, HG38_LEN, RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
+            mk.lib().check_cuda_copy(d_kept.data_ptr(), src_ptr, kept * 16)
+            kept_host[:kept * 16].copy_(d_kept[:kept * 16], non_blocking=True)
             ob1[:nnz].copy_(db1[:nnz], non_blocking=True); ob2[:nnz].copy_(db2[:nnz], non_blocking=True); oc[:nnz].copy_(dbc[:nnz], non_blocking=True)
             torch.cuda.synchronize()
             moved = pl
@@ -596,7 +606,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     return {"value": pl_all / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "read_groups_per_gpu": E, "ms_per_step": sec * 1e3, "phases_ms_rank0": {k: v / reps for k, v in phases.items()},
             "api": "mk_s2p_push/pull/pull_packed/finish from pinned host buffers" +
-                   (" + mk_pairs_dedup_bin_host" if world == 1 else " + H2D of the packed pairs, owner partition, NCCL all-to-all, mk_pairs_dedup_bin_device, D2H of kept pairs and COO") +
+                   (" + mk_pairs_dedup_bin_host" if world == 1 else " + H2D of the packed pairs, mk_xchg_* exchange over NVLink, mk_pairs_dedup_bin_device, D2H of kept pairs and COO") +
                    "; wall clock incl. all copies, max over ranks"}
 
 

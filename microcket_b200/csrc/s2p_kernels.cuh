@@ -1484,20 +1484,42 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(S2PParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ K5: SAM passthrough
-// One warp per line: the lines of emitted groups are copied verbatim (with their '\n').
+// One warp per line: the lines of emitted groups are copied verbatim (with their '\n').  Source and destination have
+// unrelated alignments, so the copy runs on the DESTINATION's 16-byte grid: every lane builds one aligned 16-byte chunk from
+// five aligned 32-bit source words and four funnel shifts and stores it with one 128-bit streaming store (the first version
+// moved one byte per lane per instruction); the ragged head and tail of the line go out bytewise.
 static __global__ void __launch_bounds__(256) k_copy_sam(S2PParams p) {
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws, base = st->out_sam;
-    const int lane = threadIdx.x & 31;
+    const u32 lane = threadIdx.x & 31u;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (u32 i = warp; i < n_lines; i += nwarps) {
         if (!(p.lmeta[i] & LM_KEEP)) continue;
         const u32 d = p.sam_dst[i];
         if (d == 0xFFFFFFFFu) continue;
-        const u64 src = ws + (i ? p.nl_pos[i - 1] + 1 : 0);
-        const u32 len = p.nl_pos[i] - (i ? p.nl_pos[i - 1] + 1 : 0) + 1;
+        const u32 start = i ? p.nl_pos[i - 1] + 1 : 0;
+        const u32 len = p.nl_pos[i] - start + 1;
+        const char *src = p.buf + ws + start;
         char *dst = p.out_sam + base + d;
-        for (u32 b = lane; b < len; b += 32) dst[b] = p.buf[src + b];
+        const u32 head = (16u - (u32)((uintptr_t)dst & 15u)) & 15u;      // bytes before the destination's first 16-byte boundary
+        const u32 h = head < len ? head : len;
+        if (lane < h) dst[lane] = src[lane];
+        const u32 body = (len - h) >> 4;                                 // whole aligned 16-byte chunks
+        const char *sb = src + h;
+        const u32 sh = (u32)((uintptr_t)sb & 3u) * 8u;
+        const u32 *sw = (const u32 *)((uintptr_t)sb & ~(uintptr_t)3);
+        for (u32 c = lane; c < body; c += 32) {
+            const u32 *q = sw + 4 * c;
+            const u32 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+            uint4 o;
+            if (sh) {
+                const u32 w4 = __ldg(q + 4);                              // at most 3 bytes past the chunk: inside the line or the buffer's slack
+                o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+            } else o = make_uint4(w0, w1, w2, w3);
+            st_stream_v4((uint4 *)(dst + h) + c, o);
+        }
+        const u32 t0 = h + (body << 4);
+        if (t0 + lane < len) dst[t0 + lane] = src[t0 + lane];
     }
 }
