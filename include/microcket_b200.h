@@ -48,6 +48,13 @@ int  mk_version(void);
 int  mk_device_count(void);          /* CUDA devices visible; 0 when there is no GPU (no error) */
 void mk_destroy(mk_ctx *);
 int  mk_copy_device(void *d_dst, const void *d_src, size_t nbytes);   /* synchronous device-to-device copy between raw pointers */
+/* raw device / pinned host memory and synchronous copies, for host programs built without the CUDA toolkit (the CLIs) */
+int  mk_dev_alloc(int device, size_t nbytes, void **d_ptr);
+void mk_dev_free(void *d_ptr);
+int  mk_host_alloc(size_t nbytes, void **h_ptr);
+void mk_host_free(void *h_ptr);
+int  mk_copy_to_device(void *d_dst, const void *h_src, size_t nbytes);
+int  mk_copy_to_host(void *h_dst, const void *d_src, size_t nbytes);
 
 /* ------------------------------------------------------------------ packed pair record (16 B) */
 typedef struct {
@@ -194,6 +201,11 @@ int  mk_pairs_sort_text_device(mk_pairs_ws *, const mk_pair *d_pairs, size_t n, 
 /* The lines of the kept pairs in input order (deduplicated, unsorted). */
 int  mk_pairs_filter_text_device(mk_pairs_ws *, size_t n, const uint8_t *d_keep, const char *d_pairs_text,
                                  const uint64_t *d_line_off, char *d_out, size_t out_cap, size_t *out_len, void *stream);
+/* A `.pairs` file's text (anno/4DN.DCIC.header:2 columns; d_text 16-byte aligned, ending with '\n', < 4 GiB per call) to
+ * packed pairs on the device: d_out[i] = line i.  Header lines ('#'), malformed lines and chromosome names outside
+ * chrom_names get chromosome id 0xFFFF, which the dedup / binning / histogram calls leave out and count. */
+int  mk_pairs_parse_text_device(mk_pairs_ws *, const char *d_text, size_t n_bytes, const char *const *chrom_names, int n_chrom,
+                                mk_pair *d_out, size_t cap, size_t *n_lines, size_t *n_skipped, void *stream);
 /* rank[i] of names[i] under `sort -d` in the C locale (only blanks and alphanumerics compare); equal keys share a rank */
 int  mk_pairs_chrom_ranks(const char *const *names, int n, uint16_t *rank);
 /* Multi-GPU: group pairs by owner rank = mix(chr1, chr2, pos1 / res) mod world into d_out (segments in rank order;

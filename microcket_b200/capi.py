@@ -128,6 +128,7 @@ class Lib:
                            ("mk_pairs_sort_text_device", [vp, vp, sz, vp, vp, vp, P(C.c_uint16), i, C.c_uint32, vp, sz, P(sz), P(sz), vp]),
                            ("mk_pairs_filter_text_device", [vp, sz, vp, vp, vp, vp, sz, P(sz), vp]),
                            ("mk_pairs_chrom_ranks", [P(C.c_char_p), i, P(C.c_uint16)]),
+                           ("mk_pairs_parse_text_device", [vp, vp, sz, P(C.c_char_p), i, vp, sz, P(sz), P(sz), vp]),
                            ("mk_hist_cells", [P(C.c_uint32), i, C.c_uint32, P(u64), P(u64)]),
                            ("mk_hist_create", [i, P(C.c_uint32), i, P(C.c_uint32), i, P(vp), P(vp)]),
                            ("mk_hist_destroy", [vp]), ("mk_hist_reset", [vp, vp]),
@@ -426,6 +427,13 @@ class PairsWorkspace:
 
     def dropped(self):
         return self.lib.L.mk_pairs_dropped(self.h)
+
+    def parse_text(self, d_text, n_bytes, chrom_names, d_out, cap, stream=0):
+        """.pairs text on the device → packed pairs, one per line → (lines, lines that are not pairs of known chromosomes)"""
+        arr = (C.c_char_p * len(chrom_names))(*[n.encode() for n in chrom_names])
+        nl, ns = C.c_size_t(), C.c_size_t()
+        self.lib.check(self.lib.L.mk_pairs_parse_text_device(self.h, d_text, n_bytes, arr, len(chrom_names), d_out, cap, C.byref(nl), C.byref(ns), stream))
+        return nl.value, ns.value
 
     def sort_text(self, d_pairs, n, d_keep, d_text, d_line_off, chrom_rank, max_pos, d_out, out_cap, stream=0):
         """Lines of the kept pairs in `sort -k2,2d -k4,4d -k3,3n -k5,5n` order → (bytes, lines)"""

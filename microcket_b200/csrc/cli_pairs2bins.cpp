@@ -1,20 +1,35 @@
 // cli_pairs2bins.cpp — contact binning of a .pairs file on the GPU (new tool; stands where the driver calls
 // `java -jar juicer_tools.jar pre -r <res,...> <sid>.final.pairs <sid>.hic <genome>.info`, microcket:525-529).
-//   pairs2bins [-d] -r <res[,res...]> <in.pairs> <out.prefix> <genome.info>
-// Writes <out.prefix>.<res>.coo with `bin1<TAB>bin2<TAB>count` (upper triangle, sorted), bins numbered in .info
-// order with bin = offset[chr] + pos / res.  -d removes coordinate duplicates first (first occurrence wins).
-// Writing .hic itself is out of scope.
+//   pairs2bins [-d] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>
+// Writes <out.prefix>.<res>.coo with `bin1<TAB>bin2<TAB>count` (upper triangle, sorted), bins numbered in .info order with
+// bin = offset[chr] + pos / res.  -d removes coordinate duplicates first (first occurrence wins).
+// The file is streamed in 256 MiB chunks from pinned memory and PARSED ON THE GPU (mk_pairs_parse_text_device); resolutions
+// whose upper triangle fits MICROCKET_DENSE_MB (default 4096) all come from one pass of the dense histogram (mk_hist_*), the
+// finer ones from the sort path.  Writing .hic itself is out of scope.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
-#include <map>
 #include <sstream>
 #include <string>
 #include <vector>
 #include "../../include/microcket_b200.h"
 using namespace std;
+
+#define CHECK(call) do { if ((call) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; } } while (0)
+
+static int write_coo(const string &path, const void *d_b1, const void *d_b2, const void *d_ct, size_t nnz) {
+    vector<uint32_t> b1(nnz + 1), b2(nnz + 1), ct(nnz + 1);
+    if (nnz) { CHECK(mk_copy_to_host(b1.data(), d_b1, nnz * 4)); CHECK(mk_copy_to_host(b2.data(), d_b2, nnz * 4)); CHECK(mk_copy_to_host(ct.data(), d_ct, nnz * 4)); }
+    FILE *fo = fopen(path.c_str(), "w");
+    if (!fo) { cerr << "Error: cannot write " << path << "\n"; return 10; }
+    static char big[1 << 22];
+    setvbuf(fo, big, _IOFBF, sizeof big);
+    for (size_t i = 0; i < nnz; ++i) fprintf(fo, "%u\t%u\t%u\n", b1[i], b2[i], ct[i]);
+    fclose(fo);
+    return 0;
+}
 
 int main(int argc, char *argv[]) {
     bool dedup = false; string reslist;
@@ -25,44 +40,112 @@ int main(int argc, char *argv[]) {
         else break;
     }
     if (argc - a < 3 || reslist.empty()) {
-        cerr << "\nUsage: " << argv[0] << " [-d] -r <res[,res...]> <in.pairs> <out.prefix> <genome.info>\n\n";
+        cerr << "\nUsage: " << argv[0] << " [-d] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>\n\n";
         return 2;
     }
     vector<uint32_t> res;
     { stringstream ss(reslist); string t; while (getline(ss, t, ',')) if (!t.empty()) res.push_back((uint32_t)strtoul(t.c_str(), NULL, 10)); }
-    map<string, int> chr_id; vector<uint32_t> chr_len;
+    for (uint32_t r : res) if (r == 0) { cerr << "Error: resolution 0\n"; return 2; }
+    vector<string> names; vector<uint32_t> chr_len;
     { ifstream fi(argv[a + 2]); if (fi.fail()) { cerr << "Error: cannot read " << argv[a + 2] << "\n"; return 10; }
-      string n; uint32_t l; while (fi >> n >> l) { chr_id[n] = (int)chr_len.size(); chr_len.push_back(l); } }
-    ifstream fp(argv[a]);
-    if (fp.fail()) { cerr << "Error: cannot read " << argv[a] << "\n"; return 10; }
-    vector<mk_pair> pairs; string line;
-    while (getline(fp, line)) {
-        if (line.empty() || line[0] == '#') continue;
-        stringstream ss(line); string id, c1, c2, s1, s2; uint32_t p1, p2;
-        if (!(ss >> id >> c1 >> p1 >> c2 >> p2 >> s1 >> s2)) continue;
-        auto i1 = chr_id.find(c1), i2 = chr_id.find(c2);
-        if (i1 == chr_id.end() || i2 == chr_id.end()) continue;
-        mk_pair r; memset(&r, 0, sizeof r);
-        r.chr1 = (uint16_t)i1->second; r.chr2 = (uint16_t)i2->second; r.pos1 = p1; r.pos2 = p2;
-        r.strands = (uint8_t)((s1 == "-" ? 1 : 0) | (s2 == "-" ? 2 : 0));
-        pairs.push_back(r);
+      string n; uint32_t l; while (fi >> n >> l) { names.push_back(n); chr_len.push_back(l); } }
+    if (names.empty()) { cerr << "Error: no chromosomes in " << argv[a + 2] << "\n"; return 10; }
+    vector<const char *> cnames; for (auto &s : names) cnames.push_back(s.c_str());
+    FILE *fp = strcmp(argv[a], "-") ? fopen(argv[a], "rb") : stdin;
+    if (!fp) { cerr << "Error: cannot read " << argv[a] << "\n"; return 10; }
+    const int dev = getenv("MICROCKET_DEVICE") ? atoi(getenv("MICROCKET_DEVICE")) : 0;
+    if (mk_device_count() < 1) { cerr << "Error: no CUDA device: microcket_b200 has no CPU fallback\n"; return 20; }
+
+    // ---- stream the text to the GPU and parse it there
+    const size_t CHUNK = (size_t)(getenv("MICROCKET_CHUNK_MB") ? atol(getenv("MICROCKET_CHUNK_MB")) : 256) << 20;
+    size_t cap = 1u << 22;                                               // pairs capacity, grown as the file goes by
+    void *d_pairs = NULL, *d_text = NULL; char *h_text = NULL;
+    CHECK(mk_dev_alloc(dev, cap * sizeof(mk_pair), &d_pairs));
+    CHECK(mk_dev_alloc(dev, CHUNK + 64, &d_text));
+    CHECK(mk_host_alloc(CHUNK + 64, (void **)&h_text));
+    mk_pairs_ws *pws = NULL;                                             // parser workspace (sized per chunk: a line is >= 14 bytes)
+    const size_t chunk_lines = CHUNK / 14 + 16;
+    CHECK(mk_pairs_ws_create(dev, chunk_lines, &pws));
+    size_t n = 0, have = 0, skipped = 0;
+    while (true) {
+        const size_t got = fread(h_text + have, 1, CHUNK - have, fp);
+        const bool eof = got == 0;
+        size_t tot = have + got;
+        if (tot == 0) break;
+        size_t cut = tot;
+        if (!eof) { while (cut > 0 && h_text[cut - 1] != '\n') --cut; if (cut == 0) { if (tot == CHUNK) { cerr << "Error: a line longer than " << CHUNK << " bytes\n"; return 10; } have = tot; continue; } }
+        else if (h_text[tot - 1] != '\n') { h_text[tot++] = '\n'; cut = tot; }   // last line without a newline
+        size_t lines_max = 0; for (size_t i = 0; i < cut; ++i) lines_max += h_text[i] == '\n';
+        if (n + lines_max > cap) {                                       // grow the pair array (device-to-device copy of what is there)
+            size_t ncap = cap; while (ncap < n + lines_max) ncap *= 2;
+            void *bigger = NULL;
+            CHECK(mk_dev_alloc(dev, ncap * sizeof(mk_pair), &bigger));
+            if (n) CHECK(mk_copy_device(bigger, d_pairs, n * sizeof(mk_pair)));
+            mk_dev_free(d_pairs); d_pairs = bigger; cap = ncap;
+        }
+        CHECK(mk_copy_to_device(d_text, h_text, cut));
+        size_t nl = 0, ns = 0;
+        CHECK(mk_pairs_parse_text_device(pws, (const char *)d_text, cut, cnames.data(), (int)cnames.size(), (mk_pair *)d_pairs + n, cap - n, &nl, &ns, NULL));
+        n += nl; skipped += ns;
+        have = tot - cut;
+        if (have) memmove(h_text, h_text + cut, have);
+        if (eof) break;
     }
-    int dev = getenv("MICROCKET_DEVICE") ? atoi(getenv("MICROCKET_DEVICE")) : 0;
+    if (fp != stdin) fclose(fp);
+    mk_pairs_ws_destroy(pws); mk_dev_free(d_text); mk_host_free(h_text);
+
+    // ---- bins
     mk_pairs_ws *ws = NULL;
-    if (mk_pairs_ws_create(dev, pairs.size() + 1, &ws) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
-    size_t n = pairs.size();
-    vector<uint32_t> b1(n + 1), b2(n + 1), ct(n + 1);
-    for (size_t k = 0; k < res.size(); ++k) {
-        size_t kept = 0, nnz = 0;
-        if (mk_pairs_dedup_bin_host(ws, pairs.data(), n, dedup && k == 0, chr_len.data(), (int)chr_len.size(), NULL, 0, res[k],
-                                    b1.data(), b2.data(), ct.data(), n + 1, &kept, &nnz) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
-        n = kept;
-        string out = string(argv[a + 1]) + "." + to_string(res[k]) + ".coo";
-        FILE *fo = fopen(out.c_str(), "w");
-        if (!fo) { cerr << "Error: cannot write " << out << "\n"; return 10; }
-        for (size_t i = 0; i < nnz; ++i) fprintf(fo, "%u\t%u\t%u\n", b1[i], b2[i], ct[i]);
-        fclose(fo);
+    CHECK(mk_pairs_ws_create(dev, n + 1, &ws));
+    void *d_b1 = NULL, *d_b2 = NULL, *d_ct = NULL;
+    CHECK(mk_dev_alloc(dev, (n + 1) * 4, &d_b1)); CHECK(mk_dev_alloc(dev, (n + 1) * 4, &d_b2)); CHECK(mk_dev_alloc(dev, (n + 1) * 4, &d_ct));
+    const double dense_budget = (double)(getenv("MICROCKET_DENSE_MB") ? atol(getenv("MICROCKET_DENSE_MB")) : 4096) * 1048576.0;
+    vector<int> dense, sparse; double used = 0;
+    {   // coarsest first into the dense set while the triangles fit the budget
+        vector<int> order(res.size()); for (size_t k = 0; k < res.size(); ++k) order[k] = (int)k;
+        for (size_t i = 0; i < order.size(); ++i) for (size_t j = i + 1; j < order.size(); ++j) if (res[order[j]] > res[order[i]]) swap(order[i], order[j]);
+        for (int k : order) {
+            uint64_t nb = 0, nc = 0; CHECK(mk_hist_cells(chr_len.data(), (int)chr_len.size(), res[k], &nb, &nc));
+            if (used + nc * 4.0 <= dense_budget && dense.size() < 12) { dense.push_back(k); used += nc * 4.0; } else sparse.push_back(k);
+        }
     }
-    mk_pairs_ws_destroy(ws);
+    size_t m = n;                                                        // pairs after duplicate removal
+    bool deduped = !dedup;
+    if (dedup) {                                                         // one sort: duplicates out, and the finest sparse resolution's COO for free
+        int k = sparse.empty() ? -1 : sparse.back();
+        for (int q : sparse) if (res[q] < res[k]) k = q;
+        const uint32_t r0 = k >= 0 ? res[k] : 5000u;
+        size_t kept = 0, nnz = 0;
+        CHECK(mk_pairs_dedup_bin_device(ws, (mk_pair *)d_pairs, n, chr_len.data(), (int)chr_len.size(), NULL, 0, r0, 0,
+                                        (uint32_t *)d_b1, (uint32_t *)d_b2, (uint32_t *)d_ct, n + 1, &kept, &nnz, NULL));
+        m = kept; deduped = true;
+        if (k >= 0) {
+            if (int rc = write_coo(string(argv[a + 1]) + "." + to_string(res[k]) + ".coo", d_b1, d_b2, d_ct, nnz)) return rc;
+            vector<int> rest; for (int q : sparse) if (q != k) rest.push_back(q);
+            sparse = rest;
+        }
+    }
+    (void)deduped;
+    for (int k : sparse) {
+        size_t nnz = 0;
+        CHECK(mk_pairs_bin_device(ws, (const mk_pair *)d_pairs, m, chr_len.data(), (int)chr_len.size(), NULL, 0, res[k],
+                                  (uint32_t *)d_b1, (uint32_t *)d_b2, (uint32_t *)d_ct, n + 1, &nnz, NULL));
+        if (int rc = write_coo(string(argv[a + 1]) + "." + to_string(res[k]) + ".coo", d_b1, d_b2, d_ct, nnz)) return rc;
+    }
+    if (!dense.empty()) {
+        vector<uint32_t> dres; for (int k : dense) dres.push_back(res[k]);
+        mk_hist *h = NULL;
+        CHECK(mk_hist_create(dev, chr_len.data(), (int)chr_len.size(), dres.data(), (int)dres.size(), NULL, &h));
+        CHECK(mk_hist_add_device(h, (const mk_pair *)d_pairs, m, NULL, 0, NULL));
+        for (size_t i = 0; i < dense.size(); ++i) {
+            size_t nnz = 0; uint64_t total = 0;
+            CHECK(mk_hist_coo_device(h, (int)i, (uint32_t *)d_b1, (uint32_t *)d_b2, (uint32_t *)d_ct, n + 1, &nnz, &total, NULL));
+            if (int rc = write_coo(string(argv[a + 1]) + "." + to_string(dres[i]) + ".coo", d_b1, d_b2, d_ct, nnz)) return rc;
+        }
+        mk_hist_destroy(h);
+    }
+    cerr << "INFO: " << n << " lines, " << skipped << " of them headers / unknown chromosomes; " << m << " pairs binned"
+         << (dedup ? " after duplicate removal" : "") << " at " << res.size() << " resolutions (" << dense.size() << " dense).\n";
+    mk_pairs_ws_destroy(ws); mk_dev_free(d_pairs); mk_dev_free(d_b1); mk_dev_free(d_b2); mk_dev_free(d_ct);
     return 0;
 }

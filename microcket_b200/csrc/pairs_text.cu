@@ -11,6 +11,7 @@
 // Lines are addressed through the offsets k_emit records (mk_s2p_dev_io.d_line_off): line e = text[off[e], off[e+1]).
 // Line format: unc2pairs.h:327-347 (rid \t chr1 \t pos1 \t chr2 \t pos2 \t s1 \t s2 \n).
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "mk_common.cuh"
@@ -268,5 +269,143 @@ extern "C" int mk_pairs_chrom_ranks(const char *const *names, int n, uint16_t *r
         if (k > 0 && key[idx[k]] != key[idx[k - 1]]) ++r;
         rank[idx[k]] = r;
     }
+    return MK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ .pairs text -> packed pairs
+// What pairs2bins needs from a `.final.pairs` file (anno/4DN.DCIC.header:2: readID chr1 pos1 chr2 pos2 strand1 strand2):
+// newline index (count per 4 KiB block, prefix, positions), then one thread per line.  Header lines ('#'), short lines and
+// chromosome names outside the table become records with chromosome id 0xFFFF: the dedup / binning calls leave those out
+// and count them, so no compaction pass is needed here.
+#define NL_T 256
+__device__ __forceinline__ u32 nl_mask16(const uint4 &w) {              // bit q <-> byte q of the 16-byte word is '\n'
+    auto y = [](u32 x) { const u32 v = x ^ 0x0A0A0A0Au; return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); };   // 0x80 where the byte is '\n' (exact)
+    return gather_flags4(y(w.x)) | (gather_flags4(y(w.y)) << 4) | (gather_flags4(y(w.z)) << 8) | (gather_flags4(y(w.w)) << 12);
+}
+__device__ __forceinline__ uint4 ld16_bounded(const char *text, u64 off, u64 n) {   // bytes at and beyond n read as 0
+    if (off + 16 <= n) return *(const uint4 *)(text + off);
+    u32 w[4] = {0, 0, 0, 0};
+    for (u32 b = 0; b < 16 && off + b < n; ++b) w[b >> 2] |= (u32)(unsigned char)text[off + b] << (8 * (b & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void __launch_bounds__(NL_T) k_nl_count(const char *text, u64 n, u32 *blk_cnt) {
+    __shared__ u32 s_w[NL_T / 32];
+    const u64 off = ((u64)blockIdx.x * NL_T + threadIdx.x) * 16;
+    u32 c = off < n ? __popc(nl_mask16(ld16_bounded(text, off, n))) : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { u32 t = 0; for (int w = 0; w < NL_T / 32; ++w) t += s_w[w]; blk_cnt[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(NL_T) k_nl_write(const char *text, u64 n, const u64 *blk_off, u32 *nl_pos, u64 cap) {
+    __shared__ u32 s_scan[NL_T / 32 + 1];
+    const u64 off = ((u64)blockIdx.x * NL_T + threadIdx.x) * 16;
+    u32 m = off < n ? nl_mask16(ld16_bounded(text, off, n)) : 0;
+    u32 tot;
+    const u32 ex = block_excl_scan<NL_T>(__popc(m), s_scan, &tot);
+    u64 o = blk_off[blockIdx.x] + ex;
+    while (m) { const u32 q = __ffs(m) - 1; m &= m - 1; if (o < cap) nl_pos[o] = (u32)(off + q); ++o; }
+}
+
+struct NameSlot { unsigned long long key; u32 id; u32 len; char name[48]; };   // open addressing by FNV-1a of the name
+__global__ void __launch_bounds__(256) k_pairs_parse(const char *text, const u32 *nl_pos, const unsigned long long *n_lines_p,
+                                                     const NameSlot *tab, u32 mask, mk_pair *out, u64 cap, unsigned long long *bad) {
+    const u64 n_lines = *n_lines_p < cap ? *n_lines_p : cap;
+    u32 nbad = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += (u64)gridDim.x * blockDim.x) {
+        u32 p = i ? nl_pos[i - 1] + 1 : 0;
+        const u32 e = nl_pos[i];
+        mk_pair r; r.pos1 = r.pos2 = 0; r.chr1 = r.chr2 = 0xFFFF; r.strands = 0; r.cls = 0; r.lane = 0;
+        bool ok = p < e && text[p] != '#';
+        u32 pos[2] = {0, 0}, chr[2] = {0xFFFF, 0xFFFF};
+        if (ok) {
+            while (p < e && text[p] != '\t') ++p;                      // read id
+            for (int k = 0; k < 2 && ok; ++k) {
+                ok = p < e; ++p;                                         // the tab
+                const u32 s0 = p;
+                u64 h = 0xCBF29CE484222325ull;
+                while (p < e && text[p] != '\t') { h = (h ^ (u64)(unsigned char)text[p]) * 0x100000001B3ull; ++p; }
+                const u32 len = p - s0;
+                if (h == 0) h = 0x9E3779B97F4A7C15ull;
+                ok = ok && len > 0 && len <= 48;
+                if (ok) {
+                    u32 s = (u32)(h ^ (h >> 29)) & mask; bool found = false;
+                    for (u32 probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
+                        const NameSlot *sl = &tab[s];
+                        if (sl->key == 0) break;
+                        if (sl->key == h && sl->len == len) {
+                            bool same = true;
+                            for (u32 b = 0; b < len && same; ++b) same = sl->name[b] == text[s0 + b];
+                            if (same) { chr[k] = sl->id; found = true; break; }
+                        }
+                    }
+                    ok = found;
+                }
+                ok = ok && p < e; ++p;                                   // the tab behind the name
+                u32 v = 0, nd = 0;
+                while (p < e && (u32)(text[p] - '0') <= 9u) { v = v * 10u + (u32)(text[p] - '0'); ++p; ++nd; }
+                ok = ok && nd > 0 && nd <= 10;
+                pos[k] = v;
+            }
+            // \t s1 \t s2
+            ok = ok && p + 3 < e + 1 && text[p] == '\t' && text[p + 2] == '\t';
+            if (ok) r.strands = (u8)((text[p + 1] == '-' ? 1 : 0) | (text[p + 3] == '-' ? 2 : 0));
+        }
+        if (ok) {
+            r.pos1 = pos[0]; r.pos2 = pos[1]; r.chr1 = (u16)chr[0]; r.chr2 = (u16)chr[1];
+            if (r.chr1 != r.chr2) r.cls = 0; else { const u32 d = r.pos2 - r.pos1; r.cls = d >= 10000u ? 1 : (d >= 1000u ? 2 : 3); }
+        } else ++nbad;
+        out[i] = r;
+    }
+    nbad = __reduce_add_sync(0xffffffffu, nbad);
+    if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
+}
+
+// d_text: n_bytes of .pairs text on the device ending with '\n' (16-byte aligned).  d_out[i] = pair of line i; *n_lines lines,
+// *n_skipped of them not pairs of known chromosomes (headers included; chromosome id 0xFFFF).
+extern "C" int mk_pairs_parse_text_device(mk_pairs_ws *w, const char *d_text, size_t n_bytes, const char *const *chrom_names, int n_chrom,
+                                          mk_pair *d_out, size_t cap, size_t *n_lines, size_t *n_skipped, void *stream) {
+    if (!w || !n_lines || !chrom_names || n_chrom <= 0 || n_chrom > 16384 || (n_bytes && (!d_text || !d_out))) { mk_set_error("mk_pairs_parse_text_device: bad argument"); return MK_ERR_ARG; }
+    if (((uintptr_t)d_text & 15) != 0) { mk_set_error("mk_pairs_parse_text_device: d_text must be 16-byte aligned"); return MK_ERR_ARG; }
+    if (n_bytes >= (1ull << 32)) { mk_set_error("mk_pairs_parse_text_device: at most 4 GiB of text per call"); return MK_ERR_CAPACITY; }
+    MK_CUDA(cudaSetDevice(w->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    *n_lines = 0; if (n_skipped) *n_skipped = 0;
+    if (n_bytes == 0) return MK_OK;
+    // chromosome table (rebuilt per call: a few KB)
+    u32 slots = 64; while (slots < (u32)n_chrom * 4) slots <<= 1;
+    std::vector<NameSlot> tab(slots);
+    memset(tab.data(), 0, tab.size() * sizeof(NameSlot));
+    for (int i = 0; i < n_chrom; ++i) {
+        const char *nm = chrom_names[i]; const size_t len = nm ? strlen(nm) : 0;
+        if (len == 0 || len > 48) { mk_set_error("mk_pairs_parse_text_device: chromosome name %d is empty or longer than 48 bytes", i); return MK_ERR_ARG; }
+        u64 h = 0xCBF29CE484222325ull;
+        for (size_t b = 0; b < len; ++b) h = (h ^ (u64)(unsigned char)nm[b]) * 0x100000001B3ull;
+        if (h == 0) h = 0x9E3779B97F4A7C15ull;
+        u32 sl = (u32)(h ^ (h >> 29)) & (slots - 1);
+        while (tab[sl].key) sl = (sl + 1) & (slots - 1);
+        tab[sl].key = h; tab[sl].id = (u32)i; tab[sl].len = (u32)len; memcpy(tab[sl].name, nm, len);
+    }
+    const u64 n_blk = (n_bytes + NL_T * 16 - 1) / (NL_T * 16);
+    MK_TRY(w->text_scratch(n_blk));
+    if (w->names.n < tab.size() * sizeof(NameSlot)) MK_TRY(w->names.alloc(tab.size() * sizeof(NameSlot)));
+    const size_t nl_cap = cap + 1;
+    if (w->nl.n < nl_cap * 4) MK_TRY(w->nl.alloc(nl_cap * 4));
+    MK_CUDA(cudaMemcpyAsync(w->names.p, tab.data(), tab.size() * sizeof(NameSlot), cudaMemcpyHostToDevice, s));
+    MK_CUDA(cudaStreamSynchronize(s));                                  // `tab` is a local
+    MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
+    unsigned long long *cnt = w->counter.as<unsigned long long>();
+    k_nl_count<<<(unsigned)n_blk, NL_T, 0, s>>>(d_text, n_bytes, w->tile_sum.as<u32>());
+    k_line_tile_prefix<<<1, 1024, 0, s>>>(w->tile_sum.as<u32>(), w->tile_off.as<u64>(), n_blk, cnt);      // total -> cnt[1]
+    k_nl_write<<<(unsigned)n_blk, NL_T, 0, s>>>(d_text, n_bytes, w->tile_off.as<u64>(), w->nl.as<u32>(), nl_cap);
+    k_pairs_parse<<<w->sms * 8, 256, 0, s>>>(d_text, w->nl.as<u32>(), cnt + 1, w->names.as<NameSlot>(), slots - 1, d_out, cap, cnt + 2);
+    w->launches += 4;
+    unsigned long long h[3];
+    MK_CUDA(cudaMemcpyAsync(h, cnt, 24, cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));
+    MK_CUDA(cudaGetLastError());
+    if (h[1] > cap) { mk_set_error("mk_pairs_parse_text_device: %llu lines, output capacity %zu", h[1], cap); return MK_ERR_CAPACITY; }
+    *n_lines = (size_t)h[1];
+    if (n_skipped) *n_skipped = (size_t)h[2];
     return MK_OK;
 }

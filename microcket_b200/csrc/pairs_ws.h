@@ -14,7 +14,7 @@ struct mk_pairs_ws {
     DevBuf h_pairs, h_b1, h_b2, h_c;   // device staging of the host-buffer API, allocated on first use
     DevBuf sort2;                      // max_pairs * 16 B: second buffer of the text sort, allocated on first use
     DevBuf tile_sum, tile_off; size_t text_tiles = 0;   // per 256-line tile: bytes, exclusive prefix (pairs_text.cu)
-    DevBuf hist;                       // dense per-resolution histograms (bin_multi), allocated on first use
+    DevBuf names, nl;                  // .pairs text parser: chromosome name table, newline positions (allocated on first use)
     u64 launches = 0;
     u64 dropped = 0;     // pairs the last dedup / binning call left out (unknown chromosome id, position past the chromosome end, lane > max_lane)
     int text_scratch(size_t n_tiles) {

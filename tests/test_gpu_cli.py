@@ -98,3 +98,30 @@ def test_pairs2bins_cli(tmp_path, oracle):
         b1, b2, ct = oracle.bin_coo(pairs, n, keep, HG38_LEN, res)
         exp = "".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1, b2, ct))
         assert (tmp_path / f"out.{res}.coo").read_text() == exp
+
+
+def test_pairs2bins_default_resolution_list_streamed_and_odd_lines(tmp_path, oracle):
+    """The driver's nine default resolutions (microcket:98) in one run, the file streamed in 1 MiB chunks (lines cut by chunk
+    boundaries), read from stdin, with lines the parser must skip: headers in the middle, an unknown chromosome, a short line,
+    and a last line without a newline."""
+    sam = mk.synth_host(56, "flash", "hg38", 0, 60000)
+    op, _, _ = oracle.sam2pairs(sam, "flash", threads=8, write_sam=False)
+    lines = op.splitlines(keepends=True)
+    odd = [b"#comment in the middle\n", b"r1\tchrUn_KI270302v1\t5\tchr1\t9\t+\t-\n", b"short\tchr1\t5\n", b"\n"]
+    body = b"".join(lines[:1000] + odd + lines[1000:])
+    body = body[:-1]                                                  # no trailing newline
+    from test_gpu_pairs import HG38_LEN
+    names = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr2", "chr20", "chr21",
+             "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
+    info = tmp_path / "hg38.info"; info.write_text("".join(f"{n}\t{l}\n" for n, l in zip(names, HG38_LEN)))
+    res = [2500000, 1000000, 500000, 250000, 100000, 50000, 25000, 10000, 5000]
+    env = dict(os.environ, MICROCKET_CHUNK_MB="1")
+    r = subprocess.run([os.path.join(BIN, "pairs2bins"), "-r", ",".join(map(str, res)), "-", str(tmp_path / "o"), str(info)],
+                       input=b"## pairs format v1.0\n" + body, capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert b"5 of them headers / unknown chromosomes" in r.stderr and b"(5 dense)" in r.stderr
+    pairs, n = oracle.pairs_parse(op, names)
+    for rs in res:
+        b1, b2, ct = oracle.bin_coo(pairs, n, None, HG38_LEN, rs)
+        exp = "".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1, b2, ct))
+        assert (tmp_path / f"o.{rs}.coo").read_text() == exp, rs
