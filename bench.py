@@ -29,6 +29,22 @@ HG38 = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "
 HG38_LEN = [248956422, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616,
             242193529, 64444167, 46709983, 50818468, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
             16569, 156040895, 57227415]
+MM10 = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr2", "chr3", "chr4", "chr5",
+        "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
+MM10_LEN = [195471971, 130694993, 122082543, 120129022, 120421639, 124902244, 104043685, 98207768, 94987271, 90702639, 61431566,
+            182113224, 160039680, 156508116, 151834684, 149736546, 145441459, 129401213, 124595110, 16299, 171031299, 91744698]
+DEFAULT_RES = [2500000, 1000000, 500000, 250000, 100000, 50000, 25000, 10000, 5000]          # microcket:98
+# --config: which BASELINE.json configuration the line measures.  The default line (what the driver records) is configs[1].
+WORKLOADS = {
+    "flash": {"mode": "flash", "genome": "hg38", "names": HG38, "lens": HG38_LEN, "chimeric": -1,
+              "title": "BASELINE configs[1]: hg38 Micro-C 150-cycle stitched-read SAM (flash mode), sam2pairs + coordinate dedup + 5kb binning"},
+    "unc": {"mode": "unc", "genome": "mm10", "names": MM10, "lens": MM10_LEN, "chimeric": 384,
+            "title": "BASELINE configs[2]: mm10 Hi-C non-stitched paired reads (unc mode), 37.5 % chimeric / split alignments "
+                     "(ligation 5'-end resolution, unc2pairs.h:191-308), sam2pairs + coordinate dedup + 5kb binning"},
+    "multires": {"mode": "flash", "genome": "hg38", "names": HG38, "lens": HG38_LEN, "chimeric": -1,
+                 "title": "BASELINE configs[4]: hg38 multi-resolution binning (2.5 Mb - 5 kb, cis + trans) of device-resident packed pairs to COO"},
+}
+WL = WORKLOADS["flash"]
 RES = 5000
 SEED = 0x4D4B0002
 METRIC = "valid pairs/sec (SAM->dedup->binned)"
@@ -39,7 +55,7 @@ DUP_PER_1024 = 128          # 12.5 % of the read groups re-use the fragment of a
 
 
 def synth_opts(mk, universe):
-    return mk.synth_opts(dup_per_1024=DUP_PER_1024, dup_universe=universe)
+    return mk.synth_opts(dup_per_1024=DUP_PER_1024, dup_universe=universe, chimeric_per_1024=WL["chimeric"])
 
 
 def measured_peak():
@@ -85,7 +101,7 @@ class ClockSampler:
 
 def synth_to_device(torch, mk, first, count, device, universe):
     """→ (uint8 cuda tensor holding the SAM text, n_bytes)"""
-    return mk.synth_device(torch, SEED, "flash", "hg38", first, count, device=device, opts=synth_opts(mk, universe))
+    return mk.synth_device(torch, SEED, WL["mode"], WL["genome"], first, count, device=device, opts=synth_opts(mk, universe))
 
 
 def reference_sample(torch, mk, n_groups, device, tmpdir, universe):
@@ -107,17 +123,17 @@ def cpu_pipeline_once(sam_path, tmpdir, threads):
     t0 = time.time()
     if os.path.exists(ref):
         kind = "reference"
-        out = subprocess.run([ref, sam_path, "flash", pre, str(threads), "0.5", "10", "0"], check=True, capture_output=True).stdout
+        out = subprocess.run([ref, sam_path, WL["mode"], pre, str(threads), "0.5", "10", "1" if SAM_ON else "0"], check=True, capture_output=True).stdout
     else:
         kind = "port"
         cli = os.path.join(ROOT, "oracle", "_build", "oracle_cli")
         if not os.path.exists(cli):
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
-        out = subprocess.run([cli, "sam2pairs", sam_path, "flash", pre, str(threads), "0.5", "10", "0"], check=True, capture_output=True).stdout
+        out = subprocess.run([cli, "sam2pairs", sam_path, WL["mode"], pre, str(threads), "0.5", "10", "1" if SAM_ON else "0"], check=True, capture_output=True).stdout
     orc = oracle_lib.load()
-    pairs, n = orc.pairs_parse(out, HG38)
+    pairs, n = orc.pairs_parse(out, WL["names"])
     keep, kept = orc.coord_dedup(pairs, n)
-    orc.bin_coo(pairs, n, keep, HG38_LEN, RES)
+    orc.bin_coo(pairs, n, keep, WL["lens"], RES)
     return n, time.time() - t0, kind
 
 
@@ -161,8 +177,8 @@ def run_reference(args):
 
 
 def workload_config(args, world, groups):
-    return {"workload": "BASELINE configs[1]: hg38 Micro-C 150-cycle stitched-read SAM (flash mode), sam2pairs + coordinate dedup + 5kb binning",
-            "read_groups_per_gpu": groups, "genome": "hg38", "mode": "flash", "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
+    return {"workload": WL["title"], "sam_passthrough": "on (the driver's default, microcket:107)" if SAM_ON else "off",
+            "read_groups_per_gpu": groups, "genome": WL["genome"], "mode": WL["mode"], "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
             "seed": SEED, "duplicates": f"{DUP_PER_1024}/1024 of the read groups copy the fragment of another group of the whole job (all shards)", "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
             "parallelism": f"shard{world}: parse by read chunk, packed pairs to their owner hash(chr1,chr2,pos1/{PART_RES}) by the library's own NVLink peer-memory kernel (MICROCKET_XCHG=nccl: partition + NCCL all-to-all), dedup + COO owner-computes"}
 
@@ -175,16 +191,19 @@ class Pipeline:
         self.torch, self.mk, self.dist, self.world = torch, mk, dist, world
         dev = torch.device(f"cuda:{local}")
         self.cap_pairs = int(groups * (1.0 if world == 1 else 1.3)) + 4096
-        self.text = torch.empty(groups * 100 + (1 << 20), dtype=torch.uint8, device=dev)
+        self.text = torch.empty(groups * 64 + (1 << 20), dtype=torch.uint8, device=dev)
         self.pairs = torch.empty(self.cap_pairs * 16, dtype=torch.uint8, device=dev)
         self.ws = mk.PairsWorkspace(self.cap_pairs, device=local)
         self.recv = torch.empty(self.cap_pairs * 16, dtype=torch.uint8, device=dev) if world > 1 else None
         self.b1 = torch.empty(self.cap_pairs, dtype=torch.int32, device=dev); self.b2 = torch.empty_like(self.b1); self.cnt = torch.empty_like(self.b1)
-        self.s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local,
-                                             window_bytes=window_bytes, sharded=(world > 1)), HG38)
+        self.samout = torch.empty(int(groups * (1400 if WL["mode"] == "unc" else 800)) + (1 << 20), dtype=torch.uint8, device=dev) if SAM_ON else None
+        self.s2p = mk.Sam2Pairs(mk.S2PConfig(mode=WL["mode"], threads=8, write_sam=SAM_ON, emit_text=True, emit_packed=True, device=local,
+                                             window_bytes=window_bytes, sharded=(world > 1)), WL["names"])
+        self.sam_len = 0
         self.stream = torch.cuda.current_stream().cuda_stream
         self.src = self.pairs
         self.src_ptr = self.pairs.data_ptr()
+        self.multires = False
         # N > 1: the library's NVLink peer-memory exchange (csrc/xchg.cu); MICROCKET_XCHG=nccl: partition + NCCL all-to-all
         self.xchg = None
         if world > 1 and os.environ.get("MICROCKET_XCHG", "p2p") != "nccl":
@@ -197,8 +216,9 @@ class Pipeline:
         torch = self.torch
         self.s2p.reset()
         io = self.s2p.run_device(sam.data_ptr(), nbytes, True, self.text.data_ptr(), self.text.numel(), self.pairs.data_ptr(), self.cap_pairs,
-                                 stream=self.stream)
+                                 d_sam=self.samout.data_ptr() if SAM_ON else 0, sam_cap=self.samout.numel() if SAM_ON else 0, stream=self.stream)
         n = io.n_pairs
+        self.sam_len = io.sam_text_len
         if text_len is not None:
             text_len[0] = io.pairs_text_len
         src_ptr = self.pairs.data_ptr()
@@ -212,13 +232,43 @@ class Pipeline:
         # duplicate removal and 5 kb binning share one sort (mk_pairs_dedup_bin_device)
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
-        kept, nnz = self.ws.dedup_bin(src_ptr, n, HG38_LEN, RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
+        kept, nnz = self.ws.dedup_bin(src_ptr, n, WL["lens"], RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
                                       stream=self.stream)
         eb.record()
         if pair_events is not None:
             pair_events.append((ea, eb, n))
         self.src_ptr = src_ptr
+        if self.multires:
+            self.run_multires(src_ptr, kept)
         return io.n_pairs, kept, nnz
+
+    def run_multires(self, kept_ptr, kept):
+        """the other eight default resolutions from the kept pairs: the five whose triangle fits HBM from ONE pass of the dense
+        histogram (shared-memory diagonals), 50 / 25 / 10 kb through the sort path (5 kb came out of the dedup's own sort)"""
+        torch = self.torch
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        self.hist.reset(stream=self.stream)
+        self.hist.add(kept_ptr, kept, stream=self.stream)
+        ev[1].record()
+        cells = {RES: None}
+        for k, r in enumerate(self.dense_res):
+            cells[r], _ = self.hist.coo(k, self.m1.data_ptr(), self.m2.data_ptr(), self.mc.data_ptr(), self.cap_pairs, stream=self.stream)
+        ev[2].record()
+        for r in self.sparse_res:
+            cells[r] = self.ws.bin(kept_ptr, kept, WL["lens"], r, self.m1.data_ptr(), self.m2.data_ptr(), self.mc.data_ptr(), self.cap_pairs, stream=self.stream)
+        ev[3].record()
+        self.multires_events.append(ev)
+        self.multires_cells = cells
+
+    def enable_multires(self):
+        mk, torch = self.mk, self.torch
+        self.multires = True
+        self.dense_res = [r for r in DEFAULT_RES if r >= 100000]
+        self.sparse_res = [r for r in DEFAULT_RES if r < 100000 and r != RES]
+        self.hist = mk.Hist(WL["lens"], self.dense_res, device=self.b1.device.index)
+        self.m1 = torch.empty_like(self.b1); self.m2 = torch.empty_like(self.b1); self.mc = torch.empty_like(self.b1)
+        self.multires_events, self.multires_cells = [], {}
 
     def kept_pairs(self, kept):
         """the kept pairs of the last run as a uint8 cuda tensor (copied out of wherever the exchange left them)"""
@@ -268,10 +318,10 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
         sam1, nb1 = synth_to_device(torch, mk, 0, universe, local, universe)
         host = sam1[:nb1].cpu().numpy().tobytes()                        # (the device generator's bytes equal the host generator's: tests/)
         orc = oracle_lib.load()
-        op, _, ost = orc.sam2pairs(host, "flash", threads=8, write_sam=False)
-        arr, n = orc.pairs_parse(op, HG38)
+        op, _, ost = orc.sam2pairs(host, WL["mode"], threads=8, write_sam=False)
+        arr, n = orc.pairs_parse(op, WL["names"])
         keep, n_keep = orc.coord_dedup(arr, n)
-        b1, b2, ct = orc.bin_coo(arr, n, keep, HG38_LEN, RES)
+        b1, b2, ct = orc.bin_coo(arr, n, keep, WL["lens"], RES)
         exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n][np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
         checks = {"groups": sum(x[3] for x in all_sizes) == ost.groups, "pairs": sum(x[2] for x in all_sizes) == n,
                   "kept": len(got_pairs) == n_keep and np.array_equal(got_pairs[key(got_pairs)], exp[key(exp)]),
@@ -294,6 +344,7 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
 
 
 VERIFY = {}
+SAM_ON = False
 
 
 def main():
@@ -308,9 +359,13 @@ def main():
     ap.add_argument("--window-mb", type=int, default=int(os.environ.get("MK_BENCH_WINDOW_MB", 2040)))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", default="flash", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: configs[1], the headline)")
+    ap.add_argument("--sam", action="store_true", help="SAM passthrough on (sam2pairs argv[7]; the driver's default) in both arms")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed, asserted reduced-size verification of the N-GPU path")
     ap.add_argument("--verify-groups", type=int, default=200_000, help="read groups per GPU of that verification")
     args = ap.parse_args()
+    global WL, SAM_ON
+    WL = WORKLOADS[args.config]; SAM_ON = args.sam
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -340,6 +395,8 @@ def main():
     sam, nbytes = synth_to_device(torch, mk, rank * G, G, local, universe)
     pipe = Pipeline(torch, mk, dist, G, world, local, args.window_mb << 20)
     s2p, ws, cnt = pipe.s2p, pipe.ws, pipe.cnt
+    if args.config == "multires":
+        pipe.enable_multires()
 
     def step():
         return pipe.run(sam, nbytes, pair_events, text_len)
@@ -355,6 +412,8 @@ def main():
     for _ in range(args.warmup):
         step()
     pair_events.clear()
+    if pipe.multires:
+        pipe.multires_events.clear()
     s2p.enable_timing(True)
     clocks = ClockSampler(local)
     launches0 = s2p.launches() + ws.launches()
@@ -423,7 +482,7 @@ def main():
     text_b = float(io_text_len)                        # bytes of pair text of one pass
     alg = {"k_scan_chunks": nbytes + 4 * lines, "k_chunk_index": 8 * lines,
            "k_parse": 117.0 * lines + 48.0 * groups, "k_group": lines + 80.0 * groups,
-           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 0.0}
+           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 2.0 * float(pipe.sam_len) + 9.0 * lines}
     per_kernel = {}
     for k, (ms_k, n_k) in dk.items():
         if ms_k > 0 and n_k > 0:
@@ -443,9 +502,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches_per_step": launches_per_step, "avg_launch_ms": dom_ms / max(dom_n, 1),
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
-                "s2p_stage": {"ms_per_step": stage_ms, "GBps": (nbytes + text_b) / (stage_ms / 1e3) / 1e9 if stage_ms else 0.0,
-                              "frac": ((nbytes + text_b) / (stage_ms / 1e3) / 1e9 / peak) if stage_ms else 0.0,
-                              "bytes": "SAM text in + pair text out (SURVEY 8d B_s2p)"},
+                "s2p_stage": {"ms_per_step": stage_ms, "GBps": (nbytes + text_b + pipe.sam_len) / (stage_ms / 1e3) / 1e9 if stage_ms else 0.0,
+                              "frac": ((nbytes + text_b + pipe.sam_len) / (stage_ms / 1e3) / 1e9 / peak) if stage_ms else 0.0,
+                              "bytes": "SAM text in + pair text out + SAM passthrough written when on (SURVEY 8d B_s2p)"},
                 "kernels": per_kernel}
     # the dedup + binning stage (pack, one radix sort of 16-byte records, unique/cell compaction), CUDA events around the call
     # on the launching stream: algorithmic = 16 B per pair in + 16 B per kept pair + 12 B per cell out; what the sort really
@@ -485,6 +544,16 @@ def main():
                       "exists: checked against oracle/pairs_oracle.c + numpy only) - that stage is %.1f of the %.1f ms step" % (
                           roofline.get("pairs_stage", {}).get("ms_per_step", 0.0), ms_step),
             "verify_sharded": VERIFY.get("result")}
+    if pipe.multires:
+        torch.cuda.synchronize()
+        me = pipe.multires_events
+        avg = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in me) / max(1, len(me))
+        line["multires"] = {"resolutions": DEFAULT_RES, "dense_histogram": pipe.dense_res, "sort_path": [RES] + pipe.sparse_res,
+                            "hist_add_ms": avg(0, 1), "hist_coo_ms": avg(1, 2), "sort_bins_ms": avg(2, 3),
+                            "cells_rank0": {str(k): v for k, v in pipe.multires_cells.items() if v is not None},
+                            "hist_algorithmic_GBps": 16.0 * float(kept) / max(avg(0, 1), 1e-9) / 1e6,
+                            "note": "N > 1: every resolution is owner-computed (partition at 5 Mb = lcm of the list), no reduce needed"}
+        line["metric"] = "valid pairs/sec (SAM->dedup->binned at the nine default resolutions)"
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
@@ -524,8 +593,8 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     ob1 = torch.empty(cap, dtype=torch.int32).pin_memory(); ob2 = torch.empty_like(ob1).pin_memory(); oc = torch.empty_like(ob1).pin_memory()
     ws = mk.PairsWorkspace(cap, device=local)
     W = 256 << 20
-    s2p = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W,
-                                    sharded=(world > 1)), HG38)
+    s2p = mk.Sam2Pairs(mk.S2PConfig(mode=WL["mode"], threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W,
+                                    sharded=(world > 1)), WL["names"])
     if world > 1:
         from microcket_b200 import shard
         d_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev); d_kept = torch.empty_like(d_pairs)
@@ -559,7 +628,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
         assert st.pairs == pl
         t_c = time.perf_counter()
         if world == 1:
-            kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, HG38_LEN, RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), cap)
+            kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, WL["lens"], RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), cap)
             moved = pl
         else:
             d_pairs[:pl * 16].copy_(out_pairs[:pl * 16], non_blocking=True)
@@ -569,7 +638,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
             else:
                 n, src = shard.exchange_pairs(mk, torch, dist, ws, d_pairs, pl, d_kept, cap, PART_RES, stream)
                 src_ptr = src.data_ptr()
-            kept, nnz = ws.dedup_bin(src_ptr, n, HG38_LEN, RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
+            kept, nnz = ws.dedup_bin(src_ptr, n, WL["lens"], RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
             mk.lib().check_cuda_copy(d_kept.data_ptr(), src_ptr, kept * 16)
             kept_host[:kept * 16].copy_(d_kept[:kept * 16], non_blocking=True)
             ob1[:nnz].copy_(db1[:nnz], non_blocking=True); ob2[:nnz].copy_(db2[:nnz], non_blocking=True); oc[:nnz].copy_(dbc[:nnz], non_blocking=True)

@@ -249,3 +249,46 @@ def test_big_synthetic_both_modes(oracle):
     for mode, seed in (("flash", 41), ("unc", 42)):
         sam = mk.synth_host(seed, mode, "hg38", 0, 250000)
         _check(oracle, sam, mode, window=64 << 20)
+
+
+@pytest.mark.parametrize("mode,genome,seed", [("flash", "hg38", 61), ("unc", "mm10", 62)])
+def test_ten_million_read_groups_full_size_windows(oracle, mode, genome, seed):
+    """10 M read groups per mode (6.6 / 8.8 GB of SAM) through the device-resident path with the bench's 2040 MiB windows and
+    12.5 % duplicated fragments: pair text, log and packed pairs equal the oracle's byte for byte, and the one-sort dedup +
+    5 kb binning of the packed pairs equals the oracle's coordinate dedup + binning (kept count, COO)."""
+    torch = pytest.importorskip("torch")
+    import numpy as np
+    from oracle_lib import Pair
+    n_groups = 10_000_000
+    opts = mk.synth_opts(dup_per_1024=128, dup_universe=n_groups, chimeric_per_1024=384 if mode == "unc" else -1)
+    buf, nb = mk.synth_device(torch, seed, mode, genome, 0, n_groups, opts=opts)
+    host = buf[:nb].cpu().numpy().tobytes()
+    op, _, ost = oracle.sam2pairs(host, mode, threads=8, write_sam=False)
+    del host
+    cap = n_groups + 1024
+    s = mk.Sam2Pairs(mk.S2PConfig(mode=mode, threads=8, write_sam=False, emit_packed=True, window_bytes=2040 << 20))
+    text = torch.empty(len(op) + (1 << 20), dtype=torch.uint8, device="cuda")
+    pairs = torch.empty(cap * 16, dtype=torch.uint8, device="cuda")
+    io = s.run_device(buf.data_ptr(), nb, True, text.data_ptr(), text.numel(), pairs.data_ptr(), cap)
+    st = s.finish()
+    assert io.pairs_text_len == len(op) and bytes(text[:io.pairs_text_len].cpu().numpy().tobytes()) == op
+    assert st.log_text() == ost.log_text() and (st.groups, st.selfCircle_true) == (ost.groups, ost.selfCircle_true)
+    names = s.chrom_names()
+    arr, n = oracle.pairs_parse(op, names)
+    assert n == io.n_pairs
+    got = np.frombuffer(pairs[:n * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+    exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n]
+    assert np.array_equal(got, exp)                                     # packed records == the text's fields, in order
+    keep, kept = oracle.coord_dedup(arr, n)
+    assert kept < 0.93 * n
+    import bench as B
+    lens = dict(zip(B.HG38, B.HG38_LEN)) if genome == "hg38" else dict(zip(B.MM10, B.MM10_LEN))
+    chrom_len = [lens[x] for x in names]                                # ids in discovery order
+    b1, b2, ct = oracle.bin_coo(arr, n, keep, chrom_len, 5000)
+    ws = mk.PairsWorkspace(n)
+    o1 = torch.empty(n, dtype=torch.int32, device="cuda"); o2 = torch.empty_like(o1); oc = torch.empty_like(o1)
+    k, z = ws.dedup_bin(pairs.data_ptr(), n, chrom_len, 5000, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), n)
+    assert (k, z) == (kept, len(b1))
+    assert np.array_equal(o1[:z].cpu().numpy().astype(np.uint32), np.array(b1, dtype=np.uint32))
+    assert np.array_equal(oc[:z].cpu().numpy().astype(np.uint32), np.array(ct, dtype=np.uint32))
+    ws.close(); s.close()
