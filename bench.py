@@ -191,7 +191,7 @@ class Pipeline:
         self.torch, self.mk, self.dist, self.world = torch, mk, dist, world
         dev = torch.device(f"cuda:{local}")
         self.cap_pairs = int(groups * (1.0 if world == 1 else 1.3)) + 4096
-        self.text = torch.empty(groups * 64 + (1 << 20), dtype=torch.uint8, device=dev)
+        self.text = torch.empty(groups * 96 + (1 << 20), dtype=torch.uint8, device=dev)
         self.pairs = torch.empty(self.cap_pairs * 16, dtype=torch.uint8, device=dev)
         self.ws = mk.PairsWorkspace(self.cap_pairs, device=local)
         self.recv = torch.empty(self.cap_pairs * 16, dtype=torch.uint8, device=dev) if world > 1 else None
@@ -574,7 +574,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
             host.copy_(sam_d[:nb])
             del sam_d
             torch.cuda.synchronize(); torch.cuda.empty_cache()
-            out_text = torch.empty(E * 56 + (1 << 20), dtype=torch.uint8).pin_memory()
+            out_text = torch.empty(E * 88 + (1 << 20), dtype=torch.uint8).pin_memory()
             out_pairs = torch.empty((E + 1024) * 16, dtype=torch.uint8).pin_memory()
             ok = 1
         except (RuntimeError, MemoryError) as e:

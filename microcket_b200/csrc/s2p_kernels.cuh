@@ -1051,6 +1051,12 @@ __device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32
 #define EMIT_TILE (EMIT_THREADS * EMIT_ITEMS)
 #define EMIT_STAGE 20480
 
+// One thread per line.  The flags of the 64 lines around a warp's 32 are gathered with two coalesced byte loads per lane and
+// two ballots each, so that the common case — a kept line whose neighbours are all kept: head test, group extent (<= 3
+// records), passthrough size and read-id position — is bit arithmetic on two 64-bit masks plus the records themselves,
+// with no per-member loop (ncu on the first version: 8.8 of 32 lanes active per instruction, the walks over p.lmeta and
+// p.nl_pos being the divergent part).  Anything else (dropped lines inside or next to the group, groups of more than three
+// records, the window's last group) takes the general walk below, which is the definition.
 static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
     WinState *st = p.st;
@@ -1058,50 +1064,84 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     __syncthreads();
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
+    const u32 lane = threadIdx.x & 31u;
     const u32 n_round = (n_lines + 31u) & ~31u;                        // whole warps stay in the loop (warp reduction at its end)
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-      u32 vA = 0, vT = 0, vS = 0;                                      // this line's contribution to its 512-line tile's sizes (K4)
+      u32 vA = 0, vT = 0, vS = 0;                                      // this line's contribution to its tile's sizes (K4)
+      // bit b of the masks <-> line (i - lane) - 1 + b: this lane's line is bit lane + 1
+      const u32 wbase = i - lane;
+      const u32 q0 = wbase + lane - 1u, q1 = wbase + lane + 31u;      // q0 wraps for the window's first warp: guarded
+      const u32 ma = (wbase + lane >= 1u && q0 < n_lines) ? p.lmeta[q0] : 0u, mb = q1 < n_lines ? p.lmeta[q1] : 0u;
+      const u64 keepm = (u64)__ballot_sync(0xFFFFFFFFu, ma & LM_KEEP) | ((u64)__ballot_sync(0xFFFFFFFFu, mb & LM_KEEP) << 32);
+      const u64 eqm = (u64)__ballot_sync(0xFFFFFFFFu, ma & LM_EQ) | ((u64)__ballot_sync(0xFFFFFFFFu, mb & LM_EQ) << 32);
       if (i < n_lines) do {                                            // `continue` below leaves this block
-        const u32 mi = p.lmeta[i];
-        if (!(mi & LM_KEEP)) continue;
-        // ---- is this kept line the head of a group?  (pairutil.h:163-173: currId != lastId among kept records)
-        bool head;
-        {
-            bool chain = line_eq(p, ws, i, mi);
-            long j = (long)i - 1;
-            while (j >= 0) { u32 mj = p.lmeta[j]; if (mj & LM_KEEP) break; chain = chain && line_eq(p, ws, (u32)j, mj); --j; }
-            if (j < 0) head = true;
-            else if (chain) head = false;
-            else if (j == (long)i - 1) head = true;
-            else head = !qname_equal_slow(p, ws, i, (u32)j);
-        }
-        if (!head) continue;
-        // ---- collect the group's kept records
+        const u32 bpos = lane + 1u;
+        if (!((keepm >> bpos) & 1ull)) continue;
+        const u32 mi = LM_KEEP | (((eqm >> bpos) & 1ull) ? LM_EQ : 0u);   // K2 wrote nothing else yet
         u32 first[2] = {i, 0}, r1[2] = {0, 0}, r2[2] = {0, 0};
-        u32 n = 0, n1 = 0, n2 = 0, sam_len = 0;
-        u32 k = i, prev = i;
-        bool chain = true, off_end = false;
-        while (true) {
-            // k is a member
-            const LineRec *rk = &p.rec[k];
-            u32 fl = rk->flag;
-            if (n < 2) first[n] = k;
-            ++n;
-            if (fl & 64u) { if (n1 < 2) r1[n1] = k; ++n1; } else if (fl & 128u) { if (n2 < 2) r2[n2] = k; ++n2; }
-            sam_len += line_len_of(p, k) + 1;
-            prev = k;
-            // next kept line
-            u32 q = k + 1; chain = true;
-            while (q < n_lines) { u32 mq = p.lmeta[q]; chain = chain && line_eq(p, ws, q, mq); if (mq & LM_KEEP) break; ++q; }
-            if (q >= n_lines) { off_end = true; break; }
-            bool same = chain ? true : (q == prev + 1 ? false : qname_equal_slow(p, ws, q, prev));
-            if (!same) break;
-            k = q;
+        u32 n = 0, n1 = 0, n2 = 0, sam_len = 0, prev = i;
+        // ---- fast path: the previous line is kept (or this is line 0), and so are the group's lines and its terminator
+        bool fast = false;
+        {
+            const bool prev_kept = i == 0 || ((keepm >> (bpos - 1u)) & 1ull);
+            if (prev_kept) {
+                if (i != 0 && (mi & LM_EQ)) continue;                   // same read id as the kept line before it: not a head
+                const u64 after = eqm >> (bpos + 1u);                   // EQ flags of the following lines
+                const u32 cnt = (u32)__ffsll((long long)~after) - 1u;   // consecutive lines with this read id behind the head
+                const u32 gn = cnt + 1u;
+                const u64 need = (1ull << (gn + 1u)) - 1ull;            // the members and the terminating line must all be kept
+                if (gn <= 3u && ((keepm >> bpos) & need) == need) {     // (a terminator past the window's last line is not kept: general path)
+                    fast = true; n = gn; prev = i + gn - 1u;
+                    first[1] = i + 1u;
+                    u32 fl[3];
+#pragma unroll
+                    for (u32 k = 0; k < 3; ++k) fl[k] = k < gn ? p.rec[i + k].flag : 0u;
+#pragma unroll
+                    for (u32 k = 0; k < 3; ++k) {
+                        if (k < gn) { if (fl[k] & 64u) { if (n1 < 2) r1[n1] = i + k; ++n1; } else if (fl[k] & 128u) { if (n2 < 2) r2[n2] = i + k; ++n2; } }
+                    }
+                    sam_len = p.nl_pos[prev] + 1u - (i ? p.nl_pos[i - 1] + 1u : 0u);   // consecutive lines: one span
+                }
+            }
         }
-        if (off_end) {                       // the window's last group: carried to the next window (or dropped at EOF)
-            st->carry_line = i;
-            p.lmeta[i] = (u8)(mi | LM_HEAD);
-            continue;
+        if (!fast) {
+            // ---- is this kept line the head of a group?  (pairutil.h:163-173: currId != lastId among kept records)
+            bool head;
+            {
+                bool chain = line_eq(p, ws, i, mi);
+                long j = (long)i - 1;
+                while (j >= 0) { u32 mj = p.lmeta[j]; if (mj & LM_KEEP) break; chain = chain && line_eq(p, ws, (u32)j, mj); --j; }
+                if (j < 0) head = true;
+                else if (chain) head = false;
+                else if (j == (long)i - 1) head = true;
+                else head = !qname_equal_slow(p, ws, i, (u32)j);
+            }
+            if (!head) continue;
+            // ---- collect the group's kept records
+            u32 k = i;
+            bool chain = true, off_end = false;
+            while (true) {
+                // k is a member
+                const LineRec *rk = &p.rec[k];
+                u32 fl = rk->flag;
+                if (n < 2) first[n] = k;
+                ++n;
+                if (fl & 64u) { if (n1 < 2) r1[n1] = k; ++n1; } else if (fl & 128u) { if (n2 < 2) r2[n2] = k; ++n2; }
+                sam_len += line_len_of(p, k) + 1;
+                prev = k;
+                // next kept line
+                u32 q = k + 1; chain = true;
+                while (q < n_lines) { u32 mq = p.lmeta[q]; chain = chain && line_eq(p, ws, q, mq); if (mq & LM_KEEP) break; ++q; }
+                if (q >= n_lines) { off_end = true; break; }
+                bool same = chain ? true : (q == prev + 1 ? false : qname_equal_slow(p, ws, q, prev));
+                if (!same) break;
+                k = q;
+            }
+            if (off_end) {                       // the window's last group: carried to the next window (or dropped at EOF)
+                st->carry_line = i;
+                p.lmeta[i] = (u8)(mi | LM_HEAD);
+                continue;
+            }
         }
         // ---- resolve
         GroupRes g; g.posA = g.posB = 0; g.chrA = g.chrB = 0; g.strands = 0;
