@@ -565,6 +565,8 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     to the host.  N > 1: every rank streams its own shard and the packed pairs cross NVLink (owner partition + all-to-all)
     before the dedup.  Wall clock between barriers, max over ranks."""
     E = min(args.e2e_groups or args.groups, args.groups)
+    if world > 1 and not args.e2e_groups:
+        E = min(E, 30_000_000)                     # N ranks pin N x the shard in host memory: 20 GB per rank keeps an 8-GPU box within 160 GB
     dev = torch.device(f"cuda:{local}")
     host = out_text = out_pairs = None
     while True:                                    # the full-size leg needs ~75 GB of pinned host memory per rank: back off if the box cannot pin it
