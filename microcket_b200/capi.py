@@ -41,7 +41,7 @@ class S2PStats(C.Structure):
 class S2PDevIO(C.Structure):
     _fields_ = [("d_pairs_text", C.c_void_p), ("pairs_text_cap", C.c_size_t), ("d_pairs", C.c_void_p), ("pairs_cap", C.c_size_t),
                 ("d_sam_text", C.c_void_p), ("sam_text_cap", C.c_size_t), ("d_line_off", C.c_void_p), ("line_off_cap", C.c_size_t),
-                ("pairs_text_len", C.c_size_t), ("n_pairs", C.c_size_t), ("sam_text_len", C.c_size_t), ("consumed", C.c_size_t)]
+                ("line_off_base", C.c_uint64), ("pairs_text_len", C.c_size_t), ("n_pairs", C.c_size_t), ("sam_text_len", C.c_size_t), ("consumed", C.c_size_t)]
 
 
 class SynthOpts(C.Structure):
@@ -284,8 +284,8 @@ class Sam2Pairs:
         return p, s, self.finish()
 
     def run_device(self, d_ptr, n, is_last, d_text=0, text_cap=0, d_pairs=0, pairs_cap=0, d_sam=0, sam_cap=0, stream=0,
-                   d_line_off=0, line_off_cap=0):
-        io = S2PDevIO(d_text, text_cap, d_pairs, pairs_cap, d_sam, sam_cap, d_line_off, line_off_cap, 0, 0, 0, 0)
+                   d_line_off=0, line_off_cap=0, line_off_base=0):
+        io = S2PDevIO(d_text, text_cap, d_pairs, pairs_cap, d_sam, sam_cap, d_line_off, line_off_cap, line_off_base, 0, 0, 0, 0)
         self.lib.check(self.lib.L.mk_s2p_run_device(self.h, d_ptr, n, int(is_last), C.byref(io), stream))
         return io
 

@@ -85,7 +85,7 @@ extern "C" void mk_s2p_default_cfg(mk_s2p_cfg *c) {
 }
 
 static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_cap, char *out_text, u64 text_cap, mk_pair *out_pairs, u64 pairs_cap,
-                             char *out_sam, u64 sam_cap, u64 window_bytes, int running, u64 *line_off = nullptr, u64 line_off_cap = 0) {
+                             char *out_sam, u64 sam_cap, u64 window_bytes, int running, u64 *line_off = nullptr, u64 line_off_cap = 0, u64 line_off_base = 0) {
     S2PParams p;
     memset(&p, 0, sizeof p);
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
@@ -98,7 +98,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.out_text = out_text; p.out_text_cap = out_text ? text_cap : 0;
     p.out_pairs = out_pairs; p.out_pairs_cap = out_pairs ? pairs_cap : 0;
     p.out_sam = out_sam; p.out_sam_cap = out_sam ? sam_cap : 0;
-    p.out_line_off = line_off; p.out_line_off_cap = line_off ? line_off_cap : 0;
+    p.out_line_off = line_off; p.out_line_off_cap = line_off ? line_off_cap : 0; p.line_off_base = line_off_base;
     p.window_bytes = window_bytes; p.cap_lines = c->cap_lines;
     p.mode = c->cfg.mode; p.min_mapq = c->cfg.min_mapq; p.ratio = c->cfg.min_mapped_ratio; p.lane = c->cfg.lane;
     p.write_sam = c->cfg.write_sam && out_sam; p.emit_text = c->cfg.emit_text && out_text; p.emit_packed = c->cfg.emit_packed && out_pairs;
@@ -657,7 +657,7 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
     WinState *dst = c->d_state.as<WinState>();
     k_set_stream<<<1, 1, 0, s>>>(dst, 0, n, is_last ? 1u : 0u);
     c->launches += 1;
-    S2PParams p = make_params(c, d_sam, c->d_sclist.as<u64>(), c->sc_cap_dev, io->d_pairs_text, io->pairs_text_cap, io->d_pairs, io->pairs_cap, io->d_sam_text, io->sam_text_cap, c->W, 1, (u64 *)io->d_line_off, io->line_off_cap);
+    S2PParams p = make_params(c, d_sam, c->d_sclist.as<u64>(), c->sc_cap_dev, io->d_pairs_text, io->pairs_text_cap, io->d_pairs, io->pairs_cap, io->d_sam_text, io->sam_text_cap, c->W, 1, (u64 *)io->d_line_off, io->line_off_cap, io->line_off_base);
     MK_TRY(upload_params(c, p, 2, s));
     // running output offsets restart at 0 for every call
     MK_CUDA(cudaMemsetAsync((char *)dst + offsetof(WinState, out_text), 0, 3 * sizeof(u64), s));

@@ -89,7 +89,7 @@ struct S2PParams {
     u64 *sc_list; u32 sc_cap;
     char *out_text; u64 out_text_cap;
     mk_pair *out_pairs; u64 out_pairs_cap;
-    u64 *out_line_off; u64 out_line_off_cap;   // optional: offset (in out_text) of every emitted pair's line, plus the end of the last one
+    u64 *out_line_off; u64 out_line_off_cap, line_off_base;   // optional: offset (in out_text) of every emitted pair's line, plus the end of the last one
     char *out_sam; u64 out_sam_cap;
     u64 window_bytes; u32 cap_lines;
     int mode, min_mapq, write_sam, emit_text, emit_packed; float ratio; u16 lane;
@@ -134,7 +134,7 @@ static __global__ void k_win_end(S2PParams p) {
     s->lines_done += (carried && !final_win) ? s->carry_line : n;
     s->groups_done += s->w_groups;
     s->out_text += s->w_text; s->out_pairs += s->w_emit; s->out_sam += s->w_sam;
-    if (p.out_line_off && s->out_pairs < p.out_line_off_cap) p.out_line_off[s->out_pairs] = s->out_text;   // end of the last line so far
+    if (p.out_line_off && s->out_pairs < p.out_line_off_cap) p.out_line_off[s->out_pairs] = p.line_off_base + s->out_text;   // end of the last line so far
 }
 
 // ------------------------------------------------------------------------------------------------ K1: newline index
@@ -1471,7 +1471,7 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(S2PParams p) {
                         p.out_pairs[o] = r;
                     } else atomicOr(&st->err, S2P_ERR_PAIRS);
                 }
-                if (p.out_line_off && p.emit_text && o < p.out_line_off_cap) p.out_line_off[o] = t_off + lT;
+                if (p.out_line_off && p.emit_text && o < p.out_line_off_cap) p.out_line_off[o] = p.line_off_base + t_off + lT;
                 if (p.emit_text && text_fits) {
                     // rid \t chrA \t posA \t chrB \t posB \t sA \t sB \n   (unc2pairs.h:327-347)
                     char *out = staged ? s_stage + phase + lT : p.out_text + t_off + lT;
