@@ -204,6 +204,7 @@ class Pipeline:
         self.src = self.pairs
         self.src_ptr = self.pairs.data_ptr()
         self.multires = False
+        self.xchg_events = []
         # N > 1: the library's NVLink peer-memory exchange (csrc/xchg.cu); MICROCKET_XCHG=nccl: partition + NCCL all-to-all
         self.xchg = None
         if world > 1 and os.environ.get("MICROCKET_XCHG", "p2p") != "nccl":
@@ -223,8 +224,13 @@ class Pipeline:
             text_len[0] = io.pairs_text_len
         src_ptr = self.pairs.data_ptr()
         if self.xchg is not None:
+            xa, xb, xc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            xa.record()
             self.xchg.scatter(self.pairs.data_ptr(), n, PART_RES, stream=self.stream)
+            xb.record()
             src_ptr, n = self.xchg.finish(stream=self.stream)
+            xc.record()
+            self.xchg_events.append((xa, xb, xc))
         elif self.world > 1:
             from microcket_b200 import shard
             n, src = shard.exchange_pairs(self.mk, torch, self.dist, self.ws, self.pairs, n, self.recv, self.cap_pairs, PART_RES, self.stream)
@@ -531,6 +537,12 @@ def main():
                                    "radix_passes": 9, "implementation_GBps": (alg_p + 9 * 32.0 * p_n) / (p_ms / 1e3) / 1e9}
     except Exception as e:
         roofline["pairs_stage"] = {"error": str(e)}
+    if pipe.xchg_events:
+        ev = pipe.xchg_events[-args.steps:]
+        roofline["exchange_stage"] = {"scatter_ms": sum(a.elapsed_time(b) for a, b, _ in ev) / len(ev),
+                                      "wait_for_all_ranks_ms": sum(b.elapsed_time(c) for _, b, c in ev) / len(ev),
+                                      "scope": "rank 0; scatter = this rank's pairs written into their owners' HBM over NVLink, wait = until "
+                                               "every rank's flag has arrived (includes the ranks' skew)"}
 
     # ---- end to end through the host-buffer C ABI (pinned host SAM in; pairs text, packed pairs and COO out)
     e2e = e2e_res

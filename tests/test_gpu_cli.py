@@ -125,3 +125,30 @@ def test_pairs2bins_default_resolution_list_streamed_and_odd_lines(tmp_path, ora
         b1, b2, ct = oracle.bin_coo(pairs, n, None, HG38_LEN, rs)
         exp = "".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1, b2, ct))
         assert (tmp_path / f"o.{rs}.coo").read_text() == exp, rs
+
+
+@pytest.mark.parametrize("mode,outmode", [("unc", "sorted"), ("flash", "sorted-dedup")])
+def test_sam2pairs_sorted_output_modes(tmp_path, oracle, mode, outmode):
+    """argv[8] = sorted | sorted-dedup: stdout is what `sam2pairs | LANG=C sort -k2,2d -k4,4d -k3,3n -k5,5n` gives (after
+    coordinate dedup for sorted-dedup); log and SAM passthrough are unchanged.  Chunks of 8 MiB: read groups and lines cross them."""
+    n = 60000
+    sam = mk.synth_host(57, mode, "hg38", 0, n, mk.synth_opts(dup_per_1024=200, dup_universe=n))
+    src = tmp_path / "in.sam"; src.write_bytes(b"@HD\tVN:1.6\n@SQ\tSN:chr1\tLN:248956422\n" + sam)
+    op, osam, ost = oracle.sam2pairs(sam, mode, threads=8)
+    env = dict(os.environ, MICROCKET_CHUNK_MB="8")
+    r = subprocess.run([os.path.join(BIN, "sam2pairs"), str(src), mode, str(tmp_path / "S"), "8", "0.5", "10", "yes", outmode],
+                       capture_output=True, env=env, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    if outmode == "sorted":
+        exp = sort_pairs(op)
+    else:
+        names = sorted({f.split(b"\t")[k].decode() for f in op.splitlines() for k in (1, 3)})
+        arr, m = oracle.pairs_parse(op, names)
+        keep, kept = oracle.coord_dedup(arr, m)
+        assert kept < m
+        exp = sort_pairs(b"".join(ln for ln, k in zip(op.splitlines(keepends=True), bytes(keep)[:m]) if k))
+    assert r.stdout == exp
+    assert (tmp_path / f"S.{mode}2pairs.log").read_bytes() == ost.log_text()
+    assert (tmp_path / f"S.{mode}.sam").read_bytes() == osam
+    assert subprocess.run([os.path.join(BIN, "sam2pairs"), str(src), mode, str(tmp_path / "T"), "8", "0.5", "10", "no", "bogus"],
+                          capture_output=True, cwd=tmp_path).returncode == 6
