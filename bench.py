@@ -584,11 +584,37 @@ def main():
         dist.barrier(); dist.destroy_process_group()
 
 
+def bind_near_gpu(local):
+    """Pin this process to the host cores of the GPU's NUMA node (if any are in its affinity mask), so that the pinned staging
+    buffers of the end-to-end leg are first-touched on the socket the GPU's PCIe root hangs off.  → description for the record"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        mine = os.sched_getaffinity(0) & cpus
+        if not mine:
+            return f"gpu on numa node {node}, none of this process's {len(os.sched_getaffinity(0))} cores there"
+        os.sched_setaffinity(0, mine)
+        return f"bound to {len(mine)} cores of numa node {node}"
+    except Exception as e:                                    # never let this break the bench
+        return f"not bound ({str(e)[:60]})"
+
+
 def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     """The same path through the host-buffer C ABI: pinned host SAM pushed window by window (H2D inside), pair text and packed
     pairs pulled to host memory (D2H inside), then duplicate removal + binning with the kept pairs and COO triplets brought back
     to the host.  N > 1: every rank streams its own shard and the packed pairs cross NVLink (owner partition + all-to-all)
     before the dedup.  Wall clock between barriers, max over ranks."""
+    numa = bind_near_gpu(local)
     E = min(args.e2e_groups or args.groups, args.groups)
     if world > 1 and not args.e2e_groups:
         E = min(E, 30_000_000)                     # N ranks pin N x the shard in host memory: 20 GB per rank keeps an 8-GPU box within 160 GB
@@ -700,7 +726,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     else:
         pl_all, h2d, d2h = float(pl), float(t[2]), float(t[3])
     return {"value": pl_all / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "read_groups_per_gpu": E, "ms_per_step": sec * 1e3, "phases_ms_rank0": {k: v / reps for k, v in phases.items()},
+            "read_groups_per_gpu": E, "host_numa": numa, "ms_per_step": sec * 1e3, "phases_ms_rank0": {k: v / reps for k, v in phases.items()},
             "api": "mk_s2p_push/pull/pull_packed/finish from pinned host buffers" +
                    (" + mk_pairs_dedup_bin_host" if world == 1 else " + H2D of the packed pairs, mk_xchg_* exchange over NVLink, mk_pairs_dedup_bin_device, D2H of kept pairs and COO") +
                    "; wall clock incl. all copies, max over ranks"}

@@ -28,7 +28,7 @@ struct Grow {
         size_t n = cap ? cap : ((size_t)64 << 20); while (n < bytes) n *= 2;
         void *q = NULL;
         if (mk_dev_alloc(dev, n, &q) != MK_OK) return MK_ERR_NOMEM;
-        if (used && mk_copy_device(q, p, used) != MK_OK) return MK_ERR_CUDA;
+        if (used && p && mk_copy_device(q, p, used) != MK_OK) return MK_ERR_CUDA;
         mk_dev_free(p); p = q; cap = n;
         return MK_OK;
     }
