@@ -212,6 +212,10 @@ class Pipeline:
             self.xchg = mk.Xchg(world, dist.get_rank(), self.cap_pairs, device=local)
             shard.connect_xchg(torch, dist, self.xchg, dev)
             self.recv = None
+            # every window's pairs are scattered on a side stream while the next window is parsed (MICROCKET_XCHG_OVERLAP=0: one scatter at the end)
+            self.overlap = os.environ.get("MICROCKET_XCHG_OVERLAP", "1") != "0"
+            if self.overlap:
+                self.s2p.attach_xchg(self.xchg, PART_RES)
 
     def run(self, sam, nbytes, pair_events=None, text_len=None):
         torch = self.torch
@@ -226,7 +230,8 @@ class Pipeline:
         if self.xchg is not None:
             xa, xb, xc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             xa.record()
-            self.xchg.scatter(self.pairs.data_ptr(), n, PART_RES, stream=self.stream)
+            if not self.overlap:
+                self.xchg.scatter(self.pairs.data_ptr(), n, PART_RES, stream=self.stream)
             xb.record()
             src_ptr, n = self.xchg.finish(stream=self.stream)
             xc.record()
@@ -541,6 +546,7 @@ def main():
         ev = pipe.xchg_events[-args.steps:]
         roofline["exchange_stage"] = {"scatter_ms": sum(a.elapsed_time(b) for a, b, _ in ev) / len(ev),
                                       "wait_for_all_ranks_ms": sum(b.elapsed_time(c) for _, b, c in ev) / len(ev),
+                                      "overlapped_with_parsing": bool(getattr(pipe, "overlap", False)),
                                       "scope": "rank 0; scatter = this rank's pairs written into their owners' HBM over NVLink, wait = until "
                                                "every rank's flag has arrived (includes the ranks' skew)"}
 

@@ -131,6 +131,11 @@ typedef struct {
     size_t   pairs_text_len, n_pairs, sam_text_len, consumed;
 } mk_s2p_dev_io;
 int  mk_s2p_run_device(mk_ctx *, const char *d_sam, size_t n, int is_last, mk_s2p_dev_io *io, void *stream);
+/* Multi-GPU: every window's packed pairs are sent to their owners (mk_xchg_*, partition resolution `res`) on a side stream
+ * while the next window is parsed; when mk_s2p_run_device returns, the epoch is closed and the caller only has to call
+ * mk_xchg_finish_device.  NULL detaches. */
+struct mk_xchg;
+int  mk_s2p_attach_xchg(mk_ctx *, struct mk_xchg *, uint32_t res);
 /* number of kernel launches issued by this context so far (for bench accounting) */
 uint64_t mk_launch_count(mk_ctx *);
 /* Optional per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figure).
@@ -262,6 +267,12 @@ int  mk_xchg_connect(mk_xchg *, const void *all_handles /* world x 128 bytes, ra
 int  mk_xchg_connect_local(mk_xchg *const *all /* rank order */, int world);
 /* enqueue: this rank's n pairs go to their owners (returns at once; d_pairs may be reused when the stream has passed it) */
 int  mk_xchg_scatter_device(mk_xchg *, const mk_pair *d_pairs, size_t n, uint32_t res, void *stream);
+/* The same exchange in pieces, overlapped with the producer: mk_xchg_begin, any number of parts (each = the d_part[1] pairs
+ * that END at index d_part[0] of d_base, both values on the DEVICE), mk_xchg_end_device; all on one stream.
+ * mk_s2p_attach_xchg makes mk_s2p_run_device do exactly this, one part per window, on a side stream of its own. */
+int  mk_xchg_begin(mk_xchg *);
+int  mk_xchg_scatter_part_device(mk_xchg *, const mk_pair *d_base, const uint64_t *d_part, uint32_t res, void *stream);
+int  mk_xchg_end_device(mk_xchg *, void *stream);
 /* wait on the device until all ranks have delivered; *d_recv / *n_recv: the pairs this rank owns (inside the object's
  * buffer, valid until the scatter after next; may be modified in place, e.g. by mk_pairs_dedup_bin_device) */
 int  mk_xchg_finish_device(mk_xchg *, mk_pair **d_recv, size_t *n_recv, void *stream);

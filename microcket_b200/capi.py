@@ -108,6 +108,7 @@ class Lib:
         L.mk_s2p_chrom_name.argtypes = [vp, i, C.c_char_p, sz]
         L.mk_s2p_run_device.argtypes = [vp, vp, sz, i, P(S2PDevIO), vp]
         L.mk_launch_count.argtypes = [vp]
+        L.mk_s2p_attach_xchg.argtypes = [vp, vp, C.c_uint32]
         L.mk_launch_count.restype = u64
         L.mk_synth_host.argtypes = [u64, i, i, u64, u64, vp, sz, P(sz)]
         L.mk_synth_device.argtypes = [i, u64, i, i, u64, u64, vp, sz, P(sz), vp]
@@ -139,7 +140,8 @@ class Lib:
                            ("mk_xchg_create", [i, i, i, sz, P(vp)]), ("mk_xchg_destroy", [vp]), ("mk_xchg_handle", [vp, vp]),
                            ("mk_xchg_connect", [vp, vp]), ("mk_xchg_connect_local", [P(vp), i]),
                            ("mk_xchg_scatter_device", [vp, vp, sz, C.c_uint32, vp]), ("mk_xchg_finish_device", [vp, P(vp), P(sz), vp]),
-                           ("mk_xchg_launch_count", [vp]),
+                           ("mk_xchg_launch_count", [vp]), ("mk_xchg_begin", [vp]), ("mk_xchg_end_device", [vp, vp]),
+                           ("mk_xchg_scatter_part_device", [vp, vp, vp, C.c_uint32, vp]),
                            ("mk_pairs_partition_device", [vp, vp, sz, i, C.c_uint32, vp, P(u64), vp]),
                            ("mk_pairs_launch_count", [vp])):
             if hasattr(L, name):
@@ -291,6 +293,10 @@ class Sam2Pairs:
 
     def launches(self):
         return self.lib.L.mk_launch_count(self.h)
+
+    def attach_xchg(self, xchg, res):
+        """every window's packed pairs leave for their owners on a side stream while the next window is parsed"""
+        self.lib.check(self.lib.L.mk_s2p_attach_xchg(self.h, xchg.h if xchg is not None else None, res))
 
     def enable_timing(self, on=True):
         self.lib.check(self.lib.L.mk_s2p_enable_timing(self.h, int(on)))

@@ -8,6 +8,12 @@
 #include "ctx.h"
 #include "s2p_kernels.cuh"
 
+struct mk_xchg;
+extern "C" int mk_xchg_begin(mk_xchg *);
+extern "C" int mk_xchg_scatter_part_device(mk_xchg *, const mk_pair *, const uint64_t *, uint32_t, void *);
+extern "C" int mk_xchg_end_device(mk_xchg *, void *);
+#define S2P_XPARTS 4096                            // windows of one mk_s2p_run_device call whose pairs can be scattered separately
+
 static const size_t S2P_CARRY = 8u << 20;          // room in front of every window for the previous window's last group
 static const u32 S2P_BATCH = 1u << 18;             // pairutil.h:48
 
@@ -52,6 +58,9 @@ struct S2PCtx : mk_ctx {
     u64 sc_full_rule = 0; std::vector<u64> sc_tail; u64 sc_true = 0;
     bool use_device_path = false;
     WinState last_state;
+    // overlapped multi-GPU scatter (mk_s2p_attach_xchg)
+    mk_xchg *xchg = nullptr; u32 xchg_res = 0; cudaStream_t s_x = nullptr; DevBuf d_xparts; u32 x_slot = 0;
+    std::vector<cudaEvent_t> x_events; size_t x_ev_used = 0;
     // optional per-kernel timing (bench.py roofline): events around every kernel of every window
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -69,6 +78,8 @@ struct S2PCtx : mk_ctx {
         if (s_comp) cudaStreamDestroy(s_comp);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
+        if (s_x) cudaStreamDestroy(s_x);
+        for (auto e : x_events) cudaEventDestroy(e);
     }
 };
 
@@ -103,6 +114,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.mode = c->cfg.mode; p.min_mapq = c->cfg.min_mapq; p.ratio = c->cfg.min_mapped_ratio; p.lane = c->cfg.lane;
     p.write_sam = c->cfg.write_sam && out_sam; p.emit_text = c->cfg.emit_text && out_text; p.emit_packed = c->cfg.emit_packed && out_pairs;
     p.running_offsets = running;
+    p.xparts = (c->xchg && c->d_xparts.p) ? c->d_xparts.as<unsigned long long>() : nullptr;
     p.self = nullptr;
     return p;
 }
@@ -138,8 +150,30 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     c->launches += 9;
     if (p.write_sam) { k_copy_sam<<<c->grid_gs, 256, 0, s>>>(p); c->launches += 1; }
     mark(5);
-    k_win_end<<<1, 1, 0, s>>>(p);
+    k_win_end<<<1, 1, 0, s>>>(p, c->x_slot);
     c->launches += 1;
+    if (p.xparts && c->xchg && p.out_pairs) {            // this window's pairs leave for their owners while the next window is parsed
+        if (c->x_ev_used == c->x_events.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->x_events.push_back(e); }
+        cudaEvent_t e = c->x_events[c->x_ev_used++];
+        cudaEventRecord(e, s);
+        cudaStreamWaitEvent(c->s_x, e, 0);
+        mk_xchg_scatter_part_device(c->xchg, p.out_pairs, (const uint64_t *)(p.xparts + 2 * c->x_slot), c->xchg_res, c->s_x);
+        c->x_slot = (c->x_slot + 1) % S2P_XPARTS;
+    }
+}
+
+extern "C" int mk_s2p_attach_xchg(mk_ctx *x, mk_xchg *xc, uint32_t res) {
+    if (!x || x->kind != MK_CTX_S2P || (xc && res == 0)) { mk_set_error("mk_s2p_attach_xchg: bad argument"); return MK_ERR_ARG; }
+    S2PCtx *c = (S2PCtx *)x;
+    MK_CUDA(cudaSetDevice(c->cfg.device));
+    c->xchg = xc; c->xchg_res = res;
+    if (xc && !c->s_x) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        MK_CUDA(cudaStreamCreateWithPriority(&c->s_x, cudaStreamNonBlocking, hi));     // its few CTAs should not queue behind a full-grid kernel
+        MK_TRY(c->d_xparts.alloc((size_t)S2P_XPARTS * 16));
+    }
+    return MK_OK;
 }
 
 // fold the recorded events into per-kernel totals (call after the stream is idle)
@@ -659,6 +693,8 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
     c->launches += 1;
     S2PParams p = make_params(c, d_sam, c->d_sclist.as<u64>(), c->sc_cap_dev, io->d_pairs_text, io->pairs_text_cap, io->d_pairs, io->pairs_cap, io->d_sam_text, io->sam_text_cap, c->W, 1, (u64 *)io->d_line_off, io->line_off_cap, io->line_off_base);
     MK_TRY(upload_params(c, p, 2, s));
+    const bool xch = c->xchg && p.xparts && p.out_pairs;
+    if (xch) { MK_TRY(mk_xchg_begin(c->xchg)); c->x_ev_used = 0; }
     // running output offsets restart at 0 for every call
     MK_CUDA(cudaMemsetAsync((char *)dst + offsetof(WinState, out_text), 0, 3 * sizeof(u64), s));
     // every window consumes at least W - (largest read group) bytes; enqueue an upper bound and top up if needed
@@ -686,5 +722,11 @@ extern "C" int mk_s2p_run_device(mk_ctx *x, const char *d_sam, size_t n, int is_
     }
     io->pairs_text_len = st.out_text; io->n_pairs = st.out_pairs; io->sam_text_len = st.out_sam; io->consumed = st.cursor;
     c->last_state = st;
+    if (xch) {                                              // every part is out: close the epoch on the side stream, and let `s` see it
+        MK_TRY(mk_xchg_end_device(c->xchg, c->s_x));
+        if (c->x_events.empty()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->x_events.push_back(e); }
+        MK_CUDA(cudaEventRecord(c->x_events[0], c->s_x));
+        MK_CUDA(cudaStreamWaitEvent(s, c->x_events[0], 0));
+    }
     return MK_OK;
 }

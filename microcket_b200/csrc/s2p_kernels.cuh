@@ -94,6 +94,7 @@ struct S2PParams {
     u64 window_bytes; u32 cap_lines;
     int mode, min_mapq, write_sam, emit_text, emit_packed; float ratio; u16 lane;
     int running_offsets;      // 1: append at st->out_* (device-resident runs); 0: every window writes at 0
+    unsigned long long *xparts;   // optional: per launched window (end, count) of its packed pairs, for the overlapped multi-GPU scatter
     const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
 };
 
@@ -115,7 +116,7 @@ static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     }
 }
 
-static __global__ void k_win_end(S2PParams p) {
+static __global__ void k_win_end(S2PParams p, u32 xslot) {
     WinState *s = p.st;
     u64 ws = s->ws, we = s->we;
     u32 n = s->n_lines;
@@ -135,6 +136,7 @@ static __global__ void k_win_end(S2PParams p) {
     s->groups_done += s->w_groups;
     s->out_text += s->w_text; s->out_pairs += s->w_emit; s->out_sam += s->w_sam;
     if (p.out_line_off && s->out_pairs < p.out_line_off_cap) p.out_line_off[s->out_pairs] = p.line_off_base + s->out_text;   // end of the last line so far
+    if (p.xparts) { p.xparts[2 * xslot] = s->out_pairs; p.xparts[2 * xslot + 1] = s->w_emit; }
 }
 
 // ------------------------------------------------------------------------------------------------ K1: newline index

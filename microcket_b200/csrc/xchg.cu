@@ -39,13 +39,17 @@ __host__ __device__ __forceinline__ u32 xc_owner_hash(u32 chr1, u32 chr2, u32 pb
 __device__ __forceinline__ void st_release_sys_u32(u32 *p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 ld_acquire_sys_u32(const u32 *p) { u32 v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-__global__ void __launch_bounds__(XC_T) k_xchg_scatter(const mk_pair *p, u64 n, XchgPeers peers, XchgCtrl *mine, u32 world, u32 rank, u32 res,
-                                                        u32 epoch, u64 half_cap) {
+// part != NULL: the pairs are the `part[1]` records that END at index part[0] of `p` (both written on the device by the
+// producer, e.g. one sam2pairs window), and nothing is published: several such launches make up one epoch, closed by
+// k_xchg_publish.  part == NULL: p[0, n) is the rank's whole contribution and the last CTA publishes the epoch itself.
+__global__ void __launch_bounds__(XC_T) k_xchg_scatter(const mk_pair *p, u64 n, const unsigned long long *part, XchgPeers peers, XchgCtrl *mine,
+                                                        u32 world, u32 rank, u32 res, u32 epoch, u64 half_cap) {
     __shared__ uint4 s_pair[XC_TILE];
     __shared__ u32 s_cnt[XC_MAX_WORLD], s_off[XC_MAX_WORLD + 1], s_fill[XC_MAX_WORLD];
     __shared__ unsigned long long s_base[XC_MAX_WORLD];
     __shared__ u32 s_last;
     const u32 tid = threadIdx.x, half = epoch & 1u;
+    if (part) { n = part[1]; p += part[0] - n; }
     const u64 n_tiles = (n + XC_TILE - 1) / XC_TILE;
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (tid < XC_MAX_WORLD) { s_cnt[tid] = 0; s_fill[tid] = 0; }
@@ -79,6 +83,7 @@ __global__ void __launch_bounds__(XC_T) k_xchg_scatter(const mk_pair *p, u64 n, 
         }
         __syncthreads();
     }
+    if (part) { __threadfence_system(); return; }
     // ---- completion: the last CTA tells every peer that this rank's pairs of this epoch are all in place
     __threadfence_system();
     __syncthreads();
@@ -95,6 +100,15 @@ __global__ void __launch_bounds__(XC_T) k_xchg_scatter(const mk_pair *p, u64 n, 
         __syncthreads();
         if (tid < world) st_release_sys_u32(&peers.ctrl[tid]->flag[rank], epoch);
     }
+}
+
+// closes an epoch made of partial scatters (all of them earlier in the same stream): what the last CTA of a whole scatter does
+__global__ void k_xchg_publish(XchgPeers peers, XchgCtrl *mine, u32 world, u32 rank, u32 epoch) {
+    const u32 tid = threadIdx.x, half = epoch & 1u;
+    if (tid == 0) { mine->cursor[half ^ 1u] = 0; mine->overflow[half ^ 1u] = 0; }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys_u32(&peers.ctrl[tid]->flag[rank], epoch);
 }
 
 // wait until every rank has delivered `epoch`, then publish the count
@@ -203,7 +217,34 @@ extern "C" int mk_xchg_scatter_device(mk_xchg *x, const mk_pair *d_pairs, size_t
     x->epoch += 1;
     const u64 n_tiles = (n + XC_TILE - 1) / XC_TILE;
     const int grid = (int)std::max<u64>(1, std::min<u64>(n_tiles, (u64)x->sms * 4));
-    k_xchg_scatter<<<grid, XC_T, 0, (cudaStream_t)stream>>>(d_pairs, n, x->peers, x->ctrl.as<XchgCtrl>(), (u32)x->world, (u32)x->rank, res, x->epoch, x->half_cap);
+    k_xchg_scatter<<<grid, XC_T, 0, (cudaStream_t)stream>>>(d_pairs, n, nullptr, x->peers, x->ctrl.as<XchgCtrl>(), (u32)x->world, (u32)x->rank, res, x->epoch, x->half_cap);
+    x->launches += 1;
+    MK_CUDA(cudaGetLastError());
+    return MK_OK;
+}
+
+// The same exchange in pieces, so that it overlaps with the producer: begin an epoch, scatter any number of parts (each the
+// d_part[1] pairs that end at index d_part[0] of d_base; both values live on the DEVICE, written by the producer, e.g. one
+// sam2pairs window), then end the epoch.  All calls of one epoch go to ONE stream.
+extern "C" int mk_xchg_begin(mk_xchg *x) {
+    if (!x) { mk_set_error("mk_xchg_begin: null"); return MK_ERR_ARG; }
+    if (!x->connected) { mk_set_error("mk_xchg_begin: mk_xchg_connect first"); return MK_ERR_STATE; }
+    x->epoch += 1;
+    return MK_OK;
+}
+extern "C" int mk_xchg_scatter_part_device(mk_xchg *x, const mk_pair *d_base, const uint64_t *d_part, uint32_t res, void *stream) {
+    if (!x || !d_base || !d_part || res == 0 || x->epoch == 0) { mk_set_error("mk_xchg_scatter_part_device: bad argument"); return MK_ERR_ARG; }
+    MK_CUDA(cudaSetDevice(x->device));
+    k_xchg_scatter<<<x->sms * 2, XC_T, 0, (cudaStream_t)stream>>>(d_base, 0, (const unsigned long long *)d_part, x->peers, x->ctrl.as<XchgCtrl>(),
+                                                                  (u32)x->world, (u32)x->rank, res, x->epoch, x->half_cap);
+    x->launches += 1;
+    MK_CUDA(cudaGetLastError());
+    return MK_OK;
+}
+extern "C" int mk_xchg_end_device(mk_xchg *x, void *stream) {
+    if (!x || x->epoch == 0) { mk_set_error("mk_xchg_end_device: bad argument"); return MK_ERR_ARG; }
+    MK_CUDA(cudaSetDevice(x->device));
+    k_xchg_publish<<<1, XC_MAX_WORLD, 0, (cudaStream_t)stream>>>(x->peers, x->ctrl.as<XchgCtrl>(), (u32)x->world, (u32)x->rank, x->epoch);
     x->launches += 1;
     MK_CUDA(cudaGetLastError());
     return MK_OK;

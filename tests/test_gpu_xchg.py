@@ -89,3 +89,49 @@ def test_receive_capacity_is_checked():
     torch.cuda.synchronize()
     for x in xs:
         x.close()
+
+
+def test_windows_scattered_while_parsing(oracle):
+    """mk_s2p_attach_xchg: every sam2pairs window's pairs leave for their owners on a side stream (one part per window, the
+    epoch closed when mk_s2p_run_device returns).  Two ranks in one process, small windows (dozens of parts), two epochs; the
+    union of the ranks' dedup + binning equals the oracle's over both shards."""
+    from test_gpu_pairs_text import HG38, HG38_LEN
+    world, n_groups, res = 2, 60000, 5000000
+    xs = [mk.Xchg(world, r, 2 * n_groups) for r in range(world)]
+    mk.Xchg.connect_local(xs)
+    ctxs = [mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_packed=True, window_bytes=1 << 20, sharded=True), HG38)
+            for _ in range(world)]
+    for r in range(world):
+        ctxs[r].attach_xchg(xs[r], res)
+    for epoch in range(2):
+        opts = mk.synth_opts(dup_per_1024=160, dup_universe=world * n_groups)
+        texts = []
+        for r in range(world):
+            buf, nb = mk.synth_device(torch, 70 + epoch, "flash", "hg38", r * n_groups, n_groups, opts=opts)
+            op, _, _ = oracle.sam2pairs(buf[:nb].cpu().numpy().tobytes(), "flash", threads=8, write_sam=False)
+            texts.append(op)
+            text = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            pairs = torch.empty((n_groups + 1024) * 16, dtype=torch.uint8, device="cuda")
+            ctxs[r].reset()
+            io = ctxs[r].run_device(buf.data_ptr(), nb, True, text.data_ptr(), text.numel(), pairs.data_ptr(), n_groups + 1024)
+            assert bytes(text[:io.pairs_text_len].cpu().numpy().tobytes()) == op
+        arr, n = oracle.pairs_parse(b"".join(texts), HG38)
+        keep, kept = oracle.coord_dedup(arr, n)
+        b1, b2, ct = oracle.bin_coo(arr, n, keep, HG38_LEN, 5000)
+        ws = mk.PairsWorkspace(2 * n_groups)
+        o1 = torch.empty(2 * n_groups, dtype=torch.int32, device="cuda"); o2 = torch.empty_like(o1); oc = torch.empty_like(o1)
+        tot_kept, coo_all, got_n = 0, [], 0
+        for r in range(world):
+            ptr, m = xs[r].finish()
+            got_n += m
+            k, z = ws.dedup_bin(ptr, m, HG38_LEN, 5000, o1.data_ptr(), o2.data_ptr(), oc.data_ptr(), 2 * n_groups)
+            tot_kept += k
+            coo_all.append(np.stack([t[:z].cpu().numpy().astype(np.uint32) for t in (o1, o2, oc)], axis=1))
+        assert got_n == n and tot_kept == kept and kept < 0.93 * n
+        coo = np.concatenate(coo_all); coo = coo[np.lexsort((coo[:, 1], coo[:, 0]))]
+        assert coo[:, 0].tolist() == b1 and coo[:, 1].tolist() == b2 and coo[:, 2].tolist() == ct
+        ws.close()
+    for c in ctxs:
+        c.close()
+    for x in xs:
+        x.close()
