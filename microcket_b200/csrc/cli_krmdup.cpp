@@ -9,10 +9,26 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/microcket_b200.h"
 using namespace std;
+
+// Three-stage host pipeline: a reader thread fills input blocks, the main thread pushes them through the GPU context and
+// pulls kept records into output blocks, a writer thread appends those to the files (or stdout).  Reading, the GPU round
+// trip and writing overlap instead of adding up (the reference overlaps them with its own loader / worker / writer threads,
+// krmdup.cpp:300-372).
+template <class T> struct Chan {                      // blocking queue
+    deque<T> q; mutex m; condition_variable cv;
+    void put(T v) { { lock_guard<mutex> l(m); q.push_back(std::move(v)); } cv.notify_one(); }
+    T get() { unique_lock<mutex> l(m); cv.wait(l, [&] { return !q.empty(); }); T v = std::move(q.front()); q.pop_front(); return v; }
+};
+struct InBlock { vector<char> buf; size_t n = 0; };
+struct OutBlock { vector<char> a, b; size_t na = 0, nb = 0; bool last = false; };
 
 static void usage(const char *prg) {
     cerr << "\nUsage: " << prg << " [options] -i <interleaved.paired-end.fq> -o <output.prefix>\n"
@@ -73,6 +89,7 @@ int main(int argc, char *argv[]) {
     if (!readx || !prefix) usage(argv[0]);
     if (cfg.klen1 + cfg.klen2 > 32 || cfg.klen1 + cfg.klen2 < 16) { cerr << "Error: invalid key sizes!\n"; exit(1); }
     if (const char *d = getenv("MICROCKET_DEVICE")) cfg.device = atoi(d);
+    cfg.window_bytes = (size_t)64 << 20;          // small windows: less pinned memory to set up, and the first output arrives early
     if (const char *w = getenv("MICROCKET_WINDOW_MB")) cfg.window_bytes = (size_t)atol(w) << 20;
 #ifndef KRMDUP_PIPE
     FILE *f1 = fopen((string(prefix) + ".read1.fq").c_str(), "a"), *f2 = fopen((string(prefix) + ".read2.fq").c_str(), "a");
@@ -88,28 +105,53 @@ int main(int argc, char *argv[]) {
     auto since = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - ts0.tv_sec) + 1e-9 * (t.tv_nsec - ts0.tv_nsec); };
     if (mk_dedup_create(&cfg, &ctx) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
     if (trace) fprintf(stderr, "[krmdup] context ready after %.3f s\n", since());
-    const size_t IN = 64u << 20, OUT = 32u << 20;
-    vector<char> in(IN), o1(OUT), o2(OUT);
+    const size_t IN = 32u << 20, OUT = 32u << 20;
+    Chan<InBlock *> in_free, in_full; Chan<OutBlock *> out_free, out_full;
+    vector<InBlock> in_pool(3); vector<OutBlock> out_pool(3);
+    for (auto &b : in_pool) { b.buf.resize(IN); in_free.put(&b); }
+    for (auto &b : out_pool) { b.a.resize(OUT); b.b.resize(OUT); out_free.put(&b); }
+    thread reader([&] {
+        while (true) {
+            InBlock *b = in_free.get();
+            b->n = fread(b->buf.data(), 1, IN, fin);
+            in_full.put(b);
+            if (b->n == 0) break;
+        }
+    });
+    thread writer([&] {
+        while (true) {
+            OutBlock *b = out_full.get();
+            if (b->last) break;
+#ifdef KRMDUP_PIPE
+            il.feed(b->a.data(), b->na, b->b.data(), b->nb);
+#else
+            if (b->na) fwrite(b->a.data(), 1, b->na, f1);
+            if (b->nb) fwrite(b->b.data(), 1, b->nb, f2);
+#endif
+            out_free.put(b);
+        }
+    });
     auto drain = [&]() -> int {
         while (true) {
-            size_t a = 0, b = 0;
-            if (mk_dedup_pull(ctx, o1.data(), OUT, &a, o2.data(), OUT, &b) != MK_OK) return -1;
-            if (!a && !b) return 0;
-#ifdef KRMDUP_PIPE
-            il.feed(o1.data(), a, o2.data(), b);
-#else
-            if (a) fwrite(o1.data(), 1, a, f1);
-            if (b) fwrite(o2.data(), 1, b, f2);
-#endif
+            OutBlock *b = out_free.get();
+            b->na = b->nb = 0; b->last = false;
+            if (mk_dedup_pull(ctx, b->a.data(), OUT, &b->na, b->b.data(), OUT, &b->nb) != MK_OK) { out_free.put(b); return -1; }
+            if (!b->na && !b->nb) { out_free.put(b); return 0; }
+            out_full.put(b);
         }
     };
+    auto stop_threads = [&]() { OutBlock *b = out_free.get(); b->last = true; out_full.put(b); writer.join(); reader.join(); };
+    int rc = 0;
     while (true) {
-        size_t n = fread(in.data(), 1, IN, fin);
-        if (n == 0) break;
-        if (mk_dedup_push(ctx, in.data(), n, 0) != MK_OK || drain()) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
+        InBlock *b = in_full.get();
+        if (b->n == 0) break;
+        if (!rc && (mk_dedup_push(ctx, b->buf.data(), b->n, 0) != MK_OK || drain())) rc = 20;
+        in_free.put(b);                                  // keep the reader going to EOF even after an error
     }
+    if (rc) { stop_threads(); cerr << "Error: " << mk_last_error() << "\n"; return 20; }
     mk_dedup_stats st;
-    if (mk_dedup_push(ctx, NULL, 0, 1) != MK_OK || drain() || mk_dedup_finish(ctx, &st) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
+    if (mk_dedup_push(ctx, NULL, 0, 1) != MK_OK || drain() || mk_dedup_finish(ctx, &st) != MK_OK) { stop_threads(); cerr << "Error: " << mk_last_error() << "\n"; return 20; }
+    stop_threads();
     fclose(fin);
 #ifndef KRMDUP_PIPE
     fclose(f1); fclose(f2);
