@@ -103,11 +103,9 @@ int main(int argc, char *argv[]) {
     const bool trace = getenv("MICROCKET_TRACE") != NULL;
     struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
     auto since = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - ts0.tv_sec) + 1e-9 * (t.tv_nsec - ts0.tv_nsec); };
-    if (mk_dedup_create(&cfg, &ctx) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; }
-    if (trace) fprintf(stderr, "[krmdup] context ready after %.3f s\n", since());
     const size_t IN = 32u << 20, OUT = 32u << 20;
     Chan<InBlock *> in_free, in_full; Chan<OutBlock *> out_free, out_full;
-    vector<InBlock> in_pool(3); vector<OutBlock> out_pool(3);
+    vector<InBlock> in_pool(12); vector<OutBlock> out_pool(3);      // 384 MiB of read-ahead: the reader runs while the CUDA context comes up
     for (auto &b : in_pool) { b.buf.resize(IN); in_free.put(&b); }
     for (auto &b : out_pool) { b.a.resize(OUT); b.b.resize(OUT); out_free.put(&b); }
     thread reader([&] {
@@ -118,6 +116,13 @@ int main(int argc, char *argv[]) {
             if (b->n == 0) break;
         }
     });
+    if (mk_dedup_create(&cfg, &ctx) != MK_OK) {                      // (the reader is already filling blocks)
+        cerr << "Error: " << mk_last_error() << "\n";
+        while (true) { InBlock *b = in_full.get(); if (b->n == 0) break; in_free.put(b); }
+        reader.join();
+        return 20;
+    }
+    if (trace) fprintf(stderr, "[krmdup] context ready after %.3f s\n", since());
     thread writer([&] {
         while (true) {
             OutBlock *b = out_full.get();

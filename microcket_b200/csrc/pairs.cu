@@ -48,15 +48,22 @@ __device__ __forceinline__ bool pair_key_differs(const uint4 &a, const uint4 &b)
 }
 
 // stream compaction of the first record of every run (sorted records); single pass with look-back
+// (tiles are claimed with a ticket, here and in the kernels below: a tile's predecessors are then always owned by CTAs that
+// are already running, so the look-back never waits on a CTA that another stream's kernel keeps from being scheduled)
 __global__ void __launch_bounds__(UQ_T) k_unique_rec16(const uint4 *b0, const uint4 *b1, const RadixPlan *plan, u64 n,
-                                                       uint4 *o0, uint4 *o1, u64 *desc, unsigned long long *n_out) {
+                                                       uint4 *o0, uint4 *o1, u64 *desc, unsigned long long *n_out, u32 *ticket) {
     __shared__ u32 s_scan[UQ_T / 32 + 1];
     __shared__ u64 s_base;
+    __shared__ u32 s_tile;
     const uint4 *in = plan->final_buf ? b1 : b0;
     uint4 *out = plan->final_buf ? o0 : o1;                   // the other buffer
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int tile = (int)s_tile;
+        if (tile >= n_tiles) break;
         const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
         uint4 r[UQ_ITEMS]; u32 f = 0, cnt = 0;
         uint4 prev = base > 0 && base <= n ? in[base - 1] : make_uint4(0, 0, 0, 0);
@@ -85,13 +92,18 @@ __global__ void __launch_bounds__(UQ_T) k_unique_rec16(const uint4 *b0, const ui
 
 // run heads of sorted 64-bit keys: head positions + keys, compacted (single pass with look-back)
 __global__ void __launch_bounds__(UQ_T) k_rle_heads(const u64 *k0, const u64 *k1, const RadixPlan *plan, u64 n,
-                                                    u64 *out_key, u32 *out_pos, u64 cap, u64 *desc, unsigned long long *n_out) {
+                                                    u64 *out_key, u32 *out_pos, u64 cap, u64 *desc, unsigned long long *n_out, u32 *ticket) {
     __shared__ u32 s_scan[UQ_T / 32 + 1];
     __shared__ u64 s_base;
+    __shared__ u32 s_tile;
     const u64 *in = plan->final_buf ? k1 : k0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int tile = (int)s_tile;
+        if (tile >= n_tiles) break;
         const u64 base = (u64)tile * UQ_T * UQ_ITEMS + (u64)tid * UQ_ITEMS;
         u64 r[UQ_ITEMS]; u32 f = 0, cnt = 0;
         u64 prev = base > 0 && base <= n ? in[base - 1] : 0;
@@ -208,7 +220,8 @@ extern "C" int mk_pairs_dedup_device(mk_pairs_ws *w, mk_pair *d_pairs, size_t n,
     MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
     MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
     k_unique_rec16<<<lookback_grid((const void *)k_unique_rec16, UQ_T, w->sms), UQ_T, 0, s>>>(
-        b.k[0], b.k[1], w->rws.plan.as<RadixPlan>(), n, b.k[0], b.k[1], w->desc.as<u64>(), w->counter.as<unsigned long long>());
+        b.k[0], b.k[1], w->rws.plan.as<RadixPlan>(), n, b.k[0], b.k[1], w->desc.as<u64>(), w->counter.as<unsigned long long>(),
+        (u32 *)(w->counter.as<unsigned long long>() + 4));
     w->launches += 1;
     struct { unsigned long long kept; } hc;
     u32 final_buf = 0;
@@ -257,7 +270,7 @@ extern "C" int mk_pairs_bin_device(mk_pairs_ws *w, const mk_pair *d_pairs, size_
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
     MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
     k_rle_heads<<<lookback_grid((const void *)k_rle_heads, UQ_T, w->sms), UQ_T, 0, s>>>(
-        k0, k1, w->rws.plan.as<RadixPlan>(), n, w->heads_key.as<u64>(), w->heads_pos.as<u32>(), w->max_pairs, w->desc.as<u64>(), cnt);
+        k0, k1, w->rws.plan.as<RadixPlan>(), n, w->heads_key.as<u64>(), w->heads_pos.as<u32>(), w->max_pairs, w->desc.as<u64>(), cnt, (u32 *)(cnt + 4));
     k_rle_trim<<<1, 1, 0, s>>>(w->heads_key.as<u64>(), w->heads_pos.as<u32>(), cnt, n, w->max_pairs);
     k_rle_finish<<<w->sms * 4, 256, 0, s>>>(w->heads_key.as<u64>(), w->heads_pos.as<u32>(), cnt, n, cap, d_bin1, d_bin2, d_cnt);
     w->launches += 3;

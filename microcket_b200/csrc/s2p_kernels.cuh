@@ -1526,42 +1526,72 @@ static __global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(S2PParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ K5: SAM passthrough
-// One warp per line: the lines of emitted groups are copied verbatim (with their '\n').  Source and destination have
-// unrelated alignments, so the copy runs on the DESTINATION's 16-byte grid: every lane builds one aligned 16-byte chunk from
-// five aligned 32-bit source words and four funnel shifts and stores it with one 128-bit streaming store (the first version
-// moved one byte per lane per instruction); the ragged head and tail of the line go out bytewise.
+// The lines of emitted groups are copied verbatim (with their '\n').  A CTA takes 256 lines: their (source, destination,
+// length) are gathered with coalesced loads into shared memory first, so that the copy loop itself has no dependent
+// metadata loads; then each warp copies its lines two at a time (both lines' loads are issued before the first store).
+// Source and destination have unrelated alignments, so the copy runs on the DESTINATION's 16-byte grid: a lane builds one
+// aligned 16-byte chunk from two aligned 128-bit source loads (word offset chosen by a warp-uniform switch, byte offset by
+// four funnel shifts) and stores it with one 128-bit streaming store; the ragged head and tail of a line go out bytewise.
+struct SamCopy { const char *src; char *dst; u32 len, h, body, q, sh; const uint4 *sa; };
+__device__ __forceinline__ SamCopy sam_copy_setup(const char *src, char *dst, u32 len) {
+    SamCopy c; c.src = src; c.dst = dst; c.len = len;
+    const u32 head = (16u - (u32)((uintptr_t)dst & 15u)) & 15u;      // bytes before the destination's first 16-byte boundary
+    c.h = head < len ? head : len;
+    c.body = (len - c.h) >> 4;                                       // whole aligned 16-byte chunks
+    const char *sb = src + c.h;
+    c.q = ((u32)((uintptr_t)sb & 15u)) >> 2; c.sh = (u32)((uintptr_t)sb & 3u) * 8u;
+    c.sa = (const uint4 *)((uintptr_t)sb & ~(uintptr_t)15);
+    return c;
+}
+__device__ __forceinline__ uint4 sam_copy_chunk(const SamCopy &c, const uint4 &a, const uint4 &b) {
+    u32 w0, w1, w2, w3, w4;                                          // the five source words the chunk is cut from (q is warp-uniform)
+    switch (c.q) {
+    case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+    case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+    case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+    default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+    }
+    return make_uint4(__funnelshift_r(w0, w1, c.sh), __funnelshift_r(w1, w2, c.sh), __funnelshift_r(w2, w3, c.sh), __funnelshift_r(w3, w4, c.sh));
+}
 static __global__ void __launch_bounds__(256) k_copy_sam(S2PParams p) {
+    __shared__ u32 s_src[256], s_dst[256], s_len[256];
     const WinState *st = p.st;
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws, base = st->out_sam;
-    const u32 lane = threadIdx.x & 31u;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (u32 i = warp; i < n_lines; i += nwarps) {
-        if (!(p.lmeta[i] & LM_KEEP)) continue;
-        const u32 d = p.sam_dst[i];
-        if (d == 0xFFFFFFFFu) continue;
-        const u32 start = i ? p.nl_pos[i - 1] + 1 : 0;
-        const u32 len = p.nl_pos[i] - start + 1;
-        const char *src = p.buf + ws + start;
-        char *dst = p.out_sam + base + d;
-        const u32 head = (16u - (u32)((uintptr_t)dst & 15u)) & 15u;      // bytes before the destination's first 16-byte boundary
-        const u32 h = head < len ? head : len;
-        if (lane < h) dst[lane] = src[lane];
-        const u32 body = (len - h) >> 4;                                 // whole aligned 16-byte chunks
-        const char *sb = src + h;
-        const u32 sh = (u32)((uintptr_t)sb & 3u) * 8u;
-        const u32 *sw = (const u32 *)((uintptr_t)sb & ~(uintptr_t)3);
-        for (u32 c = lane; c < body; c += 32) {
-            const u32 *q = sw + 4 * c;
-            const u32 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
-            uint4 o;
-            if (sh) {
-                const u32 w4 = __ldg(q + 4);                              // at most 3 bytes past the chunk: inside the line or the buffer's slack
-                o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-            } else o = make_uint4(w0, w1, w2, w3);
-            st_stream_v4((uint4 *)(dst + h) + c, o);
+    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const u32 n_tiles = (n_lines + 255u) / 256u;
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u32 i = tile * 256u + tid;
+        u32 len = 0, start = 0, d = 0;
+        if (i < n_lines && (p.lmeta[i] & LM_KEEP)) {
+            d = p.sam_dst[i];
+            if (d != 0xFFFFFFFFu) { start = i ? p.nl_pos[i - 1] + 1 : 0; len = p.nl_pos[i] - start + 1; }
         }
-        const u32 t0 = h + (body << 4);
-        if (t0 + lane < len) dst[t0 + lane] = src[t0 + lane];
+        __syncthreads();                                                 // the previous tile's entries have been consumed
+        s_src[tid] = start; s_dst[tid] = d; s_len[tid] = len;
+        __syncthreads();
+#pragma unroll 1
+        for (u32 l = wid; l < 256u; l += 16u) {                          // this warp's lines, two at a time
+            const u32 la = s_len[l], lb = s_len[l + 8u];
+            if (!la && !lb) continue;
+            const SamCopy A = sam_copy_setup(p.buf + ws + s_src[l], p.out_sam + base + s_dst[l], la);
+            const SamCopy B = sam_copy_setup(p.buf + ws + s_src[l + 8u], p.out_sam + base + s_dst[l + 8u], lb);
+            const u32 rounds = ((A.body > B.body ? A.body : B.body) + 31u) >> 5;
+            for (u32 r = 0; r < rounds; ++r) {
+                const u32 c = r * 32u + lane;
+                uint4 a0, a1, b0, b1;
+                const bool ga = c < A.body, gb = c < B.body;
+                // the second word is only read when the source is not 16-byte aligned: it then starts inside the chunk's own bytes
+                if (ga) { a0 = __ldg(A.sa + c); a1 = (A.q | A.sh) ? __ldg(A.sa + c + 1) : a0; }
+                if (gb) { b0 = __ldg(B.sa + c); b1 = (B.q | B.sh) ? __ldg(B.sa + c + 1) : b0; }
+                if (ga) st_stream_v4((uint4 *)(A.dst + A.h) + c, sam_copy_chunk(A, a0, a1));
+                if (gb) st_stream_v4((uint4 *)(B.dst + B.h) + c, sam_copy_chunk(B, b0, b1));
+            }
+            if (lane < A.h) A.dst[lane] = A.src[lane];
+            if (lane < B.h) B.dst[lane] = B.src[lane];
+            const u32 ta = A.h + (A.body << 4), tb = B.h + (B.body << 4);
+            if (ta + lane < A.len) A.dst[ta + lane] = A.src[ta + lane];
+            if (tb + lane < B.len) B.dst[tb + lane] = B.src[tb + lane];
+        }
     }
 }
