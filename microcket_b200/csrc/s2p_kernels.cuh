@@ -742,6 +742,11 @@ struct RowFetch {
 };
 __device__ __forceinline__ u64 fetch8r(const RowFetch &f, u32 r) { return f.f8(r); }
 
+// Every WARP runs its own pipeline over chunks of 32 consecutive lines (chunk = warp index + k x warps in the grid): no block
+// barrier anywhere — a lane's left neighbour is in the same warp, and lane 0 compares its QNAME with the previous chunk's
+// last line through global memory (L2: another warp has just staged those bytes).  ncu on the block-synchronous version:
+// 15 % of the stall samples on the two barriers per round (threads of a CTA finish their lines at very different times:
+// CIGAR length, the rare slow path).
 static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
     extern __shared__ __align__(16) char s_rows[];                     // [PR_STAGES][256][PR_ROW]
     __shared__ u32 s_st[PR_STAGES][256];                               // the staged line's start (relative to ws), or ~0 when not staged
@@ -750,24 +755,26 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
     const u64 ws = st->ws;
     const u64 limit = st->total;
     const int tid = threadIdx.x;
+    const u32 lane = tid & 31u;
 #pragma unroll
     for (int b = 0; b < PR_STAGES; ++b) *(uint4 *)(s_rows + ((size_t)b * 256 + tid) * PR_ROW + 112) = make_uint4(0, 0, 0, 0);
-    const u32 n_round = (n_lines + 255u) & ~255u;                     // whole CTAs stay in the loop (barriers below)
-    const u32 stride = gridDim.x * 256u;
-    u32 i = blockIdx.x * 256u + tid;
-    // start offset of a line (relative to ws) is the previous newline + 1.  The RAW newline position is what is prefetched two
-    // rounds ahead (0xFFFFFFFE for a slot past the last line, 0xFFFFFFFF for line 0): no arithmetic touches the loaded value
-    // before the round that uses it, so the load's latency is never waited for (ncu: 11 % of the stall samples sat on the
-    // `+ 1` right behind the load)
-    auto line_nl = [&](u32 k) -> u32 {
-        u32 v = 0xFFFFFFFEu;
-        if (k < n_lines) { v = 0xFFFFFFFFu; if (k) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p.nl_pos + (k - 1))); }
+    __syncwarp();
+    const u32 n_round = (n_lines + 31u) & ~31u;                       // whole warps stay in the loop
+    const u32 stride = gridDim.x * 256u;                               // lines between two chunks of one warp
+    u32 i = (blockIdx.x * 8u + (tid >> 5)) * 32u + lane;
+    // The newline in front of line k is what gives its start.  It is fetched two rounds ahead with NOTHING depending on the
+    // loaded value until the round that uses it (the index is clamped instead of the value selected), so its latency is
+    // never waited for: kind 0 = no such line, 1 = line 0 (starts at the window start), 2 = start is the loaded value + 1.
+    auto nl_kind = [&](u32 k, bool in_range) -> u32 { return (in_range && k < n_lines) ? (k ? 2u : 1u) : 0u; };
+    auto nl_load = [&](u32 k, u32 kind) -> u32 {
+        u32 v;
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p.nl_pos + (kind == 2u ? k - 1u : 0u)));
         return v;
     };
-    auto stage = [&](int b, u32 nl) {                                  // issue the copies of one line's prefix
+    auto stage = [&](int b, u32 raw, u32 kind) {                       // issue the copies of one line's prefix
         u32 staged = 0xFFFFFFFFu;
-        const u32 start = nl + 1u;
-        if (nl != 0xFFFFFFFEu) {
+        const u32 start = kind == 2u ? raw + 1u : 0u;
+        if (kind) {
             const u64 a = ws + start;
             if (a + 144 <= limit) {
                 staged = start;
@@ -780,21 +787,22 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
         s_st[b][tid] = staged;
         cp_async_commit();
     };
-    u32 nl_cur = i < n_round ? line_nl(i) : 0xFFFFFFFEu;
-    u32 nl_nxt = i + stride < n_round ? line_nl(i + stride) : 0xFFFFFFFEu;
-    if (i < n_round) stage(0, nl_cur);
+    u32 k_cur = nl_kind(i, i < n_round), k_nxt = nl_kind(i + stride, i + stride < n_round);
+    u32 r_cur = nl_load(i, k_cur), r_nxt = nl_load(i + stride, k_nxt);
+    if (i < n_round) stage(0, r_cur, k_cur);
     int b = 0;
     for (; i < n_round; i += stride, b ^= 1) {
         const bool active = i < n_lines;
-        // next round's copies go out first, then the start offset of the round after it is fetched
+        // next round's copies go out first, then the newline of the round after it is fetched
         const bool more = i + stride < n_round;
-        if (more) stage(b ^ 1, nl_nxt);
-        const u32 nl_nn = (more && i + 2 * stride < n_round) ? line_nl(i + 2 * stride) : 0xFFFFFFFEu;
+        if (more) stage(b ^ 1, r_nxt, k_nxt);
+        const u32 k_nn = nl_kind(i + 2 * stride, more && i + 2 * stride < n_round);
+        const u32 r_nn = nl_load(i + 2 * stride, k_nn);
         if (more) cp_async_wait<1>(); else cp_async_wait<0>();
-        __syncthreads();                                               // neighbours read each other's rows
+        __syncwarp();                                                  // neighbours read each other's rows
         if (active) {
             if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu;
-            const u64 a = ws + (u64)(nl_cur + 1u);
+            const u64 a = ws + (u64)(k_cur == 2u ? r_cur + 1u : 0u);
             RowFetch lf; lf.row = s_rows + ((size_t)b * 256 + tid) * PR_ROW;
             const bool staged = s_st[b][tid] != 0xFFFFFFFFu;
             LineRec rec; u32 meta = 0;
@@ -802,7 +810,7 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
             if (staged && parse_line_fast<RowFetch, false>(p, lf, a, limit, tok, rec, meta)) {
                 if (i > 0) {
                     // QNAME equal to the previous line's?  That line's prefix sits in the neighbouring row.
-                    const u32 pst = tid > 0 ? s_st[b][tid - 1] : 0xFFFFFFFFu;
+                    const u32 pst = lane > 0 ? s_st[b][tid - 1] : 0xFFFFFFFFu;
                     const u32 sp = (u32)((ws + pst) & 15u);            // the previous line's first byte inside its row
                     bool eq;
                     if (pst != 0xFFFFFFFFu && sp + tok.t0 + 1 <= 112) {
@@ -818,7 +826,7 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
                             }
                             eq = eq && is_ws(lp.byter(sp + tok.t0));
                         }
-                    } else {                                           // first thread of the CTA, or a line the staging skipped
+                    } else {                                           // first lane of the warp, or a line the staging skipped
                         const u64 pa = ws + (i > 1 ? p.nl_pos[i - 2] + 1 : 0);
                         if (is_blank((int)(unsigned char)p.buf[pa])) eq = qname_equal_slow(p, ws, i, i - 1);
                         else { GlobalFetch gf; gf.buf = p.buf; gf.A = 0; eq = qname_eq_fetch(gf, a, pa, tok.t0); }
@@ -829,8 +837,8 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
             if (meta & LM_KEEP) p.rec[i] = rec;
             p.lmeta[i] = (u8)meta;
         }
-        __syncthreads();                                               // this round's rows are the target of the next round's copies
-        nl_cur = nl_nxt; nl_nxt = nl_nn;
+        __syncwarp();                                                  // this round's rows are the target of the next round's copies
+        k_cur = k_nxt; r_cur = r_nxt; k_nxt = k_nn; r_nxt = r_nn;
     }
 }
 #define PR_SMEM (PR_STAGES * 256 * PR_ROW)
@@ -1052,6 +1060,7 @@ __device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32
 #define EMIT_ITEMS 1
 #define EMIT_TILE (EMIT_THREADS * EMIT_ITEMS)
 #define EMIT_STAGE 20480
+#define GROUP_CHUNK 2048u
 
 // One thread per line.  The flags of the 64 lines around a warp's 32 are gathered with two coalesced byte loads per lane and
 // two ballots each, so that the common case — a kept line whose neighbours are all kept: head test, group extent (<= 3
@@ -1068,7 +1077,17 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
     const u64 ws = st->ws;
     const u32 lane = threadIdx.x & 31u;
     const u32 n_round = (n_lines + 31u) & ~31u;                        // whole warps stay in the loop (warp reduction at its end)
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    // CTAs claim chunks of GROUP_CHUNK lines with a ticket: groups cost very different amounts of work (one record / two /
+    // the general walk), and with a static split the kernel's last 10 % were CTAs waiting for their slowest warp
+    __shared__ u32 s_chunk;
+    while (true) {
+      if (threadIdx.x == 0) s_chunk = atomicAdd(&st->tickets[1], 1u);
+      __syncthreads();
+      const u32 chunk0 = s_chunk * GROUP_CHUNK;
+      __syncthreads();
+      if (chunk0 >= n_round) break;
+      const u32 chunk1 = chunk0 + GROUP_CHUNK < n_round ? chunk0 + GROUP_CHUNK : n_round;
+      for (u32 i = chunk0 + threadIdx.x; i < chunk1; i += 256u) {
       u32 vA = 0, vT = 0, vS = 0;                                      // this line's contribution to its tile's sizes (K4)
       // bit b of the masks <-> line (i - lane) - 1 + b: this lane's line is bit lane + 1
       const u32 wbase = i - lane;
@@ -1178,6 +1197,7 @@ static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
           atomicAdd(tt, vA);
           if (vT) atomicAdd(tt + 1, vT);
           if (vS) atomicAdd(tt + 2, vS);
+      }
       }
     }
     __syncthreads();
