@@ -296,7 +296,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     c->grid_scan4 = sms * std::max(1, std::min(occ, 4));
     c->scan_occ4 = !(getenv("MICROCKET_SCAN_OCC4") && !atoi(getenv("MICROCKET_SCAN_OCC4")));   // 4 CTAs/SM (64 registers): 5.6 vs 6.3 ms per 19.8 GB
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
-    c->grid_emit = sms * std::max(1, std::min(occ, 4));
+    c->grid_emit = sms * std::max(1, occ);
     c->grid_gs = sms * 8;
     cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parse, 256, PR_SMEM);

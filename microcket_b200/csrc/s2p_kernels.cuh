@@ -726,7 +726,16 @@ static __device__ __forceinline__ u32 parse_line_slow(const S2PParams &p, u64 ws
 // pad that is never rewritten, so eight bytes at ANY offset below 112 are three 32-bit loads and two funnel shifts with
 // no bounds test.
 #define PR_ROW 144
-#define PR_STAGES 2
+// PR_STAGES = 2 stages a round AHEAD of the round being parsed (double buffer, 74 KB per CTA: three CTAs per SM);
+// PR_STAGES = 1 stages and parses in the same round and lets four CTAs (32 warps) share the SM.  Measured on B200, 19.8 GB:
+// 3.35 ms with the read-ahead, 3.00 ms with the extra warps (five CTAs: 3.00 ms again) — this kernel wants warps more than it
+// wants prefetch, so one stage is the default.
+#ifndef PR_OCC
+#define PR_OCC 4
+#endif
+#ifndef PR_STAGES
+#define PR_STAGES 1
+#endif
 __device__ __forceinline__ void cp_async16(u32 saddr, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -747,7 +756,7 @@ __device__ __forceinline__ u64 fetch8r(const RowFetch &f, u32 r) { return f.f8(r
 // last line through global memory (L2: another warp has just staged those bytes).  ncu on the block-synchronous version:
 // 15 % of the stall samples on the two barriers per round (threads of a CTA finish their lines at very different times:
 // CIGAR length, the rare slow path).
-static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
+static __global__ void __launch_bounds__(256, PR_STAGES == 1 ? PR_OCC : 3) k_parse(S2PParams p) {
     extern __shared__ __align__(16) char s_rows[];                     // [PR_STAGES][256][PR_ROW]
     __shared__ u32 s_st[PR_STAGES][256];                               // the staged line's start (relative to ws), or ~0 when not staged
     const WinState *st = p.st;
@@ -789,16 +798,17 @@ static __global__ void __launch_bounds__(256, 3) k_parse(S2PParams p) {
     };
     u32 k_cur = nl_kind(i, i < n_round), k_nxt = nl_kind(i + stride, i + stride < n_round);
     u32 r_cur = nl_load(i, k_cur), r_nxt = nl_load(i + stride, k_nxt);
-    if (i < n_round) stage(0, r_cur, k_cur);
+    if (PR_STAGES > 1 && i < n_round) stage(0, r_cur, k_cur);
     int b = 0;
-    for (; i < n_round; i += stride, b ^= 1) {
+    for (; i < n_round; i += stride, b ^= (PR_STAGES - 1)) {
         const bool active = i < n_lines;
         // next round's copies go out first, then the newline of the round after it is fetched
         const bool more = i + stride < n_round;
-        if (more) stage(b ^ 1, r_nxt, k_nxt);
+        if (PR_STAGES == 1) stage(0, r_cur, k_cur);                    // one stage: this round's own copies
+        else if (more) stage(b ^ 1, r_nxt, k_nxt);
         const u32 k_nn = nl_kind(i + 2 * stride, more && i + 2 * stride < n_round);
         const u32 r_nn = nl_load(i + 2 * stride, k_nn);
-        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (more && PR_STAGES > 1) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();                                                  // neighbours read each other's rows
         if (active) {
             if (p.write_sam) p.sam_dst[i] = 0xFFFFFFFFu;
@@ -1068,7 +1078,10 @@ __device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32
 // with no per-member loop (ncu on the first version: 8.8 of 32 lanes active per instruction, the walks over p.lmeta and
 // p.nl_pos being the divergent part).  Anything else (dropped lines inside or next to the group, groups of more than three
 // records, the window's last group) takes the general walk below, which is the definition.
-static __global__ void __launch_bounds__(256) k_group(S2PParams p) {
+#ifndef GROUP_OCC
+#define GROUP_OCC 6
+#endif
+static __global__ void __launch_bounds__(256, GROUP_OCC) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
     WinState *st = p.st;
     if (threadIdx.x < ST_NCOUNTER) s_cnt[threadIdx.x] = 0;
@@ -1429,7 +1442,10 @@ __device__ __forceinline__ char *put_uint_fast(char *out, u32 v, u32 nd) {
 // read id's bytes out of the SAM text (seven aligned 8-byte words, realigned in registers) — is issued before the first
 // byte is formatted: ncu had the read-id fetch, one dependent load per 8 bytes inside the formatting loop, at 25 % of this
 // kernel's stall samples.  64 registers and a 20 KiB stage leave room for five CTAs per SM (was three).
-static __global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(S2PParams p) {
+#ifndef EMIT_OCC
+#define EMIT_OCC 5
+#endif
+static __global__ void __launch_bounds__(EMIT_THREADS, EMIT_OCC) k_emit(S2PParams p) {
     __shared__ __align__(16) char s_stage[EMIT_STAGE + 16];
     __shared__ u32 s_w[2][3][EMIT_THREADS / 32];
     WinState *st = p.st;
