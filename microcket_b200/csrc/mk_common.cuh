@@ -158,54 +158,6 @@ __device__ __forceinline__ u64 lookback_exclusive(u64 *desc, int tile, int first
     return excl;
 }
 
-// Two-step form for kernels that have other work to do between publishing their aggregate and needing the prefix.
-__device__ __forceinline__ void lookback_publish(u64 *desc, int tile, int first_tile, u64 aggregate) {
-    st_volatile_u64(&desc[tile], (tile == first_tile ? LB_INC : LB_AGG) | aggregate);
-}
-__device__ __forceinline__ u64 lookback_resolve(u64 *desc, int tile, int first_tile, u64 aggregate, int lane) {
-    if (tile == first_tile) return 0;
-    u64 excl = 0;
-    int t = tile - 1;
-    while (true) {
-        const int mine = t - lane;
-        const u64 d = mine >= first_tile ? ld_volatile_u64(&desc[mine]) : LB_INC;
-        const u32 st = (u32)(d >> 62);
-        if (__any_sync(0xffffffffu, st == 0)) continue;
-        const u32 inc_mask = __ballot_sync(0xffffffffu, st == 2);
-        u64 v = LB_VAL(d);
-        if (inc_mask) { const int first_inc = __ffs(inc_mask) - 1; if (lane > first_inc) v = 0; }
-#pragma unroll
-        for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        excl += v;
-        if (inc_mask) break;
-        t -= 32;
-    }
-    if (lane == 0) st_volatile_u64(&desc[tile], LB_INC | (excl + aggregate));
-    return excl;
-}
-
-// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (sm_90+; SASS: UBLKCP / SYNCS)
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
-    u32 ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) {} }
-__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ---- forward byte reader over global memory using aligned 8-byte loads
 struct ByteReader {
     const u64 *base;   // 8-byte aligned buffer base

@@ -587,8 +587,8 @@ __global__ void k_cell_counts(const u32 *cell_first, const unsigned long long *c
 }
 
 // decoded pairs landed in the sort's other buffer: bring them home when that is not the caller's
-__global__ void k_copy_if_alt(const RadixPlan *plan, const uint4 *alt, uint4 *home, const unsigned long long *counters) {
-    if (plan->final_buf != 1) return;                                  // keys ended in `home`'s twin: the pairs are already in `home`
+__global__ void k_copy_if_alt(const RadixPlan *plan, u32 keys_in_home_when, const uint4 *alt, uint4 *home, const unsigned long long *counters) {
+    if (plan->final_buf != keys_in_home_when) return;                  // the sorted keys ended in the workspace: the pairs are already home
     const u64 n = counters[0];
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) home[i] = alt[i];
 }
@@ -629,11 +629,16 @@ extern "C" int mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *w, mk_pair *d_pair
     MK_CUDA(cudaMemsetAsync(w->counter.p, 0, 64, s));
     unsigned long long *cnt = w->counter.as<unsigned long long>();
     if (d_keep) MK_CUDA(cudaMemsetAsync(d_keep, 0, n, s));
-    uint4 *k0 = w->alt.as<uint4>(), *k1 = (uint4 *)d_pairs;           // the pairs buffer doubles as the second sort buffer
-    k_pack_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, d_by_id, d_nb_id, pc, k0, cnt + 3);
-    w->launches += 1;
     RadixSchedule sch; sch.n_pass = (int)((pc.total_bits + 7) / 8);
     for (int i = 0; i < sch.n_pass; ++i) sch.byte_of[i] = i;
+    // The pairs buffer doubles as one of the two sort buffers.  The decoded pairs go to the buffer the sorted keys are NOT in:
+    // with an odd number of passes the keys start IN the pairs buffer (packed in place: a thread reads pair i and writes key i),
+    // end in the workspace, and the kept pairs land where the caller wants them without a copy (k_copy_if_alt covers the
+    // case of a pass the device found trivial and skipped).
+    const bool in_place = (sch.n_pass & 1) != 0;
+    uint4 *k0 = in_place ? (uint4 *)d_pairs : w->alt.as<uint4>(), *k1 = in_place ? w->alt.as<uint4>() : (uint4 *)d_pairs;
+    k_pack_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, d_by_id, d_nb_id, pc, k0, cnt + 3);
+    w->launches += 1;
     Rec16::Bufs b; b.k[0] = k0; b.k[1] = k1; b.v[0] = b.v[1] = nullptr;
     MK_TRY(radix_sort<Rec16>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
@@ -644,8 +649,8 @@ extern "C" int mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *w, mk_pair *d_pair
         d_bin1, d_bin2, w->heads_pos.as<u32>(), cap, d_keep, d_kept_idx, w->desc.as<u64>(), cnt, (u32 *)(cnt + 4));
     k_uniq_trim<<<1, 1, 0, s>>>(k0, k1, plan, n, d_keep, cnt);
     k_cell_counts<<<w->sms * 4, 256, 0, s>>>(w->heads_pos.as<u32>(), cnt, cap, d_cnt);
-    // sorted keys sat in buffer final_buf; the decoded pairs went to the other one
-    k_copy_if_alt<<<w->sms * 4, 256, 0, s>>>(plan, k0, k1, cnt);
+    // sorted keys sat in buffer final_buf; the decoded pairs went to the other one: bring them home if that is the workspace
+    k_copy_if_alt<<<w->sms * 4, 256, 0, s>>>(plan, in_place ? 0u : 1u, w->alt.as<uint4>(), (uint4 *)d_pairs, cnt);
     w->launches += 4;
     unsigned long long h[4];
     MK_CUDA(cudaMemcpyAsync(h, cnt, 32, cudaMemcpyDeviceToHost, s));

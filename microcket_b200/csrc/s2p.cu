@@ -37,13 +37,13 @@ struct S2PCtx : mk_ctx {
     size_t W = 0, in_cap = 0; u32 cap_lines = 0, n_desc = 0, sc_cap = 0;
     u32 chr_slots = 0, chr_cap = 0, sc_cap_dev = 0;
     cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
-    u32 n_chunks_cap = 0; bool scan_chunks = true;
+    u32 n_chunks_cap = 0;
     DevBuf d_cklist, d_ckcnt, d_tiletot;
     DevBuf d_params;                               // device copies of the kernels' parameter blocks (S2PParams.self)
     u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
     S2PSlot slot[2];
-    int grid_scan = 0, grid_scan4 = 0, scan_occ4 = 0, grid_scan8 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0, scan_nt = 4;
+    int grid_scan4 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0;
     u64 launches = 0, fallback_windows = 0;
     // host streaming state
     std::vector<char> tail;                        // input not yet part of a window (a partial last line, or small pushes)
@@ -243,7 +243,6 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     c->n_desc = std::max<u32>((u32)((S2P_CARRY + c->W) / S2P_TILE_BYTES + 4), c->n_sub_cap);   // k_win_begin's grid covers both
     c->sc_cap = c->cap_lines / 2 + 16; c->sc_cap_dev = 0;
     c->n_chunks_cap = (u32)((S2P_CARRY + c->W) / SC_CHUNK + 8) & ~3u;       // multiple of 4: counts and prefixes are read as uint4
-    c->scan_chunks = !(getenv("MICROCKET_SCAN_CHUNKS") && !atoi(getenv("MICROCKET_SCAN_CHUNKS")));   // 0: look-back scan only (A/B)
     c->chr_cap = 16384; c->chr_slots = 32768;
     int rc = MK_OK;
 #define A(x) do { if (rc == MK_OK) rc = (x); } while (0)
@@ -286,15 +285,8 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaMemcpy(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice);
     // grids: the two look-back kernels need every CTA resident
     int sms = mk_sm_count(cfg->device), occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<4>, S2P_SCAN_THREADS, 4 * 8192);
-    c->grid_scan = sms * std::max(1, std::min(occ, 4));
-    cudaFuncSetAttribute(k_scan_lines<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<8>, S2P_SCAN_THREADS, 8 * 8192);
-    c->grid_scan8 = sms * std::max(1, std::min(occ, 4));
-    if (getenv("MICROCKET_SCAN_NT")) c->scan_nt = atoi(getenv("MICROCKET_SCAN_NT"));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_lines<4, 4>, S2P_SCAN_THREADS, 4 * 8192);
     c->grid_scan4 = sms * std::max(1, std::min(occ, 4));
-    c->scan_occ4 = !(getenv("MICROCKET_SCAN_OCC4") && !atoi(getenv("MICROCKET_SCAN_OCC4")));   // 4 CTAs/SM (64 registers): 5.6 vs 6.3 ms per 19.8 GB
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, occ);
     c->grid_gs = sms * 8;
