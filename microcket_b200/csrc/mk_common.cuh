@@ -158,6 +158,8 @@ __device__ __forceinline__ u64 lookback_exclusive(u64 *desc, int tile, int first
     return excl;
 }
 
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
 // ---- forward byte reader over global memory using aligned 8-byte loads
 struct ByteReader {
     const u64 *base;   // 8-byte aligned buffer base
