@@ -472,17 +472,25 @@ __global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, cons
     if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
 }
 
-__device__ __forceinline__ mk_pair unpack_key(uint4 k, const PackCfg &c, const u32 *dec_off, const u16 *dec_id) {
+// chromosome (index into dec_off) of a bin: last entry of dec_off that is <= bin.  `hint` is tried first: keys are sorted by
+// bin1, a thread's consecutive records mostly share their chromosome, and three quarters of all pairs are cis (bin2 on bin1's
+// chromosome), so the binary search over the table (dependent loads) is the rare path.
+__device__ __forceinline__ u32 chrom_of_bin(u32 bin, u32 hint, const PackCfg &c, const u32 *dec_off) {
+    if (dec_off[hint] <= bin && (hint + 1 == c.n_dec || bin < dec_off[hint + 1])) return hint;
+    u32 l = 0, h = c.n_dec - 1;
+    while (l < h) { const u32 m = (l + h + 1) >> 1; if (dec_off[m] <= bin) l = m; else h = m - 1; }
+    return l;
+}
+__device__ __forceinline__ mk_pair unpack_key(uint4 k, const PackCfg &c, const u32 *dec_off, const u16 *dec_id, u32 &hint) {
     u64 lo = (u64)k.x | ((u64)k.y << 32), hi = (u64)k.z;
     u32 st = (u32)take_bits(lo, hi, 2); const u32 sw = (u32)take_bits(lo, hi, 1);
     u32 r2 = (u32)take_bits(lo, hi, c.nr), r1 = (u32)take_bits(lo, hi, c.nr);
     const u32 lane = (u32)take_bits(lo, hi, c.nl);
     u32 b = (u32)take_bits(lo, hi, c.nb), a = (u32)take_bits(lo, hi, c.nb);
-    if (sw) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); }
-    // chromosome of a bin: last entry of dec_off that is <= bin
-    u32 ka = 0, kb = 0;
-    { u32 l = 0, h = c.n_dec - 1; while (l < h) { u32 m = (l + h + 1) >> 1; if (dec_off[m] <= a) l = m; else h = m - 1; } ka = l; }
-    { u32 l = 0, h = c.n_dec - 1; while (l < h) { u32 m = (l + h + 1) >> 1; if (dec_off[m] <= b) l = m; else h = m - 1; } kb = l; }
+    u32 ka = chrom_of_bin(a, hint, c, dec_off);                  // (a <= b here: the key holds the bins in upper-triangle order)
+    u32 kb = chrom_of_bin(b, ka, c, dec_off);
+    hint = ka;
+    if (sw) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; t = ka; ka = kb; kb = t; st = ((st & 1u) << 1) | (st >> 1); }
     mk_pair o;
     o.pos1 = (a - dec_off[ka]) * c.res + r1; o.pos2 = (b - dec_off[kb]) * c.res + r2;
     o.chr1 = dec_id[ka]; o.chr2 = dec_id[kb]; o.strands = (u8)st; o.lane = (u16)lane;
@@ -546,6 +554,7 @@ __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint
         }
         __syncthreads();
         u64 ok = (s_base & 0x7FFFFFFFu) + bk + ik - nk, oc = (s_base >> 31) + bc + ic - nc;
+        u32 hint = 0;
 #pragma unroll
         for (int k = 0; k < UQ_ITEMS; ++k) {
             if (fc & (1u << k)) {
@@ -558,7 +567,7 @@ __global__ void __launch_bounds__(UQ_T) k_uniq_cells(const uint4 *b0, const uint
                 ++oc;
             }
             if (fk & (1u << k)) {
-                out[ok] = unpack_key(r[k], c, dec_off, dec_id);
+                out[ok] = unpack_key(r[k], c, dec_off, dec_id, hint);
                 if (keep) keep[r[k].w] = 1;
                 if (kept_idx) kept_idx[ok] = r[k].w;
                 ++ok;

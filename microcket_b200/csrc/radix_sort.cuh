@@ -42,8 +42,14 @@ struct KV64 {
 };
 struct Rec16 {
     typedef uint4 Key;
-    static constexpr int ITEMS = 8;
-    static constexpr int MIN_BLOCKS = 4;          // 64 registers: four resident tiles per SM hide the look-back and scatter latency
+#ifndef RS_REC16_ITEMS
+#define RS_REC16_ITEMS 8
+#endif
+#ifndef RS_REC16_MINB
+#define RS_REC16_MINB 4
+#endif
+    static constexpr int ITEMS = RS_REC16_ITEMS;
+    static constexpr int MIN_BLOCKS = RS_REC16_MINB;   // 64 registers: four resident tiles per SM hide the look-back and scatter latency
     static constexpr bool HAS_VAL = false;
     struct Bufs { uint4 *k[2]; u32 *v[2]; };
     __device__ static __forceinline__ u32 digit(const uint4 &k, int byte) {

@@ -11,6 +11,7 @@
 // All window geometry lives in device memory (WinState), so consecutive windows are
 // enqueued back to back without a host round trip.
 #pragma once
+#include <type_traits>
 #include "mk_common.cuh"
 
 #define S2P_TILE_BYTES 32768
@@ -620,53 +621,112 @@ __device__ __forceinline__ bool dec_field(const F &buf, u32 abs, u32 len, u32 &o
     return ok;
 }
 
-struct FastTok { u32 t0; u64 q[5]; bool ok; };                       // QNAME length and its first 40 bytes (zero padded)
+// first byte < 0x21 in the 8 bytes of x (0..7), or 8 when there is none
+__device__ __forceinline__ u32 first_ws8(u64 x) {
+    const u32 lo = lt21_y((u32)x), hi = lt21_y((u32)(x >> 32));
+    if (lo) return (u32)(__ffs(lo) - 1) >> 3;
+    if (hi) return 4u + ((u32)(__ffs(hi) - 1) >> 3);
+    return 8u;
+}
+struct FastTok { u32 t0; };                                           // QNAME length
 
+// decimal number from the low `len` (1..8) characters of x; false if one of them is not a digit
+__device__ __forceinline__ bool dec_from8(u64 x, u32 len, u32 &v) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if ((u32)k < len) { const u32 d = (u32)((x >> (8 * k)) & 0xFF) - '0'; ok &= d <= 9u; v = v * 10u + d; }
+    }
+    return ok;
+}
+// x = the 8 bytes at a field's start: length of the field if it ends (on a single TAB) inside them, else 8
+__device__ __forceinline__ u32 field_end8(u64 x, bool &tab) {
+    const u32 e = first_ws8(x);
+    tab = e < 8u && (u32)((x >> (8u * e)) & 0xFFu) == (u32)'\t';
+    return e;
+}
+
+// Field by field: QNAME's end comes from 16-byte words (as many as the QNAME is long), every later field from the eight bytes
+// at its start, which also hold its characters (the first version built the separator mask of all seven staged words and
+// then fetched every field again: 22 % of k_parse's instructions were that mask, ncu).  Anything unusual returns false and
+// the byte-loop parser decides: separators other than a single TAB, empty fields, non-digits, FLAG > 5 / RNAME > 8 / POS > 10 /
+// MAPQ > 3 characters, a header line, or a CIGAR that does not end inside the 112 staged bytes.
 template <class F, bool WANT_Q, class RT>
 __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, const u64 a, const u64 limit, FastTok &tok, RT &rec, u32 &meta) {
-    tok.ok = false;
     if (a + 144 > limit) return false;
-    const u64 A = a & ~(u64)15;
-    const u32 s = (u32)(a - A);
-    uint4 w[7];
+    const u32 s = (u32)(a & 15u);                                     // the line's first byte inside its row
+    // ---- QNAME: first byte below 0x21 from s on
+    u32 e0 = 255u;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) w[j] = f.ld16r(16 * j);
-    if ((char)((w[0].x >> 0) & 0xFF) == '@' && s == 0) return false;   // cheap early-out; the exact test is below
-    u32 m0 = lt21_mask16(w[0]) | (lt21_mask16(w[1]) << 16), m1 = lt21_mask16(w[2]) | (lt21_mask16(w[3]) << 16);
-    u32 m2 = lt21_mask16(w[4]) | (lt21_mask16(w[5]) << 16), m3 = lt21_mask16(w[6]);
-    if (s) {                                                          // bit j <-> byte a + j
-        m0 = __funnelshift_r(m0, m1, s); m1 = __funnelshift_r(m1, m2, s); m2 = __funnelshift_r(m2, m3, s); m3 >>= s;
-    }
-    const u32 t0 = pop_lowest128(m0, m1, m2, m3), t1 = pop_lowest128(m0, m1, m2, m3), t2 = pop_lowest128(m0, m1, m2, m3);
-    const u32 t3 = pop_lowest128(m0, m1, m2, m3), t4 = pop_lowest128(m0, m1, m2, m3), t5 = pop_lowest128(m0, m1, m2, m3);
-    if (t5 >= 112 - s) return false;                                  // six separators inside the words we looked at
-    // every separator must be a single TAB, every field non-empty
-    if (t0 == 0 || t1 == t0 + 1 || t2 == t1 + 1 || t3 == t2 + 1 || t4 == t3 + 1 || t5 == t4 + 1) return false;
-    if (f.byter(s + t0) != '\t' || f.byter(s + t1) != '\t' || f.byter(s + t2) != '\t' || f.byter(s + t3) != '\t' || f.byter(s + t4) != '\t' ||
-        f.byter(s + t5) != '\t') return false;
-    if (f.byter(s) == '@') return false;
-    const u32 l_flag = t1 - t0 - 1, l_name = t2 - t1 - 1, l_pos = t3 - t2 - 1, l_mapq = t4 - t3 - 1;
-    if (l_flag > 5 || l_name > 8 || l_pos > 10 || l_mapq > 3) return false;
-    u32 flag, pos, mapq;
-    if (!dec_field(f, s + t0 + 1, l_flag, flag)) return false;
-    if (!dec_field(f, s + t2 + 1, l_pos, pos)) return false;
-    if (!dec_field(f, s + t3 + 1, l_mapq, mapq)) return false;
-    tok.t0 = t0;
-    if (WANT_Q) {                                                      // QNAME words for the neighbour-lane comparison
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            u64 x = (u32)(8 * k) < t0 ? fetch8r(f, s + 8 * k) : 0;
-            if (t0 < (u32)(8 * k + 8) && t0 > (u32)(8 * k)) x &= (1ull << (8 * (t0 - 8 * k))) - 1;
-            tok.q[k] = x;
+    for (int j = 0; j < 7; ++j) {
+        if (e0 == 255u) {
+            u32 m = lt21_mask16(f.ld16r(16 * j));
+            if (j == 0) m = (m >> s) << s;
+            if (m) e0 = 16u * j + (u32)__ffs((int)m) - 1u;
         }
     }
-    tok.ok = t0 <= 40;
+    if (e0 == 255u || e0 == s) return false;                          // no separator in the staged bytes / empty QNAME (or leading blank)
+    if (f.byter(s) == '@' || f.byter(e0) != '\t') return false;
+    const u32 t0 = e0 - s;
+    bool tab;
+    // ---- FLAG
+    u32 r = e0 + 1u;
+    u64 x = fetch8r(f, r);
+    const u32 l_flag = field_end8(x, tab);
+    if (!tab || l_flag == 0 || l_flag > 5) return false;
+    u32 flag = 0;
+    if (!dec_from8(x, l_flag, flag)) return false;
+    // ---- RNAME (up to 8 bytes: its TAB may be the ninth)
+    r += l_flag + 1u;
+    const u32 r_name = r;
+    x = fetch8r(f, r);
+    u32 l_name = field_end8(x, tab);
+    if (l_name == 8u) tab = f.byter(r + 8u) == '\t';
+    if (!tab || l_name == 0) return false;
+    u64 name8 = x;
+    if (l_name < 8) name8 &= (1ull << (8 * l_name)) - 1;
+    // ---- POS (up to 10 digits)
+    r += l_name + 1u;
+    x = fetch8r(f, r);
+    u32 l_pos = field_end8(x, tab);
+    u32 pos = 0;
+    if (l_pos == 8u) {
+        if (!dec_from8(x, 8, pos)) return false;
+        const u64 x2 = fetch8r(f, r + 8u);
+        const u32 l2 = field_end8(x2, tab);
+        if (!tab || l2 > 2) return false;
+        if (!dec_from8(x2, l2, pos)) return false;
+        l_pos = 8u + l2;
+    } else {
+        if (!tab || l_pos == 0) return false;
+        if (!dec_from8(x, l_pos, pos)) return false;
+    }
+    // ---- MAPQ
+    r += l_pos + 1u;
+    x = fetch8r(f, r);
+    const u32 l_mapq = field_end8(x, tab);
+    if (!tab || l_mapq == 0 || l_mapq > 3) return false;
+    u32 mapq = 0;
+    if (!dec_from8(x, l_mapq, mapq)) return false;
+    // ---- CIGAR: its end, eight bytes at a time (the separator must lie inside the 112 staged bytes)
+    r += l_mapq + 1u;
+    const u32 r_cig = r;
+    u64 xc = fetch8r(f, r);
+    const u64 x_first = xc;
+    u32 l_cig = 0;
+    while (true) {
+        const u32 e = field_end8(xc, tab);
+        l_cig += e;
+        if (e < 8u) break;
+        if (r_cig + l_cig + 8u > 112u) return false;
+        xc = fetch8r(f, r_cig + l_cig);
+    }
+    if (!tab || l_cig == 0 || r_cig + l_cig >= 112u) return false;
+    tok.t0 = t0;
     meta = 0;
     if (mapq < (u32)p.min_mapq || (flag & 0x700u)) return true;       // pairutil.h:157-161
     meta = LM_KEEP;
     // RNAME: FNV-1a over its bytes, same as the byte loop
-    u64 name8 = fetch8r(f, s + t1 + 1);
-    if (l_name < 8) name8 &= (1ull << (8 * l_name)) - 1;
     u64 h = 0xCBF29CE484222325ull;
 #pragma unroll
     for (int k = 0; k < 8; ++k) if ((u32)k < l_name) h = hash_step(h, (int)((name8 >> (8 * k)) & 0xFF));
@@ -674,11 +734,10 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     u32 val = 0, idx = 0, leftClip = 0, rightClip = 0, mappable = 0;
     u32 cur = pos, right0 = 0, left1 = 0, right1 = 0, last_right = 0;
     bool err = false;
-    const u32 l_cig = t5 - t4 - 1;
-    u64 x = 0;
+    u64 xw = x_first;
     for (u32 k = 0; k < l_cig; ++k) {
-        if ((k & 7) == 0) x = fetch8r(f, s + t4 + 1 + k);
-        const int c = (int)(x & 0xFF); x >>= 8;
+        if ((k & 7) == 0 && k) xw = fetch8r(f, r_cig + k);
+        const int c = (int)(xw & 0xFF); xw >>= 8;
         const u32 d = (u32)(c - '0');
         if (d <= 9u) { val = val * 10u + d; continue; }
         if (c == 'H' || c == 'S') {
@@ -698,7 +757,7 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     rec.pos = pos; rec.right0 = right0; rec.left1 = left1; rec.right1 = right1;
     rec.leftClip = leftClip; rec.rightClip = rightClip; rec.mappable = mappable; rec.line_len = 0;
     rec.flag = (u16)flag; rec.qname_len = (u16)t0;
-    rec.chr_slot = (u16)chr_lookup_insert(p, h, name8, p.buf, a + t1 + 1, l_name);
+    rec.chr_slot = (u16)chr_lookup_insert(p, h, name8, p.buf, a + (r_name - s), l_name);
     const u32 segCnt = idx + 1;
     if (last_right == 0) err = true;
     rec.segCnt = err ? 0 : (u8)(segCnt > 2 ? 3 : segCnt);
@@ -888,13 +947,6 @@ __device__ __forceinline__ bool mates(const Seg &lone, const Seg &c) {
 }
 __device__ __forceinline__ u32 distal_end(const Seg &s) { return (int)s.leftClip > (int)s.rightClip ? s.right0 : s.pos; }
 
-// first byte < 0x21 in the 8 bytes of x (0..7), or 8 when there is none
-__device__ __forceinline__ u32 first_ws8(u64 x) {
-    const u32 lo = lt21_y((u32)x), hi = lt21_y((u32)(x >> 32));
-    if (lo) return (u32)(__ffs(lo) - 1) >> 3;
-    if (hi) return 4u + ((u32)(__ffs(hi) - 1) >> 3);
-    return 8u;
-}
 // Exact comparison of the first tokens (QNAMEs) of lines a and b, 8 bytes at a time.  Bytes below 0x21 that are not
 // white space, and leading blanks, are left to the byte loop so that the result is operator>>'s in every case.
 static __device__ __noinline__ bool qname_equal_bytes(const S2PParams &p, u64 pa, u64 pb) {
@@ -1072,99 +1124,164 @@ __device__ __forceinline__ Resolved resolve_group(const S2PParams &p, u32 n, u32
 #define EMIT_STAGE 20480
 #define GROUP_CHUNK 2048u
 
-// One thread per line.  The flags of the 64 lines around a warp's 32 are gathered with two coalesced byte loads per lane and
-// two ballots each, so that the common case — a kept line whose neighbours are all kept: head test, group extent (<= 3
-// records), passthrough size and read-id position — is bit arithmetic on two 64-bit masks plus the records themselves,
-// with no per-member loop (ncu on the first version: 8.8 of 32 lanes active per instruction, the walks over p.lmeta and
-// p.nl_pos being the divergent part).  Anything else (dropped lines inside or next to the group, groups of more than three
-// records, the window's last group) takes the general walk below, which is the definition.
+// A warp takes 128 consecutive lines.  Their KEEP / EQ flags (and those of the lines around them) are gathered with five
+// coalesced byte loads per lane and ten ballots; from the masks every lane classifies its four lines by bit arithmetic: not a
+// group head, head of a group of exactly 1 / 2 / 3 consecutive kept lines whose neighbours are kept too (the common case), or
+// "needs the general walk" (dropped lines inside or next to the group, more than three records, the window's last group).
+// The heads are then COMPACTED by class into per-warp lists and resolved class by class, 32 at a time: all lanes of a batch
+// run the same case of the reference's analysis.  ncu on the one-thread-per-line version: 8.8, then (after the masks) 11 of
+// 32 lanes active per instruction — a single-record group, a two-record group and a non-head line in neighbouring lanes
+// serialise three code paths.  The general walk below is the definition; the fast classes are shortcuts to its result.
+struct GroupSums { u32 vA, vT, vS; };
+__device__ __forceinline__ void group_finish(const S2PParams &p, u32 i, u32 mi, u32 n, u32 n1, u32 n2, const u32 *first, const u32 *r1, const u32 *r2,
+                                             u32 sam_len, u32 prev, u32 *s_cnt, GroupSums &sum) {
+    GroupRes g; g.posA = g.posB = 0; g.chrA = g.chrB = 0; g.strands = 0;
+    {
+        const LineRec *rp = &p.rec[prev];
+        g.rid_len = rp->qname_len; g.rid_off = (prev ? p.nl_pos[prev - 1] + 1 : 0) + rp->qname_off;
+    }
+    g.last_line = prev; g.text_len = 0; g.sam_len = sam_len;
+    const Resolved rs = resolve_group(p, n, n1, n2, &p.rec[first[0]], &p.rec[first[1]], &p.rec[r1[0]], &p.rec[r1[1]], &p.rec[r2[0]], &p.rec[r2[1]]);
+    g.status = rs.status;
+    u32 meta = mi | LM_HEAD | LM_PROC;
+    if (rs.have) {
+        g.posA = rs.p1; g.posB = rs.p2; g.strands = rs.strands;
+        const ChrSlot *ca = &p.chr[rs.sA], *cb = &p.chr[rs.sB];
+        g.chrA = (u16)ca->id; g.chrB = (u16)cb->id;
+        if (g.status != ST_SELFCIRCLE) {
+            meta |= LM_EMIT;
+            g.text_len = (u32)g.rid_len + ca->len + cb->len + dec_digits(rs.p1) + dec_digits(rs.p2) + 9u;
+        }
+    }
+    if (!(meta & LM_EMIT)) g.sam_len = 0;
+    if (g.status != ST_NONE) atomicAdd(&s_cnt[g.status], 1u);
+    p.res[i] = g;
+    p.lmeta[i] = (u8)meta;
+    sum.vA += 1u | ((meta & LM_EMIT) ? 1u << 16 : 0u);
+    if (meta & LM_EMIT) { sum.vT += g.text_len; if (p.write_sam) sum.vS += g.sam_len; }
+}
+
+// bits [32 r + b, 32 r + b + 32) of a 160-bit mask held in five words, r a compile-time constant and b in [0, 34): only
+// static register indices (a dynamically indexed array would live in local memory)
+template <u32 R>
+__device__ __forceinline__ u32 mask_window(const u32 (&w)[5], u32 b) {
+    const u32 w2 = R + 2 < 5 ? w[R + 2 < 5 ? R + 2 : 4] : 0u;
+    return b < 32u ? __funnelshift_r(w[R], w[R + 1], b) : __funnelshift_r(w[R + 1], w2, b - 32u);
+}
+
+#define GROUP_WARP_LINES 128u
 #ifndef GROUP_OCC
 #define GROUP_OCC 6
 #endif
 static __global__ void __launch_bounds__(256, GROUP_OCC) k_group(S2PParams p) {
     __shared__ u32 s_cnt[ST_NCOUNTER];
+    __shared__ u8 s_list[8][4][GROUP_WARP_LINES];                    // per warp, per class: offsets (0..127) of the heads inside the warp's chunk
+    __shared__ u32 s_chunk;
     WinState *st = p.st;
     if (threadIdx.x < ST_NCOUNTER) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const u32 n_lines = st->n_lines;
     const u64 ws = st->ws;
-    const u32 lane = threadIdx.x & 31u;
-    const u32 n_round = (n_lines + 31u) & ~31u;                        // whole warps stay in the loop (warp reduction at its end)
-    // CTAs claim chunks of GROUP_CHUNK lines with a ticket: groups cost very different amounts of work (one record / two /
-    // the general walk), and with a static split the kernel's last 10 % were CTAs waiting for their slowest warp
-    __shared__ u32 s_chunk;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    // CTAs claim chunks of GROUP_CHUNK lines with a ticket: groups cost very different amounts of work, and with a static split
+    // the kernel's last 10 % were CTAs waiting for their slowest warp
     while (true) {
       if (threadIdx.x == 0) s_chunk = atomicAdd(&st->tickets[1], 1u);
       __syncthreads();
       const u32 chunk0 = s_chunk * GROUP_CHUNK;
       __syncthreads();
-      if (chunk0 >= n_round) break;
-      const u32 chunk1 = chunk0 + GROUP_CHUNK < n_round ? chunk0 + GROUP_CHUNK : n_round;
-      for (u32 i = chunk0 + threadIdx.x; i < chunk1; i += 256u) {
-      u32 vA = 0, vT = 0, vS = 0;                                      // this line's contribution to its tile's sizes (K4)
-      // bit b of the masks <-> line (i - lane) - 1 + b: this lane's line is bit lane + 1
-      const u32 wbase = i - lane;
-      const u32 q0 = wbase + lane - 1u, q1 = wbase + lane + 31u;      // q0 wraps for the window's first warp: guarded
-      const u32 ma = (wbase + lane >= 1u && q0 < n_lines) ? p.lmeta[q0] : 0u, mb = q1 < n_lines ? p.lmeta[q1] : 0u;
-      const u64 keepm = (u64)__ballot_sync(0xFFFFFFFFu, ma & LM_KEEP) | ((u64)__ballot_sync(0xFFFFFFFFu, mb & LM_KEEP) << 32);
-      const u64 eqm = (u64)__ballot_sync(0xFFFFFFFFu, ma & LM_EQ) | ((u64)__ballot_sync(0xFFFFFFFFu, mb & LM_EQ) << 32);
-      if (i < n_lines) do {                                            // `continue` below leaves this block
-        const u32 bpos = lane + 1u;
-        if (!((keepm >> bpos) & 1ull)) continue;
-        const u32 mi = LM_KEEP | (((eqm >> bpos) & 1ull) ? LM_EQ : 0u);   // K2 wrote nothing else yet
-        u32 first[2] = {i, 0}, r1[2] = {0, 0}, r2[2] = {0, 0};
-        u32 n = 0, n1 = 0, n2 = 0, sam_len = 0, prev = i;
-        // ---- fast path: the previous line is kept (or this is line 0), and so are the group's lines and its terminator
-        bool fast = false;
-        {
-            const bool prev_kept = i == 0 || ((keepm >> (bpos - 1u)) & 1ull);
-            if (prev_kept) {
-                if (i != 0 && (mi & LM_EQ)) continue;                   // same read id as the kept line before it: not a head
-                const u64 after = eqm >> (bpos + 1u);                   // EQ flags of the following lines
-                const u32 cnt = (u32)__ffsll((long long)~after) - 1u;   // consecutive lines with this read id behind the head
-                const u32 gn = cnt + 1u;
-                const u64 need = (1ull << (gn + 1u)) - 1ull;            // the members and the terminating line must all be kept
-                if (gn <= 3u && ((keepm >> bpos) & need) == need) {     // (a terminator past the window's last line is not kept: general path)
-                    fast = true; n = gn; prev = i + gn - 1u;
-                    first[1] = i + 1u;
-                    u32 fl[3];
+      if (chunk0 >= n_lines) break;
+      for (u32 B = chunk0 + wid * GROUP_WARP_LINES; B < chunk0 + GROUP_CHUNK && B < n_lines; B += 8u * GROUP_WARP_LINES) {
+        // ---- masks: bit j <-> line B - 1 + j, j in [0, 160)
+        u32 keepw[5], eqw[5];
 #pragma unroll
-                    for (u32 k = 0; k < 3; ++k) fl[k] = k < gn ? p.rec[i + k].flag : 0u;
-#pragma unroll
-                    for (u32 k = 0; k < 3; ++k) {
-                        if (k < gn) { if (fl[k] & 64u) { if (n1 < 2) r1[n1] = i + k; ++n1; } else if (fl[k] & 128u) { if (n2 < 2) r2[n2] = i + k; ++n2; } }
-                    }
-                    sam_len = p.nl_pos[prev] + 1u - (i ? p.nl_pos[i - 1] + 1u : 0u);   // consecutive lines: one span
+        for (u32 k = 0; k < 5; ++k) {
+            const u32 q = B + 32u * k + lane;                          // line q - 1 (q = 0 only for the window's very first slot)
+            const u32 m = (q >= 1u && q - 1u < n_lines) ? p.lmeta[q - 1u] : 0u;
+            keepw[k] = __ballot_sync(0xFFFFFFFFu, m & LM_KEEP);
+            eqw[k] = __ballot_sync(0xFFFFFFFFu, m & LM_EQ);
+        }
+        // ---- classify this lane's four lines, compact the heads by class (list entry: offset | EQ flag << 7)
+        u32 cnt[4] = {0, 0, 0, 0};
+        auto classify = [&](auto rc) {
+            constexpr u32 r = decltype(rc)::value;
+            const u32 off = lane + 32u * r, i = B + off;               // this line's bit is 32 r + lane + 1
+            const u32 self = mask_window<r>(keepw, lane + 1u), eq_self = mask_window<r>(eqw, lane + 1u);   // KEEP / EQ from this line on
+            u32 cls = 0xFFu;                                            // none
+            if (i < n_lines && (self & 1u)) {
+                const bool prev_kept = i == 0 || ((keepw[r] >> lane) & 1u);
+                if (!prev_kept) cls = 3;                                // general walk decides whether it is a head
+                else if (i != 0 && (eq_self & 1u)) cls = 0xFFu;         // same read id as the kept line before it: not a head
+                else {
+                    const u32 after_eq = mask_window<r>(eqw, lane + 2u);   // EQ of the following lines
+                    const u32 gn = (u32)__ffs((int)~after_eq);          // group size: 1 + consecutive lines with this read id behind the head
+                    const u32 need = (2u << (gn & 31u)) - 1u;           // the members and the terminating line must all be kept
+                    cls = (after_eq != 0xFFFFFFFFu && gn <= 3u && (self & need) == need) ? gn - 1u : 3u;
                 }
             }
+#pragma unroll
+            for (u32 t = 0; t < 4; ++t) {
+                const u32 bal = __ballot_sync(0xFFFFFFFFu, cls == t);
+                if (cls == t) s_list[wid][t][cnt[t] + __popc(bal & lt)] = (u8)(off | ((eq_self & 1u) << 7));
+                cnt[t] += __popc(bal);
+            }
+        };
+        classify(std::integral_constant<u32, 0>{}); classify(std::integral_constant<u32, 1>{});
+        classify(std::integral_constant<u32, 2>{}); classify(std::integral_constant<u32, 3>{});
+        __syncwarp();
+        GroupSums sum; sum.vA = sum.vT = sum.vS = 0;
+        // ---- classes 0..2: groups of gn = 1, 2, 3 consecutive kept lines, resolved 32 at a time
+#pragma unroll 1
+        for (u32 t = 0; t < 3; ++t) {
+            const u32 gn = t + 1u;
+            for (u32 b0 = 0; b0 < cnt[t]; b0 += 32u) {
+                if (b0 + lane >= cnt[t]) continue;
+                const u32 ent = s_list[wid][t][b0 + lane], i = B + (ent & 127u);
+                const u32 mi = LM_KEEP | ((ent & 128u) ? LM_EQ : 0u);
+                u32 first[2] = {i, i + 1u}, r1[2] = {0, 0}, r2[2] = {0, 0}, n1 = 0, n2 = 0;
+                u32 fl[3];
+#pragma unroll
+                for (u32 k = 0; k < 3; ++k) fl[k] = k < gn ? p.rec[i + k].flag : 0u;
+#pragma unroll
+                for (u32 k = 0; k < 3; ++k) {
+                    if (k < gn) { if (fl[k] & 64u) { if (n1 < 2) r1[n1] = i + k; ++n1; } else if (fl[k] & 128u) { if (n2 < 2) r2[n2] = i + k; ++n2; } }
+                }
+                const u32 prev = i + gn - 1u;
+                const u32 sam_len = p.nl_pos[prev] + 1u - (i ? p.nl_pos[i - 1] + 1u : 0u);   // consecutive lines: one span
+                group_finish(p, i, mi, gn, n1, n2, first, r1, r2, sam_len, prev, s_cnt, sum);
+            }
         }
-        if (!fast) {
-            // ---- is this kept line the head of a group?  (pairutil.h:163-173: currId != lastId among kept records)
+        // ---- class 3: the general walk (pairutil.h:163-173: currId != lastId among kept records)
+        for (u32 b0 = 0; b0 < cnt[3]; b0 += 32u) {
+            if (b0 + lane >= cnt[3]) continue;
+            const u32 ent = s_list[wid][3][b0 + lane], i = B + (ent & 127u);
+            const u32 mi = LM_KEEP | ((ent & 128u) ? LM_EQ : 0u);
             bool head;
             {
                 bool chain = line_eq(p, ws, i, mi);
-                long j = (long)i - 1;
-                while (j >= 0) { u32 mj = p.lmeta[j]; if (mj & LM_KEEP) break; chain = chain && line_eq(p, ws, (u32)j, mj); --j; }
-                if (j < 0) head = true;
+                long jj = (long)i - 1;
+                while (jj >= 0) { u32 mj = p.lmeta[jj]; if (mj & LM_KEEP) break; chain = chain && line_eq(p, ws, (u32)jj, mj); --jj; }
+                if (jj < 0) head = true;
                 else if (chain) head = false;
-                else if (j == (long)i - 1) head = true;
-                else head = !qname_equal_slow(p, ws, i, (u32)j);
+                else if (jj == (long)i - 1) head = true;
+                else head = !qname_equal_slow(p, ws, i, (u32)jj);
             }
             if (!head) continue;
-            // ---- collect the group's kept records
+            // collect the group's kept records
+            u32 first[2] = {i, 0}, r1[2] = {0, 0}, r2[2] = {0, 0};
+            u32 n = 0, n1 = 0, n2 = 0, sam_len = 0, prev = i;
             u32 k = i;
             bool chain = true, off_end = false;
             while (true) {
-                // k is a member
-                const LineRec *rk = &p.rec[k];
+                const LineRec *rk = &p.rec[k];                          // k is a member
                 u32 fl = rk->flag;
                 if (n < 2) first[n] = k;
                 ++n;
                 if (fl & 64u) { if (n1 < 2) r1[n1] = k; ++n1; } else if (fl & 128u) { if (n2 < 2) r2[n2] = k; ++n2; }
                 sam_len += line_len_of(p, k) + 1;
                 prev = k;
-                // next kept line
-                u32 q = k + 1; chain = true;
+                u32 q = k + 1; chain = true;                            // next kept line
                 while (q < n_lines) { u32 mq = p.lmeta[q]; chain = chain && line_eq(p, ws, q, mq); if (mq & LM_KEEP) break; ++q; }
                 if (q >= n_lines) { off_end = true; break; }
                 bool same = chain ? true : (q == prev + 1 ? false : qname_equal_slow(p, ws, q, prev));
@@ -1176,41 +1293,17 @@ static __global__ void __launch_bounds__(256, GROUP_OCC) k_group(S2PParams p) {
                 p.lmeta[i] = (u8)(mi | LM_HEAD);
                 continue;
             }
+            group_finish(p, i, mi, n, n1, n2, first, r1, r2, sam_len, prev, s_cnt, sum);
         }
-        // ---- resolve
-        GroupRes g; g.posA = g.posB = 0; g.chrA = g.chrB = 0; g.strands = 0;
-        {
-            const LineRec *rp = &p.rec[prev];
-            g.rid_len = rp->qname_len; g.rid_off = (prev ? p.nl_pos[prev - 1] + 1 : 0) + rp->qname_off;
+        __syncwarp();                                                  // the lists are rewritten by the warp's next chunk
+        // sizes per EMIT_TILE lines for K4 (the warp's 128 lines lie in one 256-line tile): one reduction per warp
+        const u32 vA = __reduce_add_sync(0xFFFFFFFFu, sum.vA), vT = __reduce_add_sync(0xFFFFFFFFu, sum.vT), vS = __reduce_add_sync(0xFFFFFFFFu, sum.vS);
+        if (lane == 0 && vA) {
+            u32 *tt = (u32 *)&p.tile_tot[B / EMIT_TILE];
+            atomicAdd(tt, vA);
+            if (vT) atomicAdd(tt + 1, vT);
+            if (vS) atomicAdd(tt + 2, vS);
         }
-        g.last_line = prev; g.text_len = 0; g.sam_len = sam_len;
-        const Resolved rs = resolve_group(p, n, n1, n2, &p.rec[first[0]], &p.rec[first[1]], &p.rec[r1[0]], &p.rec[r1[1]], &p.rec[r2[0]], &p.rec[r2[1]]);
-        g.status = rs.status;
-        u32 meta = mi | LM_HEAD | LM_PROC;
-        if (rs.have) {
-            g.posA = rs.p1; g.posB = rs.p2; g.strands = rs.strands;
-            const ChrSlot *ca = &p.chr[rs.sA], *cb = &p.chr[rs.sB];
-            g.chrA = (u16)ca->id; g.chrB = (u16)cb->id;
-            if (g.status != ST_SELFCIRCLE) {
-                meta |= LM_EMIT;
-                g.text_len = (u32)g.rid_len + ca->len + cb->len + dec_digits(rs.p1) + dec_digits(rs.p2) + 9u;
-            }
-        }
-        if (!(meta & LM_EMIT)) g.sam_len = 0;
-        if (g.status != ST_NONE) atomicAdd(&s_cnt[g.status], 1u);
-        p.res[i] = g;
-        p.lmeta[i] = (u8)meta;
-        vA = 1u | ((meta & LM_EMIT) ? 1u << 16 : 0u);
-        if (meta & LM_EMIT) { vT = g.text_len; if (p.write_sam) vS = g.sam_len; }
-      } while (0);
-      // sizes per EMIT_TILE lines for K4, which then needs no look-back: one reduction per warp (its 32 lines share a tile)
-      vA = __reduce_add_sync(0xFFFFFFFFu, vA); vT = __reduce_add_sync(0xFFFFFFFFu, vT); vS = __reduce_add_sync(0xFFFFFFFFu, vS);
-      if ((threadIdx.x & 31u) == 0 && vA) {
-          u32 *tt = (u32 *)&p.tile_tot[i / EMIT_TILE];
-          atomicAdd(tt, vA);
-          if (vT) atomicAdd(tt + 1, vT);
-          if (vS) atomicAdd(tt + 2, vS);
-      }
       }
     }
     __syncthreads();

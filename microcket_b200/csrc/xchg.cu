@@ -12,6 +12,7 @@
 // With res = the least common multiple of all binning resolutions (5 Mb for the default list, microcket:98) every
 // duplicate AND every cell of every resolution has exactly one owner, so dedup and all COO counts need no further exchange.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "mk_common.cuh"
 
@@ -112,9 +113,21 @@ __global__ void k_xchg_publish(XchgPeers peers, XchgCtrl *mine, u32 world, u32 r
 }
 
 // wait until every rank has delivered `epoch`, then publish the count
-__global__ void k_xchg_wait(XchgCtrl *mine, u32 world, u32 epoch, unsigned long long *out /* [0] pairs received, [1] overflow */) {
+// (bounded: a peer that died or failed never publishes; after `timeout_ns` the wait gives up and reports which rank is missing
+// instead of hanging the GPU)
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__global__ void k_xchg_wait(XchgCtrl *mine, u32 world, u32 epoch, unsigned long long timeout_ns,
+                            unsigned long long *out /* [0] pairs received, [1] overflow, [2] 1 + first rank that did not deliver */) {
     const u32 tid = threadIdx.x;
-    if (tid < world) { while (ld_acquire_sys_u32(&mine->flag[tid]) != epoch) __nanosleep(200); }
+    if (tid == 0) out[2] = 0;
+    __syncthreads();
+    if (tid < world) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys_u32(&mine->flag[tid]) != epoch) {
+            __nanosleep(200);
+            if (global_ns() - t0 > timeout_ns) { atomicMax(&out[2], (unsigned long long)tid + 1ull); break; }
+        }
+    }
     __syncthreads();
     if (tid == 0) { out[0] = mine->cursor[epoch & 1u]; out[1] = mine->overflow[epoch & 1u]; }
 }
@@ -139,7 +152,7 @@ extern "C" int mk_xchg_create(int device, int world, int rank, size_t cap_pairs,
     x->device = device; x->world = world; x->rank = rank; x->sms = mk_sm_count(device); x->half_cap = cap_pairs;
     int rc = x->recv.alloc(2 * cap_pairs * sizeof(mk_pair));
     if (rc == MK_OK) rc = x->ctrl.alloc(sizeof(XchgCtrl));
-    if (rc == MK_OK) rc = x->out.alloc(16);
+    if (rc == MK_OK) rc = x->out.alloc(32);
     if (rc != MK_OK) { delete x; return rc; }
     if (cudaMemset(x->ctrl.p, 0, sizeof(XchgCtrl)) != cudaSuccess) { delete x; mk_set_error("mk_xchg_create: memset failed"); return MK_ERR_CUDA; }
     memset(&x->peers, 0, sizeof x->peers);
@@ -257,11 +270,14 @@ extern "C" int mk_xchg_finish_device(mk_xchg *x, mk_pair **d_recv, size_t *n_rec
     if (x->epoch == 0) { mk_set_error("mk_xchg_finish_device: no scatter has been enqueued"); return MK_ERR_STATE; }
     MK_CUDA(cudaSetDevice(x->device));
     cudaStream_t s = (cudaStream_t)stream;
-    k_xchg_wait<<<1, XC_MAX_WORLD, 0, s>>>(x->ctrl.as<XchgCtrl>(), (u32)x->world, x->epoch, x->out.as<unsigned long long>());
+    const char *to = getenv("MICROCKET_XCHG_TIMEOUT_S");
+    const unsigned long long timeout_ns = (unsigned long long)(to ? atof(to) : 60.0) * 1000000000ull;
+    k_xchg_wait<<<1, XC_MAX_WORLD, 0, s>>>(x->ctrl.as<XchgCtrl>(), (u32)x->world, x->epoch, timeout_ns, x->out.as<unsigned long long>());
     x->launches += 1;
-    unsigned long long h[2] = {0, 0};
-    MK_CUDA(cudaMemcpyAsync(h, x->out.p, 16, cudaMemcpyDeviceToHost, s));
+    unsigned long long h[3] = {0, 0, 0};
+    MK_CUDA(cudaMemcpyAsync(h, x->out.p, 24, cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
+    if (h[2]) { mk_set_error("mk_xchg_finish_device: rank %llu did not deliver epoch %u within the timeout", h[2] - 1, x->epoch); return MK_ERR_STATE; }
     *d_recv = x->recv.as<mk_pair>() + (size_t)(x->epoch & 1u) * x->half_cap;
     *n_recv = (size_t)std::min<unsigned long long>(h[0], x->half_cap);
     if (h[1] || h[0] > x->half_cap) { mk_set_error("mk_xchg_finish_device: rank %d was sent %llu pairs, capacity %zu", x->rank, h[0], x->half_cap); return MK_ERR_CAPACITY; }

@@ -135,3 +135,17 @@ def test_windows_scattered_while_parsing(oracle):
         c.close()
     for x in xs:
         x.close()
+
+
+def test_missing_peer_times_out_instead_of_hanging(monkeypatch):
+    """A rank that never scatters (crashed peer): the waiting rank gives up after the timeout and reports it."""
+    monkeypatch.setenv("MICROCKET_XCHG_TIMEOUT_S", "1")
+    xs = [mk.Xchg(2, r, 1000) for r in range(2)]
+    mk.Xchg.connect_local(xs)
+    d = to_dev(random_pairs(100, 1))
+    xs[0].scatter(d.data_ptr(), 100, 5000)                 # rank 1 never does
+    with pytest.raises(mk.MkError, match="did not deliver"):
+        xs[0].finish()
+    torch.cuda.synchronize()
+    for x in xs:
+        x.close()
