@@ -747,6 +747,9 @@ static __device__ __forceinline__ u32 parse_line_slow(const S2PParams &p, u64 ws
 #ifndef PR_STAGES
 #define PR_STAGES 1
 #endif
+#ifndef PR_LDG
+#define PR_LDG 0
+#endif
 __device__ __forceinline__ void cp_async16(u32 saddr, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -798,10 +801,21 @@ static __global__ void __launch_bounds__(256, PR_STAGES == 1 ? PR_OCC : 3) k_par
             const u64 a = ws + start;
             if (a + 144 <= limit) {
                 staged = start;
-                const u32 sa = smem_u32(s_rows + ((size_t)b * 256 + tid) * PR_ROW);
                 const char *g = p.buf + (a & ~(u64)15);
+#if PR_LDG
+                // seven independent 128-bit loads, then seven 128-bit shared stores (four wavefronts each with the 144-byte row
+                // stride); cp.async writes every lane's 16 bytes as a wavefront of its own: 28 per instruction (ncu)
+                uint4 w[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) w[j] = __ldg((const uint4 *)g + j);
+                uint4 *row = (uint4 *)(s_rows + ((size_t)b * 256 + tid) * PR_ROW);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) row[j] = w[j];
+#else
+                const u32 sa = smem_u32(s_rows + ((size_t)b * 256 + tid) * PR_ROW);
 #pragma unroll
                 for (int j = 0; j < 7; ++j) cp_async16(sa + 16 * j, g + 16 * j);
+#endif
             }
         }
         s_st[b][tid] = staged;
