@@ -16,6 +16,9 @@
 #include "mk_common.cuh"
 
 #define RS_THREADS 256
+#ifndef RS_BALLOT_MATCH
+#define RS_BALLOT_MATCH 1
+#endif
 #define RS_MAX_PASSES 16
 
 struct RadixPlan {                 // device resident
@@ -176,7 +179,13 @@ static __global__ void __launch_bounds__(RS_THREADS, P::MIN_BLOCKS) k_radix_pass
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const u32 d = dig[j];
+#if RS_BALLOT_MATCH
+        u32 peers = 0xffffffffu;                                         // lanes with the same 8-bit digit, from eight ballots (A/B against match.any)
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) { const bool on = (d >> bit) & 1u; const u32 bl = __ballot_sync(0xffffffffu, on); peers &= on ? bl : ~bl; }
+#else
         const u32 peers = __match_any_sync(0xffffffffu, d);
+#endif
         const int leader = __ffs(peers) - 1;
         u32 old = 0;
         if (lane == leader) { old = wc[d]; wc[d] = old + (u32)__popc(peers); }
