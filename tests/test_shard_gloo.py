@@ -76,3 +76,45 @@ def test_owner_hash_matches_library():
     own = owner_np(p["chr1"], p["chr2"], p["pos1"], 5000, 8)
     for i in range(200):
         assert L.mk_pairs_owner(int(p["chr1"][i]), int(p["chr2"][i]), int(p["pos1"][i]), 5000, 8) == int(own[i])
+
+
+class _FakeXchg:
+    """stands in for mk.Xchg on a box without GPUs: a 128-byte handle that names its rank, and what connect() was given"""
+
+    def __init__(self, rank):
+        self.rank, self.connected = rank, None
+
+    def handle(self):
+        return bytes([self.rank]) * 128
+
+    def connect(self, all_handles):
+        self.connected = all_handles
+
+
+def _bootstrap_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from microcket_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = _FakeXchg(rank)
+    shard.connect_xchg(torch, dist, x, "cpu")
+    q.put((rank, x.connected))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_bootstrap_gathers_every_ranks_handle_in_rank_order():
+    """shard.connect_xchg (the only thing torch.distributed does for the NVLink peer-memory exchange): every rank receives
+    world x 128 bytes, rank r's handle at offset 128 r."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bootstrap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert res[r] == bytes([0]) * 128 + bytes([1]) * 128
