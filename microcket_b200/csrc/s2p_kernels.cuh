@@ -1,13 +1,15 @@
 // s2p_kernels.cuh — sm_100a kernels of the sam2pairs path.
 //
-// One *window* of SAM text (<= 1 GiB, device resident) goes through
-//   k_win_begin   set up the window from the device-side cursor, clear tile descriptors
-//   k_scan_lines  K1: byte-parallel newline index, single pass, decoupled look-back    (replaces getline, pairutil.h:152)
-//   k_parse       K2: one thread per line: first six fields, filter, CIGAR walk         (pairutil.h:63-126,155-161; unc2pairs.h:34-36)
-//   k_group       K3: group heads among kept records + per-group resolution             (pairutil.h:163-173; flash2pairs.h; unc2pairs.h)
-//   k_emit        K4: look-back scan of output sizes, .pairs text + packed records      (unc2pairs.h:310-348)
-//   k_copy_sam    K5: SAM passthrough of the kept lines of emitted groups               (unc2pairs.h:351-356)
-//   k_win_end     advance the cursor to the window's last (unprocessed) read group
+// One *window* of SAM text (<= 2040 MiB, device resident) goes through
+//   k_win_begin    set up the window from the device-side cursor, clear the per-tile sums
+//   k_scan_chunks  K1: byte-parallel newline index, one warp per 16 KiB chunk, no inter-CTA dependency   (replaces getline, pairutil.h:152)
+//   k_chunk_prefix / k_chunk_compact   the chunks' newline lists -> the dense nl_pos[] (k_scan_lines: look-back fallback for windows
+//                  with more than 512 newlines in a chunk; also the FASTQ path's scan)
+//   k_parse        K2: one thread per line: first six fields, filter, CIGAR walk         (pairutil.h:63-126,155-161; unc2pairs.h:34-36)
+//   k_group        K3: group heads among kept records + per-group resolution             (pairutil.h:163-173; flash2pairs.h; unc2pairs.h)
+//   k_emit_prefix / k_emit   K4: prefixes of the per-tile output sizes, .pairs text + packed records + line offsets   (unc2pairs.h:310-348)
+//   k_copy_sam     K5: SAM passthrough of the kept lines of emitted groups               (unc2pairs.h:351-356)
+//   k_win_end      advance the cursor to the window's last (unprocessed) read group
 // All window geometry lives in device memory (WinState), so consecutive windows are
 // enqueued back to back without a host round trip.
 #pragma once
@@ -85,7 +87,7 @@ struct S2PParams {
     GroupRes *res;
     u32 *sam_dst;
     u64 *desc_scan;
-    uint4 *tile_tot, *tile_pre; u32 n_sub_cap;  // per 512 lines: (groups | emitted << 16, text bytes, passthrough bytes) summed by K3; exclusive prefixes (groups, emitted, text, passthrough)
+    uint4 *tile_tot, *tile_pre; u32 n_sub_cap;  // per EMIT_TILE lines: (groups | emitted << 16, text bytes, passthrough bytes) summed by K3; exclusive prefixes (groups, emitted, text, passthrough)
     ChrSlot *chr; u32 chr_mask; int *id_to_slot; u32 chr_cap;
     u64 *sc_list; u32 sc_cap;
     char *out_text; u64 out_text_cap;
@@ -1450,12 +1452,10 @@ static __device__ __noinline__ void fs_write_pair_line_bytes(const char *buf, u6
     put_byte_mode(out++, (strands & 2) ? '-' : '+', or_mode); put_byte_mode(out++, '\n', or_mode);
 }
 
-// Tiles of 512 lines.  K3 has already summed every tile's sizes (tile_tot), k_emit_prefix turns them into exclusive prefixes
+// Tiles of EMIT_TILE (256) lines.  K3 has already summed every tile's sizes (tile_tot), k_emit_prefix turns them into exclusive prefixes
 // (one CTA, a few microseconds), so a tile here depends on no other tile: no look-back, no grid-wide dependency, and the
 // small tiles leave no idle tail (the look-back version needed 2048-line tiles to amortise its chain: 5.1 tiles per CTA
 // per 2 GiB window, i.e. a sixth round that was 90 % idle).
-#define EMIT_NT 1
-#define EMIT_BIG (EMIT_NT * EMIT_TILE)
 
 static __global__ void __launch_bounds__(1024) k_emit_prefix(S2PParams p) {
     __shared__ u32 s_w[4][32];
