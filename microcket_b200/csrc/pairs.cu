@@ -442,34 +442,46 @@ __device__ __forceinline__ u64 take_bits(u64 &lo, u64 &hi, u32 width) {         
     return v;
 }
 
+// (the keys' digit histograms for the radix sort are taken here, while the key is still in registers: one read of the keys less)
 __global__ void __launch_bounds__(256) k_pack_keys(const mk_pair *p, u64 n, const u32 *off_by_id, const u32 *len_by_id, PackCfg c, uint4 *key,
-                                                   unsigned long long *bad) {
+                                                   unsigned long long *bad, RadixSchedule sch, RadixPlan *plan) {
+    extern __shared__ u32 s_hist[];                                      // sch.n_pass * 256
+    for (int i = threadIdx.x; i < sch.n_pass * 256; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const int lane_id = threadIdx.x & 31;
     u32 nbad = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const uint4 r = ((const uint4 *)p)[i];
-        u32 pos1 = r.x, pos2 = r.y; const u32 c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
-        u32 st = r.w & 3u; const u32 lane = r.w >> 16;
+    const u64 n_round = (n + 31) & ~(u64)31;                             // whole warps stay in the loop (ballots in the histogram step)
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (u64)gridDim.x * blockDim.x) {
+        const bool valid = i < n;
         uint4 k = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, (u32)i);
-        bool ok = c1 < c.n_ids && c2 < c.n_ids && lane <= c.max_lane;
-        if (ok) {
-            const u32 q1 = pos1 / c.res, q2 = pos2 / c.res;
-            ok = pos1 <= len_by_id[c1] && pos2 <= len_by_id[c2];
+        if (valid) {
+            const uint4 r = ((const uint4 *)p)[i];
+            u32 pos1 = r.x, pos2 = r.y; const u32 c1 = r.z & 0xFFFFu, c2 = r.z >> 16;
+            u32 st = r.w & 3u; const u32 lane = r.w >> 16;
+            bool ok = c1 < c.n_ids && c2 < c.n_ids && lane <= c.max_lane;
             if (ok) {
-                u32 a = off_by_id[c1] + q1, b = off_by_id[c2] + q2;
-                u32 r1 = pos1 - q1 * c.res, r2 = pos2 - q2 * c.res;
-                u32 sw = 0;
-                if (a > b) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); sw = 1; }
-                u64 lo = 0, hi = 0;
-                put_bits(lo, hi, a, c.nb); put_bits(lo, hi, b, c.nb); put_bits(lo, hi, lane, c.nl);
-                put_bits(lo, hi, r1, c.nr); put_bits(lo, hi, r2, c.nr); put_bits(lo, hi, sw, 1); put_bits(lo, hi, st, 2);
-                k.x = (u32)lo; k.y = (u32)(lo >> 32); k.z = (u32)hi;
+                const u32 q1 = pos1 / c.res, q2 = pos2 / c.res;
+                ok = pos1 <= len_by_id[c1] && pos2 <= len_by_id[c2];
+                if (ok) {
+                    u32 a = off_by_id[c1] + q1, b = off_by_id[c2] + q2;
+                    u32 r1 = pos1 - q1 * c.res, r2 = pos2 - q2 * c.res;
+                    u32 sw = 0;
+                    if (a > b) { u32 t = a; a = b; b = t; t = r1; r1 = r2; r2 = t; st = ((st & 1u) << 1) | (st >> 1); sw = 1; }
+                    u64 lo = 0, hi = 0;
+                    put_bits(lo, hi, a, c.nb); put_bits(lo, hi, b, c.nb); put_bits(lo, hi, lane, c.nl);
+                    put_bits(lo, hi, r1, c.nr); put_bits(lo, hi, r2, c.nr); put_bits(lo, hi, sw, 1); put_bits(lo, hi, st, 2);
+                    k.x = (u32)lo; k.y = (u32)(lo >> 32); k.z = (u32)hi;
+                }
             }
+            nbad += !ok;
+            key[i] = k;
         }
-        nbad += !ok;
-        key[i] = k;
+        radix_hist_add<Rec16>(s_hist, sch, k, valid, lane_id);
     }
     nbad = __reduce_add_sync(0xffffffffu, nbad);
     if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
+    __syncthreads();
+    radix_hist_flush(s_hist, sch.n_pass, plan);
 }
 
 // chromosome (index into dec_off) of a bin: last entry of dec_off that is <= bin.  `hint` is tried first: keys are sorted by
@@ -646,10 +658,11 @@ extern "C" int mk_pairs_dedup_bin_indexed_device(mk_pairs_ws *w, mk_pair *d_pair
     // case of a pass the device found trivial and skipped).
     const bool in_place = (sch.n_pass & 1) != 0;
     uint4 *k0 = in_place ? (uint4 *)d_pairs : w->alt.as<uint4>(), *k1 = in_place ? w->alt.as<uint4>() : (uint4 *)d_pairs;
-    k_pack_keys<<<w->sms * 8, 256, 0, s>>>(d_pairs, n, d_by_id, d_nb_id, pc, k0, cnt + 3);
+    MK_CUDA(cudaMemsetAsync(w->rws.plan.p, 0, sizeof(RadixPlan), s));
+    k_pack_keys<<<w->sms * 8, 256, sch.n_pass * 256 * 4, s>>>(d_pairs, n, d_by_id, d_nb_id, pc, k0, cnt + 3, sch, w->rws.plan.as<RadixPlan>());
     w->launches += 1;
     Rec16::Bufs b; b.k[0] = k0; b.k[1] = k1; b.v[0] = b.v[1] = nullptr;
-    MK_TRY(radix_sort<Rec16>(b, n, sch, w->rws, 0, w->sms, s, &w->launches));
+    MK_TRY(radix_sort<Rec16>(b, n, sch, w->rws, 0, w->sms, s, &w->launches, /*hist_done=*/true));
     const int n_tiles = (int)((n + UQ_T * UQ_ITEMS - 1) / (UQ_T * UQ_ITEMS));
     MK_CUDA(cudaMemsetAsync(w->desc.p, 0, (size_t)(n_tiles + 1) * 8, s));
     const RadixPlan *plan = w->rws.plan.as<RadixPlan>();

@@ -64,6 +64,31 @@ struct Rec16 {
 };
 
 // ---------------------------------------------------------------- histogram of every digit in one read
+// one element's digits into the CTA's shared-memory histograms (n_pass * 256 counters); called by whole warps
+// (`valid` false for lanes past the end).  Fully unrolled over the schedule: byte_of[p] is then a constant-bank operand (no
+// dynamic indexing of the parameter array) and a pass costs ~12 instructions instead of ~75.
+template <class P>
+__device__ __forceinline__ void radix_hist_add(u32 *s_hist, const RadixSchedule &sch, const typename P::Key &k, bool valid, int lane) {
+    const u32 vmask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int p = 0; p < RS_MAX_PASSES; ++p) {
+        if (p >= sch.n_pass) break;
+        const u32 d = valid ? P::digit(k, sch.byte_of[p]) : 0u;
+        // constant digits (high bytes, unused fields) would serialise 32 ways on one counter: one add per warp instead
+        if (vmask == 0xffffffffu) {
+            const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+            if (__all_sync(0xffffffffu, d == d0)) { if (lane == 0) atomicAdd(&s_hist[p * 256 + d], 32u); }
+            else atomicAdd(&s_hist[p * 256 + d], 1u);
+        } else if (valid) atomicAdd(&s_hist[p * 256 + d], 1u);
+    }
+}
+__device__ __forceinline__ void radix_hist_flush(const u32 *s_hist, int n_pass, RadixPlan *plan) {      // after a __syncthreads()
+    for (int i = threadIdx.x; i < n_pass * 256; i += blockDim.x) {
+        u32 v = s_hist[i];
+        if (v) atomicAdd(&plan->hist[i >> 8][i & 255], v);
+    }
+}
+
 template <class P>
 static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(typename P::Bufs bufs, u64 n, RadixSchedule sch, RadixPlan *plan) {
     extern __shared__ u32 s_hist[];                  // n_pass * 256
@@ -71,31 +96,15 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(typename P::Bu
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const u64 stride = (u64)gridDim.x * RS_THREADS;
-    const u64 n_round = (n + 31) & ~(u64)31;         // keep warps converged for match.any
+    const u64 n_round = (n + 31) & ~(u64)31;         // keep warps converged
     for (u64 i = (u64)blockIdx.x * RS_THREADS + threadIdx.x; i < n_round; i += stride) {
         const bool valid = i < n;
         typename P::Key k;
         if (valid) k = P::load_key(bufs, 0, i);
-        const u32 vmask = __ballot_sync(0xffffffffu, valid);
-        // fully unrolled over the schedule: byte_of[p] is then a constant-bank operand (no dynamic indexing of the parameter
-        // array) and a pass costs ~12 instructions instead of ~75
-#pragma unroll
-        for (int p = 0; p < RS_MAX_PASSES; ++p) {
-            if (p >= sch.n_pass) break;
-            const u32 d = valid ? P::digit(k, sch.byte_of[p]) : 0u;
-            // constant digits (high bytes, unused fields) would serialise 32 ways on one counter: one add per warp instead
-            if (vmask == 0xffffffffu) {
-                const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
-                if (__all_sync(0xffffffffu, d == d0)) { if (lane == 0) atomicAdd(&s_hist[p * 256 + d], 32u); }
-                else atomicAdd(&s_hist[p * 256 + d], 1u);
-            } else if (valid) atomicAdd(&s_hist[p * 256 + d], 1u);
-        }
+        radix_hist_add<P>(s_hist, sch, k, valid, lane);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < sch.n_pass * 256; i += RS_THREADS) {
-        u32 v = s_hist[i];
-        if (v) atomicAdd(&plan->hist[i >> 8][i & 255], v);
-    }
+    radix_hist_flush(s_hist, sch.n_pass, plan);
 }
 
 // one CTA: scan histograms, decide which passes run and which buffer each reads
@@ -279,18 +288,22 @@ struct RadixWs {                   // device workspace for sorts of up to max_n 
 };
 
 // Sorts `n` elements.  Input in buffer 0; the result ends in buffer plan->final_buf (device value).
+// hist_done: the digit histograms are already in ws.plan->hist (zeroed, then filled by the kernel that produced the keys)
 template <class P>
 static int radix_sort(typename P::Bufs bufs, u64 n, const RadixSchedule &sch, RadixWs &ws, int iota_vals, int sms,
-                      cudaStream_t s, u64 *launches) {
+                      cudaStream_t s, u64 *launches, bool hist_done = false) {
     if (n >= (1ull << 30)) { mk_set_error("radix_sort: at most 2^30-1 elements per call"); return MK_ERR_CAPACITY; }
     if (n > ws.max_n) { mk_set_error("radix_sort: workspace too small"); return MK_ERR_CAPACITY; }
     RadixPlan *plan = ws.plan.as<RadixPlan>();
-    MK_CUDA(cudaMemsetAsync(plan, 0, sizeof(RadixPlan), s));
-    int grid = (int)std::min<u64>((n + RS_THREADS * 8 - 1) / (RS_THREADS * 8), (u64)sms * 8);
-    if (grid < 1) grid = 1;
-    k_radix_hist<P><<<grid, RS_THREADS, sch.n_pass * 256 * 4, s>>>(bufs, n, sch, plan);
+    if (!hist_done) {
+        MK_CUDA(cudaMemsetAsync(plan, 0, sizeof(RadixPlan), s));
+        int grid = (int)std::min<u64>((n + RS_THREADS * 8 - 1) / (RS_THREADS * 8), (u64)sms * 8);
+        if (grid < 1) grid = 1;
+        k_radix_hist<P><<<grid, RS_THREADS, sch.n_pass * 256 * 4, s>>>(bufs, n, sch, plan);
+        *launches += 1;
+    }
     k_radix_plan<<<1, 256, 0, s>>>(plan, n, sch.n_pass);
-    *launches += 2;
+    *launches += 1;
     const int TILE = RS_THREADS * P::ITEMS;
     const u64 tiles = (n + TILE - 1) / TILE;
     const size_t smem = radix_pass_smem<P>();
