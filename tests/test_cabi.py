@@ -41,3 +41,18 @@ def test_host_generator_is_deterministic_and_sharded():
     assert a == b and a != mk.synth_host(43, "unc", "hg38", 0, 2000)
     fq = mk.synth_host(42, "fastq", "mm10", 0, 100)
     assert fq.count(b"\n") == 800
+
+
+def test_chromosome_ranks_follow_gnu_sort_dictionary_order(tmp_path):
+    """mk_pairs_chrom_ranks (host-only): the rank of a name is its position under `LANG=C sort -d` (only blanks and
+    alphanumerics compare), names that compare equal under -d share a rank — checked against GNU sort itself."""
+    import subprocess
+    names = ["chr1", "chr10", "chr2", "chrX", "chr1_KI270706v1_random", "chrUn_KI270302v1", "chr_1", "chr1.alt", "chrM", "1", "MT",
+             "HLA-A*01:01", "chrEBV", "chr22_KI270731v1_random"]
+    rank = mk.chrom_ranks(names)
+    assert rank[names.index("chr_1")] == rank[names.index("chr1")]              # equal under -d
+    order = sorted(range(len(names)), key=lambda i: (rank[i], names[i]))
+    got = [names[i] for i in order]
+    exp = subprocess.run(["sort", "-d", "-s"], input="\n".join(sorted(names)) + "\n", capture_output=True, text=True,
+                         env={"LANG": "C", "LC_ALL": "C", "PATH": os.environ.get("PATH", "/usr/bin:/bin")}).stdout.split()
+    assert got == exp
