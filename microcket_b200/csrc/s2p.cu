@@ -102,6 +102,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.buf = buf; p.st = c->d_state.as<WinState>(); p.nl_pos = c->d_nl.as<u32>(); p.lmeta = c->d_lmeta.as<u8>();
     p.ck_list = c->d_cklist.as<u32>(); p.ck_cnt = c->d_ckcnt.as<u32>(); p.ck_pre = p.ck_cnt + c->n_chunks_cap; p.ck_bsum = p.ck_pre + c->n_chunks_cap; p.n_chunks_cap = c->n_chunks_cap;
     p.tile_tot = c->d_tiletot.as<uint4>(); p.tile_pre = p.tile_tot + c->n_sub_cap; p.n_sub_cap = c->n_sub_cap;
+    p.seg_tot = p.tile_pre + c->n_sub_cap; p.n_seg_cap = c->n_sub_cap / EMIT_SEG + 2;
     p.rec = c->d_rec.as<LineRec>(); p.res = c->d_res.as<GroupRes>(); p.sam_dst = c->d_samdst.as<u32>();
     p.desc_scan = c->d_desc.as<u64>();
     p.chr = c->d_chr.as<ChrSlot>(); p.chr_mask = c->chr_slots - 1; p.id_to_slot = c->d_id2slot.as<int>(); p.chr_cap = c->chr_cap;
@@ -144,7 +145,7 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     mark(2);
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
     mark(3);
-    k_emit_prefix<<<1, 1024, 0, s>>>(p);
+    k_emit_prefix<<<c->n_sub_cap / EMIT_SEG + 2, EMIT_SEG, 0, s>>>(p);
     k_emit<<<c->grid_emit, EMIT_THREADS, 0, s>>>(p);
     mark(4);
     c->launches += 9;
@@ -253,7 +254,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_samdst.alloc(cfg->write_sam ? (size_t)c->cap_lines * 4 : 16));
     A(c->d_desc.alloc((size_t)c->n_desc * 8)); A(c->d_chr.alloc((size_t)c->chr_slots * sizeof(ChrSlot)));
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
-    A(c->d_tiletot.alloc((size_t)c->n_sub_cap * 2 * sizeof(uint4)));
+    A(c->d_tiletot.alloc(((size_t)c->n_sub_cap * 2 + c->n_sub_cap / EMIT_SEG + 2) * sizeof(uint4)));
     A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4 + 160 * 4));   // counts, prefixes, 160 block sums (W <= 2040 MiB: <= 130 blocks of 1024 chunks)
 #undef A
     if (rc != MK_OK) { delete c; return rc; }

@@ -87,6 +87,7 @@ struct S2PParams {
     GroupRes *res;
     u32 *sam_dst;
     u64 *desc_scan;
+    uint4 *seg_tot; u32 n_seg_cap;              // per EMIT_SEG tiles: (groups, emitted, text bytes, passthrough bytes), also summed by K3
     uint4 *tile_tot, *tile_pre; u32 n_sub_cap;  // per EMIT_TILE lines: (groups | emitted << 16, text bytes, passthrough bytes) summed by K3; exclusive prefixes (groups, emitted, text, passthrough)
     ChrSlot *chr; u32 chr_mask; int *id_to_slot; u32 chr_cap;
     u64 *sc_list; u32 sc_cap;
@@ -105,6 +106,7 @@ struct S2PParams {
 static __global__ void k_win_begin(S2PParams p, u32 n_desc) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p.n_sub_cap) p.tile_tot[i] = make_uint4(0, 0, 0, 0);
+    if (i < p.n_seg_cap) p.seg_tot[i] = make_uint4(0, 0, 0, 0);
     if (i < n_desc) p.desc_scan[i] = 0;                        // look-back descriptors of the fallback scan
     if (i == 0) {
         WinState *s = p.st;
@@ -1271,6 +1273,10 @@ static __global__ void __launch_bounds__(256, GROUP_OCC) k_group(S2PParams p) {
             atomicAdd(tt, vA);
             if (vT) atomicAdd(tt + 1, vT);
             if (vS) atomicAdd(tt + 2, vS);
+            u32 *sg = (u32 *)&p.seg_tot[B / (EMIT_TILE * 128u)];         // EMIT_SEG tiles per segment (k_emit_prefix)
+            atomicAdd(sg, vA & 0xFFFFu); atomicAdd(sg + 1, vA >> 16);
+            if (vT) atomicAdd(sg + 2, vT);
+            if (vS) atomicAdd(sg + 3, vS);
         }
       }
     }
@@ -1457,31 +1463,40 @@ static __device__ __noinline__ void fs_write_pair_line_bytes(const char *buf, u6
 // small tiles leave no idle tail (the look-back version needed 2048-line tiles to amortise its chain: 5.1 tiles per CTA
 // per 2 GiB window, i.e. a sixth round that was 90 % idle).
 
-static __global__ void __launch_bounds__(1024) k_emit_prefix(S2PParams p) {
-    __shared__ u32 s_w[4][32];
+// One CTA per SEGMENT of EMIT_SEG tiles: its base is the sum of the earlier segments' totals (K3 accumulates those too, at
+// most a few hundred values), then one block scan of the segment's own tiles.  (One CTA scanning all 17 800 tiles of a
+// 2040 MiB window took 24 us on the critical path of every window.)
+#define EMIT_SEG 128u
+static __global__ void __launch_bounds__(EMIT_SEG) k_emit_prefix(S2PParams p) {
+    __shared__ u32 s_w[4][EMIT_SEG / 32];
+    __shared__ u32 s_base[4];
     WinState *st = p.st;
     const u32 n_sub = (st->n_lines + EMIT_TILE - 1) / EMIT_TILE;
-    const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const u32 per = (n_sub + 1023u) / 1024u;
-    const u32 lo = tid * per < n_sub ? tid * per : n_sub, hi = lo + per < n_sub ? lo + per : n_sub;
-    const uint4 *__restrict__ tot = p.tile_tot;
-    uint4 *__restrict__ pre = p.tile_pre;
+    const u32 n_seg = (n_sub + EMIT_SEG - 1) / EMIT_SEG;
+    const u32 seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (seg >= n_seg && !(seg == 0 && n_seg == 0)) return;
+    // ---- base: totals of the segments before this one
     u32 G = 0, E = 0, T = 0, S = 0;
-#pragma unroll 4
-    for (u32 i = lo; i < hi; ++i) { const uint4 v = tot[i]; G += v.x & 0xFFFFu; E += v.x >> 16; T += v.y; S += v.z; }
-    const u32 iG = warp_incl_scan(G, (int)lane), iE = warp_incl_scan(E, (int)lane), iT = warp_incl_scan(T, (int)lane), iS = warp_incl_scan(S, (int)lane);
+    for (u32 j = tid; j < seg; j += EMIT_SEG) { const uint4 v = p.seg_tot[j]; G += v.x; E += v.y; T += v.z; S += v.w; }
+    G = __reduce_add_sync(0xFFFFFFFFu, G); E = __reduce_add_sync(0xFFFFFFFFu, E); T = __reduce_add_sync(0xFFFFFFFFu, T); S = __reduce_add_sync(0xFFFFFFFFu, S);
+    if (lane == 0) { s_w[0][wid] = G; s_w[1][wid] = E; s_w[2][wid] = T; s_w[3][wid] = S; }
+    __syncthreads();
+    if (tid < 4) { u32 t = 0; for (u32 w = 0; w < EMIT_SEG / 32; ++w) t += s_w[tid][w]; s_base[tid] = t; }
+    __syncthreads();
+    // ---- this segment's tiles
+    const u32 i = seg * EMIT_SEG + tid;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < n_sub) v = p.tile_tot[i];
+    const u32 vG = v.x & 0xFFFFu, vE = v.x >> 16, vT = v.y, vS = v.z;
+    const u32 iG = warp_incl_scan(vG, (int)lane), iE = warp_incl_scan(vE, (int)lane), iT = warp_incl_scan(vT, (int)lane), iS = warp_incl_scan(vS, (int)lane);
+    __syncthreads();                                                    // s_w is reused
     if (lane == 31) { s_w[0][wid] = iG; s_w[1][wid] = iE; s_w[2][wid] = iT; s_w[3][wid] = iS; }
     __syncthreads();
-    if (wid < 4) { const u32 v = s_w[wid][lane]; const u32 vi = warp_incl_scan(v, (int)lane); s_w[wid][lane] = vi - v; }
-    __syncthreads();
-    u32 bG = s_w[0][wid] + iG - G, bE = s_w[1][wid] + iE - E, bT = s_w[2][wid] + iT - T, bS = s_w[3][wid] + iS - S;
-#pragma unroll 4
-    for (u32 i = lo; i < hi; ++i) {
-        const uint4 v = tot[i];
-        pre[i] = make_uint4(bG, bE, bT, bS);
-        bG += v.x & 0xFFFFu; bE += v.x >> 16; bT += v.y; bS += v.z;
-    }
-    if (tid == 1023) { st->w_groups = bG; st->w_emit = bE; st->w_text = bT; st->w_sam = bS; }
+    u32 bG = s_base[0], bE = s_base[1], bT = s_base[2], bS = s_base[3];
+    for (u32 w = 0; w < wid; ++w) { bG += s_w[0][w]; bE += s_w[1][w]; bT += s_w[2][w]; bS += s_w[3][w]; }
+    if (i < n_sub) p.tile_pre[i] = make_uint4(bG + iG - vG, bE + iE - vE, bT + iT - vT, bS + iS - vS);
+    if (seg + 1 == n_seg && tid == EMIT_SEG - 1) { st->w_groups = bG + iG; st->w_emit = bE + iE; st->w_text = bT + iT; st->w_sam = bS + iS; }
+    if (n_seg == 0 && tid == 0) { st->w_groups = st->w_emit = st->w_text = st->w_sam = 0; }
 }
 
 // the nd (1..10) decimal characters of v as byte stores, without a division chain
