@@ -44,6 +44,10 @@ WORKLOADS = {
     "multires": {"mode": "flash", "genome": "hg38", "names": HG38, "lens": HG38_LEN, "chimeric": -1,
                  "title": "BASELINE configs[4]: hg38 multi-resolution binning (2.5 Mb - 5 kb, cis + trans) of device-resident packed pairs to COO"},
 }
+WORKLOADS["krmdup"] = {"mode": "fastq", "genome": "hg38", "names": HG38, "lens": HG38_LEN, "chimeric": -1,
+                       "title": "BASELINE configs[3] on one box: krmdup over interleaved paired-end FASTQ (2 x 16-base keys, first occurrence "
+                                "wins, 20 % duplicated fragments), one sequencing lane per GPU (`-b`: inter-lane duplicates are retained, "
+                                "microcket:428-451, so lanes are independent and need no collective)"}
 WL = WORKLOADS["flash"]
 RES = 5000
 SEED = 0x4D4B0002
@@ -367,6 +371,138 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
     VERIFY["result"] = {"read_groups": universe, "asserted": True, "against": "CPU oracle and single-GPU path, kept pairs + COO of all ranks gathered"}
 
 
+def run_krmdup(args):
+    """--config krmdup: FASTQ duplicate removal through the host C ABI (mk_dedup_push / pull from pinned host memory; there is no
+    device-resident entry point for FASTQ, so `value` and `e2e` are the same measurement).  One lane per GPU, no collective.
+    --impl reference: the reference's krmdup binary (oracle/_ref/krmdup, its own 4 + 1 threads) on a bounded sample file."""
+    import torch
+    import microcket_b200 as mk
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    P = args.groups if args.groups != 100_000_000 else 20_000_000             # read pairs per GPU (default 20 M = 11.9 GB of FASTQ)
+    metric = "read pairs/sec (krmdup, interleaved FASTQ -> deduplicated FASTQ)"
+    cfg = {"workload": WL["title"], "read_pairs_per_gpu": P, "key": "bases [5,21) of each mate (krmdup.cpp:231-234)", "seed": SEED,
+           "l2": "inputs (>= 10 GB of FASTQ per step) far exceed the 126 MB L2; no flush needed", "parallelism": f"lane{world}: one lane per GPU, no exchange"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ref = os.path.join(ROOT, "oracle", "_ref", "krmdup")
+        S = min(P, 5_000_000)
+        tmpdir = tempfile.mkdtemp(prefix="mkbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            src = os.path.join(tmpdir, "in.fq")
+            with open(src, "wb") as f:
+                for k in range(0, S, 1_000_000):
+                    buf, nb = mk.synth_device(torch, SEED, "fastq", "hg38", k, min(1_000_000, S - k))
+                    f.write(buf[:nb].cpu().numpy().tobytes())
+            times = []
+            kind = "reference" if os.path.exists(ref) else "port"
+            for it in range(min(args.warmup, 1) + args.steps):
+                for e in ("read1.fq", "read2.fq", "log"):
+                    if os.path.exists(os.path.join(tmpdir, "o." + e)):
+                        os.remove(os.path.join(tmpdir, "o." + e))
+                t0 = time.time()
+                if kind == "reference":
+                    subprocess.run([ref, "-i", src, "-o", os.path.join(tmpdir, "o")], check=True, capture_output=True)
+                else:
+                    import oracle_lib
+                    oracle_lib.load().krmdup(open(src, "rb").read())
+                if it >= min(args.warmup, 1):
+                    times.append(time.time() - t0)
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
+        ms = 1e3 * sum(times) / len(times)
+        val = S / (ms / 1e3)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u8", "data": "synthetic", "config": dict(cfg, reference_sample_read_pairs=S),
+                          "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": 5, "kind": kind,
+                                           "sample": f"{S} read pairs per step, file in /dev/shm, files written"},
+                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    mk.lib().require_gpu()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    # this rank's lane: its own fragments (seed differs per lane), staged in pinned host memory
+    parts, nb = [], 0
+    for k in range(0, P, 2_000_000):
+        buf, n = mk.synth_device(torch, SEED + 97 * rank, "fastq", "hg38", k, min(2_000_000, P - k), device=local)
+        parts.append(buf[:n].cpu()); nb += n
+    host = torch.empty(nb, dtype=torch.uint8).pin_memory()
+    o = 0
+    for t in parts:
+        host[o:o + t.numel()] = t; o += t.numel()
+    del parts
+    out1 = torch.empty(nb // 2 + (1 << 20), dtype=torch.uint8).pin_memory(); out2 = torch.empty_like(out1).pin_memory()
+    W = 256 << 20
+    n1, n2 = C.c_size_t(), C.c_size_t()
+
+    def once():
+        kd = mk.Krmdup(device=local, window_bytes=W)
+        L = kd.lib.L
+        a = b = 0
+        off = 0
+        while off < nb or off == 0:
+            m = min(W, nb - off)
+            kd.lib.check(L.mk_dedup_push(kd.h, C.cast(host.data_ptr() + off, C.c_char_p), m, int(off + m == nb)))
+            off += m
+            while True:
+                kd.lib.check(L.mk_dedup_pull(kd.h, out1.data_ptr() + a, out1.numel() - a, C.byref(n1), out2.data_ptr() + b, out2.numel() - b, C.byref(n2)))
+                if n1.value == 0 and n2.value == 0:
+                    break
+                a += n1.value; b += n2.value
+            if off >= nb:
+                break
+        stt = kd.finish()
+        kd.close()
+        return stt, a + b
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(min(args.warmup, 2)):
+        once()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        stt, out_bytes = once()
+    barrier()
+    sec = (time.perf_counter() - t0) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([sec, float(stt.pairs), float(nb), float(out_bytes), float(stt.uniq), float(stt.dup)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        sec = float(tmax[0]); t = tsum
+    if rank == 0:
+        pairs, h2d, d2h = float(t[1]), float(t[2]), float(t[3])
+        peak, peak_src = measured_peak()
+        val = pairs / sec
+        line = {"metric": metric, "value": val, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 2),
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": dict(cfg, fastq_bytes_per_gpu=nb, uniq=float(t[4]), dup=float(t[5])),
+                "roofline": {"bound": "hbm", "kernel": "krmdup path (host-streamed)", "achieved": (h2d + d2h) / sec / 1e9, "peak": peak * world, "unit": "GB/s",
+                             "frac": (h2d + d2h) / sec / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
+                             "note": "B_dd = FASTQ bytes in + FASTQ bytes out (SURVEY 8d); the path is fed over PCIe, so this fraction is a PCIe figure, not a kernel figure"},
+                "cpu_baseline": None,
+                "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "api": "mk_dedup_push / mk_dedup_pull / mk_dedup_finish from pinned host buffers, wall clock incl. all copies, max over ranks"},
+                "gpu_launches": None, "clocks": clk,
+                "parity": "bit-exact against the reference krmdup binary (tests/test_gpu_krmdup.py, tests/test_gpu_cli.py)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 VERIFY = {}
 SAM_ON = False
 
@@ -391,6 +527,8 @@ def main():
     global WL, SAM_ON
     WL = WORKLOADS[args.config]; SAM_ON = args.sam
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.config == "krmdup":
+        return run_krmdup(args)
     if args.impl == "reference":
         return run_reference(args)
 

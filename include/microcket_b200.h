@@ -80,6 +80,16 @@ typedef struct {
     uint16_t lane;           /* stamped into mk_pair.lane */
     int   sharded;           /* 1: this context sees one shard of a larger stream; the selfCircle log value is
                                 settled in mk_s2p_finish_sharded once the global group indices are known */
+    /* SAM-space krmdup: the duplicate removal src/preprocess/krmdup.cpp does on the FASTQ before alignment,
+     * taken on the SAM instead.  A read pair = a run of consecutive lines with one QNAME; its key = bases [hskip, hskip+klen)
+     * of each mate (krmdup.cpp:168-193) read from the SEQ column of the primary records (reverse-complemented back when
+     * flag & 16; a stitched read stands for mate 1, its reverse complement for mate 2).  First occurrence in file order
+     * wins over the whole stream (krmdup.cpp:201-212); later ones, short mates and non-ACGT key bases are removed BEFORE
+     * grouping, so text / log / packed pairs are those of sam2pairs on the alignment of krmdup's output.  The fields must
+     * be tab separated (SAM spec).  mk_s2p_rmdup_stats gives krmdup's log. */
+    int   rmdup;
+    uint64_t rmdup_capacity; /* read pairs the key table is sized for (the whole stream); 0 = 16 M.  16 bytes x 2 slots per pair */
+    int   hskip1, klen1, hskip2, klen2;   /* krmdup -k -s -K -S; defaults 5,16,5,16 */
 } mk_s2p_cfg;
 
 typedef struct {
@@ -108,6 +118,9 @@ int  mk_s2p_finish(mk_ctx *, mk_s2p_stats *);
 /* Sharded finish: this context processed groups [group_base, group_base + stats.groups) of a stream of
  * total_groups processed groups (multi-GPU: bases from an all-gather of per-rank group counts). */
 int  mk_s2p_finish_sharded(mk_ctx *, uint64_t group_base, uint64_t total_groups, mk_s2p_stats *);
+struct mk_dedup_stats_s;
+/* cfg.rmdup: Total / Uniq / Dup / Discard of krmdup's log (krmdup.cpp:383-389) for the stream; after mk_s2p_finish */
+int  mk_s2p_rmdup_stats(mk_ctx *, struct mk_dedup_stats_s *);
 /* Start over on a new input with the same configuration, allocations and chromosome table. */
 int  mk_s2p_reset(mk_ctx *);
 /* Chromosome table after (or during) a run: id → name. */
@@ -139,9 +152,8 @@ int  mk_s2p_attach_xchg(mk_ctx *, struct mk_xchg *, uint32_t res);
 /* number of kernel launches issued by this context so far (for bench accounting) */
 uint64_t mk_launch_count(mk_ctx *);
 /* Optional per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figure).
- * ms[k] / count[k]; arrays of 8.  k = 6 single-pass tile kernel (scan + parse + group + emit of one 128 KiB tile), 7 its
- * tile prefix + gather; the multi-kernel path (MICROCKET_FUSED=0, or a window the tile path gives up): k = 0 newline
- * scan, 1 parse, 2 group, 3 emit, 4 SAM passthrough, 5 scan index (chunk prefix + compaction). */
+ * ms[k] / count[k]; arrays of 8.  k = 0 newline scan, 1 parse, 2 group, 3 emit, 4 SAM passthrough, 5 scan index (chunk
+ * prefix + compaction), 6 the two SAM-space krmdup kernels (cfg.rmdup), 7 unused. */
 int  mk_s2p_enable_timing(mk_ctx *, int on);
 int  mk_s2p_kernel_times(mk_ctx *, double *ms, uint64_t *count);
 
@@ -151,7 +163,7 @@ typedef struct {
     int device;
     size_t window_bytes;               /* bytes of FASTQ per device window; 0 = default */
 } mk_dedup_cfg;
-typedef struct { uint32_t uniq, dup, discard; uint64_t pairs; } mk_dedup_stats;   /* krmdup.cpp:383-389 */
+typedef struct mk_dedup_stats_s { uint32_t uniq, dup, discard; uint64_t pairs; } mk_dedup_stats;   /* krmdup.cpp:383-389 */
 
 void mk_dedup_default_cfg(mk_dedup_cfg *);
 int  mk_dedup_create(const mk_dedup_cfg *, mk_ctx **);

@@ -25,7 +25,8 @@ class MkError(RuntimeError):
 class S2PCfg(C.Structure):
     _fields_ = [("mode", C.c_int), ("min_mapped_ratio", C.c_float), ("min_mapq", C.c_int), ("write_sam", C.c_int),
                 ("emu_threads", C.c_int), ("device", C.c_int), ("emit_text", C.c_int), ("emit_packed", C.c_int),
-                ("window_bytes", C.c_size_t), ("lane", C.c_uint16), ("sharded", C.c_int)]
+                ("window_bytes", C.c_size_t), ("lane", C.c_uint16), ("sharded", C.c_int),
+                ("rmdup", C.c_int), ("rmdup_capacity", C.c_uint64), ("hskip1", C.c_int), ("klen1", C.c_int), ("hskip2", C.c_int), ("klen2", C.c_int)]
 
 
 class S2PStats(C.Structure):
@@ -103,6 +104,7 @@ class Lib:
         L.mk_s2p_pull_packed.argtypes = [vp, vp, sz, P(sz)]
         L.mk_s2p_finish.argtypes = [vp, P(S2PStats)]
         L.mk_s2p_finish_sharded.argtypes = [vp, u64, u64, P(S2PStats)]
+        L.mk_s2p_rmdup_stats.argtypes = [vp, P(DedupStats)]
         L.mk_s2p_reset.argtypes = [vp]
         L.mk_s2p_chrom_count.argtypes = [vp]
         L.mk_s2p_chrom_name.argtypes = [vp, i, C.c_char_p, sz]
@@ -185,7 +187,7 @@ def lib():
 
 class S2PConfig:
     def __init__(self, mode="unc", ratio=0.5, min_mapq=10, write_sam=False, threads=8, device=0, emit_text=True,
-                 emit_packed=False, window_bytes=0, lane=0, sharded=False):
+                 emit_packed=False, window_bytes=0, lane=0, sharded=False, rmdup=False, rmdup_capacity=0, key=(5, 16, 5, 16)):
         self.c = S2PCfg()
         lib().L.mk_s2p_default_cfg(C.byref(self.c))
         self.c.mode = {"flash": 0, "unc": 1}[mode]
@@ -199,6 +201,10 @@ class S2PConfig:
         self.c.window_bytes = window_bytes
         self.c.lane = lane
         self.c.sharded = int(sharded)
+        # SAM-space krmdup (src/preprocess/krmdup.cpp taken on the SAM): key = (hskip1, klen1, hskip2, klen2)
+        self.c.rmdup = int(rmdup)
+        self.c.rmdup_capacity = rmdup_capacity
+        self.c.hskip1, self.c.klen1, self.c.hskip2, self.c.klen2 = key
 
 
 class Sam2Pairs:
@@ -294,6 +300,12 @@ class Sam2Pairs:
     def launches(self):
         return self.lib.L.mk_launch_count(self.h)
 
+    def rmdup_stats(self) -> "DedupStats":
+        """krmdup's log of the SAM-space duplicate removal (cfg.rmdup); call after finish()"""
+        st = DedupStats()
+        self.lib.check(self.lib.L.mk_s2p_rmdup_stats(self.h, C.byref(st)))
+        return st
+
     def attach_xchg(self, xchg, res):
         """every window's packed pairs leave for their owners on a side stream while the next window is parsed"""
         self.lib.check(self.lib.L.mk_s2p_attach_xchg(self.h, xchg.h if xchg is not None else None, res))
@@ -306,7 +318,7 @@ class Sam2Pairs:
         ms = (C.c_double * 8)()
         cnt = (C.c_uint64 * 8)()
         self.lib.check(self.lib.L.mk_s2p_kernel_times(self.h, ms, cnt))
-        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index"))}
+        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index", "k_rmdup")) if cnt[k] or k < 6}
 
     def push_ptr(self, ptr, n, is_last=False):
         """push() from a raw host pointer (e.g. a pinned torch tensor): no Python-side copy."""

@@ -42,6 +42,7 @@ struct S2PCtx : mk_ctx {
     DevBuf d_params;                               // device copies of the kernels' parameter blocks (S2PParams.self)
     u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
+    DevBuf d_rmtab[2], d_rmkey, d_rmstat; u64 rm_slots[2] = {0, 0};    // SAM-space krmdup (cfg.rmdup)
     S2PSlot slot[2];
     int grid_scan4 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0;
     u64 launches = 0, fallback_windows = 0;
@@ -93,6 +94,7 @@ extern "C" void mk_s2p_default_cfg(mk_s2p_cfg *c) {
     memset(c, 0, sizeof *c);
     c->mode = 1; c->min_mapped_ratio = 0.5f; c->min_mapq = 10; c->write_sam = 1; c->emu_threads = 4;   // sam2pairs.cpp:33, pairutil.h:50-53
     c->device = 0; c->emit_text = 1; c->emit_packed = 0; c->window_bytes = 0; c->lane = 0;
+    c->rmdup = 0; c->rmdup_capacity = 0; c->hskip1 = 5; c->klen1 = 16; c->hskip2 = 5; c->klen2 = 16;                  // krmdup.cpp:231-234
 }
 
 static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_cap, char *out_text, u64 text_cap, mk_pair *out_pairs, u64 pairs_cap,
@@ -116,6 +118,12 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     p.write_sam = c->cfg.write_sam && out_sam; p.emit_text = c->cfg.emit_text && out_text; p.emit_packed = c->cfg.emit_packed && out_pairs;
     p.running_offsets = running;
     p.xparts = (c->xchg && c->d_xparts.p) ? c->d_xparts.as<unsigned long long>() : nullptr;
+    p.rm_on = c->cfg.rmdup ? 1 : 0;
+    if (p.rm_on) {
+        p.rm_hskip1 = c->cfg.hskip1; p.rm_klen1 = c->cfg.klen1; p.rm_hskip2 = c->cfg.hskip2; p.rm_klen2 = c->cfg.klen2;
+        for (int t = 0; t < 2; ++t) { p.rm_tab[t] = c->d_rmtab[t].as<unsigned long long>(); p.rm_mask[t] = c->rm_slots[t] - 1; }
+        p.rm_key = c->d_rmkey.as<unsigned long long>(); p.rm_stat = c->d_rmstat.as<u8>();
+    }
     p.self = nullptr;
     return p;
 }
@@ -142,6 +150,12 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 1);
     mark(1);
     k_parse<<<c->grid_parse, 256, PR_SMEM, s>>>(p);
+    if (p.rm_on) {                                       // SAM-space krmdup: duplicate / discarded read pairs lose LM_KEEP before grouping
+        mark(7);
+        k_rm_insert<<<c->grid_gs, 256, 0, s>>>(p);
+        k_rm_mark<<<c->grid_gs, 256, 0, s>>>(p);
+        c->launches += 2;
+    }
     mark(2);
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
     mark(3);
@@ -204,7 +218,7 @@ extern "C" int mk_s2p_kernel_times(mk_ctx *x, double *ms, uint64_t *count) {
     timing_collect(c);
     for (int k = 0; k < 5; ++k) { ms[k] = c->k_ms[k]; count[k] = c->k_cnt[k]; }
     ms[5] = c->k_ms[6]; count[5] = c->k_cnt[6];
-    ms[6] = ms[7] = 0; count[6] = count[7] = 0;
+    ms[6] = c->k_ms[7]; count[6] = c->k_cnt[7]; ms[7] = 0; count[7] = 0;
     return MK_OK;
 }
 
@@ -229,6 +243,10 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     if (!cfg || !out) { mk_set_error("mk_s2p_create: null argument"); return MK_ERR_ARG; }
     if (cfg->mode != 0 && cfg->mode != 1) { mk_set_error("mk_s2p_create: mode must be 0 (flash) or 1 (unc)"); return MK_ERR_ARG; }
     if (cfg->emu_threads < 2) { mk_set_error("mk_s2p_create: at least 2 threads are required"); return MK_ERR_ARG; }   // sam2pairs.cpp:36-39
+    if (cfg->rmdup && (cfg->hskip1 < 0 || cfg->hskip2 < 0 || cfg->klen1 < 0 || cfg->klen2 < 0 || cfg->klen1 + cfg->klen2 < 16 || cfg->klen1 + cfg->klen2 > 32)) {
+        mk_set_error("mk_s2p_create: rmdup key size must be 16..32 bases");       // krmdup.cpp:256-262
+        return MK_ERR_ARG;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { mk_set_error("no CUDA device: microcket_b200 has no CPU fallback"); return MK_ERR_CUDA; }
     MK_CUDA(cudaSetDevice(cfg->device));
@@ -256,6 +274,14 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     A(c->d_id2slot.alloc((size_t)c->chr_cap * 4));
     A(c->d_tiletot.alloc(((size_t)c->n_sub_cap * 2 + c->n_sub_cap / EMIT_SEG + 2) * sizeof(uint4)));
     A(c->d_cklist.alloc((size_t)c->n_chunks_cap * SC_CAP * 4)); A(c->d_ckcnt.alloc((size_t)c->n_chunks_cap * 2 * 4 + 160 * 4));   // counts, prefixes, 160 block sums (W <= 2040 MiB: <= 130 blocks of 1024 chunks)
+    if (cfg->rmdup) {
+        // two slots per expected read pair, {key, first line} = 16 bytes per slot; the lower-case identity space is rare
+        const u64 cap = cfg->rmdup_capacity ? cfg->rmdup_capacity : (u64)1 << 24;
+        u64 slots = 1024; while (slots < 2 * cap) slots <<= 1;
+        c->rm_slots[0] = slots; c->rm_slots[1] = std::max<u64>(slots >> 4, 1024);
+        for (int t = 0; t < 2; ++t) { A(c->d_rmtab[t].alloc(c->rm_slots[t] * 16)); if (rc == MK_OK && cudaMemset(c->d_rmtab[t].p, 0xFF, c->rm_slots[t] * 16) != cudaSuccess) rc = MK_ERR_CUDA; }
+        A(c->d_rmkey.alloc((size_t)c->cap_lines * 8)); A(c->d_rmstat.alloc(c->cap_lines));
+    }
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
     cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);
@@ -280,7 +306,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
         u64 n8 = 0; for (u32 b = 0; b < l && b < 8; ++b) n8 |= (u64)(unsigned char)names[i][b] << (8 * b);
         tab[s].name8 = n8; tab[s].id = reg; id2slot[reg] = (int)s; ++reg;
     }
-    WinState st; memset(&st, 0, sizeof st); st.n_chrom = (u32)reg;
+    WinState st; memset(&st, 0, sizeof st); st.n_chrom = (u32)reg; st.rm_allones[0] = st.rm_allones[1] = ~0ull;
     cudaMemcpy(c->d_chr.p, tab.data(), tab.size() * sizeof(ChrSlot), cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_id2slot.p, id2slot.data(), id2slot.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice);
@@ -316,6 +342,7 @@ static int s2p_err_check(u32 err) {
     else if (err & S2P_ERR_SCLIST) mk_set_error("sam2pairs: self-circle list overflow");
     else if (err & S2P_ERR_NOPROGRESS) mk_set_error("sam2pairs: a single read group (or line) is larger than the window/carry capacity");
     else if (err & S2P_ERR_CHRTABLE) mk_set_error("sam2pairs: chromosome table full");
+    else if (err & S2P_ERR_RMTABLE) mk_set_error("sam2pairs: rmdup key table full; raise cfg.rmdup_capacity (read pairs in the stream)");
     return MK_ERR_CAPACITY;
 }
 
@@ -629,6 +656,19 @@ extern "C" int mk_s2p_finish_sharded(mk_ctx *x, uint64_t group_base, uint64_t to
     return s2p_fill_stats(c, group_base, total_groups, out);
 }
 
+// krmdup's log of the SAM-space duplicate removal (krmdup.cpp:383-389); valid after mk_s2p_finish
+extern "C" int mk_s2p_rmdup_stats(mk_ctx *x, mk_dedup_stats *out) {
+    S2PCtx *c; MK_TRY(s2p_check(x, &c));
+    if (!out) { mk_set_error("mk_s2p_rmdup_stats: null stats"); return MK_ERR_ARG; }
+    if (!c->cfg.rmdup) { mk_set_error("mk_s2p_rmdup_stats: context created without cfg.rmdup"); return MK_ERR_STATE; }
+    MK_CUDA(cudaStreamSynchronize(c->s_comp));
+    WinState st;
+    MK_CUDA(cudaMemcpy(&st, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost));
+    out->uniq = (u32)st.rm_uniq; out->discard = (u32)st.rm_discard; out->dup = (u32)(st.rm_total - st.rm_uniq - st.rm_discard);
+    out->pairs = st.rm_total;
+    return MK_OK;
+}
+
 // Forget the stream (counters, carried group, pending output) but keep every allocation and the chromosome table:
 // the context can then process another input from the start.
 extern "C" int mk_s2p_reset(mk_ctx *x) {
@@ -637,8 +677,9 @@ extern "C" int mk_s2p_reset(mk_ctx *x) {
     WinState st;
     MK_CUDA(cudaMemcpy(&st, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost));
     u32 n_chrom = st.n_chrom;
-    memset(&st, 0, sizeof st); st.n_chrom = n_chrom;
+    memset(&st, 0, sizeof st); st.n_chrom = n_chrom; st.rm_allones[0] = st.rm_allones[1] = ~0ull;
     MK_CUDA(cudaMemcpy(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice));
+    for (int t = 0; t < 2; ++t) if (c->d_rmtab[t].p) MK_CUDA(cudaMemset(c->d_rmtab[t].p, 0xFF, c->rm_slots[t] * 16));
     for (auto &s : c->slot) { s.busy = false; s.free_pending = false; s.text_len = s.text_off = s.pairs_n = s.pairs_off = s.sam_len = s.sam_off = 0; }
     c->tail.clear(); c->windows = 0; c->prev_slot = -1; c->finished_input = false; c->use_device_path = false;
     c->q_text.clear(); c->q_sam.clear(); c->q_pairs.clear(); c->q_text_off = c->q_sam_off = c->q_pairs_off = 0;

@@ -66,6 +66,10 @@ struct WinState {
     unsigned long long counters[ST_NCOUNTER];
     u32 sc_count, n_chrom;
     u32 tickets[4];                  // dynamic tile tickets of look-back kernels, reset per window
+    // SAM-space krmdup (cfg.rmdup): QNAME runs counted so far end before this global line index; log counters; first
+    // occurrence (global line index) of the all-ones key, which is the tables' empty marker
+    u64 rm_counted;
+    unsigned long long rm_total, rm_uniq, rm_discard, rm_allones[2];
 };
 
 #define S2P_ERR_LINES 1u
@@ -75,6 +79,7 @@ struct WinState {
 #define S2P_ERR_SCLIST 16u
 #define S2P_ERR_NOPROGRESS 32u
 #define S2P_ERR_CHRTABLE 64u
+#define S2P_ERR_RMTABLE 128u
 
 struct S2PParams {
     const char *buf;          // SAM text base (16-byte aligned)
@@ -98,6 +103,11 @@ struct S2PParams {
     u64 window_bytes; u32 cap_lines;
     int mode, min_mapq, write_sam, emit_text, emit_packed; float ratio; u16 lane;
     int running_offsets;      // 1: append at st->out_* (device-resident runs); 0: every window writes at 0
+    // SAM-space krmdup: key tables ({key, first global line index} per slot; [1] = the T bucket's lower-case identity space),
+    // per-line key / status of the window's QNAME runs
+    int rm_on, rm_hskip1, rm_klen1, rm_hskip2, rm_klen2;
+    unsigned long long *rm_tab[2]; u64 rm_mask[2];
+    unsigned long long *rm_key; u8 *rm_stat;
     unsigned long long *xparts;   // optional: per launched window (end, count) of its packed pairs, for the overlapped multi-GPU scatter
     const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
 };
@@ -127,17 +137,23 @@ static __global__ void k_win_end(S2PParams p, u32 xslot) {
     u32 n = s->n_lines;
     u64 next;
     const bool carried = s->carry_line != 0xFFFFFFFFu;
-    if (carried) {
-        u32 c = s->carry_line;
-        next = ws + (c ? (u64)p.nl_pos[c - 1] + 1 : 0);
-    } else {
-        next = ws + (n ? (u64)p.nl_pos[n - 1] + 1 : 0);       // no kept record: everything up to the last complete line is consumed
-    }
-    bool final_win = (we == s->total) && s->is_last;
+    const bool final_win = (we == s->total) && s->is_last;
+    u32 cut = carried ? s->carry_line : n;                    // first line that is not consumed (no kept record: every complete line is)
+    if (p.rm_on && !final_win && n) {
+        // SAM-space krmdup works on whole QNAME runs (dropped lines included): the next window starts at a run's first line,
+        // and the window's last run (possibly cut by the window end) is always seen again
+        if (!carried) cut = n - 1;
+        while (cut > 0 && (p.lmeta[cut] & LM_EQ)) --cut;
+        u32 hl = n - 1;
+        while (hl > 0 && (p.lmeta[hl] & LM_EQ)) --hl;
+        s->rm_counted = s->lines_done + hl;
+    } else if (p.rm_on) s->rm_counted = s->lines_done + n;
+    if (carried || cut != n) s->carry_line = cut;
+    next = ws + (cut ? (u64)p.nl_pos[cut - 1] + 1 : 0);
     if (final_win) next = s->total;                        // the stream's last group is never processed (pairutil.h:176)
     else if (next == ws && we > ws && we - ws >= p.window_bytes) s->err |= S2P_ERR_NOPROGRESS;  // one group (or line) fills the window
     s->cursor = next;
-    s->lines_done += (carried && !final_win) ? s->carry_line : n;
+    s->lines_done += final_win ? n : cut;
     s->groups_done += s->w_groups;
     s->out_text += s->w_text; s->out_pairs += s->w_emit; s->out_sam += s->w_sam;
     if (p.out_line_off && s->out_pairs < p.out_line_off_cap) p.out_line_off[s->out_pairs] = p.line_off_base + s->out_text;   // end of the last line so far
@@ -945,6 +961,171 @@ static __device__ __noinline__ bool qname_equal_abs(const S2PParams &p, u64 pa, 
         if (tx != ty) return false;
         const u64 m = t ? ((1ull << (8 * t)) - 1) : 0;
         return (x & m) == (y & m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ SAM-space krmdup
+// The reference removes PCR duplicates from the FASTQ BEFORE alignment (src/preprocess/krmdup.cpp): key = bases
+// [hskip, hskip + klen) of each mate, 2 bits per base (:168-193); the first pair with a key in file order is kept, later ones
+// and pairs with a short mate or a non-ACGT base in a key window are dropped (:103-111,159-198,201-212); the pairs whose first
+// key base is not exactly 'A' / 'C' / 'G' share the fourth set (:134-141).  The aligner keeps the read order and SEQ holds the
+// read's bases (reverse-complemented when flag & 16), so the same decision can be taken on the SAM: a QNAME run (consecutive
+// lines with equal QNAME, dropped ones included) is one read pair, its PRIMARY records (flag & 0x900 == 0) carry the full
+// reads.  flag & 64 -> mate 1, flag & 128 -> mate 2, neither (a stitched read) -> mate 1 = the read, mate 2 = its reverse
+// complement.  Runs the reference would not have let through lose LM_KEEP before K3 sees them, so everything downstream
+// (grouping, counters, the 2^18-batch self-circle rule, the dropped last group) is what sam2pairs does on the SAM of the
+// deduplicated FASTQ.  A run without a primary record for a mate counts as discarded.
+#define RM_NOTHEAD 0u
+#define RM_SKIP 1u          // header line
+#define RM_INCOMPLETE 2u    // the run touches the window end: decided in the next window
+#define RM_DISCARD 3u
+#define RM_VALID 4u         // | tag (0 / 1)
+#define RM_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ u64 rm_tabmask(u64 w) {                      // bit 7 of every byte that is '\t' (exact)
+    const u64 x = w ^ 0x0909090909090909ull;
+    return ~(((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x) & 0x8080808080808080ull;
+}
+// first '\t' in [from, end) or end; aligned 8-byte loads (the buffer is 16-byte aligned and padded)
+__device__ __forceinline__ u64 rm_next_tab(const char *buf, u64 from, u64 end) {
+    u64 pos = from & ~7ull;
+    u64 m = rm_tabmask(__ldg((const unsigned long long *)(buf + pos))) & (~0ull << (8 * (from - pos)));
+    while (true) {
+        if (m) { const u64 t = pos + ((u32)(__ffsll((long long)m) - 1) >> 3); return t < end ? t : end; }
+        pos += 8;
+        if (pos >= end) return end;
+        m = rm_tabmask(__ldg((const unsigned long long *)(buf + pos)));
+    }
+}
+__device__ __forceinline__ int rm_comp(int c) {
+    switch (c) {
+    case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+    case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+    default: return c;
+    }
+}
+// bases [hskip, hskip + klen) of the mate that is SEQ (rev = false) or its reverse complement; false = discard
+__device__ __forceinline__ bool rm_half(const char *buf, u64 seq, u32 L, bool rev, int hskip, int klen, u64 &bits, int &first) {
+    bits = 0; first = 'N';
+    if (L < (u32)(hskip + klen)) return false;
+    bool ok = true;
+    for (int k = 0; k < klen; ++k) {
+        int c = (int)(unsigned char)(rev ? buf[seq + L - 1 - (u32)(hskip + k)] : buf[seq + (u32)(hskip + k)]);
+        if (rev) c = rm_comp(c);
+        if (k == 0) first = c;
+        const int cu = c & 0xDF;
+        const u32 code = cu == 'A' ? 1u : cu == 'T' ? 2u : cu == 'C' ? 0u : cu == 'G' ? 3u : 4u;
+        ok = ok && code < 4u;
+        bits = (bits << 2) | (code & 3u);
+    }
+    return ok;
+}
+__device__ __forceinline__ u64 rm_hash(u64 k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+// slot of `key` (inserted when absent); ~0 when the table is full
+__device__ __forceinline__ u64 rm_slot(unsigned long long *tab, u64 mask, u64 key, bool insert) {
+    u64 s = rm_hash(key) & mask;
+    for (u64 probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
+        unsigned long long cur = *(volatile unsigned long long *)&tab[2 * s];
+        if (cur == RM_EMPTY) {
+            if (!insert) return ~0ull;
+            cur = atomicCAS(&tab[2 * s], RM_EMPTY, (unsigned long long)key);
+            if (cur == RM_EMPTY) return s;
+        }
+        if (cur == key) return s;
+    }
+    return ~0ull;
+}
+
+// phase 1: one thread per line; the thread of a run's first line builds the pair's key and records its first occurrence
+static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
+    WinState *st = p.st;
+    const u32 n = st->n_lines;
+    const u64 ws = st->ws, g0 = st->lines_done;
+    const bool final_win = (st->we == st->total) && st->is_last;
+    for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        u32 stat = RM_NOTHEAD;
+        if (!(p.lmeta[i] & LM_EQ)) {
+            u64 a = ws + (i ? (u64)p.nl_pos[i - 1] + 1 : 0);
+            if (p.buf[a] == '@') stat = RM_SKIP;
+            else {
+                bool have1 = false, have2 = false, ok1 = false, ok2 = false;
+                u64 b1 = 0, b2 = 0; int first = 'N';
+                u32 j = i;
+                while (true) {
+                    const u64 e = ws + p.nl_pos[j];
+                    // FLAG = field 2, SEQ = field 10 (tab separated)
+                    const u64 t1 = rm_next_tab(p.buf, a, e);
+                    u64 t = t1 < e ? rm_next_tab(p.buf, t1 + 1, e) : e;
+                    u32 flag = 0;
+                    for (u64 q = t1 + 1; q < t; ++q) flag = flag * 10u + (u32)((unsigned char)p.buf[q] - '0');
+                    if (!(flag & 0x900u)) {
+                        const bool m1 = (flag & 64u) || !(flag & 192u), m2 = !(flag & 64u);   // 128 only -> mate 2; neither -> both
+                        if ((m1 && !have1) || (m2 && !have2)) {
+                            for (int k = 2; k < 9 && t < e; ++k) t = rm_next_tab(p.buf, t + 1, e);
+                            u64 seq = e; u32 L = 0;
+                            if (t < e) { seq = t + 1; L = (u32)(rm_next_tab(p.buf, seq, e) - seq); }
+                            const bool rev = (flag & 16u) != 0;
+                            if (m1 && !have1) { have1 = true; ok1 = rm_half(p.buf, seq, L, rev, p.rm_hskip1, p.rm_klen1, b1, first); }
+                            if (m2 && !have2) { int f2; have2 = true; ok2 = rm_half(p.buf, seq, L, (flag & 192u) ? rev : !rev, p.rm_hskip2, p.rm_klen2, b2, f2); }
+                        }
+                    }
+                    ++j;
+                    if (j >= n || !(p.lmeta[j] & LM_EQ)) break;
+                    a = e + 1;
+                }
+                if (j >= n && !final_win) stat = RM_INCOMPLETE;
+                else if (ok1 && ok2) {
+                    const u64 key = (b1 << (2 * p.rm_klen2)) | b2;
+                    const u32 tag = (first == 'a' || first == 'c' || first == 'g') ? 1u : 0u;   // T bucket, not 'T' / 't' (krmdup.cpp:134-141)
+                    stat = RM_VALID | tag;
+                    p.rm_key[i] = key;
+                    if (key == RM_EMPTY) atomicMin(&st->rm_allones[tag], (unsigned long long)(g0 + i));
+                    else {
+                        const u64 sl = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, true);
+                        if (sl == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); stat = RM_INCOMPLETE; }
+                        else atomicMin(&p.rm_tab[tag][2 * sl + 1], (unsigned long long)(g0 + i));
+                    }
+                } else stat = RM_DISCARD;
+            }
+        }
+        p.rm_stat[i] = (u8)stat;
+    }
+}
+
+// phase 2 (after every insert of the window): a run survives iff it is the first occurrence of its key; the others lose LM_KEEP
+static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
+    WinState *st = p.st;
+    const u32 n = st->n_lines;
+    const u64 g0 = st->lines_done, counted = st->rm_counted;
+    u32 c_tot = 0, c_uniq = 0, c_disc = 0;
+    for (u32 i0 = blockIdx.x * 256u; i0 < n; i0 += gridDim.x * 256u) {
+        const u32 i = i0 + threadIdx.x;
+        const u32 stat = i < n ? p.rm_stat[i] : RM_NOTHEAD;
+        if (stat >= RM_DISCARD) {
+            bool keep = false;
+            if (stat >= RM_VALID) {
+                const u32 tag = stat & 1u;
+                const u64 key = p.rm_key[i];
+                unsigned long long first;
+                if (key == RM_EMPTY) first = st->rm_allones[tag];
+                else { const u64 sl = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, false); first = sl == ~0ull ? 0ull : p.rm_tab[tag][2 * sl + 1]; }
+                keep = first == g0 + i;
+            }
+            if (g0 + i >= counted) { ++c_tot; if (keep) ++c_uniq; else if (stat == RM_DISCARD) ++c_disc; }
+            if (!keep) {
+                u32 j = i;
+                do { const u32 m = p.lmeta[j]; if (m & LM_KEEP) p.lmeta[j] = (u8)(m & ~LM_KEEP); ++j; } while (j < n && (p.lmeta[j] & LM_EQ));
+            }
+        }
+    }
+    c_tot = __reduce_add_sync(0xFFFFFFFFu, c_tot); c_uniq = __reduce_add_sync(0xFFFFFFFFu, c_uniq); c_disc = __reduce_add_sync(0xFFFFFFFFu, c_disc);
+    if ((threadIdx.x & 31u) == 0) {
+        if (c_tot) atomicAdd(&st->rm_total, (unsigned long long)c_tot);
+        if (c_uniq) atomicAdd(&st->rm_uniq, (unsigned long long)c_uniq);
+        if (c_disc) atomicAdd(&st->rm_discard, (unsigned long long)c_disc);
     }
 }
 

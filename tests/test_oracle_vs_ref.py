@@ -3,6 +3,8 @@
 Runs wherever oracle/_ref exists (the dev container builds it from /root/reference/src; the built
 binaries travel to the GPU box).  Nothing here touches the GPU.
 """
+import os
+
 import pytest
 
 import microcket_b200 as mk
@@ -59,3 +61,29 @@ def test_krmdup_port_lanes(oracle, ref_bin):
     assert b"".join(o[0] for o in outs) == r1
     assert b"".join(o[1] for o in outs) == r2
     assert b"".join(o[2].log_text() for o in outs) == log
+
+
+def test_sam_space_krmdup_restatement(oracle, ref_bin):
+    """oracle/sam_rmdup_oracle.py: the FASTQ it derives from a SAM (primary records, flag 16 undone, stitched read = mate 1 +
+    its reverse complement) gives krmdup the same decisions as the reads the SAM was made from — with the reference's own
+    krmdup binary when it is built, and with the C restatement."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sam_rmdup_oracle as R
+    from rmdup_cases import crafted
+    for mode in ("unc", "flash"):
+        sam, fq = crafted(random.Random(99), 3000, mode)
+        fq2, _ = R.sam_to_fastq(sam)
+        r1, _, dd = oracle.krmdup(fq)
+        r1b, _, ddb = oracle.krmdup(fq2)
+        assert (dd.uniq, dd.dup, dd.discard) == (ddb.uniq, ddb.dup, ddb.discard) and dd.dup > 500 and dd.discard > 50
+        assert R.kept_runs(r1) == {k - 2 for k in R.kept_runs(r1b)}
+        if ref_bin is not None:
+            q1, _, log = ref_krmdup(ref_bin, fq2)
+            assert q1 == r1b and log == ddb.log_text()
+        # the filtered SAM keeps exactly the surviving runs' lines, in order
+        kept = R.kept_runs(r1b)
+        out = R.filter_sam(sam, kept)
+        names = {ln.split(b"\t")[0] for ln in out.splitlines() if not ln.startswith(b"@")}
+        assert names <= {b"r%d" % (k - 2) for k in kept} and out.startswith(b"@HD")
