@@ -42,7 +42,7 @@ struct S2PCtx : mk_ctx {
     DevBuf d_params;                               // device copies of the kernels' parameter blocks (S2PParams.self)
     u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
-    DevBuf d_rmtab[2], d_rmkey, d_rmstat; u64 rm_slots[2] = {0, 0};    // SAM-space krmdup (cfg.rmdup)
+    DevBuf d_rmtab[2], d_rmkey, d_rmstat, d_rminfo; u64 rm_slots[2] = {0, 0};    // SAM-space krmdup (cfg.rmdup)
     S2PSlot slot[2];
     int grid_scan4 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0;
     u64 launches = 0, fallback_windows = 0;
@@ -122,7 +122,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     if (p.rm_on) {
         p.rm_hskip1 = c->cfg.hskip1; p.rm_klen1 = c->cfg.klen1; p.rm_hskip2 = c->cfg.hskip2; p.rm_klen2 = c->cfg.klen2;
         for (int t = 0; t < 2; ++t) { p.rm_tab[t] = c->d_rmtab[t].as<unsigned long long>(); p.rm_mask[t] = c->rm_slots[t] - 1; }
-        p.rm_key = c->d_rmkey.as<unsigned long long>(); p.rm_stat = c->d_rmstat.as<u8>();
+        p.rm_key = c->d_rmkey.as<unsigned long long>(); p.rm_stat = c->d_rmstat.as<u8>(); p.rm_run = p.rm_stat + c->cap_lines; p.rm_info = c->d_rminfo.as<u32>();
     }
     p.self = nullptr;
     return p;
@@ -149,13 +149,14 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     k_chunk_compact<<<(c->n_chunks_cap + 7) / 8, 256, 0, s>>>(p);
     k_scan_lines<4, 4><<<c->grid_scan4, S2P_SCAN_THREADS, 4 * 8192, s>>>(p, 1);
     mark(1);
-    k_parse<<<c->grid_parse, 256, PR_SMEM, s>>>(p);
     if (p.rm_on) {                                       // SAM-space krmdup: duplicate / discarded read pairs lose LM_KEEP before grouping
+        k_parse<true><<<c->grid_parse, 256, PR_SMEM, s>>>(p);
         mark(7);
+        k_rm_keys<<<c->grid_gs, 256, 0, s>>>(p);
         k_rm_insert<<<c->grid_gs, 256, 0, s>>>(p);
         k_rm_mark<<<c->grid_gs, 256, 0, s>>>(p);
-        c->launches += 2;
-    }
+        c->launches += 3;
+    } else k_parse<false><<<c->grid_parse, 256, PR_SMEM, s>>>(p);
     mark(2);
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
     mark(3);
@@ -280,7 +281,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
         u64 slots = 1024; while (slots < 2 * cap) slots <<= 1;
         c->rm_slots[0] = slots; c->rm_slots[1] = std::max<u64>(slots >> 4, 1024);
         for (int t = 0; t < 2; ++t) { A(c->d_rmtab[t].alloc(c->rm_slots[t] * 16)); if (rc == MK_OK && cudaMemset(c->d_rmtab[t].p, 0xFF, c->rm_slots[t] * 16) != cudaSuccess) rc = MK_ERR_CUDA; }
-        A(c->d_rmkey.alloc((size_t)c->cap_lines * 8)); A(c->d_rmstat.alloc(c->cap_lines));
+        A(c->d_rmkey.alloc((size_t)c->cap_lines * 16)); A(c->d_rmstat.alloc((size_t)c->cap_lines * 2)); A(c->d_rminfo.alloc((size_t)c->cap_lines * 4));
     }
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
@@ -317,8 +318,10 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, occ);
     c->grid_gs = sms * 8;
-    cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parse, 256, PR_SMEM);
+    cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
+    cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
+    if (cfg->rmdup) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parse<true>, 256, PR_SMEM);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parse<false>, 256, PR_SMEM);
     c->grid_parse = sms * std::max(1, occ);                 // one resident wave: every CTA then pipelines many rounds
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mk_set_error("mk_s2p_create: %s", cudaGetErrorString(e)); delete c; return MK_ERR_CUDA; }

@@ -107,7 +107,7 @@ struct S2PParams {
     // per-line key / status of the window's QNAME runs
     int rm_on, rm_hskip1, rm_klen1, rm_hskip2, rm_klen2;
     unsigned long long *rm_tab[2]; u64 rm_mask[2];
-    unsigned long long *rm_key; u8 *rm_stat;
+    unsigned long long *rm_key; u8 *rm_stat, *rm_run; u32 *rm_info;   // rm_info: K2's (flag | SEQ offset << 16) per line
     unsigned long long *xparts;   // optional: per launched window (end, count) of its packed pairs, for the overlapped multi-GPU scatter
     const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
 };
@@ -653,8 +653,8 @@ __device__ __forceinline__ u32 first_ws8(u64 x) {
 // of all seven staged words below, whose loads and SWAR tests are independent.  This kernel is bound by per-thread latency.)
 struct FastTok { u32 t0; u64 q[5]; bool ok; };                       // QNAME length and its first 40 bytes (zero padded)
 
-template <class F, bool WANT_Q, class RT>
-__device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, const u64 a, const u64 limit, FastTok &tok, RT &rec, u32 &meta) {
+template <class F, bool WANT_Q, bool RM, class RT>
+__device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, const u64 a, const u64 limit, FastTok &tok, RT &rec, u32 &meta, u32 &rminfo) {
     tok.ok = false;
     if (a + 144 > limit) return false;
     const u64 A = a & ~(u64)15;
@@ -682,6 +682,11 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     if (!dec_field(f, s + t0 + 1, l_flag, flag)) return false;
     if (!dec_field(f, s + t2 + 1, l_pos, pos)) return false;
     if (!dec_field(f, s + t3 + 1, l_mapq, mapq)) return false;
+    if (RM) {                                                          // SAM-space krmdup: where SEQ (field 10) starts, when the prefix shows it
+        const u32 t6 = pop_lowest128(m0, m1, m2, m3), t7 = pop_lowest128(m0, m1, m2, m3), t8 = pop_lowest128(m0, m1, m2, m3);
+        if (t8 < 112 - s && flag <= 0xFFFFu && f.byter(s + t6) == '\t' && f.byter(s + t7) == '\t' && f.byter(s + t8) == '\t')
+            rminfo = flag | ((t8 + 1) << 16);
+    }
     tok.t0 = t0;
     if (WANT_Q) {                                                      // QNAME words for the neighbour-lane comparison
 #pragma unroll
@@ -790,6 +795,7 @@ __device__ __forceinline__ u64 fetch8r(const RowFetch &f, u32 r) { return f.f8(r
 // last line through global memory (L2: another warp has just staged those bytes).  ncu on the block-synchronous version:
 // 15 % of the stall samples on the two barriers per round (threads of a CTA finish their lines at very different times:
 // CIGAR length, the rare slow path).
+template <bool RM>
 static __global__ void __launch_bounds__(256, PR_STAGES == 1 ? PR_OCC : 3) k_parse(S2PParams p) {
     extern __shared__ __align__(16) char s_rows[];                     // [PR_STAGES][256][PR_ROW]
     __shared__ u32 s_st[PR_STAGES][256];                               // the staged line's start (relative to ws), or ~0 when not staged
@@ -862,7 +868,8 @@ static __global__ void __launch_bounds__(256, PR_STAGES == 1 ? PR_OCC : 3) k_par
             const bool staged = s_st[b][tid] != 0xFFFFFFFFu;
             LineRec rec; u32 meta = 0;
             FastTok tok;
-            if (staged && parse_line_fast<RowFetch, false>(p, lf, a, limit, tok, rec, meta)) {
+            u32 rminfo = 0xFFFF0000u;                                  // SEQ offset unknown
+            if (staged && parse_line_fast<RowFetch, false, RM>(p, lf, a, limit, tok, rec, meta, rminfo)) {
                 if (i > 0) {
                     // QNAME equal to the previous line's?  That line's prefix sits in the neighbouring row.
                     const u32 pst = lane > 0 ? s_st[b][tid - 1] : 0xFFFFFFFFu;
@@ -891,6 +898,7 @@ static __global__ void __launch_bounds__(256, PR_STAGES == 1 ? PR_OCC : 3) k_par
             } else meta = parse_line_slow(p, ws, i, a, rec);
             if (meta & LM_KEEP) p.rec[i] = rec;
             p.lmeta[i] = (u8)meta;
+            if (RM) p.rm_info[i] = rminfo;
         }
         __syncwarp();                                                  // this round's rows are the target of the next round's copies
         k_cur = k_nxt; r_cur = r_nxt; k_nxt = k_nn; r_nxt = r_nn;
@@ -981,42 +989,54 @@ static __device__ __noinline__ bool qname_equal_abs(const S2PParams &p, u64 pa, 
 #define RM_DISCARD 3u
 #define RM_VALID 4u         // | tag (0 / 1)
 #define RM_EMPTY 0xFFFFFFFFFFFFFFFFull
+// per-line status (rm_stat): which mates the line's SEQ provides and whether their key windows are valid
+#define RL_M1 1u
+#define RL_M2 2u
+#define RL_OK1 4u
+#define RL_OK2 8u
+#define RL_TAG 16u
+#define RL_HDR 32u
 
 __device__ __forceinline__ u64 rm_tabmask(u64 w) {                      // bit 7 of every byte that is '\t' (exact)
     const u64 x = w ^ 0x0909090909090909ull;
     return ~(((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x) & 0x8080808080808080ull;
 }
-// first '\t' in [from, end) or end; aligned 8-byte loads (the buffer is 16-byte aligned and padded)
+// first '\t' in [from, end) or end; aligned 16-byte loads (the buffer is 16-byte aligned and padded)
 __device__ __forceinline__ u64 rm_next_tab(const char *buf, u64 from, u64 end) {
-    u64 pos = from & ~7ull;
-    u64 m = rm_tabmask(__ldg((const unsigned long long *)(buf + pos))) & (~0ull << (8 * (from - pos)));
+    u64 pos = from & ~15ull;
+    uint4 w = __ldg((const uint4 *)(buf + pos));
+    u64 lo = rm_tabmask((u64)w.x | ((u64)w.y << 32)), hi = rm_tabmask((u64)w.z | ((u64)w.w << 32));
+    const u32 sk = (u32)(from - pos);                                   // bytes before `from` do not count
+    if (sk >= 8) { lo = 0; hi &= ~0ull << (8 * (sk - 8)); } else lo &= ~0ull << (8 * sk);
     while (true) {
-        if (m) { const u64 t = pos + ((u32)(__ffsll((long long)m) - 1) >> 3); return t < end ? t : end; }
-        pos += 8;
+        if (lo | hi) {
+            const u64 t = pos + (lo ? ((u32)(__ffsll((long long)lo) - 1) >> 3) : 8u + ((u32)(__ffsll((long long)hi) - 1) >> 3));
+            return t < end ? t : end;
+        }
+        pos += 16;
         if (pos >= end) return end;
-        m = rm_tabmask(__ldg((const unsigned long long *)(buf + pos)));
+        w = __ldg((const uint4 *)(buf + pos));
+        lo = rm_tabmask((u64)w.x | ((u64)w.y << 32)); hi = rm_tabmask((u64)w.z | ((u64)w.w << 32));
     }
 }
-__device__ __forceinline__ int rm_comp(int c) {
-    switch (c) {
-    case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
-    case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
-    default: return c;
-    }
-}
-// bases [hskip, hskip + klen) of the mate that is SEQ (rev = false) or its reverse complement; false = discard
-__device__ __forceinline__ bool rm_half(const char *buf, u64 seq, u32 L, bool rev, int hskip, int klen, u64 &bits, int &first) {
-    bits = 0; first = 'N';
+// bases [hskip, hskip + klen) of the mate that is SEQ (rev = false) or its reverse complement; false = discard.
+// 2-bit code of krmdup.cpp:171-177 (A 1, T 2, C 0, G 3, either case) from (c >> 1) & 3 = A 0, C 1, T 2, G 3; the
+// complement is code ^ 3.  lower_first: the mate's first key base is a lower-case a / c / g (krmdup.cpp:134-141: T bucket)
+__device__ __forceinline__ bool rm_half(const char *buf, u64 seq, u32 L, bool rev, int hskip, int klen, u64 &bits, bool &lower_first) {
+    bits = 0; lower_first = false;
     if (L < (u32)(hskip + klen)) return false;
     bool ok = true;
-    for (int k = 0; k < klen; ++k) {
-        int c = (int)(unsigned char)(rev ? buf[seq + L - 1 - (u32)(hskip + k)] : buf[seq + (u32)(hskip + k)]);
-        if (rev) c = rm_comp(c);
-        if (k == 0) first = c;
-        const int cu = c & 0xDF;
-        const u32 code = cu == 'A' ? 1u : cu == 'T' ? 2u : cu == 'C' ? 0u : cu == 'G' ? 3u : 4u;
-        ok = ok && code < 4u;
-        bits = (bits << 2) | (code & 3u);
+    const char *q = rev ? buf + seq + L - 1 - (u32)hskip : buf + seq + (u32)hskip;
+    const int step = rev ? -1 : 1;
+#pragma unroll 4
+    for (int k = 0; k < klen; ++k, q += step) {
+        const u32 c = (u32)(unsigned char)*q, cu = c & 0xDFu;
+        const u32 x = (c >> 1) & 3u;
+        u32 code = x ^ ((~x >> 1) & 1u);
+        if (rev) code ^= 3u;
+        ok = ok && (cu == 'A' || cu == 'C' || cu == 'G' || cu == 'T');
+        if (k == 0) lower_first = (c & 0x20u) && code != 2u;
+        bits = (bits << 2) | code;
     }
     return ok;
 }
@@ -1039,63 +1059,86 @@ __device__ __forceinline__ u64 rm_slot(unsigned long long *tab, u64 mask, u64 ke
     return ~0ull;
 }
 
-// phase 1: one thread per line; the thread of a run's first line builds the pair's key and records its first occurrence
-static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
-    WinState *st = p.st;
+// phase A: one thread per line: the key bits its SEQ gives to mate 1 and / or mate 2 (primary records only)
+static __global__ void __launch_bounds__(256) k_rm_keys(S2PParams p) {
+    const WinState *st = p.st;
     const u32 n = st->n_lines;
-    const u64 ws = st->ws, g0 = st->lines_done;
-    const bool final_win = (st->we == st->total) && st->is_last;
+    const u64 ws = st->ws;
     for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        u32 stat = RM_NOTHEAD;
-        if (!(p.lmeta[i] & LM_EQ)) {
-            u64 a = ws + (i ? (u64)p.nl_pos[i - 1] + 1 : 0);
-            if (p.buf[a] == '@') stat = RM_SKIP;
+        const u32 info = p.rm_info[i];
+        const u64 a = ws + (i ? (u64)p.nl_pos[i - 1] + 1 : 0), e = ws + p.nl_pos[i];
+        u32 flag = info & 0xFFFFu, stat = 0;
+        u64 seq = a + (info >> 16), key = 0, key2 = 0;
+        bool primary = true;
+        if ((info >> 16) == 0xFFFFu) {                                  // K2 did not see the SEQ column: FLAG = field 2, SEQ = field 10
+            if (p.buf[a] == '@') { stat = RL_HDR; primary = false; }
             else {
-                bool have1 = false, have2 = false, ok1 = false, ok2 = false;
-                u64 b1 = 0, b2 = 0; int first = 'N';
-                u32 j = i;
-                while (true) {
-                    const u64 e = ws + p.nl_pos[j];
-                    // FLAG = field 2, SEQ = field 10 (tab separated)
-                    const u64 t1 = rm_next_tab(p.buf, a, e);
-                    u64 t = t1 < e ? rm_next_tab(p.buf, t1 + 1, e) : e;
-                    u32 flag = 0;
-                    for (u64 q = t1 + 1; q < t; ++q) flag = flag * 10u + (u32)((unsigned char)p.buf[q] - '0');
-                    if (!(flag & 0x900u)) {
-                        const bool m1 = (flag & 64u) || !(flag & 192u), m2 = !(flag & 64u);   // 128 only -> mate 2; neither -> both
-                        if ((m1 && !have1) || (m2 && !have2)) {
-                            for (int k = 2; k < 9 && t < e; ++k) t = rm_next_tab(p.buf, t + 1, e);
-                            u64 seq = e; u32 L = 0;
-                            if (t < e) { seq = t + 1; L = (u32)(rm_next_tab(p.buf, seq, e) - seq); }
-                            const bool rev = (flag & 16u) != 0;
-                            if (m1 && !have1) { have1 = true; ok1 = rm_half(p.buf, seq, L, rev, p.rm_hskip1, p.rm_klen1, b1, first); }
-                            if (m2 && !have2) { int f2; have2 = true; ok2 = rm_half(p.buf, seq, L, (flag & 192u) ? rev : !rev, p.rm_hskip2, p.rm_klen2, b2, f2); }
-                        }
-                    }
-                    ++j;
-                    if (j >= n || !(p.lmeta[j] & LM_EQ)) break;
-                    a = e + 1;
-                }
-                if (j >= n && !final_win) stat = RM_INCOMPLETE;
-                else if (ok1 && ok2) {
-                    const u64 key = (b1 << (2 * p.rm_klen2)) | b2;
-                    const u32 tag = (first == 'a' || first == 'c' || first == 'g') ? 1u : 0u;   // T bucket, not 'T' / 't' (krmdup.cpp:134-141)
-                    stat = RM_VALID | tag;
-                    p.rm_key[i] = key;
-                    if (key == RM_EMPTY) atomicMin(&st->rm_allones[tag], (unsigned long long)(g0 + i));
-                    else {
-                        const u64 sl = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, true);
-                        if (sl == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); stat = RM_INCOMPLETE; }
-                        else atomicMin(&p.rm_tab[tag][2 * sl + 1], (unsigned long long)(g0 + i));
-                    }
-                } else stat = RM_DISCARD;
+                const u64 t1 = rm_next_tab(p.buf, a, e);
+                u64 t = t1 < e ? rm_next_tab(p.buf, t1 + 1, e) : e;
+                flag = 0;
+                for (u64 q = t1 + 1; q < t; ++q) flag = flag * 10u + (u32)((unsigned char)p.buf[q] - '0');
+                for (int k = 2; k < 9 && t < e; ++k) t = rm_next_tab(p.buf, t + 1, e);
+                seq = t < e ? t + 1 : e;
             }
         }
+        if (primary && !(flag & 0x900u)) {
+            const u32 L = seq < e ? (u32)(rm_next_tab(p.buf, seq, e) - seq) : 0u;
+            const bool m1 = (flag & 64u) || !(flag & 192u), m2 = !(flag & 64u);   // 128 only -> mate 2; neither (stitched) -> both
+            const bool rev = (flag & 16u) != 0;
+            u64 b1 = 0, b2 = 0; bool lf = false, l2;
+            if (m1) { stat |= RL_M1; if (rm_half(p.buf, seq, L, rev, p.rm_hskip1, p.rm_klen1, b1, lf)) stat |= RL_OK1; if (lf) stat |= RL_TAG; }
+            if (m2) { stat |= RL_M2; if (rm_half(p.buf, seq, L, (flag & 192u) ? rev : !rev, p.rm_hskip2, p.rm_klen2, b2, l2)) stat |= RL_OK2; }
+            key = b1; key2 = b2;
+        }
         p.rm_stat[i] = (u8)stat;
+        ((ulonglong2 *)p.rm_key)[i] = make_ulonglong2(key, key2);
     }
 }
 
-// phase 2 (after every insert of the window): a run survives iff it is the first occurrence of its key; the others lose LM_KEEP
+// phase B: the thread of a run's first line combines the run's mates into the pair's key and records its first occurrence
+static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
+    WinState *st = p.st;
+    const u32 n = st->n_lines;
+    const u64 g0 = st->lines_done;
+    const bool final_win = (st->we == st->total) && st->is_last;
+    for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        u32 run = RM_NOTHEAD;
+        if (!(p.lmeta[i] & LM_EQ)) {
+            u32 sl = p.rm_stat[i];
+            if (sl & RL_HDR) run = RM_SKIP;
+            else {
+                u32 have = 0; u64 b1 = 0, b2 = 0;
+                u32 j = i;
+                while (true) {
+                    if (sl & ~have & (RL_M1 | RL_M2)) {
+                        const ulonglong2 k = ((const ulonglong2 *)p.rm_key)[j];
+                        if (sl & ~have & RL_M1) { b1 = k.x; have |= RL_M1 | (sl & (RL_OK1 | RL_TAG)); }
+                        if (sl & ~have & RL_M2) { b2 = k.y; have |= RL_M2 | (sl & RL_OK2); }
+                    }
+                    ++j;
+                    if (j >= n || !(p.lmeta[j] & LM_EQ)) break;
+                    sl = p.rm_stat[j];
+                }
+                if (j >= n && !final_win) run = RM_INCOMPLETE;
+                else if ((have & (RL_OK1 | RL_OK2)) == (RL_OK1 | RL_OK2)) {
+                    const u64 key = (b1 << (2 * p.rm_klen2)) | b2;
+                    const u32 tag = (have & RL_TAG) ? 1u : 0u;
+                    run = RM_VALID | tag;
+                    p.rm_key[2 * (size_t)i] = key;
+                    if (key == RM_EMPTY) atomicMin(&st->rm_allones[tag], (unsigned long long)(g0 + i));
+                    else {
+                        const u64 s = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, true);
+                        if (s == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); run = RM_INCOMPLETE; }
+                        else atomicMin(&p.rm_tab[tag][2 * s + 1], (unsigned long long)(g0 + i));
+                    }
+                } else run = RM_DISCARD;
+            }
+        }
+        p.rm_run[i] = (u8)run;
+    }
+}
+
+// phase C (after every insert of the window): a run survives iff it is the first occurrence of its key; the others lose LM_KEEP
 static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
     WinState *st = p.st;
     const u32 n = st->n_lines;
@@ -1103,12 +1146,12 @@ static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
     u32 c_tot = 0, c_uniq = 0, c_disc = 0;
     for (u32 i0 = blockIdx.x * 256u; i0 < n; i0 += gridDim.x * 256u) {
         const u32 i = i0 + threadIdx.x;
-        const u32 stat = i < n ? p.rm_stat[i] : RM_NOTHEAD;
+        const u32 stat = i < n ? p.rm_run[i] : RM_NOTHEAD;
         if (stat >= RM_DISCARD) {
             bool keep = false;
             if (stat >= RM_VALID) {
                 const u32 tag = stat & 1u;
-                const u64 key = p.rm_key[i];
+                const u64 key = p.rm_key[2 * (size_t)i];
                 unsigned long long first;
                 if (key == RM_EMPTY) first = st->rm_allones[tag];
                 else { const u64 sl = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, false); first = sl == ~0ull ? 0ull : p.rm_tab[tag][2 * sl + 1]; }
