@@ -682,10 +682,15 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     if (!dec_field(f, s + t0 + 1, l_flag, flag)) return false;
     if (!dec_field(f, s + t2 + 1, l_pos, pos)) return false;
     if (!dec_field(f, s + t3 + 1, l_mapq, mapq)) return false;
+    u32 rm_so = 0, qlen = 0;
     if (RM) {                                                          // SAM-space krmdup: where SEQ (field 10) starts, when the prefix shows it
         const u32 t6 = pop_lowest128(m0, m1, m2, m3), t7 = pop_lowest128(m0, m1, m2, m3), t8 = pop_lowest128(m0, m1, m2, m3);
-        if (t8 < 112 - s && flag <= 0xFFFFu && f.byter(s + t6) == '\t' && f.byter(s + t7) == '\t' && f.byter(s + t8) == '\t')
-            rminfo = flag | ((t8 + 1) << 16);
+        if (flag <= 0xFFFu) {
+            // SEQ's offset when the staged prefix reaches it, else the offset of field 7 (three short tab searches are left)
+            if (t8 < 112 - s && f.byter(s + t6) == '\t' && f.byter(s + t7) == '\t' && f.byter(s + t8) == '\t') rm_so = (t8 + 1) | 128u;
+            else rm_so = t5 + 1;
+        }
+        rminfo = flag | (rm_so << 12);                                 // rm_so = 0: k_rm_keys finds FLAG and SEQ itself
     }
     tok.t0 = t0;
     if (WANT_Q) {                                                      // QNAME words for the neighbour-lane comparison
@@ -698,7 +703,22 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
     }
     tok.ok = t0 <= 40;
     meta = 0;
-    if (mapq < (u32)p.min_mapq || (flag & 0x700u)) return true;       // pairutil.h:157-161
+    if (mapq < (u32)p.min_mapq || (flag & 0x700u)) {                  // pairutil.h:157-161
+        if (RM && rm_so && !(flag & 0x900u)) {                         // a dropped PRIMARY record still carries its read: SEQ length from the CIGAR
+            const u32 lc = t5 - t4 - 1;
+            u32 v = 0; u64 y = 0;
+            for (u32 k = 0; k < lc; ++k) {
+                if ((k & 7) == 0) y = fetch8r(f, s + t4 + 1 + k);
+                const int c = (int)(y & 0xFF); y >>= 8;
+                const u32 d = (u32)(c - '0');
+                if (d <= 9u) { v = v * 10u + d; continue; }
+                if (c == 'M' || c == 'I' || c == 'S' || c == '=' || c == 'X') qlen += v;
+                v = 0;
+            }
+            if (qlen < 4096u) rminfo |= qlen << 20;
+        }
+        return true;
+    }
     meta = LM_KEEP;
     // RNAME: FNV-1a over its bytes, same as the byte loop
     u64 name8 = fetch8r(f, s + t1 + 1);
@@ -729,8 +749,10 @@ __device__ __forceinline__ bool parse_line_fast(const S2PParams &p, const F &f, 
             cur += val; ++idx; last_right = 0;
             if (idx == 1) left1 = cur;
         } else if (c != 'I') err = true;
+        if (RM && (c == 'M' || c == 'I' || c == 'S')) qlen += val;     // bases present in SEQ (SAM spec 1.4.6)
         val = 0;
     }
+    if (RM && rm_so && !err && qlen < 4096u) rminfo |= qlen << 20;
     rec.pos = pos; rec.right0 = right0; rec.left1 = left1; rec.right1 = right1;
     rec.leftClip = leftClip; rec.rightClip = rightClip; rec.mappable = mappable; rec.line_len = 0;
     rec.flag = (u16)flag; rec.qname_len = (u16)t0;
@@ -868,7 +890,7 @@ static __global__ void __launch_bounds__(256, PR_STAGES == 1 ? PR_OCC : 3) k_par
             const bool staged = s_st[b][tid] != 0xFFFFFFFFu;
             LineRec rec; u32 meta = 0;
             FastTok tok;
-            u32 rminfo = 0xFFFF0000u;                                  // SEQ offset unknown
+            u32 rminfo = 0;                                            // SEQ offset unknown
             if (staged && parse_line_fast<RowFetch, false, RM>(p, lf, a, limit, tok, rec, meta, rminfo)) {
                 if (i > 0) {
                     // QNAME equal to the previous line's?  That line's prefix sits in the neighbouring row.
@@ -1013,31 +1035,49 @@ __device__ __forceinline__ u64 rm_next_tab(const char *buf, u64 from, u64 end) {
             const u64 t = pos + (lo ? ((u32)(__ffsll((long long)lo) - 1) >> 3) : 8u + ((u32)(__ffsll((long long)hi) - 1) >> 3));
             return t < end ? t : end;
         }
-        pos += 16;
-        if (pos >= end) return end;
-        w = __ldg((const uint4 *)(buf + pos));
+        do {                                                            // four SIMD compares per 16 bytes until a word holds a tab
+            pos += 16;
+            if (pos >= end) return end;
+            w = __ldg((const uint4 *)(buf + pos));
+        } while (!(__vcmpeq4(w.x, 0x09090909u) | __vcmpeq4(w.y, 0x09090909u) | __vcmpeq4(w.z, 0x09090909u) | __vcmpeq4(w.w, 0x09090909u)));
         lo = rm_tabmask((u64)w.x | ((u64)w.y << 32)); hi = rm_tabmask((u64)w.z | ((u64)w.w << 32));
     }
 }
+// 8 bases in memory order -> their 2-bit codes, base k at bits 2k (krmdup.cpp:171-177: A 1, T 2, C 0, G 3, either case; from
+// (c >> 1) & 3 = A 0, C 1, T 2, G 3); ok is cleared when one of the first nb bytes is not a base
+__device__ __forceinline__ u32 rm_codes8(u64 w, int nb, bool &ok) {
+    const u32 ul = (u32)w & 0xDFDFDFDFu, uh = (u32)(w >> 32) & 0xDFDFDFDFu;
+    const u32 vl = __vcmpeq4(ul, 0x41414141u) | __vcmpeq4(ul, 0x43434343u) | __vcmpeq4(ul, 0x47474747u) | __vcmpeq4(ul, 0x54545454u);
+    const u32 vh = __vcmpeq4(uh, 0x41414141u) | __vcmpeq4(uh, 0x43434343u) | __vcmpeq4(uh, 0x47474747u) | __vcmpeq4(uh, 0x54545454u);
+    const u64 need = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1);
+    ok = ok && ((((u64)vl | ((u64)vh << 32)) & need) == need);
+    const u64 x = (w >> 1) & 0x0303030303030303ull;
+    u64 c = (x ^ ((~x >> 1) & 0x0101010101010101ull)) & need;
+    c = (c | (c >> 6)) & 0x000F000F000F000Full;
+    c = (c | (c >> 12)) & 0x000000FF000000FFull;
+    c = (c | (c >> 24)) & 0xFFFFull;
+    return (u32)c;
+}
 // bases [hskip, hskip + klen) of the mate that is SEQ (rev = false) or its reverse complement; false = discard.
-// 2-bit code of krmdup.cpp:171-177 (A 1, T 2, C 0, G 3, either case) from (c >> 1) & 3 = A 0, C 1, T 2, G 3; the
-// complement is code ^ 3.  lower_first: the mate's first key base is a lower-case a / c / g (krmdup.cpp:134-141: T bucket)
+// The klen bytes are fetched in memory order, eight at a time: for the reverse complement that IS the key's order once
+// every code is complemented (code ^ 3); for the forward mate the 2-bit groups are reversed.
+// lower_first: the mate's first key base is a lower-case a / c / g (krmdup.cpp:134-141: T bucket, own identity space)
 __device__ __forceinline__ bool rm_half(const char *buf, u64 seq, u32 L, bool rev, int hskip, int klen, u64 &bits, bool &lower_first) {
     bits = 0; lower_first = false;
     if (L < (u32)(hskip + klen)) return false;
-    bool ok = true;
-    const char *q = rev ? buf + seq + L - 1 - (u32)hskip : buf + seq + (u32)hskip;
-    const int step = rev ? -1 : 1;
-#pragma unroll 4
-    for (int k = 0; k < klen; ++k, q += step) {
-        const u32 c = (u32)(unsigned char)*q, cu = c & 0xDFu;
-        const u32 x = (c >> 1) & 3u;
-        u32 code = x ^ ((~x >> 1) & 1u);
-        if (rev) code ^= 3u;
-        ok = ok && (cu == 'A' || cu == 'C' || cu == 'G' || cu == 'T');
-        if (k == 0) lower_first = (c & 0x20u) && code != 2u;
-        bits = (bits << 2) | code;
+    if (klen == 0) return true;
+    GlobalFetch gf; gf.buf = buf; gf.A = 0;
+    const u64 start = rev ? seq + L - (u32)(hskip + klen) : seq + (u32)hskip;
+    u64 le = 0; bool ok = true;
+    for (int o = 0; o < klen; o += 8) le |= (u64)rm_codes8(fetch8(gf, start + (u32)o), klen - o, ok) << (2 * o);
+    const u32 c0 = (u32)(unsigned char)buf[rev ? start + (u32)klen - 1 : start];
+    if (rev) bits = le ^ (klen >= 32 ? ~0ull : ((1ull << (2 * klen)) - 1));
+    else {
+        u64 r = __brevll(le);
+        r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+        bits = r >> (64 - 2 * klen);
     }
+    lower_first = (c0 & 0x20u) && ((bits >> (2 * klen - 2)) & 3u) != 2u;
     return ok;
 }
 __device__ __forceinline__ u64 rm_hash(u64 k) {
@@ -1065,12 +1105,18 @@ static __global__ void __launch_bounds__(256) k_rm_keys(S2PParams p) {
     const u32 n = st->n_lines;
     const u64 ws = st->ws;
     for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        const u32 info = p.rm_info[i];
+        const u32 info = p.rm_info[i];                                  // K2: flag | offset << 12 | (offset is SEQ's, not field 7's) << 19 | SEQ length by the CIGAR << 20
         const u64 a = ws + (i ? (u64)p.nl_pos[i - 1] + 1 : 0), e = ws + p.nl_pos[i];
-        u32 flag = info & 0xFFFFu, stat = 0;
-        u64 seq = a + (info >> 16), key = 0, key2 = 0;
+        u32 flag = info & 0xFFFu, stat = 0;
+        const u32 so = (info >> 12) & 0x7Fu, ql = info >> 20;
+        u64 seq = a + so, key = 0, key2 = 0;
         bool primary = true;
-        if ((info >> 16) == 0xFFFFu) {                                  // K2 did not see the SEQ column: FLAG = field 2, SEQ = field 10
+        if (so && !(info & (1u << 19)) && !(flag & 0x900u)) {           // from field 7 (RNEXT): PNEXT, TLEN, SEQ
+            u64 t = seq;
+            for (int k = 0; k < 3 && t < e; ++k) { t = rm_next_tab(p.buf, t, e); if (t < e) ++t; }
+            seq = t;
+        }
+        if (so == 0) {                                                  // K2 did not parse the line: FLAG = field 2, SEQ = field 10
             if (p.buf[a] == '@') { stat = RL_HDR; primary = false; }
             else {
                 const u64 t1 = rm_next_tab(p.buf, a, e);
@@ -1082,7 +1128,10 @@ static __global__ void __launch_bounds__(256) k_rm_keys(S2PParams p) {
             }
         }
         if (primary && !(flag & 0x900u)) {
-            const u32 L = seq < e ? (u32)(rm_next_tab(p.buf, seq, e) - seq) : 0u;
+            // SEQ length: the CIGAR's when the byte behind it ends the field (no scan over the bases), else counted
+            u32 L;
+            if (so && ql && seq + ql <= e && (seq + ql == e || p.buf[seq + ql] == '\t') && p.buf[seq + ql - 1] != '\t') L = ql;
+            else L = seq < e ? (u32)(rm_next_tab(p.buf, seq, e) - seq) : 0u;
             const bool m1 = (flag & 64u) || !(flag & 192u), m2 = !(flag & 64u);   // 128 only -> mate 2; neither (stitched) -> both
             const bool rev = (flag & 16u) != 0;
             u64 b1 = 0, b2 = 0; bool lf = false, l2;
@@ -1103,15 +1152,17 @@ static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
     const bool final_win = (st->we == st->total) && st->is_last;
     for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
         u32 run = RM_NOTHEAD;
-        if (!(p.lmeta[i] & LM_EQ)) {
-            u32 sl = p.rm_stat[i];
+        const u32 m_i = p.lmeta[i];                                     // the three loads of the common case go out together
+        u32 sl = p.rm_stat[i];
+        const ulonglong2 k_i = ((const ulonglong2 *)p.rm_key)[i];
+        if (!(m_i & LM_EQ)) {
             if (sl & RL_HDR) run = RM_SKIP;
             else {
                 u32 have = 0; u64 b1 = 0, b2 = 0;
                 u32 j = i;
                 while (true) {
                     if (sl & ~have & (RL_M1 | RL_M2)) {
-                        const ulonglong2 k = ((const ulonglong2 *)p.rm_key)[j];
+                        const ulonglong2 k = j == i ? k_i : ((const ulonglong2 *)p.rm_key)[j];
                         if (sl & ~have & RL_M1) { b1 = k.x; have |= RL_M1 | (sl & (RL_OK1 | RL_TAG)); }
                         if (sl & ~have & RL_M2) { b2 = k.y; have |= RL_M2 | (sl & RL_OK2); }
                     }
@@ -1152,9 +1203,17 @@ static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
             if (stat >= RM_VALID) {
                 const u32 tag = stat & 1u;
                 const u64 key = p.rm_key[2 * (size_t)i];
-                unsigned long long first;
+                unsigned long long first = 0;
                 if (key == RM_EMPTY) first = st->rm_allones[tag];
-                else { const u64 sl = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, false); first = sl == ~0ull ? 0ull : p.rm_tab[tag][2 * sl + 1]; }
+                else {                                                  // every insert of the window is done: {key, first line} in one load
+                    const u64 mask = p.rm_mask[tag];
+                    u64 sl = rm_hash(key) & mask;
+                    for (u64 probe = 0; probe <= mask; ++probe, sl = (sl + 1) & mask) {
+                        const ulonglong2 e = __ldcg((const ulonglong2 *)p.rm_tab[tag] + sl);
+                        if (e.x == key) { first = e.y; break; }
+                        if (e.x == RM_EMPTY) break;
+                    }
+                }
                 keep = first == g0 + i;
             }
             if (g0 + i >= counted) { ++c_tot; if (keep) ++c_uniq; else if (stat == RM_DISCARD) ++c_disc; }

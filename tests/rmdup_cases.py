@@ -39,7 +39,7 @@ def crafted(rng, n_frag, mode):
         def rec(read, flag, pos, mapq=60, cigar=None):
             if rng.random() < 0.5:
                 flag |= 16; read = R.revcomp(read)
-            cigar = cigar or b"%dM" % len(read)
+            cigar = cigar or b"%dM" % (len(read) if rng.random() < 0.95 else rng.choice((7, len(read) // 2, len(read) + 9)))   # a CIGAR that lies about SEQ
             return b"\t".join([q, b"%d" % flag, b"chr1", b"%d" % pos, b"%d" % mapq, cigar, b"=", b"1", b"0", read, b"F" * len(read), b"NM:i:0"]) + b"\n"
         pos = rng.randrange(1000, 200000000)
         lines = []
