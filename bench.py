@@ -182,6 +182,8 @@ def run_reference(args):
 
 def workload_config(args, world, groups):
     return {"workload": WL["title"], "sam_passthrough": "on (the driver's default, microcket:107)" if SAM_ON else "off",
+            "dedup": ("seq: krmdup's rule (bases [5,21) of each mate, first occurrence wins, src/preprocess/krmdup.cpp) on the SAM's primary records, inside sam2pairs"
+                      if DEDUP_SEQ else "coord: (lane, chr1,pos1,s1, chr2,pos2,s2) of the emitted pairs, same sort as the binning"),
             "read_groups_per_gpu": groups, "genome": WL["genome"], "mode": WL["mode"], "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
             "seed": SEED, "duplicates": f"{DUP_PER_1024}/1024 of the read groups copy the fragment of another group of the whole job (all shards)", "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
             "parallelism": f"shard{world}: parse by read chunk, packed pairs to their owner hash(chr1,chr2,pos1/{PART_RES}) by the library's own NVLink peer-memory kernel (MICROCKET_XCHG=nccl: partition + NCCL all-to-all), dedup + COO owner-computes"}
@@ -202,7 +204,7 @@ class Pipeline:
         self.b1 = torch.empty(self.cap_pairs, dtype=torch.int32, device=dev); self.b2 = torch.empty_like(self.b1); self.cnt = torch.empty_like(self.b1)
         self.samout = torch.empty(int(groups * (1400 if WL["mode"] == "unc" else 800)) + (1 << 20), dtype=torch.uint8, device=dev) if SAM_ON else None
         self.s2p = mk.Sam2Pairs(mk.S2PConfig(mode=WL["mode"], threads=8, write_sam=SAM_ON, emit_text=True, emit_packed=True, device=local,
-                                             window_bytes=window_bytes, sharded=(world > 1)), WL["names"])
+                                             window_bytes=window_bytes, sharded=(world > 1), rmdup=DEDUP_SEQ, rmdup_capacity=groups + 1024), WL["names"])
         self.sam_len = 0
         self.stream = torch.cuda.current_stream().cuda_stream
         self.src = self.pairs
@@ -247,8 +249,12 @@ class Pipeline:
         # duplicate removal and 5 kb binning share one sort (mk_pairs_dedup_bin_device)
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
-        kept, nnz = self.ws.dedup_bin(src_ptr, n, WL["lens"], RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
-                                      stream=self.stream)
+        if DEDUP_SEQ:                                  # duplicates are gone already (cfg.rmdup): binning only
+            kept = n
+            nnz = self.ws.bin(src_ptr, n, WL["lens"], RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs, stream=self.stream)
+        else:
+            kept, nnz = self.ws.dedup_bin(src_ptr, n, WL["lens"], RES, self.b1.data_ptr(), self.b2.data_ptr(), self.cnt.data_ptr(), self.cap_pairs,
+                                          stream=self.stream)
         eb.record()
         if pair_events is not None:
             pair_events.append((ea, eb, n))
@@ -505,6 +511,7 @@ def run_krmdup(args):
 
 VERIFY = {}
 SAM_ON = False
+DEDUP_SEQ = False       # --dedup seq: SAM-space krmdup inside sam2pairs (cfg.rmdup) + binning, instead of coordinate dedup + binning
 
 
 def main():
@@ -521,11 +528,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", default="flash", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: configs[1], the headline)")
     ap.add_argument("--sam", action="store_true", help="SAM passthrough on (sam2pairs argv[7]; the driver's default) in both arms")
+    ap.add_argument("--dedup", default="coord", choices=["coord", "seq"],
+                    help="coord: duplicates by (lane, chr1,pos1,s1, chr2,pos2,s2) of the emitted pairs, one sort with the binning (default; no reference "
+                         "implementation exists). seq: the reference's own krmdup rule (2 x 16 read bases, src/preprocess/krmdup.cpp) applied to the "
+                         "SAM's primary records before grouping - pinned by the reference binaries - then binning")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed, asserted reduced-size verification of the N-GPU path")
     ap.add_argument("--verify-groups", type=int, default=200_000, help="read groups per GPU of that verification")
     args = ap.parse_args()
-    global WL, SAM_ON
-    WL = WORKLOADS[args.config]; SAM_ON = args.sam
+    global WL, SAM_ON, DEDUP_SEQ
+    WL = WORKLOADS[args.config]; SAM_ON = args.sam; DEDUP_SEQ = args.dedup == "seq"
+    if DEDUP_SEQ and (int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.config == "multires"):
+        raise SystemExit("bench.py: --dedup seq is a single-GPU configuration of configs[1] / [2] (a krmdup key table per GPU = one lane per GPU)")
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.config == "krmdup":
         return run_krmdup(args)
@@ -644,7 +657,8 @@ def main():
     text_b = float(io_text_len)                        # bytes of pair text of one pass
     alg = {"k_scan_chunks": nbytes + 4 * lines, "k_chunk_index": 8 * lines,
            "k_parse": 117.0 * lines + 48.0 * groups, "k_group": lines + 80.0 * groups,
-           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 2.0 * float(pipe.sam_len) + 9.0 * lines}
+           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 2.0 * float(pipe.sam_len) + 9.0 * lines,
+           "k_rmdup": 136.0 * lines + 32.0 * groups}     # --dedup seq: 8 B of K2's notes + the two key windows' sectors (4 x 32 B) per line, one 16-byte table slot read + written per read pair
     per_kernel = {}
     for k, (ms_k, n_k) in dk.items():
         if ms_k > 0 and n_k > 0:
@@ -709,8 +723,11 @@ def main():
             "config": dict(workload_config(args, world, G), sam_bytes_per_gpu=nbytes, pairs_per_step=n_pairs_all, kept_after_dedup=kept_all,
                            coo_cells=nnz_all, window_mb=args.window_mb),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checks": checks,
-            "parity": "sam2pairs pinned by the reference binary (tests/); coordinate dedup + binning UNPINNED (no reference implementation "
-                      "exists: checked against oracle/pairs_oracle.c + numpy only) - that stage is %.1f of the %.1f ms step" % (
+            "parity": ("sam2pairs AND the duplicate removal pinned by the reference binaries (krmdup's own rule taken on the SAM, tests/test_gpu_s2p_rmdup.py); "
+                       "binning UNPINNED (juicer_tools absent: checked against oracle/pairs_oracle.c + numpy only) - that stage is %.1f of the %.1f ms step"
+                       if DEDUP_SEQ else
+                       "sam2pairs pinned by the reference binary (tests/); coordinate dedup + binning UNPINNED (no reference implementation "
+                       "exists: checked against oracle/pairs_oracle.c + numpy only) - that stage is %.1f of the %.1f ms step") % (
                           roofline.get("pairs_stage", {}).get("ms_per_step", 0.0), ms_step),
             "verify_sharded": VERIFY.get("result")}
     if pipe.multires:
@@ -791,7 +808,10 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     ws = mk.PairsWorkspace(cap, device=local)
     W = 256 << 20
     s2p = mk.Sam2Pairs(mk.S2PConfig(mode=WL["mode"], threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W,
-                                    sharded=(world > 1)), WL["names"])
+                                    sharded=(world > 1), rmdup=DEDUP_SEQ, rmdup_capacity=E + 1024), WL["names"])
+    if DEDUP_SEQ:
+        sd_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+        sb1 = torch.empty(cap, dtype=torch.int32, device=dev); sb2 = torch.empty_like(sb1); sbc = torch.empty_like(sb1)
     if world > 1:
         from microcket_b200 import shard
         d_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev); d_kept = torch.empty_like(d_pairs)
@@ -824,7 +844,14 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
         st = s2p.finish(0, 0) if world > 1 else s2p.finish()
         assert st.pairs == pl
         t_c = time.perf_counter()
-        if world == 1:
+        if DEDUP_SEQ:                                  # the pulled pairs are already deduplicated: back to the device for the binning, COO to the host
+            sd_pairs[:pl * 16].copy_(out_pairs[:pl * 16], non_blocking=True)
+            kept = pl
+            nnz = ws.bin(sd_pairs.data_ptr(), pl, WL["lens"], RES, sb1.data_ptr(), sb2.data_ptr(), sbc.data_ptr(), cap, stream=torch.cuda.current_stream().cuda_stream)
+            ob1[:nnz].copy_(sb1[:nnz], non_blocking=True); ob2[:nnz].copy_(sb2[:nnz], non_blocking=True); oc[:nnz].copy_(sbc[:nnz], non_blocking=True)
+            torch.cuda.synchronize()
+            moved = pl
+        elif world == 1:
             kept, nnz = ws.dedup_bin_host(out_pairs.data_ptr(), pl, WL["lens"], RES, ob1.data_ptr(), ob2.data_ptr(), oc.data_ptr(), cap)
             moved = pl
         else:
@@ -862,7 +889,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     barrier()
     sec = (time.perf_counter() - t0) / reps
     s2p.close(); ws.close()
-    t = torch.tensor([sec, float(pl), float(nb + moved * 16), float(tl + pl * 16 + kept * 16 + nnz * 12)], dtype=torch.float64, device=dev)
+    t = torch.tensor([sec, float(pl), float(nb + moved * 16), float(tl + pl * 16 + (0 if DEDUP_SEQ else kept * 16) + nnz * 12)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
@@ -872,7 +899,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     return {"value": pl_all / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "read_groups_per_gpu": E, "host_numa": numa, "ms_per_step": sec * 1e3, "phases_ms_rank0": {k: v / reps for k, v in phases.items()},
             "api": "mk_s2p_push/pull/pull_packed/finish from pinned host buffers" +
-                   (" + mk_pairs_dedup_bin_host" if world == 1 else " + H2D of the packed pairs, mk_xchg_* exchange over NVLink, mk_pairs_dedup_bin_device, D2H of kept pairs and COO") +
+                   (" (cfg.rmdup) + H2D of the packed pairs, mk_pairs_bin_device, D2H of the COO" if DEDUP_SEQ else " + mk_pairs_dedup_bin_host" if world == 1 else " + H2D of the packed pairs, mk_xchg_* exchange over NVLink, mk_pairs_dedup_bin_device, D2H of kept pairs and COO") +
                    "; wall clock incl. all copies, max over ranks"}
 
 

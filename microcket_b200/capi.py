@@ -318,7 +318,7 @@ class Sam2Pairs:
         ms = (C.c_double * 8)()
         cnt = (C.c_uint64 * 8)()
         self.lib.check(self.lib.L.mk_s2p_kernel_times(self.h, ms, cnt))
-        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index", "k_rmdup")) if cnt[k] or k < 6}
+        return {n: (ms[k], cnt[k]) for k, n in enumerate(("k_scan_chunks", "k_parse", "k_group", "k_emit", "k_copy_sam", "k_chunk_index", "k_rmdup"))}
 
     def push_ptr(self, ptr, n, is_last=False):
         """push() from a raw host pointer (e.g. a pinned torch tensor): no Python-side copy."""

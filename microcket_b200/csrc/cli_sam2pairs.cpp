@@ -7,6 +7,9 @@
 // `LANG=C sort -k2,2d -k4,4d -k3,3n -k5,5n` (microcket:480,484,502,506), so that sort becomes a pass-through;
 // `sorted-dedup` also removes coordinate duplicates first (first occurrence wins).  Pairs, their text and the line offsets
 // then stay in HBM until the end of the input (mk_s2p_run_device + mk_pairs_sort_text_device).
+// Extension (MICROCKET_RMDUP=1 or =k,s,K,S): krmdup's duplicate removal (src/preprocess/krmdup.cpp) is taken on the SAM,
+// before grouping, so a driver may skip its FASTQ krmdup step; krmdup's four log lines are appended to <out.prefix>.rmdup.log
+// (the file `krmdup -o $sid.rmdup` writes, microcket:413,445).  MICROCKET_RMDUP_PAIRS sizes the key table (read pairs).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -152,8 +155,21 @@ int main(int argc, char *argv[]) {
     if (!outmode.empty() && outmode != "sorted" && outmode != "sorted-dedup") { cerr << "Error: Unknown output mode, must be 'sorted' or 'sorted-dedup'.\n"; return 6; }
     if (!outmode.empty()) { cfg.emit_packed = 1; if (!cfg.window_bytes) cfg.window_bytes = (size_t)1020 << 20; }
 
+    if (const char *r = getenv("MICROCKET_RMDUP")) {
+        if (r[0] && r[0] != '0') {
+            cfg.rmdup = 1;
+            int a, b, c, d;
+            if (sscanf(r, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { cfg.hskip1 = a; cfg.klen1 = b; cfg.hskip2 = c; cfg.klen2 = d; }
+            if (cfg.klen1 + cfg.klen2 < 16 || cfg.klen1 + cfg.klen2 > 32) { cerr << "ERROR: key size must be larger than 16 and smaller than 32!\n"; return 1; }   // krmdup.cpp:256-262
+            cfg.rmdup_capacity = getenv("MICROCKET_RMDUP_PAIRS") ? strtoull(getenv("MICROCKET_RMDUP_PAIRS"), NULL, 10) : (uint64_t)1 << 27;
+        }
+    }
     FILE *fin = fopen(argv[1], "rb");
     if (!fin) { cerr << "Error: read input file failed!\n"; return 10; }
+    if (cfg.rmdup && !getenv("MICROCKET_RMDUP_PAIRS")) {                  // a regular file: no more read pairs than bytes / 128
+        if (fseek(fin, 0, SEEK_END) == 0) { long sz = ftell(fin); if (sz > 0) cfg.rmdup_capacity = (uint64_t)sz / 128 + 1024; }
+        fseek(fin, 0, SEEK_SET);
+    }
     string base = string(argv[3]) + "." + argv[2];
     FILE *fsam = NULL;
     if (cfg.write_sam) {
@@ -198,6 +214,13 @@ int main(int argc, char *argv[]) {
     flog << "lowMap\t" << st.lowMap << "\nmanyHits\t" << st.manyHits << "\nunpaired\t" << st.unpaired << "\nselfCircle\t" << st.selfCircle
          << "\ntrans\t" << st.trans << "\ncis10K\t" << st.cis10K << "\ncis1K\t" << st.cis1K << "\ncis0\t" << st.cis0 << '\n';
     flog.close();
+    if (cfg.rmdup) {
+        mk_dedup_stats dd;
+        if (mk_s2p_rmdup_stats(ctx, &dd) != MK_OK) return fail("sam2pairs");
+        ofstream fr((string(argv[3]) + ".rmdup.log").c_str(), ios::app);                          // krmdup.cpp:375-390 appends
+        if (fr.fail()) { cerr << "Error: write log file failed!\n"; return 10; }
+        fr << "Total\t" << (dd.uniq + dd.dup + dd.discard) << "\nUniq\t" << dd.uniq << "\nDup\t" << dd.dup << "\nDiscard\t" << dd.discard << '\n';
+    }
     mk_destroy(ctx);
     return 0;
 }

@@ -1198,7 +1198,9 @@ static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
     for (u32 i0 = blockIdx.x * 256u; i0 < n; i0 += gridDim.x * 256u) {
         const u32 i = i0 + threadIdx.x;
         const u32 stat = i < n ? p.rm_run[i] : RM_NOTHEAD;
-        if (stat >= RM_DISCARD) {
+        if (stat >= RM_INCOMPLETE) {
+            // a run cut by the window end is decided in the next window; until then its lines do not count as kept, so that the
+            // group before it stays the window's last (carried) group: it may yet turn out to be the stream's last one
             bool keep = false;
             if (stat >= RM_VALID) {
                 const u32 tag = stat & 1u;
@@ -1216,7 +1218,7 @@ static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
                 }
                 keep = first == g0 + i;
             }
-            if (g0 + i >= counted) { ++c_tot; if (keep) ++c_uniq; else if (stat == RM_DISCARD) ++c_disc; }
+            if (g0 + i >= counted && stat != RM_INCOMPLETE) { ++c_tot; if (keep) ++c_uniq; else if (stat == RM_DISCARD) ++c_disc; }
             if (!keep) {
                 u32 j = i;
                 do { const u32 m = p.lmeta[j]; if (m & LM_KEEP) p.lmeta[j] = (u8)(m & ~LM_KEEP); ++j; } while (j < n && (p.lmeta[j] & LM_EQ));

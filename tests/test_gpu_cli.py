@@ -152,3 +152,26 @@ def test_sam2pairs_sorted_output_modes(tmp_path, oracle, mode, outmode):
     assert (tmp_path / f"S.{mode}.sam").read_bytes() == osam
     assert subprocess.run([os.path.join(BIN, "sam2pairs"), str(src), mode, str(tmp_path / "T"), "8", "0.5", "10", "no", "bogus"],
                           capture_output=True, cwd=tmp_path).returncode == 6
+
+
+@pytest.mark.parametrize("outmode", ["", "sorted"])
+def test_sam2pairs_cli_rmdup(tmp_path, oracle, outmode):
+    """MICROCKET_RMDUP=1: krmdup's decisions taken on the SAM (both the streaming and the device-resident chunked path of the
+    executable), krmdup's log lines appended to <prefix>.rmdup.log"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sam_rmdup_oracle as R
+    n = 30000
+    sam = mk.synth_host(57, "unc", "hg38", 0, n, mk.synth_opts(dup_per_1024=150, dup_universe=n))
+    fq, _ = R.sam_to_fastq(sam)
+    r1, _, dd = oracle.krmdup(fq)
+    op, osam, ost = oracle.sam2pairs(R.filter_sam(sam, R.kept_runs(r1)), "unc", threads=8)
+    src = tmp_path / "in.sam"; src.write_bytes(sam)
+    (tmp_path / "g.rmdup.log").write_bytes(b"Total\t1\n")             # appended to, like krmdup's own log
+    env = dict(os.environ, MICROCKET_RMDUP="1", MICROCKET_CHUNK_MB="8")
+    r = run([os.path.join(BIN, "sam2pairs"), str(src), "unc", str(tmp_path / "g"), "8", "0.5", "10", "yes"] + ([outmode] if outmode else []), env=env)
+    assert r.returncode == 0, r.stderr
+    assert (r.stdout == sort_pairs(op)) if outmode else (r.stdout == op)
+    assert (tmp_path / "g.unc2pairs.log").read_bytes() == ost.log_text()
+    assert sort_lines((tmp_path / "g.unc.sam").read_bytes()) == sort_lines(osam)
+    assert (tmp_path / "g.rmdup.log").read_bytes() == b"Total\t1\n" + dd.log_text()

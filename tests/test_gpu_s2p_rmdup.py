@@ -94,3 +94,25 @@ def test_reference_binaries(oracle, ref_bin):
     p, so, st, dd = gpu(sam, "unc")
     assert dd.log_text() == log
     assert st.log_text() == rlog and sort_pairs(p) == rp and sort_lines(so) == rsam
+
+
+@pytest.mark.parametrize("mode", ["unc", "flash"])
+def test_stream_ends_with_a_duplicate(oracle, mode):
+    """The stream's last read pair is a duplicate and arrives in a push of its own: the group before it is then the stream's
+    last kept group, which sam2pairs never processes (pairutil.h:176) - it must not have been emitted earlier."""
+    sam = mk.synth_host(8, mode, "hg38", 0, 3000)
+    rs, lines = R.runs(sam)
+    a, n, _ = rs[5]
+    tail = b"".join(b"LAST" + ln[ln.index(b"\t"):] + b"\n" for ln in lines[a:a + n])
+    whole = sam + tail
+    e = expected(oracle, whole, mode)
+    assert e[3].dup == 1
+    for window in (0, 1 << 16):
+        s = mk.Sam2Pairs(mk.S2PConfig(mode=mode, threads=8, write_sam=True, window_bytes=window, rmdup=True, rmdup_capacity=1 << 16))
+        try:
+            s.push(sam, False); s.push(tail, False); s.push(b"", True)
+            p, so = s.pull()
+            st = s.finish()
+            same((p, so, st, s.rmdup_stats()), e)
+        finally:
+            s.close()
