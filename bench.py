@@ -447,8 +447,10 @@ def run_krmdup(args):
     W = 256 << 20
     n1, n2 = C.c_size_t(), C.c_size_t()
 
+    kd = mk.Krmdup(device=local, window_bytes=W)           # one context: reset() between steps = a new krmdup process (empty key sets)
+
     def once():
-        kd = mk.Krmdup(device=local, window_bytes=W)
+        kd.reset()
         L = kd.lib.L
         a = b = 0
         off = 0
@@ -464,7 +466,6 @@ def run_krmdup(args):
             if off >= nb:
                 break
         stt = kd.finish()
-        kd.close()
         return stt, a + b
 
     def barrier():

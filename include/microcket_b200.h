@@ -167,11 +167,15 @@ typedef struct mk_dedup_stats_s { uint32_t uniq, dup, discard; uint64_t pairs; }
 
 void mk_dedup_default_cfg(mk_dedup_cfg *);
 int  mk_dedup_create(const mk_dedup_cfg *, mk_ctx **);
+/* Pageable memory is copied before the call returns.  Memory that is already pinned (cudaHostAlloc / cudaHostRegister) is
+ * DMA'd straight from the caller's buffer and its unconsumed tail (krmdup works in whole 65 536-pair batches) is left
+ * there until the next call: it must stay valid and unchanged until mk_dedup_finish returns. */
 int  mk_dedup_push(mk_ctx *, const char *fq_bytes, size_t n, int is_last);
 /* read1/read2 records of kept pairs in the reference's file order (per 65 536-pair batch: buckets A,C,G,T;
  * krmdup.cpp:216-226).  For krmdup.pipe interleave the two streams record by record. */
 int  mk_dedup_pull(mk_ctx *, char *r1_out, size_t cap1, size_t *n1, char *r2_out, size_t cap2, size_t *n2);
 int  mk_dedup_finish(mk_ctx *, mk_dedup_stats *);
+int  mk_dedup_reset(mk_ctx *);   /* a new krmdup process on the same allocations: empty key sets, zero counters */
 /* Device-resident key path: 64-bit krmdup keys (or any 64-bit keys) already in HBM.
  * keep[i] = 1 iff key i is the first occurrence in index order.  d_keep: n bytes on the device. */
 int  mk_dedup_keys_device(int device, const uint64_t *d_keys, size_t n, uint8_t *d_keep,

@@ -118,7 +118,7 @@ class Lib:
         L.mk_synth_device_ex.argtypes = [i, u64, i, i, P(SynthOpts), u64, u64, vp, sz, P(sz), vp]
         for name, args in (("mk_dedup_default_cfg", [P(DedupCfg)]), ("mk_dedup_create", [P(DedupCfg), P(vp)]),
                            ("mk_dedup_push", [vp, C.c_char_p, sz, i]), ("mk_dedup_pull", [vp, vp, sz, P(sz), vp, sz, P(sz)]),
-                           ("mk_dedup_finish", [vp, P(DedupStats)]),
+                           ("mk_dedup_finish", [vp, P(DedupStats)]), ("mk_dedup_reset", [vp]),
                            ("mk_dedup_keys_device", [i, vp, sz, vp, P(u64), vp]),
                            ("mk_pairs_ws_create", [i, sz, P(vp)]), ("mk_pairs_ws_destroy", [vp]),
                            ("mk_pairs_dedup_device", [vp, vp, sz, P(sz), vp]),
@@ -372,6 +372,9 @@ class Krmdup:
             o1.append(self._b1.raw[:n1.value])
             o2.append(self._b2.raw[:n2.value])
         return b"".join(o1), b"".join(o2)
+
+    def reset(self):
+        self.lib.check(self.lib.L.mk_dedup_reset(self.h))
 
     def finish(self) -> DedupStats:
         st = DedupStats()

@@ -1,8 +1,11 @@
 // cli_pairs2bins.cpp — contact binning of a .pairs file on the GPU (new tool; stands where the driver calls
 // `java -jar juicer_tools.jar pre -r <res,...> <sid>.final.pairs <sid>.hic <genome>.info`, microcket:525-529).
-//   pairs2bins [-d] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>
+//   pairs2bins [-d] [-b] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>
 // Writes <out.prefix>.<res>.coo with `bin1<TAB>bin2<TAB>count` (upper triangle, sorted), bins numbered in .info order with
 // bin = offset[chr] + pos / res.  -d removes coordinate duplicates first (first occurrence wins).
+// -b also writes <out.prefix>.<res>.bins.bed (`chrom<TAB>start<TAB>end`, one line per bin id): the pair of files is what
+// `cooler load -f coo <bins.bed> <coo> out.cool` takes, i.e. the hand-over point to the .cool branch of the driver
+// (microcket:531-551) without `cooler cload pairs` re-reading and re-binning the pairs.
 // The file is streamed in 256 MiB chunks from pinned memory and PARSED ON THE GPU (mk_pairs_parse_text_device); resolutions
 // whose upper triangle fits MICROCKET_DENSE_MB (default 4096) all come from one pass of the dense histogram (mk_hist_*), the
 // finer ones from the sort path.  Writing .hic itself is out of scope.
@@ -32,15 +35,16 @@ static int write_coo(const string &path, const void *d_b1, const void *d_b2, con
 }
 
 int main(int argc, char *argv[]) {
-    bool dedup = false; string reslist;
+    bool dedup = false, bins_bed = false; string reslist;
     int a = 1;
     while (a < argc && argv[a][0] == '-' && argv[a][1]) {
         if (!strcmp(argv[a], "-d")) { dedup = true; ++a; }
+        else if (!strcmp(argv[a], "-b")) { bins_bed = true; ++a; }
         else if (!strcmp(argv[a], "-r") && a + 1 < argc) { reslist = argv[a + 1]; a += 2; }
         else break;
     }
     if (argc - a < 3 || reslist.empty()) {
-        cerr << "\nUsage: " << argv[0] << " [-d] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>\n\n";
+        cerr << "\nUsage: " << argv[0] << " [-d] [-b] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>\n\n";
         return 2;
     }
     vector<uint32_t> res;
@@ -51,6 +55,17 @@ int main(int argc, char *argv[]) {
       string n; uint32_t l; while (fi >> n >> l) { names.push_back(n); chr_len.push_back(l); } }
     if (names.empty()) { cerr << "Error: no chromosomes in " << argv[a + 2] << "\n"; return 10; }
     vector<const char *> cnames; for (auto &s : names) cnames.push_back(s.c_str());
+    if (bins_bed) for (uint32_t r : res) {                                // bin id = line number: chromosomes in .info order, pos / res
+        const string path = string(argv[a + 1]) + "." + to_string(r) + ".bins.bed";
+        FILE *fb = fopen(path.c_str(), "w");
+        if (!fb) { cerr << "Error: cannot write " << path << "\n"; return 10; }
+        for (size_t c = 0; c < names.size(); ++c)
+            for (uint64_t s0 = 0; s0 <= chr_len[c]; s0 += r) {           // pos / res of a 1-based pos <= len: bins 0 .. len / res
+                const uint64_t e0 = s0 + r < (uint64_t)chr_len[c] + 1 ? s0 + r : (uint64_t)chr_len[c] + 1;
+                fprintf(fb, "%s\t%llu\t%llu\n", names[c].c_str(), (unsigned long long)s0, (unsigned long long)e0);
+            }
+        fclose(fb);
+    }
     FILE *fp = strcmp(argv[a], "-") ? fopen(argv[a], "rb") : stdin;
     if (!fp) { cerr << "Error: cannot read " << argv[a] << "\n"; return 10; }
     const int dev = getenv("MICROCKET_DEVICE") ? atoi(getenv("MICROCKET_DEVICE")) : 0;

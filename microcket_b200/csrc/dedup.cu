@@ -247,9 +247,10 @@ struct DedupCtx : mk_ctx {
     DevBuf d_in, d_state, d_nl, d_desc, d_rec0, d_rec1, d_cls, d_eoff, d_btab, d_ldesc, d_out1, d_out2;
     DevBuf d_hset[2]; u64 hslots[2] = {0, 0}; u64 hcount[2] = {0, 0};
     RadixWs rws;
-    PinBuf h_in, h_out1, h_out2;                   // pinned: the window being filled by push(); the last window's kept records
+    PinBuf h_in;                                   // pinned: the window being filled by push() (input that is already pinned is DMA'd from the caller's memory)
     size_t fill = 0;                               // bytes of h_in filled so far
-    size_t ho_len[2] = {0, 0}, ho_off[2] = {0, 0}; // undrained part of h_out1 / h_out2
+    const char *ext_ptr = nullptr; size_t ext_len = 0;   // unconsumed tail of the last push, still in the caller's PINNED memory (fill == 0 then)
+    size_t ho_len[2] = {0, 0}, ho_off[2] = {0, 0}; // undrained part of d_out1 / d_out2: the last window's kept records stay on the device until pulled
     bool finished = false;
     std::deque<std::vector<char>> q1, q2; size_t q1_off = 0, q2_off = 0;
     u64 pairs_total = 0;
@@ -310,7 +311,7 @@ extern "C" int mk_dedup_create(const mk_dedup_cfg *cfg, mk_ctx **out) {
     A(c->d_ldesc.alloc((size_t)c->n_tiles_cap * 4 * 8)); A(c->d_out1.alloc(c->W + 64)); A(c->d_out2.alloc(c->W + 64));
     A(c->rws.alloc(c->cap_pairs));
     if (trace) fprintf(stderr, "[krmdup create] + device buffers %.3f s\n", dd_now() - t_start);
-    A(c->h_in.alloc(c->W + 64)); A(c->h_out1.alloc(c->W + 64)); A(c->h_out2.alloc(c->W + 64));
+    A(c->h_in.alloc(c->W + 64));
     if (trace) fprintf(stderr, "[krmdup create] + pinned buffers %.3f s\n", dd_now() - t_start);
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
@@ -331,9 +332,27 @@ static int dd_check(mk_ctx *x, DedupCtx **c) {
     return MK_OK;
 }
 
-// one window: `n` bytes of complete lines already in h_in; returns bytes consumed (whole batches unless last)
-static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
+static bool dd_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// one window of complete lines: the first n_stage bytes of h_in followed by n_direct bytes DMA'd straight from `direct`
+// (caller memory that is already pinned); returns bytes consumed (whole batches unless last)
+static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_direct, bool is_last, size_t *consumed) {
     cudaStream_t s = c->s;
+    const size_t n = n_stage + n_direct;
+    // kept records of the previous window that nobody pulled yet: off the device before the kernels overwrite them
+    for (int w = 0; w < 2; ++w) {
+        if (c->ho_off[w] < c->ho_len[w]) {
+            std::vector<char> v(c->ho_len[w] - c->ho_off[w]);
+            MK_CUDA(cudaMemcpyAsync(v.data(), (w ? c->d_out2 : c->d_out1).as<char>() + c->ho_off[w], v.size(), cudaMemcpyDeviceToHost, s));
+            MK_CUDA(cudaStreamSynchronize(s));
+            (w ? c->q2 : c->q1).emplace_back(std::move(v));
+        }
+        c->ho_len[w] = c->ho_off[w] = 0;
+    }
     const bool trace = getenv("MICROCKET_TRACE") != nullptr;
     const double t0 = dd_now();
     // the window can insert at most one key per pair into EITHER set (tag 1 = lower-case first key base, e.g. soft-masked
@@ -352,7 +371,8 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     for (int w = 0; w < 2; ++w) { p.hset[w] = c->d_hset[w].as<u64>(); p.hmask[w] = c->hslots[w] - 1; }
     p.out1 = c->d_out1.as<char>(); p.out2 = c->d_out2.as<char>(); p.out_cap = c->W;
     p.hskip1 = c->cfg.hskip1; p.klen1 = c->cfg.klen1; p.hskip2 = c->cfg.hskip2; p.klen2 = c->cfg.klen2;
-    MK_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, n, cudaMemcpyHostToDevice, s));
+    if (n_stage) MK_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, n_stage, cudaMemcpyHostToDevice, s));
+    if (n_direct) MK_CUDA(cudaMemcpyAsync(c->d_in.as<char>() + n_stage, direct, n_direct, cudaMemcpyHostToDevice, s));
     k_fq_begin<<<(c->n_desc + 255) / 256, 256, 0, s>>>(p, c->n_desc, n, is_last ? 1u : 0u);
     int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fq_scan, S2P_SCAN_THREADS, 4 * 8192);
     k_fq_scan<<<c->sms * std::max(1, std::min(occ, 4)), S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
@@ -386,21 +406,10 @@ static int dd_window(DedupCtx *c, size_t n, bool is_last, size_t *consumed) {
     c->hcount[0] += hst.inserted[0]; c->hcount[1] += hst.inserted[1];
     MK_CUDA(cudaMemsetAsync((char *)c->d_state.p + offsetof(FqState, inserted), 0, 8, s));
     c->pairs_total += np;
-    // kept records: DMA into the pinned output buffers; whatever the caller has not pulled from the previous window is
-    // moved to the overflow queues first (only when several windows are pushed between two pulls)
-    for (int w = 0; w < 2; ++w) {
-        if (c->ho_off[w] < c->ho_len[w]) {
-            const char *src = (w ? c->h_out2 : c->h_out1).as<char>() + c->ho_off[w];
-            (w ? c->q2 : c->q1).emplace_back(src, src + (c->ho_len[w] - c->ho_off[w]));
-        }
-        c->ho_len[w] = c->ho_off[w] = 0;
-    }
-    if (hst.out1) MK_CUDA(cudaMemcpyAsync(c->h_out1.p, c->d_out1.p, hst.out1, cudaMemcpyDeviceToHost, s));
-    if (hst.out2) MK_CUDA(cudaMemcpyAsync(c->h_out2.p, c->d_out2.p, hst.out2, cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaStreamSynchronize(s));
+    // the kept records stay in d_out1 / d_out2 until mk_dedup_pull copies them straight into the caller's buffers
     c->ho_len[0] = hst.out1; c->ho_len[1] = hst.out2;
-    if (trace) fprintf(stderr, "[krmdup window] %zu bytes, %llu pairs: h2d+scan+keys %.1f ms, sort+mark+layout+copy %.1f ms, d2h %.1f ms\n",
-                       n, (unsigned long long)np, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (dd_now() - t2) * 1e3);
+    if (trace) fprintf(stderr, "[krmdup window] %zu bytes (%zu staged), %llu pairs: h2d+scan+keys %.1f ms, sort+mark+layout+copy %.1f ms\n",
+                       n, n_stage, (unsigned long long)np, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
     return MK_OK;
 }
 
@@ -408,11 +417,36 @@ extern "C" int mk_dedup_push(mk_ctx *x, const char *bytes, size_t n, int is_last
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     if (c->finished) { mk_set_error("mk_dedup_push after the last chunk"); return MK_ERR_STATE; }
     char *h = c->h_in.as<char>();
+    bool pinned = n >= (1u << 20) && dd_ptr_is_pinned(bytes);
+    if (c->ext_len) {
+        // the tail the last push left in the caller's pinned memory: one region with this push when it continues it (a caller
+        // walking through one big pinned buffer), else it moves to the staging buffer now
+        if (pinned && bytes == c->ext_ptr + c->ext_len) { bytes = c->ext_ptr; n += c->ext_len; }
+        else { memcpy(h, c->ext_ptr, c->ext_len); c->fill = c->ext_len; }
+        c->ext_len = 0; c->ext_ptr = nullptr;
+    }
     size_t off = 0;
     while (true) {
         const size_t take = std::min(c->W - c->fill, n - off);
+        const bool final_chunk = is_last && off + take == n;
+        if (pinned && !is_last && c->fill == 0 && n - off < c->W) {     // not a window's worth: it stays where it is until the next push
+            c->ext_ptr = bytes + off; c->ext_len = n - off;
+            break;
+        }
+        // pinned caller memory: the window is [what h_in holds][bytes + off, + take), the second part DMA'd in place
+        if (pinned && take && c->fill + take == c->W && !final_chunk) {
+            const void *nl = memrchr(bytes + off, '\n', take);
+            if (nl) {
+                const size_t nd = (size_t)((const char *)nl - (bytes + off)) + 1, staged = c->fill;
+                size_t consumed = 0;
+                MK_TRY(dd_window(c, staged, bytes + off, nd, false, &consumed));
+                if (consumed == 0) { mk_set_error("krmdup: one 65 536-pair batch does not fit the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
+                if (consumed >= staged) { off += consumed - staged; c->fill = 0; }
+                else { memmove(h, h + consumed, staged - consumed); c->fill = staged - consumed; }     // (a batch never ends inside the staged part in practice)
+                continue;
+            }
+        }
         if (take) { memcpy(h + c->fill, bytes + off, take); c->fill += take; off += take; }
-        const bool final_chunk = is_last && off == n;
         if (c->fill < c->W && !final_chunk) break;                       // wait for more input
         if (c->fill == 0) break;
         if (final_chunk && h[c->fill - 1] != '\n') h[c->fill++] = '\n';   // getline accepts a last line without '\n' (room: W + 64)
@@ -423,7 +457,7 @@ extern "C" int mk_dedup_push(mk_ctx *x, const char *bytes, size_t n, int is_last
             len = (size_t)((const char *)nl - h) + 1;
         }
         size_t consumed = 0;
-        MK_TRY(dd_window(c, len, final_chunk, &consumed));
+        MK_TRY(dd_window(c, len, nullptr, 0, final_chunk, &consumed));
         if (final_chunk) { c->fill = 0; break; }
         if (consumed == 0) { mk_set_error("krmdup: one 65 536-pair batch does not fit the window (%zu bytes)", c->W); return MK_ERR_CAPACITY; }
         memmove(h, h + consumed, c->fill - consumed);                    // whole batches only: the rest opens the next window
@@ -448,11 +482,33 @@ static size_t dd_drain(std::deque<std::vector<char>> &q, size_t &qoff, char *out
 extern "C" int mk_dedup_pull(mk_ctx *x, char *r1, size_t cap1, size_t *n1, char *r2, size_t cap2, size_t *n2) {
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     size_t a = dd_drain(c->q1, c->q1_off, r1, cap1), b = dd_drain(c->q2, c->q2_off, r2, cap2);
-    // then the last window's records, straight from the pinned buffers
-    if (r1 && c->q1.empty() && a < cap1) { const size_t m = std::min(cap1 - a, c->ho_len[0] - c->ho_off[0]); memcpy(r1 + a, c->h_out1.as<char>() + c->ho_off[0], m); a += m; c->ho_off[0] += m; }
-    if (r2 && c->q2.empty() && b < cap2) { const size_t m = std::min(cap2 - b, c->ho_len[1] - c->ho_off[1]); memcpy(r2 + b, c->h_out2.as<char>() + c->ho_off[1], m); b += m; c->ho_off[1] += m; }
+    // then the last window's records, from the device straight into the caller's buffers (both copies in flight together)
+    bool copied = false;
+    if (r1 && c->q1.empty() && a < cap1) {
+        const size_t m = std::min(cap1 - a, c->ho_len[0] - c->ho_off[0]);
+        if (m) { MK_CUDA(cudaMemcpyAsync(r1 + a, c->d_out1.as<char>() + c->ho_off[0], m, cudaMemcpyDeviceToHost, c->s)); copied = true; }
+        a += m; c->ho_off[0] += m;
+    }
+    if (r2 && c->q2.empty() && b < cap2) {
+        const size_t m = std::min(cap2 - b, c->ho_len[1] - c->ho_off[1]);
+        if (m) { MK_CUDA(cudaMemcpyAsync(r2 + b, c->d_out2.as<char>() + c->ho_off[1], m, cudaMemcpyDeviceToHost, c->s)); copied = true; }
+        b += m; c->ho_off[1] += m;
+    }
+    if (copied) MK_CUDA(cudaStreamSynchronize(c->s));
     if (n1) *n1 = a;
     if (n2) *n2 = b;
+    return MK_OK;
+}
+
+// Forget the stream (key sets, counters, pending output) but keep every allocation: the context then stands for a new krmdup process.
+extern "C" int mk_dedup_reset(mk_ctx *x) {
+    DedupCtx *c; MK_TRY(dd_check(x, &c));
+    MK_CUDA(cudaStreamSynchronize(c->s));
+    MK_CUDA(cudaMemsetAsync(c->d_state.p, 0, sizeof(FqState), c->s));
+    for (int w = 0; w < 2; ++w) { MK_CUDA(cudaMemsetAsync(c->d_hset[w].p, 0xFF, c->hslots[w] * 8, c->s)); c->hcount[w] = 0; c->ho_len[w] = c->ho_off[w] = 0; }
+    MK_CUDA(cudaStreamSynchronize(c->s));
+    c->fill = 0; c->ext_ptr = nullptr; c->ext_len = 0; c->finished = false; c->pairs_total = 0;
+    c->q1.clear(); c->q2.clear(); c->q1_off = c->q2_off = 0;
     return MK_OK;
 }
 

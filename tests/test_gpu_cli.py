@@ -90,7 +90,7 @@ def test_pairs2bins_cli(tmp_path, oracle):
              "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
     from test_gpu_pairs import HG38_LEN
     info = tmp_path / "hg38.info"; info.write_text("".join(f"{n}\t{l}\n" for n, l in zip(names, HG38_LEN)))
-    r = run([os.path.join(BIN, "pairs2bins"), "-d", "-r", "1000000,5000", str(pf), str(tmp_path / "out"), str(info)])
+    r = run([os.path.join(BIN, "pairs2bins"), "-d", "-b", "-r", "1000000,5000", str(pf), str(tmp_path / "out"), str(info)])
     assert r.returncode == 0, r.stderr
     pairs, n = oracle.pairs_parse(op, names)
     keep, kept = oracle.coord_dedup(pairs, n)
@@ -98,6 +98,13 @@ def test_pairs2bins_cli(tmp_path, oracle):
         b1, b2, ct = oracle.bin_coo(pairs, n, keep, HG38_LEN, res)
         exp = "".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1, b2, ct))
         assert (tmp_path / f"out.{res}.coo").read_text() == exp
+        # -b: the bin table `cooler load -f coo` needs: line k = bin id k, chromosomes in .info order, bin = pos / res
+        bed = [ln.split("\t") for ln in (tmp_path / f"out.{res}.bins.bed").read_text().splitlines()]
+        assert len(bed) == sum(l // res + 1 for l in HG38_LEN) and max(b2) < len(bed)
+        off = 0
+        for nme, l in zip(names, HG38_LEN):
+            assert bed[off] == [nme, "0", str(min(res, l + 1))] and bed[off + l // res] == [nme, str(l // res * res), str(l + 1)]
+            off += l // res + 1
 
 
 def test_pairs2bins_default_resolution_list_streamed_and_odd_lines(tmp_path, oracle):

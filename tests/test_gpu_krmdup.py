@@ -86,3 +86,28 @@ def test_all_lowercase_reads_fill_the_second_key_set(oracle):
     r1, r2, st = gpu_krmdup(low)
     assert r1 == o1 and r2 == o2 and st.log_text() == ost.log_text()
     assert st.uniq > 100000
+
+
+def test_reset_and_pinned_input(oracle):
+    """mk_dedup_reset = a new krmdup process on the same context; input from one big PINNED buffer pushed piece by piece (DMA'd
+    in place, the unconsumed tail of a piece stays in the caller's memory until the next push) gives the same bytes"""
+    import ctypes as C
+    import torch
+    fq = mk.synth_host(91, "fastq", "hg38", 0, 300000)
+    e1, e2, est = oracle.krmdup(fq)
+    host = torch.frombuffer(bytearray(fq), dtype=torch.uint8).pin_memory()
+    kd = mk.Krmdup(window_bytes=64 << 20)             # a 65 536-pair batch is ~39 MB
+    try:
+        for piece in (64 << 20, 50_000_000):
+            kd.reset()
+            o1, o2 = [], []
+            for off in range(0, len(fq), piece):
+                m = min(piece, len(fq) - off)
+                kd.lib.check(kd.lib.L.mk_dedup_push(kd.h, C.cast(host.data_ptr() + off, C.c_char_p), m, int(off + m == len(fq))))
+                a, b = kd.pull(); o1.append(a); o2.append(b)
+            st = kd.finish()
+            a, b = kd.pull(); o1.append(a); o2.append(b)
+            assert b"".join(o1) == e1 and b"".join(o2) == e2
+            assert (st.uniq, st.dup, st.discard) == (est.uniq, est.dup, est.discard)
+    finally:
+        kd.close()
