@@ -308,7 +308,7 @@ extern "C" int mk_dedup_create(const mk_dedup_cfg *cfg, mk_ctx **out) {
     A(c->d_in.alloc(c->W + 64)); A(c->d_state.alloc(sizeof(FqState))); A(c->d_nl.alloc((size_t)c->cap_lines * 4));
     A(c->d_desc.alloc((size_t)c->n_desc * 8)); A(c->d_rec0.alloc((size_t)c->cap_pairs * 16)); A(c->d_rec1.alloc((size_t)c->cap_pairs * 16));
     A(c->d_cls.alloc(c->cap_pairs)); A(c->d_eoff.alloc((size_t)c->cap_pairs * 8)); A(c->d_btab.alloc((size_t)(c->cap_pairs / FQ_BATCH + 4) * 32));
-    A(c->d_ldesc.alloc((size_t)c->n_tiles_cap * 4 * 8)); A(c->d_out1.alloc(c->W + 64)); A(c->d_out2.alloc(c->W + 64));
+    A(c->d_ldesc.alloc((size_t)c->n_tiles_cap * 4 * 8)); A(c->d_out1.alloc(2 * c->W + 64)); A(c->d_out2.alloc(2 * c->W + 64));
     A(c->rws.alloc(c->cap_pairs));
     if (trace) fprintf(stderr, "[krmdup create] + device buffers %.3f s\n", dd_now() - t_start);
     A(c->h_in.alloc(c->W + 64));
@@ -343,8 +343,12 @@ static bool dd_ptr_is_pinned(const void *p) {
 static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_direct, bool is_last, size_t *consumed) {
     cudaStream_t s = c->s;
     const size_t n = n_stage + n_direct;
-    // kept records of the previous window that nobody pulled yet: off the device before the kernels overwrite them
-    for (int w = 0; w < 2; ++w) {
+    // kept records of earlier windows that nobody pulled yet (several windows inside one push): this window's records are
+    // appended behind them while the output buffers (2 W each; a window's output is smaller than its input) have room;
+    // only then are they moved off the device before the kernels overwrite them
+    const bool pending = c->ho_off[0] < c->ho_len[0] || c->ho_off[1] < c->ho_len[1];
+    const bool append = pending && c->ho_len[0] + n <= 2 * c->W && c->ho_len[1] + n <= 2 * c->W;
+    for (int w = 0; w < 2 && !append; ++w) {
         if (c->ho_off[w] < c->ho_len[w]) {
             std::vector<char> v(c->ho_len[w] - c->ho_off[w]);
             MK_CUDA(cudaMemcpyAsync(v.data(), (w ? c->d_out2 : c->d_out1).as<char>() + c->ho_off[w], v.size(), cudaMemcpyDeviceToHost, s));
@@ -369,7 +373,8 @@ static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_d
     p.desc = c->d_desc.as<u64>(); p.rec0 = c->d_rec0.as<uint4>(); p.rec1 = c->d_rec1.as<uint4>(); p.cls = c->d_cls.as<u8>();
     p.eoff = c->d_eoff.as<u32>(); p.btab = c->d_btab.as<u32>();
     for (int w = 0; w < 2; ++w) { p.hset[w] = c->d_hset[w].as<u64>(); p.hmask[w] = c->hslots[w] - 1; }
-    p.out1 = c->d_out1.as<char>(); p.out2 = c->d_out2.as<char>(); p.out_cap = c->W;
+    const size_t base1 = append ? c->ho_len[0] : 0, base2 = append ? c->ho_len[1] : 0;
+    p.out1 = c->d_out1.as<char>() + base1; p.out2 = c->d_out2.as<char>() + base2; p.out_cap = 2 * c->W - std::max(base1, base2);
     p.hskip1 = c->cfg.hskip1; p.klen1 = c->cfg.klen1; p.hskip2 = c->cfg.hskip2; p.klen2 = c->cfg.klen2;
     if (n_stage) MK_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, n_stage, cudaMemcpyHostToDevice, s));
     if (n_direct) MK_CUDA(cudaMemcpyAsync(c->d_in.as<char>() + n_stage, direct, n_direct, cudaMemcpyHostToDevice, s));
@@ -407,7 +412,7 @@ static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_d
     MK_CUDA(cudaMemsetAsync((char *)c->d_state.p + offsetof(FqState, inserted), 0, 8, s));
     c->pairs_total += np;
     // the kept records stay in d_out1 / d_out2 until mk_dedup_pull copies them straight into the caller's buffers
-    c->ho_len[0] = hst.out1; c->ho_len[1] = hst.out2;
+    c->ho_len[0] = base1 + hst.out1; c->ho_len[1] = base2 + hst.out2;
     if (trace) fprintf(stderr, "[krmdup window] %zu bytes (%zu staged), %llu pairs: h2d+scan+keys %.1f ms, sort+mark+layout+copy %.1f ms\n",
                        n, n_stage, (unsigned long long)np, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
     return MK_OK;
@@ -417,6 +422,7 @@ extern "C" int mk_dedup_push(mk_ctx *x, const char *bytes, size_t n, int is_last
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     if (c->finished) { mk_set_error("mk_dedup_push after the last chunk"); return MK_ERR_STATE; }
     char *h = c->h_in.as<char>();
+    const double t_push = dd_now();
     bool pinned = n >= (1u << 20) && dd_ptr_is_pinned(bytes);
     if (c->ext_len) {
         // the tail the last push left in the caller's pinned memory: one region with this push when it continues it (a caller
@@ -464,6 +470,8 @@ extern "C" int mk_dedup_push(mk_ctx *x, const char *bytes, size_t n, int is_last
         c->fill -= consumed;
     }
     if (is_last) c->finished = true;
+    if (getenv("MICROCKET_TRACE")) fprintf(stderr, "[krmdup push] %zu bytes in %.1f ms, %zu staged, %zu left in caller memory, %zu + %zu spilled\n",
+                                           n, (dd_now() - t_push) * 1e3, c->fill, c->ext_len, c->q1.size(), c->q2.size());
     return MK_OK;
 }
 
@@ -494,7 +502,9 @@ extern "C" int mk_dedup_pull(mk_ctx *x, char *r1, size_t cap1, size_t *n1, char 
         if (m) { MK_CUDA(cudaMemcpyAsync(r2 + b, c->d_out2.as<char>() + c->ho_off[1], m, cudaMemcpyDeviceToHost, c->s)); copied = true; }
         b += m; c->ho_off[1] += m;
     }
+    const double t_p = copied && getenv("MICROCKET_TRACE") ? dd_now() : 0;
     if (copied) MK_CUDA(cudaStreamSynchronize(c->s));
+    if (t_p != 0) fprintf(stderr, "[krmdup pull] %zu + %zu bytes to the host in %.1f ms\n", a, b, (dd_now() - t_p) * 1e3);
     if (n1) *n1 = a;
     if (n2) *n2 = b;
     return MK_OK;
