@@ -122,7 +122,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     if (p.rm_on) {
         p.rm_hskip1 = c->cfg.hskip1; p.rm_klen1 = c->cfg.klen1; p.rm_hskip2 = c->cfg.hskip2; p.rm_klen2 = c->cfg.klen2;
         for (int t = 0; t < 2; ++t) { p.rm_tab[t] = c->d_rmtab[t].as<unsigned long long>(); p.rm_mask[t] = c->rm_slots[t] - 1; }
-        p.rm_key = c->d_rmkey.as<unsigned long long>(); p.rm_stat = c->d_rmstat.as<u8>(); p.rm_run = p.rm_stat + c->cap_lines; p.rm_info = c->d_rminfo.as<u32>();
+        p.rm_key = c->d_rmkey.as<unsigned long long>(); p.rm_stat = c->d_rmstat.as<u8>(); p.rm_info = c->d_rminfo.as<u32>();
     }
     p.self = nullptr;
     return p;
@@ -154,8 +154,7 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
         mark(7);
         k_rm_keys<<<c->grid_gs, 256, 0, s>>>(p);
         k_rm_insert<<<c->grid_gs, 256, 0, s>>>(p);
-        k_rm_mark<<<c->grid_gs, 256, 0, s>>>(p);
-        c->launches += 3;
+        c->launches += 2;
     } else k_parse<false><<<c->grid_parse, 256, PR_SMEM, s>>>(p);
     mark(2);
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
@@ -281,7 +280,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
         u64 slots = 1024; while (slots < 2 * cap) slots <<= 1;
         c->rm_slots[0] = slots; c->rm_slots[1] = std::max<u64>(slots >> 4, 1024);
         for (int t = 0; t < 2; ++t) { A(c->d_rmtab[t].alloc(c->rm_slots[t] * 16)); if (rc == MK_OK && cudaMemset(c->d_rmtab[t].p, 0xFF, c->rm_slots[t] * 16) != cudaSuccess) rc = MK_ERR_CUDA; }
-        A(c->d_rmkey.alloc((size_t)c->cap_lines * 16)); A(c->d_rmstat.alloc((size_t)c->cap_lines * 2)); A(c->d_rminfo.alloc((size_t)c->cap_lines * 4));
+        A(c->d_rmkey.alloc((size_t)c->cap_lines * 16)); A(c->d_rmstat.alloc(c->cap_lines)); A(c->d_rminfo.alloc((size_t)c->cap_lines * 4));
     }
 #undef A
     if (rc != MK_OK) { delete c; return rc; }

@@ -107,7 +107,7 @@ struct S2PParams {
     // per-line key / status of the window's QNAME runs
     int rm_on, rm_hskip1, rm_klen1, rm_hskip2, rm_klen2;
     unsigned long long *rm_tab[2]; u64 rm_mask[2];
-    unsigned long long *rm_key; u8 *rm_stat, *rm_run; u32 *rm_info;   // rm_info: K2's (flag | SEQ offset << 16) per line
+    unsigned long long *rm_key; u8 *rm_stat; u32 *rm_info;   // rm_info: K2's (flag | SEQ offset << 16) per line
     unsigned long long *xparts;   // optional: per launched window (end, count) of its packed pairs, for the overlapped multi-GPU scatter
     const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
 };
@@ -1005,11 +1005,6 @@ static __device__ __noinline__ bool qname_equal_abs(const S2PParams &p, u64 pa, 
 // complement.  Runs the reference would not have let through lose LM_KEEP before K3 sees them, so everything downstream
 // (grouping, counters, the 2^18-batch self-circle rule, the dropped last group) is what sam2pairs does on the SAM of the
 // deduplicated FASTQ.  A run without a primary record for a mate counts as discarded.
-#define RM_NOTHEAD 0u
-#define RM_SKIP 1u          // header line
-#define RM_INCOMPLETE 2u    // the run touches the window end: decided in the next window
-#define RM_DISCARD 3u
-#define RM_VALID 4u         // | tag (0 / 1)
 #define RM_EMPTY 0xFFFFFFFFFFFFFFFFull
 // per-line status (rm_stat): which mates the line's SEQ provides and whether their key windows are valid
 #define RL_M1 1u
@@ -1084,19 +1079,24 @@ __device__ __forceinline__ u64 rm_hash(u64 k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return k;
 }
-// slot of `key` (inserted when absent); ~0 when the table is full
-__device__ __forceinline__ u64 rm_slot(unsigned long long *tab, u64 mask, u64 key, bool insert) {
+// slot of `key`, inserted when absent (claimed = this call put it there); ~0 when the table is full
+__device__ __forceinline__ u64 rm_slot(unsigned long long *tab, u64 mask, u64 key, bool &claimed) {
     u64 s = rm_hash(key) & mask;
+    claimed = false;
     for (u64 probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
         unsigned long long cur = *(volatile unsigned long long *)&tab[2 * s];
         if (cur == RM_EMPTY) {
-            if (!insert) return ~0ull;
             cur = atomicCAS(&tab[2 * s], RM_EMPTY, (unsigned long long)key);
-            if (cur == RM_EMPTY) return s;
+            if (cur == RM_EMPTY) { claimed = true; return s; }
         }
         if (cur == key) return s;
     }
     return ~0ull;
+}
+// the lines of the run that starts at line h stop counting as kept
+__device__ __forceinline__ void rm_drop_run(const S2PParams &p, u32 h, u32 n) {
+    u32 j = h;
+    do { const u32 m = p.lmeta[j]; if (m & LM_KEEP) p.lmeta[j] = (u8)(m & ~LM_KEEP); ++j; } while (j < n && (p.lmeta[j] & LM_EQ));
 }
 
 // phase A: one thread per line: the key bits its SEQ gives to mate 1 and / or mate 2 (primary records only)
@@ -1144,20 +1144,27 @@ static __global__ void __launch_bounds__(256) k_rm_keys(S2PParams p) {
     }
 }
 
-// phase B: the thread of a run's first line combines the run's mates into the pair's key and records its first occurrence
+// phase B: the thread of a run's first line combines the run's mates into the pair's key and settles the run on the spot.
+// The table keeps, per key, the smallest global line index seen so far (atomicMin), and the value it held before tells
+// everything: nothing or this very line (a re-parsed run) -> this run is the first occurrence so far; a larger index ->
+// likewise, and the run that index belongs to (necessarily of this window: earlier windows hold smaller indices) is a
+// duplicate after all, so ITS lines are dropped here - every index is handed back to exactly one later, smaller insert;
+// a smaller index -> this run is the duplicate.  No second pass over the table.  Uniq = keys ever claimed.
+// A run cut by the window end is decided in the next window; until then its lines do not count as kept, so that the group
+// before it stays the window's last (carried) group: it may yet turn out to be the stream's last one (pairutil.h:176).
 static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
     WinState *st = p.st;
     const u32 n = st->n_lines;
-    const u64 g0 = st->lines_done;
+    const u64 g0 = st->lines_done, counted = st->rm_counted;
     const bool final_win = (st->we == st->total) && st->is_last;
-    for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        u32 run = RM_NOTHEAD;
-        const u32 m_i = p.lmeta[i];                                     // the three loads of the common case go out together
-        u32 sl = p.rm_stat[i];
-        const ulonglong2 k_i = ((const ulonglong2 *)p.rm_key)[i];
-        if (!(m_i & LM_EQ)) {
-            if (sl & RL_HDR) run = RM_SKIP;
-            else {
+    u32 c_tot = 0, c_uniq = 0, c_disc = 0;
+    for (u32 i0 = blockIdx.x * 256u; i0 < n; i0 += gridDim.x * 256u) {
+        const u32 i = i0 + threadIdx.x;
+        if (i < n) {
+            const u32 m_i = p.lmeta[i];                                 // the three loads of the common case go out together
+            u32 sl = p.rm_stat[i];
+            const ulonglong2 k_i = ((const ulonglong2 *)p.rm_key)[i];
+            if (!(m_i & LM_EQ) && !(sl & RL_HDR)) {
                 u32 have = 0; u64 b1 = 0, b2 = 0;
                 u32 j = i;
                 while (true) {
@@ -1170,58 +1177,26 @@ static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
                     if (j >= n || !(p.lmeta[j] & LM_EQ)) break;
                     sl = p.rm_stat[j];
                 }
-                if (j >= n && !final_win) run = RM_INCOMPLETE;
+                bool keep = false;
+                if (j >= n && !final_win) ;                              // undecided
                 else if ((have & (RL_OK1 | RL_OK2)) == (RL_OK1 | RL_OK2)) {
-                    const u64 key = (b1 << (2 * p.rm_klen2)) | b2;
+                    const u64 key = (b1 << (2 * p.rm_klen2)) | b2, me = g0 + i;
                     const u32 tag = (have & RL_TAG) ? 1u : 0u;
-                    run = RM_VALID | tag;
-                    p.rm_key[2 * (size_t)i] = key;
-                    if (key == RM_EMPTY) atomicMin(&st->rm_allones[tag], (unsigned long long)(g0 + i));
+                    unsigned long long old = 0; bool claimed = false, full = false;
+                    if (key == RM_EMPTY) { old = atomicMin(&st->rm_allones[tag], (unsigned long long)me); claimed = old == RM_EMPTY; }
                     else {
-                        const u64 s = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, true);
-                        if (s == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); run = RM_INCOMPLETE; }
-                        else atomicMin(&p.rm_tab[tag][2 * s + 1], (unsigned long long)(g0 + i));
+                        const u64 s = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, claimed);
+                        if (s == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); full = true; }
+                        else old = atomicMin(&p.rm_tab[tag][2 * s + 1], (unsigned long long)me);
                     }
-                } else run = RM_DISCARD;
-            }
-        }
-        p.rm_run[i] = (u8)run;
-    }
-}
-
-// phase C (after every insert of the window): a run survives iff it is the first occurrence of its key; the others lose LM_KEEP
-static __global__ void __launch_bounds__(256) k_rm_mark(S2PParams p) {
-    WinState *st = p.st;
-    const u32 n = st->n_lines;
-    const u64 g0 = st->lines_done, counted = st->rm_counted;
-    u32 c_tot = 0, c_uniq = 0, c_disc = 0;
-    for (u32 i0 = blockIdx.x * 256u; i0 < n; i0 += gridDim.x * 256u) {
-        const u32 i = i0 + threadIdx.x;
-        const u32 stat = i < n ? p.rm_run[i] : RM_NOTHEAD;
-        if (stat >= RM_INCOMPLETE) {
-            // a run cut by the window end is decided in the next window; until then its lines do not count as kept, so that the
-            // group before it stays the window's last (carried) group: it may yet turn out to be the stream's last one
-            bool keep = false;
-            if (stat >= RM_VALID) {
-                const u32 tag = stat & 1u;
-                const u64 key = p.rm_key[2 * (size_t)i];
-                unsigned long long first = 0;
-                if (key == RM_EMPTY) first = st->rm_allones[tag];
-                else {                                                  // every insert of the window is done: {key, first line} in one load
-                    const u64 mask = p.rm_mask[tag];
-                    u64 sl = rm_hash(key) & mask;
-                    for (u64 probe = 0; probe <= mask; ++probe, sl = (sl + 1) & mask) {
-                        const ulonglong2 e = __ldcg((const ulonglong2 *)p.rm_tab[tag] + sl);
-                        if (e.x == key) { first = e.y; break; }
-                        if (e.x == RM_EMPTY) break;
+                    if (!full) {
+                        keep = old >= me;                                // RM_EMPTY (all ones) included
+                        if (old != RM_EMPTY && old > me) rm_drop_run(p, (u32)(old - g0), n);
+                        if (claimed) ++c_uniq;
+                        if (me >= counted) ++c_tot;
                     }
-                }
-                keep = first == g0 + i;
-            }
-            if (g0 + i >= counted && stat != RM_INCOMPLETE) { ++c_tot; if (keep) ++c_uniq; else if (stat == RM_DISCARD) ++c_disc; }
-            if (!keep) {
-                u32 j = i;
-                do { const u32 m = p.lmeta[j]; if (m & LM_KEEP) p.lmeta[j] = (u8)(m & ~LM_KEEP); ++j; } while (j < n && (p.lmeta[j] & LM_EQ));
+                } else if (g0 + i >= counted) { ++c_tot; ++c_disc; }
+                if (!keep) rm_drop_run(p, i, n);
             }
         }
     }
