@@ -186,6 +186,7 @@ def workload_config(args, world, groups):
                       if DEDUP_SEQ else "coord: (lane, chr1,pos1,s1, chr2,pos2,s2) of the emitted pairs, same sort as the binning"),
             "read_groups_per_gpu": groups, "genome": WL["genome"], "mode": WL["mode"], "resolution": RES, "min_mapq": 10, "min_mapped_ratio": 0.5,
             "seed": SEED, "duplicates": f"{DUP_PER_1024}/1024 of the read groups copy the fragment of another group of the whole job (all shards)", "l2": "inputs (>= 60 GB of SAM text per step at full size) far exceed the 126 MB L2; no flush needed",
+            "lanes": (f"{world} (one krmdup key table per GPU = `microcket -b`: duplicates across lanes are retained, microcket:428-451)" if DEDUP_SEQ else "1 (duplicates are removed across all shards)"),
             "parallelism": f"shard{world}: parse by read chunk, packed pairs to their owner hash(chr1,chr2,pos1/{PART_RES}) by the library's own NVLink peer-memory kernel (MICROCKET_XCHG=nccl: partition + NCCL all-to-all), dedup + COO owner-computes"}
 
 
@@ -340,41 +341,59 @@ def verify_sharded(torch, mk, np, dist, args, world, rank, local):
         # coordinate dedup + binning over the union of the shards' pairs
         orc = oracle_lib.load()
         texts, groups = [], 0
+        if DEDUP_SEQ:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import sam_rmdup_oracle as RM
         for r in range(world):
             sh, nbs = synth_to_device(torch, mk, r * V, V + (1 if r + 1 < world else 0), local, universe)
-            op_r, _, ost_r = orc.sam2pairs(sh[:nbs].cpu().numpy().tobytes(), WL["mode"], threads=8, write_sam=False)
+            sam_r = sh[:nbs].cpu().numpy().tobytes()
+            if DEDUP_SEQ:                          # one krmdup process per shard = per lane (`-b`: duplicates across lanes are retained, microcket:428-451)
+                r1_r, _, _ = orc.krmdup(RM.sam_to_fastq(sam_r)[0])
+                sam_r = RM.filter_sam(sam_r, RM.kept_runs(r1_r))
+            op_r, _, ost_r = orc.sam2pairs(sam_r, WL["mode"], threads=8, write_sam=False)
             texts.append(op_r); groups += ost_r.groups
             del sh
         op = b"".join(texts)
         arr, n = orc.pairs_parse(op, WL["names"])
-        keep, n_keep = orc.coord_dedup(arr, n)
-        b1, b2, ct = orc.bin_coo(arr, n, keep, WL["lens"], RES)
-        exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n][np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
+        if DEDUP_SEQ:
+            keep, n_keep = None, n
+            b1, b2, ct = orc.bin_coo(arr, n, None, WL["lens"], RES)
+            exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n]
+        else:
+            keep, n_keep = orc.coord_dedup(arr, n)
+            b1, b2, ct = orc.bin_coo(arr, n, keep, WL["lens"], RES)
+            exp = np.frombuffer(bytes(arr), dtype=mk.PAIR_DTYPE)[:n][np.frombuffer(bytes(keep), dtype=np.uint8)[:n] == 1]
         checks = {"groups": sum(x[3] for x in all_sizes) == groups, "pairs": sum(x[2] for x in all_sizes) == n,
                   "kept": len(got_pairs) == n_keep and np.array_equal(got_pairs[key(got_pairs)], exp[key(exp)]),
                   "coo": got_coo[:, 0].tolist() == b1 and got_coo[:, 1].tolist() == b2 and got_coo[:, 2].tolist() == ct,
-                  "duplicates_removed": n - n_keep > 0.05 * n}
-        # (b) the single-GPU path over the whole input against the oracle over the whole input (one stream, one dropped group)
-        sam1, nb1 = synth_to_device(torch, mk, 0, universe, local, universe)
-        op1, _, ost1 = orc.sam2pairs(sam1[:nb1].cpu().numpy().tobytes(), WL["mode"], threads=8, write_sam=False)
-        arr1, n1 = orc.pairs_parse(op1, WL["names"])
-        keep1, n_keep1 = orc.coord_dedup(arr1, n1)
-        c1, c2, cc = orc.bin_coo(arr1, n1, keep1, WL["lens"], RES)
-        exp1 = np.frombuffer(bytes(arr1), dtype=mk.PAIR_DTYPE)[:n1][np.frombuffer(bytes(keep1), dtype=np.uint8)[:n1] == 1]
-        one = Pipeline(torch, mk, None, universe, 1, local, 64 << 20)
-        p1, k1, z1 = one.run(sam1, nb1)
-        single = np.frombuffer(one.kept_pairs(k1).cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
-        checks["single_gpu_equals_oracle"] = (p1 == n1 and k1 == n_keep1 and z1 == len(c1) and np.array_equal(single[key(single)], exp1[key(exp1)])
-                                              and one.cnt[:z1].cpu().numpy().astype(np.uint32).tolist() == cc)
-        checks["sharded_vs_unsharded_kept_pairs_differ_by_at_most_world_minus_1"] = abs(len(got_pairs) - k1) <= world - 1
-        one.close()
-        ok = all(checks.values()); why = json.dumps(checks)
-        print(f"[bench] verified {world}-GPU path on {universe} read groups: {why}", file=sys.stderr)
+                  "duplicates_removed": (sum(x[3] for x in all_sizes) < 0.95 * universe) if DEDUP_SEQ else (n - n_keep > 0.05 * n)}
+        if DEDUP_SEQ:                              # lanes are independent by definition: there is no unsharded result to compare with
+            ok = all(checks.values()); why = json.dumps(checks)
+            print(f"[bench] verified {world}-GPU path (--dedup seq, one lane per GPU) on {universe} read groups: {why}", file=sys.stderr)
+        else:
+            # (b) the single-GPU path over the whole input against the oracle over the whole input (one stream, one dropped group)
+            sam1, nb1 = synth_to_device(torch, mk, 0, universe, local, universe)
+            op1, _, ost1 = orc.sam2pairs(sam1[:nb1].cpu().numpy().tobytes(), WL["mode"], threads=8, write_sam=False)
+            arr1, n1 = orc.pairs_parse(op1, WL["names"])
+            keep1, n_keep1 = orc.coord_dedup(arr1, n1)
+            c1, c2, cc = orc.bin_coo(arr1, n1, keep1, WL["lens"], RES)
+            exp1 = np.frombuffer(bytes(arr1), dtype=mk.PAIR_DTYPE)[:n1][np.frombuffer(bytes(keep1), dtype=np.uint8)[:n1] == 1]
+            one = Pipeline(torch, mk, None, universe, 1, local, 64 << 20)
+            p1, k1, z1 = one.run(sam1, nb1)
+            single = np.frombuffer(one.kept_pairs(k1).cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+            checks["single_gpu_equals_oracle"] = (p1 == n1 and k1 == n_keep1 and z1 == len(c1) and np.array_equal(single[key(single)], exp1[key(exp1)])
+                                                  and one.cnt[:z1].cpu().numpy().astype(np.uint32).tolist() == cc)
+            checks["sharded_vs_unsharded_kept_pairs_differ_by_at_most_world_minus_1"] = abs(len(got_pairs) - k1) <= world - 1
+            one.close()
+            ok = all(checks.values()); why = json.dumps(checks)
+            print(f"[bench] verified {world}-GPU path on {universe} read groups: {why}", file=sys.stderr)
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
     dist.broadcast(flag, 0)
     if int(flag.item()) != 1:
         raise SystemExit(f"bench.py: the {world}-GPU result differs from the oracle / single-GPU result: {why}")
-    VERIFY["result"] = {"read_groups": universe, "asserted": True, "against": "CPU oracle and single-GPU path, kept pairs + COO of all ranks gathered"}
+    VERIFY["result"] = {"read_groups": universe, "asserted": True,
+                        "against": ("CPU oracle: one krmdup + sam2pairs replay per lane (shard), union binned; kept pairs + COO of all ranks gathered" if DEDUP_SEQ
+                                    else "CPU oracle and single-GPU path, kept pairs + COO of all ranks gathered")}
 
 
 def run_krmdup(args):
@@ -538,8 +557,8 @@ def main():
     args = ap.parse_args()
     global WL, SAM_ON, DEDUP_SEQ
     WL = WORKLOADS[args.config]; SAM_ON = args.sam; DEDUP_SEQ = args.dedup == "seq"
-    if DEDUP_SEQ and (int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.config == "multires"):
-        raise SystemExit("bench.py: --dedup seq is a single-GPU configuration of configs[1] / [2] (a krmdup key table per GPU = one lane per GPU)")
+    if DEDUP_SEQ and args.config == "multires":
+        raise SystemExit("bench.py: --dedup seq goes with --config flash / unc")
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.config == "krmdup":
         return run_krmdup(args)
@@ -810,7 +829,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     W = 256 << 20
     s2p = mk.Sam2Pairs(mk.S2PConfig(mode=WL["mode"], threads=8, write_sam=False, emit_text=True, emit_packed=True, device=local, window_bytes=W,
                                     sharded=(world > 1), rmdup=DEDUP_SEQ, rmdup_capacity=E + 1024), WL["names"])
-    if DEDUP_SEQ:
+    if DEDUP_SEQ and world == 1:
         sd_pairs = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
         sb1 = torch.empty(cap, dtype=torch.int32, device=dev); sb2 = torch.empty_like(sb1); sbc = torch.empty_like(sb1)
     if world > 1:
@@ -845,7 +864,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
         st = s2p.finish(0, 0) if world > 1 else s2p.finish()
         assert st.pairs == pl
         t_c = time.perf_counter()
-        if DEDUP_SEQ:                                  # the pulled pairs are already deduplicated: back to the device for the binning, COO to the host
+        if DEDUP_SEQ and world == 1:                   # the pulled pairs are already deduplicated: back to the device for the binning, COO to the host
             sd_pairs[:pl * 16].copy_(out_pairs[:pl * 16], non_blocking=True)
             kept = pl
             nnz = ws.bin(sd_pairs.data_ptr(), pl, WL["lens"], RES, sb1.data_ptr(), sb2.data_ptr(), sbc.data_ptr(), cap, stream=torch.cuda.current_stream().cuda_stream)
@@ -863,7 +882,11 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
             else:
                 n, src = shard.exchange_pairs(mk, torch, dist, ws, d_pairs, pl, d_kept, cap, PART_RES, stream)
                 src_ptr = src.data_ptr()
-            kept, nnz = ws.dedup_bin(src_ptr, n, WL["lens"], RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
+            if DEDUP_SEQ:                              # lanes: duplicates are gone (per lane), the owner only bins what it received
+                kept = n
+                nnz = ws.bin(src_ptr, n, WL["lens"], RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
+            else:
+                kept, nnz = ws.dedup_bin(src_ptr, n, WL["lens"], RES, db1.data_ptr(), db2.data_ptr(), dbc.data_ptr(), cap, stream=stream)
             mk.lib().check_cuda_copy(d_kept.data_ptr(), src_ptr, kept * 16)
             kept_host[:kept * 16].copy_(d_kept[:kept * 16], non_blocking=True)
             ob1[:nnz].copy_(db1[:nnz], non_blocking=True); ob2[:nnz].copy_(db2[:nnz], non_blocking=True); oc[:nnz].copy_(dbc[:nnz], non_blocking=True)
@@ -890,7 +913,7 @@ def measure_e2e(torch, mk, np, dist, args, world, rank, local):
     barrier()
     sec = (time.perf_counter() - t0) / reps
     s2p.close(); ws.close()
-    t = torch.tensor([sec, float(pl), float(nb + moved * 16), float(tl + pl * 16 + (0 if DEDUP_SEQ else kept * 16) + nnz * 12)], dtype=torch.float64, device=dev)
+    t = torch.tensor([sec, float(pl), float(nb + moved * 16), float(tl + pl * 16 + (0 if DEDUP_SEQ and world == 1 else kept * 16) + nnz * 12)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
