@@ -162,6 +162,10 @@ typedef struct {
     int hskip1, klen1, hskip2, klen2;  /* -k -s -K -S; defaults 5,16,5,16 (krmdup.cpp:231-234); 16 <= klen1+klen2 <= 32 */
     int device;
     size_t window_bytes;               /* bytes of FASTQ per device window; 0 = default */
+    int async_pull;                    /* 1: mk_dedup_pull only ENQUEUES its device-to-host copies, so that they run while the next
+                                          mk_dedup_push copies its window in (PCIe both ways at once).  The bytes a pull reported are
+                                          in the caller's buffers once the NEXT mk_dedup_pull, or mk_dedup_finish, has returned; the
+                                          buffers should be pinned.  0 (default): they are there when the pull returns. */
 } mk_dedup_cfg;
 typedef struct mk_dedup_stats_s { uint32_t uniq, dup, discard; uint64_t pairs; } mk_dedup_stats;   /* krmdup.cpp:383-389 */
 

@@ -56,7 +56,7 @@ def synth_opts(dup_per_1024=0, dup_universe=0, chimeric_per_1024=-1, noise_per_1
 
 class DedupCfg(C.Structure):
     _fields_ = [("hskip1", C.c_int), ("klen1", C.c_int), ("hskip2", C.c_int), ("klen2", C.c_int), ("device", C.c_int),
-                ("window_bytes", C.c_size_t)]
+                ("window_bytes", C.c_size_t), ("async_pull", C.c_int)]
 
 
 class DedupStats(C.Structure):
@@ -336,12 +336,13 @@ class Sam2Pairs:
 class Krmdup:
     """One krmdup process (persistent key sets): push()/pull()/finish()."""
 
-    def __init__(self, hskip1=5, klen1=16, hskip2=5, klen2=16, device=0, window_bytes=0):
+    def __init__(self, hskip1=5, klen1=16, hskip2=5, klen2=16, device=0, window_bytes=0, async_pull=False):
         self.lib = lib()
         self.lib.require_gpu()
         c = DedupCfg()
         self.lib.L.mk_dedup_default_cfg(C.byref(c))
         c.hskip1, c.klen1, c.hskip2, c.klen2, c.device, c.window_bytes = hskip1, klen1, hskip2, klen2, device, window_bytes
+        c.async_pull = int(async_pull)
         self.h = C.c_void_p()
         self.lib.check(self.lib.L.mk_dedup_create(C.byref(c), C.byref(self.h)))
         self._b1 = C.create_string_buffer(8 << 20)

@@ -251,11 +251,15 @@ struct DedupCtx : mk_ctx {
     size_t fill = 0;                               // bytes of h_in filled so far
     const char *ext_ptr = nullptr; size_t ext_len = 0;   // unconsumed tail of the last push, still in the caller's PINNED memory (fill == 0 then)
     size_t ho_len[2] = {0, 0}, ho_off[2] = {0, 0}; // undrained part of d_out1 / d_out2: the last window's kept records stay on the device until pulled
+    // cfg.async_pull: mk_dedup_pull only enqueues its device-to-host copies (stream s_out), so that they run while the next
+    // push's host-to-device copy does; bytes [0, fly_end) of the output buffers may still be being read
+    cudaStream_t s_out = nullptr; cudaEvent_t ev_out = nullptr; size_t fly_end[2] = {0, 0}; bool fly = false;
+    size_t out_cap = 0;                            // bytes of d_out1 / d_out2: 2 W (4 W with async_pull: room behind the copies in flight)
     bool finished = false;
     std::deque<std::vector<char>> q1, q2; size_t q1_off = 0, q2_off = 0;
     u64 pairs_total = 0;
     DedupCtx() { kind = MK_CTX_DEDUP; }
-    ~DedupCtx() override { cudaSetDevice(cfg.device); if (s) cudaStreamDestroy(s); }
+    ~DedupCtx() override { cudaSetDevice(cfg.device); if (s_out) { cudaStreamSynchronize(s_out); cudaStreamDestroy(s_out); } if (ev_out) cudaEventDestroy(ev_out); if (s) cudaStreamDestroy(s); }
 };
 
 static double dd_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -308,7 +312,8 @@ extern "C" int mk_dedup_create(const mk_dedup_cfg *cfg, mk_ctx **out) {
     A(c->d_in.alloc(c->W + 64)); A(c->d_state.alloc(sizeof(FqState))); A(c->d_nl.alloc((size_t)c->cap_lines * 4));
     A(c->d_desc.alloc((size_t)c->n_desc * 8)); A(c->d_rec0.alloc((size_t)c->cap_pairs * 16)); A(c->d_rec1.alloc((size_t)c->cap_pairs * 16));
     A(c->d_cls.alloc(c->cap_pairs)); A(c->d_eoff.alloc((size_t)c->cap_pairs * 8)); A(c->d_btab.alloc((size_t)(c->cap_pairs / FQ_BATCH + 4) * 32));
-    A(c->d_ldesc.alloc((size_t)c->n_tiles_cap * 4 * 8)); A(c->d_out1.alloc(2 * c->W + 64)); A(c->d_out2.alloc(2 * c->W + 64));
+    A(c->d_ldesc.alloc((size_t)c->n_tiles_cap * 4 * 8)); c->out_cap = (cfg->async_pull ? 4 : 2) * c->W;
+    A(c->d_out1.alloc(c->out_cap + 64)); A(c->d_out2.alloc(c->out_cap + 64));
     A(c->rws.alloc(c->cap_pairs));
     if (trace) fprintf(stderr, "[krmdup create] + device buffers %.3f s\n", dd_now() - t_start);
     A(c->h_in.alloc(c->W + 64));
@@ -316,6 +321,7 @@ extern "C" int mk_dedup_create(const mk_dedup_cfg *cfg, mk_ctx **out) {
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
     cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking);
+    if (cfg->async_pull) { cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking); cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming); }
     MK_CUDA(cudaMemsetAsync(c->d_state.p, 0, sizeof(FqState), c->s));
     MK_CUDA(cudaMemsetAsync(c->d_in.p, '\n', c->W + 64, c->s));
     rc = hs_alloc(c, 0, 1ull << 22);
@@ -347,7 +353,7 @@ static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_d
     // appended behind them while the output buffers (2 W each; a window's output is smaller than its input) have room;
     // only then are they moved off the device before the kernels overwrite them
     const bool pending = c->ho_off[0] < c->ho_len[0] || c->ho_off[1] < c->ho_len[1];
-    const bool append = pending && c->ho_len[0] + n <= 2 * c->W && c->ho_len[1] + n <= 2 * c->W;
+    const bool append = pending && c->ho_len[0] + n <= c->out_cap && c->ho_len[1] + n <= c->out_cap;
     for (int w = 0; w < 2 && !append; ++w) {
         if (c->ho_off[w] < c->ho_len[w]) {
             std::vector<char> v(c->ho_len[w] - c->ho_off[w]);
@@ -373,11 +379,20 @@ static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_d
     p.desc = c->d_desc.as<u64>(); p.rec0 = c->d_rec0.as<uint4>(); p.rec1 = c->d_rec1.as<uint4>(); p.cls = c->d_cls.as<u8>();
     p.eoff = c->d_eoff.as<u32>(); p.btab = c->d_btab.as<u32>();
     for (int w = 0; w < 2; ++w) { p.hset[w] = c->d_hset[w].as<u64>(); p.hmask[w] = c->hslots[w] - 1; }
-    const size_t base1 = append ? c->ho_len[0] : 0, base2 = append ? c->ho_len[1] : 0;
-    p.out1 = c->d_out1.as<char>() + base1; p.out2 = c->d_out2.as<char>() + base2; p.out_cap = 2 * c->W - std::max(base1, base2);
+    size_t base1 = append ? c->ho_len[0] : 0, base2 = append ? c->ho_len[1] : 0;
+    bool wait_out = false;
+    if (c->fly && !append) {
+        // copies of earlier pulls may still be reading the front of the buffers: write behind them while there is room, else
+        // the kernels (not this window's host-to-device copy, which is already enqueued) wait for those copies
+        // (room for two windows: a second window of the same push appends behind this one)
+        if (c->fly_end[0] + 2 * n <= c->out_cap && c->fly_end[1] + 2 * n <= c->out_cap) { base1 = c->fly_end[0]; base2 = c->fly_end[1]; }
+        else wait_out = true;
+    }
+    p.out1 = c->d_out1.as<char>() + base1; p.out2 = c->d_out2.as<char>() + base2; p.out_cap = c->out_cap - std::max(base1, base2);
     p.hskip1 = c->cfg.hskip1; p.klen1 = c->cfg.klen1; p.hskip2 = c->cfg.hskip2; p.klen2 = c->cfg.klen2;
     if (n_stage) MK_CUDA(cudaMemcpyAsync(c->d_in.p, c->h_in.p, n_stage, cudaMemcpyHostToDevice, s));
     if (n_direct) MK_CUDA(cudaMemcpyAsync(c->d_in.as<char>() + n_stage, direct, n_direct, cudaMemcpyHostToDevice, s));
+    if (wait_out) { MK_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0)); c->fly = false; c->fly_end[0] = c->fly_end[1] = 0; }
     k_fq_begin<<<(c->n_desc + 255) / 256, 256, 0, s>>>(p, c->n_desc, n, is_last ? 1u : 0u);
     int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fq_scan, S2P_SCAN_THREADS, 4 * 8192);
     k_fq_scan<<<c->sms * std::max(1, std::min(occ, 4)), S2P_SCAN_THREADS, 4 * 8192, s>>>(p);
@@ -412,6 +427,7 @@ static int dd_window(DedupCtx *c, size_t n_stage, const char *direct, size_t n_d
     MK_CUDA(cudaMemsetAsync((char *)c->d_state.p + offsetof(FqState, inserted), 0, 8, s));
     c->pairs_total += np;
     // the kept records stay in d_out1 / d_out2 until mk_dedup_pull copies them straight into the caller's buffers
+    if (!append) { c->ho_off[0] = base1; c->ho_off[1] = base2; }
     c->ho_len[0] = base1 + hst.out1; c->ho_len[1] = base2 + hst.out2;
     if (trace) fprintf(stderr, "[krmdup window] %zu bytes (%zu staged), %llu pairs: h2d+scan+keys %.1f ms, sort+mark+layout+copy %.1f ms\n",
                        n, n_stage, (unsigned long long)np, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
@@ -491,19 +507,25 @@ extern "C" int mk_dedup_pull(mk_ctx *x, char *r1, size_t cap1, size_t *n1, char 
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     size_t a = dd_drain(c->q1, c->q1_off, r1, cap1), b = dd_drain(c->q2, c->q2_off, r2, cap2);
     // then the last window's records, from the device straight into the caller's buffers (both copies in flight together)
+    const bool async = c->s_out != nullptr;
+    if (async && c->fly) MK_CUDA(cudaStreamSynchronize(c->s_out));      // what earlier pulls reported has landed now
+    cudaStream_t cs = async ? c->s_out : c->s;
     bool copied = false;
     if (r1 && c->q1.empty() && a < cap1) {
         const size_t m = std::min(cap1 - a, c->ho_len[0] - c->ho_off[0]);
-        if (m) { MK_CUDA(cudaMemcpyAsync(r1 + a, c->d_out1.as<char>() + c->ho_off[0], m, cudaMemcpyDeviceToHost, c->s)); copied = true; }
+        if (m) { MK_CUDA(cudaMemcpyAsync(r1 + a, c->d_out1.as<char>() + c->ho_off[0], m, cudaMemcpyDeviceToHost, cs)); copied = true; }
         a += m; c->ho_off[0] += m;
     }
     if (r2 && c->q2.empty() && b < cap2) {
         const size_t m = std::min(cap2 - b, c->ho_len[1] - c->ho_off[1]);
-        if (m) { MK_CUDA(cudaMemcpyAsync(r2 + b, c->d_out2.as<char>() + c->ho_off[1], m, cudaMemcpyDeviceToHost, c->s)); copied = true; }
+        if (m) { MK_CUDA(cudaMemcpyAsync(r2 + b, c->d_out2.as<char>() + c->ho_off[1], m, cudaMemcpyDeviceToHost, cs)); copied = true; }
         b += m; c->ho_off[1] += m;
     }
     const double t_p = copied && getenv("MICROCKET_TRACE") ? dd_now() : 0;
-    if (copied) MK_CUDA(cudaStreamSynchronize(c->s));
+    if (copied && async) {                                              // the copies run on while the caller pushes the next window
+        MK_CUDA(cudaEventRecord(c->ev_out, c->s_out));
+        c->fly = true; c->fly_end[0] = c->ho_off[0]; c->fly_end[1] = c->ho_off[1];
+    } else if (copied) MK_CUDA(cudaStreamSynchronize(c->s));
     if (t_p != 0) fprintf(stderr, "[krmdup pull] %zu + %zu bytes to the host in %.1f ms\n", a, b, (dd_now() - t_p) * 1e3);
     if (n1) *n1 = a;
     if (n2) *n2 = b;
@@ -514,6 +536,8 @@ extern "C" int mk_dedup_pull(mk_ctx *x, char *r1, size_t cap1, size_t *n1, char 
 extern "C" int mk_dedup_reset(mk_ctx *x) {
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     MK_CUDA(cudaStreamSynchronize(c->s));
+    if (c->s_out) MK_CUDA(cudaStreamSynchronize(c->s_out));
+    c->fly = false; c->fly_end[0] = c->fly_end[1] = 0;
     MK_CUDA(cudaMemsetAsync(c->d_state.p, 0, sizeof(FqState), c->s));
     for (int w = 0; w < 2; ++w) { MK_CUDA(cudaMemsetAsync(c->d_hset[w].p, 0xFF, c->hslots[w] * 8, c->s)); c->hcount[w] = 0; c->ho_len[w] = c->ho_off[w] = 0; }
     MK_CUDA(cudaStreamSynchronize(c->s));
@@ -526,6 +550,7 @@ extern "C" int mk_dedup_finish(mk_ctx *x, mk_dedup_stats *out) {
     DedupCtx *c; MK_TRY(dd_check(x, &c));
     if (!out) { mk_set_error("mk_dedup_finish: null stats"); return MK_ERR_ARG; }
     if (!c->finished) MK_TRY(mk_dedup_push(x, nullptr, 0, 1));
+    if (c->s_out) MK_CUDA(cudaStreamSynchronize(c->s_out));             // async_pull: everything reported so far has landed
     FqState st;
     MK_CUDA(cudaMemcpyAsync(&st, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost, c->s));
     MK_CUDA(cudaStreamSynchronize(c->s));

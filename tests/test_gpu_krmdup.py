@@ -111,3 +111,27 @@ def test_reset_and_pinned_input(oracle):
             assert (st.uniq, st.dup, st.discard) == (est.uniq, est.dup, est.discard)
     finally:
         kd.close()
+    # cfg.async_pull: a pull only enqueues its copies (they overlap the next push); the bytes are there once the next pull or finish returned
+    out1 = torch.empty(len(fq), dtype=torch.uint8).pin_memory(); out2 = torch.empty(len(fq), dtype=torch.uint8).pin_memory()
+    kd = mk.Krmdup(window_bytes=64 << 20, async_pull=True)
+    try:
+        for piece in (64 << 20, 50_000_000, len(fq)):
+            kd.reset(); out1.zero_(); out2.zero_()
+            a = b = 0
+            n1, n2 = C.c_size_t(), C.c_size_t()
+            for off in range(0, len(fq), piece):
+                m = min(piece, len(fq) - off)
+                kd.lib.check(kd.lib.L.mk_dedup_push(kd.h, C.cast(host.data_ptr() + off, C.c_char_p), m, int(off + m == len(fq))))
+                kd.lib.check(kd.lib.L.mk_dedup_pull(kd.h, out1.data_ptr() + a, out1.numel() - a, C.byref(n1), out2.data_ptr() + b, out2.numel() - b, C.byref(n2)))
+                a += n1.value; b += n2.value
+            st = kd.finish()
+            while True:
+                kd.lib.check(kd.lib.L.mk_dedup_pull(kd.h, out1.data_ptr() + a, out1.numel() - a, C.byref(n1), out2.data_ptr() + b, out2.numel() - b, C.byref(n2)))
+                if not (n1.value or n2.value):
+                    break
+                a += n1.value; b += n2.value
+            st = kd.finish()
+            assert out1[:a].numpy().tobytes() == e1 and out2[:b].numpy().tobytes() == e2, piece
+            assert (st.uniq, st.dup, st.discard) == (est.uniq, est.dup, est.discard)
+    finally:
+        kd.close()
