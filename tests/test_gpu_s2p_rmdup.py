@@ -116,3 +116,40 @@ def test_stream_ends_with_a_duplicate(oracle, mode):
             same((p, so, st, s.rmdup_stats()), e)
         finally:
             s.close()
+
+
+def test_device_resident_path(oracle):
+    """mk_s2p_run_device with cfg.rmdup (what bench.py --dedup seq times): 1 MiB windows over SAM text resident in HBM, two calls
+    (the second continues where the first one stopped); text, packed pairs and krmdup's log against the replay"""
+    import numpy as np
+    import torch
+    n = 60000
+    hg38 = ["chr1", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr2", "chr20", "chr21",
+            "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
+    buf, nb = mk.synth_device(torch, 77, "flash", "hg38", 0, n, opts=mk.synth_opts(dup_per_1024=180, dup_universe=n))
+    sam = buf[:nb].cpu().numpy().tobytes()
+    ep, _, est, edd = expected(oracle, sam, "flash")
+    s = mk.Sam2Pairs(mk.S2PConfig(mode="flash", threads=8, write_sam=False, emit_packed=True, window_bytes=1 << 20, rmdup=True, rmdup_capacity=n), hg38)
+    try:
+        text = torch.empty(nb, dtype=torch.uint8, device="cuda"); pairs = torch.empty((n + 16) * 16, dtype=torch.uint8, device="cuda")
+        cut = sam.rfind(b"\n", 0, nb // 2) + 1                      # first call: half of the text, not the last chunk
+        cut -= cut % 16
+        cut = sam.rfind(b"\n", 0, cut) + 1
+        part = torch.empty(cut + 64, dtype=torch.uint8, device="cuda"); part[:cut] = buf[:cut]
+        io1 = s.run_device(part.data_ptr(), cut, False, text.data_ptr(), nb, pairs.data_ptr(), n + 16)
+        rest = torch.empty(nb - io1.consumed + 64, dtype=torch.uint8, device="cuda"); rest[:nb - io1.consumed] = buf[io1.consumed:nb]
+        io2 = s.run_device(rest.data_ptr(), nb - io1.consumed, True, text.data_ptr() + io1.pairs_text_len, nb - io1.pairs_text_len,
+                           pairs.data_ptr() + io1.n_pairs * 16, n + 16 - io1.n_pairs)
+        st = s.finish()
+        dd = s.rmdup_stats()
+        got = text[:io1.pairs_text_len + io2.pairs_text_len].cpu().numpy().tobytes()
+        assert got == ep and st.log_text() == est.log_text()
+        assert (dd.uniq, dd.dup, dd.discard) == (edd.uniq, edd.dup, edd.discard)
+        pk = np.frombuffer(pairs[:(io1.n_pairs + io2.n_pairs) * 16].cpu().numpy().tobytes(), dtype=mk.PAIR_DTYPE)
+        lines = ep.decode().splitlines()
+        assert len(pk) == len(lines)
+        for ln, r in list(zip(lines, pk))[::97]:
+            f = ln.split("\t")
+            assert (f[1], int(f[2]), f[3], int(f[4])) == (hg38[r["chr1"]], int(r["pos1"]), hg38[r["chr2"]], int(r["pos2"]))
+    finally:
+        s.close()
