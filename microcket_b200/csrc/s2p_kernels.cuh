@@ -1192,7 +1192,7 @@ static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
                     }
                     if (!full) {
                         keep = old >= me;                                // RM_EMPTY (all ones) included
-                        if (old != RM_EMPTY && old > me) rm_drop_run(p, (u32)(old - g0), n);
+                        if (old != RM_EMPTY && old > me && old - g0 < n) rm_drop_run(p, (u32)(old - g0), n);
                         if (claimed) ++c_uniq;
                         if (me >= counted) ++c_tot;
                     }
