@@ -56,3 +56,35 @@ def test_chromosome_ranks_follow_gnu_sort_dictionary_order(tmp_path):
     exp = subprocess.run(["sort", "-d", "-s"], input="\n".join(sorted(names)) + "\n", capture_output=True, text=True,
                          env={"LANG": "C", "LC_ALL": "C", "PATH": os.environ.get("PATH", "/usr/bin:/bin")}).stdout.split()
     assert got == exp
+
+
+def test_ctypes_mirror_matches_the_header_layout(tmp_path):
+    """The structs of include/microcket_b200.h compiled by gcc have the sizes and field offsets of their ctypes mirrors in
+    microcket_b200/capi.py (a silent mismatch would hand the library a scrambled configuration)."""
+    import subprocess
+    from microcket_b200 import capi
+    structs = {"mk_s2p_cfg": capi.S2PCfg, "mk_s2p_stats": capi.S2PStats, "mk_s2p_dev_io": capi.S2PDevIO, "mk_dedup_cfg": capi.DedupCfg,
+               "mk_dedup_stats": capi.DedupStats, "mk_synth_opts": capi.SynthOpts}
+    lines = []
+    for cname, mirror in structs.items():
+        lines.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('printf("\\n");')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "microcket_b200.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line, (cname, mirror) in zip(out, structs.items()):
+        f = line.split()
+        assert f[0] == cname and int(f[1]) == C.sizeof(mirror), (cname, f[1], C.sizeof(mirror))
+        assert [int(x) for x in f[2:]] == [getattr(mirror, n).offset for n, _ in mirror._fields_], cname
+    assert C.sizeof(np_pair()) == 16
+
+
+def np_pair():
+    class Pair(C.Structure):
+        _fields_ = [("pos1", C.c_uint32), ("pos2", C.c_uint32), ("chr1", C.c_uint16), ("chr2", C.c_uint16), ("strands", C.c_uint8), ("cls", C.c_uint8),
+                    ("lane", C.c_uint16)]
+    return Pair
