@@ -747,6 +747,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": dict(workload_config(args, world, G), sam_bytes_per_gpu=nbytes, pairs_per_step=n_pairs_all, kept_after_dedup=kept_all,
                            coo_cells=nnz_all, window_mb=args.window_mb),
+            "read_groups_per_s": universe / (ms_step / 1e3),     # input read groups of all ranks per second (SURVEY 8d asks for both rates)
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checks": checks,
             "parity": ("sam2pairs AND the duplicate removal pinned by the reference binaries (krmdup's own rule taken on the SAM, tests/test_gpu_s2p_rmdup.py); "
                        "binning UNPINNED (juicer_tools absent: checked against oracle/pairs_oracle.c + numpy only) - that stage is %.1f of the %.1f ms step"
