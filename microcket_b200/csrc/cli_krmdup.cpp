@@ -28,7 +28,7 @@ template <class T> struct Chan {                      // blocking queue
     T get() { unique_lock<mutex> l(m); cv.wait(l, [&] { return !q.empty(); }); T v = std::move(q.front()); q.pop_front(); return v; }
 };
 struct InBlock { vector<char> buf; size_t n = 0; };
-struct OutBlock { vector<char> a, b; size_t na = 0, nb = 0; bool last = false; };
+struct OutBlock { char *a = NULL, *b = NULL; size_t na = 0, nb = 0; bool last = false; };   // pinned (mk_host_alloc): kept records are DMA'd straight into them
 
 static void usage(const char *prg) {
     cerr << "\nUsage: " << prg << " [options] -i <interleaved.paired-end.fq> -o <output.prefix>\n"
@@ -107,7 +107,7 @@ int main(int argc, char *argv[]) {
     Chan<InBlock *> in_free, in_full; Chan<OutBlock *> out_free, out_full;
     vector<InBlock> in_pool(12); vector<OutBlock> out_pool(3);      // 384 MiB of read-ahead: the reader runs while the CUDA context comes up
     for (auto &b : in_pool) { b.buf.resize(IN); in_free.put(&b); }
-    for (auto &b : out_pool) { b.a.resize(OUT); b.b.resize(OUT); out_free.put(&b); }
+
     thread reader([&] {
         while (true) {
             InBlock *b = in_free.get();
@@ -116,11 +116,16 @@ int main(int argc, char *argv[]) {
             if (b->n == 0) break;
         }
     });
-    if (mk_dedup_create(&cfg, &ctx) != MK_OK) {                      // (the reader is already filling blocks)
+    auto fail_early = [&]() {                                        // (the reader is already filling blocks: let it run to EOF)
         cerr << "Error: " << mk_last_error() << "\n";
         while (true) { InBlock *b = in_full.get(); if (b->n == 0) break; in_free.put(b); }
         reader.join();
         return 20;
+    };
+    if (mk_dedup_create(&cfg, &ctx) != MK_OK) return fail_early();
+    for (auto &b : out_pool) {                                       // (pinned memory needs the CUDA context)
+        if (mk_host_alloc(OUT, (void **)&b.a) != MK_OK || mk_host_alloc(OUT, (void **)&b.b) != MK_OK) return fail_early();
+        out_free.put(&b);
     }
     if (trace) fprintf(stderr, "[krmdup] context ready after %.3f s\n", since());
     thread writer([&] {
@@ -128,10 +133,10 @@ int main(int argc, char *argv[]) {
             OutBlock *b = out_full.get();
             if (b->last) break;
 #ifdef KRMDUP_PIPE
-            il.feed(b->a.data(), b->na, b->b.data(), b->nb);
+            il.feed(b->a, b->na, b->b, b->nb);
 #else
-            if (b->na) fwrite(b->a.data(), 1, b->na, f1);
-            if (b->nb) fwrite(b->b.data(), 1, b->nb, f2);
+            if (b->na) fwrite(b->a, 1, b->na, f1);
+            if (b->nb) fwrite(b->b, 1, b->nb, f2);
 #endif
             out_free.put(b);
         }
@@ -140,7 +145,7 @@ int main(int argc, char *argv[]) {
         while (true) {
             OutBlock *b = out_free.get();
             b->na = b->nb = 0; b->last = false;
-            if (mk_dedup_pull(ctx, b->a.data(), OUT, &b->na, b->b.data(), OUT, &b->nb) != MK_OK) { out_free.put(b); return -1; }
+            if (mk_dedup_pull(ctx, b->a, OUT, &b->na, b->b, OUT, &b->nb) != MK_OK) { out_free.put(b); return -1; }
             if (!b->na && !b->nb) { out_free.put(b); return 0; }
             out_full.put(b);
         }
