@@ -153,3 +153,17 @@ def test_device_resident_path(oracle):
             assert (f[1], int(f[2]), f[3], int(f[4])) == (hg38[r["chr1"]], int(r["pos1"]), hg38[r["chr2"]], int(r["pos2"]))
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("mode", ["unc", "flash"])
+def test_golden_vectors(mode):
+    """tests/golden/rmdup_*: outputs of the reference's own krmdup (given the original reads) and sam2pairs (given the surviving
+    lines), generated in the dev container by tests/golden/make_golden_rmdup.py"""
+    from oracle_lib import sort_lines, sort_pairs
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    rd = lambda n: open(os.path.join(g, n), "rb").read()
+    for kw in ({}, {"window": 1 << 16, "chunk": 4099}):
+        p, so, st, dd = gpu(rd(f"rmdup_{mode}.sam"), mode, threads=4, **kw)
+        assert dd.log_text() == rd(f"rmdup_{mode}.krmdup.log")
+        assert sort_pairs(p) == rd(f"rmdup_{mode}.pairs.sorted") and st.log_text() == rd(f"rmdup_{mode}.log")
+        assert sort_lines(so) == rd(f"rmdup_{mode}.samout.sorted")

@@ -47,3 +47,20 @@ def test_cigar_quirks(oracle):
     assert ok and s.right[0] == 5148 and s.mappable == 147
     assert not oracle.cigar("10=", 1)[0]
     assert not oracle.cigar("*", 1)[0]
+
+
+def test_sam_space_krmdup_golden(oracle):
+    """tests/golden/rmdup_*: krmdup (on the original reads) -> sam2pairs (on the surviving lines), both the REFERENCE's own
+    programs (make_golden_rmdup.py).  The replay the GPU path is checked against (oracle/sam_rmdup_oracle.py + the C oracle)
+    reproduces them from the SAM alone."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sam_rmdup_oracle as R
+    from oracle_lib import sort_lines, sort_pairs
+    for mode in ("unc", "flash"):
+        sam = rd(f"rmdup_{mode}.sam")
+        r1, _, dd = oracle.krmdup(R.sam_to_fastq(sam)[0])
+        p, so, st = oracle.sam2pairs(R.filter_sam(sam, R.kept_runs(r1)), mode, threads=4)
+        assert dd.log_text() == rd(f"rmdup_{mode}.krmdup.log")
+        assert sort_pairs(p) == rd(f"rmdup_{mode}.pairs.sorted") and st.log_text() == rd(f"rmdup_{mode}.log")
+        assert sort_lines(so) == rd(f"rmdup_{mode}.samout.sorted")
