@@ -88,3 +88,17 @@ def np_pair():
         _fields_ = [("pos1", C.c_uint32), ("pos2", C.c_uint32), ("chr1", C.c_uint16), ("chr2", C.c_uint16), ("strands", C.c_uint8), ("cls", C.c_uint8),
                     ("lane", C.c_uint16)]
     return Pair
+
+
+def test_product_path_never_touches_the_oracle():
+    """Nothing under microcket_b200/ or include/ names the oracle or the reference build (test infrastructure only): the CUDA path
+    is the only path, and it fails loudly without a GPU (test_no_cpu_fallback_without_gpu)."""
+    import glob
+    hits = []
+    for pat in ("microcket_b200/*.py", "microcket_b200/csrc/*.cu", "microcket_b200/csrc/*.cuh", "microcket_b200/csrc/*.cpp",
+                "microcket_b200/csrc/*.h", "include/*.h"):
+        for path in glob.glob(os.path.join(ROOT, pat)):
+            txt = open(path, errors="replace").read()
+            if re.search(r"oracle|_ref\b|/root/reference", txt):
+                hits.append(os.path.relpath(path, ROOT))
+    assert not hits, hits
