@@ -42,9 +42,9 @@ struct S2PCtx : mk_ctx {
     DevBuf d_params;                               // device copies of the kernels' parameter blocks (S2PParams.self)
     u32 n_sub_cap = 0;
     DevBuf d_state, d_nl, d_lmeta, d_rec, d_res, d_samdst, d_desc, d_chr, d_id2slot, d_sclist;
-    DevBuf d_rmtab[2], d_rmkey, d_rmstat, d_rminfo; u64 rm_slots[2] = {0, 0};    // SAM-space krmdup (cfg.rmdup)
+    DevBuf d_rmtab[2], d_rminfo; u64 rm_slots[2] = {0, 0};    // SAM-space krmdup (cfg.rmdup)
     S2PSlot slot[2];
-    int grid_scan4 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0;
+    int grid_scan4 = 0, grid_emit = 0, grid_gs = 0, grid_parse = 0, grid_rm = 0;
     u64 launches = 0, fallback_windows = 0;
     // host streaming state
     std::vector<char> tail;                        // input not yet part of a window (a partial last line, or small pushes)
@@ -122,7 +122,7 @@ static S2PParams make_params(S2PCtx *c, const char *buf, u64 *sc_list, u32 sc_ca
     if (p.rm_on) {
         p.rm_hskip1 = c->cfg.hskip1; p.rm_klen1 = c->cfg.klen1; p.rm_hskip2 = c->cfg.hskip2; p.rm_klen2 = c->cfg.klen2;
         for (int t = 0; t < 2; ++t) { p.rm_tab[t] = c->d_rmtab[t].as<unsigned long long>(); p.rm_mask[t] = c->rm_slots[t] - 1; }
-        p.rm_key = c->d_rmkey.as<unsigned long long>(); p.rm_stat = c->d_rmstat.as<u8>(); p.rm_info = c->d_rminfo.as<u32>();
+        p.rm_info = c->d_rminfo.as<u32>();
     }
     p.self = nullptr;
     return p;
@@ -152,9 +152,8 @@ static void launch_window(S2PCtx *c, const S2PParams &p, cudaStream_t s) {
     if (p.rm_on) {                                       // SAM-space krmdup: duplicate / discarded read pairs lose LM_KEEP before grouping
         k_parse<true><<<c->grid_parse, 256, PR_SMEM, s>>>(p);
         mark(7);
-        k_rm_keys<<<c->grid_gs, 256, 0, s>>>(p);
-        k_rm_insert<<<c->grid_gs, 256, 0, s>>>(p);
-        c->launches += 2;
+        k_rm_insert<<<c->grid_rm, 256, 0, s>>>(p);
+        c->launches += 1;
     } else k_parse<false><<<c->grid_parse, 256, PR_SMEM, s>>>(p);
     mark(2);
     k_group<<<c->grid_gs, 256, 0, s>>>(p);
@@ -280,7 +279,7 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
         u64 slots = 1024; while (slots < 2 * cap) slots <<= 1;
         c->rm_slots[0] = slots; c->rm_slots[1] = std::max<u64>(slots >> 4, 1024);
         for (int t = 0; t < 2; ++t) { A(c->d_rmtab[t].alloc(c->rm_slots[t] * 16)); if (rc == MK_OK && cudaMemset(c->d_rmtab[t].p, 0xFF, c->rm_slots[t] * 16) != cudaSuccess) rc = MK_ERR_CUDA; }
-        A(c->d_rmkey.alloc((size_t)c->cap_lines * 16)); A(c->d_rmstat.alloc(c->cap_lines)); A(c->d_rminfo.alloc((size_t)c->cap_lines * 4));
+        A(c->d_rminfo.alloc((size_t)c->cap_lines * 4));
     }
 #undef A
     if (rc != MK_OK) { delete c; return rc; }
@@ -317,6 +316,8 @@ extern "C" int mk_s2p_create(const mk_s2p_cfg *cfg, const char *const *names, in
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_emit, EMIT_THREADS, 0);
     c->grid_emit = sms * std::max(1, occ);
     c->grid_gs = sms * 8;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rm_insert, 256, 0);
+    c->grid_rm = sms * std::max(1, occ);                   // one resident wave: the rounds are split statically
     cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
     if (cfg->rmdup) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_parse<true>, 256, PR_SMEM);

@@ -108,7 +108,7 @@ struct S2PParams {
     // per-line key / status of the window's QNAME runs
     int rm_on, rm_hskip1, rm_klen1, rm_hskip2, rm_klen2;
     unsigned long long *rm_tab[2]; u64 rm_mask[2];
-    unsigned long long *rm_key; u8 *rm_stat; u32 *rm_info;   // rm_info: K2's (flag | SEQ offset << 16) per line
+    u32 *rm_info;   // rm_info: K2's (flag | SEQ offset << 16) per line
     unsigned long long *xparts;   // optional: per launched window (end, count) of its packed pairs, for the overlapped multi-GPU scatter
     const S2PParams *self;    // device copy of this struct: what out-of-line callees are handed, so that the kernels' parameter block is never copied to local memory
 };
@@ -1100,52 +1100,48 @@ __device__ __forceinline__ void rm_drop_run(const S2PParams &p, u32 h, u32 n) {
     do { const u32 m = p.lmeta[j]; if (m & LM_KEEP) p.lmeta[j] = (u8)(m & ~LM_KEEP); ++j; } while (j < n && (p.lmeta[j] & LM_EQ));
 }
 
-// phase A: one thread per line: the key bits its SEQ gives to mate 1 and / or mate 2 (primary records only)
-static __global__ void __launch_bounds__(256) k_rm_keys(S2PParams p) {
-    const WinState *st = p.st;
-    const u32 n = st->n_lines;
-    const u64 ws = st->ws;
-    for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        const u32 info = p.rm_info[i];                                  // K2: flag | offset << 12 | (offset is SEQ's, not field 7's) << 19 | SEQ length by the CIGAR << 20
-        const u64 a = ws + (i ? (u64)p.nl_pos[i - 1] + 1 : 0), e = ws + p.nl_pos[i];
-        u32 flag = info & 0xFFFu, stat = 0;
-        const u32 so = (info >> 12) & 0x7Fu, ql = info >> 20;
-        u64 seq = a + so, key = 0, key2 = 0;
-        bool primary = true;
-        if (so && !(info & (1u << 19)) && !(flag & 0x900u)) {           // from field 7 (RNEXT): PNEXT, TLEN, SEQ
-            u64 t = seq;
-            for (int k = 0; k < 3 && t < e; ++k) { t = rm_next_tab(p.buf, t, e); if (t < e) ++t; }
-            seq = t;
+// the key bits the SEQ of line i gives to mate 1 and / or mate 2 (primary records only)
+static __device__ __forceinline__ void rm_line_keys(const S2PParams &p, const u64 ws, const u32 i, u32 &stat, u64 &key, u64 &key2) {
+    const u32 info = p.rm_info[i];                                      // K2: flag | offset << 12 | (offset is SEQ's, not field 7's) << 19 | SEQ length by the CIGAR << 20
+    const u64 a = ws + (i ? (u64)p.nl_pos[i - 1] + 1 : 0), e = ws + p.nl_pos[i];
+    u32 flag = info & 0xFFFu;
+    const u32 so = (info >> 12) & 0x7Fu, ql = info >> 20;
+    u64 seq = a + so;
+    bool primary = true;
+    stat = 0; key = 0; key2 = 0;
+    if (so && !(info & (1u << 19)) && !(flag & 0x900u)) {               // from field 7 (RNEXT): PNEXT, TLEN, SEQ
+        u64 t = seq;
+        for (int k = 0; k < 3 && t < e; ++k) { t = rm_next_tab(p.buf, t, e); if (t < e) ++t; }
+        seq = t;
+    }
+    if (so == 0) {                                                      // K2 did not parse the line: FLAG = field 2, SEQ = field 10
+        if (p.buf[a] == '@') { stat = RL_HDR; primary = false; }
+        else {
+            const u64 t1 = rm_next_tab(p.buf, a, e);
+            u64 t = t1 < e ? rm_next_tab(p.buf, t1 + 1, e) : e;
+            flag = 0;
+            for (u64 q = t1 + 1; q < t; ++q) flag = flag * 10u + (u32)((unsigned char)p.buf[q] - '0');
+            for (int k = 2; k < 9 && t < e; ++k) t = rm_next_tab(p.buf, t + 1, e);
+            seq = t < e ? t + 1 : e;
         }
-        if (so == 0) {                                                  // K2 did not parse the line: FLAG = field 2, SEQ = field 10
-            if (p.buf[a] == '@') { stat = RL_HDR; primary = false; }
-            else {
-                const u64 t1 = rm_next_tab(p.buf, a, e);
-                u64 t = t1 < e ? rm_next_tab(p.buf, t1 + 1, e) : e;
-                flag = 0;
-                for (u64 q = t1 + 1; q < t; ++q) flag = flag * 10u + (u32)((unsigned char)p.buf[q] - '0');
-                for (int k = 2; k < 9 && t < e; ++k) t = rm_next_tab(p.buf, t + 1, e);
-                seq = t < e ? t + 1 : e;
-            }
-        }
-        if (primary && !(flag & 0x900u)) {
-            // SEQ length: the CIGAR's when the byte behind it ends the field (no scan over the bases), else counted
-            u32 L;
-            if (so && ql && seq + ql <= e && (seq + ql == e || p.buf[seq + ql] == '\t') && p.buf[seq + ql - 1] != '\t') L = ql;
-            else L = seq < e ? (u32)(rm_next_tab(p.buf, seq, e) - seq) : 0u;
-            const bool m1 = (flag & 64u) || !(flag & 192u), m2 = !(flag & 64u);   // 128 only -> mate 2; neither (stitched) -> both
-            const bool rev = (flag & 16u) != 0;
-            u64 b1 = 0, b2 = 0; bool lf = false, l2;
-            if (m1) { stat |= RL_M1; if (rm_half(p.buf, seq, L, rev, p.rm_hskip1, p.rm_klen1, b1, lf)) stat |= RL_OK1; if (lf) stat |= RL_TAG; }
-            if (m2) { stat |= RL_M2; if (rm_half(p.buf, seq, L, (flag & 192u) ? rev : !rev, p.rm_hskip2, p.rm_klen2, b2, l2)) stat |= RL_OK2; }
-            key = b1; key2 = b2;
-        }
-        p.rm_stat[i] = (u8)stat;
-        ((ulonglong2 *)p.rm_key)[i] = make_ulonglong2(key, key2);
+    }
+    if (primary && !(flag & 0x900u)) {
+        // SEQ length: the CIGAR's when the byte behind it ends the field (no scan over the bases), else counted
+        u32 L;
+        if (so && ql && seq + ql <= e && (seq + ql == e || p.buf[seq + ql] == '\t') && p.buf[seq + ql - 1] != '\t') L = ql;
+        else L = seq < e ? (u32)(rm_next_tab(p.buf, seq, e) - seq) : 0u;
+        const bool m1 = (flag & 64u) || !(flag & 192u), m2 = !(flag & 64u);   // 128 only -> mate 2; neither (stitched) -> both
+        const bool rev = (flag & 16u) != 0;
+        bool lf = false, l2;
+        if (m1) { stat |= RL_M1; if (rm_half(p.buf, seq, L, rev, p.rm_hskip1, p.rm_klen1, key, lf)) stat |= RL_OK1; if (lf) stat |= RL_TAG; }
+        if (m2) { stat |= RL_M2; if (rm_half(p.buf, seq, L, (flag & 192u) ? rev : !rev, p.rm_hskip2, p.rm_klen2, key2, l2)) stat |= RL_OK2; }
     }
 }
+// the same for a line of another CTA's tile (a run that crosses a tile boundary: one in ~100); out of line to keep the kernel small
+static __device__ __noinline__ void rm_line_keys_far(const S2PParams &p, u64 ws, u32 i, u32 &stat, u64 &key, u64 &key2) { rm_line_keys(p, ws, i, stat, key, key2); }
 
-// phase B: the thread of a run's first line combines the run's mates into the pair's key and settles the run on the spot.
+// One kernel, 256 consecutive lines per CTA round.  Every thread first works out what ITS line contributes (staged in shared
+// memory); then the thread of a run's first line combines the run's mates into the pair's key and settles the run on the spot.
 // The table keeps, per key, the smallest global line index seen so far (atomicMin), and the value it held before tells
 // everything: nothing or this very line (a re-parsed run) -> this run is the first occurrence so far; a larger index ->
 // likewise, and the run that index belongs to (necessarily of this window: earlier windows hold smaller indices) is a
@@ -1154,51 +1150,53 @@ static __global__ void __launch_bounds__(256) k_rm_keys(S2PParams p) {
 // A run cut by the window end is decided in the next window; until then its lines do not count as kept, so that the group
 // before it stays the window's last (carried) group: it may yet turn out to be the stream's last one (pairutil.h:176).
 static __global__ void __launch_bounds__(256) k_rm_insert(S2PParams p) {
+    __shared__ unsigned long long s_k1[256], s_k2[256];
+    __shared__ u8 s_stat[256], s_meta[256];
     WinState *st = p.st;
     const u32 n = st->n_lines;
-    const u64 g0 = st->lines_done, counted = st->rm_counted;
+    const u64 ws = st->ws, g0 = st->lines_done, counted = st->rm_counted;
     const bool final_win = (st->we == st->total) && st->is_last;
+    const u32 tid = threadIdx.x;
     u32 c_tot = 0, c_uniq = 0, c_disc = 0;
     for (u32 i0 = blockIdx.x * 256u; i0 < n; i0 += gridDim.x * 256u) {
-        const u32 i = i0 + threadIdx.x;
-        if (i < n) {
-            const u32 m_i = p.lmeta[i];                                 // the three loads of the common case go out together
-            u32 sl = p.rm_stat[i];
-            const ulonglong2 k_i = ((const ulonglong2 *)p.rm_key)[i];
-            if (!(m_i & LM_EQ) && !(sl & RL_HDR)) {
-                u32 have = 0; u64 b1 = 0, b2 = 0;
-                u32 j = i;
-                while (true) {
-                    if (sl & ~have & (RL_M1 | RL_M2)) {
-                        const ulonglong2 k = j == i ? k_i : ((const ulonglong2 *)p.rm_key)[j];
-                        if (sl & ~have & RL_M1) { b1 = k.x; have |= RL_M1 | (sl & (RL_OK1 | RL_TAG)); }
-                        if (sl & ~have & RL_M2) { b2 = k.y; have |= RL_M2 | (sl & RL_OK2); }
-                    }
-                    ++j;
-                    if (j >= n || !(p.lmeta[j] & LM_EQ)) break;
-                    sl = p.rm_stat[j];
-                }
-                bool keep = false;
-                if (j >= n && !final_win) ;                              // undecided
-                else if ((have & (RL_OK1 | RL_OK2)) == (RL_OK1 | RL_OK2)) {
-                    const u64 key = (b1 << (2 * p.rm_klen2)) | b2, me = g0 + i;
-                    const u32 tag = (have & RL_TAG) ? 1u : 0u;
-                    unsigned long long old = 0; bool claimed = false, full = false;
-                    if (key == RM_EMPTY) { old = atomicMin(&st->rm_allones[tag], (unsigned long long)me); claimed = old == RM_EMPTY; }
-                    else {
-                        const u64 s = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, claimed);
-                        if (s == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); full = true; }
-                        else old = atomicMin(&p.rm_tab[tag][2 * s + 1], (unsigned long long)me);
-                    }
-                    if (!full) {
-                        keep = old >= me;                                // RM_EMPTY (all ones) included
-                        if (old != RM_EMPTY && old > me && old - g0 < n) rm_drop_run(p, (u32)(old - g0), n);
-                        if (claimed) ++c_uniq;
-                        if (me >= counted) ++c_tot;
-                    }
-                } else if (g0 + i >= counted) { ++c_tot; ++c_disc; }
-                if (!keep) rm_drop_run(p, i, n);
+        const u32 i = i0 + tid;
+        u32 m_i = 0, sl = 0; u64 k1 = 0, k2 = 0;
+        if (i < n) { m_i = p.lmeta[i]; rm_line_keys(p, ws, i, sl, k1, k2); }
+        __syncthreads();                                                // the previous round's entries have been consumed
+        s_meta[tid] = (u8)m_i; s_stat[tid] = (u8)sl; s_k1[tid] = k1; s_k2[tid] = k2;
+        __syncthreads();
+        if (i < n && !(m_i & LM_EQ) && !(sl & RL_HDR)) {
+            u32 have = 0; u64 b1 = 0, b2 = 0;
+            u32 j = i;
+            while (true) {
+                if (sl & ~have & RL_M1) { b1 = k1; have |= RL_M1 | (sl & (RL_OK1 | RL_TAG)); }
+                if (sl & ~have & RL_M2) { b2 = k2; have |= RL_M2 | (sl & RL_OK2); }
+                ++j;
+                if (j >= n) break;
+                const u32 t = j - i0;
+                if (t < 256u) { if (!(s_meta[t] & LM_EQ)) break; sl = s_stat[t]; k1 = s_k1[t]; k2 = s_k2[t]; }
+                else { if (!(p.lmeta[j] & LM_EQ)) break; rm_line_keys_far(*p.self, ws, j, sl, k1, k2); }
             }
+            bool keep = false;
+            if (j >= n && !final_win) ;                                  // undecided
+            else if ((have & (RL_OK1 | RL_OK2)) == (RL_OK1 | RL_OK2)) {
+                const u64 key = (b1 << (2 * p.rm_klen2)) | b2, me = g0 + i;
+                const u32 tag = (have & RL_TAG) ? 1u : 0u;
+                unsigned long long old = 0; bool claimed = false, full = false;
+                if (key == RM_EMPTY) { old = atomicMin(&st->rm_allones[tag], (unsigned long long)me); claimed = old == RM_EMPTY; }
+                else {
+                    const u64 s = rm_slot(p.rm_tab[tag], p.rm_mask[tag], key, claimed);
+                    if (s == ~0ull) { atomicOr(&st->err, S2P_ERR_RMTABLE); full = true; }
+                    else old = atomicMin(&p.rm_tab[tag][2 * s + 1], (unsigned long long)me);
+                }
+                if (!full) {
+                    keep = old >= me;                                    // RM_EMPTY (all ones) included
+                    if (old != RM_EMPTY && old > me && old - g0 < n) rm_drop_run(p, (u32)(old - g0), n);
+                    if (claimed) ++c_uniq;
+                    if (me >= counted) ++c_tot;
+                }
+            } else if (g0 + i >= counted) { ++c_tot; ++c_disc; }
+            if (!keep) rm_drop_run(p, i, n);
         }
     }
     c_tot = __reduce_add_sync(0xFFFFFFFFu, c_tot); c_uniq = __reduce_add_sync(0xFFFFFFFFu, c_uniq); c_disc = __reduce_add_sync(0xFFFFFFFFu, c_disc);
