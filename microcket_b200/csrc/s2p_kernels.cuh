@@ -6,7 +6,7 @@
 //   k_chunk_prefix / k_chunk_compact   the chunks' newline lists -> the dense nl_pos[] (k_scan_lines: look-back fallback for windows
 //                  with more than 512 newlines in a chunk; also the FASTQ path's scan)
 //   k_parse        K2: one thread per line: first six fields, filter, CIGAR walk         (pairutil.h:63-126,155-161; unc2pairs.h:34-36)
-//   k_rm_keys / k_rm_insert   (cfg.rmdup only) krmdup's duplicate removal taken on the SAM: duplicate read pairs lose LM_KEEP    (src/preprocess/krmdup.cpp:103-212)
+//   k_rm_insert    (cfg.rmdup only) krmdup's duplicate removal taken on the SAM: duplicate read pairs lose LM_KEEP    (src/preprocess/krmdup.cpp:103-212)
 //   k_group        K3: group heads among kept records + per-group resolution             (pairutil.h:163-173; flash2pairs.h; unc2pairs.h)
 //   k_emit_prefix / k_emit   K4: prefixes of the per-tile output sizes, .pairs text + packed records + line offsets   (unc2pairs.h:310-348)
 //   k_copy_sam     K5: SAM passthrough of the kept lines of emitted groups               (unc2pairs.h:351-356)
