@@ -153,7 +153,7 @@ int  mk_s2p_attach_xchg(mk_ctx *, struct mk_xchg *, uint32_t res);
 uint64_t mk_launch_count(mk_ctx *);
 /* Optional per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figure).
  * ms[k] / count[k]; arrays of 8.  k = 0 newline scan, 1 parse, 2 group, 3 emit, 4 SAM passthrough, 5 scan index (chunk
- * prefix + compaction), 6 the two SAM-space krmdup kernels (cfg.rmdup), 7 unused. */
+ * prefix + compaction), 6 the SAM-space krmdup kernel (cfg.rmdup), 7 unused. */
 int  mk_s2p_enable_timing(mk_ctx *, int on);
 int  mk_s2p_kernel_times(mk_ctx *, double *ms, uint64_t *count);
 
