@@ -1,6 +1,6 @@
 // cli_pairs2bins.cpp — contact binning of a .pairs file on the GPU (new tool; stands where the driver calls
 // `java -jar juicer_tools.jar pre -r <res,...> <sid>.final.pairs <sid>.hic <genome>.info`, microcket:525-529).
-//   pairs2bins [-d] [-b] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>
+//   pairs2bins [-d] [-b] [-H <out.hic>] [-g <genomeId>] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>
 // Writes <out.prefix>.<res>.coo with `bin1<TAB>bin2<TAB>count` (upper triangle, sorted), bins numbered in .info order with
 // bin = offset[chr] + pos / res.  -d removes coordinate duplicates first (first occurrence wins).
 // -b also writes <out.prefix>.<res>.bins.bed (`chrom<TAB>start<TAB>end`, one line per bin id): the pair of files is what
@@ -8,7 +8,10 @@
 // (microcket:531-551) without `cooler cload pairs` re-reading and re-binning the pairs.
 // The file is streamed in 256 MiB chunks from pinned memory and PARSED ON THE GPU (mk_pairs_parse_text_device); resolutions
 // whose upper triangle fits MICROCKET_DENSE_MB (default 4096) all come from one pass of the dense histogram (mk_hist_*), the
-// finer ones from the sort path.  Writing .hic itself is out of scope.
+// finer ones from the sort path.
+// -H <out.hic> also packs every resolution's counts into one `.hic` (version 8) container, i.e. the file the driver's
+// `juicer_tools pre` call produces (host code over the arrays copied back for the .coo files: hic_writer.hpp; -g names the
+// genome in its header, default: the .info file's stem).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,13 +21,18 @@
 #include <string>
 #include <vector>
 #include "../../include/microcket_b200.h"
+#include "hic_writer.hpp"
 using namespace std;
 
 #define CHECK(call) do { if ((call) != MK_OK) { cerr << "Error: " << mk_last_error() << "\n"; return 20; } } while (0)
 
-static int write_coo(const string &path, const void *d_b1, const void *d_b2, const void *d_ct, size_t nnz) {
+static hic::Writer *g_hic = NULL;                                         // -H: every resolution's arrays also go into the container
+
+static int write_coo(const string &prefix, uint32_t res, const void *d_b1, const void *d_b2, const void *d_ct, size_t nnz) {
+    const string path = prefix + "." + to_string(res) + ".coo";
     vector<uint32_t> b1(nnz + 1), b2(nnz + 1), ct(nnz + 1);
     if (nnz) { CHECK(mk_copy_to_host(b1.data(), d_b1, nnz * 4)); CHECK(mk_copy_to_host(b2.data(), d_b2, nnz * 4)); CHECK(mk_copy_to_host(ct.data(), d_ct, nnz * 4)); }
+    if (g_hic) { string err; if (g_hic->add(res, b1.data(), b2.data(), ct.data(), nnz, &err)) { cerr << "Error: " << err << "\n"; return 10; } }
     FILE *fo = fopen(path.c_str(), "w");
     if (!fo) { cerr << "Error: cannot write " << path << "\n"; return 10; }
     static char big[1 << 22];
@@ -35,16 +43,18 @@ static int write_coo(const string &path, const void *d_b1, const void *d_b2, con
 }
 
 int main(int argc, char *argv[]) {
-    bool dedup = false, bins_bed = false; string reslist;
+    bool dedup = false, bins_bed = false; string reslist, hic_path, genome;
     int a = 1;
     while (a < argc && argv[a][0] == '-' && argv[a][1]) {
         if (!strcmp(argv[a], "-d")) { dedup = true; ++a; }
         else if (!strcmp(argv[a], "-b")) { bins_bed = true; ++a; }
         else if (!strcmp(argv[a], "-r") && a + 1 < argc) { reslist = argv[a + 1]; a += 2; }
+        else if (!strcmp(argv[a], "-H") && a + 1 < argc) { hic_path = argv[a + 1]; a += 2; }
+        else if (!strcmp(argv[a], "-g") && a + 1 < argc) { genome = argv[a + 1]; a += 2; }
         else break;
     }
     if (argc - a < 3 || reslist.empty()) {
-        cerr << "\nUsage: " << argv[0] << " [-d] [-b] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>\n\n";
+        cerr << "\nUsage: " << argv[0] << " [-d] [-b] [-H <out.hic>] [-g <genomeId>] -r <res[,res...]> <in.pairs|-> <out.prefix> <genome.info>\n\n";
         return 2;
     }
     vector<uint32_t> res;
@@ -55,6 +65,14 @@ int main(int argc, char *argv[]) {
       string n; uint32_t l; while (fi >> n >> l) { names.push_back(n); chr_len.push_back(l); } }
     if (names.empty()) { cerr << "Error: no chromosomes in " << argv[a + 2] << "\n"; return 10; }
     vector<const char *> cnames; for (auto &s : names) cnames.push_back(s.c_str());
+    if (!hic_path.empty()) {
+        if (genome.empty()) {                                            // hg38.info -> hg38, as the driver names its genomes
+            genome = argv[a + 2];
+            const size_t sl = genome.find_last_of('/'); if (sl != string::npos) genome = genome.substr(sl + 1);
+            const size_t dt = genome.find_last_of('.'); if (dt != string::npos && dt > 0) genome = genome.substr(0, dt);
+        }
+        g_hic = new hic::Writer(genome, names, chr_len, res);
+    }
     if (bins_bed) for (uint32_t r : res) {                                // bin id = line number: chromosomes in .info order, pos / res
         const string path = string(argv[a + 1]) + "." + to_string(r) + ".bins.bed";
         FILE *fb = fopen(path.c_str(), "w");
@@ -135,7 +153,7 @@ int main(int argc, char *argv[]) {
                                         (uint32_t *)d_b1, (uint32_t *)d_b2, (uint32_t *)d_ct, n + 1, &kept, &nnz, NULL));
         m = kept; deduped = true;
         if (k >= 0) {
-            if (int rc = write_coo(string(argv[a + 1]) + "." + to_string(res[k]) + ".coo", d_b1, d_b2, d_ct, nnz)) return rc;
+            if (int rc = write_coo(argv[a + 1], res[k], d_b1, d_b2, d_ct, nnz)) return rc;
             vector<int> rest; for (int q : sparse) if (q != k) rest.push_back(q);
             sparse = rest;
         }
@@ -145,7 +163,7 @@ int main(int argc, char *argv[]) {
         size_t nnz = 0;
         CHECK(mk_pairs_bin_device(ws, (const mk_pair *)d_pairs, m, chr_len.data(), (int)chr_len.size(), NULL, 0, res[k],
                                   (uint32_t *)d_b1, (uint32_t *)d_b2, (uint32_t *)d_ct, n + 1, &nnz, NULL));
-        if (int rc = write_coo(string(argv[a + 1]) + "." + to_string(res[k]) + ".coo", d_b1, d_b2, d_ct, nnz)) return rc;
+        if (int rc = write_coo(argv[a + 1], res[k], d_b1, d_b2, d_ct, nnz)) return rc;
     }
     if (!dense.empty()) {
         vector<uint32_t> dres; for (int k : dense) dres.push_back(res[k]);
@@ -155,12 +173,13 @@ int main(int argc, char *argv[]) {
         for (size_t i = 0; i < dense.size(); ++i) {
             size_t nnz = 0; uint64_t total = 0;
             CHECK(mk_hist_coo_device(h, (int)i, (uint32_t *)d_b1, (uint32_t *)d_b2, (uint32_t *)d_ct, n + 1, &nnz, &total, NULL));
-            if (int rc = write_coo(string(argv[a + 1]) + "." + to_string(dres[i]) + ".coo", d_b1, d_b2, d_ct, nnz)) return rc;
+            if (int rc = write_coo(argv[a + 1], dres[i], d_b1, d_b2, d_ct, nnz)) return rc;
         }
         mk_hist_destroy(h);
     }
     cerr << "INFO: " << n << " lines, " << skipped << " of them headers / unknown chromosomes; " << m << " pairs binned"
          << (dedup ? " after duplicate removal" : "") << " at " << res.size() << " resolutions (" << dense.size() << " dense).\n";
     mk_pairs_ws_destroy(ws); mk_dev_free(d_pairs); mk_dev_free(d_b1); mk_dev_free(d_b2); mk_dev_free(d_ct);
+    if (g_hic) { string err; if (g_hic->write(hic_path, &err)) { cerr << "Error: " << err << "\n"; return 10; } }
     return 0;
 }

@@ -90,10 +90,13 @@ def test_pairs2bins_cli(tmp_path, oracle):
              "chr22", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chrM", "chrX", "chrY"]
     from test_gpu_pairs import HG38_LEN
     info = tmp_path / "hg38.info"; info.write_text("".join(f"{n}\t{l}\n" for n, l in zip(names, HG38_LEN)))
-    r = run([os.path.join(BIN, "pairs2bins"), "-d", "-b", "-r", "1000000,5000", str(pf), str(tmp_path / "out"), str(info)])
+    r = run([os.path.join(BIN, "pairs2bins"), "-d", "-b", "-H", str(tmp_path / "out.hic"), "-r", "1000000,5000", str(pf), str(tmp_path / "out"), str(info)])
     assert r.returncode == 0, r.stderr
     pairs, n = oracle.pairs_parse(op, names)
     keep, kept = oracle.coord_dedup(pairs, n)
+    # -H: the same counts packed into a .hic container (read back by tests/hic_reader.py; parity unpinned, no juicer_tools here)
+    from hic_check import check_hic
+    check_hic(str(tmp_path / "out.hic"), "hg38", names, HG38_LEN, {res: oracle.bin_coo(pairs, n, keep, HG38_LEN, res) for res in (1000000, 5000)})
     for res in (1000000, 5000):
         b1, b2, ct = oracle.bin_coo(pairs, n, keep, HG38_LEN, res)
         exp = "".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1, b2, ct))

@@ -1,0 +1,91 @@
+"""`.hic` container writer (csrc/hic_writer.hpp through bin/coo2hic, host-only) read back by the independent reader of
+tests/hic_reader.py.  PARITY UNPINNED: juicer_tools (microcket:525-529) is an absent third-party jar; the test pins the file
+against the published format description and against the COO triplets it was made from."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hic_check import check_hic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COO2HIC = os.path.join(ROOT, "microcket_b200", "bin", "coo2hic")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "microcket_b200", "csrc"), "../bin/coo2hic"], check=True, capture_output=True)
+
+
+def coo(lens, res, c1, p1, c2, p2):
+    """numpy restatement of the binning the COO files hold: bin = offset[chr] + pos // res, upper triangle, sorted"""
+    off = np.concatenate([[0], np.cumsum(np.array(lens) // res + 1)])
+    a, b = off[c1] + p1 // res, off[c2] + p2 // res
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    keys, cnt = np.unique((lo.astype(np.uint64) << np.uint64(32)) | hi.astype(np.uint64), return_counts=True)
+    return (keys >> np.uint64(32)).astype(np.int64), (keys & np.uint64(0xFFFFFFFF)).astype(np.int64), cnt.astype(np.int64)
+
+
+def contacts(lens, n, seed, near=0.7):
+    rng = np.random.default_rng(seed)
+    L = np.array(lens)
+    c1 = rng.choice(len(lens), n, p=L / L.sum())
+    c2 = np.where(rng.random(n) < 0.8, c1, rng.integers(0, len(lens), n))
+    p1 = (rng.random(n) * (L[c1] - 1)).astype(np.int64) + 1
+    p2 = np.where((c1 == c2) & (rng.random(n) < near), np.minimum(p1 + (rng.exponential(30000, n)).astype(np.int64), L[c2]),
+                  (rng.random(n) * (L[c2] - 1)).astype(np.int64) + 1)
+    return c1, p1, c2, p2
+
+
+def write_coo(prefix, res, b1, b2, ct):
+    with open(f"{prefix}.{res}.coo", "w") as f:
+        f.write("".join(f"{a}\t{b}\t{c}\n" for a, b, c in zip(b1.tolist(), b2.tolist(), ct.tolist())))
+
+
+def run(tmp_path, names, lens, by_res, genome=None, res_order=None):
+    info = tmp_path / "toy.info"
+    info.write_text("".join(f"{n}\t{l}\n" for n, l in zip(names, lens)))
+    for res, (b1, b2, ct) in by_res.items():
+        write_coo(str(tmp_path / "in"), res, b1, b2, ct)
+    cmd = [COO2HIC] + (["-g", genome] if genome else []) + ["-r", ",".join(map(str, res_order or by_res)), str(tmp_path / "in"), str(tmp_path / "o.hic"), str(info)]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+def test_multi_resolution_round_trip(tmp_path):
+    """Five chromosomes (one shorter than the coarsest bin, one without any contact), matrices spanning several 1000-bin blocks,
+    three resolutions given in no particular order; the genome id defaults to the .info file's stem."""
+    names = ["chr1", "chr10", "chr2", "chrM", "chrX", "chrEmpty"]
+    lens = [24895642, 13379742, 9000001, 16569, 4999999, 700000]
+    c1, p1, c2, p2 = contacts(lens[:5], 300000, 7)
+    by_res = {r: coo(lens, r, c1, p1, c2, p2) for r in (5000, 1000000, 50000)}
+    r = run(tmp_path, names, lens, by_res)
+    assert r.returncode == 0, r.stderr
+    h = check_hic(str(tmp_path / "o.hic"), "toy", names, lens, by_res)
+    assert (6, 6) not in h["matrices"] and len(h["matrices"][(1, 1)][5000]["blocks"]) > 1
+    assert h["matrices"][(1, 1)][5000]["block_bin_count"] <= 1000
+
+
+def test_large_counts_use_float_blocks_and_plain_expected_values(tmp_path):
+    """Counts past int16 switch a block to float values; with >= 400 counts on the diagonal the expected value is the plain average."""
+    names, lens = ["a", "b"], [100000, 50000]
+    b1 = np.array([0, 0, 1, 3, 10, 11, 12]); b2 = np.array([0, 1, 1, 11, 10, 12, 12]); ct = np.array([500, 40000, 70000, 7, 900, 3, 32766])
+    by_res = {10000: (b1, b2, ct)}
+    r = run(tmp_path, names, lens, by_res, genome="toyG")
+    assert r.returncode == 0, r.stderr
+    h = check_hic(str(tmp_path / "o.hic"), "toyG", names, lens, by_res)
+    assert sorted(h["matrices"]) == [(0, 0), (1, 1), (1, 2), (2, 2)]
+    assert h["attributes"]["software"].startswith("microcket-b200")
+
+
+def test_bad_input_is_refused(tmp_path):
+    names, lens = ["a"], [100000]
+    ok = (np.array([0, 1]), np.array([1, 2]), np.array([3, 4]))
+    assert run(tmp_path, names, lens, {10000: (np.array([1, 0]), np.array([1, 2]), np.array([3, 4]))}).returncode == 10      # not sorted
+    assert run(tmp_path, names, lens, {10000: (np.array([2]), np.array([1]), np.array([3]))}).returncode == 10                # lower triangle
+    assert run(tmp_path, names, lens, {10000: (np.array([0]), np.array([11]), np.array([3]))}).returncode == 10               # bin past the genome
+    assert run(tmp_path, names, lens, {10000: ok}, res_order=[10000, 5000]).returncode == 10                                   # missing file
+    (tmp_path / "in.10000.coo").write_text("0\t1\n")
+    info = tmp_path / "toy.info"
+    assert subprocess.run([COO2HIC, "-r", "10000", str(tmp_path / "in"), str(tmp_path / "o.hic"), str(info)], capture_output=True).returncode == 10
+    assert subprocess.run([COO2HIC], capture_output=True).returncode == 2
