@@ -10,14 +10,18 @@
 // Extension (MICROCKET_RMDUP=1 or =k,s,K,S): krmdup's duplicate removal (src/preprocess/krmdup.cpp) is taken on the SAM,
 // before grouping, so a driver may skip its FASTQ krmdup step; krmdup's four log lines are appended to <out.prefix>.rmdup.log
 // (the file `krmdup -o $sid.rmdup` writes, microcket:413,445).  MICROCKET_RMDUP_PAIRS sizes the key table (read pairs).
+// Extension: <in.sam> may be a BAM file or stream; it is decoded on host threads to the text `samtools view` would pipe in
+// (bam_input.hpp; microcket:478,500 `samtools view -@ $vthread x.bam | sam2pairs /dev/stdin ...`).  MICROCKET_BAM_THREADS.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/microcket_b200.h"
+#include "bam_input.hpp"
 using namespace std;
 
 static int fail(const char *what) { cerr << "Error: " << what << ": " << mk_last_error() << "\n"; return 20; }
@@ -40,7 +44,7 @@ struct Grow {
 
 // The whole input through the device-resident API in chunks; text, packed pairs and line offsets accumulate in HBM, then one
 // sort (and optionally one dedup) and one pass over the lines.
-static int run_sorted(mk_ctx *ctx, const mk_s2p_cfg &cfg, FILE *fin, FILE *fsam, bool dedup, mk_s2p_stats *st) {
+static int run_sorted(mk_ctx *ctx, const mk_s2p_cfg &cfg, mkbam::SamSource &src, FILE *fsam, bool dedup, mk_s2p_stats *st) {
     const size_t CHUNK = (size_t)(getenv("MICROCKET_CHUNK_MB") ? atol(getenv("MICROCKET_CHUNK_MB")) : 1024) << 20;
     const int dev = cfg.device;
     char *h_in = NULL; void *d_in = NULL, *d_sam = NULL; char *h_sam = NULL;
@@ -50,7 +54,7 @@ static int run_sorted(mk_ctx *ctx, const mk_s2p_cfg &cfg, FILE *fin, FILE *fsam,
     Grow text, pairs, off; text.dev = pairs.dev = off.dev = dev;
     size_t text_total = 0, n_total = 0, have = 0;
     while (true) {
-        const size_t got = fread(h_in + have, 1, CHUNK - have, fin);
+        const size_t got = src.read(h_in + have, CHUNK - have);
         const bool eof = got == 0;
         size_t tot = have + got;
         if (tot == 0) break;
@@ -166,9 +170,17 @@ int main(int argc, char *argv[]) {
     }
     FILE *fin = fopen(argv[1], "rb");
     if (!fin) { cerr << "Error: read input file failed!\n"; return 10; }
+    long in_size = 0;
     if (cfg.rmdup && !getenv("MICROCKET_RMDUP_PAIRS")) {                  // a regular file: no more read pairs than bytes / 128
-        if (fseek(fin, 0, SEEK_END) == 0) { long sz = ftell(fin); if (sz > 0) cfg.rmdup_capacity = (uint64_t)sz / 128 + 1024; }
+        if (fseek(fin, 0, SEEK_END) == 0) { in_size = ftell(fin); if (in_size > 0) cfg.rmdup_capacity = (uint64_t)in_size / 128 + 1024; }
         fseek(fin, 0, SEEK_SET);
+    }
+    // SAM text as it is; BAM decoded to text.  Looking at the first bytes blocks on a pipe, so it waits until the GPU context
+    // exists unless the key table has to be sized from a regular file first
+    std::unique_ptr<mkbam::SamSource> srcp;
+    if (in_size > 0) {
+        srcp.reset(new mkbam::SamSource(fin));
+        if (srcp->is_bam()) cfg.rmdup_capacity = (uint64_t)in_size / 16 + 1024;   // compressed records: far fewer bytes per read pair
     }
     string base = string(argv[3]) + "." + argv[2];
     FILE *fsam = NULL;
@@ -179,9 +191,11 @@ int main(int argc, char *argv[]) {
     mk_ctx *ctx = NULL;
     if (mk_s2p_create(&cfg, NULL, 0, &ctx) != MK_OK) return fail("cannot create the GPU context");
 
+    if (!srcp) srcp.reset(new mkbam::SamSource(fin));
+    mkbam::SamSource &src = *srcp;
     mk_s2p_stats st;
     if (!outmode.empty()) {
-        if (int rc = run_sorted(ctx, cfg, fin, fsam, outmode == "sorted-dedup", &st)) return rc;
+        if (int rc = run_sorted(ctx, cfg, src, fsam, outmode == "sorted-dedup", &st)) return rc;
     } else {
     const size_t IN = 64u << 20, OUT = 32u << 20;
     vector<char> in(IN), out(OUT), samo(OUT);
@@ -195,7 +209,7 @@ int main(int argc, char *argv[]) {
         }
     };
     while (true) {
-        size_t n = fread(in.data(), 1, IN, fin);
+        size_t n = src.read(in.data(), IN);
         if (n == 0) break;
         if (mk_s2p_push(ctx, in.data(), n, 0) != MK_OK) return fail("sam2pairs");
         if (drain()) return fail("sam2pairs");
@@ -205,6 +219,7 @@ int main(int argc, char *argv[]) {
     if (mk_s2p_finish(ctx, &st) != MK_OK) return fail("sam2pairs");
     if (drain()) return fail("sam2pairs");
     }
+    if (src.failed()) { cerr << "Error: " << src.error() << "\n"; return 10; }
     fclose(fin);
     if (fsam) fclose(fsam);
     fflush(stdout);

@@ -1,0 +1,85 @@
+"""BAM (BGZF) input of the sam2pairs executable (csrc/bam_input.hpp, host-only), through bin/bam2sam: BAM made by the independent
+encoder of tests/bam_writer.py must decode to the SAM text it was made from (= what `samtools view` prints: no header), and SAM
+text must pass through byte for byte.  Reference call sites: microcket:478,500 (`samtools view ... | sam2pairs /dev/stdin`)."""
+import os
+import subprocess
+
+import pytest
+
+import microcket_b200 as mk
+from bam_writer import sam_to_bam
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BAM2SAM = os.path.join(ROOT, "microcket_b200", "bin", "bam2sam")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "microcket_b200", "csrc"), "../bin/bam2sam"], check=True, capture_output=True)
+
+
+def refs_of(sam: bytes):
+    """the reference dictionary: every name the records use (the synthetic SAM may come without @SQ lines)"""
+    names = set()
+    for ln in sam.split(b"\n"):
+        if ln and not ln.startswith(b"@"):
+            f = ln.split(b"\t")
+            names.update(x.decode() for x in (f[2], f[6]) if x not in (b"*", b"="))
+    return [(n, 250000000) for n in sorted(names)]
+
+
+def body_of(sam: bytes) -> bytes:
+    return b"".join(ln + b"\n" for ln in sam.split(b"\n") if ln and not ln.startswith(b"@"))
+
+
+def run(data: bytes, *args, env=None):
+    return subprocess.run([BAM2SAM, "-", *args], input=data, capture_output=True, env=dict(os.environ, **(env or {})))
+
+
+@pytest.mark.parametrize("mode,max_block,read_bytes,threads", [("unc", 0xff00, "1048576", "4"), ("flash", 700, "977", "3"), ("unc", 64, "65536", "1")])
+def test_synthetic_alignments_round_trip(mode, max_block, read_bytes, threads):
+    """The synthetic aligner output (chimeric CIGARs, supplementary records, SA / NM / AS tags) as BAM: blocks of random sizes down
+    to a few bytes, so that headers, reference names and records straddle blocks; reads of odd sizes; 1 to 4 inflate threads."""
+    sam = mk.synth_host(21, mode, "hg38", 0, 4000)
+    refs, body = refs_of(sam), body_of(sam)
+    assert len(refs) >= 20 and body.count(b"\n") > 4000
+    header = "@HD\tVN:1.6\tSO:unsorted\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
+    bam = sam_to_bam(body.decode(), refs, header, seed=5, max_block=max_block, extra_subfield=True)
+    r = run(bam, read_bytes, env={"MICROCKET_BAM_THREADS": threads})
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == body
+
+
+def test_every_field_kind():
+    refs = [("chr1", 1000), ("chrUn_x", 50)]
+    lines = [
+        "r1\t99\tchr1\t5\t60\t3S10M2I4D5M1N6M2H\t=\t105\t120\tACGTNACGTNACGTNACGTNACGTNA\tIIIIIIIIII#########!!!!!~~\tNM:i:3\tXA:A:q\tMD:Z:10^ACGT5\tXF:f:0.5\tXH:H:1AE301"
+        "\tZB:B:c,-3,4\tZC:B:S,65535,0\tZD:B:f,1.5,-2\tn1:i:-129\tn2:i:-70000\tn3:i:255\tn4:i:256\tn5:i:65536\tn6:i:4000000000",
+        "r2\t4\t*\t0\t0\t*\t*\t0\t0\tACG\t*",                                                    # unmapped, no qualities, odd length
+        "r3\t2113\tchrUn_x\t7\t0\t5M\tchr1\t900\t-17\t*\t*\tSA:Z:chr1,5,+,10M,60,0;",              # no sequence, mate elsewhere
+        "r4\t0\tchr1\t1000\t255\t1=1X1P\t*\t0\t0\tAC\t!~",
+    ]
+    text = "".join(l + "\n" for l in lines)
+    r = run(sam_to_bam(text, refs, "@HD\tVN:1.6\n", max_block=40))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.decode() == text
+
+
+def test_sam_text_passes_through():
+    sam = mk.synth_host(22, "unc", "hg38", 0, 500)
+    for data in (sam, b"", b"@HD\n", b"short\tline\n", sam[:-1]):
+        r = run(data, "333")
+        assert r.returncode == 0 and r.stdout == data
+
+
+def test_damaged_bam_is_refused():
+    refs = [("chr1", 1000)]
+    text = "".join(f"r{i}\t0\tchr1\t{i + 1}\t60\t10M\t*\t0\t0\tACGTACGTAC\tIIIIIIIIII\n" for i in range(3000))
+    bam = sam_to_bam(text, refs, max_block=5000)
+    assert run(bam).stdout.decode() == text
+    assert run(bam[:len(bam) // 2]).returncode == 10                                              # cut inside a block
+    flipped = bytearray(bam); flipped[len(bam) // 2] ^= 0x55
+    assert run(bytes(flipped)).returncode == 10                                                   # CRC / inflate error
+    eof = bam[-28:]
+    assert run(bam[:-28 - 30] + eof).returncode == 10                                             # the last data block lost its tail
+    assert run(b"\x1f\x8b\x08\x04" + b"\0" * 30).returncode == 10                                # gzip with an extra field, but no BC subfield
