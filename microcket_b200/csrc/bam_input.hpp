@@ -152,7 +152,7 @@ private:
     void fail(const std::string &why) { err_ = why; failed_ = true; }
     void push(std::string &&s) {
         std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [this] { return q_.size() < 4 || stop_; });
+        cv_.wait(l, [this] { return q_.size() < 256 || stop_; });
         if (!stop_) q_.push_back(std::move(s));
         l.unlock(); cv_.notify_all();
     }
@@ -244,10 +244,7 @@ private:
                     for (size_t k = a; k < b; ++k) if (!rec_to_sam(raw.data() + recs[k].first, recs[k].second, refs_, o)) { bad = true; return; }
                 });
                 if (bad) { fail("BAM input: malformed alignment record"); break; }
-                size_t tot = 0; for (auto &s : part) tot += s.size();
-                std::string text; text.reserve(tot);
-                for (auto &s : part) text += s;
-                push(std::move(text));
+                for (auto &s : part) push(std::move(s));               // read() takes the slices in order: no concatenation
             }
             carry = end - p;
             if (carry && p) memmove(raw.data(), raw.data() + p, carry);
