@@ -682,7 +682,7 @@ def main():
     text_b = float(io_text_len)                        # bytes of pair text of one pass
     alg = {"k_scan_chunks": nbytes + 4 * lines, "k_chunk_index": 8 * lines,
            "k_parse": 117.0 * lines + 48.0 * groups, "k_group": lines + 80.0 * groups,
-           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": 2.0 * float(pipe.sam_len) + 9.0 * lines,
+           "k_emit": 32.0 * groups + (40.0 + 72.0 + 16.0) * n_pairs, "k_copy_sam": (2.0 * float(pipe.sam_len) + 9.0 * lines) if pipe.sam_len else 0.0,   # passthrough off: the launch only returns
            "k_rmdup": 136.0 * lines + 32.0 * groups}     # --dedup seq: 8 B of K2's notes + the two key windows' sectors (4 x 32 B) per line, one 16-byte table slot read + written per read pair
     per_kernel = {}
     for k, (ms_k, n_k) in dk.items():
