@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -29,68 +30,81 @@ namespace mkbam {
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 
-static inline void put_u(std::string &o, uint64_t v) { char b[24]; int n = 0; do { b[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) o.push_back(b[--n]); }
-static inline void put_i(std::string &o, int64_t v) { if (v < 0) { o.push_back('-'); put_u(o, (uint64_t)(-(v + 1)) + 1); } else put_u(o, (uint64_t)v); }
+// text goes through a raw pointer into a buffer sized by text_bound(): no per-character capacity checks
+static inline char *put_u(char *o, uint64_t v) { char b[24]; int n = 0; do { b[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *o++ = b[--n]; return o; }
+static inline char *put_i(char *o, int64_t v) { if (v < 0) { *o++ = '-'; return put_u(o, (uint64_t)(-(v + 1)) + 1); } return put_u(o, (uint64_t)v); }
+static inline char *put_s(char *o, const std::string &s) { memcpy(o, s.data(), s.size()); return o + s.size(); }
 
-// one alignment record (without its block_size word) -> one SAM line.  false: the record does not fit its own length
-static inline bool rec_to_sam(const uint8_t *r, size_t len, const std::vector<std::string> &refs, std::string &o) {
-    if (len < 32) return false;
+// upper bound of the text of a record of `len` bytes: the densest field is an int8 array element (1 byte -> ",-128"); the 32
+// fixed bytes become at most five numbers, two reference names and eleven tabs
+static inline size_t text_bound(size_t len, size_t max_ref) { return 5 * len + 2 * max_ref + 96; }
+
+struct NibblePairs { char t[256][2]; NibblePairs() { const char *a = "=ACMGRSVTWYHKDBN"; for (int i = 0; i < 256; ++i) { t[i][0] = a[i >> 4]; t[i][1] = a[i & 15]; } } };
+
+// one alignment record (without its block_size word) -> one SAM line at o; returns the end of the line, NULL when the
+// record does not fit its own length
+static inline char *rec_to_sam(const uint8_t *r, size_t len, const std::vector<std::string> &refs, char *o) {
+    static const NibblePairs NP;
+    if (len < 32) return NULL;
     const int32_t ref = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
     const uint32_t l_name = r[8], mapq = r[9], n_cig = rd16(r + 12), flag = rd16(r + 14), l_seq = rd32(r + 16);
     const int32_t nref = (int32_t)rd32(r + 20), npos = (int32_t)rd32(r + 24), tlen = (int32_t)rd32(r + 28);
     size_t p = 32;
     const size_t need = (size_t)l_name + (size_t)n_cig * 4 + ((size_t)l_seq + 1) / 2 + l_seq;
-    if (l_name == 0 || p + need > len || ref >= (int32_t)refs.size() || nref >= (int32_t)refs.size()) return false;
-    o.append((const char *)r + p, l_name - 1); p += l_name;
-    o.push_back('\t'); put_u(o, flag);
-    o.push_back('\t'); if (ref < 0) o.push_back('*'); else o += refs[ref];
-    o.push_back('\t'); put_i(o, (int64_t)pos + 1);
-    o.push_back('\t'); put_u(o, mapq);
-    o.push_back('\t');
-    if (n_cig == 0) o.push_back('*');
-    for (uint32_t k = 0; k < n_cig; ++k, p += 4) { const uint32_t c = rd32(r + p); put_u(o, c >> 4); o.push_back("MIDNSHP=X???????"[c & 15]); }
-    o.push_back('\t'); if (nref < 0) o.push_back('*'); else if (nref == ref) o.push_back('='); else o += refs[nref];
-    o.push_back('\t'); put_i(o, (int64_t)npos + 1);
-    o.push_back('\t'); put_i(o, tlen);
-    o.push_back('\t');
-    if (l_seq == 0) o.push_back('*');
-    for (uint32_t k = 0; k < l_seq; ++k) o.push_back("=ACMGRSVTWYHKDBN"[(r[p + (k >> 1)] >> ((~k & 1) << 2)) & 15]);
-    p += ((size_t)l_seq + 1) / 2;
-    o.push_back('\t');
-    if (l_seq == 0 || r[p] == 0xFF) o.push_back('*'); else for (uint32_t k = 0; k < l_seq; ++k) o.push_back((char)(r[p + k] + 33));
+    if (l_name == 0 || p + need > len || ref >= (int32_t)refs.size() || nref >= (int32_t)refs.size()) return NULL;
+    memcpy(o, r + p, l_name - 1); o += l_name - 1; p += l_name;
+    *o++ = '\t'; o = put_u(o, flag);
+    *o++ = '\t'; if (ref < 0) *o++ = '*'; else o = put_s(o, refs[ref]);
+    *o++ = '\t'; o = put_i(o, (int64_t)pos + 1);
+    *o++ = '\t'; o = put_u(o, mapq);
+    *o++ = '\t';
+    if (n_cig == 0) *o++ = '*';
+    for (uint32_t k = 0; k < n_cig; ++k, p += 4) { const uint32_t c = rd32(r + p); o = put_u(o, c >> 4); *o++ = "MIDNSHP=X???????"[c & 15]; }
+    *o++ = '\t'; if (nref < 0) *o++ = '*'; else if (nref == ref) *o++ = '='; else o = put_s(o, refs[nref]);
+    *o++ = '\t'; o = put_i(o, (int64_t)npos + 1);
+    *o++ = '\t'; o = put_i(o, tlen);
+    *o++ = '\t';
+    if (l_seq == 0) *o++ = '*';
+    for (uint32_t k = 0; k + 1 < l_seq; k += 2) { const char *t = NP.t[r[p + (k >> 1)]]; o[k] = t[0]; o[k + 1] = t[1]; }
+    if (l_seq & 1) o[l_seq - 1] = NP.t[r[p + (l_seq >> 1)]][0];
+    o += l_seq; p += ((size_t)l_seq + 1) / 2;
+    *o++ = '\t';
+    if (l_seq == 0 || r[p] == 0xFF) *o++ = '*'; else { for (uint32_t k = 0; k < l_seq; ++k) o[k] = (char)(r[p + k] + 33); o += l_seq; }
     p += l_seq;
     while (p < len) {                                                   // optional fields: tag[2] type value
-        if (p + 3 > len) return false;
-        o.push_back('\t'); o.push_back((char)r[p]); o.push_back((char)r[p + 1]); o.push_back(':');
-        char t = (char)r[p + 2]; p += 3;
+        if (p + 3 > len) return NULL;
+        *o++ = '\t'; *o++ = (char)r[p]; *o++ = (char)r[p + 1]; *o++ = ':';
+        const char t = (char)r[p + 2]; p += 3;
         auto scalar = [&](char ty) -> bool {
             switch (ty) {
-                case 'c': if (p + 1 > len) return false; put_i(o, (int8_t)r[p]); p += 1; return true;
-                case 'C': if (p + 1 > len) return false; put_u(o, r[p]); p += 1; return true;
-                case 's': if (p + 2 > len) return false; put_i(o, (int16_t)rd16(r + p)); p += 2; return true;
-                case 'S': if (p + 2 > len) return false; put_u(o, rd16(r + p)); p += 2; return true;
-                case 'i': if (p + 4 > len) return false; put_i(o, (int32_t)rd32(r + p)); p += 4; return true;
-                case 'I': if (p + 4 > len) return false; put_u(o, rd32(r + p)); p += 4; return true;
-                case 'f': { if (p + 4 > len) return false; float f; memcpy(&f, r + p, 4); char b[32]; snprintf(b, sizeof b, "%g", f); o += b; p += 4; return true; }
+                case 'c': if (p + 1 > len) return false; o = put_i(o, (int8_t)r[p]); p += 1; return true;
+                case 'C': if (p + 1 > len) return false; o = put_u(o, r[p]); p += 1; return true;
+                case 's': if (p + 2 > len) return false; o = put_i(o, (int16_t)rd16(r + p)); p += 2; return true;
+                case 'S': if (p + 2 > len) return false; o = put_u(o, rd16(r + p)); p += 2; return true;
+                case 'i': if (p + 4 > len) return false; o = put_i(o, (int32_t)rd32(r + p)); p += 4; return true;
+                case 'I': if (p + 4 > len) return false; o = put_u(o, rd32(r + p)); p += 4; return true;
+                case 'f': { if (p + 4 > len) return false; float f; memcpy(&f, r + p, 4); o += snprintf(o, 16, "%g", f); p += 4; return true; }
                 default: return false;
             }
         };
-        if (t == 'A') { if (p + 1 > len) return false; o += "A:"; o.push_back((char)r[p++]); }
+        if (t == 'A') { if (p + 1 > len) return NULL; *o++ = 'A'; *o++ = ':'; *o++ = (char)r[p++]; }
         else if (t == 'Z' || t == 'H') {
-            o.push_back(t); o.push_back(':');
-            const void *e = memchr(r + p, 0, len - p); if (!e) return false;
-            const size_t n = (const uint8_t *)e - (r + p); o.append((const char *)r + p, n); p += n + 1;
+            *o++ = t; *o++ = ':';
+            const void *e = memchr(r + p, 0, len - p); if (!e) return NULL;
+            const size_t n = (const uint8_t *)e - (r + p); memcpy(o, r + p, n); o += n; p += n + 1;
         } else if (t == 'B') {
-            if (p + 5 > len) return false;
+            if (p + 5 > len) return NULL;
             const char st = (char)r[p]; const uint32_t cnt = rd32(r + p + 1); p += 5;
-            o += "B:"; o.push_back(st);
-            for (uint32_t k = 0; k < cnt; ++k) { o.push_back(','); if (!scalar(st)) return false; }
-        } else if (t == 'f') { o += "f:"; if (!scalar('f')) return false; }
-        else { o += "i:"; if (!scalar(t)) return false; }              // every integer width prints as type i
+            *o++ = 'B'; *o++ = ':'; *o++ = st;
+            for (uint32_t k = 0; k < cnt; ++k) { *o++ = ','; if (!scalar(st)) return NULL; }
+        } else if (t == 'f') { *o++ = 'f'; *o++ = ':'; if (!scalar('f')) return NULL; }
+        else { *o++ = 'i'; *o++ = ':'; if (!scalar(t)) return NULL; }  // every integer width prints as type i
     }
-    o.push_back('\n');
-    return true;
+    *o++ = '\n';
+    return o;
 }
+
+struct Chunk { std::unique_ptr<char[]> p; size_t n = 0; };              // a slice of decoded text
 
 class SamSource {
 public:
@@ -126,16 +140,16 @@ public:
         }
         size_t got = 0;
         while (got < n) {
-            if (cur_off_ == cur_.size()) {
+            if (cur_off_ == cur_.n) {
                 std::unique_lock<std::mutex> l(m_);
                 cv_.wait(l, [this] { return !q_.empty() || done_; });
                 if (q_.empty()) break;
-                cur_.swap(q_.front()); q_.pop_front(); cur_off_ = 0;
+                cur_ = std::move(q_.front()); q_.pop_front(); cur_off_ = 0;
                 l.unlock(); cv_.notify_all();
                 continue;
             }
-            const size_t m = std::min(n - got, cur_.size() - cur_off_);
-            memcpy(dst + got, cur_.data() + cur_off_, m); got += m; cur_off_ += m;
+            const size_t m = std::min(n - got, cur_.n - cur_off_);
+            memcpy(dst + got, cur_.p.get() + cur_off_, m); got += m; cur_off_ += m;
         }
         return got;
     }
@@ -150,7 +164,7 @@ private:
         return got;
     }
     void fail(const std::string &why) { err_ = why; failed_ = true; }
-    void push(std::string &&s) {
+    void push(Chunk &&s) {
         std::unique_lock<std::mutex> l(m_);
         cv_.wait(l, [this] { return q_.size() < 256 || stop_; });
         if (!stop_) q_.push_back(std::move(s));
@@ -222,6 +236,7 @@ private:
                         const size_t ln = rd32(raw.data() + p);
                         if (end - p < 4 + ln + 4) break;
                         refs_.emplace_back((const char *)raw.data() + p + 4, ln ? ln - 1 : 0); p += 8 + ln; ++refs_seen;
+                        max_ref_ = std::max(max_ref_, refs_.back().size());
                     } else { header_done = true; break; }
                 }
                 if (failed_) break;
@@ -237,11 +252,15 @@ private:
             if (failed_) break;
             if (!recs.empty()) {
                 const size_t slices = std::min<size_t>(recs.size(), (size_t)nthreads_ * 4);
-                std::vector<std::string> part(slices);
+                std::vector<Chunk> part(slices);
                 parallel(slices, [&](size_t s) {
                     const size_t a = recs.size() * s / slices, b = recs.size() * (s + 1) / slices;
-                    std::string &o = part[s]; o.reserve((recs[b - 1].first + recs[b - 1].second - recs[a].first) * 2);
-                    for (size_t k = a; k < b; ++k) if (!rec_to_sam(raw.data() + recs[k].first, recs[k].second, refs_, o)) { bad = true; return; }
+                    const size_t bytes = recs[b - 1].first + recs[b - 1].second - recs[a].first;
+                    Chunk &c = part[s];
+                    c.p.reset(new char[text_bound(bytes, max_ref_) + (b - a) * (2 * max_ref_ + 96)]);   // untouched pages cost nothing
+                    char *o = c.p.get();
+                    for (size_t k = a; k < b; ++k) { o = rec_to_sam(raw.data() + recs[k].first, recs[k].second, refs_, o); if (!o) { bad = true; return; } }
+                    c.n = (size_t)(o - c.p.get());
                 });
                 if (bad) { fail("BAM input: malformed alignment record"); break; }
                 for (auto &s : part) push(std::move(s));               // read() takes the slices in order: no concatenation
@@ -257,10 +276,10 @@ private:
 
     FILE *f_; uint8_t peek_[18]; size_t npeek_ = 0, peek_off_ = 0; bool bam_ = false;
     unsigned nthreads_ = 1;
-    std::vector<std::string> refs_;
+    std::vector<std::string> refs_; size_t max_ref_ = 0;
     std::thread producer_; std::mutex m_; std::condition_variable cv_;
-    std::deque<std::string> q_; bool done_ = false, stop_ = false;
-    std::string cur_; size_t cur_off_ = 0;
+    std::deque<Chunk> q_; bool done_ = false, stop_ = false;
+    Chunk cur_; size_t cur_off_ = 0;
     std::atomic<bool> failed_{false}; std::string err_;
 };
 
