@@ -83,3 +83,37 @@ def test_damaged_bam_is_refused():
     eof = bam[-28:]
     assert run(bam[:-28 - 30] + eof).returncode == 10                                             # the last data block lost its tail
     assert run(b"\x1f\x8b\x08\x04" + b"\0" * 30).returncode == 10                                # gzip with an extra field, but no BC subfield
+
+
+def test_mutated_records_never_crash_the_decoder(tmp_path):
+    """Bytes of the UNCOMPRESSED BAM stream are overwritten at random and the stream is packed again (so CRC and sizes are right and
+    the damage reaches the record decoder): an AddressSanitizer + UBSan build of bam2sam must end with exit code 0 or 10, never with
+    a sanitizer report or a signal."""
+    import numpy as np
+    from bam_writer import bgzf, encode_records
+    import struct
+    exe = str(tmp_path / "bam2sam_asan")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-o", exe,
+                         os.path.join(ROOT, "microcket_b200", "csrc", "cli_bam2sam.cpp"), "-lz"], capture_output=True)
+    if cc.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here")
+    refs = [("chr1", 100000), ("chr2", 5000)]
+    lines = [f"q{i}\t{(i * 37) % 4096}\tchr{1 + i % 2}\t{1 + i * 13}\t{i % 61}\t{5 + i % 9}M{1 + i % 3}I7M\t=\t{i + 1}\t{i - 40}\t" + "ACGTN"[i % 5] * (13 + i % 9) + "\t" + "I" * (13 + i % 9)
+             + f"\tNM:i:{i % 300 - 100}\tSA:Z:chr2,{i},+,5M,3,0;\tZB:B:s,{i},-{i}\tXF:f:{i / 7}" for i in range(400)]
+    text = "".join(l + "\n" for l in lines)
+    hdr = b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", len(refs)) + b"".join(struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l) for n, l in refs)
+    raw = hdr + encode_records(text, refs)
+    ok = subprocess.run([exe, "-"], input=bgzf(raw, 1, 3000), capture_output=True)
+    assert ok.returncode == 0 and ok.stdout == run(bgzf(raw, 2, 900)).stdout and ok.stdout.count(b"\n") == 400    # same text as the shipped build
+    rng = np.random.default_rng(11)
+    outcomes = set()
+    for trial in range(120):
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 6))):
+            at = int(rng.integers(4, len(b)))                         # the header fields and the reference table are fair game too
+            b[at] = int(rng.integers(0, 256)) if trial % 3 else (0xFF, 0x00, 0x7F, 0x80)[int(rng.integers(0, 4))]
+        r = subprocess.run([exe, "-"], input=bgzf(bytes(b), trial, 3000), capture_output=True, env=dict(os.environ, MICROCKET_BAM_THREADS="2"))
+        assert r.returncode in (0, 10), (trial, r.returncode, r.stderr[-2000:])
+        assert b"Sanitizer" not in r.stderr and b"runtime error" not in r.stderr, (trial, r.stderr[-2000:])
+        outcomes.add(r.returncode)
+    assert outcomes == {0, 10}
