@@ -6,6 +6,8 @@
 //   ISIZE checked) -> alignment records (they may straddle blocks) -> text, again in parallel slices -> bounded queue -> read().
 // The device path is unchanged: it still tokenises text.  A BAM-native device parser (fixed-offset fields instead of text
 // tokenising) is the next step and is NOT built.
+// BAM stores bases as 4-bit codes: lower case and characters such as '.' do not survive the aligner's SAM -> BAM step (they come
+// back upper case / as N, exactly as through `samtools view`), which matters only to cfg.rmdup's treatment of soft-masked reads.
 // Parity: the decoder follows the SAM/BAM specification (SAMv1 §4.2); samtools is not in this image, so the tests encode BAM
 // with an independent Python writer (tests/bam_writer.py) and require the decoded text to equal the SAM it was made from.
 #pragma once

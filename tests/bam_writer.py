@@ -57,7 +57,7 @@ def encode_records(sam_text, refs):
         reflen = sum(n for n, o in cig if o in (0, 2, 3, 7, 8))
         p0 = int(pos) - 1
         l_seq = 0 if seq == "*" else len(seq)
-        nib = [_NT[c] for c in seq] if l_seq else []
+        nib = [_NT.get(c, 15) for c in seq.upper()] if l_seq else []     # 4-bit codes: no case, anything unknown is N (as htslib's table does)
         if len(nib) & 1:
             nib.append(0)
         packed = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))

@@ -117,3 +117,18 @@ def test_mutated_records_never_crash_the_decoder(tmp_path):
         assert b"Sanitizer" not in r.stderr and b"runtime error" not in r.stderr, (trial, r.stderr[-2000:])
         outcomes.add(r.returncode)
     assert outcomes == {0, 10}
+
+
+@pytest.mark.parametrize("name", ["appB_unc.sam", "appB_flash_r05.sam", "appB_flash_r08.sam", "rmdup_unc.sam", "rmdup_flash.sam"])
+def test_reference_golden_sams_as_bam(name):
+    """The SURVEY Appendix-B vectors and the SAM-space krmdup vectors (tests/golden, the inputs the reference binaries were run on)
+    packed as BAM decode to their own record lines: what sam2pairs is fed is the same text either way."""
+    sam = open(os.path.join(ROOT, "tests", "golden", name), "rb").read()
+    body = body_of(sam)
+    assert body
+    r = run(sam_to_bam(body.decode(), refs_of(sam), seed=9, max_block=300), "4096")
+    assert r.returncode == 0, r.stderr
+    as_bam = lambda q: bytes(c if c in b"=ACMGRSVTWYHKDBN" else ord("N") for c in q.upper())
+    upper = b"".join(b"\t".join(f[:9] + [as_bam(f[9])] + f[10:]) + b"\n" for f in (ln.split(b"\t") for ln in body.splitlines()))
+    assert r.stdout == upper                                          # BAM's 4-bit base codes: no lower case, '.' becomes N (the rmdup vectors use both)
+    assert (upper == body) == (not name.startswith("rmdup"))
