@@ -58,3 +58,25 @@ def test_lines_that_separate_the_rules(tmp_path):
 def test_usage_and_missing_file(tmp_path):
     assert subprocess.run([EXE], capture_output=True).returncode == 2
     assert subprocess.run([EXE, str(tmp_path / "none")], capture_output=True).returncode == 10
+
+
+def test_random_odd_lines_against_gnu_sort(tmp_path):
+    """Seeded random lines over an alphabet chosen to hit the corners of -d and -n in the C locale: punctuation and bytes >= 0x80 (ignored
+    by -d), spaces as well as tabs between fields, runs of blanks, signs, leading zeros, fractions, empty and missing fields."""
+    import numpy as np
+    rng = np.random.default_rng(17)
+    name_chars = [b"c", b"h", b"r", b"1", b"2", b"X", b"_", b"-", b".", b"\xc3", b"\xa9", b"Z", b"0", b"#"]
+    num_forms = [b"5", b"05", b"5.0", b"5.25", b"-5", b"-0", b"0", b"", b"50", b"4x", b"+5", b".5", b"1e3", b"  7", b"007.10"]
+    seps = [b"\t", b" ", b"\t\t", b" \t"]
+
+    def field(chars, lo, hi):
+        return b"".join(chars[int(i)] for i in rng.integers(0, len(chars), int(rng.integers(lo, hi))))
+
+    def line():
+        f = [b"id" + str(int(rng.integers(0, 50))).encode(), field(name_chars, 1, 5), num_forms[int(rng.integers(0, len(num_forms)))].strip() or b"0",
+             field(name_chars, 1, 5), num_forms[int(rng.integers(0, len(num_forms)))].strip() or b"0", b"+", b"-"]
+        f = f[:int(rng.integers(2, 8))] if rng.random() < 0.1 else f
+        return b"".join(x + seps[int(rng.integers(0, len(seps)))] for x in f[:-1]) + f[-1]
+
+    parts = [b"".join(line() + b"\n" for _ in range(700)) for _ in range(3)]
+    check(tmp_path, parts)
