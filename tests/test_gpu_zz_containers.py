@@ -49,7 +49,7 @@ def test_sam2pairs_cli_reads_bam(tmp_path, oracle, via_stdin, outmode):
     bam = sam_to_bam(sam.decode(), refs_of(sam), "@HD\tVN:1.6\n", seed=3)
     src = tmp_path / "in.bam"; src.write_bytes(bam)
     args = [os.path.join(BIN, "sam2pairs"), "/dev/stdin" if via_stdin else str(src), "unc", str(tmp_path / "b"), "8", "0.5", "10", "yes"] + ([outmode] if outmode else [])
-    r = run(args, input=bam if via_stdin else None)
+    r = run(args, input=bam if via_stdin else None, env=dict(os.environ, MICROCKET_CHUNK_MB="8"))   # sorted mode: 8 MiB chunks, lines and groups cross them
     assert r.returncode == 0, r.stderr
     op, osam, ost = oracle.sam2pairs(sam, "unc", threads=8)
     assert (r.stdout == sort_pairs(op)) if outmode else (sort_pairs(r.stdout) == sort_pairs(op))
