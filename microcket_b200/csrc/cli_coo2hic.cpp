@@ -24,9 +24,10 @@ static int read_coo(const string &path, vector<uint32_t> &b1, vector<uint32_t> &
     while ((got = fread(buf, 1, sizeof buf, f)) > 0)
         for (size_t i = 0; i < got; ++i) {
             const char c = buf[i];
-            if (c >= '0' && c <= '9') { v[k] = v[k] * 10 + (uint64_t)(c - '0'); digits = true; }
+            if (c >= '0' && c <= '9') { v[k] = v[k] > 0xFFFFFFFFull ? v[k] : v[k] * 10 + (uint64_t)(c - '0'); digits = true; }
             else if (c == '\t' && k < 2 && digits) { ++k; digits = false; }
             else if (c == '\n') {
+                if (k == 2 && digits && (v[0] | v[1] | v[2]) > 0xFFFFFFFFull) { cerr << "Error: " << path << ": line " << line << " holds a number past 32 bits\n"; fclose(f); return 10; }
                 if (k == 2 && digits) { b1.push_back((uint32_t)v[0]); b2.push_back((uint32_t)v[1]); ct.push_back((uint32_t)v[2]); }
                 else if (k || digits) { cerr << "Error: " << path << ": line " << line << " is not bin1<TAB>bin2<TAB>count\n"; fclose(f); return 10; }
                 v[0] = v[1] = v[2] = 0; k = 0; digits = false; ++line;

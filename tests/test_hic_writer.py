@@ -85,6 +85,8 @@ def test_bad_input_is_refused(tmp_path):
     assert run(tmp_path, names, lens, {10000: (np.array([2]), np.array([1]), np.array([3]))}).returncode == 10                # lower triangle
     assert run(tmp_path, names, lens, {10000: (np.array([0]), np.array([11]), np.array([3]))}).returncode == 10               # bin past the genome
     assert run(tmp_path, names, lens, {10000: ok}, res_order=[10000, 5000]).returncode == 10                                   # missing file
+    (tmp_path / "in.10000.coo").write_text("0\t1\t99999999999\n")
+    assert subprocess.run([COO2HIC, "-r", "10000", str(tmp_path / "in"), str(tmp_path / "o.hic"), str(tmp_path / "toy.info")], capture_output=True).returncode == 10   # count past 32 bits
     (tmp_path / "in.10000.coo").write_text("0\t1\n")
     info = tmp_path / "toy.info"
     assert subprocess.run([COO2HIC, "-r", "10000", str(tmp_path / "in"), str(tmp_path / "o.hic"), str(info)], capture_output=True).returncode == 10
